@@ -1,0 +1,256 @@
+// fe_lk.cuh -- pyramidal Lucas-Kanade, one warp per point, bit-exact with OpenCV 4.13's SSE path.
+//
+// Replaces the two cv::calcOpticalFlowPyrLK calls of FeatureTracker::trackImage
+// (reference vins_estimator/src/featureTracker/feature_tracker.cpp:118-153).  The arithmetic follows
+// oracle/fe_cv_restate.c (pinned bit-for-bit against cv2 4.13.0): fixed-point bilinear windows
+// (W_BITS=14), Scharr derivatives computed on the fly from the staged u8 window (no derivative image
+// ever touches HBM), float32 sums accumulated in OpenCV's SIMD lane order:
+//   A11/A12/A22: 4 lane chains over columns 0..15 (lane l <- columns l, l+4, l+8, l+12, row-major)
+//                + 1 scalar tail chain over columns 16..20, result = tail + ((l0+l2)+(l1+l3))
+//   b1/b2:       4 chains of pmaddwd pairs (col k, col k+4 | k+8, k+12) + 1 tail chain,
+//                result = tail + ((c0+c2) + (c1+c3))
+// Each chain is owned by one lane (15 lanes for A, 10 for b); everything else is spread over 32 lanes.
+// Compile with -fmad=false: every float op must round on its own.
+#pragma once
+#include "gf_common.cuh"
+
+namespace gf {
+
+constexpr int LK_WIN = 21;
+constexpr int LK_NPIX = LK_WIN * LK_WIN;  // 441
+constexpr int LK_IREG = 24;               // staged I window incl. Scharr apron + bilinear +1
+constexpr int LK_SCH = 22;                // integer positions needing a derivative
+constexpr int LK_JR = 40;                 // cached J region (window 22 + 9 px drift each side)
+constexpr int LK_WARPS = 4;
+
+struct __align__(16) LKSmem {
+    uint8_t ireg[LK_IREG * LK_IREG];
+    int16_t sch[LK_SCH * LK_SCH * 2];
+    int16_t pI[LK_NPIX + 1];
+    int16_t pdx[LK_NPIX + 1];
+    int16_t pdy[LK_NPIX + 1];
+    int16_t diff[LK_NPIX + 1];
+    uint8_t jreg[LK_JR * LK_JR];
+};
+
+__device__ __forceinline__ int lk_descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
+
+__device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11)
+{
+    w00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+    w01 = __float2int_rn(a * (1.f - b) * 16384.f);
+    w10 = __float2int_rn((1.f - a) * b * 16384.f);
+    w11 = 16384 - w00 - w01 - w10;
+}
+
+// One pyramid level for one point (all 32 lanes call this with identical scalar arguments).
+__device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, const Level& J, float px,
+                                         float py, float& nx, float& ny, int level, int& status)
+{
+    const float FLT_SCALE = 1.f / (1 << 20);
+    float ppx = px - 10.f, ppy = py - 10.f;
+    int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+    if (ipx < -LK_WIN || ipx >= I.w || ipy < -LK_WIN || ipy >= I.h) {
+        if (level == 0) status = 0;
+        return;
+    }
+    float a = ppx - (float)ipx, b = ppy - (float)ipy;
+    int iw00, iw01, iw10, iw11;
+    lk_weights(a, b, iw00, iw01, iw10, iw11);
+
+    // ---- stage the 24x24 u8 window of I (REFLECT_101) ----
+    __syncwarp();
+    for (int i = lane; i < LK_IREG * LK_IREG; i += 32) {
+        int r = i / LK_IREG, c = i - r * LK_IREG;
+        int yy = reflect101(ipy - 1 + r, I.h), xx = reflect101(ipx - 1 + c, I.w);
+        S.ireg[i] = __ldg(I.ptr + (size_t)yy * I.pitch + xx);
+    }
+    __syncwarp();
+    // ---- Scharr derivative at the 22x22 integer positions (0 outside the image) ----
+    for (int i = lane; i < LK_SCH * LK_SCH; i += 32) {
+        int r = i / LK_SCH, c = i - r * LK_SCH;
+        int X = ipx + c, Y = ipy + r;
+        int ix = 0, iy = 0;
+        if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
+            const uint8_t* u = S.ireg + r * LK_IREG + c;  // row above, column left of the centre
+            const uint8_t* m = u + LK_IREG;
+            const uint8_t* d = m + LK_IREG;
+            int t0l = (u[0] + d[0]) * 3 + m[0] * 10, t0r = (u[2] + d[2]) * 3 + m[2] * 10;
+            int t1l = d[0] - u[0], t1c = d[1] - u[1], t1r = d[2] - u[2];
+            ix = t0r - t0l;
+            iy = (t1r + t1l) * 3 + t1c * 10;
+        }
+        S.sch[2 * i] = (int16_t)ix;
+        S.sch[2 * i + 1] = (int16_t)iy;
+    }
+    __syncwarp();
+    // ---- bilinear 21x21 patches: I*32 and (Ix, Iy) ----
+    for (int i = lane; i < LK_NPIX; i += 32) {
+        int y = i / LK_WIN, x = i - y * LK_WIN;
+        const uint8_t* p = S.ireg + (y + 1) * LK_IREG + (x + 1);
+        int iv = p[0] * iw00 + p[1] * iw01 + p[LK_IREG] * iw10 + p[LK_IREG + 1] * iw11;
+        S.pI[i] = (int16_t)lk_descale(iv, 9);
+        const int16_t* s = S.sch + 2 * (y * LK_SCH + x);
+        int dxv = s[0] * iw00 + s[2] * iw01 + s[2 * LK_SCH] * iw10 + s[2 * LK_SCH + 2] * iw11;
+        int dyv = s[1] * iw00 + s[3] * iw01 + s[2 * LK_SCH + 1] * iw10 + s[2 * LK_SCH + 3] * iw11;
+        S.pdx[i] = (int16_t)lk_descale(dxv, 14);
+        S.pdy[i] = (int16_t)lk_descale(dyv, 14);
+    }
+    __syncwarp();
+    // ---- gradient matrix, OpenCV lane order ----
+    float acc = 0.f;
+    {
+        int q = lane / 5, c = lane - q * 5;
+        if (lane < 15) {
+            const int16_t* u = (q == 2) ? S.pdy : S.pdx;
+            const int16_t* v = (q == 0) ? S.pdx : S.pdy;
+            if (c < 4) {
+#pragma unroll 3
+                for (int y = 0; y < LK_WIN; y++) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        int k = y * LK_WIN + c + 4 * j;
+                        acc = (float)u[k] * (float)v[k] + acc;
+                    }
+                }
+            } else {
+#pragma unroll 3
+                for (int y = 0; y < LK_WIN; y++) {
+#pragma unroll
+                    for (int x = 16; x < LK_WIN; x++) {
+                        int k = y * LK_WIN + x;
+                        acc += (float)((int)u[k] * (int)v[k]);
+                    }
+                }
+            }
+        }
+    }
+    float A[3];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        float l0 = __shfl_sync(0xffffffffu, acc, q * 5 + 0), l1 = __shfl_sync(0xffffffffu, acc, q * 5 + 1);
+        float l2 = __shfl_sync(0xffffffffu, acc, q * 5 + 2), l3 = __shfl_sync(0xffffffffu, acc, q * 5 + 3);
+        float t = __shfl_sync(0xffffffffu, acc, q * 5 + 4);
+        A[q] = t + ((l0 + l2) + (l1 + l3));
+    }
+    float A11 = A[0] * FLT_SCALE, A12 = A[1] * FLT_SCALE, A22 = A[2] * FLT_SCALE;
+    float D = A11 * A22 - A12 * A12;
+    float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / 882.f;
+    if (minEig < 1e-4f || D < 1.1920928955078125e-07f) {
+        if (level == 0) status = 0;
+        return;
+    }
+    D = 1.f / D;
+
+    float qx = nx - 10.f, qy = ny - 10.f;
+    float pdx_ = 0.f, pdy_ = 0.f;
+    int jx0 = 0, jy0 = 0;
+    bool jvalid = false;
+    for (int j = 0; j < 30; j++) {
+        int iqx = __float2int_rd(qx), iqy = __float2int_rd(qy);
+        if (iqx < -LK_WIN || iqx >= J.w || iqy < -LK_WIN || iqy >= J.h) {
+            if (level == 0) status = 0;
+            break;
+        }
+        if (!(jvalid && iqx >= jx0 && iqy >= jy0 && iqx + 22 <= jx0 + LK_JR && iqy + 22 <= jy0 + LK_JR)) {
+            jx0 = iqx - 9;
+            jy0 = iqy - 9;
+            __syncwarp();
+            for (int i = lane; i < LK_JR * LK_JR; i += 32) {
+                int r = i / LK_JR, c = i - r * LK_JR;
+                int yy = reflect101(jy0 + r, J.h), xx = reflect101(jx0 + c, J.w);
+                S.jreg[i] = __ldg(J.ptr + (size_t)yy * J.pitch + xx);
+            }
+            jvalid = true;
+            __syncwarp();
+        }
+        a = qx - (float)iqx;
+        b = qy - (float)iqy;
+        lk_weights(a, b, iw00, iw01, iw10, iw11);
+        const uint8_t* jb = S.jreg + (iqy - jy0) * LK_JR + (iqx - jx0);
+        for (int i = lane; i < LK_NPIX; i += 32) {
+            int y = i / LK_WIN, x = i - y * LK_WIN;
+            const uint8_t* p = jb + y * LK_JR + x;
+            int jv = p[0] * iw00 + p[1] * iw01 + p[LK_JR] * iw10 + p[LK_JR + 1] * iw11;
+            S.diff[i] = (int16_t)(lk_descale(jv, 9) - S.pI[i]);
+        }
+        __syncwarp();
+        float bacc = 0.f;
+        {
+            int comp = lane / 5, c = lane - comp * 5;
+            if (lane < 10) {
+                const int16_t* d = comp ? S.pdy : S.pdx;
+                if (c < 4) {
+#pragma unroll 3
+                    for (int y = 0; y < LK_WIN; y++) {
+#pragma unroll
+                        for (int x0 = 0; x0 < 16; x0 += 8) {
+                            int k = y * LK_WIN + x0 + c;
+                            int s = (int)S.diff[k] * (int)d[k] + (int)S.diff[k + 4] * (int)d[k + 4];
+                            bacc += (float)s;
+                        }
+                    }
+                } else {
+#pragma unroll 3
+                    for (int y = 0; y < LK_WIN; y++) {
+#pragma unroll
+                        for (int x = 16; x < LK_WIN; x++) {
+                            int k = y * LK_WIN + x;
+                            bacc += (float)((int)S.diff[k] * (int)d[k]);
+                        }
+                    }
+                }
+            }
+        }
+        float bb[2];
+#pragma unroll
+        for (int comp = 0; comp < 2; comp++) {
+            float c0 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 0), c1 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 1);
+            float c2 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 2), c3 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 3);
+            float t = __shfl_sync(0xffffffffu, bacc, comp * 5 + 4);
+            float x02 = c0 + c2, x13 = c1 + c3;
+            bb[comp] = t + ((x02 + 0.f) + (x13 + 0.f));
+        }
+        __syncwarp();
+        float b1 = bb[0] * FLT_SCALE, b2 = bb[1] * FLT_SCALE;
+        float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
+        qx += dx;
+        qy += dy;
+        nx = qx + 10.f;
+        ny = qy + 10.f;
+        if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
+        if (j > 0 && fabs((double)(dx + pdx_)) < 0.01 && fabs((double)(dy + pdy_)) < 0.01) {
+            nx -= dx * 0.5f;
+            ny -= dy * 0.5f;
+            break;
+        }
+        pdx_ = dx;
+        pdy_ = dy;
+    }
+    // epilogue of OpenCV's err computation (level 0): final window origin must still be in range
+    if (level == 0 && status) {
+        int fx = __float2int_rd(nx - 10.f), fy = __float2int_rd(ny - 10.f);
+        if (fx < -LK_WIN || fx >= J.w || fy < -LK_WIN || fy >= J.h) status = 0;
+    }
+}
+
+// Whole pyramid for one point.  init is only read when use_init.
+__device__ __forceinline__ void lk_track_point(LKSmem& S, int lane, const Pyramid& I, const Pyramid& J,
+                                               float2 p, float2 init, bool use_init, int max_level,
+                                               float2& out, int& status)
+{
+    status = 1;
+    float nx = 0.f, ny = 0.f;
+    for (int l = max_level; l >= 0; l--) {
+        float sc = (float)(1. / (double)(1 << l));
+        float px = p.x * sc, py = p.y * sc;
+        if (l == max_level) {
+            if (use_init) { nx = init.x * sc; ny = init.y * sc; }
+            else { nx = px; ny = py; }
+        } else { nx = nx * 2.f; ny = ny * 2.f; }
+        lk_level(S, lane, I.lv[l], J.lv[l], px, py, nx, ny, l, status);
+    }
+    out = make_float2(nx, ny);
+}
+
+}  // namespace gf

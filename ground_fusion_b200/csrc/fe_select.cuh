@@ -1,0 +1,432 @@
+// fe_select.cuh -- the order-dependent part of the front end, kept on the device:
+//   k_compact_setmask : reduceVector x4 + track_cnt++ + setMask   (feature_tracker.cpp:170-179, 56-83)
+//   k_mask_disks      : the mask goodFeaturesToTrack sees          (cv::circle == integer disk d^2<=r^2)
+//   k_eig_max / k_candidates : minMaxLoc(masked) -> threshold -> 3x3 dilate -> local maxima
+//   k_nms_round / k_nms_finish : cv::goodFeaturesToTrack's greedy min-distance pass, parallelised by
+//                       rounds ("accept a candidate once every higher-ranked neighbour within r is
+//                       rejected; reject it once any neighbour within r is accepted") - the accepted set
+//                       is exactly the sequential greedy's; the maxCorners cap = top-K of that set by rank
+//   k_finalize        : top-K by (eig desc, address desc), addPoints, undistortedPts, ptsVelocity, depth
+// Arithmetic and ordering follow oracle/fe_cv_restate.c and oracle/fe_oracle.py.
+#pragma once
+#include "fe_sort.cuh"
+#include "gf_common.cuh"
+
+namespace gf {
+
+constexpr int FE_CAP = 1024;        // max max_cnt (one thread per feature in the single-CTA kernels)
+constexpr int FE_SORT_CAP = 4096;   // accepted corners sorted in shared memory by k_finalize
+constexpr int NMS_ACC = 1, NMS_REJ = 2;
+
+struct TrackScalars {
+    int n_prev;       // features entering LK this frame (= features at the end of the previous frame)
+    int n_id;         // next feature id (FeatureTracker::n_id)
+    int n_tracked;
+    int n_kept;
+    int n_new;
+    int n_cand;
+    unsigned int max_key;   // order-preserving encoding of the masked eig maximum (0 = no unmasked pixel)
+    int eig_fixups;
+    int pred_succ;    // successes of the prediction LK pass (feature_tracker.cpp:125-131)
+    int n_out;
+    int nms_rounds;
+    int nms_remaining[16];
+};
+
+struct FeatArrays {   // all device pointers, capacity FE_CAP
+    float2* prev_pts; int* ids; int* track_cnt; float2* prev_un;      // persistent feature state
+    float2* cur_pts; uint8_t* status;                                  // LK output for the n_prev features
+    float2* kept_pts; int* kept_ids; int* kept_cnt; float2* kept_un;  // after setMask
+    float2* pred_pts;
+};
+
+__device__ __forceinline__ unsigned int float_order_key(float v)
+{
+    unsigned int b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // monotone, never 0 for finite v
+}
+__device__ __forceinline__ float float_from_order_key(unsigned int k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, FeatArrays fa, int min_dist)
+{
+    __shared__ sort_elem elems[FE_CAP];
+    __shared__ float2 c_pt[FE_CAP];
+    __shared__ float2 c_un[FE_CAP];
+    __shared__ int c_id[FE_CAP];
+    __shared__ int c_cnt[FE_CAP];
+    __shared__ short2 rc[FE_CAP];          // rounded centres in sorted order
+    __shared__ uint8_t st[FE_CAP];
+    __shared__ int warp_sums[32];
+    __shared__ int s_m;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = sc->n_prev;
+    // ---- reduceVector (stable compaction by status) ----
+    int keep = (tid < n) ? (fa.status[tid] != 0) : 0;
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int pre = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_sums[lane];
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        warp_sums[lane] = incl - v;
+        if (lane == 31) s_m = incl;
+    }
+    __syncthreads();
+    const int m = s_m;
+    if (keep) {
+        int p = warp_sums[wid] + pre;
+        c_pt[p] = fa.cur_pts[tid];
+        c_un[p] = fa.prev_un[tid];
+        c_id[p] = fa.ids[tid];
+        int cnt = fa.track_cnt[tid] + 1;                     // for (auto &n : track_cnt) n++;
+        c_cnt[p] = cnt;
+        elems[p] = ((sort_elem)(unsigned)cnt << 32) | (unsigned)p;
+    }
+    __syncthreads();
+    // ---- std::sort replica (single thread: the permutation is a property of the sequential algorithm) ----
+    if (tid == 0) setmask_sort(elems, m);
+    __syncthreads();
+    int src = 0;
+    if (tid < m) {
+        src = (int)(elems[tid] & 0xffffffffu);
+        float2 p = c_pt[src];
+        rc[tid] = make_short2((short)__float2int_rn(p.x), (short)__float2int_rn(p.y));
+        st[tid] = 0;
+    }
+    __syncthreads();
+    // ---- greedy "mask == 255 then draw disk" by rounds; conflict: d^2 <= r^2 with an earlier kept ----
+    const int r2 = min_dist * min_dist;
+    int my = 0;  // 0 undecided, 1 kept, 2 rejected
+    while (true) {
+        int ns = my;
+        if (tid < m && my == 0) {
+            bool rej = false, blk = false;
+            short2 c = rc[tid];
+            for (int i = 0; i < tid; i++) {
+                int dx = c.x - rc[i].x, dy = c.y - rc[i].y;
+                if (dx * dx + dy * dy <= r2) {
+                    int s = st[i];
+                    if (s == 1) { rej = true; break; }
+                    if (s == 0) blk = true;
+                }
+            }
+            ns = rej ? 2 : (blk ? 0 : 1);
+        }
+        __syncthreads();
+        if (tid < m) { st[tid] = (uint8_t)ns; my = ns; }
+        int undecided = __syncthreads_or((tid < m) && ns == 0);
+        if (!undecided) break;
+    }
+    // ---- emit kept features in sorted order ----
+    int k = (tid < m) && (my == 1);
+    bal = __ballot_sync(0xffffffffu, k);
+    pre = __popc(bal & ((1u << lane) - 1));
+    __syncthreads();
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_sums[lane];
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        warp_sums[lane] = incl - v;
+        if (lane == 31) { sc->n_kept = incl; sc->n_tracked = m; }
+    }
+    __syncthreads();
+    if (k) {
+        int p = warp_sums[wid] + pre;
+        fa.kept_pts[p] = c_pt[src];
+        fa.kept_un[p] = c_un[src];
+        fa.kept_ids[p] = c_id[src];
+        fa.kept_cnt[p] = c_cnt[src];
+    }
+    if (tid == 0) {   // per-frame counters consumed downstream
+        sc->n_cand = 0; sc->max_key = 0; sc->n_new = 0; sc->nms_rounds = 0;
+        for (int i = 0; i < 16; i++) sc->nms_remaining[i] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask (pre-set to 255): zero the integer disk d^2 <= r^2 around each kept feature's rounded centre
+__global__ void k_mask_disks(const TrackScalars* sc, const float2* kept_pts, uint8_t* mask, int w, int h,
+                             int mpitch, int r)
+{
+    if ((int)blockIdx.x >= sc->n_kept) return;
+    float2 p = kept_pts[blockIdx.x];
+    int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
+    int side = 2 * r + 1;
+    for (int i = threadIdx.x; i < side * side; i += blockDim.x) {
+        int dy = i / side - r, dx = i - (i / side) * side - r;
+        int x = cx + dx, y = cy + dy;
+        if (dx * dx + dy * dy <= r * r && x >= 0 && x < w && y >= 0 && y < h) mask[(size_t)y * mpitch + x] = 0;
+    }
+}
+
+// masked maximum of the eig map (cv::minMaxLoc(eig, 0, &maxVal, 0, 0, mask))
+__global__ void __launch_bounds__(256) k_eig_max(TrackScalars* sc, const float* eig, int epitch,
+                                                 const uint8_t* mask, int mpitch, int w, int h)
+{
+    unsigned int best = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x) {
+        int y = i / w, x = i - y * w;
+        if (mask[(size_t)y * mpitch + x]) best = max(best, float_order_key(eig[(size_t)y * epitch + x]));
+    }
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    __shared__ unsigned int wb[8];
+    if ((threadIdx.x & 31) == 0) wb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) best = max(best, wb[i]);
+        if (best) atomicMax(&sc->max_key, best);
+    }
+}
+
+struct NmsGrid {
+    int cs, gw, gh, cap;            // cell size (= min_dist), grid dims, bucket capacity (cs*cs)
+    int* cell_cnt;                  // [gw*gh]
+    unsigned long long* key;        // [gw*gh*cap]   (eig bits << 32 | y*w + x)
+    uint8_t* state;                 // [gw*gh*cap]
+    int* cand_ref;                  // flat list -> cell*cap + slot
+};
+
+// threshold(TOZERO, 0.01*max) -> dilate 3x3 -> val != 0 && val == dilated && mask, on the interior
+__global__ void __launch_bounds__(256) k_candidates(TrackScalars* sc, const float* eig, int epitch,
+                                                    const uint8_t* mask, int mpitch, int w, int h, NmsGrid g)
+{
+    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x < 1 || x >= w - 1 || y < 1 || y >= h - 1) return;
+    double maxVal = sc->max_key ? (double)float_from_order_key(sc->max_key) : 0.0;
+    float thr = (float)(maxVal * 0.01);
+    const float* e = eig + (size_t)y * epitch + x;
+    float v = __ldg(e);
+    if (!(v > thr) || v == 0.f) return;
+    if (!mask[(size_t)y * mpitch + x]) return;
+    float m = fmaxf(fmaxf(__ldg(e - 1), __ldg(e + 1)), fmaxf(__ldg(e - epitch), __ldg(e + epitch)));
+    m = fmaxf(m, fmaxf(fmaxf(__ldg(e - epitch - 1), __ldg(e - epitch + 1)), fmaxf(__ldg(e + epitch - 1), __ldg(e + epitch + 1))));
+    if (m > v) return;   // a larger neighbour is itself > thr, so the dilated value would exceed v
+    int cell = (y / g.cs) * g.gw + (x / g.cs);
+    int slot = atomicAdd(&g.cell_cnt[cell], 1);
+    int ref = cell * g.cap + slot;
+    g.key[ref] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+    g.state[ref] = 0;
+    int i = atomicAdd(&sc->n_cand, 1);
+    g.cand_ref[i] = ref;
+}
+
+// One candidate's decision from the current (possibly stale, always monotone) neighbour states.
+__device__ __forceinline__ int nms_decide(const NmsGrid& g, int ref, int w, int r2)
+{
+    unsigned long long key = g.key[ref];
+    unsigned addr = (unsigned)(key & 0xffffffffu);
+    int y = addr / w, x = addr - y * w;
+    int cx = x / g.cs, cy = y / g.cs;
+    bool blocked = false;
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.gh - 1); yy++)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g.gw - 1); xx++) {
+            int cell = yy * g.gw + xx;
+            int cnt = g.cell_cnt[cell];
+            const unsigned long long* kk = g.key + (size_t)cell * g.cap;
+            const volatile uint8_t* ss = g.state + (size_t)cell * g.cap;
+            for (int s = 0; s < cnt; s++) {
+                unsigned long long ok = kk[s];
+                unsigned oa = (unsigned)(ok & 0xffffffffu);
+                int oy = oa / w, ox = oa - oy * w;
+                int dx = x - ox, dy = y - oy;
+                if (dx * dx + dy * dy < r2 && oa != addr) {
+                    int os = ss[s];
+                    if (os == NMS_ACC) return NMS_REJ;
+                    if (os == 0 && ok > key) blocked = true;
+                }
+            }
+        }
+    return blocked ? 0 : NMS_ACC;
+}
+
+__global__ void __launch_bounds__(256) k_nms_round(TrackScalars* sc, NmsGrid g, int w, int min_dist, int round)
+{
+    if (round > 0 && sc->nms_remaining[round - 1] == 0) return;
+    const int n = sc->n_cand;
+    int undecided = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int ref = g.cand_ref[i];
+        if (((volatile uint8_t*)g.state)[ref] != 0) continue;
+        int d = nms_decide(g, ref, w, min_dist * min_dist);
+        if (d) ((volatile uint8_t*)g.state)[ref] = (uint8_t)d;
+        else undecided++;
+    }
+    undecided = __reduce_add_sync(0xffffffffu, undecided);
+    if ((threadIdx.x & 31) == 0 && undecided) atomicAdd(&sc->nms_remaining[round], undecided);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&sc->nms_rounds, round + 1);
+}
+
+// Single CTA: iterate until every candidate is decided (normally nothing is left after the rounds).
+__global__ void __launch_bounds__(1024) k_nms_finish(TrackScalars* sc, NmsGrid g, int w, int min_dist, int last_round)
+{
+    if (sc->nms_remaining[last_round] == 0) return;
+    const int n = sc->n_cand;
+    int rounds = 0;
+    while (true) {
+        int undecided = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            int ref = g.cand_ref[i];
+            if (((volatile uint8_t*)g.state)[ref] != 0) continue;
+            int d = nms_decide(g, ref, w, min_dist * min_dist);
+            if (d) ((volatile uint8_t*)g.state)[ref] = (uint8_t)d;
+            else undecided++;
+        }
+        __threadfence_block();
+        rounds++;
+        if (!__syncthreads_or(undecided)) break;
+    }
+    if (threadIdx.x == 0) sc->nms_rounds += rounds;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct CamParams { double fx, fy, cx, cy, k1, k2, p1, p2; int no_distortion; };
+
+__device__ __forceinline__ void cam_distortion(const CamParams& c, double x, double y, double& dx, double& dy)
+{   // PinholeCamera::distortion, camera_models/src/camera_models/PinholeCamera.cc:646-662
+    double mx2 = x * x, my2 = y * y, mxy = x * y;
+    double rho2 = mx2 + my2;
+    double rad = c.k1 * rho2 + c.k2 * rho2 * rho2;
+    dx = x * rad + 2.0 * c.p1 * mxy + c.p2 * (rho2 + 2.0 * mx2);
+    dy = y * rad + 2.0 * c.p2 * mxy + c.p1 * (rho2 + 2.0 * my2);
+}
+__device__ __forceinline__ void cam_lift(const CamParams& c, double u, double v, double& ox, double& oy)
+{   // PinholeCamera::liftProjective, PinholeCamera.cc:450-510 (recursive distortion model, n = 8)
+    double ik11 = 1.0 / c.fx, ik13 = -c.cx / c.fx, ik22 = 1.0 / c.fy, ik23 = -c.cy / c.fy;
+    double mx_d = ik11 * u + ik13, my_d = ik22 * v + ik23;
+    if (c.no_distortion) { ox = mx_d; oy = my_d; return; }
+    double dx, dy;
+    cam_distortion(c, mx_d, my_d, dx, dy);
+    double mx_u = mx_d - dx, my_u = my_d - dy;
+    for (int i = 1; i < 8; i++) {
+        cam_distortion(c, mx_u, my_u, dx, dy);
+        mx_u = mx_d - dx;
+        my_u = my_d - dy;
+    }
+    ox = mx_u; oy = my_u;
+}
+__device__ __forceinline__ void cam_project(const CamParams& c, double X, double Y, double Z, double& u, double& v)
+{   // PinholeCamera::spaceToPlane, PinholeCamera.cc:520-541
+    double x = X / Z, y = Y / Z;
+    if (!c.no_distortion) { double dx, dy; cam_distortion(c, x, y, dx, dy); x = x + dx; y = y + dy; }
+    u = c.fx * x + c.cx;
+    v = c.fy * y + c.cy;
+}
+
+struct OutHeader { int n_out, n_prev, n_tracked, n_kept, n_new, n_cand, nms_rounds, eig_fixups; };
+
+// top-K of the accepted corners, addPoints, undistortedPts, ptsVelocity, depth, next-frame state.
+__global__ void __launch_bounds__(1024) k_finalize(TrackScalars* sc, FeatArrays fa, NmsGrid g, int w, int max_cnt,
+                                                   CamParams cam, double dt, const uint16_t* depth, int dpitch /*elements*/,
+                                                   int depth_cam, int h, OutHeader* out_hdr, gf_obs* out_obs)
+{
+    __shared__ unsigned long long keys[FE_SORT_CAP];
+    __shared__ int s_nacc;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_nacc = 0;
+    __syncthreads();
+    const int ncand = sc->n_cand;
+    const int n_kept = sc->n_kept;
+    const int want = max(max_cnt - n_kept, 0);
+    for (int i = tid; i < ncand; i += blockDim.x) {
+        int ref = g.cand_ref[i];
+        if (g.state[ref] == NMS_ACC) {
+            int p = atomicAdd(&s_nacc, 1);
+            if (p < FE_SORT_CAP) keys[p] = g.key[ref];
+        }
+    }
+    __syncthreads();
+    int nacc = s_nacc;
+    int n_new;
+    if (nacc <= FE_SORT_CAP) {
+        int np2 = 1;
+        while (np2 < nacc) np2 <<= 1;
+        for (int i = nacc + tid; i < np2; i += blockDim.x) keys[i] = 0ull;
+        __syncthreads();
+        for (int k = 2; k <= np2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < np2; i += blockDim.x) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        unsigned long long a = keys[i], b = keys[ixj];
+                        bool desc = ((i & k) == 0);
+                        if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        n_new = min(want, nacc);
+    } else {
+        // more accepted corners than the shared sort buffer (tiny min_dist): K selection passes over HBM
+        __shared__ unsigned long long s_best[32];
+        __shared__ unsigned long long s_prev;
+        n_new = min(min(want, nacc), FE_SORT_CAP);
+        if (tid == 0) s_prev = ~0ull;
+        __syncthreads();
+        for (int k = 0; k < n_new; k++) {
+            unsigned long long lim = s_prev, best = 0ull;
+            for (int i = tid; i < ncand; i += blockDim.x) {
+                int ref = g.cand_ref[i];
+                if (g.state[ref] == NMS_ACC) { unsigned long long kk = g.key[ref]; if (kk < lim && kk > best) best = kk; }
+            }
+            for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); if (t > best) best = t; }
+            if ((tid & 31) == 0) s_best[tid >> 5] = best;
+            __syncthreads();
+            if (tid == 0) { for (int i = 1; i < 32; i++) if (s_best[i] > best) best = s_best[i]; keys[k] = best; s_prev = best; }
+            __syncthreads();
+        }
+    }
+    const int total = n_kept + n_new;
+    const int n_id = sc->n_id;
+    // addPoints + per-feature outputs; thread i <-> feature i of the new cur_pts order (kept..., new...)
+    if (tid < total) {
+        float2 p, un_prev = make_float2(0.f, 0.f);
+        int id, cnt;
+        bool has_prev = false;
+        if (tid < n_kept) {
+            p = fa.kept_pts[tid]; id = fa.kept_ids[tid]; cnt = fa.kept_cnt[tid]; un_prev = fa.kept_un[tid]; has_prev = true;
+        } else {
+            unsigned addr = (unsigned)(keys[tid - n_kept] & 0xffffffffu);
+            int y = addr / w, x = addr - y * w;
+            p = make_float2((float)x, (float)y); id = n_id + (tid - n_kept); cnt = 1;
+        }
+        double ux, uy;
+        cam_lift(cam, (double)p.x, (double)p.y, ux, uy);
+        float2 un = make_float2((float)(ux / 1.0), (float)(uy / 1.0));
+        float2 vel = make_float2(0.f, 0.f);
+        if (has_prev) {
+            double vx = (double)(un.x - un_prev.x) / dt, vy = (double)(un.y - un_prev.y) / dt;
+            vel = make_float2((float)vx, (float)vy);
+        }
+        double dval = -2.4;
+        if (depth_cam) {
+            int r = (int)round((double)p.y), c = (int)round((double)p.x);
+            r = min(max(r, 0), h - 1); c = min(max(c, 0), w - 1);   // always in range after inBorder; belt and braces
+            dval = (double)(int)depth[(size_t)r * dpitch + c] / 1000.0;
+        }
+        gf_obs o;
+        o.id = id; o.track_cnt = cnt;
+        o.v[0] = (double)un.x; o.v[1] = (double)un.y; o.v[2] = 1.0; o.v[3] = (double)p.x; o.v[4] = (double)p.y;
+        o.v[5] = (double)vel.x; o.v[6] = (double)vel.y; o.v[7] = dval;
+        out_obs[tid] = o;
+        // state for the next frame (prev_pts = cur_pts; prev_un_pts_map = cur_un_pts_map)
+        fa.prev_pts[tid] = p; fa.ids[tid] = id; fa.track_cnt[tid] = cnt; fa.prev_un[tid] = un;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        out_hdr->n_out = total; out_hdr->n_prev = sc->n_prev; out_hdr->n_tracked = sc->n_tracked;
+        out_hdr->n_kept = n_kept; out_hdr->n_new = n_new; out_hdr->n_cand = ncand;
+        out_hdr->nms_rounds = sc->nms_rounds; out_hdr->eig_fixups = sc->eig_fixups;
+        sc->n_new = n_new; sc->n_out = total;
+        sc->n_prev = total; sc->n_id = n_id + n_new; sc->eig_fixups = 0;
+    }
+}
+
+}  // namespace gf

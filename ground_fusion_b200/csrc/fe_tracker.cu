@@ -1,0 +1,683 @@
+// fe_tracker.cu -- gf_tracker_* and gf_stage_* (C ABI), the host side of the B200 front end.
+//
+// Mirrors FeatureTracker::trackImage (reference vins_estimator/src/featureTracker/feature_tracker.cpp:103-372).
+// One frame = one fixed sequence of copies and kernels on two streams (no host round trip inside the
+// frame; the only synchronisation is the wait for the result):
+//
+//   s_main: H2D gray/depth -> pyrDown x3 -> [prediction LK] -> k_track (fwd LK 3 lvls + bwd LK 1 lvl +
+//           status rules) -> k_compact_setmask -> mask disks -> (join) -> masked max -> candidates ->
+//           min-distance rounds -> k_finalize (top-K, addPoints, undistort, velocity, depth) -> D2H
+//   s_aux : (fork after H2D) k_min_eig -> k_eig_verify                       [independent of LK/mask]
+//
+// All feature state (prev_pts, ids, track_cnt, undistorted points, n_id) lives in HBM between frames.
+#include <new>
+#include <vector>
+
+#include "fe_eig.cuh"
+#include "fe_lk.cuh"
+#include "fe_select.cuh"
+
+namespace gf {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+constexpr int NMS_ROUNDS = 6;   // multi-CTA rounds launched unconditionally; k_nms_finish mops up
+
+struct FrameParams { double dt; int has_pred; int depth_valid; };
+
+// ------------------------------------------------------------------------------------------------
+// kernels that need the LK device code
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LK_WARPS * 32) k_lk_stage(Pyramid I, Pyramid J, const float2* prev_pts, float2* next_pts,
+                                                            int n, int max_level, int use_init, uint8_t* status)
+{
+    __shared__ LKSmem sm[LK_WARPS];
+    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int i = blockIdx.x * LK_WARPS + wid;
+    if (i >= n) return;
+    float2 p = prev_pts[i], init = use_init ? next_pts[i] : p, out;
+    int st;
+    lk_track_point(sm[wid], lane, I, J, p, init, use_init != 0, max_level, out, st);
+    if (lane == 0) { next_pts[i] = out; status[i] = (uint8_t)st; }
+}
+
+// Prediction pass (feature_tracker.cpp:118-124): maxLevel 1 seeded with predict_pts; counts successes.
+__global__ void __launch_bounds__(LK_WARPS * 32) k_lk_pred(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa)
+{
+    __shared__ LKSmem sm[LK_WARPS];
+    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int i = blockIdx.x * LK_WARPS + wid;
+    if (i >= sc->n_prev) return;
+    float2 out;
+    int st;
+    lk_track_point(sm[wid], lane, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st);
+    if (lane == 0) { fa.cur_pts[i] = out; fa.status[i] = (uint8_t)st; if (st) atomicAdd(&sc->pred_succ, 1); }
+}
+
+// Forward LK (3 levels) + reverse check (1 level, USE_INITIAL_FLOW) + inBorder + grey<=250
+// (feature_tracker.cpp:118-168).  One warp per feature.
+__global__ void __launch_bounds__(LK_WARPS * 32) k_track(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa,
+                                                         const FrameParams* fp, int flow_back)
+{
+    __shared__ LKSmem sm[LK_WARPS];
+    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int i = blockIdx.x * LK_WARPS + wid;
+    if (i >= sc->n_prev) return;
+    const float2 p = fa.prev_pts[i];
+    float2 q;
+    int st;
+    if (fp->has_pred && sc->pred_succ >= 10) { q = fa.cur_pts[i]; st = fa.status[i]; }
+    else lk_track_point(sm[wid], lane, prev, cur, p, p, false, 3, q, st);
+    if (flow_back) {
+        float2 r;
+        int rst;
+        lk_track_point(sm[wid], lane, cur, prev, q, p, true, 1, r, rst);
+        double dx = (double)(p.x - r.x), dy = (double)(p.y - r.y);
+        st = (st && rst && sqrt(dx * dx + dy * dy) <= 0.5) ? 1 : 0;
+    }
+    const int col = cur.lv[0].w, row = cur.lv[0].h;
+    if (st) {   // inBorder (feature_tracker.cpp:14-20)
+        int ix = __float2int_rn(q.x), iy = __float2int_rn(q.y);
+        if (!(1 <= ix && ix < col - 1 && 1 <= iy && iy < row - 1)) st = 0;
+    }
+    if (st) {   // cur_img.at<uchar>((int)x, (int)y): row = x, col = y (sic); out of bounds => not saturated
+        int p_u = __float2int_rz(q.x), p_v = __float2int_rz(q.y);
+        int grey = (p_u >= 0 && p_u < row && p_v >= 0 && p_v < col) ? cur.lv[0].ptr[(size_t)p_u * cur.lv[0].pitch + p_v] : 0;
+        if (grey > 250) st = 0;
+    }
+    if (lane == 0) { fa.cur_pts[i] = q; fa.status[i] = (uint8_t)st; }
+}
+
+// setPrediction (feature_tracker.cpp:1006-1027)
+__global__ void k_set_prediction(TrackScalars* sc, FeatArrays fa, const int* ids, const double* xyz, int n, CamParams cam)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sc->n_prev) return;
+    int id = fa.ids[i];
+    float2 pp = fa.prev_pts[i];
+    for (int k = 0; k < n; k++)
+        if (ids[k] == id) {
+            double u, v;
+            cam_project(cam, xyz[3 * k], xyz[3 * k + 1], xyz[3 * k + 2], u, v);
+            pp = make_float2((float)u, (float)v);
+            break;
+        }
+    fa.pred_pts[i] = pp;
+    if (i == 0) sc->pred_succ = 0;
+}
+
+// removeOutliers (feature_tracker.cpp:1029-1045): stable removal from prev_pts / ids / track_cnt
+__global__ void __launch_bounds__(FE_CAP) k_remove_ids(TrackScalars* sc, FeatArrays fa, const int* ids, int n)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int s_m;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int np = sc->n_prev;
+    int keep = 0;
+    float2 p, un; int id = 0, cnt = 0;
+    if (tid < np) {
+        id = fa.ids[tid]; p = fa.prev_pts[tid]; un = fa.prev_un[tid]; cnt = fa.track_cnt[tid];
+        keep = 1;
+        for (int k = 0; k < n; k++) if (ids[k] == id) { keep = 0; break; }
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int pre = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_sums[wid] = __popc(bal);
+    __syncthreads();
+    if (wid == 0) {
+        int v = warp_sums[lane], incl = v;
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        warp_sums[lane] = incl - v;
+        if (lane == 31) s_m = incl;
+    }
+    __syncthreads();
+    if (keep) {
+        int d = warp_sums[wid] + pre;
+        fa.prev_pts[d] = p; fa.ids[d] = id; fa.track_cnt[d] = cnt; fa.prev_un[d] = un;
+    }
+    if (tid == 0) sc->n_prev = s_m;
+}
+
+__global__ void k_pitch_copy_u8(const uint8_t* src, int spitch, uint8_t* dst, int dpitch, int w, int h)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x < w && y < h) dst[(size_t)y * dpitch + x] = src[(size_t)y * spitch + x];
+}
+
+}  // namespace gf
+
+using namespace gf;
+
+// ------------------------------------------------------------------------------------------------
+struct gf_tracker {
+    int device, w, h;
+    gf_tracker_cfg cfg;
+    CamParams cam;
+    cudaStream_t s_main, s_aux;
+    cudaEvent_t ev_fork, ev_eig, ev_t0, ev_t1;
+    uint8_t* d_pyr[2][4];
+    int lw[4], lh[4], lp[4];
+    uint16_t* d_depth; int depth_pitch_el;
+    float* d_eig; int epitch;
+    uint8_t* d_mask; int mpitch;
+    double *d_spec_start, *d_spec_end; int nbands;
+    NmsGrid grid; size_t grid_cells;
+    TrackScalars* d_sc;
+    FeatArrays fa;
+    OutHeader* d_hdr; gf_obs* d_obs;
+    FrameParams* d_fp;
+    int* d_tmp_ids; double* d_tmp_xyz;
+    // pinned host
+    uint8_t* h_gray; uint16_t* h_depth; OutHeader* h_hdr; gf_obs* h_obs; uint8_t* h_status; FrameParams* h_fp;
+    int* h_tmp_ids; double* h_tmp_xyz;
+    int cur;             // pyramid slot that receives the next frame
+    double prev_time;
+    bool has_pred, pending, depth_last;
+    float last_ms;
+};
+
+static Pyramid make_pyr(const gf_tracker* t, int slot)
+{
+    Pyramid P;
+    for (int l = 0; l < 4; l++) { P.lv[l].ptr = t->d_pyr[slot][l]; P.lv[l].w = t->lw[l]; P.lv[l].h = t->lh[l]; P.lv[l].pitch = t->lp[l]; }
+    return P;
+}
+
+static CamParams make_cam(const double* p)
+{
+    CamParams c;
+    c.fx = p[0]; c.fy = p[1]; c.cx = p[2]; c.cy = p[3]; c.k1 = p[4]; c.k2 = p[5]; c.p1 = p[6]; c.p2 = p[7];
+    c.no_distortion = (p[4] == 0.0 && p[5] == 0.0 && p[6] == 0.0 && p[7] == 0.0);
+    return c;
+}
+
+static int select_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        snprintf(g_err, sizeof(g_err), "no CUDA device visible (%s); libgf_b200 has no CPU fallback", cudaGetErrorString(e));
+        return GF_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) return set_err(GF_ERR_INVALID_ARG, "device index out of range");
+    GF_CUDA(cudaSetDevice(device));
+    return GF_OK;
+}
+
+static int alloc_nms_grid(NmsGrid& g, int w, int h, int min_dist, size_t* cells_out)
+{
+    g.cs = min_dist;
+    g.gw = (w + g.cs - 1) / g.cs;
+    g.gh = (h + g.cs - 1) / g.cs;
+    g.cap = g.cs * g.cs;
+    size_t cells = (size_t)g.gw * g.gh;
+    GF_CUDA(cudaMalloc(&g.cell_cnt, cells * sizeof(int)));
+    GF_CUDA(cudaMalloc(&g.key, cells * g.cap * sizeof(unsigned long long)));
+    GF_CUDA(cudaMalloc(&g.state, cells * g.cap));
+    GF_CUDA(cudaMalloc(&g.cand_ref, (size_t)w * h * sizeof(int)));
+    if (cells_out) *cells_out = cells;
+    return GF_OK;
+}
+static void free_nms_grid(NmsGrid& g)
+{
+    cudaFree(g.cell_cnt); cudaFree(g.key); cudaFree(g.state); cudaFree(g.cand_ref);
+}
+
+// GFTT tail shared by the tracker and gf_stage_gftt: mask -> max -> candidates -> NMS rounds
+static int enqueue_gftt_select(cudaStream_t s, TrackScalars* d_sc, const float2* kept_pts, int max_kept, const float* d_eig,
+                               int epitch, uint8_t* d_mask, int mpitch, int w, int h, int min_dist, NmsGrid& grid, size_t cells)
+{
+    GF_CUDA(cudaMemsetAsync(d_mask, 255, (size_t)mpitch * h, s));
+    GF_CUDA(cudaMemsetAsync(grid.cell_cnt, 0, cells * sizeof(int), s));
+    if (max_kept > 0) { k_mask_disks<<<max_kept, 256, 0, s>>>(d_sc, kept_pts, d_mask, w, h, mpitch, min_dist); GF_LAUNCHED(); }
+    k_eig_max<<<296, 256, 0, s>>>(d_sc, d_eig, epitch, d_mask, mpitch, w, h); GF_LAUNCHED();
+    dim3 cg((w + 31) / 32, (h + 7) / 8);
+    k_candidates<<<cg, 256, 0, s>>>(d_sc, d_eig, epitch, d_mask, mpitch, w, h, grid); GF_LAUNCHED();
+    for (int r = 0; r < NMS_ROUNDS; r++) { k_nms_round<<<296, 256, 0, s>>>(d_sc, grid, w, min_dist, r); GF_LAUNCHED(); }
+    k_nms_finish<<<1, 1024, 0, s>>>(d_sc, grid, w, min_dist, NMS_ROUNDS - 1); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    return GF_OK;
+}
+
+static int enqueue_min_eig(cudaStream_t s, const Level& img, float* d_eig, int epitch, double* spec_start, double* spec_end,
+                           int nbands, int* d_fixups)
+{
+    dim3 g((img.w + EIG_TX - 1) / EIG_TX, nbands);
+    k_min_eig<<<g, EIG_TX, 0, s>>>(img, d_eig, epitch, spec_start, spec_end); GF_LAUNCHED();
+    k_eig_verify<<<(img.w + 127) / 128, 128, 0, s>>>(img, d_eig, epitch, spec_start, spec_end, nbands, d_fixups); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    return GF_OK;
+}
+
+static int enqueue_pyramid(cudaStream_t s, const gf_tracker* t, int slot)
+{
+    for (int l = 1; l < 4; l++) {
+        Level src{t->d_pyr[slot][l - 1], t->lw[l - 1], t->lh[l - 1], t->lp[l - 1]};
+        dim3 g((t->lw[l] + PD_TX - 1) / PD_TX, (t->lh[l] + PD_TY - 1) / PD_TY), b(PD_TX, PD_TY);
+        k_pyr_down<<<g, b, 0, s>>>(src, t->d_pyr[slot][l], t->lw[l], t->lh[l], t->lp[l]); GF_LAUNCHED();
+    }
+    GF_CUDA(cudaGetLastError());
+    return GF_OK;
+}
+
+extern "C" {
+
+const char* gf_last_error(void) { return g_err; }
+const char* gf_version(void) { return "gf_b200 0.1 sm_100a"; }
+uint64_t gf_kernel_launch_count(void) { return g_launches.load(); }
+
+int gf_tracker_create(gf_tracker** out, int device, int width, int height, const gf_tracker_cfg* cfg)
+{
+    if (!out || !cfg) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->max_cnt < 1 || cfg->max_cnt > FE_CAP) return set_err(GF_ERR_CAPACITY, "max_cnt must be in [1, 1024]");
+    if (cfg->min_dist < 1 || cfg->min_dist > 255) return set_err(GF_ERR_INVALID_ARG, "min_dist must be in [1, 255]");
+    // the 4-level pyramid needs every level larger than the 21x21 window plus the cached-region reach
+    if (((width + 7) / 8) < 48 || ((height + 7) / 8) < 48 || width > 8192 || height > 8192)
+        return set_err(GF_ERR_UNSUPPORTED, "image must be at least 377x377 and at most 8192x8192");
+    int rc = select_device(device);
+    if (rc) return rc;
+    gf_tracker* t = new (std::nothrow) gf_tracker();
+    if (!t) return set_err(GF_ERR_CUDA, "out of host memory");
+    memset(t, 0, sizeof(*t));
+    t->device = device; t->w = width; t->h = height; t->cfg = *cfg; t->cam = make_cam(cfg->pinhole);
+    GF_CUDA(cudaStreamCreateWithFlags(&t->s_main, cudaStreamNonBlocking));
+    GF_CUDA(cudaStreamCreateWithFlags(&t->s_aux, cudaStreamNonBlocking));
+    GF_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
+    GF_CUDA(cudaEventCreateWithFlags(&t->ev_eig, cudaEventDisableTiming));
+    GF_CUDA(cudaEventCreate(&t->ev_t0));
+    GF_CUDA(cudaEventCreate(&t->ev_t1));
+    int lw = width, lh = height;
+    for (int l = 0; l < 4; l++) {
+        t->lw[l] = lw; t->lh[l] = lh; t->lp[l] = align_up(lw, 16);
+        for (int s = 0; s < 2; s++) {
+            GF_CUDA(cudaMalloc(&t->d_pyr[s][l], (size_t)t->lp[l] * lh));
+            GF_CUDA(cudaMemset(t->d_pyr[s][l], 0, (size_t)t->lp[l] * lh));
+        }
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+    }
+    t->depth_pitch_el = align_up(width, 8);
+    GF_CUDA(cudaMalloc(&t->d_depth, (size_t)t->depth_pitch_el * height * sizeof(uint16_t)));
+    t->epitch = align_up(width, 4);
+    GF_CUDA(cudaMalloc(&t->d_eig, (size_t)t->epitch * height * sizeof(float)));
+    t->mpitch = align_up(width, 16);
+    GF_CUDA(cudaMalloc(&t->d_mask, (size_t)t->mpitch * height));
+    t->nbands = (height + EIG_BAND - 1) / EIG_BAND;
+    GF_CUDA(cudaMalloc(&t->d_spec_start, (size_t)t->nbands * 3 * width * sizeof(double)));
+    GF_CUDA(cudaMalloc(&t->d_spec_end, (size_t)t->nbands * 3 * width * sizeof(double)));
+    rc = alloc_nms_grid(t->grid, width, height, cfg->min_dist, &t->grid_cells);
+    if (rc) return rc;
+    GF_CUDA(cudaMalloc(&t->d_sc, sizeof(TrackScalars)));
+    GF_CUDA(cudaMemset(t->d_sc, 0, sizeof(TrackScalars)));
+    FeatArrays& fa = t->fa;
+    GF_CUDA(cudaMalloc(&fa.prev_pts, FE_CAP * sizeof(float2))); GF_CUDA(cudaMalloc(&fa.ids, FE_CAP * sizeof(int)));
+    GF_CUDA(cudaMalloc(&fa.track_cnt, FE_CAP * sizeof(int))); GF_CUDA(cudaMalloc(&fa.prev_un, FE_CAP * sizeof(float2)));
+    GF_CUDA(cudaMalloc(&fa.cur_pts, FE_CAP * sizeof(float2))); GF_CUDA(cudaMalloc(&fa.status, FE_CAP));
+    GF_CUDA(cudaMalloc(&fa.kept_pts, FE_CAP * sizeof(float2))); GF_CUDA(cudaMalloc(&fa.kept_ids, FE_CAP * sizeof(int)));
+    GF_CUDA(cudaMalloc(&fa.kept_cnt, FE_CAP * sizeof(int))); GF_CUDA(cudaMalloc(&fa.kept_un, FE_CAP * sizeof(float2)));
+    GF_CUDA(cudaMalloc(&fa.pred_pts, FE_CAP * sizeof(float2)));
+    GF_CUDA(cudaMemset(fa.status, 0, FE_CAP));
+    GF_CUDA(cudaMalloc(&t->d_hdr, sizeof(OutHeader)));
+    GF_CUDA(cudaMalloc(&t->d_obs, FE_CAP * sizeof(gf_obs)));
+    GF_CUDA(cudaMalloc(&t->d_fp, sizeof(FrameParams)));
+    GF_CUDA(cudaMalloc(&t->d_tmp_ids, FE_CAP * sizeof(int)));
+    GF_CUDA(cudaMalloc(&t->d_tmp_xyz, FE_CAP * 3 * sizeof(double)));
+    GF_CUDA(cudaHostAlloc(&t->h_gray, (size_t)width * height, cudaHostAllocDefault));
+    GF_CUDA(cudaHostAlloc(&t->h_depth, (size_t)width * height * sizeof(uint16_t), cudaHostAllocDefault));
+    GF_CUDA(cudaHostAlloc(&t->h_hdr, sizeof(OutHeader), cudaHostAllocDefault));
+    GF_CUDA(cudaHostAlloc(&t->h_obs, FE_CAP * sizeof(gf_obs), cudaHostAllocDefault));
+    GF_CUDA(cudaHostAlloc(&t->h_status, FE_CAP, cudaHostAllocDefault));
+    GF_CUDA(cudaHostAlloc(&t->h_fp, sizeof(FrameParams), cudaHostAllocDefault));
+    GF_CUDA(cudaHostAlloc(&t->h_tmp_ids, FE_CAP * sizeof(int), cudaHostAllocDefault));
+    GF_CUDA(cudaHostAlloc(&t->h_tmp_xyz, FE_CAP * 3 * sizeof(double), cudaHostAllocDefault));
+    GF_CUDA(cudaDeviceSynchronize());
+    *out = t;
+    return GF_OK;
+}
+
+void gf_tracker_destroy(gf_tracker* t)
+{
+    if (!t) return;
+    cudaSetDevice(t->device);
+    cudaStreamSynchronize(t->s_main); cudaStreamSynchronize(t->s_aux);
+    for (int s = 0; s < 2; s++) for (int l = 0; l < 4; l++) cudaFree(t->d_pyr[s][l]);
+    cudaFree(t->d_depth); cudaFree(t->d_eig); cudaFree(t->d_mask); cudaFree(t->d_spec_start); cudaFree(t->d_spec_end);
+    free_nms_grid(t->grid);
+    cudaFree(t->d_sc);
+    FeatArrays& fa = t->fa;
+    cudaFree(fa.prev_pts); cudaFree(fa.ids); cudaFree(fa.track_cnt); cudaFree(fa.prev_un); cudaFree(fa.cur_pts); cudaFree(fa.status);
+    cudaFree(fa.kept_pts); cudaFree(fa.kept_ids); cudaFree(fa.kept_cnt); cudaFree(fa.kept_un); cudaFree(fa.pred_pts);
+    cudaFree(t->d_hdr); cudaFree(t->d_obs); cudaFree(t->d_fp); cudaFree(t->d_tmp_ids); cudaFree(t->d_tmp_xyz);
+    cudaFreeHost(t->h_gray); cudaFreeHost(t->h_depth); cudaFreeHost(t->h_hdr); cudaFreeHost(t->h_obs); cudaFreeHost(t->h_status);
+    cudaFreeHost(t->h_fp); cudaFreeHost(t->h_tmp_ids); cudaFreeHost(t->h_tmp_xyz);
+    cudaStreamDestroy(t->s_main); cudaStreamDestroy(t->s_aux);
+    cudaEventDestroy(t->ev_fork); cudaEventDestroy(t->ev_eig); cudaEventDestroy(t->ev_t0); cudaEventDestroy(t->ev_t1);
+    delete t;
+}
+
+int gf_tracker_host_buffers(gf_tracker* t, uint8_t** gray, uint16_t** depth)
+{
+    if (!t) return set_err(GF_ERR_INVALID_ARG, "null tracker");
+    if (gray) *gray = t->h_gray;
+    if (depth) *depth = t->h_depth;
+    return GF_OK;
+}
+
+// Everything after the frame is in HBM (d_pyr[cur][0], d_depth).
+static int enqueue_frame(gf_tracker* t, double time, bool depth_valid)
+{
+    const int cur = t->cur, prev = cur ^ 1;
+    cudaStream_t s = t->s_main;
+    t->h_fp->dt = time - t->prev_time;
+    t->h_fp->has_pred = t->has_pred ? 1 : 0;
+    t->h_fp->depth_valid = depth_valid ? 1 : 0;
+    GF_CUDA(cudaMemcpyAsync(t->d_fp, t->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
+    Pyramid Pc = make_pyr(t, cur), Pp = make_pyr(t, prev);
+    // fork: min-eig of the new frame does not depend on tracking
+    GF_CUDA(cudaEventRecord(t->ev_fork, s));
+    GF_CUDA(cudaStreamWaitEvent(t->s_aux, t->ev_fork, 0));
+    int rc = enqueue_min_eig(t->s_aux, Pc.lv[0], t->d_eig, t->epitch, t->d_spec_start, t->d_spec_end, t->nbands, &t->d_sc->eig_fixups);
+    if (rc) return rc;
+    GF_CUDA(cudaEventRecord(t->ev_eig, t->s_aux));
+    rc = enqueue_pyramid(s, t, cur);
+    if (rc) return rc;
+    const int lk_grid = (t->cfg.max_cnt + LK_WARPS - 1) / LK_WARPS;
+    if (t->has_pred) { k_lk_pred<<<lk_grid, LK_WARPS * 32, 0, s>>>(Pp, Pc, t->d_sc, t->fa); GF_LAUNCHED(); }
+    k_track<<<lk_grid, LK_WARPS * 32, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp, t->cfg.flow_back); GF_LAUNCHED();
+    k_compact_setmask<<<1, FE_CAP, 0, s>>>(t->d_sc, t->fa, t->cfg.min_dist); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaMemcpyAsync(t->h_status, t->fa.status, t->cfg.max_cnt, cudaMemcpyDeviceToHost, s));
+    GF_CUDA(cudaStreamWaitEvent(s, t->ev_eig, 0));
+    rc = enqueue_gftt_select(s, t->d_sc, t->fa.kept_pts, t->cfg.max_cnt, t->d_eig, t->epitch, t->d_mask, t->mpitch, t->w, t->h,
+                             t->cfg.min_dist, t->grid, t->grid_cells);
+    if (rc) return rc;
+    // reference quirk: depth_cam with an empty depth image produces an empty featureFrame (feature_tracker.cpp:342)
+    const int depth_mode = t->cfg.depth_cam ? 1 : 0;
+    k_finalize<<<1, 1024, 0, s>>>(t->d_sc, t->fa, t->grid, t->w, t->cfg.max_cnt, t->cam, t->h_fp->dt, t->d_depth, t->depth_pitch_el,
+                                  depth_mode && depth_valid, t->h, t->d_hdr, t->d_obs); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaMemcpyAsync(t->h_hdr, t->d_hdr, sizeof(OutHeader), cudaMemcpyDeviceToHost, s));
+    GF_CUDA(cudaMemcpyAsync(t->h_obs, t->d_obs, (size_t)t->cfg.max_cnt * sizeof(gf_obs), cudaMemcpyDeviceToHost, s));
+    GF_CUDA(cudaEventRecord(t->ev_t1, s));
+    t->prev_time = time;
+    t->has_pred = false;
+    t->cur = prev;
+    t->pending = true;
+    t->depth_last = depth_valid;
+    return GF_OK;
+}
+
+int gf_tracker_submit(gf_tracker* t, double time, const uint8_t* gray, size_t gray_pitch, const uint16_t* depth, size_t depth_pitch)
+{
+    if (!t || !gray) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected: call gf_tracker_wait first");
+    GF_CUDA(cudaSetDevice(t->device));
+    const int w = t->w, h = t->h;
+    if (gray_pitch < (size_t)w) return set_err(GF_ERR_INVALID_ARG, "gray_pitch smaller than width");
+    if (gray != t->h_gray) {
+        if (gray_pitch == (size_t)w) memcpy(t->h_gray, gray, (size_t)w * h);
+        else for (int y = 0; y < h; y++) memcpy(t->h_gray + (size_t)y * w, gray + (size_t)y * gray_pitch, w);
+    }
+    if (depth && depth != t->h_depth) {
+        if (depth_pitch < (size_t)w * 2) return set_err(GF_ERR_INVALID_ARG, "depth_pitch smaller than width*2");
+        if (depth_pitch == (size_t)w * 2) memcpy(t->h_depth, depth, (size_t)w * h * 2);
+        else for (int y = 0; y < h; y++) memcpy(t->h_depth + (size_t)y * w, (const uint8_t*)depth + (size_t)y * depth_pitch, (size_t)w * 2);
+    }
+    cudaStream_t s = t->s_main;
+    GF_CUDA(cudaEventRecord(t->ev_t0, s));
+    GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[t->cur][0], t->lp[0], t->h_gray, w, w, h, cudaMemcpyHostToDevice, s));
+    if (depth)
+        GF_CUDA(cudaMemcpy2DAsync(t->d_depth, (size_t)t->depth_pitch_el * 2, t->h_depth, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, s));
+    return enqueue_frame(t, time, depth != nullptr);
+}
+
+int gf_tracker_wait(gf_tracker* t, gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info)
+{
+    if (!t) return set_err(GF_ERR_INVALID_ARG, "null tracker");
+    if (!t->pending) return set_err(GF_ERR_INVALID_ARG, "no frame in flight");
+    GF_CUDA(cudaSetDevice(t->device));
+    GF_CUDA(cudaStreamSynchronize(t->s_main));
+    t->pending = false;
+    GF_CUDA(cudaEventElapsedTime(&t->last_ms, t->ev_t0, t->ev_t1));
+    const OutHeader& hd = *t->h_hdr;
+    int n = hd.n_out;
+    if (t->cfg.depth_cam && !t->depth_last) n = 0;   // see enqueue_frame
+    if (n_out) *n_out = n;
+    if (out && n > 0) memcpy(out, t->h_obs, (size_t)n * sizeof(gf_obs));
+    if (status_out && hd.n_prev > 0) memcpy(status_out, t->h_status, hd.n_prev);
+    if (info) {
+        info->n_prev = hd.n_prev; info->n_tracked = hd.n_tracked; info->n_kept = hd.n_kept; info->n_new = hd.n_new;
+        info->n_candidates = hd.n_cand; info->nms_rounds = hd.nms_rounds; info->eig_fixups = hd.eig_fixups; info->reserved = 0;
+    }
+    return GF_OK;
+}
+
+int gf_tracker_track(gf_tracker* t, double time, const uint8_t* gray, size_t gray_pitch, const uint16_t* depth, size_t depth_pitch,
+                     gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info)
+{
+    int rc = gf_tracker_submit(t, time, gray, gray_pitch, depth, depth_pitch);
+    if (rc) return rc;
+    return gf_tracker_wait(t, out, n_out, status_out, info);
+}
+
+int gf_tracker_track_device(gf_tracker* t, double time, const void* d_gray, const void* d_depth, gf_obs* out, int* n_out,
+                            uint8_t* status_out, gf_track_info* info)
+{
+    if (!t || !d_gray) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected");
+    GF_CUDA(cudaSetDevice(t->device));
+    cudaStream_t s = t->s_main;
+    const int w = t->w, h = t->h;
+    GF_CUDA(cudaEventRecord(t->ev_t0, s));
+    GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[t->cur][0], t->lp[0], d_gray, w, w, h, cudaMemcpyDeviceToDevice, s));
+    if (d_depth)
+        GF_CUDA(cudaMemcpy2DAsync(t->d_depth, (size_t)t->depth_pitch_el * 2, d_depth, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToDevice, s));
+    int rc = enqueue_frame(t, time, d_depth != nullptr);
+    if (rc) return rc;
+    return gf_tracker_wait(t, out, n_out, status_out, info);
+}
+
+int gf_tracker_set_prediction(gf_tracker* t, const int32_t* ids, const double* xyz, int n)
+{
+    if (!t || (n > 0 && (!ids || !xyz))) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    if (n < 0 || n > FE_CAP) return set_err(GF_ERR_CAPACITY, "too many predictions");
+    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
+    GF_CUDA(cudaSetDevice(t->device));
+    cudaStream_t s = t->s_main;
+    if (n > 0) {
+        memcpy(t->h_tmp_ids, ids, (size_t)n * sizeof(int));
+        memcpy(t->h_tmp_xyz, xyz, (size_t)n * 3 * sizeof(double));
+        GF_CUDA(cudaMemcpyAsync(t->d_tmp_ids, t->h_tmp_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+        GF_CUDA(cudaMemcpyAsync(t->d_tmp_xyz, t->h_tmp_xyz, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    k_set_prediction<<<(FE_CAP + 255) / 256, 256, 0, s>>>(t->d_sc, t->fa, t->d_tmp_ids, t->d_tmp_xyz, n, t->cam); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaStreamSynchronize(s));
+    t->has_pred = true;
+    return GF_OK;
+}
+
+int gf_tracker_remove_ids(gf_tracker* t, const int32_t* ids, int n)
+{
+    if (!t || (n > 0 && !ids)) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    if (n < 0 || n > FE_CAP) return set_err(GF_ERR_CAPACITY, "too many ids");
+    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
+    if (n == 0) return GF_OK;
+    GF_CUDA(cudaSetDevice(t->device));
+    cudaStream_t s = t->s_main;
+    memcpy(t->h_tmp_ids, ids, (size_t)n * sizeof(int));
+    GF_CUDA(cudaMemcpyAsync(t->d_tmp_ids, t->h_tmp_ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+    k_remove_ids<<<1, FE_CAP, 0, s>>>(t->d_sc, t->fa, t->d_tmp_ids, n); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaStreamSynchronize(s));
+    return GF_OK;
+}
+
+int gf_tracker_last_device_ms(gf_tracker* t, float* ms)
+{
+    if (!t || !ms) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    *ms = t->last_ms;
+    return GF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-level entry points (tests)
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { GF_CUDA(cudaMalloc(&p, n ? n : 1)); return GF_OK; }
+    template <class T> T* as() { return (T*)p; }
+};
+
+static int upload_image(const uint8_t* src, int w, int h, DevBuf& d, int& pitch)
+{
+    pitch = align_up(w, 16);
+    int rc = d.alloc((size_t)pitch * h);
+    if (rc) return rc;
+    GF_CUDA(cudaMemcpy2D(d.p, pitch, src, w, w, h, cudaMemcpyHostToDevice));
+    return GF_OK;
+}
+
+extern "C" {
+
+int gf_stage_pyr_down(int device, const uint8_t* src, int w, int h, uint8_t* dst)
+{
+    if (!src || !dst || w < 3 || h < 3) return set_err(GF_ERR_INVALID_ARG, "bad argument");
+    int rc = select_device(device); if (rc) return rc;
+    DevBuf ds, dd; int sp;
+    rc = upload_image(src, w, h, ds, sp); if (rc) return rc;
+    int dw = (w + 1) / 2, dh = (h + 1) / 2, dp = align_up(dw, 16);
+    rc = dd.alloc((size_t)dp * dh); if (rc) return rc;
+    Level L{ds.as<uint8_t>(), w, h, sp};
+    dim3 g((dw + PD_TX - 1) / PD_TX, (dh + PD_TY - 1) / PD_TY), b(PD_TX, PD_TY);
+    k_pyr_down<<<g, b>>>(L, dd.as<uint8_t>(), dw, dh, dp); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaMemcpy2D(dst, dw, dd.p, dp, dw, dh, cudaMemcpyDeviceToHost));
+    return GF_OK;
+}
+
+int gf_stage_min_eig(int device, const uint8_t* img, int w, int h, float* eig, int* n_fixups)
+{
+    if (!img || !eig || w < 4 || h < 4) return set_err(GF_ERR_INVALID_ARG, "bad argument");
+    int rc = select_device(device); if (rc) return rc;
+    DevBuf di, de, s0, s1, fx; int ip;
+    rc = upload_image(img, w, h, di, ip); if (rc) return rc;
+    int ep = align_up(w, 4), nb = (h + EIG_BAND - 1) / EIG_BAND;
+    if ((rc = de.alloc((size_t)ep * h * 4)) || (rc = s0.alloc((size_t)nb * 3 * w * 8)) || (rc = s1.alloc((size_t)nb * 3 * w * 8)) || (rc = fx.alloc(4))) return rc;
+    GF_CUDA(cudaMemset(fx.p, 0, 4));
+    Level L{di.as<uint8_t>(), w, h, ip};
+    rc = enqueue_min_eig(0, L, de.as<float>(), ep, s0.as<double>(), s1.as<double>(), nb, fx.as<int>()); if (rc) return rc;
+    GF_CUDA(cudaMemcpy2D(eig, (size_t)w * 4, de.p, (size_t)ep * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
+    if (n_fixups) GF_CUDA(cudaMemcpy(n_fixups, fx.p, 4, cudaMemcpyDeviceToHost));
+    return GF_OK;
+}
+
+int gf_stage_lk(int device, const uint8_t* prev, const uint8_t* next, int w, int h, const float* prev_pts, float* next_pts, int n,
+                int max_level, int use_initial_flow, uint8_t* status)
+{
+    if (!prev || !next || !prev_pts || !next_pts || !status || n < 0 || max_level < 0 || max_level > 3) return set_err(GF_ERR_INVALID_ARG, "bad argument");
+    if ((w >> max_level) < 48 || (h >> max_level) < 48) return set_err(GF_ERR_UNSUPPORTED, "coarsest pyramid level must be at least 48x48");
+    int rc = select_device(device); if (rc) return rc;
+    if (n == 0) return GF_OK;
+    DevBuf lv[2][4], dp, dq, dst;
+    Pyramid P[2];
+    for (int k = 0; k < 2; k++) {
+        int lw = w, lh = h;
+        for (int l = 0; l <= max_level; l++) {
+            int pitch = align_up(lw, 16);
+            if (l == 0) { rc = upload_image(k ? next : prev, w, h, lv[k][0], pitch); if (rc) return rc; }
+            else {
+                rc = lv[k][l].alloc((size_t)pitch * lh); if (rc) return rc;
+                dim3 g((lw + PD_TX - 1) / PD_TX, (lh + PD_TY - 1) / PD_TY), b(PD_TX, PD_TY);
+                k_pyr_down<<<g, b>>>(P[k].lv[l - 1], lv[k][l].as<uint8_t>(), lw, lh, pitch); GF_LAUNCHED();
+            }
+            P[k].lv[l] = Level{lv[k][l].as<uint8_t>(), lw, lh, pitch};
+            lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+        }
+        for (int l = max_level + 1; l < 4; l++) P[k].lv[l] = P[k].lv[max_level];
+    }
+    if ((rc = dp.alloc((size_t)n * 8)) || (rc = dq.alloc((size_t)n * 8)) || (rc = dst.alloc(n))) return rc;
+    GF_CUDA(cudaMemcpy(dp.p, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice));
+    GF_CUDA(cudaMemcpy(dq.p, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice));
+    k_lk_stage<<<(n + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32>>>(P[0], P[1], dp.as<float2>(), dq.as<float2>(), n, max_level, use_initial_flow, dst.as<uint8_t>()); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaMemcpy(next_pts, dq.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    GF_CUDA(cudaMemcpy(status, dst.p, n, cudaMemcpyDeviceToHost));
+    return GF_OK;
+}
+
+int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kept_pts, int n_kept, int max_corners, int min_dist,
+                  float* corners, int* n_corners, gf_track_info* info)
+{
+    if (!img || !corners || !n_corners || max_corners < 0 || n_kept < 0 || n_kept + max_corners > FE_CAP || min_dist < 1 || min_dist > 255)
+        return set_err(GF_ERR_INVALID_ARG, "bad argument");
+    int rc = select_device(device); if (rc) return rc;
+    DevBuf di, de, dm, s0, s1, dsc, dk, dhdr, dobs, dummy[8]; int ip;
+    rc = upload_image(img, w, h, di, ip); if (rc) return rc;
+    int ep = align_up(w, 4), mp = align_up(w, 16), nb = (h + EIG_BAND - 1) / EIG_BAND;
+    if ((rc = de.alloc((size_t)ep * h * 4)) || (rc = dm.alloc((size_t)mp * h)) || (rc = s0.alloc((size_t)nb * 3 * w * 8)) ||
+        (rc = s1.alloc((size_t)nb * 3 * w * 8)) || (rc = dsc.alloc(sizeof(TrackScalars))) || (rc = dk.alloc((size_t)FE_CAP * 8)) ||
+        (rc = dhdr.alloc(sizeof(OutHeader))) || (rc = dobs.alloc(FE_CAP * sizeof(gf_obs))))
+        return rc;
+    for (int i = 0; i < 8; i++) if ((rc = dummy[i].alloc(FE_CAP * 8))) return rc;
+    TrackScalars hs; memset(&hs, 0, sizeof(hs));
+    hs.n_kept = n_kept;
+    GF_CUDA(cudaMemcpy(dsc.p, &hs, sizeof(hs), cudaMemcpyHostToDevice));
+    if (n_kept) GF_CUDA(cudaMemcpy(dk.p, kept_pts, (size_t)n_kept * 8, cudaMemcpyHostToDevice));
+    NmsGrid grid; size_t cells;
+    rc = alloc_nms_grid(grid, w, h, min_dist, &cells); if (rc) return rc;
+    Level L{di.as<uint8_t>(), w, h, ip};
+    TrackScalars* sc = dsc.as<TrackScalars>();
+    rc = enqueue_min_eig(0, L, de.as<float>(), ep, s0.as<double>(), s1.as<double>(), nb, &sc->eig_fixups);
+    if (!rc) rc = enqueue_gftt_select(0, sc, dk.as<float2>(), n_kept, de.as<float>(), ep, dm.as<uint8_t>(), mp, w, h, min_dist, grid, cells);
+    if (!rc) {
+        FeatArrays fa;
+        fa.prev_pts = dummy[0].as<float2>(); fa.ids = dummy[1].as<int>(); fa.track_cnt = dummy[2].as<int>(); fa.prev_un = dummy[3].as<float2>();
+        fa.cur_pts = nullptr; fa.status = nullptr; fa.pred_pts = nullptr;
+        fa.kept_pts = dk.as<float2>(); fa.kept_ids = dummy[4].as<int>(); fa.kept_cnt = dummy[5].as<int>(); fa.kept_un = dummy[6].as<float2>();
+        CamParams cam; memset(&cam, 0, sizeof(cam)); cam.fx = cam.fy = 1.0; cam.no_distortion = 1;
+        // max_cnt such that exactly max_corners new corners are requested
+        k_finalize<<<1, 1024>>>(sc, fa, grid, w, n_kept + max_corners, cam, 1.0, nullptr, 0, 0, h, dhdr.as<OutHeader>(), dobs.as<gf_obs>()); GF_LAUNCHED();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "k_finalize launch: %s", cudaGetErrorString(e)); rc = GF_ERR_CUDA; }
+    }
+    OutHeader hd; memset(&hd, 0, sizeof(hd));
+    std::vector<gf_obs> obs(FE_CAP);
+    if (!rc) {
+        cudaError_t e = cudaMemcpy(&hd, dhdr.p, sizeof(hd), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(obs.data(), dobs.p, FE_CAP * sizeof(gf_obs), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "gftt stage: %s", cudaGetErrorString(e)); rc = GF_ERR_CUDA; }
+    }
+    free_nms_grid(grid);
+    if (rc) return rc;
+    *n_corners = hd.n_new;
+    for (int i = 0; i < hd.n_new; i++) { corners[2 * i] = (float)obs[n_kept + i].v[3]; corners[2 * i + 1] = (float)obs[n_kept + i].v[4]; }
+    if (info) { memset(info, 0, sizeof(*info)); info->n_kept = hd.n_kept; info->n_new = hd.n_new; info->n_candidates = hd.n_cand; info->nms_rounds = hd.nms_rounds; info->eig_fixups = hd.eig_fixups; }
+    return GF_OK;
+}
+
+}  // extern "C"
+__global__ void k_sort_stage(sort_elem* e, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) setmask_sort(e, n); }
+extern "C" {
+
+int gf_stage_setmask_order(int device, const int32_t* track_cnt, int n, int32_t* perm)
+{
+    if (!track_cnt || !perm || n < 0 || n > FE_CAP) return set_err(GF_ERR_INVALID_ARG, "bad argument");
+    int rc = select_device(device); if (rc) return rc;
+    if (n == 0) return GF_OK;
+    std::vector<sort_elem> e(n);
+    for (int i = 0; i < n; i++) e[i] = ((sort_elem)(unsigned)track_cnt[i] << 32) | (unsigned)i;
+    DevBuf d; rc = d.alloc((size_t)n * 8); if (rc) return rc;
+    GF_CUDA(cudaMemcpy(d.p, e.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    k_sort_stage<<<1, 32>>>(d.as<sort_elem>(), n); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaMemcpy(e.data(), d.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) perm[i] = (int32_t)(e[i] & 0xffffffffu);
+    return GF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// gf_common.cuh -- shared helpers for libgf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/gf_b200.h"
+
+namespace gf {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline int set_err(int code, const char* fmt, const char* a = "", const char* b = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+#define GF_CUDA(call)                                                                              \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(gf::g_err, sizeof(gf::g_err), "%s failed: %s (%s:%d)", #call,                 \
+                     cudaGetErrorString(e_), __FILE__, __LINE__);                                  \
+            return GF_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define GF_LAUNCHED() (gf::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// BORDER_REFLECT_101; valid for -n < i < 2n-1
+__host__ __device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i;
+}
+
+__host__ __device__ __forceinline__ int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// One pyramid level in HBM: tightly described by (ptr, w, h, pitch in bytes)
+struct Level {
+    const uint8_t* ptr;
+    int w, h, pitch;
+};
+struct Pyramid {
+    Level lv[4];
+};
+
+}  // namespace gf

@@ -1,0 +1,91 @@
+"""CPU tests of the host-side logic and of the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ground_fusion_b200 import _lib
+    L = _lib.lib()
+    names = set()
+    for hdr in os.listdir(os.path.join(ROOT, "include")):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(gf_[a-z0-9_]+)\s*\(", src))
+    assert len(names) >= 15
+    for n in sorted(names):
+        assert hasattr(L, n), "libgf_b200.so does not export %s" % n
+    assert b"sm_100a" in L.gf_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device every entry point fails loudly (GF_ERR_NO_DEVICE), never computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from ground_fusion_b200 import feature_tracker
+    from ground_fusion_b200._lib import GfError
+    with pytest.raises(GfError, match="no CUDA device|CPU fallback"):
+        feature_tracker.FeatureTracker(640, 480, [600, 600, 320, 240, 0, 0, 0, 0])
+    with pytest.raises(GfError):
+        feature_tracker.pyr_down(np.zeros((480, 640), np.uint8))
+
+
+def test_product_does_not_import_oracle_or_cv2():
+    pkg = os.path.join(ROOT, "ground_fusion_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py") and fn != "synth.py":   # synth.py is data generation, not the hot path
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import cv2" not in src and "oracle" not in src.replace("the oracle", ""), fn
+    for fn in os.listdir(os.path.join(pkg, "csrc")):
+        src = open(os.path.join(pkg, "csrc", fn)).read()
+        assert "oracle/" not in src.replace("oracle/fe_cv_restate.c", "").replace("oracle/fe_oracle.py", ""), fn  # comments may cite the oracle files
+
+
+@pytest.fixture(scope="module")
+def host_sort(tmp_path_factory):
+    """Host build of the device std::sort replica (same header the CUDA kernel compiles)."""
+    d = tmp_path_factory.mktemp("hs")
+    src = d / "hs.cpp"
+    src.write_text('#include "%s/ground_fusion_b200/csrc/fe_sort.cuh"\n'
+                   'extern "C" void hs(const int* c, int n, int* perm) {\n'
+                   '  gf::sort_elem* e = new gf::sort_elem[n];\n'
+                   '  for (int i = 0; i < n; i++) e[i] = ((gf::sort_elem)(unsigned)c[i] << 32) | (unsigned)i;\n'
+                   '  gf::setmask_sort(e, n); for (int i = 0; i < n; i++) perm[i] = (int)(e[i] & 0xffffffffu); delete[] e; }\n' % ROOT)
+    so = d / "hs.so"
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", str(so), str(src)])
+    L = ctypes.CDLL(str(so))
+    L.hs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    return L
+
+
+def test_sort_replica_matches_libstdcxx(host_sort):
+    from oracle.fe_oracle import setmask_order
+    rng = np.random.default_rng(0)
+    for trial in range(3000):
+        n = int(rng.integers(1, 700))
+        span = int(rng.choice([2, 3, 8, 40, 1000]))
+        tc = rng.integers(1, span + 1, n).astype(np.int32)
+        if trial % 2:
+            tc = np.sort(tc)[::-1].copy()      # the tracker's input is already non-increasing
+        perm = np.empty(n, np.int32)
+        host_sort.hs(tc.ctypes.data, n, perm.ctypes.data)
+        assert np.array_equal(perm, setmask_order(tc)), (n, span)
+
+
+def test_setmask_sort_is_not_stable():
+    """The reason the replica exists: std::sort permutes equal keys once n > 16."""
+    from oracle.fe_oracle import setmask_order
+    tc = np.array([5] * 10 + [4] * 30 + [2] * 40, np.int32)
+    assert not np.array_equal(setmask_order(tc), np.arange(len(tc)))
+
+
+def test_obs_struct_layout():
+    from ground_fusion_b200._lib import OBS_DTYPE, Obs
+    assert ctypes.sizeof(Obs) == 72 and OBS_DTYPE.fields["v"][1] == 8
