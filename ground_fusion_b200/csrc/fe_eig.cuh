@@ -5,7 +5,7 @@
 //
 // Min-eig, one fused kernel (u8 image in, float map out; no Sobel/cov image in HBM):
 //   dx = fma(d0+d2, s, 2s*d1)                 d  = P[x+1]-P[x-1] per row           (float32)
-//   dy = r2 - r0,  r = fma(s,P[x+1], fma(2s,P[x], s*P[x-1]))
+//   dy = r2 - r0,  r = fma(s,P[x+1], fma(2s,P[x], s*P[x-1]))   (columns >= (w/32)*32: (s*P[x-1]+2s*P[x])+s*P[x+1])
 //   cov = (dx*dx, dx*dy, dy*dy)  float32
 //   box: row sums (S0+S1)+S2 in double; column sums are ONE RUNNING double sum per column and channel
 //        down the whole image in OpenCV (s0 = SUM + D[y+1]; out = (float)s0; SUM = s0 - D[y-1]).
@@ -59,16 +59,23 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) k_pyr_down(Level src, uint8_t* d
 constexpr int EIG_TX = 128;   // columns per CTA (= threads per CTA)
 constexpr int EIG_BAND = 16;  // rows per speculative band
 
+// tail: column >= (w/32)*32, where cv2's row filter runs its scalar (non-FMA) remainder loop
 __device__ __forceinline__ void sobel_dxdy(int p00, int p01, int p02, int p10, int p11, int p12, int p20,
-                                           int p21, int p22, float& dx, float& dy)
+                                           int p21, int p22, bool tail, float& dx, float& dy)
 {
     const float s = (float)(1.0 / (4.0 * 3.0 * 255.0));
     const float s2 = 2.f * s;
     (void)p11;
     int d0 = p02 - p00, d1 = p12 - p10, d2 = p22 - p20;
     dx = __fmaf_rn((float)(d0 + d2), s, s2 * (float)d1);
-    float r0 = __fmaf_rn(s, (float)p02, __fmaf_rn(s2, (float)p01, s * (float)p00));
-    float r2 = __fmaf_rn(s, (float)p22, __fmaf_rn(s2, (float)p21, s * (float)p20));
+    float r0, r2;
+    if (!tail) {
+        r0 = __fmaf_rn(s, (float)p02, __fmaf_rn(s2, (float)p01, s * (float)p00));
+        r2 = __fmaf_rn(s, (float)p22, __fmaf_rn(s2, (float)p21, s * (float)p20));
+    } else {
+        r0 = __fadd_rn(__fadd_rn(__fmul_rn(s, (float)p00), __fmul_rn(s2, (float)p01)), __fmul_rn(s, (float)p02));
+        r2 = __fadd_rn(__fadd_rn(__fmul_rn(s, (float)p20), __fmul_rn(s2, (float)p21)), __fmul_rn(s, (float)p22));
+    }
     dy = r2 - r0;
 }
 
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(EIG_TX) k_min_eig(Level img, float* eig, int e
             const uint8_t* p = &timg[r][c];  // timg row r <-> image row yy-1, col c <-> xx-1
             float dx, dy;
             sobel_dxdy(p[0], p[1], p[2], p[IW + 4], p[IW + 5], p[IW + 6], p[2 * (IW + 4)], p[2 * (IW + 4) + 1],
-                       p[2 * (IW + 4) + 2], dx, dy);
+                       p[2 * (IW + 4) + 2], xx >= (w / 32) * 32, dx, dy);
             tdx[r][c] = dx;
             tdy[r][c] = dy;
         }
@@ -179,7 +186,7 @@ __device__ inline void eig_rowsum_global(const Level& img, int r, int x, double&
 #pragma unroll
             for (int i = 0; i < 3; i++)
                 p[j][i] = __ldg(img.ptr + (size_t)reflect101(rr - 1 + j, h) * img.pitch + reflect101(cc - 1 + i, w));
-        sobel_dxdy(p[0][0], p[0][1], p[0][2], p[1][0], p[1][1], p[1][2], p[2][0], p[2][1], p[2][2], cx[k], cy[k]);
+        sobel_dxdy(p[0][0], p[0][1], p[0][2], p[1][0], p[1][1], p[1][2], p[2][0], p[2][1], p[2][2], cc >= (w / 32) * 32, cx[k], cy[k]);
     }
     d0 = ((double)(cx[0] * cx[0]) + (double)(cx[1] * cx[1])) + (double)(cx[2] * cx[2]);
     d1 = ((double)(cx[0] * cy[0]) + (double)(cx[1] * cy[1])) + (double)(cx[2] * cy[2]);

@@ -132,6 +132,117 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
 /* The permutation libstdc++'s std::sort produces for setMask's comparator (device replica). */
 int gf_stage_setmask_order(int device, const int32_t* track_cnt, int n, int32_t* perm);
 
+/* ------------------------------------------------------------------------------------------------
+ * Back end: Estimator::optimization() (estimator.cpp:2890-3636).  The caller (the Estimator adaptor)
+ * fills one gf_ba_problem per call from its members exactly where the reference builds the
+ * ceres::Problem (estimator.cpp:2895-3300); the library replaces ceres::Solve (DENSE_SCHUR + DOGLEG,
+ * estimator.cpp:3303-3318) and writes the optimised parameter blocks back in place.
+ * All doubles; quaternions are stored x,y,z,w as in para_Pose (estimator.cpp:2276-2353).
+ * ---------------------------------------------------------------------------------------------- */
+#define GF_BA_MAX_FRAMES 11          /* WINDOW_SIZE + 1 (parameters.h:24) */
+#define GF_BA_MAX_ITERATIONS 16
+
+/* ProjectionTwoFrameOneCamFactor (factor/projectionTwoFrameOneCamFactor.h:21, .cpp:43-151) */
+typedef struct gf_ba_visual_factor {
+    int32_t imu_i, imu_j;     /* para_Pose[imu_i], para_Pose[imu_j]                      */
+    int32_t feature;          /* para_Feature[feature]                                     */
+    int32_t reserved;
+    double pts_i[3], pts_j[3];
+    double vel_i[2], vel_j[2];
+    double td_i, td_j;
+} gf_ba_visual_factor;
+
+/* IMUFactor (factor/imu_factor.h:20-191) with the IntegrationBase members Evaluate reads
+ * (factor/integration_base.h:169-195): delta_{p,q,v}, jacobian, covariance, linearized biases. */
+typedef struct gf_ba_imu_factor {
+    int32_t i, j;             /* para_Pose[i], para_SpeedBias[i], para_Pose[j], para_SpeedBias[j] */
+    double sum_dt;
+    double delta_p[3], delta_q[4], delta_v[3];
+    double linearized_ba[3], linearized_bg[3];
+    double jacobian[225];     /* 15x15 row-major, order O_P O_R O_V O_BA O_BG               */
+    double covariance[225];
+} gf_ba_imu_factor;
+
+/* WheelFactor (factor/wheel_factor.h:20-247) with the WheelIntegrationBase members it reads. */
+typedef struct gf_ba_wheel_factor {
+    int32_t i, j;
+    double sum_dt;
+    double delta_p[3], delta_q[4];
+    double jacobian[18];      /* 6x3 row-major: d(p,q)/d(sx,sy,sw)                           */
+    double covariance[36];
+    double linearized_sx, linearized_sy, linearized_sw, linearized_td;
+    double linearized_vel[3], linearized_gyr[3], vel_1[3], gyr_1[3];
+} gf_ba_wheel_factor;
+
+typedef enum gf_ba_block_kind {
+    GF_BA_BLOCK_POSE = 0, GF_BA_BLOCK_SPEEDBIAS = 1, GF_BA_BLOCK_EX_POSE = 2, GF_BA_BLOCK_TD = 3,
+    GF_BA_BLOCK_EX_WHEEL = 4, GF_BA_BLOCK_SX = 5, GF_BA_BLOCK_SY = 6, GF_BA_BLOCK_SW = 7,
+    GF_BA_BLOCK_TD_WHEEL = 8, GF_BA_BLOCK_FEATURE = 9
+} gf_ba_block_kind;
+
+/* MarginalizationInfo as consumed by MarginalizationFactor::Evaluate
+ * (factor/marginalization_factor.cpp:332-392): r = r0 + J0 * dx(x, x0). */
+typedef struct gf_ba_prior {
+    int32_t n;                        /* rows = columns = kept local dimension (0: no prior)     */
+    int32_t n_blocks;                 /* keep_block_size.size()                                   */
+    int32_t block_kind[64];           /* gf_ba_block_kind of every kept block                     */
+    int32_t block_index[64];          /* frame index for POSE / SPEEDBIAS, 0 otherwise            */
+    int32_t block_idx[64];            /* keep_block_idx - m: first column of the block            */
+    const double* x0;                 /* keep_block_data, concatenated in block order (global sizes) */
+    const double* linearized_jacobians; /* n x n, row-major                                       */
+    const double* linearized_residuals; /* n                                                      */
+} gf_ba_prior;
+
+typedef struct gf_ba_problem {
+    int32_t n_frames;                 /* frame_count + 1, <= GF_BA_MAX_FRAMES                     */
+    int32_t n_features;               /* entries of para_feature                                  */
+    int32_t n_visual, n_imu, n_wheel;
+    int32_t max_num_iterations;       /* NUM_ITERATIONS (estimator.cpp:3308)                      */
+    /* parameter blocks, updated in place by gf_ba_solve */
+    double* para_pose;                /* [n_frames][7]                                            */
+    double* para_speed_bias;          /* [n_frames][9]                                            */
+    double* para_ex_pose;             /* [7]  para_Ex_Pose[0]                                     */
+    double* para_feature;             /* [n_features] inverse depths                              */
+    double* para_td;                  /* [1]                                                      */
+    double* para_ex_wheel;            /* [7]  para_Ex_Pose_wheel[0]  (read only if n_wheel > 0)   */
+    double* para_ix_wheel;            /* [3]  sx sy sw                                            */
+    double* para_td_wheel;            /* [1]                                                      */
+    /* SetParameterBlockConstant decisions (estimator.cpp:2960-3100, 3233-3246, 3291-3292) */
+    const uint8_t* feature_const;     /* [n_features] 1 = depth from the depth image, held fixed  */
+    int32_t frames_const;             /* systemstationary && stationary_detect                    */
+    int32_t pose0_const;              /* !USE_IMU                                                 */
+    int32_t ex_pose_const, td_const, ex_wheel_const, ix_wheel_const, td_wheel_const;
+    const gf_ba_visual_factor* visual;
+    const gf_ba_imu_factor* imu;
+    const gf_ba_wheel_factor* wheel;
+    const gf_ba_prior* prior;         /* nullable                                                 */
+    double gravity[3];                /* global G (parameters.cpp:74)                             */
+    double visual_sqrt_info;          /* FOCAL_LENGTH / 1.5 (estimator.cpp:193)                   */
+} gf_ba_problem;
+
+typedef enum gf_ba_termination {
+    GF_BA_NO_CONVERGENCE = 0,         /* max_num_iterations reached                               */
+    GF_BA_CONVERGENCE_FUNCTION = 1, GF_BA_CONVERGENCE_PARAMETER = 2, GF_BA_CONVERGENCE_GRADIENT = 3,
+    GF_BA_FAILURE = 4
+} gf_ba_termination;
+
+typedef struct gf_ba_summary {
+    int32_t iterations;               /* iterations run (successful or not), excluding iteration 0 */
+    int32_t num_successful_steps;
+    int32_t termination;              /* gf_ba_termination                                        */
+    int32_t reduced_dim, n_free_landmarks, n_residuals;
+    double initial_cost, final_cost;
+    double cost[GF_BA_MAX_ITERATIONS + 1];    /* cost after iteration k (k = 0: initial)          */
+    double radius[GF_BA_MAX_ITERATIONS + 1];  /* trust-region radius after iteration k            */
+    double device_ms;                 /* CUDA-event time of the solve (0 for the CPU oracle)      */
+} gf_ba_summary;
+
+typedef struct gf_ba gf_ba;           /* opaque solver workspace bound to one GPU */
+int gf_ba_create(gf_ba** out, int device);
+void gf_ba_destroy(gf_ba* s);
+/* ceres::Solve + double2vector's input: optimises the blocks of `p` in place. */
+int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* summary);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -309,8 +309,14 @@ GF_EXPORT void gfo_min_eig(const uint8_t* img, int w, int h, float* eig, int var
                  * RowFilter<uchar,float> is FMA-contracted in the AVX2 dispatch; column [-1 0 1] is a
                  * plain subtraction.  Pinned against cv2.Sobel / cv2.cornerMinEigenVal 4.13.0. */
                 dx = fmaf((float)(d0 + d2), s, s2 * (float)d1);
-                float rr0 = fmaf(s, (float)r0[xp], fmaf(s2, (float)r0[x], s * (float)r0[xm]));
-                float rr2 = fmaf(s, (float)r2[xp], fmaf(s2, (float)r2[x], s * (float)r2[xm]));
+                float rr0, rr2;
+                if (x < (w / 32) * 32) {   /* vectorised body of the row filter (32-column groups): FMA chain */
+                    rr0 = fmaf(s, (float)r0[xp], fmaf(s2, (float)r0[x], s * (float)r0[xm]));
+                    rr2 = fmaf(s, (float)r2[xp], fmaf(s2, (float)r2[x], s * (float)r2[xm]));
+                } else {                   /* scalar tail of the row filter: separately rounded */
+                    rr0 = (s * (float)r0[xm] + s2 * (float)r0[x]) + s * (float)r0[xp];
+                    rr2 = (s * (float)r2[xm] + s2 * (float)r2[x]) + s * (float)r2[xp];
+                }
                 dy = rr2 - rr0;
             } else {
                 dx = (float)(d0 + 2 * d1 + d2) * s;
