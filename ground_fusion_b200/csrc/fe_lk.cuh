@@ -45,7 +45,7 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 
 // One pyramid level for one point (all 32 lanes call this with identical scalar arguments).
 __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, const Level& J, float px,
-                                         float py, float& nx, float& ny, int level, int& status)
+                                         float py, float& nx, float& ny, int level, int& status, int& iters)
 {
     const float FLT_SCALE = 1.f / (1 << 20);
     float ppx = px - 10.f, ppy = py - 10.f;
@@ -212,6 +212,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
             bb[comp] = t + ((x02 + 0.f) + (x13 + 0.f));
         }
         __syncwarp();
+        iters++;
         float b1 = bb[0] * FLT_SCALE, b2 = bb[1] * FLT_SCALE;
         float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
         qx += dx;
@@ -237,7 +238,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
 // Whole pyramid for one point.  init is only read when use_init.
 __device__ __forceinline__ void lk_track_point(LKSmem& S, int lane, const Pyramid& I, const Pyramid& J,
                                                float2 p, float2 init, bool use_init, int max_level,
-                                               float2& out, int& status)
+                                               float2& out, int& status, int& iters)
 {
     status = 1;
     float nx = 0.f, ny = 0.f;
@@ -248,7 +249,7 @@ __device__ __forceinline__ void lk_track_point(LKSmem& S, int lane, const Pyrami
             if (use_init) { nx = init.x * sc; ny = init.y * sc; }
             else { nx = px; ny = py; }
         } else { nx = nx * 2.f; ny = ny * 2.f; }
-        lk_level(S, lane, I.lv[l], J.lv[l], px, py, nx, ny, l, status);
+        lk_level(S, lane, I.lv[l], J.lv[l], px, py, nx, ny, l, status, iters);
     }
     out = make_float2(nx, ny);
 }

@@ -22,9 +22,9 @@ namespace gf {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 
-constexpr int NMS_ROUNDS = 6;   // multi-CTA rounds launched unconditionally; k_nms_finish mops up
 
 struct FrameParams { double dt; int has_pred; int depth_valid; };
+constexpr int NMS_CELL_BYTES = 16;   // head key + two accepted buffers per cell (nms_cells)
 
 // ------------------------------------------------------------------------------------------------
 // kernels that need the LK device code
@@ -37,8 +37,8 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_stage(Pyramid I, Pyramid J
     int i = blockIdx.x * LK_WARPS + wid;
     if (i >= n) return;
     float2 p = prev_pts[i], init = use_init ? next_pts[i] : p, out;
-    int st;
-    lk_track_point(sm[wid], lane, I, J, p, init, use_init != 0, max_level, out, st);
+    int st, iters = 0;
+    lk_track_point(sm[wid], lane, I, J, p, init, use_init != 0, max_level, out, st, iters);
     if (lane == 0) { next_pts[i] = out; status[i] = (uint8_t)st; }
 }
 
@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_lk_pred(Pyramid prev, Pyramid
     int i = blockIdx.x * LK_WARPS + wid;
     if (i >= sc->n_prev) return;
     float2 out;
-    int st;
-    lk_track_point(sm[wid], lane, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st);
-    if (lane == 0) { fa.cur_pts[i] = out; fa.status[i] = (uint8_t)st; if (st) atomicAdd(&sc->pred_succ, 1); }
+    int st, iters = 0;
+    lk_track_point(sm[wid], lane, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st, iters);
+    if (lane == 0) { fa.cur_pts[i] = out; fa.status[i] = (uint8_t)st; if (st) atomicAdd(&sc->pred_succ, 1); atomicAdd(&sc->lk_iters, iters); }
 }
 
 // Forward LK (3 levels) + reverse check (1 level, USE_INITIAL_FLOW) + inBorder + grey<=250
@@ -66,13 +66,13 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_track(Pyramid prev, Pyramid c
     if (i >= sc->n_prev) return;
     const float2 p = fa.prev_pts[i];
     float2 q;
-    int st;
+    int st, iters = 0;
     if (fp->has_pred && sc->pred_succ >= 10) { q = fa.cur_pts[i]; st = fa.status[i]; }
-    else lk_track_point(sm[wid], lane, prev, cur, p, p, false, 3, q, st);
+    else lk_track_point(sm[wid], lane, prev, cur, p, p, false, 3, q, st, iters);
     if (flow_back) {
         float2 r;
         int rst;
-        lk_track_point(sm[wid], lane, cur, prev, q, p, true, 1, r, rst);
+        lk_track_point(sm[wid], lane, cur, prev, q, p, true, 1, r, rst, iters);
         double dx = (double)(p.x - r.x), dy = (double)(p.y - r.y);
         st = (st && rst && sqrt(dx * dx + dy * dy) <= 0.5) ? 1 : 0;
     }
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_track(Pyramid prev, Pyramid c
         int grey = (p_u >= 0 && p_u < row && p_v >= 0 && p_v < col) ? cur.lv[0].ptr[(size_t)p_u * cur.lv[0].pitch + p_v] : 0;
         if (grey > 250) st = 0;
     }
-    if (lane == 0) { fa.cur_pts[i] = q; fa.status[i] = (uint8_t)st; }
+    if (lane == 0) { fa.cur_pts[i] = q; fa.status[i] = (uint8_t)st; atomicAdd(&sc->lk_iters, iters); }
 }
 
 // setPrediction (feature_tracker.cpp:1006-1027)
@@ -156,6 +156,9 @@ struct gf_tracker {
     CamParams cam;
     cudaStream_t s_main, s_aux;
     cudaEvent_t ev_fork, ev_eig, ev_t0, ev_t1;
+    cudaEvent_t ev_st[GF_FE_STAGES + 2];   // stage boundaries on s_main (0..6) + aux start/end (7,8)
+    bool profiling;
+    float stage_ms[GF_FE_STAGES];
     uint8_t* d_pyr[2][4];
     int lw[4], lh[4], lp[4];
     uint16_t* d_depth; int depth_pitch_el;
@@ -205,23 +208,24 @@ static int select_device(int device)
     return GF_OK;
 }
 
-static int alloc_nms_grid(NmsGrid& g, int w, int h, int min_dist, size_t* cells_out)
+static int alloc_nms_grid(NmsGrid& g, int w, int h, int min_dist, size_t* smem_bytes)
 {
-    g.cs = min_dist;
+    g.cs = min_dist > 16 ? min_dist : 16;
     g.gw = (w + g.cs - 1) / g.cs;
     g.gh = (h + g.cs - 1) / g.cs;
-    g.cap = g.cs * g.cs;
-    size_t cells = (size_t)g.gw * g.gh;
-    GF_CUDA(cudaMalloc(&g.cell_cnt, cells * sizeof(int)));
-    GF_CUDA(cudaMalloc(&g.key, cells * g.cap * sizeof(unsigned long long)));
-    GF_CUDA(cudaMalloc(&g.state, cells * g.cap));
-    GF_CUDA(cudaMalloc(&g.cand_ref, (size_t)w * h * sizeof(int)));
-    if (cells_out) *cells_out = cells;
+    g.acc_cap = w * h / 16 + 64;
+    GF_CUDA(cudaMalloc(&g.cand_key, (size_t)w * h * sizeof(unsigned long long)));
+    GF_CUDA(cudaMalloc(&g.acc_key, (size_t)g.acc_cap * sizeof(unsigned long long)));
+    size_t bytes = (size_t)g.gw * g.gh * NMS_CELL_BYTES;
+    if (bytes > 160 * 1024) return set_err(GF_ERR_UNSUPPORTED, "image too large for the min-distance cell grid");
+    GF_CUDA(cudaMalloc(&g.dead, (size_t)w * h));
+    GF_CUDA(cudaFuncSetAttribute(k_select_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    if (smem_bytes) *smem_bytes = bytes;
     return GF_OK;
 }
 static void free_nms_grid(NmsGrid& g)
 {
-    cudaFree(g.cell_cnt); cudaFree(g.key); cudaFree(g.state); cudaFree(g.cand_ref);
+    cudaFree(g.cand_key); cudaFree(g.acc_key); cudaFree(g.dead);
 }
 
 // GFTT tail shared by the tracker and gf_stage_gftt: mask -> max -> candidates -> NMS rounds
@@ -229,13 +233,10 @@ static int enqueue_gftt_select(cudaStream_t s, TrackScalars* d_sc, const float2*
                                int epitch, uint8_t* d_mask, int mpitch, int w, int h, int min_dist, NmsGrid& grid, size_t cells)
 {
     GF_CUDA(cudaMemsetAsync(d_mask, 255, (size_t)mpitch * h, s));
-    GF_CUDA(cudaMemsetAsync(grid.cell_cnt, 0, cells * sizeof(int), s));
     if (max_kept > 0) { k_mask_disks<<<max_kept, 256, 0, s>>>(d_sc, kept_pts, d_mask, w, h, mpitch, min_dist); GF_LAUNCHED(); }
     k_eig_max<<<296, 256, 0, s>>>(d_sc, d_eig, epitch, d_mask, mpitch, w, h); GF_LAUNCHED();
     dim3 cg((w + 31) / 32, (h + 7) / 8);
     k_candidates<<<cg, 256, 0, s>>>(d_sc, d_eig, epitch, d_mask, mpitch, w, h, grid); GF_LAUNCHED();
-    for (int r = 0; r < NMS_ROUNDS; r++) { k_nms_round<<<296, 256, 0, s>>>(d_sc, grid, w, min_dist, r); GF_LAUNCHED(); }
-    k_nms_finish<<<1, 1024, 0, s>>>(d_sc, grid, w, min_dist, NMS_ROUNDS - 1); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     return GF_OK;
 }
@@ -272,7 +273,7 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     if (!out || !cfg) return set_err(GF_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
     if (cfg->max_cnt < 1 || cfg->max_cnt > FE_CAP) return set_err(GF_ERR_CAPACITY, "max_cnt must be in [1, 1024]");
-    if (cfg->min_dist < 1 || cfg->min_dist > 255) return set_err(GF_ERR_INVALID_ARG, "min_dist must be in [1, 255]");
+    if (cfg->min_dist < 5 || cfg->min_dist > 255) return set_err(GF_ERR_INVALID_ARG, "min_dist must be in [5, 255]");
     // the 4-level pyramid needs every level larger than the 21x21 window plus the cached-region reach
     if (((width + 7) / 8) < 48 || ((height + 7) / 8) < 48 || width > 8192 || height > 8192)
         return set_err(GF_ERR_UNSUPPORTED, "image must be at least 377x377 and at most 8192x8192");
@@ -288,6 +289,7 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     GF_CUDA(cudaEventCreateWithFlags(&t->ev_eig, cudaEventDisableTiming));
     GF_CUDA(cudaEventCreate(&t->ev_t0));
     GF_CUDA(cudaEventCreate(&t->ev_t1));
+    for (int i = 0; i < GF_FE_STAGES + 2; i++) GF_CUDA(cudaEventCreate(&t->ev_st[i]));
     int lw = width, lh = height;
     for (int l = 0; l < 4; l++) {
         t->lw[l] = lw; t->lh[l] = lh; t->lp[l] = align_up(lw, 16);
@@ -352,6 +354,7 @@ void gf_tracker_destroy(gf_tracker* t)
     cudaFreeHost(t->h_gray); cudaFreeHost(t->h_depth); cudaFreeHost(t->h_hdr); cudaFreeHost(t->h_obs); cudaFreeHost(t->h_status);
     cudaFreeHost(t->h_fp); cudaFreeHost(t->h_tmp_ids); cudaFreeHost(t->h_tmp_xyz);
     cudaStreamDestroy(t->s_main); cudaStreamDestroy(t->s_aux);
+    for (int i = 0; i < GF_FE_STAGES + 2; i++) cudaEventDestroy(t->ev_st[i]);
     cudaEventDestroy(t->ev_fork); cudaEventDestroy(t->ev_eig); cudaEventDestroy(t->ev_t0); cudaEventDestroy(t->ev_t1);
     delete t;
 }
@@ -375,28 +378,37 @@ static int enqueue_frame(gf_tracker* t, double time, bool depth_valid)
     GF_CUDA(cudaMemcpyAsync(t->d_fp, t->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
     Pyramid Pc = make_pyr(t, cur), Pp = make_pyr(t, prev);
     // fork: min-eig of the new frame does not depend on tracking
+#define GF_MARK(k) do { if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[k], s)); } while (0)
+    GF_MARK(0);   // end of upload
     GF_CUDA(cudaEventRecord(t->ev_fork, s));
     GF_CUDA(cudaStreamWaitEvent(t->s_aux, t->ev_fork, 0));
+    if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[7], t->s_aux));
     int rc = enqueue_min_eig(t->s_aux, Pc.lv[0], t->d_eig, t->epitch, t->d_spec_start, t->d_spec_end, t->nbands, &t->d_sc->eig_fixups);
     if (rc) return rc;
     GF_CUDA(cudaEventRecord(t->ev_eig, t->s_aux));
+    if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[8], t->s_aux));
     rc = enqueue_pyramid(s, t, cur);
     if (rc) return rc;
+    GF_MARK(1);
     const int lk_grid = (t->cfg.max_cnt + LK_WARPS - 1) / LK_WARPS;
     if (t->has_pred) { k_lk_pred<<<lk_grid, LK_WARPS * 32, 0, s>>>(Pp, Pc, t->d_sc, t->fa); GF_LAUNCHED(); }
     k_track<<<lk_grid, LK_WARPS * 32, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp, t->cfg.flow_back); GF_LAUNCHED();
+    GF_MARK(2);
     k_compact_setmask<<<1, FE_CAP, 0, s>>>(t->d_sc, t->fa, t->cfg.min_dist); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
+    GF_MARK(3);
     GF_CUDA(cudaMemcpyAsync(t->h_status, t->fa.status, t->cfg.max_cnt, cudaMemcpyDeviceToHost, s));
     GF_CUDA(cudaStreamWaitEvent(s, t->ev_eig, 0));
     rc = enqueue_gftt_select(s, t->d_sc, t->fa.kept_pts, t->cfg.max_cnt, t->d_eig, t->epitch, t->d_mask, t->mpitch, t->w, t->h,
                              t->cfg.min_dist, t->grid, t->grid_cells);
     if (rc) return rc;
+    GF_MARK(4);
     // reference quirk: depth_cam with an empty depth image produces an empty featureFrame (feature_tracker.cpp:342)
     const int depth_mode = t->cfg.depth_cam ? 1 : 0;
-    k_finalize<<<1, 1024, 0, s>>>(t->d_sc, t->fa, t->grid, t->w, t->cfg.max_cnt, t->cam, t->h_fp->dt, t->d_depth, t->depth_pitch_el,
-                                  depth_mode && depth_valid, t->h, t->d_hdr, t->d_obs); GF_LAUNCHED();
+    k_select_finalize<<<1, 1024, t->grid_cells, s>>>(t->d_sc, t->fa, t->grid, t->w, t->cfg.max_cnt, t->cfg.min_dist, t->cam, &t->d_fp->dt,
+                                                     t->d_depth, t->depth_pitch_el, depth_mode && depth_valid, t->h, t->d_hdr, t->d_obs); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
+    GF_MARK(5);
     GF_CUDA(cudaMemcpyAsync(t->h_hdr, t->d_hdr, sizeof(OutHeader), cudaMemcpyDeviceToHost, s));
     GF_CUDA(cudaMemcpyAsync(t->h_obs, t->d_obs, (size_t)t->cfg.max_cnt * sizeof(gf_obs), cudaMemcpyDeviceToHost, s));
     GF_CUDA(cudaEventRecord(t->ev_t1, s));
@@ -415,20 +427,15 @@ int gf_tracker_submit(gf_tracker* t, double time, const uint8_t* gray, size_t gr
     GF_CUDA(cudaSetDevice(t->device));
     const int w = t->w, h = t->h;
     if (gray_pitch < (size_t)w) return set_err(GF_ERR_INVALID_ARG, "gray_pitch smaller than width");
-    if (gray != t->h_gray) {
-        if (gray_pitch == (size_t)w) memcpy(t->h_gray, gray, (size_t)w * h);
-        else for (int y = 0; y < h; y++) memcpy(t->h_gray + (size_t)y * w, gray + (size_t)y * gray_pitch, w);
-    }
-    if (depth && depth != t->h_depth) {
-        if (depth_pitch < (size_t)w * 2) return set_err(GF_ERR_INVALID_ARG, "depth_pitch smaller than width*2");
-        if (depth_pitch == (size_t)w * 2) memcpy(t->h_depth, depth, (size_t)w * h * 2);
-        else for (int y = 0; y < h; y++) memcpy(t->h_depth + (size_t)y * w, (const uint8_t*)depth + (size_t)y * depth_pitch, (size_t)w * 2);
-    }
+    if (depth && depth_pitch < (size_t)w * 2) return set_err(GF_ERR_INVALID_ARG, "depth_pitch smaller than width*2");
+    // The caller's buffers are read by the copy engine directly: truly asynchronous when they are pinned
+    // (gf_tracker_host_buffers or any cudaHostAlloc/cudaHostRegister memory); for pageable memory CUDA stages
+    // the data before cudaMemcpy2DAsync returns, so the "only read during the call" contract holds either way.
     cudaStream_t s = t->s_main;
     GF_CUDA(cudaEventRecord(t->ev_t0, s));
-    GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[t->cur][0], t->lp[0], t->h_gray, w, w, h, cudaMemcpyHostToDevice, s));
+    GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[t->cur][0], t->lp[0], gray, gray_pitch, w, h, cudaMemcpyHostToDevice, s));
     if (depth)
-        GF_CUDA(cudaMemcpy2DAsync(t->d_depth, (size_t)t->depth_pitch_el * 2, t->h_depth, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyHostToDevice, s));
+        GF_CUDA(cudaMemcpy2DAsync(t->d_depth, (size_t)t->depth_pitch_el * 2, depth, depth_pitch, (size_t)w * 2, h, cudaMemcpyHostToDevice, s));
     return enqueue_frame(t, time, depth != nullptr);
 }
 
@@ -440,6 +447,11 @@ int gf_tracker_wait(gf_tracker* t, gf_obs* out, int* n_out, uint8_t* status_out,
     GF_CUDA(cudaStreamSynchronize(t->s_main));
     t->pending = false;
     GF_CUDA(cudaEventElapsedTime(&t->last_ms, t->ev_t0, t->ev_t1));
+    if (t->profiling) {
+        cudaEvent_t b[8] = {t->ev_t0, t->ev_st[0], t->ev_st[1], t->ev_st[2], t->ev_st[3], t->ev_st[4], t->ev_st[5], t->ev_t1};
+        for (int i = 0; i < 7; i++) GF_CUDA(cudaEventElapsedTime(&t->stage_ms[i], b[i], b[i + 1]));
+        GF_CUDA(cudaEventElapsedTime(&t->stage_ms[7], t->ev_st[7], t->ev_st[8]));
+    }
     const OutHeader& hd = *t->h_hdr;
     int n = hd.n_out;
     if (t->cfg.depth_cam && !t->depth_last) n = 0;   // see enqueue_frame
@@ -448,7 +460,7 @@ int gf_tracker_wait(gf_tracker* t, gf_obs* out, int* n_out, uint8_t* status_out,
     if (status_out && hd.n_prev > 0) memcpy(status_out, t->h_status, hd.n_prev);
     if (info) {
         info->n_prev = hd.n_prev; info->n_tracked = hd.n_tracked; info->n_kept = hd.n_kept; info->n_new = hd.n_new;
-        info->n_candidates = hd.n_cand; info->nms_rounds = hd.nms_rounds; info->eig_fixups = hd.eig_fixups; info->reserved = 0;
+        info->n_candidates = hd.n_cand; info->nms_rounds = hd.nms_rounds; info->eig_fixups = hd.eig_fixups; info->lk_iterations = hd.lk_iters;
     }
     return GF_OK;
 }
@@ -511,6 +523,21 @@ int gf_tracker_remove_ids(gf_tracker* t, const int32_t* ids, int n)
     k_remove_ids<<<1, FE_CAP, 0, s>>>(t->d_sc, t->fa, t->d_tmp_ids, n); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaStreamSynchronize(s));
+    return GF_OK;
+}
+
+int gf_tracker_set_profiling(gf_tracker* t, int enable)
+{
+    if (!t) return set_err(GF_ERR_INVALID_ARG, "null tracker");
+    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
+    t->profiling = enable != 0;
+    return GF_OK;
+}
+
+int gf_tracker_last_stage_ms(gf_tracker* t, float* ms)
+{
+    if (!t || !ms) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    memcpy(ms, t->stage_ms, sizeof(t->stage_ms));
     return GF_OK;
 }
 
@@ -613,7 +640,7 @@ int gf_stage_lk(int device, const uint8_t* prev, const uint8_t* next, int w, int
 int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kept_pts, int n_kept, int max_corners, int min_dist,
                   float* corners, int* n_corners, gf_track_info* info)
 {
-    if (!img || !corners || !n_corners || max_corners < 0 || n_kept < 0 || n_kept + max_corners > FE_CAP || min_dist < 1 || min_dist > 255)
+    if (!img || !corners || !n_corners || max_corners < 0 || n_kept < 0 || n_kept + max_corners > FE_CAP || min_dist < 5 || min_dist > 255)
         return set_err(GF_ERR_INVALID_ARG, "bad argument");
     int rc = select_device(device); if (rc) return rc;
     DevBuf di, de, dm, s0, s1, dsc, dk, dhdr, dobs, dummy[8]; int ip;
@@ -641,9 +668,9 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
         fa.kept_pts = dk.as<float2>(); fa.kept_ids = dummy[4].as<int>(); fa.kept_cnt = dummy[5].as<int>(); fa.kept_un = dummy[6].as<float2>();
         CamParams cam; memset(&cam, 0, sizeof(cam)); cam.fx = cam.fy = 1.0; cam.no_distortion = 1;
         // max_cnt such that exactly max_corners new corners are requested
-        k_finalize<<<1, 1024>>>(sc, fa, grid, w, n_kept + max_corners, cam, 1.0, nullptr, 0, 0, h, dhdr.as<OutHeader>(), dobs.as<gf_obs>()); GF_LAUNCHED();
+        k_select_finalize<<<1, 1024, cells>>>(sc, fa, grid, w, n_kept + max_corners, min_dist, cam, nullptr, nullptr, 0, 0, h, dhdr.as<OutHeader>(), dobs.as<gf_obs>()); GF_LAUNCHED();
         cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "k_finalize launch: %s", cudaGetErrorString(e)); rc = GF_ERR_CUDA; }
+        if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "k_select_finalize launch: %s", cudaGetErrorString(e)); rc = GF_ERR_CUDA; }
     }
     OutHeader hd; memset(&hd, 0, sizeof(hd));
     std::vector<gf_obs> obs(FE_CAP);

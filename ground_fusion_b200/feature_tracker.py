@@ -148,6 +148,16 @@ class FeatureTracker:
         ids = np.array(sorted(removePtsIds), np.int32)
         check(self.L.gf_tracker_remove_ids(self._h, ids.ctypes.data if len(ids) else None, len(ids)))
 
+    def set_profiling(self, on=True):
+        check(self.L.gf_tracker_set_profiling(self._h, int(bool(on))))
+
+    STAGES = ("upload", "pyramid", "lk", "setmask", "gftt_select", "finalize", "download", "min_eig_aux")
+
+    def last_stage_ms(self):
+        ms = (ctypes.c_float * 8)()
+        check(self.L.gf_tracker_last_stage_ms(self._h, ms))
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
+
     def last_device_ms(self):
         ms = ctypes.c_float(0)
         check(self.L.gf_tracker_last_device_ms(self._h, ctypes.byref(ms)))

@@ -68,7 +68,7 @@ typedef struct gf_track_info {
     int32_t n_candidates; /* GFTT local-maximum candidates before the min-distance pass      */
     int32_t nms_rounds; /* parallel min-distance rounds used                                 */
     int32_t eig_fixups; /* column bands re-run by the box-filter verifier                    */
-    int32_t reserved;
+    int32_t lk_iterations; /* total LK Newton iterations of this frame (all points, levels, both passes) */
 } gf_track_info;
 
 /* FeatureTracker::FeatureTracker + readIntrinsicParameter (feature_tracker.cpp:48-54, 745-759). */
@@ -110,6 +110,12 @@ int gf_tracker_remove_ids(gf_tracker* t, const int32_t* ids, int n);
 
 /* Device time (ms, CUDA events on the tracker's stream) of the last completed frame. */
 int gf_tracker_last_device_ms(gf_tracker* t, float* ms);
+/* Optional per-stage CUDA-event timing (adds event records, no synchronisation).  Stage order:
+ * 0 upload, 1 pyramid, 2 lk (k_track), 3 setmask, 4 gftt select (mask..nms), 5 finalize, 6 download,
+ * 7 min-eig (aux stream, overlaps 1-3). */
+#define GF_FE_STAGES 8
+int gf_tracker_set_profiling(gf_tracker* t, int enable);
+int gf_tracker_last_stage_ms(gf_tracker* t, float* ms /* GF_FE_STAGES */);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage-level entry points (same kernels as the tracker; used by the parity tests, which read like

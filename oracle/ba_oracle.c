@@ -629,6 +629,11 @@ static int schur_solve(const layout_t* L, const double* H, const double* g, cons
     return 0;
 }
 
+/* Test aid: override Ceres' default tolerances (function 1e-6, gradient 1e-10, parameter 1e-8) to drive the
+ * same loop to the exact optimum when it is compared with an independent solver. */
+static double g_func_tol = 1e-6, g_grad_tol = 1e-10, g_param_tol = 1e-8;
+GFO void gfo_ba_set_tolerances(double f, double g, double x) { g_func_tol = f; g_grad_tol = g; g_param_tol = x; }
+
 GFO int gfo_ba_solve(const gf_ba_problem* p, gf_ba_summary* sum)
 {
     layout_t L; make_layout(p, &L);
@@ -646,7 +651,7 @@ GFO int gfo_ba_solve(const gf_ba_problem* p, gf_ba_summary* sum)
     double *gs = (double*)calloc(n + 1, 8), *gn = (double*)calloc(n + 1, 8), *step = (double*)calloc(n + 1, 8), *delta = (double*)calloc(n + 1, 8), *tv = (double*)calloc(n + 1, 8);
     /* Ceres defaults (solver.h) + the reference's options (estimator.cpp:3305-3315; the wall-clock cap is disabled) */
     double radius = 1e4, mu = 1e-8; const double min_mu = 1e-8, max_mu = 1.0, mu_inc = 10.0;
-    const double min_diag = 1e-6, max_diag = 1e32, func_tol = 1e-6, grad_tol = 1e-10, param_tol = 1e-8, min_rel_dec = 1e-3;
+    const double min_diag = 1e-6, max_diag = 1e32, func_tol = g_func_tol, grad_tol = g_grad_tol, param_tol = g_param_tol, min_rel_dec = 1e-3;
     int reuse = 0, termination = GF_BA_NO_CONVERGENCE, n_success = 0, invalid_streak = 0;
     double alpha = 0, dogleg_norm = 0, x_norm, grad_max;
     double x_cost;

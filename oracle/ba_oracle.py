@@ -1,0 +1,87 @@
+"""ctypes wrapper of oracle/ba_oracle.c -- TEST INFRASTRUCTURE ONLY (CPU oracle of the back end)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+from ground_fusion_b200._lib import BaImuFactor, BaPrior, BaProblem, BaSummary, BaVisualFactor
+from ground_fusion_b200.ba_problem import Prior
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libgf_oracle_ba.so")
+_LIB = None
+_dp = ctypes.POINTER(ctypes.c_double)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        src = os.path.join(_HERE, "ba_oracle.c")
+        hdr = os.path.join(_HERE, "..", "include", "gf_b200.h")
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            os.makedirs(os.path.dirname(_SO), exist_ok=True)
+            subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", _SO, src, "-lm"])
+        L = ctypes.CDLL(_SO)
+        L.gfo_ba_solve.argtypes = [ctypes.POINTER(BaProblem), ctypes.POINTER(BaSummary)]
+        L.gfo_ba_cost.argtypes = [ctypes.POINTER(BaProblem)]
+        L.gfo_ba_cost.restype = ctypes.c_double
+        L.gfo_ba_linearize.argtypes = [ctypes.POINTER(BaProblem), _dp, _dp, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]
+        L.gfo_ba_plus.argtypes = [ctypes.POINTER(BaProblem), _dp]
+        L.gfo_ba_plus.restype = None
+        L.gfo_ba_marginalize_old.argtypes = [ctypes.POINTER(BaProblem), ctypes.POINTER(BaPrior), _dp, _dp, _dp]
+        L.gfo_ba_set_tolerances.argtypes = [ctypes.c_double] * 3
+        L.gfo_ba_set_tolerances.restype = None
+        L.gfo_sqrt_info.argtypes = [_dp, ctypes.c_int, _dp]
+        _LIB = L
+    return _LIB
+
+
+def solve(pb):
+    """ceres::Solve restatement; updates pb's para_* arrays in place, returns the summary dict."""
+    s = BaSummary()
+    p = pb.struct()
+    rc = lib().gfo_ba_solve(ctypes.byref(p), ctypes.byref(s))
+    if rc:
+        raise RuntimeError("oracle solve failed: %d" % rc)
+    return s.as_dict()
+
+
+def cost(pb):
+    p = pb.struct()
+    return lib().gfo_ba_cost(ctypes.byref(p))
+
+
+def linearize(pb, cap_rows=6000, cap_cols=600):
+    p = pb.struct()
+    r = np.zeros(cap_rows); J = np.zeros((cap_rows * cap_cols,))
+    nc = ctypes.c_int(0)
+    rows = lib().gfo_ba_linearize(ctypes.byref(p), r.ctypes.data_as(_dp), J.ctypes.data_as(_dp), ctypes.byref(nc), cap_rows, cap_cols)
+    if rows < 0:
+        raise RuntimeError("capacity")
+    n = nc.value
+    return r[:rows].copy(), J[:rows * n].reshape(rows, n).copy()
+
+
+def plus(pb, delta):
+    p = pb.struct()
+    d = np.ascontiguousarray(delta, np.float64)
+    lib().gfo_ba_plus(ctypes.byref(p), d.ctypes.data_as(_dp))
+
+
+def marginalize_old(pb):
+    """MARGIN_OLD: returns the Prior for the next window (block indices already shifted by one frame)."""
+    p = pb.struct()
+    F = pb.n_frames
+    cap = 16 * F + 8
+    x0 = np.zeros(cap); J = np.zeros(cap * cap); r = np.zeros(cap)
+    out = BaPrior()
+    n = lib().gfo_ba_marginalize_old(ctypes.byref(p), ctypes.byref(out), x0.ctypes.data_as(_dp), J.ctypes.data_as(_dp), r.ctypes.data_as(_dp))
+    if n <= 0:
+        raise RuntimeError("marginalisation failed: %d" % n)
+    nb = out.n_blocks
+    return Prior(list(out.block_kind)[:nb], list(out.block_index)[:nb], list(out.block_idx)[:nb], x0.copy(), J[:n * n].reshape(n, n).copy(), r[:n].copy())
+
+
+def set_tolerances(function=1e-6, gradient=1e-10, parameter=1e-8):
+    lib().gfo_ba_set_tolerances(function, gradient, parameter)

@@ -1,0 +1,198 @@
+"""CPU tests that pin the back-end oracle (oracle/ba_oracle.c).
+
+The reference has no tests for Estimator::optimization() and Ceres is not available, so the oracle is
+pinned (a) factor by factor with central finite differences on the manifold -- the method of
+ProjectionTwoFrameOneCamFactor::check (projectionTwoFrameOneCamFactor.cpp:153-275) -- (b) by an
+independent SciPy trust-region solve of the same cost (agreement of the optimum, not of the path), and
+(c) by the Schur-complement identity the marginalisation prior has to satisfy.
+"""
+import numpy as np
+import pytest
+
+from ground_fusion_b200.synth_ba import make_window
+from oracle import ba_oracle as O
+
+
+def fd_jacobian(pb, cols, eps=1e-6):
+    r0, J = O.linearize(pb)
+    out = {}
+    for c in cols:
+        d = np.zeros(J.shape[1]); d[c] = eps
+        a = pb.clone(); O.plus(a, d); r2, _ = O.linearize(a)
+        a = pb.clone(); O.plus(a, -d); r1, _ = O.linearize(a)
+        out[c] = (r2 - r1) / (2 * eps)
+    return J, out
+
+
+def test_imu_and_visual_jacobians_match_finite_differences():
+    pb, _ = make_window(seed=1, n_landmarks=60)
+    pb.visual_sqrt_info = 1.0          # keeps |r| < 1: Huber inactive, corrected Jacobian == dr/dx
+    pb.ex_pose_const = 0; pb.td_const = 0
+    n_imu_rows = 15 * pb.n_imu
+    J, num = fd_jacobian(pb, range(0, 11 * 6 + 11 * 9 + 7 + 10))
+    for c, g in num.items():
+        for sl in (slice(0, n_imu_rows), slice(n_imu_rows, None)):
+            scale = np.abs(J[sl, c]).max()
+            if scale > 0:
+                assert np.abs(g[sl] - J[sl, c]).max() <= 1e-6 * scale + 1e-7, c
+
+
+def test_huber_corrector_scales_residual_and_jacobian():
+    pb, _ = make_window(seed=2, n_landmarks=40)
+    r_a, J_a = O.linearize(pb)
+    pb2 = pb.clone(); pb2.visual_sqrt_info = pb.visual_sqrt_info * 1e-3
+    r_b, J_b = O.linearize(pb2)
+    nv = 2 * pb.n_visual
+    ra = r_a[-nv:].reshape(-1, 2); rb = r_b[-nv:].reshape(-1, 2) * 1e3        # raw residuals (Huber inactive at 1e-3)
+    s = (rb ** 2).sum(1)
+    w = np.where(s > 1, 1 / np.sqrt(np.sqrt(s)), 1.0)                          # sqrt(rho') = s^(-1/4)
+    assert np.allclose(ra, rb * w[:, None], rtol=1e-9, atol=1e-12)
+    rho = np.where(s > 1, 2 * np.sqrt(s) - 1, s)
+    imu_cost = 0.5 * (r_a[:-nv] ** 2).sum()
+    assert np.isclose(O.cost(pb), imu_cost + 0.5 * rho.sum(), rtol=1e-12)
+
+
+def test_solve_reduces_cost_and_error():
+    pb, truth = make_window(seed=0)
+    q = pb.clone()
+    s = O.solve(q)
+    assert s["final_cost"] < 1e-3 * s["initial_cost"] and s["iterations"] <= 8
+    assert all(b <= a * (1 + 1e-12) for a, b in zip(s["cost"], s["cost"][1:]))
+    e0 = np.abs(pb.para_pose[:, :3] - truth["P"]).max(); e1 = np.abs(q.para_pose[:, :3] - truth["P"]).max()
+    assert e1 < e0
+    assert s["reduced_dim"] == 165 and s["n_free_landmarks"] > 0
+
+
+def _gauge_prior(pb, weight=1e3):
+    """A 6-row prior on pose[0] (removes the 4-DoF gauge freedom so that optima are comparable)."""
+    from ground_fusion_b200.ba_problem import Prior
+    return Prior([0], [0], [0], pb.para_pose[0].copy(), weight * np.eye(6), np.zeros(6))
+
+
+def test_optimum_agrees_with_scipy_least_squares():
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    pb, _ = make_window(seed=3, n_landmarks=80, pix_noise=0.05 / 460.0, free_fraction=1.0)   # |r| << 1 at the optimum: Huber inactive there
+    pb.prior = _gauge_prior(pb)
+    # Ceres' dogleg never drops its regulariser below mu = 1e-8 * diag(J^T J); with the real IMU information
+    # (1e8..1e10) against the visual one (1e5) that makes the last digits of the optimum take hundreds of
+    # iterations.  De-weight the IMU factors so both solvers reach the optimum to 1e-8 and can be compared.
+    for k in range(pb.n_imu):
+        for e in range(225):
+            pb.imu[k].covariance[e] *= 1e6
+    a = pb.clone(); a.max_num_iterations = 16
+    O.set_tolerances(1e-15, 1e-14, 1e-14)      # drive the restated Ceres loop to the exact optimum
+    try:
+        for _ in range(12):
+            s = O.solve(a)
+            if s["iterations"] <= 1:
+                break
+    finally:
+        O.set_tolerances()
+    r, J = O.linearize(a)
+    nv = 2 * a.n_visual
+    assert (r[-nv:].reshape(-1, 2) ** 2).sum(1).max() < 1.0
+    n = J.shape[1]
+
+    def fun(d):
+        q = a.clone(); O.plus(q, d); return O.linearize(q)[0]
+
+    def jac(d):
+        q = a.clone(); O.plus(q, d); return O.linearize(q)[1]
+    # an independent trust-region solver started at the oracle's answer must not find anything better
+    res = scipy_opt.least_squares(fun, np.zeros(n), jac=jac, method="trf", x_scale="jac", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=60)
+    assert res.cost <= s["final_cost"] * (1 + 1e-12)
+    assert res.cost >= s["final_cost"] * (1 - 1e-7)
+    b = a.clone(); O.plus(b, res.x)
+    assert np.abs(a.para_pose[:, :3] - b.para_pose[:, :3]).max() < 1e-4
+    # and from the initial guess it lands in the same optimum
+    def fun0(d):
+        q = pb.clone(); O.plus(q, d); return O.linearize(q)[0]
+
+    def jac0(d):
+        q = pb.clone(); O.plus(q, d); return O.linearize(q)[1]
+    res0 = scipy_opt.least_squares(fun0, np.zeros(n), jac=jac0, method="trf", x_scale="jac", xtol=1e-14, ftol=1e-14, gtol=1e-14, max_nfev=300)
+    c = pb.clone(); O.plus(c, res0.x)
+    r_c = O.linearize(c)[0]
+    if (r_c[-nv:].reshape(-1, 2) ** 2).sum(1).max() < 1.0:      # scipy minimised sum r^2; equal to the Huber cost only if inactive
+        assert np.isclose(res0.cost, s["final_cost"], rtol=1e-5)
+        assert np.abs(a.para_pose[:, :3] - c.para_pose[:, :3]).max() < 1e-3
+
+
+def test_all_constant_and_empty_problems():
+    pb, _ = make_window(seed=4, n_landmarks=30)
+    q = pb.clone(); q.frames_const = 1; q.feature_const[:] = 1     # systemstationary: nothing left to optimise
+    s = O.solve(q)
+    assert s["iterations"] == 0 and np.array_equal(q.para_pose, pb.para_pose)
+
+
+def test_marginalization_is_the_schur_complement():
+    pb, _ = make_window(seed=5, n_landmarks=90)
+    q = pb.clone(); O.solve(q)
+    prior = O.marginalize_old(q)
+    # the factor set of MARGIN_OLD as a stand-alone problem with every block free
+    sub = q.clone()
+    rows = [(f.imu_i, f.imu_j, f.feature, list(f.pts_i), list(f.pts_j), list(f.vel_i), list(f.vel_j), f.td_i, f.td_j)
+            for f in list(q.visual)[:q.n_visual] if f.imu_i == 0]
+    sub.set_visual(rows)
+    sub.n_imu = 1                                   # IMU factor 0 -> 1 is the first entry
+    sub.feature_const[:] = 0; sub.ex_pose_const = 0; sub.td_const = 0
+    r, J = O.linearize(sub)
+    H, b = J.T @ J, J.T @ r
+    # oracle column order: pose[0..10] (6 each), speedbias[0..10] (9 each), ex (6), td (1), landmarks
+    F = 11
+    pose = lambda f: list(range(6 * f, 6 * f + 6)); sb = lambda f: list(range(66 + 9 * f, 66 + 9 * f + 9))
+    marg = pose(0) + sb(0) + list(range(66 + 99 + 7, J.shape[1]))
+    keep = []
+    for k, i in zip(prior.kinds, prior.indices):
+        keep += pose(i + 1) if k == 0 else sb(i + 1) if k == 1 else list(range(165, 171)) if k == 2 else [171]
+    Amm = H[np.ix_(marg, marg)]; Amm = 0.5 * (Amm + Amm.T)
+    w, V = np.linalg.eigh(Amm)
+    Ainv = (V * np.where(w > 1e-8, 1 / np.where(w > 1e-8, w, 1), 0)) @ V.T
+    A = H[np.ix_(keep, keep)] - H[np.ix_(keep, marg)] @ Ainv @ H[np.ix_(marg, keep)]
+    bb = b[keep] - H[np.ix_(keep, marg)] @ Ainv @ b[marg]
+    # prior columns follow block_idx; build the permutation from prior order to `keep` order
+    cols = []
+    for k, c in zip(prior.kinds, prior.idx):
+        cols += list(range(c, c + (6 if k in (0, 2) else 9 if k == 1 else 1)))
+    JtJ = (prior.J.T @ prior.J)[np.ix_(cols, cols)]; Jtr = (prior.J.T @ prior.r)[cols]
+    w2 = np.linalg.eigvalsh(0.5 * (A + A.T))
+    if w2.min() > 1e-6:                               # no truncated direction: J0^T J0 == A and J0^T r0 == b
+        assert np.allclose(JtJ, A, rtol=1e-6, atol=1e-6 * np.abs(A).max())
+        assert np.allclose(Jtr, bb, rtol=1e-6, atol=1e-6 * np.abs(bb).max())
+    else:                                             # eigenvalues <= 1e-8 are dropped (marginalization_factor.cpp:294-302)
+        wv, Vv = np.linalg.eigh(0.5 * (A + A.T)); keepv = wv > 1e-8
+        assert np.allclose(JtJ, (Vv[:, keepv] * wv[keepv]) @ Vv[:, keepv].T, rtol=1e-5, atol=1e-6 * np.abs(A).max())
+    assert prior.n == len(cols) and sorted(cols) == list(range(prior.n))
+
+
+def test_prior_is_consistent_across_a_window_shift():
+    """Solving window k+1 with the prior keeps the poses it shares with window k (no new information added)."""
+    pb, truth = make_window(seed=6, n_landmarks=100)
+    q = pb.clone(); q.max_num_iterations = 16
+    O.solve(q); O.solve(q)                       # converged window
+    prior = O.marginalize_old(q)
+    # next problem: frames 1..10 of the same window, only the prior + their own factors
+    nxt = q.clone()
+    nxt.n_frames = 10
+    nxt.para_pose = q.para_pose[1:].copy(); nxt.para_speed_bias = q.para_speed_bias[1:].copy()
+    rows = [(f.imu_i - 1, f.imu_j - 1, f.feature, list(f.pts_i), list(f.pts_j), list(f.vel_i), list(f.vel_j), f.td_i, f.td_j)
+            for f in list(q.visual)[:q.n_visual] if f.imu_i >= 1]
+    nxt.set_visual(rows)
+    imus = []
+    for f in list(q.imu)[1:q.n_imu]:
+        imus.append(dict(i=f.i - 1, j=f.j - 1, sum_dt=f.sum_dt, delta_p=list(f.delta_p), delta_q=list(f.delta_q), delta_v=list(f.delta_v),
+                         linearized_ba=list(f.linearized_ba), linearized_bg=list(f.linearized_bg),
+                         jacobian=np.array(f.jacobian).reshape(15, 15), covariance=np.array(f.covariance).reshape(15, 15)))
+    nxt.set_imu(imus)
+    nxt.prior = prior
+    def relative(pose):      # gauge-invariant: positions in the first frame's body frame
+        from ground_fusion_b200.synth_ba import q_to_R
+        R0 = q_to_R(pose[0, 3:])
+        return (pose[:, :3] - pose[0, :3]) @ R0
+    before = relative(nxt.para_pose)
+    s = O.solve(nxt)
+    # the window keeps drifting slowly along its weakest (scale/bias) direction, exactly as further iterations on
+    # the un-marginalised window do (Ceres' mu floor, see the SciPy test); the rigorous check of the prior is the
+    # Schur identity above, here only gross consistency is asserted
+    assert np.abs(relative(nxt.para_pose) - before).max() < 5e-2
+    assert s["final_cost"] <= s["initial_cost"] * (1 + 1e-9)
