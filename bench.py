@@ -98,6 +98,47 @@ def cpu_reference_fps(gray, depth, budget_s, warm=3):
     return done / dt, done, cv2.getNumThreads()
 
 
+def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
+    """Sliding-window solves/s (C2: 11 frames, ~1.5 k visual factors, 10 IMU factors, 8 iterations max) on the GPU
+    through gf_ba_solve (host descriptor in, optimised blocks out: this IS the end-to-end call) next to the CPU oracle."""
+    from ground_fusion_b200.estimator import BundleAdjuster
+    from ground_fusion_b200.synth_ba import make_window
+    wins = [make_window(seed=100 + k)[0] for k in range(n_windows)]
+    saved = [(w.para_pose.copy(), w.para_speed_bias.copy(), w.para_feature.copy(), w.para_ex_pose.copy(), w.para_td.copy()) for w in wins]
+    structs = [w.struct() for w in wins]
+
+    def restore(k):
+        w, sv = wins[k], saved[k]
+        w.para_pose[:] = sv[0]; w.para_speed_bias[:] = sv[1]; w.para_feature[:] = sv[2]; w.para_ex_pose[:] = sv[3]; w.para_td[:] = sv[4]
+    ba = BundleAdjuster(device)
+    for k in range(n_windows):
+        restore(k); ba.solve_struct(structs[k])
+    dev_ms = 0.0; iters = 0
+    t0 = time.perf_counter()
+    for r in range(reps):
+        k = r % n_windows
+        restore(k)
+        sm = ba.solve_struct(structs[k])
+        dev_ms += sm.device_ms; iters += sm.iterations
+    el = time.perf_counter() - t0
+    out = {"metric": "ba_solves_per_sec", "value": reps / el, "unit": "solves/s", "ms_per_solve": 1e3 * el / reps,
+           "device_ms_per_solve": dev_ms / reps, "iterations_per_solve": iters / reps,
+           "workload": "C2 window: 11 frames, %d visual factors, %d IMU factors, reduced system %d + %d free landmarks, max 8 iterations"
+                       % (wins[0].n_visual, wins[0].n_imu, sm.reduced_dim, sm.n_free_landmarks),
+           "e2e": "value already includes the host->device upload of the problem and the download of the blocks"}
+    ba.close()
+    if with_cpu:
+        from oracle import ba_oracle
+        t0 = time.perf_counter(); done = 0
+        while time.perf_counter() - t0 < cpu_seconds:
+            k = done % n_windows
+            restore(k); ba_oracle.solve(wins[k]); done += 1
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": done / dt, "unit": "solves/s", "cores": 1, "kind": "port",
+                               "sample": "%d solves of the same windows, oracle/ba_oracle.c (block-sparse, -O2, 1 thread)" % done}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -228,6 +269,10 @@ def main():
         fps, done, cores = cpu_reference_fps(gray[:60], depth[:60], args.cpu_seconds)
         out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                "sample": "%d frames of the same C2 stream, cv2-based oracle (reference's OpenCV calls + glue)" % done}
+        try:
+            out["ba"] = ba_bench(local, cpu_seconds=min(args.cpu_seconds, 8.0))
+        except Exception as e:      # the FE line must survive a BA problem
+            out["ba"] = {"error": repr(e)}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -559,6 +559,99 @@ static double evaluate(const gf_ba_problem* p, const layout_t* L, const state_t*
     return cost;
 }
 
+/* Block-sparse linearisation: H = J^T J (n x n, unscaled), g = J^T r, cost, without materialising J.  This is
+ * what a production CPU solver does (Ceres' block-sparse Jacobian + Schur eliminator); the dense evaluate() above is
+ * kept for the finite-difference tests.  Hp = J0^T J0 of the prior mapped to the layout is passed in (constant). */
+static void add_blocks(double* H, double* g, int n, int nres, const double* res, int nb, const int* cols, const int* sizes, const int* lds, double* const* Js)
+{
+    for (int a = 0; a < nb; a++) {
+        if (cols[a] < 0) continue;
+        for (int b = 0; b < nb; b++) {
+            if (cols[b] < 0) continue;
+            for (int i = 0; i < sizes[a]; i++)
+                for (int j = 0; j < sizes[b]; j++) {
+                    double v = 0;
+                    for (int k = 0; k < nres; k++) v += Js[a][k * lds[a] + i] * Js[b][k * lds[b] + j];
+                    H[(size_t)(cols[a] + i) * n + cols[b] + j] += v;
+                }
+        }
+        for (int i = 0; i < sizes[a]; i++) { double v = 0; for (int k = 0; k < nres; k++) v += Js[a][k * lds[a] + i] * res[k]; g[cols[a] + i] += v; }
+    }
+}
+static double linearize_blocks(const gf_ba_problem* p, const layout_t* L, const state_t* s, const double* imu_sqrt_info, const double* Hp, double* H, double* g)
+{
+    const int n = L->n_cols;
+    double cost = 0;
+    memcpy(H, Hp, sizeof(double) * (size_t)n * n);
+    memset(g, 0, sizeof(double) * n);
+    if (p->prior && p->prior->n > 0) {
+        const gf_ba_prior* pr = p->prior;
+        int pn = pr->n;
+        double* dx = (double*)malloc(sizeof(double) * pn); double* r = (double*)malloc(sizeof(double) * pn);
+        prior_dx(pr, s, dx);
+        for (int i = 0; i < pn; i++) { double v = pr->linearized_residuals[i]; for (int k = 0; k < pn; k++) v += pr->linearized_jacobians[(size_t)i * pn + k] * dx[k]; r[i] = v; cost += 0.5 * v * v; }
+        for (int b = 0; b < pr->n_blocks; b++) {
+            int col = block_col(L, pr->block_kind[b], pr->block_index[b]);
+            if (col < 0) continue;
+            int ls = block_global_size(pr->block_kind[b]); if (ls == 7) ls = 6;
+            for (int k = 0; k < ls; k++) { double v = 0; for (int i = 0; i < pn; i++) v += pr->linearized_jacobians[(size_t)i * pn + pr->block_idx[b] + k] * r[i]; g[col + k] += v; }
+        }
+        free(dx); free(r);
+    }
+    for (int m = 0; m < p->n_imu; m++) {
+        const gf_ba_imu_factor* f = &p->imu[m];
+        double res[15], J0[105], J1[135], J2[105], J3[135];
+        gfo_eval_imu(f, imu_sqrt_info + 225 * m, p->gravity, s->pose[f->i], s->sb[f->i], s->pose[f->j], s->sb[f->j], res, J0, J1, J2, J3);
+        for (int i = 0; i < 15; i++) cost += 0.5 * res[i] * res[i];
+        int cols[4] = {L->col_pose[f->i], L->col_sb[f->i], L->col_pose[f->j], L->col_sb[f->j]}, sizes[4] = {6, 9, 6, 9}, lds[4] = {7, 9, 7, 9};
+        double* Js[4] = {J0, J1, J2, J3};
+        add_blocks(H, g, n, 15, res, 4, cols, sizes, lds, Js);
+    }
+    for (int v = 0; v < p->n_visual; v++) {
+        const gf_ba_visual_factor* f = &p->visual[v];
+        double res[2], Ji[14], Jj[14], Jex[14], Jf[2], Jtd[2];
+        gfo_eval_visual(f, p->visual_sqrt_info, s->pose[f->imu_i], s->pose[f->imu_j], s->ex, s->feat[f->feature], s->td, res, Ji, Jj, Jex, Jf, Jtd);
+        double sq = res[0] * res[0] + res[1] * res[1], rho0, rho1;
+        if (sq > 1.0) { double rr = sqrt(sq); rho0 = 2.0 * rr - 1.0; rho1 = 1.0 / rr; if (rho1 < 2.2250738585072014e-308) rho1 = 2.2250738585072014e-308; }
+        else { rho0 = sq; rho1 = 1.0; }
+        cost += 0.5 * rho0;
+        double sc = sqrt(rho1);
+        for (int k = 0; k < 14; k++) { Ji[k] *= sc; Jj[k] *= sc; Jex[k] *= sc; }
+        for (int k = 0; k < 2; k++) { Jf[k] *= sc; Jtd[k] *= sc; res[k] *= sc; }
+        int cols[5] = {L->col_pose[f->imu_i], L->col_pose[f->imu_j], L->col_ex, L->col_feat[f->feature], L->col_td}, sizes[5] = {6, 6, 6, 1, 1}, lds[5] = {7, 7, 7, 1, 1};
+        double* Js[5] = {Ji, Jj, Jex, Jf, Jtd};
+        if (f->imu_i == f->imu_j) cols[1] = -1;
+        add_blocks(H, g, n, 2, res, 5, cols, sizes, lds, Js);
+    }
+    return cost;
+}
+static double cost_only(const gf_ba_problem* p, const layout_t* L, const state_t* s, const double* imu_sqrt_info)
+{
+    double cost = 0;
+    if (p->prior && p->prior->n > 0) {
+        const gf_ba_prior* pr = p->prior;
+        int pn = pr->n;
+        double* dx = (double*)malloc(sizeof(double) * pn);
+        prior_dx(pr, s, dx);
+        for (int i = 0; i < pn; i++) { double v = pr->linearized_residuals[i]; for (int k = 0; k < pn; k++) v += pr->linearized_jacobians[(size_t)i * pn + k] * dx[k]; cost += 0.5 * v * v; }
+        free(dx);
+    }
+    for (int m = 0; m < p->n_imu; m++) {
+        const gf_ba_imu_factor* f = &p->imu[m];
+        double res[15];
+        gfo_eval_imu(f, imu_sqrt_info + 225 * m, p->gravity, s->pose[f->i], s->sb[f->i], s->pose[f->j], s->sb[f->j], res, NULL, NULL, NULL, NULL);
+        for (int i = 0; i < 15; i++) cost += 0.5 * res[i] * res[i];
+    }
+    for (int v = 0; v < p->n_visual; v++) {
+        const gf_ba_visual_factor* f = &p->visual[v];
+        double res[2];
+        gfo_eval_visual(f, p->visual_sqrt_info, s->pose[f->imu_i], s->pose[f->imu_j], s->ex, s->feat[f->feature], s->td, res, NULL, NULL, NULL, NULL, NULL);
+        double sq = res[0] * res[0] + res[1] * res[1];
+        cost += 0.5 * (sq > 1.0 ? 2.0 * sqrt(sq) - 1.0 : sq);
+    }
+    return cost;
+}
+
 /* Evaluator::Plus: PoseLocalParameterization::Plus (pose_local_parameterization.cpp:12-26) for 7-blocks */
 static void pose_plus(const double* x, const double* d, double* out)
 {
@@ -645,8 +738,18 @@ GFO int gfo_ba_solve(const gf_ba_problem* p, gf_ba_summary* sum)
     state_t x, cand, tmp; state_load(p, &x); state_load(p, &cand); state_load(p, &tmp);
     double* r = (double*)malloc(sizeof(double) * (m + 1));
     double* rc = (double*)malloc(sizeof(double) * (m + 1));
-    double* J = (double*)malloc(sizeof(double) * ((size_t)m * n + 1));
     double* H = (double*)malloc(sizeof(double) * ((size_t)n * n + 1));
+    double* Hp = (double*)calloc((size_t)n * n + 1, 8);      /* J0^T J0 of the prior, constant during the solve */
+    if (p->prior && p->prior->n > 0) {
+        const gf_ba_prior* pr = p->prior; int pn = pr->n;
+        int* pc = (int*)malloc(sizeof(int) * pn);
+        for (int k = 0; k < pn; k++) pc[k] = -1;
+        for (int b = 0; b < pr->n_blocks; b++) { int col = block_col(&L, pr->block_kind[b], pr->block_index[b]); if (col < 0) continue;
+            int ls = block_global_size(pr->block_kind[b]); if (ls == 7) ls = 6; for (int k = 0; k < ls; k++) pc[pr->block_idx[b] + k] = col + k; }
+        for (int a = 0; a < pn; a++) { if (pc[a] < 0) continue; for (int b = 0; b < pn; b++) { if (pc[b] < 0) continue; double v = 0;
+            for (int k = 0; k < pn; k++) v += pr->linearized_jacobians[(size_t)k * pn + a] * pr->linearized_jacobians[(size_t)k * pn + b]; Hp[(size_t)pc[a] * n + pc[b]] = v; } }
+        free(pc);
+    }
     double *g = (double*)calloc(n + 1, 8), *scale = (double*)calloc(n + 1, 8), *diag = (double*)calloc(n + 1, 8), *lmd = (double*)calloc(n + 1, 8);
     double *gs = (double*)calloc(n + 1, 8), *gn = (double*)calloc(n + 1, 8), *step = (double*)calloc(n + 1, 8), *delta = (double*)calloc(n + 1, 8), *tv = (double*)calloc(n + 1, 8);
     /* Ceres defaults (solver.h) + the reference's options (estimator.cpp:3305-3315; the wall-clock cap is disabled) */
@@ -657,14 +760,12 @@ GFO int gfo_ba_solve(const gf_ba_problem* p, gf_ba_summary* sum)
     double x_cost;
 
 #define LINEARIZE(first) do {                                                                                 \
-        x_cost = evaluate(p, &L, &x, imu_sqrt, r, J);                                                          \
-        if (first) for (int c = 0; c < n; c++) { double s2 = 0; for (int i = 0; i < m; i++) s2 += J[(size_t)i * n + c] * J[(size_t)i * n + c]; scale[c] = 1.0 / (1.0 + sqrt(s2)); } \
+        x_cost = linearize_blocks(p, &L, &x, imu_sqrt, Hp, H, g);                                              \
+        if (first) for (int c = 0; c < n; c++) scale[c] = 1.0 / (1.0 + sqrt(H[(size_t)c * n + c]));            \
         /* gradient of the unscaled problem -> gradient_max_norm = |x - Plus(x, -g)|_inf */                   \
-        for (int c = 0; c < n; c++) { double s = 0; for (int i = 0; i < m; i++) s += J[(size_t)i * n + c] * r[i]; tv[c] = -s; } \
+        for (int c = 0; c < n; c++) tv[c] = -g[c];                                                             \
         state_plus(p, &L, &x, tv, &tmp); state_diff_norms(&L, &x, &tmp, NULL, &grad_max);                      \
-        for (int i = 0; i < m; i++) for (int c = 0; c < n; c++) J[(size_t)i * n + c] *= scale[c];              \
-        for (int a = 0; a < n; a++) { for (int b = a; b < n; b++) { double s = 0; for (int i = 0; i < m; i++) s += J[(size_t)i * n + a] * J[(size_t)i * n + b]; H[(size_t)a * n + b] = H[(size_t)b * n + a] = s; } \
-                                      double s = 0; for (int i = 0; i < m; i++) s += J[(size_t)i * n + a] * r[i]; g[a] = s; } \
+        for (int a = 0; a < n; a++) { for (int b = 0; b < n; b++) H[(size_t)a * n + b] *= scale[a] * scale[b]; g[a] *= scale[a]; } \
     } while (0)
 
     LINEARIZE(1);
@@ -728,7 +829,7 @@ GFO int gfo_ba_solve(const gf_ba_problem* p, gf_ba_summary* sum)
         invalid_streak = 0;
         for (int c = 0; c < n; c++) delta[c] = step[c] * scale[c];
         state_plus(p, &L, &x, delta, &cand);
-        double cand_cost = evaluate(p, &L, &cand, imu_sqrt, rc, NULL);
+        double cand_cost = cost_only(p, &L, &cand, imu_sqrt);
         double step_norm; state_diff_norms(&L, &x, &cand, &step_norm, NULL);
         if (step_norm <= param_tol * (x_norm + param_tol)) { termination = GF_BA_CONVERGENCE_PARAMETER; sum->cost[it] = x_cost; sum->radius[it] = radius; break; }
         if (fabs(x_cost - cand_cost) <= func_tol * x_cost) { termination = GF_BA_CONVERGENCE_FUNCTION; sum->cost[it] = x_cost; sum->radius[it] = radius; break; }
@@ -752,7 +853,7 @@ GFO int gfo_ba_solve(const gf_ba_problem* p, gf_ba_summary* sum)
 done:
     sum->iterations = it; sum->num_successful_steps = n_success; sum->termination = termination; sum->final_cost = x_cost;
     state_store(p, &x);
-    free(x.feat); free(cand.feat); free(tmp.feat); free(imu_sqrt); free(r); free(rc); free(J); free(H);
+    free(x.feat); free(cand.feat); free(tmp.feat); free(imu_sqrt); free(r); free(rc); free(H); free(Hp);
     free(g); free(scale); free(diag); free(lmd); free(gs); free(gn); free(step); free(delta); free(tv); free(L.col_feat);
     return 0;
 }
