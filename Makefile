@@ -10,8 +10,16 @@ HDRS := $(wildcard $(CSRC)/*.cuh) include/gf_b200.h
 
 all: $(OUT) oracle
 
-$(OUT): $(SRCS) $(HDRS)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRCS) -Xptxas -v 2> build_ptxas.log || (cat build_ptxas.log; false)
+# front end: -fmad=false (bit-exact with OpenCV's separately-rounded float ops; FMA only where written)
+# back end: default FMA contraction (parity is 1e-6 m against an FP64 oracle, not bit-exactness)
+BUILD := ground_fusion_b200/csrc/_obj
+$(BUILD)/fe_tracker.o: $(CSRC)/fe_tracker.cu $(HDRS)
+	@mkdir -p $(BUILD); $(NVCC) $(NVFLAGS) -dc -o $@ $< -Xptxas -v 2> build_ptxas_fe.log || (cat build_ptxas_fe.log; false)
+$(BUILD)/ba_solver.o: $(CSRC)/ba_solver.cu $(HDRS)
+	@mkdir -p $(BUILD); $(NVCC) $(filter-out -fmad=false,$(NVFLAGS)) -dc -o $@ $< -Xptxas -v 2> build_ptxas_ba.log || (cat build_ptxas_ba.log; false)
+$(OUT): $(BUILD)/fe_tracker.o $(BUILD)/ba_solver.o
+	$(NVCC) $(ARCH) -shared -o $@ $^
+	@cat build_ptxas_fe.log build_ptxas_ba.log > build_ptxas.log
 
 oracle:
 	$(MAKE) -C oracle

@@ -28,13 +28,16 @@ namespace gfba {
 constexpr int MAXF = GF_BA_MAX_FRAMES;
 constexpr int X_POSE = 0, X_SB = 7 * MAXF, X_EX = X_SB + 9 * MAXF, X_TD = X_EX + 7, X_FEAT = X_TD + 1;
 constexpr int PAIR_THREADS = 256, PAIR_CHUNK = 64;   // factors staged per pass (2*64 rows x 20 cols in smem)
-constexpr int MAX_NC = 208;                          // reduced (camera-side) dimension supported by k_ba_step
+constexpr int RB_THREADS = 512;                      // k_ba_step block size: 128 registers per thread
+constexpr int MAX_NC = 175;                          // reduced dimension supported by k_ba_step: 4x4 blocks of the (nc+1)-row system <= 1024 threads
 
 struct BaState {
     double x_cost, cand_cost, radius, mu, alpha, dogleg_norm, model_change, x_norm, step_norm, grad_max;
     double cost_hist[GF_BA_MAX_ITERATIONS + 1], radius_hist[GF_BA_MAX_ITERATIONS + 1];
     double acc_cost[2];          // cost accumulated by k_ba_eval into buffer 0/1
+    double cauchy_num, cauchy_den;   // |gs|^2 and v^T H' v accumulated by k_ba_schur
     int it, reuse, done, termination, n_success, invalid_streak, need_linearize, step_valid, cur, first, max_iter, solver_failed;
+    long long prof[16];          // clock64() cycles per phase of k_ba_step, summed over iterations (debug)
 };
 
 struct BaDev {
@@ -53,6 +56,7 @@ struct BaDev {
     double* Hp;               // [nc*nc]
     double* acc[2];           // accumulators: [H nc*nc | g n | W L*nc | hll L]
     double *scale, *diag, *gs, *gn, *step, *delta;
+    double* Sg;               // [(nc+1)*nc] reduced system written by k_ba_schur (row nc = rhs)
     double gravity[3], vis_sqrt_info;
     BaState* st;
 };
@@ -83,22 +87,69 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sh)
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void k_ba_setup(BaDev d)
+// IMU sqrt-information matrices, one warp per factor: the same Gauss-Jordan (partial pivoting) + Cholesky as
+// gfba::sqrt_info_from_cov / the oracle, element updates spread over the lanes (identical arithmetic per element).
+__global__ void __launch_bounds__(128) k_ba_setup(BaDev d)
 {
-    int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    // H_prior = J0^T J0 mapped to the layout's columns
-    const int nc = d.nc, pn = d.pn;
+    __shared__ double Ms[4][15 * 30];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    const int nc = d.nc;
     for (int e = gid; e < nc * nc; e += gsz) d.Hp[e] = 0.0;
-    if (gid < d.n_imu) {
-        double M[15 * 30];
-        if (!sqrt_info_from_cov(d.imu[gid].covariance, 15, d.imu_sqrt + 225 * gid, M)) d.st->termination = GF_BA_FAILURE;
-    }
     if (gid == 0) {
         BaState& s = *d.st;
         s.radius = 1e4; s.mu = 1e-8; s.reuse = 0; s.done = 0; s.it = 0; s.n_success = 0; s.invalid_streak = 0;
         s.need_linearize = 1; s.step_valid = 0; s.cur = 1; s.first = 1; s.acc_cost[0] = s.acc_cost[1] = 0.0;   // first linearisation goes to buffer 0
         s.x_cost = 0; s.cand_cost = 0;
     }
+    const int m = blockIdx.x * 4 + warp;
+    if (m >= d.n_imu) return;
+    double* M = Ms[warp];
+    const double* cov = d.imu[m].covariance;
+    const int n = 15, w2 = 30;
+    for (int e = lane; e < n * w2; e += 32) { int i = e / w2, j = e - i * w2; M[e] = j < n ? cov[i * n + j] : ((j - n) == i ? 1.0 : 0.0); }
+    __syncwarp();
+    bool ok = true;
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int r = c + 1; r < n; r++) if (fabs(M[r * w2 + c]) > fabs(M[piv * w2 + c])) piv = r;   // uniform across lanes
+        if (M[piv * w2 + c] == 0.0) { ok = false; break; }
+        __syncwarp();
+        if (piv != c && lane < w2) { double t = M[c * w2 + lane]; M[c * w2 + lane] = M[piv * w2 + lane]; M[piv * w2 + lane] = t; }
+        __syncwarp();
+        double dpiv = M[c * w2 + c];
+        __syncwarp();
+        if (lane < w2) M[c * w2 + lane] /= dpiv;
+        __syncwarp();
+        for (int e = lane; e < n * w2; e += 32) {
+            int r = e / w2, j = e - r * w2;
+            if (r == c) continue;
+            double fct = M[r * w2 + c];
+            // every lane of row r must read fct before column c of that row is overwritten: column c itself is updated last
+            if (j != c && fct != 0.0) M[e] -= fct * M[c * w2 + j];
+        }
+        __syncwarp();
+        if (lane < n && lane != c) { double fct = M[lane * w2 + c]; if (fct != 0.0) M[lane * w2 + c] -= fct * M[c * w2 + c]; }
+        __syncwarp();
+    }
+    if (ok && lane == 0) {          // Cholesky (lower) of the inverse held in the right half, then transpose out
+        double* A = M + n;
+        for (int j = 0; j < n && ok; j++) {
+            double dd = A[j * w2 + j];
+            for (int k = 0; k < j; k++) dd -= A[j * w2 + k] * A[j * w2 + k];
+            if (!(dd > 0.0)) { ok = false; break; }
+            dd = sqrt(dd);
+            A[j * w2 + j] = dd;
+            for (int i = j + 1; i < n; i++) {
+                double t = A[i * w2 + j];
+                for (int k = 0; k < j; k++) t -= A[i * w2 + k] * A[j * w2 + k];
+                A[i * w2 + j] = t / dd;
+            }
+        }
+        double* out = d.imu_sqrt + 225 * m;
+        if (ok) for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) out[i * n + j] = (j >= i) ? A[j * w2 + i] : 0.0;
+    }
+    if (!ok && lane == 0) d.st->termination = GF_BA_FAILURE;
 }
 __global__ void k_ba_prior_hessian(BaDev d)
 {
@@ -258,6 +309,85 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Reduced camera system for the Gauss-Newton solve, (H' + mu D^2) with the free landmarks eliminated:
+//   S[a][b] = H'[a][b] + [a==b] mu D_a^2 - s_a s_b sum_l c_l W[l][a] W[l][b],   c_l = s_l^2 / (h'_ll + mu D_l^2)
+//   rhs[b]  = g'[b] - s_b sum_l c_l W[l][b] g_l
+// (primes = Jacobi-scaled).  One thread per entry of the lower triangle; W stays in L2.  Everything it needs
+// (scale, D, c_l) is recomputed locally from the accumulators so that it can run before k_ba_step adopts them.
+__global__ void __launch_bounds__(256) k_ba_schur(BaDev d)
+{
+    extern __shared__ double cl[];                 // [L]
+    const BaState& st = *d.st;
+    if (st.done) return;
+    const bool fresh = st.need_linearize != 0;
+    if (!fresh && st.reuse) return;               // the previous Gauss-Newton step is still valid
+    const int cur = fresh ? (st.cur ^ 1) : st.cur;
+    const int nc = d.nc, L = d.L;
+    const double* H = acc_H(d, cur); const double* Hp = d.Hp; const double* g = acc_g(d, cur);
+    const double* W = acc_W(d, cur); const double* hll = acc_hll(d, cur);
+    const bool first = st.first != 0;
+    const double mu = st.mu;
+    const int tid = threadIdx.y * 16 + threadIdx.x;
+    auto scale_of = [&](int c) { return first ? 1.0 / (1.0 + sqrt(c < nc ? H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c] : hll[c - nc])) : d.scale[c]; };
+    for (int l = tid; l < L; l += 256) {
+        double sl = scale_of(nc + l);
+        double hd = hll[l] * sl * sl;
+        double hc = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);     // D_l^2
+        cl[l] = sl * sl / (hd + mu * hc);
+    }
+    __syncthreads();
+    // v = gs / D (times the Jacobi scale, because H below is unscaled): v_c = g_c s_c^2 / D_c^2
+    auto vcam = [&](int c) { double sc_ = scale_of(c); double hd = (H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c]) * sc_ * sc_;
+                             hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd); return g[c] * sc_ * sc_ / hd; };
+    __shared__ double sred2[8];
+    double num = 0, den = 0;
+    const int a = blockIdx.y * 16 + threadIdx.y, b = blockIdx.x * 16 + threadIdx.x;
+    if (a <= nc && b < nc && b <= a) {
+        const double sb = scale_of(b);
+        double acc = 0;
+        if (a < nc) {
+            const double sa = scale_of(a);
+            for (int l = 0; l < L; l++) acc += cl[l] * W[(size_t)l * nc + a] * W[(size_t)l * nc + b];
+            const double hab = H[(size_t)a * nc + b] + Hp[(size_t)a * nc + b];
+            double v = hab * sa * sb;
+            if (a == b) {
+                double hd = v; hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd); v += mu * hd;
+                double gsa = g[a] * sa / sqrt(hd); num += gsa * gsa;
+            }
+            d.Sg[(size_t)a * (a + 1) / 2 + b] = v - acc * sa * sb;
+            den += (a == b ? 1.0 : 2.0) * vcam(a) * hab * vcam(b);
+        } else {
+            for (int l = 0; l < L; l++) acc += cl[l] * W[(size_t)l * nc + b] * g[nc + l];
+            d.Sg[(size_t)nc * (nc + 1) / 2 + b] = g[b] * sb - acc * sb;
+        }
+    }
+    // landmark part of the Cauchy quadratic form: 2 v_l (W v_c)_l + h_ll v_l^2, warp per landmark in the column-0 CTAs
+    if (blockIdx.x == 0) {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int l = blockIdx.y * 8 + warp; l < L; l += gridDim.y * 8) {
+            double t = 0;
+            for (int c = lane; c < nc; c += 32) t += W[(size_t)l * nc + c] * vcam(c);
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) {
+                double sl = scale_of(nc + l), hd = hll[l] * sl * sl;
+                double hc = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);
+                double vl = g[nc + l] * sl * sl / hc;
+                den += 2.0 * vl * t + hll[l] * vl * vl;
+                double gsl = g[nc + l] * sl / sqrt(hc); num += gsl * gsl;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
+    if ((tid & 31) == 0) sred2[tid >> 5] = den;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int k = 0; k < 8; k++) t += sred2[k]; if (t != 0.0) atomicAdd(&d.st->cauchy_den, t); }
+    __syncthreads();
+    if ((tid & 31) == 0) sred2[tid >> 5] = num;
+    __syncthreads();
+    if (tid == 0) { double t = 0; for (int k = 0; k < 8; k++) t += sred2[k]; if (t != 0.0) atomicAdd(&d.st->cauchy_num, t); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ambient-space helpers over the non-constant blocks
 __device__ __forceinline__ void for_each_free_block(const BaDev& d, int t, int nt, double (*fn)(const BaDev&, int off, int size, void* ctx), void* ctx, double& acc);
 
@@ -308,17 +438,20 @@ __device__ __forceinline__ double block_reduce_max(double v, double* sh)
 
 // DoglegStrategy::ComputeStep + TrustRegionMinimizer::ComputeTrustRegionStep + candidate point.
 // Dynamic shared memory: packed lower triangle of the (nc+1) x (nc+1) augmented reduced system.
-__global__ void __launch_bounds__(1024) k_ba_step(BaDev d)
+__global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
 {
     extern __shared__ double S[];                 // packed: S[i*(i+1)/2 + j], j <= i ; row nc = rhs
     __shared__ double sred[32];
-    __shared__ double colbuf[MAX_NC + 1];
+    __shared__ double colbuf[MAX_NC + 2];
     __shared__ double yc[MAX_NC + 1];
+    __shared__ double zb[MAX_NC + 5], accb[MAX_NC + 5], ybl[4];
     __shared__ int s_fail;
     BaState& st = *d.st;
     if (st.done) return;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nc = d.nc, L = d.L, n = d.n;
+    long long t_last = clock64();
+#define PH(k) do { if (tid == 0) { long long t_ = clock64(); st.prof[k] += t_ - t_last; t_last = t_; } } while (0)
     if (st.need_linearize) {                      // a fresh linearisation landed in the inactive buffer: adopt it
         __syncthreads();
         if (tid == 0) { st.cur ^= 1; st.need_linearize = 0; st.x_cost = st.acc_cost[st.cur]; }
@@ -349,6 +482,7 @@ __global__ void __launch_bounds__(1024) k_ba_step(BaDev d)
         __syncthreads();
         if (st.done) return;
     }
+    PH(0);   // adoption, scaling, gradient norms
     // ---- TrustRegionMinimizer: iteration bookkeeping ----
     if (st.it >= st.max_iter || st.radius < 1e-32) { if (tid == 0) { st.done = 1; st.termination = GF_BA_NO_CONVERGENCE; } return; }
     __syncthreads();
@@ -369,23 +503,11 @@ __global__ void __launch_bounds__(1024) k_ba_step(BaDev d)
             d.gs[c] = g[c] * sc[c] / D;
         }
         __syncthreads();
-        double num = 0, den = 0;
-        for (int c = tid; c < n; c += nt) num += d.gs[c] * d.gs[c];
-        // v^T H' v = vc^T H'cc vc + 2 vl^T W' vc + sum h'll vl^2,  v = gs / D
-        for (int a = tid; a < nc; a += nt) {
-            double va = d.gs[a] / d.diag[a] * sc[a], s = 0;
-            for (int b = 0; b < nc; b++) s += (H[(size_t)a * nc + b] + Hp[(size_t)a * nc + b]) * (d.gs[b] / d.diag[b] * sc[b]);
-            den += va * s;
-        }
-        for (int l = tid; l < L; l += nt) {
-            double vl = d.gs[nc + l] / d.diag[nc + l] * sc[nc + l], s = 0;
-            for (int b = 0; b < nc; b++) s += W[(size_t)l * nc + b] * (d.gs[b] / d.diag[b] * sc[b]);
-            den += 2.0 * vl * s + hll[l] * vl * vl;
-        }
-        num = block_reduce_sum(num, sred);
-        den = block_reduce_sum(den, sred);
-        if (tid == 0) st.alpha = num / den;
+        if (tid == 0) { st.alpha = st.cauchy_num / st.cauchy_den; st.cauchy_num = 0.0; st.cauchy_den = 0.0; }   // accumulated by k_ba_schur
+        PH(1);   // diag, Cauchy point
         // ---- ComputeGaussNewtonStep: (H' + mu D^2) y = g' by Schur complement on the landmarks + Cholesky ----
+        const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+        bool first_try = true;
         while (true) {
             const double mu = st.mu;
             __syncthreads();
@@ -398,80 +520,248 @@ __global__ void __launch_bounds__(1024) k_ba_step(BaDev d)
                 d.gn[nc + l] = 1.0 / v;
             }
             __syncthreads();
-            const int tri = (nc + 1) * (nc + 2) / 2;
-            for (int e = tid; e < tri; e += nt) {
-                // unpack (a, b), a >= b
-                int a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-                while ((a + 1) * (a + 2) / 2 <= e) a++;
-                while (a * (a + 1) / 2 > e) a--;
-                int b = e - a * (a + 1) / 2;
-                double v;
-                if (a < nc) {
-                    v = (H[(size_t)a * nc + b] + Hp[(size_t)a * nc + b]) * sc[a] * sc[b];
-                    if (a == b) v += mu * d.diag[a] * d.diag[a];
-                    double s = 0;
-                    for (int l = 0; l < L; l++) s += d.gn[nc + l] * sc[nc + l] * sc[nc + l] * W[(size_t)l * nc + a] * W[(size_t)l * nc + b];
-                    v -= s * sc[a] * sc[b];
-                } else if (b < nc) {                  // rhs row
-                    v = g[b] * sc[b];
-                    double s = 0;
-                    for (int l = 0; l < L; l++) s += d.gn[nc + l] * sc[nc + l] * sc[nc + l] * W[(size_t)l * nc + b] * g[nc + l];
-                    v -= s * sc[b];
-                } else v = 0.0;
-                S[e] = v;
+            if (first_try) {
+                // the reduced system was assembled by k_ba_schur (same mu) in packed order: flat copy into shared memory
+                const int tri = (nc + 1) * (nc + 2) / 2;
+                for (int e = tid; e < tri - 1; e += nt) S[e] = d.Sg[e];
+                if (tid == 0) S[tri - 1] = 0.0;
+            } else {
+                // retry with a larger mu (rare): assemble here
+                for (int a = warp; a <= nc; a += nwarp)
+                    for (int b = lane; b <= a; b += 32) {
+                        double v;
+                        if (a < nc) {
+                            v = (H[(size_t)a * nc + b] + Hp[(size_t)a * nc + b]) * sc[a] * sc[b];
+                            if (a == b) v += mu * d.diag[a] * d.diag[a];
+                            double t = 0;
+                            for (int l = 0; l < L; l++) t += d.gn[nc + l] * sc[nc + l] * sc[nc + l] * W[(size_t)l * nc + a] * W[(size_t)l * nc + b];
+                            v -= t * sc[a] * sc[b];
+                        } else if (b < nc) {
+                            v = g[b] * sc[b];
+                            double t = 0;
+                            for (int l = 0; l < L; l++) t += d.gn[nc + l] * sc[nc + l] * sc[nc + l] * W[(size_t)l * nc + b] * g[nc + l];
+                            v -= t * sc[b];
+                        } else v = 0.0;
+                        S[a * (a + 1) / 2 + b] = v;
+                    }
             }
+            first_try = false;
             __syncthreads();
-            // right-looking Cholesky on the packed lower triangle; row nc (the rhs) is carried along: after the
-            // loop S[nc][0..nc) = L^-1 rhs
-            for (int j = 0; j < nc && !s_fail; j++) {
-                double dj = S[j * (j + 1) / 2 + j];
-                if (!(dj > 0.0)) { s_fail = 1; break; }      // same value seen by all threads
-                double inv = 1.0 / sqrt(dj);
-                for (int i = j + tid; i <= nc; i += nt) colbuf[i] = S[i * (i + 1) / 2 + j] * inv;
-                __syncthreads();
-                for (int i = j + tid; i <= nc; i += nt) S[i * (i + 1) / 2 + j] = colbuf[i];
-                const int m = nc - j;                        // trailing rows j+1..nc
-                for (int e = tid; e < m * (m + 1) / 2; e += nt) {
-                    int a = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-                    while ((a + 1) * (a + 2) / 2 <= e) a++;
-                    while (a * (a + 1) / 2 > e) a--;
-                    int b = e - a * (a + 1) / 2;
-                    int i = j + 1 + a, k = j + 1 + b;
-                    if (i == nc && k == nc) continue;
-                    S[i * (i + 1) / 2 + k] -= colbuf[i] * colbuf[k];
+            PH(2);   // load / assemble reduced system
+            // Register-blocked right-looking Cholesky, block size 4.  The (nc+1)-row augmented system (row nc = rhs,
+            // rows above nc padded with identity) is cut into 4x4 blocks (bi, bj), bi >= bj, ordered column-major;
+            // thread t owns blocks t and t + 512 in registers (512 threads x 128 registers: no spills -- with most of
+            // the SM carved out as shared memory a spill costs an L2 round trip).
+            // Per panel p (4 columns): the diagonal owner factors its block and publishes inv(L_pp) [barrier];
+            // panel owners compute L_ip = A_ip L_pp^-T and publish their rows [barrier]; trailing owners apply the
+            // rank-4 update a -= L_i L_j^T (16 LDS.128 -> 64 DFMA).  The factor never leaves the registers: the
+            // blocked back substitution L^T y = z below uses it in place.
+            {
+                const int N4 = (nc + 4) >> 2;                       // block rows covering rows 0..nc
+                const int nblk = N4 * (N4 + 1) / 2;
+                double* colL4 = S + (((size_t)(nc + 1) * (nc + 2) / 2 + 1) & ~(size_t)1);  // [4][4*N4] panel columns (16 B aligned)
+                double* Linv = colL4 + 16 * N4;                        // [16]
+                const int ld = 4 * N4;
+                int bi[2], bj[2];
+                bool mine[2];
+                double a[2][4][4];
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    const int t = tid + b * RB_THREADS;
+                    mine[b] = t < nblk;
+                    int cj = 0, off = 0;
+                    { int tt = min(t, nblk - 1); while (tt >= off + (N4 - cj)) { off += N4 - cj; cj++; } bi[b] = cj + (tt - off); bj[b] = cj; }
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                        for (int cc = 0; cc < 4; cc++) {
+                            const int i = 4 * bi[b] + rr, k = 4 * bj[b] + cc;
+                            double v = 0.0;
+                            if (mine[b]) {
+                                if (i > nc || (i == nc && k == nc)) v = (i == k) ? 1.0 : 0.0;      // padding / unused rhs diagonal
+                                else if (k <= i) v = S[i * (i + 1) / 2 + k];
+                            }
+                            a[b][rr][cc] = v;
+                        }
                 }
                 __syncthreads();
-            }
-            __syncthreads();
-            if (!s_fail) {
-                // back substitution L^T y = z (z = row nc), one warp, column sweeps over contiguous packed rows
-                if (tid < 32) {
-                    for (int c = tid; c < nc; c += 32) yc[c] = S[nc * (nc + 1) / 2 + c];
-                    __syncwarp();
-                    for (int j = nc - 1; j >= 0; j--) {
-                        double xj = yc[j] / S[j * (j + 1) / 2 + j];
-                        __syncwarp();
-                        if (tid == 0) yc[j] = xj;
-                        for (int k = tid; k < j; k += 32) yc[k] -= S[j * (j + 1) / 2 + k] * xj;
-                        __syncwarp();
+                long long tq = clock64(), tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PQ(k) do { if (tid == 0) { long long t_ = clock64(); tacc[k] += t_ - tq; tq = t_; } } while (0)
+                for (int pnl = 0; pnl < N4; pnl++) {
+                    {   // ---- diagonal block (at most one of the two owned blocks): work on a selected copy to keep the code small ----
+                        const bool d0 = mine[0] && bi[0] == pnl && bj[0] == pnl, d1 = mine[1] && bi[1] == pnl && bj[1] == pnl;
+                        if (d0 || d1) {
+                            double w[4][4], iv[4];
+#pragma unroll
+                            for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                                for (int cc = 0; cc < 4; cc++) w[rr][cc] = d1 ? a[1][rr][cc] : a[0][rr][cc];
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                const int j = 4 * pnl + jj;
+                                if (j < nc) {
+                                    const double dj = w[jj][jj];
+                                    if (!(dj > 0.0)) s_fail = 1;
+                                    const double inv = rsqrt(dj);
+                                    iv[jj] = inv;
+                                    w[jj][jj] = dj * inv;
+                                    colbuf[1 + j] = inv;
+#pragma unroll
+                                    for (int rr = jj + 1; rr < 4; rr++) w[rr][jj] *= inv;
+#pragma unroll
+                                    for (int rr = jj + 1; rr < 4; rr++)
+#pragma unroll
+                                        for (int cc = jj + 1; cc <= rr; cc++) w[rr][cc] -= w[rr][jj] * w[cc][jj];
+                                } else {
+                                    w[jj][jj] = 1.0; iv[jj] = 1.0;
+#pragma unroll
+                                    for (int rr = jj + 1; rr < 4; rr++) w[rr][jj] = 0.0;
+                                }
+                            }
+                            // inverse of the lower-triangular factor: li[r][c] = (delta_rc - sum_{c<=m<r} w[r][m] li[m][c]) / w[r][r]
+#pragma unroll
+                            for (int cc = 0; cc < 4; cc++) {
+                                double li[4];
+#pragma unroll
+                                for (int rr = 0; rr < 4; rr++) {
+                                    if (rr < cc) { li[rr] = 0.0; continue; }
+                                    double t = (rr == cc) ? 1.0 : 0.0;
+#pragma unroll
+                                    for (int m = 0; m < 4; m++) if (m >= cc && m < rr) t -= w[rr][m] * li[m];
+                                    li[rr] = t * iv[rr];
+                                }
+#pragma unroll
+                                for (int rr = 0; rr < 4; rr++) Linv[rr * 4 + cc] = li[rr];
+                            }
+#pragma unroll
+                            for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                                for (int cc = 0; cc < 4; cc++) { if (d1) a[1][rr][cc] = w[rr][cc]; else a[0][rr][cc] = w[rr][cc]; }
+                        }
+                    }
+                    PQ(0);
+                    __syncthreads();
+                    PQ(1);
+                    if (s_fail) break;
+                    {   // ---- panel blocks: X = A L_pp^-T (a thread owns at most one block of a given column... or two: loop) ----
+#pragma unroll 1
+                        for (int b = 0; b < 2; b++) {
+                            const bool pb_ = b == 0 ? (mine[0] && bj[0] == pnl && bi[0] > pnl) : (mine[1] && bj[1] == pnl && bi[1] > pnl);
+                            if (!pb_) continue;
+                            double x[4][4];
+#pragma unroll
+                            for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                                for (int cc = 0; cc < 4; cc++) {
+                                    double t = 0.0;
+#pragma unroll
+                                    for (int m = 0; m < 4; m++) if (m <= cc) t += (b == 0 ? a[0][rr][m] : a[1][rr][m]) * Linv[cc * 4 + m];
+                                    x[rr][cc] = t;
+                                }
+                            const int brow = b == 0 ? bi[0] : bi[1];
+#pragma unroll
+                            for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                                for (int cc = 0; cc < 4; cc++) { if (b == 0) a[0][rr][cc] = x[rr][cc]; else a[1][rr][cc] = x[rr][cc]; colL4[cc * ld + 4 * brow + rr] = x[rr][cc]; }
+                        }
+                    }
+                    PQ(2);
+                    __syncthreads();
+                    PQ(3);
+#pragma unroll
+                    for (int b = 0; b < 2; b++)
+                        if (mine[b] && bj[b] > pnl) {                                 // ---- trailing block: rank-4 update ----
+#pragma unroll
+                            for (int m = 0; m < 4; m++) {
+                                const double2 r01 = *reinterpret_cast<const double2*>(colL4 + m * ld + 4 * bi[b]);
+                                const double2 r23 = *reinterpret_cast<const double2*>(colL4 + m * ld + 4 * bi[b] + 2);
+                                const double2 c01 = *reinterpret_cast<const double2*>(colL4 + m * ld + 4 * bj[b]);
+                                const double2 c23 = *reinterpret_cast<const double2*>(colL4 + m * ld + 4 * bj[b] + 2);
+                                const double lr[4] = {r01.x, r01.y, r23.x, r23.y}, lc[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+                                for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                                    for (int cc = 0; cc < 4; cc++) a[b][rr][cc] -= lr[rr] * lc[cc];
+                            }
+                        }
+                    PQ(4);
+                }
+                PQ(5);
+                if (tid == 0) for (int k = 0; k < 6; k++) st.prof[8 + k] += tacc[k];
+                // ---- blocked back substitution  L^T y = z ----
+                // z = row nc of the factor (owned by the blocks of block row nc/4); accb[4q..4q+3] accumulates
+                // sum_{p>q} L_pq^T y_p.  Per block row p (descending): the diagonal owner solves its 4x4 system
+                // [barrier], the owners of block row p push L_pq^T y_p to the accumulators of q < p [barrier].
+                __syncthreads();
+                if (!s_fail) {
+                    const int brhs = nc >> 2, rrhs = nc & 3;
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        if (mine[b] && bi[b] == brhs) {
+#pragma unroll
+                            for (int cc = 0; cc < 4; cc++) {
+                                const int k = 4 * bj[b] + cc;
+                                const double zv = rrhs == 0 ? a[b][0][cc] : rrhs == 1 ? a[b][1][cc] : rrhs == 2 ? a[b][2][cc] : a[b][3][cc];
+                                if (k < nc) zb[k] = zv;
+                            }
+                        }
+                        if (mine[b] && bi[b] == bj[b]) {
+#pragma unroll
+                            for (int cc = 0; cc < 4; cc++) { accb[4 * bi[b] + cc] = 0.0; if (4 * bi[b] + cc >= nc) zb[4 * bi[b] + cc] = 0.0; }
+                        }
+                    }
+                    __syncthreads();
+                    for (int pb = N4 - 1; pb >= 0; pb--) {
+#pragma unroll
+                        for (int b = 0; b < 2; b++)
+                            if (mine[b] && bi[b] == pb && bj[b] == pb) {
+                                const double t3 = zb[4 * pb + 3] - accb[4 * pb + 3], t2 = zb[4 * pb + 2] - accb[4 * pb + 2];
+                                const double t1 = zb[4 * pb + 1] - accb[4 * pb + 1], t0 = zb[4 * pb + 0] - accb[4 * pb + 0];
+                                // unknowns beyond nc (the rhs row, padding) are zero: their inverse pivot is taken as 0
+                                const double i3 = 4 * pb + 3 < nc ? colbuf[1 + 4 * pb + 3] : 0.0, i2 = 4 * pb + 2 < nc ? colbuf[1 + 4 * pb + 2] : 0.0;
+                                const double i1 = 4 * pb + 1 < nc ? colbuf[1 + 4 * pb + 1] : 0.0, i0 = 4 * pb < nc ? colbuf[1 + 4 * pb] : 0.0;
+                                const double y3 = t3 * i3;
+                                const double y2 = (t2 - a[b][3][2] * y3) * i2;
+                                const double y1 = (t1 - a[b][2][1] * y2 - a[b][3][1] * y3) * i1;
+                                const double y0 = (t0 - a[b][1][0] * y1 - a[b][2][0] * y2 - a[b][3][0] * y3) * i0;
+                                if (4 * pb < nc) yc[4 * pb] = y0;
+                                if (4 * pb + 1 < nc) yc[4 * pb + 1] = y1;
+                                if (4 * pb + 2 < nc) yc[4 * pb + 2] = y2;
+                                if (4 * pb + 3 < nc) yc[4 * pb + 3] = y3;
+                                ybl[0] = y0; ybl[1] = y1; ybl[2] = y2; ybl[3] = y3;
+                            }
+                        __syncthreads();
+#pragma unroll
+                        for (int b = 0; b < 2; b++)
+                            if (mine[b] && bi[b] == pb && bj[b] < pb) {
+                                const double y0 = ybl[0], y1 = ybl[1], y2 = ybl[2], y3 = ybl[3];
+#pragma unroll
+                                for (int cc = 0; cc < 4; cc++) accb[4 * bj[b] + cc] += a[b][0][cc] * y0 + a[b][1][cc] * y1 + a[b][2][cc] * y2 + a[b][3][cc] * y3;
+                            }
+                        __syncthreads();
                     }
                 }
+            }
+            __syncthreads();
+            PH(3);   // Cholesky
+            if (!s_fail) {
                 __syncthreads();
                 for (int c = tid; c < nc; c += nt) if (!isfinite(yc[c])) s_fail = 1;
                 __syncthreads();
+                PH(4);   // back substitution
             }
             if (!s_fail) {
                 // y_l = e_l (g'_l - w'_l . y_c) ; gn = -D y
-                for (int l = tid; l < L; l += nt) {
-                    double s = g[nc + l] * sc[nc + l];
+                for (int l = warp; l < L; l += nwarp) {
                     double t = 0;
-                    for (int b = 0; b < nc; b++) t += W[(size_t)l * nc + b] * sc[b] * yc[b];
-                    double yl = d.gn[nc + l] * (s - t * sc[nc + l]);
-                    d.step[nc + l] = yl;                       // temp
+                    for (int b = lane; b < nc; b += 32) t += W[(size_t)l * nc + b] * sc[b] * yc[b];
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    if (lane == 0) d.step[nc + l] = d.gn[nc + l] * (g[nc + l] * sc[nc + l] - t * sc[nc + l]);   // temp
                 }
                 __syncthreads();
                 for (int c = tid; c < n; c += nt) { double y = (c < nc) ? yc[c] : d.step[c]; d.gn[c] = -d.diag[c] * y; }
                 __syncthreads();
+                PH(5);   // landmark back substitution
                 break;
             }
             __syncthreads();
@@ -494,10 +784,10 @@ __global__ void __launch_bounds__(1024) k_ba_step(BaDev d)
         else if (gnorm * alpha >= radius) { ca = -(radius / gnorm); cb = 0; dn = radius; }
         else {
             double b_dot_a = -alpha * ga;
-            double a2 = pow(alpha * gnorm, 2.0);
-            double bma2 = a2 - 2 * b_dot_a + pow(gnn, 2);
+            double a2 = (alpha * gnorm) * (alpha * gnorm);
+            double bma2 = a2 - 2 * b_dot_a + gnn * gnn;
             double cc = b_dot_a - a2;
-            double dd = sqrt(cc * cc + bma2 * (pow(radius, 2.0) - a2));
+            double dd = sqrt(cc * cc + bma2 * (radius * radius - a2));
             double beta = (cc <= 0) ? (dd - cc) / bma2 : (radius * radius - a2) / (dd + cc);
             ca = -alpha * (1.0 - beta); cb = beta; dn = -1.0;
         }
@@ -505,22 +795,26 @@ __global__ void __launch_bounds__(1024) k_ba_step(BaDev d)
         for (int c = tid; c < n; c += nt) { double s = ca * d.gs[c] + cb * d.gn[c]; nn += s * s; d.step[c] = s / d.diag[c]; }
         nn = block_reduce_sum(nn, sred);
         if (dn < 0) dn = sqrt(nn);
-        // model_cost_change = -(s^T g' + s^T H' s / 2)
+        // model_cost_change = -(s^T g' + s^T H' s / 2) with s = (ca gs + cb gn) / D.  No mat-vec is needed:
+        //   u = gs / D, w = gn / D = -y;  u^T H' u = |gs|^2 / alpha (Cauchy),  H' y = g' - mu D^2 y  =>
+        //   w^T H' w = y^T g' - mu y^T D^2 y,   u^T H' w = -(u^T g' - mu u^T D^2 y)
         double sg = 0, sHs = 0;
-        for (int c = tid; c < n; c += nt) sg += d.step[c] * g[c] * sc[c];
-        for (int a = tid; a < nc; a += nt) {
-            double s = 0;
-            for (int b = 0; b < nc; b++) s += (H[(size_t)a * nc + b] + Hp[(size_t)a * nc + b]) * sc[b] * d.step[b];
-            sHs += d.step[a] * sc[a] * s;
-        }
-        for (int l = tid; l < L; l += nt) {
-            double sl = d.step[nc + l] * sc[nc + l], s = 0;
-            for (int b = 0; b < nc; b++) s += W[(size_t)l * nc + b] * sc[b] * d.step[b];
-            sHs += 2.0 * sl * s + hll[l] * sl * sl;
+        {
+            double ygp = 0, yDy = 0, ugp = 0, uDy = 0;
+            for (int c = tid; c < n; c += nt) {
+                double gp = g[c] * sc[c], D = d.diag[c], u = d.gs[c] / D, y = -d.gn[c] / D;
+                sg += d.step[c] * gp;
+                ygp += y * gp; yDy += y * D * D * y; ugp += u * gp; uDy += u * D * D * y;
+            }
+            ygp = block_reduce_sum(ygp, sred); yDy = block_reduce_sum(yDy, sred); ugp = block_reduce_sum(ugp, sred); uDy = block_reduce_sum(uDy, sred);
+            const double mu_used = st.mu;
+            const double uHu = g2 / alpha, wHw = ygp - mu_used * yDy, uHw = -(ugp - mu_used * uDy);
+            sHs = (tid == 0) ? (ca * ca * uHu + 2.0 * ca * cb * uHw + cb * cb * wHw) : 0.0;
+            for (int c = tid; c < n; c += nt) d.delta[c] = d.step[c] * sc[c];
         }
         sg = block_reduce_sum(sg, sred); sHs = block_reduce_sum(sHs, sred);
+        PH(6);   // dogleg + model cost change
         const double model_change = -(sg + 0.5 * sHs);
-        for (int c = tid; c < n; c += nt) d.delta[c] = d.step[c] * sc[c];
         __syncthreads();
         plus_all(d, d.X, d.delta, d.Xc, tid, nt);
         double s2, mx; diff_norms(d, d.X, d.Xc, s2, mx, tid, nt);
@@ -530,6 +824,7 @@ __global__ void __launch_bounds__(1024) k_ba_step(BaDev d)
             st.step_valid = model_change > 0.0 ? 1 : 0;
             st.cand_cost = 0.0;
         }
+        PH(7);   // candidate point
     }
 }
 
@@ -582,6 +877,7 @@ struct gf_ba {
     // growable device buffers
     void* dbuf; size_t dcap;
     void* hbuf; size_t hcap;     // pinned staging
+    long long prof[16];
 };
 
 static int ensure(gf_ba* s, size_t dbytes)
@@ -660,7 +956,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     }
     for (int k = 0; k < nfeat; k++) if (col_feat[k] == -2) col_feat[k] = c++;
     d.L = c - d.nc; d.n = c;
-    if (d.nc > MAX_NC) return set_err(GF_ERR_CAPACITY, "reduced system larger than 208");
+    if (d.nc > MAX_NC) return set_err(GF_ERR_CAPACITY, "reduced system larger than 175");
     // ---- sort visual factors by pose pair ----
     std::vector<int> pair_id(F * F, -1), pair_cnt;
     std::vector<int> pair_ij;
@@ -703,7 +999,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     const size_t upload_bytes = off;
     const size_t o_Xc = take(sizeof(double) * (X_FEAT + nfeat)), o_sq = take(sizeof(double) * 225 * (size_t)(p->n_imu > 0 ? p->n_imu : 1)),
                  o_Hp = take(sizeof(double) * (size_t)nc * nc), o_a0 = take(sizeof(double) * acc_size(nc, L)), o_a1 = take(sizeof(double) * acc_size(nc, L)),
-                 o_vec = take(sizeof(double) * 6 * (size_t)(n > 0 ? n : 1)), o_st = take(sizeof(BaState));
+                 o_vec = take(sizeof(double) * 6 * (size_t)(n > 0 ? n : 1)), o_Sg = take(sizeof(double) * (size_t)(nc + 1) * (nc > 0 ? nc : 1)), o_st = take(sizeof(BaState));
     int rc = ensure(s, off);
     if (rc) return rc;
     char* hb = (char*)s->hbuf; char* db = (char*)s->dbuf;
@@ -738,6 +1034,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     double* vec = (double*)(db + o_vec);
     const size_t nn = (size_t)(n > 0 ? n : 1);
     d.scale = vec; d.diag = vec + nn; d.gs = vec + 2 * nn; d.gn = vec + 3 * nn; d.step = vec + 4 * nn; d.delta = vec + 5 * nn;
+    d.Sg = (double*)(db + o_Sg);
     d.st = (BaState*)(db + o_st);
     for (int k = 0; k < 3; k++) d.gravity[k] = p->gravity[k];
     d.vis_sqrt_info = p->visual_sqrt_info;
@@ -747,7 +1044,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     GF_CUDA(cudaMemcpyAsync(db, hb, upload_bytes, cudaMemcpyHostToDevice, st));
     GF_CUDA(cudaMemsetAsync(db + o_a0, 0, al(sizeof(double) * acc_size(nc, L)) * 2, st));
     GF_CUDA(cudaMemsetAsync(db + o_st, 0, sizeof(BaState), st));
-    k_ba_setup<<<(nc * nc + 255) / 256 + 1, 256, 0, st>>>(d); GF_LAUNCHED();
+    k_ba_setup<<<(p->n_imu + 3) / 4 + 1, 128, 0, st>>>(d); GF_LAUNCHED();
     {   // max_iter into the state (after setup zeroed/initialised it)
         int mi = p->max_num_iterations;
         GF_CUDA(cudaMemcpyAsync((char*)d.st + offsetof(BaState, max_iter), &mi, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -755,11 +1052,13 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
     const int eval_blocks = n_pairs + p->n_imu + (pn ? 1 : 0);
     const size_t prior_smem = sizeof(double) * 2 * (size_t)pn;
-    const size_t step_smem = sizeof(double) * (size_t)(nc + 1) * (nc + 2) / 2;
+    const size_t step_smem = sizeof(double) * ((size_t)(nc + 1) * (nc + 2) / 2 + 16 * (size_t)((nc + 4) / 4) + 16);
     const int iters = p->max_num_iterations;
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 0); GF_LAUNCHED(); }
+    const dim3 sgrid((nc + 15) / 16, (nc + 16) / 16), sblock(16, 16);
     for (int it = 0; it <= iters; it++) {
-        k_ba_step<<<1, 1024, step_smem, st>>>(d); GF_LAUNCHED();
+        if (nc > 0 && it < iters) { k_ba_schur<<<sgrid, sblock, sizeof(double) * (size_t)(L > 0 ? L : 1), st>>>(d); GF_LAUNCHED(); }
+        k_ba_step<<<1, RB_THREADS, step_smem, st>>>(d); GF_LAUNCHED();
         if (it == iters) break;                  // the extra k_ba_step adopts the last linearisation and closes the run
         if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 1); GF_LAUNCHED(); }
         k_ba_decide<<<1, 256, 0, st>>>(d); GF_LAUNCHED();
@@ -783,6 +1082,15 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     sum->initial_cost = hs->cost_hist[0]; sum->final_cost = hs->x_cost;
     for (int k = 0; k <= GF_BA_MAX_ITERATIONS; k++) { sum->cost[k] = hs->cost_hist[k]; sum->radius[k] = hs->radius_hist[k]; }
     sum->device_ms = ms;
+    memcpy(s->prof, hs->prof, sizeof(s->prof));
+    return GF_OK;
+}
+
+/* debug: clock64() cycles per phase of k_ba_step of the last solve (see PH() markers) */
+int gf_ba_debug_profile(gf_ba* s, long long* out16)
+{
+    if (!s || !out16) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    memcpy(out16, s->prof, sizeof(s->prof));
     return GF_OK;
 }
 

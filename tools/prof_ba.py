@@ -1,0 +1,19 @@
+"""Small driver for ncu: a few gf_ba_solve calls on C2 windows."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ground_fusion_b200.estimator import BundleAdjuster
+from ground_fusion_b200.synth_ba import make_window
+ba = BundleAdjuster(0)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+for k in range(n):
+    pb, _ = make_window(seed=100 + k)
+    print(ba.optimization(pb)["device_ms"])
+
+import ctypes
+prof = (ctypes.c_longlong * 16)()
+ba.L.gf_ba_debug_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+ba.L.gf_ba_debug_profile(ba._h, prof)
+names = ["adopt+norms", "diag+cauchy", "load S", "cholesky", "backsubst", "landmark backsubst", "dogleg+model", "candidate", "rb:t0 diag", "rb:t0 barA", "rb:t0 panel", "rb:t0 barB", "rb:t0 update", "rb:t0 exit"]
+tot = sum(list(prof)[:8])
+for n_, v in zip(names, prof):
+    print("%-20s %9d cycles %5.1f%%" % (n_, v, 100.0 * v / max(tot, 1)))
