@@ -9,8 +9,11 @@
 //                + 1 scalar tail chain over columns 16..20, result = tail + ((l0+l2)+(l1+l3))
 //   b1/b2:       4 chains of pmaddwd pairs (col k, col k+4 | k+8, k+12) + 1 tail chain,
 //                result = tail + ((c0+c2) + (c1+c3))
-// Each chain is owned by one lane (15 lanes for A, 10 for b); everything else is spread over 32 lanes.
-// Compile with -fmad=false: every float op must round on its own.
+// The order of the float additions is what makes the result bit-exact, and it is inherently sequential.
+// Everything around it is organised to keep those chains short in instructions: the 32-lane parallel phase
+// produces the *terms* (exact integers converted to float, pair sums for the pmaddwd chains) already laid
+// out in chain order in shared memory, so that the chain phase is one predicated LDS+FADD loop of 105 steps
+// run by 15 (A) or 10 (b) lanes.  Compile with -fmad=false: every float op must round on its own.
 #pragma once
 #include "gf_common.cuh"
 
@@ -19,18 +22,25 @@ namespace gf {
 constexpr int LK_WIN = 21;
 constexpr int LK_NPIX = LK_WIN * LK_WIN;  // 441
 constexpr int LK_IREG = 24;               // staged I window incl. Scharr apron + bilinear +1
+constexpr int LK_IPITCH = 32;             // bytes per staged I row (24 + up to 3 bytes of alignment slack)
 constexpr int LK_SCH = 22;                // integer positions needing a derivative
 constexpr int LK_JR = 40;                 // cached J region (window 22 + 9 px drift each side)
-constexpr int LK_WARPS = 4;
+constexpr int LK_JPITCH = 48;             // bytes per staged J row (40 + up to 3 bytes of alignment slack)
+constexpr int LK_WARPS = 2;                // features per CTA: one warp per scheduler, CTAs spread over the SMs
+constexpr int LK_CHAIN = 84, LK_TAIL = 105;        // terms per SIMD-lane chain / tail chain of the A sums
+constexpr int LK_BCHAIN = 42;                       // pair terms per chain of the b sums
+constexpr int LK_AT = 4 * LK_CHAIN + LK_TAIL;       // 441 terms per A quantity
+constexpr int LK_BT = 4 * LK_BCHAIN + LK_TAIL;      // 273 terms per b component (168 pair units + 105 tail pixels)
+constexpr int LK_Q = 5 * LK_TAIL;                   // slots per quantity: [step 0..104][chain 0..4], short chains padded with +0.0f
 
 struct __align__(16) LKSmem {
-    uint8_t ireg[LK_IREG * LK_IREG];
+    uint8_t ireg[LK_IREG * LK_IPITCH];     // raw bytes, row r at r*32, first needed column at byte xoff
     int16_t sch[LK_SCH * LK_SCH * 2];
     int16_t pI[LK_NPIX + 1];
     int16_t pdx[LK_NPIX + 1];
     int16_t pdy[LK_NPIX + 1];
-    int16_t diff[LK_NPIX + 1];
-    uint8_t jreg[LK_JR * LK_JR];
+    uint8_t jreg[LK_JR * LK_JPITCH];
+    float terms[3 * LK_Q];                 // [quantity][step][chain]; slots beyond a chain's length hold +0.0f (x + 0 is exact)
 };
 
 __device__ __forceinline__ int lk_descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
@@ -41,6 +51,45 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
     w01 = __float2int_rn(a * (1.f - b) * 16384.f);
     w10 = __float2int_rn((1.f - a) * b * 16384.f);
     w11 = 16384 - w00 - w01 - w10;
+}
+
+// Stages the RW x RH window of img whose top-left pixel is (x0, y0) into dst (row pitch DP bytes).
+// Inside the image: aligned 32-bit loads, the first needed column sits at byte offset (x0 & 3), returned.
+// Touching the border: REFLECT_101 byte gathers, offset 0.
+template <int RW, int RH, int DP>
+__device__ __forceinline__ int lk_stage(uint8_t* dst, const Level& L, int x0, int y0, int lane)
+{
+    if (x0 >= 0 && y0 >= 0 && x0 + RW <= L.w && y0 + RH <= L.h) {
+        const int xa = x0 & ~3, xoff = x0 - xa;
+        constexpr int WPR = DP / 4;                      // words per staged row
+        const int need = (xoff + RW + 3) >> 2;           // words actually needed per row
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+        for (int i = lane; i < RH * WPR; i += 32) {
+            int r = i / WPR, c = i - r * WPR;
+            if (c < need) d32[i] = __ldg(reinterpret_cast<const uint32_t*>(L.ptr + (size_t)(y0 + r) * L.pitch + xa) + c);
+        }
+        return xoff;
+    }
+    for (int i = lane; i < RW * RH; i += 32) {
+        int r = i / RW, c = i - r * RW;
+        int yy = reflect101(y0 + r, L.h), xx = reflect101(x0 + c, L.w);
+        dst[r * DP + c] = __ldg(L.ptr + (size_t)yy * L.pitch + xx);
+    }
+    return 0;
+}
+
+// One sequential float chain per lane: lane (q*5 + c) of the first nq*5 lanes adds the 105 slots of chain c of
+// quantity q in order.  Chains shorter than 105 are padded with +0.0f, so the loop is a bare LDS + FADD.
+__device__ __forceinline__ float lk_chain(const float* T, int lane, int nq)
+{
+    float acc = 0.f;
+    if (lane < nq * 5) {
+        const int q = lane / 5, c = lane - q * 5;
+        const float* p = T + q * LK_Q + c;
+#pragma unroll
+        for (int s = 0; s < LK_TAIL; s++) acc += p[5 * s];
+    }
+    return acc;
 }
 
 // One pyramid level for one point (all 32 lanes call this with identical scalar arguments).
@@ -60,11 +109,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
 
     // ---- stage the 24x24 u8 window of I (REFLECT_101) ----
     __syncwarp();
-    for (int i = lane; i < LK_IREG * LK_IREG; i += 32) {
-        int r = i / LK_IREG, c = i - r * LK_IREG;
-        int yy = reflect101(ipy - 1 + r, I.h), xx = reflect101(ipx - 1 + c, I.w);
-        S.ireg[i] = __ldg(I.ptr + (size_t)yy * I.pitch + xx);
-    }
+    const int ioff = lk_stage<LK_IREG, LK_IREG, LK_IPITCH>(S.ireg, I, ipx - 1, ipy - 1, lane);
     __syncwarp();
     // ---- Scharr derivative at the 22x22 integer positions (0 outside the image) ----
     for (int i = lane; i < LK_SCH * LK_SCH; i += 32) {
@@ -72,9 +117,9 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
         int X = ipx + c, Y = ipy + r;
         int ix = 0, iy = 0;
         if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
-            const uint8_t* u = S.ireg + r * LK_IREG + c;  // row above, column left of the centre
-            const uint8_t* m = u + LK_IREG;
-            const uint8_t* d = m + LK_IREG;
+            const uint8_t* u = S.ireg + r * LK_IPITCH + ioff + c;  // row above, column left of the centre
+            const uint8_t* m = u + LK_IPITCH;
+            const uint8_t* d = m + LK_IPITCH;
             int t0l = (u[0] + d[0]) * 3 + m[0] * 10, t0r = (u[2] + d[2]) * 3 + m[2] * 10;
             int t1l = d[0] - u[0], t1c = d[1] - u[1], t1r = d[2] - u[2];
             ix = t0r - t0l;
@@ -84,46 +129,32 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
         S.sch[2 * i + 1] = (int16_t)iy;
     }
     __syncwarp();
-    // ---- bilinear 21x21 patches: I*32 and (Ix, Iy) ----
+    // ---- bilinear 21x21 patches I*32, (Ix, Iy), and the gradient-matrix terms in chain order ----
     for (int i = lane; i < LK_NPIX; i += 32) {
         int y = i / LK_WIN, x = i - y * LK_WIN;
-        const uint8_t* p = S.ireg + (y + 1) * LK_IREG + (x + 1);
-        int iv = p[0] * iw00 + p[1] * iw01 + p[LK_IREG] * iw10 + p[LK_IREG + 1] * iw11;
+        const uint8_t* p = S.ireg + (y + 1) * LK_IPITCH + ioff + (x + 1);
+        int iv = p[0] * iw00 + p[1] * iw01 + p[LK_IPITCH] * iw10 + p[LK_IPITCH + 1] * iw11;
         S.pI[i] = (int16_t)lk_descale(iv, 9);
         const int16_t* s = S.sch + 2 * (y * LK_SCH + x);
         int dxv = s[0] * iw00 + s[2] * iw01 + s[2 * LK_SCH] * iw10 + s[2 * LK_SCH + 2] * iw11;
         int dyv = s[1] * iw00 + s[3] * iw01 + s[2 * LK_SCH + 1] * iw10 + s[2 * LK_SCH + 3] * iw11;
-        S.pdx[i] = (int16_t)lk_descale(dxv, 14);
-        S.pdy[i] = (int16_t)lk_descale(dyv, 14);
+        int gx = (int16_t)lk_descale(dxv, 14), gy = (int16_t)lk_descale(dyv, 14);
+        S.pdx[i] = (int16_t)gx;
+        S.pdy[i] = (int16_t)gy;
+        // products are exact integers below 2^24, so (float)(int product) == fx*fy of OpenCV's float path
+        int slot = (x < 16) ? (y * 4 + (x >> 2)) * 5 + (x & 3) : (y * 5 + (x - 16)) * 5 + 4;     // [step][chain]
+        S.terms[slot] = (float)(gx * gx);
+        S.terms[LK_Q + slot] = (float)(gx * gy);
+        S.terms[2 * LK_Q + slot] = (float)(gy * gy);
     }
     __syncwarp();
     // ---- gradient matrix, OpenCV lane order ----
-    float acc = 0.f;
-    {
-        int q = lane / 5, c = lane - q * 5;
-        if (lane < 15) {
-            const int16_t* u = (q == 2) ? S.pdy : S.pdx;
-            const int16_t* v = (q == 0) ? S.pdx : S.pdy;
-            if (c < 4) {
-#pragma unroll 3
-                for (int y = 0; y < LK_WIN; y++) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        int k = y * LK_WIN + c + 4 * j;
-                        acc = (float)u[k] * (float)v[k] + acc;
-                    }
-                }
-            } else {
-#pragma unroll 3
-                for (int y = 0; y < LK_WIN; y++) {
-#pragma unroll
-                    for (int x = 16; x < LK_WIN; x++) {
-                        int k = y * LK_WIN + x;
-                        acc += (float)((int)u[k] * (int)v[k]);
-                    }
-                }
-            }
-        }
+    const float acc = lk_chain(S.terms, lane, 3);
+    __syncwarp();
+    // the mismatch chains are 42 pair terms long: clear steps 42..83 of the SIMD chains of the two quantities they reuse
+    for (int i = lane; i < 2 * 4 * (LK_CHAIN - LK_BCHAIN); i += 32) {
+        int q = i / (4 * (LK_CHAIN - LK_BCHAIN)), r = i - q * 4 * (LK_CHAIN - LK_BCHAIN);
+        S.terms[q * LK_Q + (LK_BCHAIN + (r >> 2)) * 5 + (r & 3)] = 0.f;
     }
     float A[3];
 #pragma unroll
@@ -144,7 +175,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
 
     float qx = nx - 10.f, qy = ny - 10.f;
     float pdx_ = 0.f, pdy_ = 0.f;
-    int jx0 = 0, jy0 = 0;
+    int jx0 = 0, jy0 = 0, joff = 0;
     bool jvalid = false;
     for (int j = 0; j < 30; j++) {
         int iqx = __float2int_rd(qx), iqy = __float2int_rd(qy);
@@ -156,52 +187,44 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
             jx0 = iqx - 9;
             jy0 = iqy - 9;
             __syncwarp();
-            for (int i = lane; i < LK_JR * LK_JR; i += 32) {
-                int r = i / LK_JR, c = i - r * LK_JR;
-                int yy = reflect101(jy0 + r, J.h), xx = reflect101(jx0 + c, J.w);
-                S.jreg[i] = __ldg(J.ptr + (size_t)yy * J.pitch + xx);
-            }
+            joff = lk_stage<LK_JR, LK_JR, LK_JPITCH>(S.jreg, J, jx0, jy0, lane);
             jvalid = true;
             __syncwarp();
         }
         a = qx - (float)iqx;
         b = qy - (float)iqy;
         lk_weights(a, b, iw00, iw01, iw10, iw11);
-        const uint8_t* jb = S.jreg + (iqy - jy0) * LK_JR + (iqx - jx0);
-        for (int i = lane; i < LK_NPIX; i += 32) {
-            int y = i / LK_WIN, x = i - y * LK_WIN;
-            const uint8_t* p = jb + y * LK_JR + x;
-            int jv = p[0] * iw00 + p[1] * iw01 + p[LK_JR] * iw10 + p[LK_JR + 1] * iw11;
-            S.diff[i] = (int16_t)(lk_descale(jv, 9) - S.pI[i]);
+        const uint8_t* jb = S.jreg + (iqy - jy0) * LK_JPITCH + joff + (iqx - jx0);
+        // ---- mismatch terms in chain order: 168 pmaddwd pair units (row y, k in 0..3, half h) + 105 tail pixels ----
+        for (int u = lane; u < LK_BT; u += 32) {
+            int i0, i1, slot;
+            if (u < 4 * LK_BCHAIN) {
+                int y = u >> 3, r = u & 7, k = r & 3, hh = r >> 2;
+                i0 = y * LK_WIN + 8 * hh + k;
+                i1 = i0 + 4;
+                slot = (y * 2 + hh) * 5 + k;
+            } else {
+                int t = u - 4 * LK_BCHAIN, y = t / 5, x = 16 + (t - y * 5);
+                i0 = i1 = y * LK_WIN + x;
+                slot = t * 5 + 4;
+            }
+            int y0 = i0 / LK_WIN, x0 = i0 - y0 * LK_WIN;
+            const uint8_t* p = jb + y0 * LK_JPITCH + x0;
+            int jv = p[0] * iw00 + p[1] * iw01 + p[LK_JPITCH] * iw10 + p[LK_JPITCH + 1] * iw11;
+            int d0 = lk_descale(jv, 9) - S.pI[i0];
+            int sx = d0 * S.pdx[i0], sy = d0 * S.pdy[i0];
+            if (i1 != i0) {
+                p += 4;
+                jv = p[0] * iw00 + p[1] * iw01 + p[LK_JPITCH] * iw10 + p[LK_JPITCH + 1] * iw11;
+                int d1 = lk_descale(jv, 9) - S.pI[i1];
+                sx += d1 * S.pdx[i1];   // pmaddwd: exact int32 pair sum, converted once
+                sy += d1 * S.pdy[i1];
+            }
+            S.terms[slot] = (float)sx;
+            S.terms[LK_Q + slot] = (float)sy;
         }
         __syncwarp();
-        float bacc = 0.f;
-        {
-            int comp = lane / 5, c = lane - comp * 5;
-            if (lane < 10) {
-                const int16_t* d = comp ? S.pdy : S.pdx;
-                if (c < 4) {
-#pragma unroll 3
-                    for (int y = 0; y < LK_WIN; y++) {
-#pragma unroll
-                        for (int x0 = 0; x0 < 16; x0 += 8) {
-                            int k = y * LK_WIN + x0 + c;
-                            int s = (int)S.diff[k] * (int)d[k] + (int)S.diff[k + 4] * (int)d[k + 4];
-                            bacc += (float)s;
-                        }
-                    }
-                } else {
-#pragma unroll 3
-                    for (int y = 0; y < LK_WIN; y++) {
-#pragma unroll
-                        for (int x = 16; x < LK_WIN; x++) {
-                            int k = y * LK_WIN + x;
-                            bacc += (float)((int)S.diff[k] * (int)d[k]);
-                        }
-                    }
-                }
-            }
-        }
+        const float bacc = lk_chain(S.terms, lane, 2);
         float bb[2];
 #pragma unroll
         for (int comp = 0; comp < 2; comp++) {
@@ -242,6 +265,8 @@ __device__ __forceinline__ void lk_track_point(LKSmem& S, int lane, const Pyrami
 {
     status = 1;
     float nx = 0.f, ny = 0.f;
+    for (int i = lane; i < 3 * LK_Q; i += 32) S.terms[i] = 0.f;    // chain padding must read +0.0f
+    __syncwarp();
     for (int l = max_level; l >= 0; l--) {
         float sc = (float)(1. / (double)(1 << l));
         float px = p.x * sc, py = p.y * sc;

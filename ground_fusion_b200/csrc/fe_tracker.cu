@@ -294,8 +294,8 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     for (int l = 0; l < 4; l++) {
         t->lw[l] = lw; t->lh[l] = lh; t->lp[l] = align_up(lw, 16);
         for (int s = 0; s < 2; s++) {
-            GF_CUDA(cudaMalloc(&t->d_pyr[s][l], (size_t)t->lp[l] * lh));
-            GF_CUDA(cudaMemset(t->d_pyr[s][l], 0, (size_t)t->lp[l] * lh));
+            GF_CUDA(cudaMalloc(&t->d_pyr[s][l], (size_t)t->lp[l] * lh + 16));   // +16: aligned window loads may overrun the last row by <4 B
+            GF_CUDA(cudaMemset(t->d_pyr[s][l], 0, (size_t)t->lp[l] * lh + 16));
         }
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
     }
@@ -563,7 +563,7 @@ struct DevBuf {
 static int upload_image(const uint8_t* src, int w, int h, DevBuf& d, int& pitch)
 {
     pitch = align_up(w, 16);
-    int rc = d.alloc((size_t)pitch * h);
+    int rc = d.alloc((size_t)pitch * h + 16);
     if (rc) return rc;
     GF_CUDA(cudaMemcpy2D(d.p, pitch, src, w, w, h, cudaMemcpyHostToDevice));
     return GF_OK;
@@ -618,7 +618,7 @@ int gf_stage_lk(int device, const uint8_t* prev, const uint8_t* next, int w, int
             int pitch = align_up(lw, 16);
             if (l == 0) { rc = upload_image(k ? next : prev, w, h, lv[k][0], pitch); if (rc) return rc; }
             else {
-                rc = lv[k][l].alloc((size_t)pitch * lh); if (rc) return rc;
+                rc = lv[k][l].alloc((size_t)pitch * lh + 16); if (rc) return rc;
                 dim3 g((lw + PD_TX - 1) / PD_TX, (lh + PD_TY - 1) / PD_TY), b(PD_TX, PD_TY);
                 k_pyr_down<<<g, b>>>(P[k].lv[l - 1], lv[k][l].as<uint8_t>(), lw, lh, pitch); GF_LAUNCHED();
             }
