@@ -26,7 +26,7 @@ constexpr int LK_IPITCH = 32;             // bytes per staged I row (24 + up to 
 constexpr int LK_SCH = 22;                // integer positions needing a derivative
 constexpr int LK_JR = 40;                 // cached J region (window 22 + 9 px drift each side)
 constexpr int LK_JPITCH = 48;             // bytes per staged J row (40 + up to 3 bytes of alignment slack)
-constexpr int LK_WARPS = 2;                // features per CTA: one warp per scheduler, CTAs spread over the SMs
+constexpr int LK_THREADS = 128;            // one CTA of 4 warps per feature: one warp per SM scheduler, ~one feature per SM
 constexpr int LK_CHAIN = 84, LK_TAIL = 105;        // terms per SIMD-lane chain / tail chain of the A sums
 constexpr int LK_BCHAIN = 42;                       // pair terms per chain of the b sums
 constexpr int LK_AT = 4 * LK_CHAIN + LK_TAIL;       // 441 terms per A quantity
@@ -41,6 +41,7 @@ struct __align__(16) LKSmem {
     int16_t pdy[LK_NPIX + 1];
     uint8_t jreg[LK_JR * LK_JPITCH];
     float terms[3 * LK_Q];                 // [quantity][step][chain]; slots beyond a chain's length hold +0.0f (x + 0 is exact)
+    float sums[4];                         // chain results broadcast from warp 0
 };
 
 __device__ __forceinline__ int lk_descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
@@ -57,25 +58,53 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 // Inside the image: aligned 32-bit loads, the first needed column sits at byte offset (x0 & 3), returned.
 // Touching the border: REFLECT_101 byte gathers, offset 0.
 template <int RW, int RH, int DP>
-__device__ __forceinline__ int lk_stage(uint8_t* dst, const Level& L, int x0, int y0, int lane)
+__device__ __forceinline__ int lk_stage(uint8_t* dst, const Level& L, int x0, int y0, int tid)
 {
     if (x0 >= 0 && y0 >= 0 && x0 + RW <= L.w && y0 + RH <= L.h) {
         const int xa = x0 & ~3, xoff = x0 - xa;
         constexpr int WPR = DP / 4;                      // words per staged row
         const int need = (xoff + RW + 3) >> 2;           // words actually needed per row
         uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        for (int i = lane; i < RH * WPR; i += 32) {
+        for (int i = tid; i < RH * WPR; i += LK_THREADS) {
             int r = i / WPR, c = i - r * WPR;
             if (c < need) d32[i] = __ldg(reinterpret_cast<const uint32_t*>(L.ptr + (size_t)(y0 + r) * L.pitch + xa) + c);
         }
         return xoff;
     }
-    for (int i = lane; i < RW * RH; i += 32) {
+    for (int i = tid; i < RW * RH; i += LK_THREADS) {
         int r = i / RW, c = i - r * RW;
         int yy = reflect101(y0 + r, L.h), xx = reflect101(x0 + c, L.w);
         dst[r * DP + c] = __ldg(L.ptr + (size_t)yy * L.pitch + xx);
     }
     return 0;
+}
+
+// Same staging executed by a subset of the CTA (thread index t of nt), and the byte offset lk_stage would return.
+template <int RW, int RH, int DP>
+__device__ __forceinline__ int lk_stage_part(uint8_t* dst, const Level& L, int x0, int y0, int t, int nt)
+{
+    if (x0 >= 0 && y0 >= 0 && x0 + RW <= L.w && y0 + RH <= L.h) {
+        const int xa = x0 & ~3, xoff = x0 - xa;
+        constexpr int WPR = DP / 4;
+        const int need = (xoff + RW + 3) >> 2;
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+        for (int i = t; i < RH * WPR; i += nt) {
+            int r = i / WPR, c = i - r * WPR;
+            if (c < need) d32[i] = __ldg(reinterpret_cast<const uint32_t*>(L.ptr + (size_t)(y0 + r) * L.pitch + xa) + c);
+        }
+        return xoff;
+    }
+    for (int i = t; i < RW * RH; i += nt) {
+        int r = i / RW, c = i - r * RW;
+        int yy = reflect101(y0 + r, L.h), xx = reflect101(x0 + c, L.w);
+        dst[r * DP + c] = __ldg(L.ptr + (size_t)yy * L.pitch + xx);
+    }
+    return 0;
+}
+template <int RW, int RH>
+__device__ __forceinline__ int lk_stage_offset(const Level& L, int x0, int y0)
+{
+    return (x0 >= 0 && y0 >= 0 && x0 + RW <= L.w && y0 + RH <= L.h) ? (x0 & 3) : 0;
 }
 
 // One sequential float chain per lane: lane (q*5 + c) of the first nq*5 lanes adds the 105 slots of chain c of
@@ -92,8 +121,9 @@ __device__ __forceinline__ float lk_chain(const float* T, int lane, int nq)
     return acc;
 }
 
-// One pyramid level for one point (all 32 lanes call this with identical scalar arguments).
-__device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, const Level& J, float px,
+// One pyramid level for one point.  All LK_THREADS threads of the CTA call this with identical scalar arguments
+// and keep identical copies of the scalar state; warp 0 owns the sequential chains.
+__device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, const Level& J, float px,
                                          float py, float& nx, float& ny, int level, int& status, int& iters)
 {
     const float FLT_SCALE = 1.f / (1 << 20);
@@ -108,11 +138,11 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
     lk_weights(a, b, iw00, iw01, iw10, iw11);
 
     // ---- stage the 24x24 u8 window of I (REFLECT_101) ----
-    __syncwarp();
-    const int ioff = lk_stage<LK_IREG, LK_IREG, LK_IPITCH>(S.ireg, I, ipx - 1, ipy - 1, lane);
-    __syncwarp();
+    __syncthreads();
+    const int ioff = lk_stage<LK_IREG, LK_IREG, LK_IPITCH>(S.ireg, I, ipx - 1, ipy - 1, tid);
+    __syncthreads();
     // ---- Scharr derivative at the 22x22 integer positions (0 outside the image) ----
-    for (int i = lane; i < LK_SCH * LK_SCH; i += 32) {
+    for (int i = tid; i < LK_SCH * LK_SCH; i += LK_THREADS) {
         int r = i / LK_SCH, c = i - r * LK_SCH;
         int X = ipx + c, Y = ipy + r;
         int ix = 0, iy = 0;
@@ -128,9 +158,9 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
         S.sch[2 * i] = (int16_t)ix;
         S.sch[2 * i + 1] = (int16_t)iy;
     }
-    __syncwarp();
+    __syncthreads();
     // ---- bilinear 21x21 patches I*32, (Ix, Iy), and the gradient-matrix terms in chain order ----
-    for (int i = lane; i < LK_NPIX; i += 32) {
+    for (int i = tid; i < LK_NPIX; i += LK_THREADS) {
         int y = i / LK_WIN, x = i - y * LK_WIN;
         const uint8_t* p = S.ireg + (y + 1) * LK_IPITCH + ioff + (x + 1);
         int iv = p[0] * iw00 + p[1] * iw01 + p[LK_IPITCH] * iw10 + p[LK_IPITCH + 1] * iw11;
@@ -147,24 +177,37 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
         S.terms[LK_Q + slot] = (float)(gx * gy);
         S.terms[2 * LK_Q + slot] = (float)(gy * gy);
     }
-    __syncwarp();
-    // ---- gradient matrix, OpenCV lane order ----
-    const float acc = lk_chain(S.terms, lane, 3);
-    __syncwarp();
+    __syncthreads();
+    // ---- gradient matrix, OpenCV lane order: warp 0 runs the 15 chains while warps 1-3 already stage the
+    //      search window of the first iteration (its position does not depend on A) ----
+    float qx = nx - 10.f, qy = ny - 10.f;
+    int jx0 = 0, jy0 = 0, joff = 0;
+    bool jvalid = false;
+    {
+        int iqx = __float2int_rd(qx), iqy = __float2int_rd(qy);
+        const bool inwin = !(iqx < -LK_WIN || iqx >= J.w || iqy < -LK_WIN || iqy >= J.h);
+        if (inwin) { jx0 = iqx - 9; jy0 = iqy - 9; jvalid = true; }
+        if (tid < 32) {
+            const float acc = lk_chain(S.terms, tid, 3);
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                float l0 = __shfl_sync(0xffffffffu, acc, q * 5 + 0), l1 = __shfl_sync(0xffffffffu, acc, q * 5 + 1);
+                float l2 = __shfl_sync(0xffffffffu, acc, q * 5 + 2), l3 = __shfl_sync(0xffffffffu, acc, q * 5 + 3);
+                float t = __shfl_sync(0xffffffffu, acc, q * 5 + 4);
+                if (tid == 0) S.sums[q] = t + ((l0 + l2) + (l1 + l3));
+            }
+        } else if (inwin) {
+            joff = lk_stage_part<LK_JR, LK_JR, LK_JPITCH>(S.jreg, J, jx0, jy0, tid - 32, LK_THREADS - 32);
+        }
+        if (inwin) joff = lk_stage_offset<LK_JR, LK_JR>(J, jx0, jy0);
+    }
+    __syncthreads();
+    float A11 = S.sums[0] * FLT_SCALE, A12 = S.sums[1] * FLT_SCALE, A22 = S.sums[2] * FLT_SCALE;
     // the mismatch chains are 42 pair terms long: clear steps 42..83 of the SIMD chains of the two quantities they reuse
-    for (int i = lane; i < 2 * 4 * (LK_CHAIN - LK_BCHAIN); i += 32) {
+    for (int i = tid; i < 2 * 4 * (LK_CHAIN - LK_BCHAIN); i += LK_THREADS) {
         int q = i / (4 * (LK_CHAIN - LK_BCHAIN)), r = i - q * 4 * (LK_CHAIN - LK_BCHAIN);
         S.terms[q * LK_Q + (LK_BCHAIN + (r >> 2)) * 5 + (r & 3)] = 0.f;
     }
-    float A[3];
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-        float l0 = __shfl_sync(0xffffffffu, acc, q * 5 + 0), l1 = __shfl_sync(0xffffffffu, acc, q * 5 + 1);
-        float l2 = __shfl_sync(0xffffffffu, acc, q * 5 + 2), l3 = __shfl_sync(0xffffffffu, acc, q * 5 + 3);
-        float t = __shfl_sync(0xffffffffu, acc, q * 5 + 4);
-        A[q] = t + ((l0 + l2) + (l1 + l3));
-    }
-    float A11 = A[0] * FLT_SCALE, A12 = A[1] * FLT_SCALE, A22 = A[2] * FLT_SCALE;
     float D = A11 * A22 - A12 * A12;
     float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / 882.f;
     if (minEig < 1e-4f || D < 1.1920928955078125e-07f) {
@@ -173,10 +216,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
     }
     D = 1.f / D;
 
-    float qx = nx - 10.f, qy = ny - 10.f;
     float pdx_ = 0.f, pdy_ = 0.f;
-    int jx0 = 0, jy0 = 0, joff = 0;
-    bool jvalid = false;
     for (int j = 0; j < 30; j++) {
         int iqx = __float2int_rd(qx), iqy = __float2int_rd(qy);
         if (iqx < -LK_WIN || iqx >= J.w || iqy < -LK_WIN || iqy >= J.h) {
@@ -186,17 +226,17 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
         if (!(jvalid && iqx >= jx0 && iqy >= jy0 && iqx + 22 <= jx0 + LK_JR && iqy + 22 <= jy0 + LK_JR)) {
             jx0 = iqx - 9;
             jy0 = iqy - 9;
-            __syncwarp();
-            joff = lk_stage<LK_JR, LK_JR, LK_JPITCH>(S.jreg, J, jx0, jy0, lane);
+            __syncthreads();
+            joff = lk_stage<LK_JR, LK_JR, LK_JPITCH>(S.jreg, J, jx0, jy0, tid);
             jvalid = true;
-            __syncwarp();
         }
         a = qx - (float)iqx;
         b = qy - (float)iqy;
         lk_weights(a, b, iw00, iw01, iw10, iw11);
         const uint8_t* jb = S.jreg + (iqy - jy0) * LK_JPITCH + joff + (iqx - jx0);
+        __syncthreads();    // staged window and cleared/previous terms are visible; previous sums have been read
         // ---- mismatch terms in chain order: 168 pmaddwd pair units (row y, k in 0..3, half h) + 105 tail pixels ----
-        for (int u = lane; u < LK_BT; u += 32) {
+        for (int u = tid; u < LK_BT; u += LK_THREADS) {
             int i0, i1, slot;
             if (u < 4 * LK_BCHAIN) {
                 int y = u >> 3, r = u & 7, k = r & 3, hh = r >> 2;
@@ -223,20 +263,21 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
             S.terms[slot] = (float)sx;
             S.terms[LK_Q + slot] = (float)sy;
         }
-        __syncwarp();
-        const float bacc = lk_chain(S.terms, lane, 2);
-        float bb[2];
+        __syncthreads();
+        if (tid < 32) {
+            const float bacc = lk_chain(S.terms, tid, 2);
 #pragma unroll
-        for (int comp = 0; comp < 2; comp++) {
-            float c0 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 0), c1 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 1);
-            float c2 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 2), c3 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 3);
-            float t = __shfl_sync(0xffffffffu, bacc, comp * 5 + 4);
-            float x02 = c0 + c2, x13 = c1 + c3;
-            bb[comp] = t + ((x02 + 0.f) + (x13 + 0.f));
+            for (int comp = 0; comp < 2; comp++) {
+                float c0 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 0), c1 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 1);
+                float c2 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 2), c3 = __shfl_sync(0xffffffffu, bacc, comp * 5 + 3);
+                float t = __shfl_sync(0xffffffffu, bacc, comp * 5 + 4);
+                float x02 = c0 + c2, x13 = c1 + c3;
+                if (tid == 0) S.sums[comp] = t + ((x02 + 0.f) + (x13 + 0.f));
+            }
         }
-        __syncwarp();
+        __syncthreads();
         iters++;
-        float b1 = bb[0] * FLT_SCALE, b2 = bb[1] * FLT_SCALE;
+        float b1 = S.sums[0] * FLT_SCALE, b2 = S.sums[1] * FLT_SCALE;
         float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
         qx += dx;
         qy += dy;
@@ -259,14 +300,15 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int lane, const Level& I, co
 }
 
 // Whole pyramid for one point.  init is only read when use_init.
-__device__ __forceinline__ void lk_track_point(LKSmem& S, int lane, const Pyramid& I, const Pyramid& J,
+__device__ __forceinline__ void lk_track_point(LKSmem& S, int tid, const Pyramid& I, const Pyramid& J,
                                                float2 p, float2 init, bool use_init, int max_level,
                                                float2& out, int& status, int& iters)
 {
     status = 1;
     float nx = 0.f, ny = 0.f;
-    for (int i = lane; i < 3 * LK_Q; i += 32) S.terms[i] = 0.f;    // chain padding must read +0.0f
-    __syncwarp();
+    __syncthreads();
+    for (int i = tid; i < 3 * LK_Q; i += LK_THREADS) S.terms[i] = 0.f;    // chain padding must read +0.0f
+    __syncthreads();
     for (int l = max_level; l >= 0; l--) {
         float sc = (float)(1. / (double)(1 << l));
         float px = p.x * sc, py = p.y * sc;
@@ -274,7 +316,7 @@ __device__ __forceinline__ void lk_track_point(LKSmem& S, int lane, const Pyrami
             if (use_init) { nx = init.x * sc; ny = init.y * sc; }
             else { nx = px; ny = py; }
         } else { nx = nx * 2.f; ny = ny * 2.f; }
-        lk_level(S, lane, I.lv[l], J.lv[l], px, py, nx, ny, l, status, iters);
+        lk_level(S, tid, I.lv[l], J.lv[l], px, py, nx, ny, l, status, iters);
     }
     out = make_float2(nx, ny);
 }

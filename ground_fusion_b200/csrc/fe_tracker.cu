@@ -29,50 +29,47 @@ constexpr int NMS_CELL_BYTES = 16;   // head key + two accepted buffers per cell
 // ------------------------------------------------------------------------------------------------
 // kernels that need the LK device code
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LK_WARPS * 32) k_lk_stage(Pyramid I, Pyramid J, const float2* prev_pts, float2* next_pts,
-                                                            int n, int max_level, int use_init, uint8_t* status)
+__global__ void __launch_bounds__(LK_THREADS) k_lk_stage(Pyramid I, Pyramid J, const float2* prev_pts, float2* next_pts,
+                                                         int n, int max_level, int use_init, uint8_t* status)
 {
-    __shared__ LKSmem sm[LK_WARPS];
-    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int i = blockIdx.x * LK_WARPS + wid;
+    __shared__ LKSmem sm;
+    const int tid = threadIdx.x, i = blockIdx.x;
     if (i >= n) return;
     float2 p = prev_pts[i], init = use_init ? next_pts[i] : p, out;
     int st, iters = 0;
-    lk_track_point(sm[wid], lane, I, J, p, init, use_init != 0, max_level, out, st, iters);
-    if (lane == 0) { next_pts[i] = out; status[i] = (uint8_t)st; }
+    lk_track_point(sm, tid, I, J, p, init, use_init != 0, max_level, out, st, iters);
+    if (tid == 0) { next_pts[i] = out; status[i] = (uint8_t)st; }
 }
 
 // Prediction pass (feature_tracker.cpp:118-124): maxLevel 1 seeded with predict_pts; counts successes.
-__global__ void __launch_bounds__(LK_WARPS * 32) k_lk_pred(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa)
+__global__ void __launch_bounds__(LK_THREADS) k_lk_pred(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa)
 {
-    __shared__ LKSmem sm[LK_WARPS];
-    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int i = blockIdx.x * LK_WARPS + wid;
+    __shared__ LKSmem sm;
+    const int tid = threadIdx.x, i = blockIdx.x;
     if (i >= sc->n_prev) return;
     float2 out;
     int st, iters = 0;
-    lk_track_point(sm[wid], lane, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st, iters);
-    if (lane == 0) { fa.cur_pts[i] = out; fa.status[i] = (uint8_t)st; if (st) atomicAdd(&sc->pred_succ, 1); atomicAdd(&sc->lk_iters, iters); }
+    lk_track_point(sm, tid, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st, iters);
+    if (tid == 0) { fa.cur_pts[i] = out; fa.status[i] = (uint8_t)st; if (st) atomicAdd(&sc->pred_succ, 1); atomicAdd(&sc->lk_iters, iters); }
 }
 
 // Forward LK (3 levels) + reverse check (1 level, USE_INITIAL_FLOW) + inBorder + grey<=250
-// (feature_tracker.cpp:118-168).  One warp per feature.
-__global__ void __launch_bounds__(LK_WARPS * 32) k_track(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa,
-                                                         const FrameParams* fp, int flow_back)
+// (feature_tracker.cpp:118-168).  One CTA of 4 warps per feature.
+__global__ void __launch_bounds__(LK_THREADS) k_track(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa,
+                                                      const FrameParams* fp, int flow_back)
 {
-    __shared__ LKSmem sm[LK_WARPS];
-    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int i = blockIdx.x * LK_WARPS + wid;
+    __shared__ LKSmem sm;
+    const int tid = threadIdx.x, i = blockIdx.x;
     if (i >= sc->n_prev) return;
     const float2 p = fa.prev_pts[i];
     float2 q;
     int st, iters = 0;
     if (fp->has_pred && sc->pred_succ >= 10) { q = fa.cur_pts[i]; st = fa.status[i]; }
-    else lk_track_point(sm[wid], lane, prev, cur, p, p, false, 3, q, st, iters);
+    else lk_track_point(sm, tid, prev, cur, p, p, false, 3, q, st, iters);
     if (flow_back) {
         float2 r;
         int rst;
-        lk_track_point(sm[wid], lane, cur, prev, q, p, true, 1, r, rst, iters);
+        lk_track_point(sm, tid, cur, prev, q, p, true, 1, r, rst, iters);
         double dx = (double)(p.x - r.x), dy = (double)(p.y - r.y);
         st = (st && rst && sqrt(dx * dx + dy * dy) <= 0.5) ? 1 : 0;
     }
@@ -86,7 +83,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) k_track(Pyramid prev, Pyramid c
         int grey = (p_u >= 0 && p_u < row && p_v >= 0 && p_v < col) ? cur.lv[0].ptr[(size_t)p_u * cur.lv[0].pitch + p_v] : 0;
         if (grey > 250) st = 0;
     }
-    if (lane == 0) { fa.cur_pts[i] = q; fa.status[i] = (uint8_t)st; atomicAdd(&sc->lk_iters, iters); }
+    if (tid == 0) { fa.cur_pts[i] = q; fa.status[i] = (uint8_t)st; atomicAdd(&sc->lk_iters, iters); }
 }
 
 // setPrediction (feature_tracker.cpp:1006-1027)
@@ -390,9 +387,9 @@ static int enqueue_frame(gf_tracker* t, double time, bool depth_valid)
     rc = enqueue_pyramid(s, t, cur);
     if (rc) return rc;
     GF_MARK(1);
-    const int lk_grid = (t->cfg.max_cnt + LK_WARPS - 1) / LK_WARPS;
-    if (t->has_pred) { k_lk_pred<<<lk_grid, LK_WARPS * 32, 0, s>>>(Pp, Pc, t->d_sc, t->fa); GF_LAUNCHED(); }
-    k_track<<<lk_grid, LK_WARPS * 32, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp, t->cfg.flow_back); GF_LAUNCHED();
+    const int lk_grid = t->cfg.max_cnt;
+    if (t->has_pred) { k_lk_pred<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa); GF_LAUNCHED(); }
+    k_track<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp, t->cfg.flow_back); GF_LAUNCHED();
     GF_MARK(2);
     k_compact_setmask<<<1, FE_CAP, 0, s>>>(t->d_sc, t->fa, t->cfg.min_dist); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
@@ -630,7 +627,7 @@ int gf_stage_lk(int device, const uint8_t* prev, const uint8_t* next, int w, int
     if ((rc = dp.alloc((size_t)n * 8)) || (rc = dq.alloc((size_t)n * 8)) || (rc = dst.alloc(n))) return rc;
     GF_CUDA(cudaMemcpy(dp.p, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice));
     GF_CUDA(cudaMemcpy(dq.p, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice));
-    k_lk_stage<<<(n + LK_WARPS - 1) / LK_WARPS, LK_WARPS * 32>>>(P[0], P[1], dp.as<float2>(), dq.as<float2>(), n, max_level, use_initial_flow, dst.as<uint8_t>()); GF_LAUNCHED();
+    k_lk_stage<<<n, LK_THREADS>>>(P[0], P[1], dp.as<float2>(), dq.as<float2>(), n, max_level, use_initial_flow, dst.as<uint8_t>()); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpy(next_pts, dq.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     GF_CUDA(cudaMemcpy(status, dst.p, n, cudaMemcpyDeviceToHost));
