@@ -171,35 +171,24 @@ __global__ void __launch_bounds__(EIG_TX) k_min_eig(Level img, float* eig, int e
     spec_end[so + 2 * (size_t)w] = S2;
 }
 
-// Slow exact path for one column: D at image row r (REFLECT_101 at the cov level), from global memory.
-__device__ inline void eig_rowsum_global(const Level& img, int r, int x, double& d0, double& d1, double& d2)
-{
-    const int w = img.w, h = img.h;
-    int rr = reflect101(r, h);
-    float cx[3], cy[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        int cc = reflect101(x - 1 + k, w);
-        int p[3][3];
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-                p[j][i] = __ldg(img.ptr + (size_t)reflect101(rr - 1 + j, h) * img.pitch + reflect101(cc - 1 + i, w));
-        sobel_dxdy(p[0][0], p[0][1], p[0][2], p[1][0], p[1][1], p[1][2], p[2][0], p[2][1], p[2][2], cc >= (w / 32) * 32, cx[k], cy[k]);
-    }
-    d0 = ((double)(cx[0] * cx[0]) + (double)(cx[1] * cx[1])) + (double)(cx[2] * cx[2]);
-    d1 = ((double)(cx[0] * cy[0]) + (double)(cx[1] * cy[1])) + (double)(cx[2] * cy[2]);
-    d2 = ((double)(cy[0] * cy[0]) + (double)(cy[1] * cy[1])) + (double)(cy[2] * cy[2]);
-}
-
-// One thread per column: walk the bands, replay those whose speculated start state was wrong.
+// One thread per column: check every band's speculated start against the end of the band above (independent
+// loads), and replay the rare mismatching bands from the true state.  The replay first pulls the band's
+// (BAND+4) x 5 pixel neighbourhood into local memory with independent loads, then runs without touching HBM.
 __global__ void k_eig_verify(Level img, float* eig, int epitch, const double* spec_start,
                              const double* spec_end, int nbands, int* fixups)
 {
     const int w = img.w, h = img.h;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
+    {   // common case: nothing to do
+        bool any = false;
+#pragma unroll 4
+        for (int b = 1; b < nbands; b++) {
+            size_t so = ((size_t)b * 3) * w + x, sp = ((size_t)(b - 1) * 3) * w + x;
+            any |= (spec_start[so] != spec_end[sp]) | (spec_start[so + w] != spec_end[sp + w]) | (spec_start[so + 2 * (size_t)w] != spec_end[sp + 2 * (size_t)w]);
+        }
+        if (!any) return;
+    }
     double t0 = spec_end[x], t1 = spec_end[(size_t)w + x], t2 = spec_end[2 * (size_t)w + x];
     for (int b = 1; b < nbands; b++) {
         size_t so = ((size_t)b * 3) * w + x;
@@ -209,13 +198,39 @@ __global__ void k_eig_verify(Level img, float* eig, int epitch, const double* sp
             continue;
         }
         atomicAdd(fixups, 1);
-        int y0 = b * EIG_BAND, nrows = min(EIG_BAND, h - y0);
+        const int y0 = b * EIG_BAND, nrows = min(EIG_BAND, h - y0);
+        // pixels of image rows y0-2 .. y0+BAND+1 and columns x-2 .. x+2 (image-level REFLECT_101 applied here)
+        uint8_t P[EIG_BAND + 4][5];
+#pragma unroll
+        for (int r = 0; r < EIG_BAND + 4; r++) {
+            int yy = min(max(y0 - 2 + r, -1), h); yy = reflect101(yy, h);
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                int xx = min(max(x - 2 + c, -1), w); xx = reflect101(xx, w);
+                P[r][c] = __ldg(img.ptr + (size_t)yy * img.pitch + xx);
+            }
+        }
+        // D at image row r (REFLECT_101 at the cov level) for this column
+        auto rowsum = [&](int r, double& d0, double& d1, double& d2) {
+            const int rr = reflect101(min(max(r, -1), h), h);
+            float cx[3], cy[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int cc = reflect101(min(max(x - 1 + k, -1), w), w);
+                const int pr = rr - (y0 - 2), pc = cc - (x - 2);          // centre of the 3x3 neighbourhood inside P
+                sobel_dxdy(P[pr - 1][pc - 1], P[pr - 1][pc], P[pr - 1][pc + 1], P[pr][pc - 1], P[pr][pc], P[pr][pc + 1],
+                           P[pr + 1][pc - 1], P[pr + 1][pc], P[pr + 1][pc + 1], cc >= (w / 32) * 32, cx[k], cy[k]);
+            }
+            d0 = ((double)(cx[0] * cx[0]) + (double)(cx[1] * cx[1])) + (double)(cx[2] * cx[2]);
+            d1 = ((double)(cx[0] * cy[0]) + (double)(cx[1] * cy[1])) + (double)(cx[2] * cy[2]);
+            d2 = ((double)(cy[0] * cy[0]) + (double)(cy[1] * cy[1])) + (double)(cy[2] * cy[2]);
+        };
         double a0, a1, a2, b0, b1, b2;
-        eig_rowsum_global(img, y0 - 1, x, a0, a1, a2);
-        eig_rowsum_global(img, y0, x, b0, b1, b2);
+        rowsum(y0 - 1, a0, a1, a2);
+        rowsum(y0, b0, b1, b2);
         for (int k = 0; k < nrows; k++) {
             double c0, c1, c2;
-            eig_rowsum_global(img, y0 + k + 1, x, c0, c1, c2);
+            rowsum(y0 + k + 1, c0, c1, c2);
             double u0 = t0 + c0, u1 = t1 + c1, u2 = t2 + c2;
             eig[(size_t)(y0 + k) * epitch + x] = eig_from_box(u0, u1, u2);
             t0 = u0 - a0; t1 = u1 - a1; t2 = u2 - a2;

@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
     __shared__ uint8_t st[FE_CAP];
     __shared__ int warp_sums[32];
     __shared__ int s_m;
+    __shared__ SortWork swork;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = sc->n_prev;
     // ---- reduceVector (stable compaction by status) ----
@@ -90,9 +91,8 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
         elems[p] = ((sort_elem)(unsigned)cnt << 32) | (unsigned)p;
     }
     __syncthreads();
-    // ---- std::sort replica (single thread: the permutation is a property of the sequential algorithm) ----
-    if (tid == 0) setmask_sort(elems, m);
-    __syncthreads();
+    // ---- std::sort replica: same comparisons and moves as libstdc++, independent ranges replayed in parallel ----
+    setmask_sort_parallel(elems, m, swork);
     int src = 0;
     if (tid < m) {
         src = (int)(elems[tid] & 0xffffffffu);
@@ -153,32 +153,59 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
 }
 
 // ------------------------------------------------------------------------------------------------
-// mask (pre-set to 255): zero the integer disk d^2 <= r^2 around each kept feature's rounded centre
-__global__ void k_mask_disks(const TrackScalars* sc, const float2* kept_pts, uint8_t* mask, int w, int h,
-                             int mpitch, int r)
+// The mask goodFeaturesToTrack sees (setMask, feature_tracker.cpp:56-83) is 255 except inside the integer disks
+// d^2 <= r^2 around the rounded centres of the kept features (cv::circle == integer disk).  It is never
+// materialised: every CTA collects the kept features that can touch its tile into shared memory and tests pixels
+// against that short list.
+constexpr int MASK_TX = 64, MASK_TY = 16, MASK_LIST = 64;
+struct MaskTile { short2 pt[MASK_LIST]; int n; int overflow; };
+
+__device__ __forceinline__ void mask_tile_load(MaskTile& M, const TrackScalars* sc, const float2* kept, int x0, int y0, int r)
 {
-    if ((int)blockIdx.x >= sc->n_kept) return;
-    float2 p = kept_pts[blockIdx.x];
-    int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
-    int side = 2 * r + 1;
-    for (int i = threadIdx.x; i < side * side; i += blockDim.x) {
-        int dy = i / side - r, dx = i - (i / side) * side - r;
-        int x = cx + dx, y = cy + dy;
-        if (dx * dx + dy * dy <= r * r && x >= 0 && x < w && y >= 0 && y < h) mask[(size_t)y * mpitch + x] = 0;
+    if (threadIdx.x == 0) { M.n = 0; M.overflow = 0; }
+    __syncthreads();
+    const int nk = sc->n_kept;
+    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+        float2 p = kept[i];
+        int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
+        if (cx >= x0 - r && cx < x0 + MASK_TX + r && cy >= y0 - r && cy < y0 + MASK_TY + r) {
+            int k = atomicAdd(&M.n, 1);
+            if (k < MASK_LIST) M.pt[k] = make_short2((short)cx, (short)cy); else M.overflow = 1;
+        }
     }
+    __syncthreads();
+}
+__device__ __forceinline__ bool mask_open(const MaskTile& M, const TrackScalars* sc, const float2* kept, int x, int y, int r2)
+{
+    if (M.overflow) {      // more neighbours than the list holds (cannot happen for features that are > r apart): exact slow path
+        for (int i = 0; i < sc->n_kept; i++) {
+            int dx = x - __float2int_rn(kept[i].x), dy = y - __float2int_rn(kept[i].y);
+            if (dx * dx + dy * dy <= r2) return false;
+        }
+        return true;
+    }
+    const int n = M.n;
+    for (int i = 0; i < n; i++) {
+        int dx = x - M.pt[i].x, dy = y - M.pt[i].y;
+        if (dx * dx + dy * dy <= r2) return false;
+    }
+    return true;
 }
 
-// masked maximum of the eig map (cv::minMaxLoc(eig, 0, &maxVal, 0, 0, mask))
-__global__ void __launch_bounds__(256) k_eig_max(TrackScalars* sc, const float* eig, int epitch,
-                                                 const uint8_t* mask, int mpitch, int w, int h)
+// masked maximum of the eig map (cv::minMaxLoc(eig, 0, &maxVal, 0, 0, mask)); one 64x16 tile per CTA of 256 threads
+__global__ void __launch_bounds__(256) k_eig_max(TrackScalars* sc, const float2* kept, const float* eig, int epitch, int w, int h, int r)
 {
+    __shared__ MaskTile M;
+    __shared__ unsigned int wb[8];
+    const int x0 = blockIdx.x * MASK_TX, y0 = blockIdx.y * MASK_TY;
+    mask_tile_load(M, sc, kept, x0, y0, r);
     unsigned int best = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x) {
-        int y = i / w, x = i - y * w;
-        if (mask[(size_t)y * mpitch + x]) best = max(best, float_order_key(eig[(size_t)y * epitch + x]));
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int yy = ty; yy < MASK_TY; yy += 4) {
+        int x = x0 + tx, y = y0 + yy;
+        if (x < w && y < h && mask_open(M, sc, kept, x, y, r * r)) best = max(best, float_order_key(eig[(size_t)y * epitch + x]));
     }
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-    __shared__ unsigned int wb[8];
     if ((threadIdx.x & 31) == 0) wb[threadIdx.x >> 5] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -198,18 +225,24 @@ struct NmsGrid {
 };
 
 // threshold(TOZERO, 0.01*max) -> dilate 3x3 -> val != 0 && val == dilated && mask, on the interior
-__global__ void __launch_bounds__(256) k_candidates(TrackScalars* sc, const float* eig, int epitch,
-                                                    const uint8_t* mask, int mpitch, int w, int h, NmsGrid g)
+__global__ void __launch_bounds__(256) k_candidates(TrackScalars* sc, const float2* kept, const float* eig, int epitch,
+                                                    int w, int h, int r, NmsGrid g)
 {
-    int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    __shared__ MaskTile M;
+    const int x0 = blockIdx.x * MASK_TX, y0 = blockIdx.y * MASK_TY;
+    mask_tile_load(M, sc, kept, x0, y0, r);
+    const double maxVal = sc->max_key ? (double)float_from_order_key(sc->max_key) : 0.0;
+    const float thr = (float)(maxVal * 0.01);
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+#pragma unroll 1
+    for (int yy = ty; yy < MASK_TY; yy += 4) {
+    const int x = x0 + tx, y = y0 + yy;
     bool is_cand = false;
     float v = 0.f;
     if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
-        double maxVal = sc->max_key ? (double)float_from_order_key(sc->max_key) : 0.0;
-        float thr = (float)(maxVal * 0.01);
         const float* e = eig + (size_t)y * epitch + x;
         v = __ldg(e);
-        if (v > thr && v != 0.f && mask[(size_t)y * mpitch + x]) {
+        if (v > thr && v != 0.f && mask_open(M, sc, kept, x, y, r * r)) {
             float m = fmaxf(fmaxf(__ldg(e - 1), __ldg(e + 1)), fmaxf(__ldg(e - epitch), __ldg(e + epitch)));
             m = fmaxf(m, fmaxf(fmaxf(__ldg(e - epitch - 1), __ldg(e - epitch + 1)), fmaxf(__ldg(e + epitch - 1), __ldg(e + epitch + 1))));
             is_cand = !(m > v);   // a larger neighbour is itself > thr, so the dilated value would exceed v
@@ -222,6 +255,7 @@ __global__ void __launch_bounds__(256) k_candidates(TrackScalars* sc, const floa
         if (lane == (__ffs(bal) - 1)) base = atomicAdd(&sc->n_cand, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
         if (is_cand) g.cand_key[base + __popc(bal & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+    }
     }
 }
 
@@ -351,13 +385,14 @@ struct OutHeader { int n_out, n_prev, n_tracked, n_kept, n_new, n_cand, nms_roun
 // next-frame state.  Single CTA of 1024 threads; dynamic shared memory for the cell grid (see nms_cells).
 __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, FeatArrays fa, NmsGrid g, int w, int max_cnt, int min_dist,
                                                           CamParams cam, const double* dt_ptr, const uint16_t* depth, int dpitch /*elements*/,
-                                                          int depth_cam, int h, OutHeader* out_hdr, gf_obs* out_obs)
+                                                          int depth_cam_cfg, const int* depth_valid_ptr, int h, OutHeader* out_hdr, gf_obs* out_obs)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ unsigned long long keys[FE_SORT_CAP];
     const int tid = threadIdx.x;
     nms_cells(sc, g, w, min_dist, dyn_smem);
     const double dt = dt_ptr ? *dt_ptr : 1.0;
+    const int depth_cam = depth_cam_cfg && depth_valid_ptr && *depth_valid_ptr;
     const int ncand = sc->n_cand;
     const int n_kept = sc->n_kept;
     const int want = max(max_cnt - n_kept, 0);

@@ -146,4 +146,75 @@ GF_HD inline void setmask_sort(sort_elem* v, int n)
         sm_insertion_sort(v, v + n);
 }
 
+
+#ifdef __CUDACC__
+// Parallel replay of setmask_sort by one CTA (call from all threads; v and the work arrays live in shared memory).
+// __introsort_loop recurses on disjoint ranges [first, cut) and [cut, last) with the same decremented depth limit,
+// so all ranges of one recursion level can be partitioned concurrently, one thread each, performing exactly the
+// comparisons and swaps of the sequential code.  __final_insertion_sort then only moves an element within its
+// leaf range (every element left of a cut is >= every element right of it and the comparator is strict), so each
+// leaf is finished by one thread: the leaf that contains index 0 with the guarded __insertion_sort logic, the others
+// with __unguarded_linear_insert (their left neighbour is the sentinel, as in the sequential run).
+constexpr int SORT_PAR_MAX = 512;   // larger inputs use the sequential replay (leaf/range tables are sized for this)
+struct SortWork { int first[2][128], last[2][128], depth[2][128], n[2]; short leaf_first[SORT_PAR_MAX], leaf_last[SORT_PAR_MAX]; int nleaf; };
+
+__device__ inline void setmask_sort_parallel(sort_elem* v, int n, SortWork& W)
+{
+    const int tid = threadIdx.x;
+    if (n <= 0) return;
+    if (n > SORT_PAR_MAX) { if (tid == 0) setmask_sort(v, n); __syncthreads(); return; }
+    if (tid == 0) {
+        int lg = 0;
+        for (int t = n; t > 1; t >>= 1) lg++;
+        W.first[0][0] = 0; W.last[0][0] = n; W.depth[0][0] = 2 * lg; W.n[0] = 1; W.n[1] = 0; W.nleaf = 0;
+    }
+    __syncthreads();
+    int cur = 0;
+    while (true) {
+        const int nr = W.n[cur];
+        if (nr == 0) break;
+        if (tid < nr) {
+            int first = W.first[cur][tid], last = W.last[cur][tid], depth = W.depth[cur][tid];
+            if (last - first > 16) {
+                if (depth == 0) {
+                    sm_heap_sort(v + first, v + last);                 // __partial_sort(first, last, last): range is final
+                    int k = atomicAdd(&W.nleaf, 1); W.leaf_first[k] = (short)first; W.leaf_last[k] = (short)last;
+                } else {
+                    --depth;
+                    int cut = (int)(sm_partition_pivot(v + first, v + last) - v);
+                    int k = atomicAdd(&W.n[cur ^ 1], 2);
+                    W.first[cur ^ 1][k] = first; W.last[cur ^ 1][k] = cut; W.depth[cur ^ 1][k] = depth;
+                    W.first[cur ^ 1][k + 1] = cut; W.last[cur ^ 1][k + 1] = last; W.depth[cur ^ 1][k + 1] = depth;
+                }
+            } else if (last > first) {
+                int k = atomicAdd(&W.nleaf, 1); W.leaf_first[k] = (short)first; W.leaf_last[k] = (short)last;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) W.n[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
+    }
+    // final insertion sort, leaf by leaf
+    const int nl = W.nleaf;
+    if (tid < nl) {
+        const int first = W.leaf_first[tid], last = W.leaf_last[tid];
+        for (int i = first; i < last; i++) {
+            if (i == 0) continue;
+            // __final_insertion_sort: elements 1..15 use the guarded form (compare with *begin first), the rest the unguarded one
+            if (i < 16 && n > 16 ? true : (n <= 16)) {
+                if (sm_comp(v[i], v[0])) {
+                    sort_elem val = v[i];
+                    for (int p = i; p != 0; --p) v[p] = v[p - 1];
+                    v[0] = val;
+                    continue;
+                }
+            }
+            sm_unguarded_linear_insert(v + i);
+        }
+    }
+    __syncthreads();
+}
+#endif
+
 }  // namespace gf

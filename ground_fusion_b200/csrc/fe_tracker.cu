@@ -10,6 +10,7 @@
 //   s_aux : (fork after H2D) k_min_eig -> k_eig_verify                       [independent of LK/mask]
 //
 // All feature state (prev_pts, ids, track_cnt, undistorted points, n_id) lives in HBM between frames.
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -156,6 +157,9 @@ struct gf_tracker {
     cudaEvent_t ev_st[GF_FE_STAGES + 2];   // stage boundaries on s_main (0..6) + aux start/end (7,8)
     bool profiling;
     float stage_ms[GF_FE_STAGES];
+    cudaGraphExec_t graph[4];            // frame body, keyed by (pyramid slot, prediction pending)
+    int graph_kernels[4];
+    bool use_graph;
     uint8_t* d_pyr[2][4];
     int lw[4], lh[4], lp[4];
     uint16_t* d_depth; int depth_pitch_el;
@@ -229,11 +233,10 @@ static void free_nms_grid(NmsGrid& g)
 static int enqueue_gftt_select(cudaStream_t s, TrackScalars* d_sc, const float2* kept_pts, int max_kept, const float* d_eig,
                                int epitch, uint8_t* d_mask, int mpitch, int w, int h, int min_dist, NmsGrid& grid, size_t cells)
 {
-    GF_CUDA(cudaMemsetAsync(d_mask, 255, (size_t)mpitch * h, s));
-    if (max_kept > 0) { k_mask_disks<<<max_kept, 256, 0, s>>>(d_sc, kept_pts, d_mask, w, h, mpitch, min_dist); GF_LAUNCHED(); }
-    k_eig_max<<<296, 256, 0, s>>>(d_sc, d_eig, epitch, d_mask, mpitch, w, h); GF_LAUNCHED();
-    dim3 cg((w + 31) / 32, (h + 7) / 8);
-    k_candidates<<<cg, 256, 0, s>>>(d_sc, d_eig, epitch, d_mask, mpitch, w, h, grid); GF_LAUNCHED();
+    (void)d_mask; (void)mpitch; (void)max_kept; (void)cells; (void)grid;
+    dim3 tg((w + MASK_TX - 1) / MASK_TX, (h + MASK_TY - 1) / MASK_TY);
+    k_eig_max<<<tg, 256, 0, s>>>(d_sc, kept_pts, d_eig, epitch, w, h, min_dist); GF_LAUNCHED();
+    k_candidates<<<tg, 256, 0, s>>>(d_sc, kept_pts, d_eig, epitch, w, h, min_dist, grid); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     return GF_OK;
 }
@@ -330,6 +333,7 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     GF_CUDA(cudaHostAlloc(&t->h_fp, sizeof(FrameParams), cudaHostAllocDefault));
     GF_CUDA(cudaHostAlloc(&t->h_tmp_ids, FE_CAP * sizeof(int), cudaHostAllocDefault));
     GF_CUDA(cudaHostAlloc(&t->h_tmp_xyz, FE_CAP * 3 * sizeof(double), cudaHostAllocDefault));
+    t->use_graph = getenv("GF_NO_GRAPH") == nullptr;
     GF_CUDA(cudaDeviceSynchronize());
     *out = t;
     return GF_OK;
@@ -340,6 +344,7 @@ void gf_tracker_destroy(gf_tracker* t)
     if (!t) return;
     cudaSetDevice(t->device);
     cudaStreamSynchronize(t->s_main); cudaStreamSynchronize(t->s_aux);
+    for (int k = 0; k < 4; k++) if (t->graph[k]) cudaGraphExecDestroy(t->graph[k]);
     for (int s = 0; s < 2; s++) for (int l = 0; l < 4; l++) cudaFree(t->d_pyr[s][l]);
     cudaFree(t->d_depth); cudaFree(t->d_eig); cudaFree(t->d_mask); cudaFree(t->d_spec_start); cudaFree(t->d_spec_end);
     free_nms_grid(t->grid);
@@ -364,19 +369,17 @@ int gf_tracker_host_buffers(gf_tracker* t, uint8_t** gray, uint16_t** depth)
     return GF_OK;
 }
 
-// Everything after the frame is in HBM (d_pyr[cur][0], d_depth).
-static int enqueue_frame(gf_tracker* t, double time, bool depth_valid)
+// The frame body: everything after the frame is in HBM (d_pyr[cur][0], d_depth) and FrameParams are in h_fp.
+// Pure stream work with fixed addresses, so it can be captured into a CUDA graph.
+static int enqueue_body(gf_tracker* t, int cur, bool has_pred)
 {
-    const int cur = t->cur, prev = cur ^ 1;
+    const int prev = cur ^ 1;
     cudaStream_t s = t->s_main;
-    t->h_fp->dt = time - t->prev_time;
-    t->h_fp->has_pred = t->has_pred ? 1 : 0;
-    t->h_fp->depth_valid = depth_valid ? 1 : 0;
     GF_CUDA(cudaMemcpyAsync(t->d_fp, t->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
     Pyramid Pc = make_pyr(t, cur), Pp = make_pyr(t, prev);
-    // fork: min-eig of the new frame does not depend on tracking
 #define GF_MARK(k) do { if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[k], s)); } while (0)
     GF_MARK(0);   // end of upload
+    // fork: min-eig of the new frame does not depend on tracking
     GF_CUDA(cudaEventRecord(t->ev_fork, s));
     GF_CUDA(cudaStreamWaitEvent(t->s_aux, t->ev_fork, 0));
     if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[7], t->s_aux));
@@ -388,7 +391,7 @@ static int enqueue_frame(gf_tracker* t, double time, bool depth_valid)
     if (rc) return rc;
     GF_MARK(1);
     const int lk_grid = t->cfg.max_cnt;
-    if (t->has_pred) { k_lk_pred<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa); GF_LAUNCHED(); }
+    if (has_pred) { k_lk_pred<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa); GF_LAUNCHED(); }
     k_track<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp, t->cfg.flow_back); GF_LAUNCHED();
     GF_MARK(2);
     k_compact_setmask<<<1, FE_CAP, 0, s>>>(t->d_sc, t->fa, t->cfg.min_dist); GF_LAUNCHED();
@@ -403,15 +406,47 @@ static int enqueue_frame(gf_tracker* t, double time, bool depth_valid)
     // reference quirk: depth_cam with an empty depth image produces an empty featureFrame (feature_tracker.cpp:342)
     const int depth_mode = t->cfg.depth_cam ? 1 : 0;
     k_select_finalize<<<1, 1024, t->grid_cells, s>>>(t->d_sc, t->fa, t->grid, t->w, t->cfg.max_cnt, t->cfg.min_dist, t->cam, &t->d_fp->dt,
-                                                     t->d_depth, t->depth_pitch_el, depth_mode && depth_valid, t->h, t->d_hdr, t->d_obs); GF_LAUNCHED();
+                                                     t->d_depth, t->depth_pitch_el, depth_mode, &t->d_fp->depth_valid, t->h, t->d_hdr, t->d_obs); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_MARK(5);
     GF_CUDA(cudaMemcpyAsync(t->h_hdr, t->d_hdr, sizeof(OutHeader), cudaMemcpyDeviceToHost, s));
     GF_CUDA(cudaMemcpyAsync(t->h_obs, t->d_obs, (size_t)t->cfg.max_cnt * sizeof(gf_obs), cudaMemcpyDeviceToHost, s));
+    return GF_OK;
+}
+
+static int enqueue_frame(gf_tracker* t, double time, bool depth_valid)
+{
+    const int cur = t->cur;
+    cudaStream_t s = t->s_main;
+    t->h_fp->dt = time - t->prev_time;
+    t->h_fp->has_pred = t->has_pred ? 1 : 0;
+    t->h_fp->depth_valid = depth_valid ? 1 : 0;
+    int rc = GF_OK;
+    if (t->use_graph && !t->profiling) {
+        const int key = cur * 2 + (t->has_pred ? 1 : 0);
+        if (!t->graph[key]) {
+            const uint64_t l0 = g_launches.load();
+            cudaGraph_t g = nullptr;
+            GF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_body(t, cur, t->has_pred);
+            cudaError_t e = cudaStreamEndCapture(s, &g);
+            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "graph capture failed: %s", cudaGetErrorString(e)); return GF_ERR_CUDA; }
+            GF_CUDA(cudaGraphInstantiate(&t->graph[key], g, 0));
+            cudaGraphDestroy(g);
+            t->graph_kernels[key] = (int)(g_launches.load() - l0);
+            g_launches.fetch_sub(t->graph_kernels[key]);      // capture did not launch anything
+        }
+        GF_CUDA(cudaGraphLaunch(t->graph[key], s));
+        g_launches.fetch_add(t->graph_kernels[key]);
+    } else {
+        rc = enqueue_body(t, cur, t->has_pred);
+        if (rc) return rc;
+    }
     GF_CUDA(cudaEventRecord(t->ev_t1, s));
     t->prev_time = time;
     t->has_pred = false;
-    t->cur = prev;
+    t->cur = cur ^ 1;
     t->pending = true;
     t->depth_last = depth_valid;
     return GF_OK;
@@ -665,7 +700,7 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
         fa.kept_pts = dk.as<float2>(); fa.kept_ids = dummy[4].as<int>(); fa.kept_cnt = dummy[5].as<int>(); fa.kept_un = dummy[6].as<float2>();
         CamParams cam; memset(&cam, 0, sizeof(cam)); cam.fx = cam.fy = 1.0; cam.no_distortion = 1;
         // max_cnt such that exactly max_corners new corners are requested
-        k_select_finalize<<<1, 1024, cells>>>(sc, fa, grid, w, n_kept + max_corners, min_dist, cam, nullptr, nullptr, 0, 0, h, dhdr.as<OutHeader>(), dobs.as<gf_obs>()); GF_LAUNCHED();
+        k_select_finalize<<<1, 1024, cells>>>(sc, fa, grid, w, n_kept + max_corners, min_dist, cam, nullptr, nullptr, 0, 0, nullptr, h, dhdr.as<OutHeader>(), dobs.as<gf_obs>()); GF_LAUNCHED();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "k_select_finalize launch: %s", cudaGetErrorString(e)); rc = GF_ERR_CUDA; }
     }
@@ -685,7 +720,15 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
 }
 
 }  // extern "C"
-__global__ void k_sort_stage(sort_elem* e, int n) { if (threadIdx.x == 0 && blockIdx.x == 0) setmask_sort(e, n); }
+__global__ void k_sort_stage(sort_elem* e, int n)
+{
+    __shared__ sort_elem v[FE_CAP];
+    __shared__ SortWork W;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v[i] = e[i];
+    __syncthreads();
+    setmask_sort_parallel(v, n, W);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) e[i] = v[i];
+}
 extern "C" {
 
 int gf_stage_setmask_order(int device, const int32_t* track_cnt, int n, int32_t* perm)
@@ -697,7 +740,7 @@ int gf_stage_setmask_order(int device, const int32_t* track_cnt, int n, int32_t*
     for (int i = 0; i < n; i++) e[i] = ((sort_elem)(unsigned)track_cnt[i] << 32) | (unsigned)i;
     DevBuf d; rc = d.alloc((size_t)n * 8); if (rc) return rc;
     GF_CUDA(cudaMemcpy(d.p, e.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
-    k_sort_stage<<<1, 32>>>(d.as<sort_elem>(), n); GF_LAUNCHED();
+    k_sort_stage<<<1, 256>>>(d.as<sort_elem>(), n); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpy(e.data(), d.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) perm[i] = (int32_t)(e[i] & 0xffffffffu);
