@@ -197,15 +197,22 @@ def main():
         torch.cuda.synchronize()
 
     def run(n, mode, k0):
-        dev_ms = 0.0
+        """n frames through the asynchronous API, two in flight (submit k+1 before collecting k).  Returns the
+        device time of the whole run (CUDA events around the first copy and the last result copy)."""
+        tr.timer_start()
+        pending = 0
         for k in range(k0, k0 + n):
             i = tri(k, args.ring)
             if mode == "device":
-                tr.trackDevice(k / 30.0, d_gray[i].data_ptr(), d_depth[i].data_ptr())
+                tr.submitDevice(k / 30.0, d_gray[i].data_ptr(), d_depth[i].data_ptr())
             else:
-                tr.trackImageRaw(k / 30.0, hg[i], hd[i])
-            dev_ms += tr.last_device_ms()
-        return dev_ms
+                tr.submit(k / 30.0, hg[i], hd[i])      # pinned ring: unchanged until collected
+            pending += 1
+            if pending == 2:
+                tr.wait(); pending -= 1
+        while pending:
+            tr.wait(); pending -= 1
+        return tr.timer_stop()
 
     sampler = ClockSampler(local); sampler.start()
     launches0 = _lib.lib().gf_kernel_launch_count()
@@ -229,14 +236,14 @@ def main():
     k1 = args.warmup + args.steps + 50
     run(args.warmup, "host", k1)
     barrier(); t0 = time.perf_counter()
-    run(args.steps, "host", k1 + args.warmup)
+    dev_ms_e2e = run(args.steps, "host", k1 + args.warmup)
     barrier(); el_e2e = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join(timeout=2)
 
     if dist is not None:
-        tt = torch.tensor([el_dev, el_e2e], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([el_dev, el_e2e, dev_ms, dev_ms_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        el_dev, el_e2e = float(tt[0]), float(tt[1])
+        el_dev, el_e2e, dev_ms, dev_ms_e2e = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -261,7 +268,10 @@ def main():
     out = {"metric": "tracker_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1000.0 * el_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8/i32 fixed point + f32 (LK, min-eig), f64 (box sums, undistortion)", "data": "synthetic", "config": cfg,
-           "device_ms_per_step": dev_ms / args.steps, "stage_ms": stage,
+           "device_ms_per_step": dev_ms / args.steps, "device_ms_per_step_e2e": dev_ms_e2e / args.steps,
+           "timing": "value/e2e: wall clock between barrier+synchronize, max over ranks; device_ms_per_step*: CUDA events "
+                     "around the same K frames on the tracker's streams (first copy .. last result copy), max over ranks",
+           "frames_in_flight": 2, "stage_ms": stage,
            "e2e": {"value": world * args.steps / el_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H * 3,
                    "d2h_bytes_per_step": MAX_CNT * 72 + 40 + MAX_CNT},
            "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary()}

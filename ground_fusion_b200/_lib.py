@@ -55,6 +55,9 @@ def lib():
         L.gf_tracker_host_buffers.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
         L.gf_tracker_track.argtypes = [vp, d, vp, sz, vp, sz, vp, ctypes.POINTER(i), vp, ctypes.POINTER(TrackInfo)]
         L.gf_tracker_submit.argtypes = [vp, d, vp, sz, vp, sz]
+        L.gf_tracker_submit_device.argtypes = [vp, d, vp, vp]
+        L.gf_tracker_timer_start.argtypes = [vp]
+        L.gf_tracker_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.gf_tracker_wait.argtypes = [vp, vp, ctypes.POINTER(i), vp, ctypes.POINTER(TrackInfo)]
         L.gf_tracker_track_device.argtypes = [vp, d, vp, vp, vp, ctypes.POINTER(i), vp, ctypes.POINTER(TrackInfo)]
         L.gf_tracker_set_prediction.argtypes = [vp, vp, vp, i]
@@ -62,6 +65,7 @@ def lib():
         L.gf_tracker_last_device_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.gf_tracker_set_profiling.argtypes = [vp, i]
         L.gf_tracker_last_stage_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+        L.gf_tracker_debug_read.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
         L.gf_stage_pyr_down.argtypes = [i, vp, i, i, vp]
         L.gf_stage_min_eig.argtypes = [i, vp, i, i, vp, ctypes.POINTER(i)]
         L.gf_stage_lk.argtypes = [i, vp, vp, i, i, vp, vp, i, i, i, vp]

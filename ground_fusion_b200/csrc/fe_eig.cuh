@@ -9,10 +9,15 @@
 //   cov = (dx*dx, dx*dy, dy*dy)  float32
 //   box: row sums (S0+S1)+S2 in double; column sums are ONE RUNNING double sum per column and channel
 //        down the whole image in OpenCV (s0 = SUM + D[y+1]; out = (float)s0; SUM = s0 - D[y-1]).
-//        That chain is inherently sequential, so it is cut into bands that each start from the
-//        speculated state fl(D[y0-1]+D[y0]) (the exact value whenever no rounding happened above,
-//        which is the case for >99.9 % of the states); every band records its start and end state and
-//        k_eig_verify replays the rare bands whose start differs from the true end of the band above.
+//        That chain is inherently sequential per column, but it is only two dependent DADDs per row; everything
+//        else is not.  So the work is split in three kernels:
+//          k_cov_rows    (parallel)  D[y][x] = the three row sums, as doubles, in a column-block-tiled layout with
+//                                    the two reflected border rows materialised, so that the rows one chain warp needs
+//                                    are one contiguous stream
+//          k_box_chain   (serial)    one lane per (column, channel); the D stream is fetched ahead of the chain by
+//                                    1-D TMA bulk copies into a shared-memory ring (cp.async.bulk + mbarrier), so the
+//                                    chain runs at DADD latency: ~16 cycles per image row
+//          k_eig_from_box (parallel) min-eig from the float box sums
 //   eig = (a+c) - sqrt((a-c)^2 + b*b), a = c0/2, b = c1, c = c2/2                 (float32)
 // Compile with -fmad=false.
 #pragma once
@@ -56,8 +61,17 @@ __global__ void __launch_bounds__(PD_TX* PD_TY) k_pyr_down(Level src, uint8_t* d
 // ------------------------------------------------------------------------------------------------
 // min-eig
 // ------------------------------------------------------------------------------------------------
-constexpr int EIG_TX = 128;   // columns per CTA (= threads per CTA)
-constexpr int EIG_BAND = 16;  // rows per speculative band
+constexpr int EIG_TX = 128;   // columns per CTA (= threads per CTA) of k_cov_rows
+constexpr int EIG_BAND = 16;  // rows per CTA of k_cov_rows
+constexpr int BC_R = 16;      // padded rows per TMA chunk of k_box_chain (16 * 768 B = 12 KB)
+constexpr int BC_NST = 6;     // ring stages: the chain runs 5 chunks (80 rows, > 1200 cycles) behind the copies
+constexpr int BC_ROW = 96;    // doubles per padded row of one 32-column block: [channel 3][column 32]
+constexpr size_t BC_SMEM = (size_t)BC_NST * BC_R * BC_ROW * sizeof(double);
+
+// size in doubles of the tiled D buffer for a w x h image
+__host__ __device__ inline size_t cov_rows_elems(int w, int h) { return (size_t)((w + 31) / 32) * (h + 2) * BC_ROW; }
+// size in floats of the box-sum buffer
+__host__ __device__ inline size_t box_elems(int w, int h) { return (size_t)3 * ((w + 31) / 32 * 32) * h; }
 
 // tail: column >= (w/32)*32, where cv2's row filter runs its scalar (non-FMA) remainder loop
 __device__ __forceinline__ void sobel_dxdy(int p00, int p01, int p02, int p10, int p11, int p12, int p20,
@@ -86,12 +100,12 @@ __device__ __forceinline__ float eig_from_box(double c0, double c1, double c2)
     return (a + c) - sqrtf(t * t + b * b);
 }
 
-// spec_start/spec_end: [band][3][w] doubles
-__global__ void __launch_bounds__(EIG_TX) k_min_eig(Level img, float* eig, int epitch /*floats*/,
-                                                    double* spec_start, double* spec_end)
+// D in the layout k_box_chain streams: [column block x/32][padded row y+1][channel][x%32]; padded row 0 = D[1],
+// padded row h+1 = D[h-2] (cv::boxFilter's BORDER_REFLECT_101 applied to the cov rows).
+__global__ void __launch_bounds__(EIG_TX) k_cov_rows(Level img, double* __restrict__ Dt)
 {
-    constexpr int IH = EIG_BAND + 4, IW = EIG_TX + 4;     // image tile rows y0-2.., cols x0-2..
-    constexpr int CH = EIG_BAND + 2, CW = EIG_TX + 2;     // dx/dy tile rows y0-1.., cols x0-1..
+    constexpr int IH = EIG_BAND + 2, IW = EIG_TX + 4;     // image tile rows y0-1.., cols x0-2..
+    constexpr int CH = EIG_BAND, CW = EIG_TX + 2;         // dx/dy tile rows y0.., cols x0-1..
     __shared__ uint8_t timg[IH][IW + 4];
     __shared__ float tdx[CH][CW + 2];
     __shared__ float tdy[CH][CW + 2];
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(EIG_TX) k_min_eig(Level img, float* eig, int e
     const int tid = threadIdx.x;
     for (int i = tid; i < IH * IW; i += EIG_TX) {
         int r = i / IW, c = i - r * IW;
-        int yy = y0 - 2 + r, xx = x0 - 2 + c;
+        int yy = y0 - 1 + r, xx = x0 - 2 + c;
         // clamp far-out indices (only reached by slots that are never used), reflect the border ring
         yy = min(max(yy, -1), h);
         xx = min(max(xx, -1), w);
@@ -109,11 +123,11 @@ __global__ void __launch_bounds__(EIG_TX) k_min_eig(Level img, float* eig, int e
         timg[r][c] = __ldg(img.ptr + (size_t)yy * img.pitch + xx);
     }
     __syncthreads();
-    // Sobel at slots whose (row, col) is inside the image; ring slots are filled by reflection below
+    // Sobel at slots whose (row, col) is inside the image; the column ring is filled by reflection below
     for (int i = tid; i < CH * CW; i += EIG_TX) {
         int r = i / CW, c = i - r * CW;
-        int yy = y0 - 1 + r, xx = x0 - 1 + c;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        int yy = y0 + r, xx = x0 - 1 + c;
+        if (yy < h && xx >= 0 && xx < w) {
             const uint8_t* p = &timg[r][c];  // timg row r <-> image row yy-1, col c <-> xx-1
             float dx, dy;
             sobel_dxdy(p[0], p[1], p[2], p[IW + 4], p[IW + 5], p[IW + 6], p[2 * (IW + 4)], p[2 * (IW + 4) + 1],
@@ -123,119 +137,148 @@ __global__ void __launch_bounds__(EIG_TX) k_min_eig(Level img, float* eig, int e
         }
     }
     __syncthreads();
-    // cov is extended by REFLECT_101 at the *cov* level: slot (-1) := slot (+1), slot (n) := slot (n-2)
-    for (int i = tid; i < CH * CW; i += EIG_TX) {
-        int r = i / CW, c = i - r * CW;
-        int yy = y0 - 1 + r, xx = x0 - 1 + c;
-        bool in = (yy >= 0 && yy < h && xx >= 0 && xx < w);
-        if (!in && yy >= -1 && yy <= h && xx >= -1 && xx <= w) {
-            int ry = reflect101(yy, h) - (y0 - 1), rx = reflect101(xx, w) - (x0 - 1);
-            if (ry >= 0 && ry < CH && rx >= 0 && rx < CW) {
-                tdx[r][c] = tdx[ry][rx];
-                tdy[r][c] = tdy[ry][rx];
-            }
+    // cov is extended by REFLECT_101 at the *cov* level: column slot (-1) := slot (+1), slot (w) := slot (w-2)
+    for (int i = tid; i < CH * 2; i += EIG_TX) {
+        int r = i >> 1, c = (i & 1) ? CW - 1 : 0;
+        int xx = x0 - 1 + c;
+        if (xx == -1 || xx == w) {
+            int rx = reflect101(xx, w) - (x0 - 1);
+            if (rx >= 0 && rx < CW) { tdx[r][c] = tdx[r][rx]; tdy[r][c] = tdy[r][rx]; }
+        }
+    }
+    if (x0 + EIG_TX > w) {   // last column block: the slot right of the image is not the tile's last slot
+        for (int r = tid; r < CH; r += EIG_TX) {
+            int c = w - (x0 - 1);           // slot of column w
+            if (c >= 0 && c < CW && c - 2 >= 0) { tdx[r][c] = tdx[r][c - 2]; tdy[r][c] = tdy[r][c - 2]; }
         }
     }
     __syncthreads();
     const int x = x0 + tid;
     if (x >= w) return;
     const int nrows = min(EIG_BAND, h - y0);
-    // D for tile row r (image row y0-1+r) at this thread's column
-    auto rowsum = [&](int r, double& d0, double& d1, double& d2) {
+    const size_t rows = (size_t)h + 2;
+    double* dst = Dt + (size_t)(x >> 5) * rows * BC_ROW + (x & 31);
+    for (int r = 0; r < nrows; r++) {
         const float* ax = &tdx[r][tid];  // cols x-1, x, x+1 <-> tid, tid+1, tid+2
         const float* ay = &tdy[r][tid];
         float xl = ax[0], xc = ax[1], xr = ax[2], yl = ay[0], yc = ay[1], yr = ay[2];
-        d0 = ((double)(xl * xl) + (double)(xc * xc)) + (double)(xr * xr);
-        d1 = ((double)(xl * yl) + (double)(xc * yc)) + (double)(xr * yr);
-        d2 = ((double)(yl * yl) + (double)(yc * yc)) + (double)(yr * yr);
-    };
-    double a0, a1, a2, b0, b1, b2;  // D[y-1], D[y]
-    rowsum(0, a0, a1, a2);
-    rowsum(1, b0, b1, b2);
-    double S0 = (0.0 + a0) + b0, S1 = (0.0 + a1) + b1, S2 = (0.0 + a2) + b2;
-    const size_t so = ((size_t)blockIdx.y * 3) * w + x;
-    spec_start[so] = S0;
-    spec_start[so + w] = S1;
-    spec_start[so + 2 * (size_t)w] = S2;
-    for (int k = 0; k < nrows; k++) {
-        double c0, c1, c2;
-        rowsum(k + 2, c0, c1, c2);
-        double s0 = S0 + c0, s1 = S1 + c1, s2 = S2 + c2;
-        eig[(size_t)(y0 + k) * epitch + x] = eig_from_box(s0, s1, s2);
-        S0 = s0 - a0; S1 = s1 - a1; S2 = s2 - a2;
-        a0 = b0; a1 = b1; a2 = b2;
-        b0 = c0; b1 = c1; b2 = c2;
+        double d0 = ((double)(xl * xl) + (double)(xc * xc)) + (double)(xr * xr);
+        double d1 = ((double)(xl * yl) + (double)(xc * yc)) + (double)(xr * yr);
+        double d2 = ((double)(yl * yl) + (double)(yc * yc)) + (double)(yr * yr);
+        const int y = y0 + r;
+        double* o = dst + (size_t)(y + 1) * BC_ROW;
+        o[0] = d0; o[32] = d1; o[64] = d2;
+        if (y == 1) { o = dst; o[0] = d0; o[32] = d1; o[64] = d2; }
+        if (y == h - 2) { o = dst + (size_t)(h + 1) * BC_ROW; o[0] = d0; o[32] = d1; o[64] = d2; }
     }
-    spec_end[so] = S0;
-    spec_end[so + w] = S1;
-    spec_end[so + 2 * (size_t)w] = S2;
 }
 
-// One thread per column: check every band's speculated start against the end of the band above (independent
-// loads), and replay the rare mismatching bands from the true state.  The replay first pulls the band's
-// (BAND+4) x 5 pixel neighbourhood into local memory with independent loads, then runs without touching HBM.
-__global__ void k_eig_verify(Level img, float* eig, int epitch, const double* spec_start,
-                             const double* spec_end, int nbands, int* fixups)
+// ---- mbarrier / 1-D TMA bulk copy (sm_90+) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
 {
-    const int w = img.w, h = img.h;
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= w) return;
-    {   // common case: nothing to do
-        bool any = false;
-#pragma unroll 4
-        for (int b = 1; b < nbands; b++) {
-            size_t so = ((size_t)b * 3) * w + x, sp = ((size_t)(b - 1) * 3) * w + x;
-            any |= (spec_start[so] != spec_end[sp]) | (spec_start[so + w] != spec_end[sp + w]) | (spec_start[so + 2 * (size_t)w] != spec_end[sp + 2 * (size_t)w]);
-        }
-        if (!any) return;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// The running column sums: one CTA of 3 warps per 32-column block, warp q <-> channel q, lane <-> column.
+//   SUM = (0 + D[-1]) + D[0];  per row: s = SUM + D[y+1]; box[y] = (float)s; SUM = s - D[y-1]
+// box: [channel][y][x] floats, row pitch bp = w rounded up to 32 (every lane stores).
+__global__ void __launch_bounds__(96) k_box_chain(const double* __restrict__ Dt, float* __restrict__ box, int bp, int w, int h)
+{
+    extern __shared__ __align__(128) unsigned char bc_smem[];
+    __shared__ __align__(8) unsigned long long mbar[BC_NST];
+    double* buf = reinterpret_cast<double*>(bc_smem);              // [stage][row][channel][32]
+    const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+    const int x = blockIdx.x * 32 + lane;
+    const int rows = h + 2, nchunk = (rows + BC_R - 1) / BC_R;
+    const double* src = Dt + (size_t)blockIdx.x * rows * BC_ROW;
+    if (tid == 0) {
+        for (int i = 0; i < BC_NST; i++) mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    double t0 = spec_end[x], t1 = spec_end[(size_t)w + x], t2 = spec_end[2 * (size_t)w + x];
-    for (int b = 1; b < nbands; b++) {
-        size_t so = ((size_t)b * 3) * w + x;
-        double s0 = spec_start[so], s1 = spec_start[so + w], s2 = spec_start[so + 2 * (size_t)w];
-        if (s0 == t0 && s1 == t1 && s2 == t2) {
-            t0 = spec_end[so]; t1 = spec_end[so + w]; t2 = spec_end[so + 2 * (size_t)w];
-            continue;
+    __syncthreads();
+    auto issue = [&](int k) {
+        const int r0 = k * BC_R, nr = min(BC_R, rows - r0);
+        const unsigned bytes = (unsigned)(nr * BC_ROW * sizeof(double));
+        mbar_expect_tx(&mbar[k % BC_NST], bytes);
+        tma_load_1d(buf + (size_t)(k % BC_NST) * BC_R * BC_ROW, src + (size_t)r0 * BC_ROW, bytes, &mbar[k % BC_NST]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < BC_NST - 1 && k < nchunk; k++) issue(k);
+    float* o = box + (size_t)q * bp * h + x;               // next output row of this lane (pitch bp >= 32-aligned w: no bounds test)
+    double a = 0.0, b = 0.0, S = 0.0;
+    for (int k = 0; k < nchunk; k++) {
+        __syncthreads();                                   // everyone is done with the stage that is refilled next
+        if (tid == 0 && k + BC_NST - 1 < nchunk) issue(k + BC_NST - 1);
+        {
+            unsigned spins = 0;
+            while (!mbar_try_wait(&mbar[k % BC_NST], (unsigned)((k / BC_NST) & 1)))
+                if (++spins > (1u << 24)) __trap();        // a lost copy must not hang the GPU
         }
-        atomicAdd(fixups, 1);
-        const int y0 = b * EIG_BAND, nrows = min(EIG_BAND, h - y0);
-        // pixels of image rows y0-2 .. y0+BAND+1 and columns x-2 .. x+2 (image-level REFLECT_101 applied here)
-        uint8_t P[EIG_BAND + 4][5];
+        const double* B = buf + (size_t)(k % BC_NST) * BC_R * BC_ROW + q * 32 + lane;
+        const int nr = min(BC_R, rows - k * BC_R);
+        int r = 0;
+        if (k == 0) {                                      // padded rows 0 and 1: D[-1] and D[0]
+            a = B[0];
+            b = B[BC_ROW];
+            S = (0.0 + a) + b;
+            r = 2;
+        }
+        if (r == 0 && nr == BC_R) {
 #pragma unroll
-        for (int r = 0; r < EIG_BAND + 4; r++) {
-            int yy = min(max(y0 - 2 + r, -1), h); yy = reflect101(yy, h);
-#pragma unroll
-            for (int c = 0; c < 5; c++) {
-                int xx = min(max(x - 2 + c, -1), w); xx = reflect101(xx, w);
-                P[r][c] = __ldg(img.ptr + (size_t)yy * img.pitch + xx);
+            for (int rr = 0; rr < BC_R; rr++) {
+                const double c = B[rr * BC_ROW];
+                const double s = S + c;
+                *o = (float)s;
+                o += bp;
+                S = s - a;
+                a = b;
+                b = c;
+            }
+        } else {
+            for (; r < nr; r++) {
+                const double c = B[r * BC_ROW];
+                const double s = S + c;
+                *o = (float)s;
+                o += bp;
+                S = s - a;
+                a = b;
+                b = c;
             }
         }
-        // D at image row r (REFLECT_101 at the cov level) for this column
-        auto rowsum = [&](int r, double& d0, double& d1, double& d2) {
-            const int rr = reflect101(min(max(r, -1), h), h);
-            float cx[3], cy[3];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_eig_from_box(const float* __restrict__ box, int bp, float* __restrict__ eig, int epitch, int w, int h)
+{
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int yb = blockIdx.y * 16 + (threadIdx.x >> 6);
+    if (x >= w) return;
+    const size_t plane = (size_t)bp * h;
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int cc = reflect101(min(max(x - 1 + k, -1), w), w);
-                const int pr = rr - (y0 - 2), pc = cc - (x - 2);          // centre of the 3x3 neighbourhood inside P
-                sobel_dxdy(P[pr - 1][pc - 1], P[pr - 1][pc], P[pr - 1][pc + 1], P[pr][pc - 1], P[pr][pc], P[pr][pc + 1],
-                           P[pr + 1][pc - 1], P[pr + 1][pc], P[pr + 1][pc + 1], cc >= (w / 32) * 32, cx[k], cy[k]);
-            }
-            d0 = ((double)(cx[0] * cx[0]) + (double)(cx[1] * cx[1])) + (double)(cx[2] * cx[2]);
-            d1 = ((double)(cx[0] * cy[0]) + (double)(cx[1] * cy[1])) + (double)(cx[2] * cy[2]);
-            d2 = ((double)(cy[0] * cy[0]) + (double)(cy[1] * cy[1])) + (double)(cy[2] * cy[2]);
-        };
-        double a0, a1, a2, b0, b1, b2;
-        rowsum(y0 - 1, a0, a1, a2);
-        rowsum(y0, b0, b1, b2);
-        for (int k = 0; k < nrows; k++) {
-            double c0, c1, c2;
-            rowsum(y0 + k + 1, c0, c1, c2);
-            double u0 = t0 + c0, u1 = t1 + c1, u2 = t2 + c2;
-            eig[(size_t)(y0 + k) * epitch + x] = eig_from_box(u0, u1, u2);
-            t0 = u0 - a0; t1 = u1 - a1; t2 = u2 - a2;
-            a0 = b0; a1 = b1; a2 = b2;
-            b0 = c0; b1 = c1; b2 = c2;
+    for (int j = 0; j < 4; j++) {
+        const int y = yb + 4 * j;
+        if (y < h) {
+            const size_t o = (size_t)y * bp + x;
+            float a = box[o] * 0.5f, b = box[plane + o], c = box[2 * plane + o] * 0.5f;
+            float t = a - c;
+            eig[(size_t)y * epitch + x] = (a + c) - sqrtf(t * t + b * b);
         }
     }
 }

@@ -26,7 +26,8 @@ constexpr int LK_IPITCH = 32;             // bytes per staged I row (24 + up to 
 constexpr int LK_SCH = 22;                // integer positions needing a derivative
 constexpr int LK_JR = 40;                 // cached J region (window 22 + 9 px drift each side)
 constexpr int LK_JPITCH = 48;             // bytes per staged J row (40 + up to 3 bytes of alignment slack)
-constexpr int LK_THREADS = 128;            // one CTA of 4 warps per feature: one warp per SM scheduler, ~one feature per SM
+constexpr int LK_THREADS = 256;            // one CTA of 8 warps per feature (two warps per SM scheduler), ~one feature per SM
+constexpr int LK_MAXLEV = 4;               // pyramid levels 0..3
 constexpr int LK_CHAIN = 84, LK_TAIL = 105;        // terms per SIMD-lane chain / tail chain of the A sums
 constexpr int LK_BCHAIN = 42;                       // pair terms per chain of the b sums
 constexpr int LK_AT = 4 * LK_CHAIN + LK_TAIL;       // 441 terms per A quantity
@@ -34,7 +35,7 @@ constexpr int LK_BT = 4 * LK_BCHAIN + LK_TAIL;      // 273 terms per b component
 constexpr int LK_Q = 5 * LK_TAIL;                   // slots per quantity: [step 0..104][chain 0..4], short chains padded with +0.0f
 
 struct __align__(16) LKSmem {
-    uint8_t ireg[LK_IREG * LK_IPITCH];     // raw bytes, row r at r*32, first needed column at byte xoff
+    uint8_t ireg[LK_MAXLEV][LK_IREG * LK_IPITCH];   // per level: raw bytes, row r at r*32, first needed column at byte xoff
     int16_t sch[LK_SCH * LK_SCH * 2];
     int16_t pI[LK_NPIX + 1];
     int16_t pdx[LK_NPIX + 1];
@@ -123,12 +124,50 @@ __device__ __forceinline__ float lk_chain(const float* T, int lane, int nq)
 
 // One pyramid level for one point.  All LK_THREADS threads of the CTA call this with identical scalar arguments
 // and keep identical copies of the scalar state; warp 0 owns the sequential chains.
-__device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, const Level& J, float px,
-                                         float py, float& nx, float& ny, int level, int& status, int& iters)
+#define LKP(i) do { long long t_ = clock64(); pc[i] += t_ - tl; tl = t_; } while (0)
+
+// Window origin of a point on one level (OpenCV: prevPt = prevPts[i] * (1/(1<<level)) - halfWin, then floor)
+__device__ __forceinline__ void lk_origin(float2 p, int l, float& ppx, float& ppy, int& ipx, int& ipy)
 {
+    const float sc = (float)(1. / (double)(1 << l));
+    ppx = p.x * sc - 10.f;
+    ppy = p.y * sc - 10.f;
+    ipx = __float2int_rd(ppx);
+    ipy = __float2int_rd(ppy);
+}
+
+// A thread's fixed share of the mismatch terms: one unit of the chain layout (a pmaddwd pair or a tail pixel) plus,
+// for 17 threads, a second tail pixel -- at most two pixels per thread, the same for every level and iteration.
+struct LKUnit { int i0, i1, slot, off0, off1; };
+__device__ __forceinline__ LKUnit lk_unit(int u)
+{
+    LKUnit U;
+    if (u < 4 * LK_BCHAIN) {
+        int y = u >> 3, r = u & 7, k = r & 3, hh = r >> 2;
+        U.i0 = y * LK_WIN + 8 * hh + k;
+        U.i1 = U.i0 + 4;
+        U.slot = (y * 2 + hh) * 5 + k;
+    } else {
+        int t = u - 4 * LK_BCHAIN, y = t / 5, x = 16 + (t - y * 5);
+        U.i0 = U.i1 = y * LK_WIN + x;
+        U.slot = t * 5 + 4;
+    }
+    U.off0 = (U.i0 / LK_WIN) * LK_JPITCH + (U.i0 % LK_WIN);
+    U.off1 = (U.i1 / LK_WIN) * LK_JPITCH + (U.i1 % LK_WIN);
+    return U;
+}
+
+// One pyramid level for one point.  All LK_THREADS threads of the CTA call this with identical scalar arguments
+// and keep identical copies of the scalar state; warp 0 owns the sequential chains.  The level's 24x24 window of I
+// is already staged in S.ireg[level] (lk_track_point).
+__device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, const Level& J, float2 p,
+                                         float& nx, float& ny, int level, int& status, int& iters, long long* pc)
+{
+    long long tl = clock64();
     const float FLT_SCALE = 1.f / (1 << 20);
-    float ppx = px - 10.f, ppy = py - 10.f;
-    int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+    float ppx, ppy;
+    int ipx, ipy;
+    lk_origin(p, level, ppx, ppy, ipx, ipy);
     if (ipx < -LK_WIN || ipx >= I.w || ipy < -LK_WIN || ipy >= I.h) {
         if (level == 0) status = 0;
         return;
@@ -136,18 +175,16 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
     float a = ppx - (float)ipx, b = ppy - (float)ipy;
     int iw00, iw01, iw10, iw11;
     lk_weights(a, b, iw00, iw01, iw10, iw11);
-
-    // ---- stage the 24x24 u8 window of I (REFLECT_101) ----
-    __syncthreads();
-    const int ioff = lk_stage<LK_IREG, LK_IREG, LK_IPITCH>(S.ireg, I, ipx - 1, ipy - 1, tid);
-    __syncthreads();
+    const uint8_t* ireg = S.ireg[level];
+    const int ioff = lk_stage_offset<LK_IREG, LK_IREG>(I, ipx - 1, ipy - 1);
+    __syncthreads();     // previous level's readers of sch / pI / terms are done
     // ---- Scharr derivative at the 22x22 integer positions (0 outside the image) ----
     for (int i = tid; i < LK_SCH * LK_SCH; i += LK_THREADS) {
         int r = i / LK_SCH, c = i - r * LK_SCH;
         int X = ipx + c, Y = ipy + r;
         int ix = 0, iy = 0;
         if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
-            const uint8_t* u = S.ireg + r * LK_IPITCH + ioff + c;  // row above, column left of the centre
+            const uint8_t* u = ireg + r * LK_IPITCH + ioff + c;  // row above, column left of the centre
             const uint8_t* m = u + LK_IPITCH;
             const uint8_t* d = m + LK_IPITCH;
             int t0l = (u[0] + d[0]) * 3 + m[0] * 10, t0r = (u[2] + d[2]) * 3 + m[2] * 10;
@@ -155,15 +192,15 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
             ix = t0r - t0l;
             iy = (t1r + t1l) * 3 + t1c * 10;
         }
-        S.sch[2 * i] = (int16_t)ix;
-        S.sch[2 * i + 1] = (int16_t)iy;
+        reinterpret_cast<int*>(S.sch)[i] = (ix & 0xffff) | (iy << 16);
     }
     __syncthreads();
+    LKP(1);
     // ---- bilinear 21x21 patches I*32, (Ix, Iy), and the gradient-matrix terms in chain order ----
     for (int i = tid; i < LK_NPIX; i += LK_THREADS) {
         int y = i / LK_WIN, x = i - y * LK_WIN;
-        const uint8_t* p = S.ireg + (y + 1) * LK_IPITCH + ioff + (x + 1);
-        int iv = p[0] * iw00 + p[1] * iw01 + p[LK_IPITCH] * iw10 + p[LK_IPITCH + 1] * iw11;
+        const uint8_t* q = ireg + (y + 1) * LK_IPITCH + ioff + (x + 1);
+        int iv = q[0] * iw00 + q[1] * iw01 + q[LK_IPITCH] * iw10 + q[LK_IPITCH + 1] * iw11;
         S.pI[i] = (int16_t)lk_descale(iv, 9);
         const int16_t* s = S.sch + 2 * (y * LK_SCH + x);
         int dxv = s[0] * iw00 + s[2] * iw01 + s[2 * LK_SCH] * iw10 + s[2 * LK_SCH + 2] * iw11;
@@ -178,7 +215,8 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
         S.terms[2 * LK_Q + slot] = (float)(gy * gy);
     }
     __syncthreads();
-    // ---- gradient matrix, OpenCV lane order: warp 0 runs the 15 chains while warps 1-3 already stage the
+    LKP(2);
+    // ---- gradient matrix, OpenCV lane order: warp 0 runs the 15 chains while the other warps already stage the
     //      search window of the first iteration (its position does not depend on A) ----
     float qx = nx - 10.f, qy = ny - 10.f;
     int jx0 = 0, jy0 = 0, joff = 0;
@@ -201,7 +239,15 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
         }
         if (inwin) joff = lk_stage_offset<LK_JR, LK_JR>(J, jx0, jy0);
     }
+    // this thread's share of the mismatch terms and the template values it needs (constant over the iterations)
+    const LKUnit U1 = lk_unit(tid < LK_BT ? tid : 0);
+    const bool has2 = (tid >= 4 * LK_BCHAIN) && (LK_THREADS + tid - 4 * LK_BCHAIN < LK_BT);
+    const LKUnit U2 = lk_unit(has2 ? LK_THREADS + tid - 4 * LK_BCHAIN : 4 * LK_BCHAIN);
+    const int t1I0 = S.pI[U1.i0], t1x0 = S.pdx[U1.i0], t1y0 = S.pdy[U1.i0];
+    const int t1I1 = S.pI[U1.i1], t1x1 = S.pdx[U1.i1], t1y1 = S.pdy[U1.i1];
+    const int t2I = S.pI[U2.i0], t2x = S.pdx[U2.i0], t2y = S.pdy[U2.i0];
     __syncthreads();
+    LKP(3);
     float A11 = S.sums[0] * FLT_SCALE, A12 = S.sums[1] * FLT_SCALE, A22 = S.sums[2] * FLT_SCALE;
     // the mismatch chains are 42 pair terms long: clear steps 42..83 of the SIMD chains of the two quantities they reuse
     for (int i = tid; i < 2 * 4 * (LK_CHAIN - LK_BCHAIN); i += LK_THREADS) {
@@ -217,6 +263,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
     D = 1.f / D;
 
     float pdx_ = 0.f, pdy_ = 0.f;
+    LKP(4);
     for (int j = 0; j < 30; j++) {
         int iqx = __float2int_rd(qx), iqy = __float2int_rd(qy);
         if (iqx < -LK_WIN || iqx >= J.w || iqy < -LK_WIN || iqy >= J.h) {
@@ -236,34 +283,30 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
         const uint8_t* jb = S.jreg + (iqy - jy0) * LK_JPITCH + joff + (iqx - jx0);
         __syncthreads();    // staged window and cleared/previous terms are visible; previous sums have been read
         // ---- mismatch terms in chain order: 168 pmaddwd pair units (row y, k in 0..3, half h) + 105 tail pixels ----
-        for (int u = tid; u < LK_BT; u += LK_THREADS) {
-            int i0, i1, slot;
-            if (u < 4 * LK_BCHAIN) {
-                int y = u >> 3, r = u & 7, k = r & 3, hh = r >> 2;
-                i0 = y * LK_WIN + 8 * hh + k;
-                i1 = i0 + 4;
-                slot = (y * 2 + hh) * 5 + k;
-            } else {
-                int t = u - 4 * LK_BCHAIN, y = t / 5, x = 16 + (t - y * 5);
-                i0 = i1 = y * LK_WIN + x;
-                slot = t * 5 + 4;
+        if (tid < LK_BT) {
+            const uint8_t* q = jb + U1.off0;
+            int jv = q[0] * iw00 + q[1] * iw01 + q[LK_JPITCH] * iw10 + q[LK_JPITCH + 1] * iw11;
+            int d0 = lk_descale(jv, 9) - t1I0;
+            int sx = d0 * t1x0, sy = d0 * t1y0;
+            if (tid < 4 * LK_BCHAIN) {
+                q = jb + U1.off1;
+                jv = q[0] * iw00 + q[1] * iw01 + q[LK_JPITCH] * iw10 + q[LK_JPITCH + 1] * iw11;
+                int d1 = lk_descale(jv, 9) - t1I1;
+                sx += d1 * t1x1;   // pmaddwd: exact int32 pair sum, converted once
+                sy += d1 * t1y1;
             }
-            int y0 = i0 / LK_WIN, x0 = i0 - y0 * LK_WIN;
-            const uint8_t* p = jb + y0 * LK_JPITCH + x0;
-            int jv = p[0] * iw00 + p[1] * iw01 + p[LK_JPITCH] * iw10 + p[LK_JPITCH + 1] * iw11;
-            int d0 = lk_descale(jv, 9) - S.pI[i0];
-            int sx = d0 * S.pdx[i0], sy = d0 * S.pdy[i0];
-            if (i1 != i0) {
-                p += 4;
-                jv = p[0] * iw00 + p[1] * iw01 + p[LK_JPITCH] * iw10 + p[LK_JPITCH + 1] * iw11;
-                int d1 = lk_descale(jv, 9) - S.pI[i1];
-                sx += d1 * S.pdx[i1];   // pmaddwd: exact int32 pair sum, converted once
-                sy += d1 * S.pdy[i1];
-            }
-            S.terms[slot] = (float)sx;
-            S.terms[LK_Q + slot] = (float)sy;
+            S.terms[U1.slot] = (float)sx;
+            S.terms[LK_Q + U1.slot] = (float)sy;
+        }
+        if (has2) {
+            const uint8_t* q = jb + U2.off0;
+            int jv = q[0] * iw00 + q[1] * iw01 + q[LK_JPITCH] * iw10 + q[LK_JPITCH + 1] * iw11;
+            int d0 = lk_descale(jv, 9) - t2I;
+            S.terms[U2.slot] = (float)(d0 * t2x);
+            S.terms[LK_Q + U2.slot] = (float)(d0 * t2y);
         }
         __syncthreads();
+        LKP(5);
         if (tid < 32) {
             const float bacc = lk_chain(S.terms, tid, 2);
 #pragma unroll
@@ -276,6 +319,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
             }
         }
         __syncthreads();
+        LKP(6);
         iters++;
         float b1 = S.sums[0] * FLT_SCALE, b2 = S.sums[1] * FLT_SCALE;
         float dx = (A12 * b2 - A22 * b1) * D, dy = (A12 * b1 - A11 * b2) * D;
@@ -291,6 +335,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
         }
         pdx_ = dx;
         pdy_ = dy;
+        LKP(7);
     }
     // epilogue of OpenCV's err computation (level 0): final window origin must still be in range
     if (level == 0 && status) {
@@ -302,21 +347,30 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
 // Whole pyramid for one point.  init is only read when use_init.
 __device__ __forceinline__ void lk_track_point(LKSmem& S, int tid, const Pyramid& I, const Pyramid& J,
                                                float2 p, float2 init, bool use_init, int max_level,
-                                               float2& out, int& status, int& iters)
+                                               float2& out, int& status, int& iters, long long* pc)
 {
     status = 1;
     float nx = 0.f, ny = 0.f;
+    long long tl = clock64();
     __syncthreads();
     for (int i = tid; i < 3 * LK_Q; i += LK_THREADS) S.terms[i] = 0.f;    // chain padding must read +0.0f
+    // the template windows of all levels depend only on p: fetch them together (one memory latency instead of one per level)
+    for (int l = 0; l <= max_level; l++) {
+        float ppx, ppy;
+        int ipx, ipy;
+        lk_origin(p, l, ppx, ppy, ipx, ipy);
+        if (!(ipx < -LK_WIN || ipx >= I.lv[l].w || ipy < -LK_WIN || ipy >= I.lv[l].h))
+            lk_stage<LK_IREG, LK_IREG, LK_IPITCH>(S.ireg[l], I.lv[l], ipx - 1, ipy - 1, tid);
+    }
     __syncthreads();
+    LKP(0);
     for (int l = max_level; l >= 0; l--) {
         float sc = (float)(1. / (double)(1 << l));
-        float px = p.x * sc, py = p.y * sc;
         if (l == max_level) {
             if (use_init) { nx = init.x * sc; ny = init.y * sc; }
-            else { nx = px; ny = py; }
+            else { nx = p.x * sc; ny = p.y * sc; }
         } else { nx = nx * 2.f; ny = ny * 2.f; }
-        lk_level(S, tid, I.lv[l], J.lv[l], px, py, nx, ny, l, status, iters);
+        lk_level(S, tid, I.lv[l], J.lv[l], p, nx, ny, l, status, iters, pc);
     }
     out = make_float2(nx, ny);
 }

@@ -39,7 +39,10 @@ struct FeatArrays {   // all device pointers, capacity FE_CAP
     float2* cur_pts; uint8_t* status;                                  // LK output for the n_prev features
     float2* kept_pts; int* kept_ids; int* kept_cnt; float2* kept_un;  // after setMask
     float2* pred_pts;
+    long long* dbg;                                                    // clock64 phase counters (gf_tracker_debug_read); may be null
 };
+constexpr int FE_DBG_N = 64 + 8 * FE_CAP;
+#define GF_DBG(slot, v) do { if (fa.dbg && threadIdx.x == 0 && blockIdx.x == 0) fa.dbg[slot] = (v); } while (0)
 
 __device__ __forceinline__ unsigned int float_order_key(float v)
 {
@@ -52,25 +55,28 @@ __device__ __forceinline__ float float_from_order_key(unsigned int k)
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int SM_CF_MAX = 6;   // earlier features within min_dist remembered per feature (more: full rescans)
 __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, FeatArrays fa, int min_dist)
 {
     __shared__ sort_elem elems[FE_CAP];
     __shared__ float2 c_pt[FE_CAP];
-    __shared__ float2 c_un[FE_CAP];
-    __shared__ int c_id[FE_CAP];
-    __shared__ int c_cnt[FE_CAP];
+    __shared__ short c_orig[FE_CAP];       // compacted position -> index before reduceVector
     __shared__ short2 rc[FE_CAP];          // rounded centres in sorted order
+    __shared__ short cf[FE_CAP * SM_CF_MAX];
+    __shared__ int ncf[FE_CAP];
     __shared__ uint8_t st[FE_CAP];
     __shared__ int warp_sums[32];
     __shared__ int s_m;
     __shared__ SortWork swork;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = sc->n_prev;
+    const long long c0 = clock64();
     // ---- reduceVector (stable compaction by status) ----
     int keep = (tid < n) ? (fa.status[tid] != 0) : 0;
     unsigned bal = __ballot_sync(0xffffffffu, keep);
     int pre = __popc(bal & ((1u << lane) - 1));
     if (lane == 0) warp_sums[wid] = __popc(bal);
+    ncf[tid] = 0;
     __syncthreads();
     if (wid == 0) {
         int v = warp_sums[lane];
@@ -84,15 +90,15 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
     if (keep) {
         int p = warp_sums[wid] + pre;
         c_pt[p] = fa.cur_pts[tid];
-        c_un[p] = fa.prev_un[tid];
-        c_id[p] = fa.ids[tid];
+        c_orig[p] = (short)tid;
         int cnt = fa.track_cnt[tid] + 1;                     // for (auto &n : track_cnt) n++;
-        c_cnt[p] = cnt;
         elems[p] = ((sort_elem)(unsigned)cnt << 32) | (unsigned)p;
     }
     __syncthreads();
-    // ---- std::sort replica: same comparisons and moves as libstdc++, independent ranges replayed in parallel ----
+    const long long c1 = clock64();
+    // ---- std::sort replica: same comparisons and moves as libstdc++, replayed in parallel (fe_sort.cuh) ----
     setmask_sort_parallel(elems, m, swork);
+    const long long c2 = clock64();
     int src = 0;
     if (tid < m) {
         src = (int)(elems[tid] & 0xffffffffu);
@@ -101,20 +107,47 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
         st[tid] = 0;
     }
     __syncthreads();
-    // ---- greedy "mask == 255 then draw disk" by rounds; conflict: d^2 <= r^2 with an earlier kept ----
+    // ---- "if (mask.at(pt) == 255) keep, draw disk": feature j is kept iff no kept earlier feature i has
+    //      d^2 <= r^2.  Pass 1 (all threads): the earlier features within range of each j.  Pass 2: rounds over those
+    //      short lists (a feature decides once all of its listed predecessors have). ----
     const int r2 = min_dist * min_dist;
+    {
+        const int mp = (m + 31) & ~31;
+        const int parts = mp ? max(1, FE_CAP / mp) : 1;
+        const int j = mp ? tid % mp : 0, part = mp ? tid / mp : parts;
+        if (j < m && part < parts) {
+            const short2 c = rc[j];
+            for (int i = part; i < j; i += parts) {
+                int dx = c.x - rc[i].x, dy = c.y - rc[i].y;
+                if (dx * dx + dy * dy <= r2) {
+                    int k = atomicAdd(&ncf[j], 1);
+                    if (k < SM_CF_MAX) cf[j * SM_CF_MAX + k] = (short)i;
+                }
+            }
+        }
+    }
+    __syncthreads();
     int my = 0;  // 0 undecided, 1 kept, 2 rejected
+    const int nc = (tid < m) ? ncf[tid] : 0;
     while (true) {
         int ns = my;
         if (tid < m && my == 0) {
             bool rej = false, blk = false;
-            short2 c = rc[tid];
-            for (int i = 0; i < tid; i++) {
-                int dx = c.x - rc[i].x, dy = c.y - rc[i].y;
-                if (dx * dx + dy * dy <= r2) {
-                    int s = st[i];
-                    if (s == 1) { rej = true; break; }
+            if (nc <= SM_CF_MAX) {
+                for (int k = 0; k < nc; k++) {
+                    int s = st[cf[tid * SM_CF_MAX + k]];
+                    if (s == 1) rej = true;
                     if (s == 0) blk = true;
+                }
+            } else {
+                short2 c = rc[tid];
+                for (int i = 0; i < tid; i++) {
+                    int dx = c.x - rc[i].x, dy = c.y - rc[i].y;
+                    if (dx * dx + dy * dy <= r2) {
+                        int s = st[i];
+                        if (s == 1) { rej = true; break; }
+                        if (s == 0) blk = true;
+                    }
                 }
             }
             ns = rej ? 2 : (blk ? 0 : 1);
@@ -124,6 +157,7 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
         int undecided = __syncthreads_or((tid < m) && ns == 0);
         if (!undecided) break;
     }
+    const long long c3 = clock64();
     // ---- emit kept features in sorted order ----
     int k = (tid < m) && (my == 1);
     bal = __ballot_sync(0xffffffffu, k);
@@ -141,15 +175,17 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
     __syncthreads();
     if (k) {
         int p = warp_sums[wid] + pre;
+        const int o = c_orig[src];
         fa.kept_pts[p] = c_pt[src];
-        fa.kept_un[p] = c_un[src];
-        fa.kept_ids[p] = c_id[src];
-        fa.kept_cnt[p] = c_cnt[src];
+        fa.kept_un[p] = fa.prev_un[o];
+        fa.kept_ids[p] = fa.ids[o];
+        fa.kept_cnt[p] = (int)(elems[tid] >> 32);
     }
     if (tid == 0) {   // per-frame counters consumed downstream
         sc->n_cand = 0; sc->max_key = 0; sc->n_new = 0; sc->nms_rounds = 0;
         for (int i = 0; i < 16; i++) sc->nms_remaining[i] = 0;
     }
+    GF_DBG(0, c1 - c0); GF_DBG(1, c2 - c1); GF_DBG(2, c3 - c2); GF_DBG(3, clock64() - c3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -218,7 +254,7 @@ __global__ void __launch_bounds__(256) k_eig_max(TrackScalars* sc, const float2*
 // r-neighbourhood is covered by the 3x3 cells around it.
 struct NmsGrid {
     int cs, gw, gh;                 // cell size, grid dims
-    unsigned long long* cand_key;   // [w*h] flat candidate list: (eig bits << 32 | y*w + x), any order
+    unsigned long long* cand_key;   // [w*h] flat candidate list: (eig bits << 32 | y << 16 | x), any order; same order as (eig, address)
     unsigned long long* acc_key;    // [w*h / 16 + 64] accepted corners (any order), count in TrackScalars::n_acc
     int acc_cap;
     uint8_t* dead;                  // [w*h] slow path only (more than 65536 candidates)
@@ -254,93 +290,162 @@ __global__ void __launch_bounds__(256) k_candidates(TrackScalars* sc, const floa
         int lane = threadIdx.x & 31, base = 0;
         if (lane == (__ffs(bal) - 1)) base = atomicAdd(&sc->n_cand, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-        if (is_cand) g.cand_key[base + __popc(bal & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)(y * w + x);
+        if (is_cand) g.cand_key[base + __popc(bal & ((1u << lane) - 1))] = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)((y << 16) | x);
     }
     }
 }
 
 // cv::goodFeaturesToTrack's greedy min-distance pass, exact, by rounds (single CTA, 1024 threads):
 //   every alive candidate is killed if one of LAST round's accepted corners in its 3x3 cells is closer than r
-//   (older accepted corners have already killed their neighbours), otherwise it bids for the head of its cell
-//   (atomicMax on the 64-bit key).  A head that outranks the heads of the 8 surrounding cells has no undecided
-//   higher-ranked candidate within r (every candidate of a cell ranks below its head) and no accepted corner
-//   within r (else it would be dead), so the sequential greedy would accept it too.  The globally best head can
-//   always decide, so the loop terminates; measured 5-11 rounds at 640x480.
-// Dynamic shared memory: gw*gh * (8 + 4 + 4) bytes.
+//   (older accepted corners have already killed their neighbours), otherwise it bids for the head of its cell.
+//   A head that outranks the heads of the 8 surrounding cells has no undecided higher-ranked candidate within r
+//   (every candidate of a cell ranks below its head) and no accepted corner within r (else it would be dead), so the
+//   sequential greedy would accept it too.  The globally best head can always decide, so the loop terminates;
+//   measured 5-11 rounds at 640x480.
+// The single SM is issue-bound on this, so the rounds are kept lean: the head election is two native 32-bit
+// ATOMS.MAX (eig bits, then packed address among the ties; a 64-bit shared atomicMax is a CAS spin loop), a per-cell
+// flag says whether any of the 3x3 cells accepted a corner last round (most candidates skip the distance tests),
+// the first two candidates of a thread and their cells live in registers, and the per-round arrays are double-buffered
+// so that a round needs three barriers.
+// Dynamic shared memory: nms_smem_bytes(gw, gh).
 constexpr int NMS_MAX_PER_THREAD = 64;
-__device__ __forceinline__ void nms_cells(TrackScalars* sc, const NmsGrid& g, int w, int min_dist, unsigned char* smem_raw)
+constexpr int NMS_CELL_BYTES = 32;   // per padded cell: head_hi[2] + head_lo[2] + acc[2] (4 B each) + flag[2] (1 B each) + index (2 B), rounded up
+__device__ __forceinline__ int div_cell(int x, float rcp, int cs)
+{   // x / cs for 0 <= x < 65536 without an integer division
+    int q = (int)((float)x * rcp);
+    if (q * cs > x) q--;
+    else if ((q + 1) * cs <= x) q++;
+    return q;
+}
+__host__ __device__ inline size_t nms_smem_bytes(int gw, int gh) { return (size_t)(gw + 2) * (gh + 2) * NMS_CELL_BYTES; }
+__device__ __forceinline__ void nms_cells(TrackScalars* sc, const NmsGrid& g, int w, int min_dist, unsigned char* smem_raw, long long* dbg)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int ncell = g.gw * g.gh;
-    unsigned long long* head = reinterpret_cast<unsigned long long*>(smem_raw);
-    int* new_acc = reinterpret_cast<int*>(head + ncell);        // packed (y << 16 | x) or -1, previous round
-    int* nxt_acc = new_acc + ncell;
+    // the grid is padded by one ring of empty cells: the 3x3 neighbourhoods below are nine unconditional loads
+    const int gwp = g.gw + 2, ncp = gwp * (g.gh + 2), ncell = g.gw * g.gh;
+    unsigned int* head_hi = reinterpret_cast<unsigned int*>(smem_raw);   // [2][ncp] eig bits of the cell's best alive candidate
+    unsigned int* head_lo = head_hi + 2 * ncp;                            // [2][ncp] its packed address (y << 16 | x)
+    int* acc = reinterpret_cast<int*>(head_lo + 2 * ncp);                 // [2][ncp] corner accepted by the cell in a round, or -1
+    uint8_t* flag = reinterpret_cast<uint8_t*>(acc + 2 * ncp);            // [2][ncp] some 3x3 neighbour accepted a corner in that round
+    unsigned short* pidx = reinterpret_cast<unsigned short*>(flag + 2 * ncp);   // [ncell] interior cell -> padded index
     const int n = sc->n_cand;
     const int r2 = min_dist * min_dist;
+    const float rcp = 1.0f / (float)g.cs;
     unsigned long long alive = 0ull;                            // bit k <-> candidate tid + k*nt
     const int per = (n + nt - 1) / nt;
     for (int k = 0; k < per && k < NMS_MAX_PER_THREAD; k++) if (tid + k * nt < n) alive |= (1ull << k);
-    for (int c = tid; c < ncell; c += nt) { new_acc[c] = -1; nxt_acc[c] = -1; }
+    // the first two candidates of a thread stay in registers (covers 2 * blockDim candidates without reloads)
+    const unsigned long long key0 = (tid < n) ? __ldg(&g.cand_key[tid]) : 0ull, key1 = (tid + nt < n) ? __ldg(&g.cand_key[tid + nt]) : 0ull;
+    auto cell_of = [&](unsigned long long key) {
+        return (div_cell((int)((key >> 16) & 0xffffu), rcp, g.cs) + 1) * gwp + div_cell((int)(key & 0xffffu), rcp, g.cs) + 1;
+    };
+    const int cell0 = cell_of(key0), cell1 = cell_of(key1);
+    for (int c = tid; c < 2 * ncp; c += nt) { head_hi[c] = 0u; head_lo[c] = 0u; acc[c] = -1; flag[c] = 0; }
+    for (int i = tid; i < ncell; i += nt) { int cy = i / g.gw, cx = i - cy * g.gw; pidx[i] = (unsigned short)((cy + 1) * gwp + cx + 1); }
     __shared__ int s_nacc;
     if (tid == 0) s_nacc = 0;
     int rounds = 0;
+    long long tA = 0, tB = 0, tC = 0, tl = clock64();
+    const long long tstart = tl;
     __syncthreads();
     while (true) {
-        for (int c = tid; c < ncell; c += nt) head[c] = 0ull;
-        __syncthreads();
-        auto visit = [&](unsigned long long key) -> bool {     // returns true if the candidate dies this round
-            unsigned addr = (unsigned)(key & 0xffffffffu);
-            int y = addr / w, x = addr - y * w;
-            int cx = x / g.cs, cy = y / g.cs;
-            if (rounds > 0) {
-                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.gh - 1); yy++)
-                    for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g.gw - 1); xx++) {
-                        int p = new_acc[yy * g.gw + xx];
-                        if (p >= 0) {
-                            int dx = x - (p & 0xffff), dy = y - (p >> 16);
-                            if (dx * dx + dy * dy < r2) return true;
-                        }
+        const int p = rounds & 1;
+        unsigned int* hh = head_hi + p * ncp;
+        unsigned int* hl = head_lo + p * ncp;
+        const int* acc_prev = acc + p * ncp;                    // written by the previous round as its "next"
+        const uint8_t* flag_prev = flag + p * ncp;
+        // phase A: kill by last round's accepted corners, bid the eig bits
+        auto visit = [&](unsigned long long key, int c) -> bool {     // returns true if the candidate dies this round
+            if (rounds > 0 && flag_prev[c]) {
+                const int x = (int)(key & 0xffffu), y = (int)((key >> 16) & 0xffffu);
+                bool dead = false;
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; dx++) {
+                        const int q = acc_prev[c + dy * gwp + dx];
+                        const int ex = x - (q & 0xffff), ey = y - (q >> 16);
+                        dead |= (q >= 0) && (ex * ex + ey * ey < r2);
                     }
+                if (dead) return true;
             }
-            atomicMax(&head[cy * g.gw + cx], key);
+            atomicMax(&hh[c], (unsigned)(key >> 32));
             return false;
         };
-        unsigned long long a = alive;
-        while (a) {
-            int k = __ffsll((long long)a) - 1;
-            a &= a - 1;
-            if (visit(__ldg(&g.cand_key[tid + k * nt]))) alive &= ~(1ull << k);
+        if ((alive & 1ull) && visit(key0, cell0)) alive &= ~1ull;
+        if ((alive & 2ull) && visit(key1, cell1)) alive &= ~2ull;
+        {
+            unsigned long long a = alive & ~3ull;
+            while (a) {
+                int k = __ffsll((long long)a) - 1;
+                a &= a - 1;
+                const unsigned long long key = __ldg(&g.cand_key[tid + k * nt]);
+                if (visit(key, cell_of(key))) alive &= ~(1ull << k);
+            }
         }
         for (int i = tid + NMS_MAX_PER_THREAD * nt; i < n; i += nt) {   // slow path: liveness in HBM
             if (rounds == 0) g.dead[i] = 0;
-            if (!g.dead[i] && visit(__ldg(&g.cand_key[i]))) g.dead[i] = 1;
+            if (!g.dead[i]) { const unsigned long long key = __ldg(&g.cand_key[i]); if (visit(key, cell_of(key))) g.dead[i] = 1; }
         }
         __syncthreads();
+        { long long t_ = clock64(); tA += t_ - tl; tl = t_; }
+        // phase B: among the candidates that carry the cell's best eig bits, the largest address wins
+        auto visit2 = [&](unsigned long long key, int c) {
+            if (hh[c] == (unsigned)(key >> 32)) atomicMax(&hl[c], (unsigned)(key & 0xffffffffu));
+        };
+        if (alive & 1ull) visit2(key0, cell0);
+        if (alive & 2ull) visit2(key1, cell1);
+        {
+            unsigned long long a = alive & ~3ull;
+            while (a) {
+                int k = __ffsll((long long)a) - 1;
+                a &= a - 1;
+                const unsigned long long key = __ldg(&g.cand_key[tid + k * nt]);
+                visit2(key, cell_of(key));
+            }
+        }
+        for (int i = tid + NMS_MAX_PER_THREAD * nt; i < n; i += nt)
+            if (!g.dead[i]) { const unsigned long long key = __ldg(&g.cand_key[i]); visit2(key, cell_of(key)); }
+        // next round's election arrays and this round's "accepted nearby" flags start clean
+        for (int c = tid; c < ncp; c += nt) { head_hi[(p ^ 1) * ncp + c] = 0u; head_lo[(p ^ 1) * ncp + c] = 0u; flag[(p ^ 1) * ncp + c] = 0; }
+        __syncthreads();
+        { long long t_ = clock64(); tB += t_ - tl; tl = t_; }
+        // phase C: a head that outranks its 8 neighbours is accepted
         int any = 0;
-        for (int c = tid; c < ncell; c += nt) {
-            unsigned long long hk = head[c];
+        int* acc_next = acc + (p ^ 1) * ncp;
+        uint8_t* flag_next = flag + (p ^ 1) * ncp;
+        for (int i = tid; i < ncell; i += nt) {
+            const int c = pidx[i];
+            const unsigned long long hk = ((unsigned long long)hh[c] << 32) | hl[c];
             int out = -1;
             if (hk) {
                 any = 1;
-                int cy = c / g.gw, cx = c - cy * g.gw;
                 bool top = true;
-                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.gh - 1); yy++)
-                    for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g.gw - 1); xx++)
-                        if (head[yy * g.gw + xx] > hk) top = false;
+#pragma unroll
+                for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                    for (int dx = -1; dx <= 1; dx++) {
+                        const int o = c + dy * gwp + dx;
+                        top &= !((((unsigned long long)hh[o] << 32) | hl[o]) > hk);
+                    }
                 if (top) {
-                    unsigned addr = (unsigned)(hk & 0xffffffffu);
-                    int y = addr / w, x = addr - y * w;
-                    out = (y << 16) | x;
-                    int p = atomicAdd(&s_nacc, 1);
-                    if (p < g.acc_cap) g.acc_key[p] = hk;
+                    out = (int)(hk & 0xffffffffu);          // (y << 16) | x
+#pragma unroll
+                    for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; dx++) flag_next[c + dy * gwp + dx] = 1;
+                    int q = atomicAdd(&s_nacc, 1);
+                    if (q < g.acc_cap) g.acc_key[q] = hk;
                 }
             }
-            nxt_acc[c] = out;
+            acc_next[c] = out;
         }
         rounds++;
-        if (!__syncthreads_or(any)) break;
-        int* t = new_acc; new_acc = nxt_acc; nxt_acc = t;
+        const int more = __syncthreads_or(any);
+        { long long t_ = clock64(); tC += t_ - tl; tl = t_; }
+        if (!more) break;
     }
+    if (dbg && tid == 0) { dbg[13] = tA; dbg[14] = tB; dbg[15] = tC; dbg[17] = clock64() - tstart; }
     if (tid == 0) { sc->n_acc = min(s_nacc, g.acc_cap); sc->nms_rounds = rounds; }
     __syncthreads();
 }
@@ -385,12 +490,15 @@ struct OutHeader { int n_out, n_prev, n_tracked, n_kept, n_new, n_cand, nms_roun
 // next-frame state.  Single CTA of 1024 threads; dynamic shared memory for the cell grid (see nms_cells).
 __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, FeatArrays fa, NmsGrid g, int w, int max_cnt, int min_dist,
                                                           CamParams cam, const double* dt_ptr, const uint16_t* depth, int dpitch /*elements*/,
-                                                          int depth_cam_cfg, const int* depth_valid_ptr, int h, OutHeader* out_hdr, gf_obs* out_obs)
+                                                          int depth_cam_cfg, const int* depth_valid_ptr, int h, OutHeader* out_hdr, gf_obs* out_obs,
+                                                          uint8_t* out_status /* may be null: copy of the LK status of the n_prev input features */)
 {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ unsigned long long keys[FE_SORT_CAP];
     const int tid = threadIdx.x;
-    nms_cells(sc, g, w, min_dist, dyn_smem);
+    const long long c0 = clock64();
+    nms_cells(sc, g, w, min_dist, dyn_smem, fa.dbg);
+    const long long c1 = clock64();
     const double dt = dt_ptr ? *dt_ptr : 1.0;
     const int depth_cam = depth_cam_cfg && depth_valid_ptr && *depth_valid_ptr;
     const int ncand = sc->n_cand;
@@ -398,7 +506,19 @@ __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, Feat
     const int want = max(max_cnt - n_kept, 0);
     const int nacc = sc->n_acc;
     int n_new;
-    if (nacc <= FE_SORT_CAP) {
+    if (nacc <= (int)blockDim.x) {
+        // few accepted corners (the usual case): position = number of larger keys (keys are distinct)
+        if (tid < nacc) keys[FE_SORT_CAP / 2 + tid] = g.acc_key[tid];
+        __syncthreads();
+        if (tid < nacc) {
+            const unsigned long long mine = keys[FE_SORT_CAP / 2 + tid];
+            int rank = 0;
+            for (int j = 0; j < nacc; j++) rank += keys[FE_SORT_CAP / 2 + j] > mine;
+            keys[rank] = mine;
+        }
+        __syncthreads();
+        n_new = min(want, nacc);
+    } else if (nacc <= FE_SORT_CAP) {
         int np2 = 1;
         while (np2 < nacc) np2 <<= 1;
         for (int i = tid; i < np2; i += blockDim.x) keys[i] = (i < nacc) ? g.acc_key[i] : 0ull;
@@ -433,6 +553,7 @@ __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, Feat
             __syncthreads();
         }
     }
+    const long long c2 = clock64();
     const int total = n_kept + n_new;
     const int n_id = sc->n_id;
     // addPoints + per-feature outputs; thread i <-> feature i of the new cur_pts order (kept..., new...)
@@ -443,9 +564,8 @@ __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, Feat
         if (tid < n_kept) {
             p = fa.kept_pts[tid]; id = fa.kept_ids[tid]; cnt = fa.kept_cnt[tid]; un_prev = fa.kept_un[tid]; has_prev = true;
         } else {
-            unsigned addr = (unsigned)(keys[tid - n_kept] & 0xffffffffu);
-            int y = addr / w, x = addr - y * w;
-            p = make_float2((float)x, (float)y); id = n_id + (tid - n_kept); cnt = 1;
+            const unsigned addr = (unsigned)(keys[tid - n_kept] & 0xffffffffu);
+            p = make_float2((float)(addr & 0xffffu), (float)(addr >> 16)); id = n_id + (tid - n_kept); cnt = 1;
         }
         double ux, uy;
         cam_lift(cam, (double)p.x, (double)p.y, ux, uy);
@@ -469,6 +589,7 @@ __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, Feat
         // state for the next frame (prev_pts = cur_pts; prev_un_pts_map = cur_un_pts_map)
         fa.prev_pts[tid] = p; fa.ids[tid] = id; fa.track_cnt[tid] = cnt; fa.prev_un[tid] = un;
     }
+    if (out_status && tid < sc->n_prev) out_status[tid] = fa.status[tid];
     __syncthreads();
     if (tid == 0) {
         out_hdr->n_out = total; out_hdr->n_prev = sc->n_prev; out_hdr->n_tracked = sc->n_tracked;
@@ -477,6 +598,7 @@ __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, Feat
         sc->n_new = n_new; sc->n_out = total;
         sc->n_prev = total; sc->n_id = n_id + n_new; sc->eig_fixups = 0;
     }
+    GF_DBG(8, c1 - c0); GF_DBG(9, c2 - c1); GF_DBG(10, clock64() - c2); GF_DBG(11, nacc); GF_DBG(12, ncand);
 }
 
 }  // namespace gf

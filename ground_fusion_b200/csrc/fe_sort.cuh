@@ -148,46 +148,109 @@ GF_HD inline void setmask_sort(sort_elem* v, int n)
 
 
 #ifdef __CUDACC__
-// Parallel replay of setmask_sort by one CTA (call from all threads; v and the work arrays live in shared memory).
-// __introsort_loop recurses on disjoint ranges [first, cut) and [cut, last) with the same decremented depth limit,
-// so all ranges of one recursion level can be partitioned concurrently, one thread each, performing exactly the
-// comparisons and swaps of the sequential code.  __final_insertion_sort then only moves an element within its
-// leaf range (every element left of a cut is >= every element right of it and the comparator is strict), so each
-// leaf is finished by one thread: the leaf that contains index 0 with the guarded __insertion_sort logic, the others
-// with __unguarded_linear_insert (their left neighbour is the sentinel, as in the sequential run).
-constexpr int SORT_PAR_MAX = 512;   // larger inputs use the sequential replay (leaf/range tables are sized for this)
-struct SortWork { int first[2][128], last[2][128], depth[2][128], n[2]; short leaf_first[SORT_PAR_MAX], leaf_last[SORT_PAR_MAX]; int nleaf; };
+// Parallel replay of setmask_sort by one CTA (call from all threads, blockDim.x >= n and a multiple of 32; v and the
+// work arrays live in shared memory).  Three observations make the sequential algorithm parallel without changing a
+// single comparison outcome or element position:
+//  (1) __introsort_loop recurses on the disjoint ranges [first, cut) and [cut, last) with the same decremented depth
+//      limit, so all ranges of one recursion level are independent: one warp per range.
+//  (2) __unguarded_partition only ever looks at elements it has not moved yet: before swap k, lo scans originals in
+//      (L[k-1], R[k-1]) and hi scans originals below R[k-1].  With L = ascending positions where lo stops
+//      (!comp(x, pivot)) and R = descending positions where hi stops (!comp(pivot, x)) in the ORIGINAL range, swap k
+//      exchanges L[k] and R[k] for every k with L[k] < R[k] (a monotone condition, k* swaps in total), and the
+//      returned cut is min(L[k*], R[k*-1]) (lo runs into the first element hi has already moved).  Ranks in L and R are
+//      warp prefix sums, the swaps touch disjoint positions.
+//  (3) __final_insertion_sort never moves an element across a cut (left of a cut everything is >= pivot >= everything
+//      right of it, and the comparator is strict), and insertion sort is stable: its result is the stable sort of every
+//      leaf range, i.e. element i of a leaf goes to leaf_first + #{j: key_j > key_i} + #{j < i: key_j == key_i}.
+constexpr int SORT_PAR_MAX = 512;   // larger inputs use the sequential replay
+constexpr int SORT_QCAP = 64;       // ranges longer than 16 on one level: at most n/17
+struct SortWork {
+    short first[2][SORT_QCAP], last[2][SORT_QCAP], depth[2][SORT_QCAP];
+    int n[2];
+    short lpos[SORT_PAR_MAX], rasc[SORT_PAR_MAX];      // per range, at offset first: stop positions of lo / hi (ascending)
+    short leaf_first[SORT_PAR_MAX], leaf_last[SORT_PAR_MAX];   // per position: its leaf range
+};
+
+// one warp: libstdc++ __unguarded_partition_pivot on [first, last), last - first > 16; returns the cut
+__device__ inline int sm_warp_partition(sort_elem* v, int first, int last, SortWork& W, int lane)
+{
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+    if (lane == 0) {                                                // __move_median_to_first
+        sort_elem *f = v + first, *a = f + 1, *b = f + (last - first) / 2, *c = v + last - 1;
+        if (sm_comp(*a, *b)) {
+            if (sm_comp(*b, *c)) sm_swap(f, b);
+            else if (sm_comp(*a, *c)) sm_swap(f, c);
+            else sm_swap(f, a);
+        } else if (sm_comp(*a, *c)) sm_swap(f, a);
+        else if (sm_comp(*b, *c)) sm_swap(f, c);
+        else sm_swap(f, b);
+    }
+    __syncwarp();
+    const int pv = (int)(v[first] >> 32);
+    short* lpos = W.lpos + first;
+    short* rasc = W.rasc + first;
+    int nL = 0, nR = 0;
+    for (int base = first + 1; base < last; base += 32) {
+        const int p = base + lane;
+        const int c = (p < last) ? (int)(v[p] >> 32) : 0;
+        const bool sl = (p < last) && !(c > pv), sr = (p < last) && !(pv > c);
+        const unsigned bl = __ballot_sync(full, sl), br = __ballot_sync(full, sr);
+        if (sl) lpos[nL + __popc(bl & lt)] = (short)p;
+        if (sr) rasc[nR + __popc(br & lt)] = (short)p;
+        nL += __popc(bl);
+        nR += __popc(br);
+    }
+    __syncwarp();
+    const int m = min(nL, nR);
+    int ks = 0;                                                     // number of swaps
+    for (int base = 0; base < m; base += 32) {
+        const int k = base + lane;
+        const bool ok = (k < m) && (lpos[k] < rasc[nR - 1 - k]);
+        ks += __popc(__ballot_sync(full, ok));
+    }
+    for (int k = lane; k < ks; k += 32) sm_swap(v + lpos[k], v + rasc[nR - 1 - k]);
+    int cut = 0x7fffffff;
+    if (ks < nL) cut = lpos[ks];
+    if (ks >= 1) cut = min(cut, (int)rasc[nR - ks]);
+    __syncwarp();
+    return cut;
+}
 
 __device__ inline void setmask_sort_parallel(sort_elem* v, int n, SortWork& W)
 {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     if (n <= 0) return;
     if (n > SORT_PAR_MAX) { if (tid == 0) setmask_sort(v, n); __syncthreads(); return; }
     if (tid == 0) {
         int lg = 0;
         for (int t = n; t > 1; t >>= 1) lg++;
-        W.first[0][0] = 0; W.last[0][0] = n; W.depth[0][0] = 2 * lg; W.n[0] = 1; W.n[1] = 0; W.nleaf = 0;
+        W.first[0][0] = 0; W.last[0][0] = (short)n; W.depth[0][0] = (short)(2 * lg); W.n[0] = (n > 16) ? 1 : 0; W.n[1] = 0;
     }
+    if (n <= 16 && tid < n) { W.leaf_first[tid] = 0; W.leaf_last[tid] = (short)n; }
     __syncthreads();
     int cur = 0;
     while (true) {
         const int nr = W.n[cur];
         if (nr == 0) break;
-        if (tid < nr) {
-            int first = W.first[cur][tid], last = W.last[cur][tid], depth = W.depth[cur][tid];
-            if (last - first > 16) {
-                if (depth == 0) {
-                    sm_heap_sort(v + first, v + last);                 // __partial_sort(first, last, last): range is final
-                    int k = atomicAdd(&W.nleaf, 1); W.leaf_first[k] = (short)first; W.leaf_last[k] = (short)last;
-                } else {
-                    --depth;
-                    int cut = (int)(sm_partition_pivot(v + first, v + last) - v);
-                    int k = atomicAdd(&W.n[cur ^ 1], 2);
-                    W.first[cur ^ 1][k] = first; W.last[cur ^ 1][k] = cut; W.depth[cur ^ 1][k] = depth;
-                    W.first[cur ^ 1][k + 1] = cut; W.last[cur ^ 1][k + 1] = last; W.depth[cur ^ 1][k + 1] = depth;
-                }
-            } else if (last > first) {
-                int k = atomicAdd(&W.nleaf, 1); W.leaf_first[k] = (short)first; W.leaf_last[k] = (short)last;
+        for (int r = wid; r < nr; r += nw) {
+            const int first = W.first[cur][r], last = W.last[cur][r], depth = W.depth[cur][r];
+            if (depth == 0) {                                      // __partial_sort(first, last, last): the range is final
+                if (lane == 0) sm_heap_sort(v + first, v + last);
+                for (int p = first + lane; p < last; p += 32) { W.leaf_first[p] = (short)first; W.leaf_last[p] = (short)last; }
+                __syncwarp();
+                continue;
+            }
+            const int cut = sm_warp_partition(v, first, last, W, lane);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const int a = half ? cut : first, b = half ? last : cut;
+                if (b - a > 16) {
+                    if (lane == 0) {
+                        const int k = atomicAdd(&W.n[cur ^ 1], 1);
+                        W.first[cur ^ 1][k] = (short)a; W.last[cur ^ 1][k] = (short)b; W.depth[cur ^ 1][k] = (short)(depth - 1);
+                    }
+                } else
+                    for (int p = a + lane; p < b; p += 32) { W.leaf_first[p] = (short)a; W.leaf_last[p] = (short)b; }
             }
         }
         __syncthreads();
@@ -195,24 +258,21 @@ __device__ inline void setmask_sort_parallel(sort_elem* v, int n, SortWork& W)
         cur ^= 1;
         __syncthreads();
     }
-    // final insertion sort, leaf by leaf
-    const int nl = W.nleaf;
-    if (tid < nl) {
-        const int first = W.leaf_first[tid], last = W.leaf_last[tid];
-        for (int i = first; i < last; i++) {
-            if (i == 0) continue;
-            // __final_insertion_sort: elements 1..15 use the guarded form (compare with *begin first), the rest the unguarded one
-            if (i < 16 && n > 16 ? true : (n <= 16)) {
-                if (sm_comp(v[i], v[0])) {
-                    sort_elem val = v[i];
-                    for (int p = i; p != 0; --p) v[p] = v[p - 1];
-                    v[0] = val;
-                    continue;
-                }
-            }
-            sm_unguarded_linear_insert(v + i);
+    // __final_insertion_sort == stable sort of every leaf
+    sort_elem e = 0;
+    int dst = -1;
+    if (tid < n) {
+        const int a = W.leaf_first[tid], b = W.leaf_last[tid];
+        e = v[tid];
+        const int c = (int)(e >> 32);
+        dst = a;
+        for (int j = a; j < b; j++) {
+            const int cj = (int)(v[j] >> 32);
+            dst += (cj > c) || (cj == c && j < tid);
         }
     }
+    __syncthreads();
+    if (dst >= 0) v[dst] = e;
     __syncthreads();
 }
 #endif

@@ -1,15 +1,20 @@
 // fe_tracker.cu -- gf_tracker_* and gf_stage_* (C ABI), the host side of the B200 front end.
 //
 // Mirrors FeatureTracker::trackImage (reference vins_estimator/src/featureTracker/feature_tracker.cpp:103-372).
-// One frame = one fixed sequence of copies and kernels on two streams (no host round trip inside the
-// frame; the only synchronisation is the wait for the result):
+// One frame = fixed sequences of copies and kernels on three streams (no host round trip inside the frame; the only
+// synchronisation is the wait for the result).  Up to two frames are in flight: everything that does not depend on
+// the previous frame's result (upload, pyramid, min-eig map) runs ahead on s_pre while s_main is still tracking the
+// previous frame, so in steady state the frame period is the dependent chain alone.
 //
-//   s_main: H2D gray/depth -> pyrDown x3 -> [prediction LK] -> k_track (fwd LK 3 lvls + bwd LK 1 lvl +
-//           status rules) -> k_compact_setmask -> mask disks -> (join) -> masked max -> candidates ->
-//           min-distance rounds -> k_finalize (top-K, addPoints, undistort, velocity, depth) -> D2H
-//   s_aux : (fork after H2D) k_min_eig -> k_eig_verify                       [independent of LK/mask]
+//   s_pre : H2D gray/depth -> pyrDown x3 (ev_pyr) -> k_cov_rows -> k_box_chain -> k_eig_from_box (ev_eig)
+//   s_main: (ev_pyr) [prediction LK] -> k_track (fwd LK 3 lvls + bwd LK 1 lvl + status rules) -> k_compact_setmask
+//           -> (ev_eig) masked max -> candidates -> k_select_finalize (min-distance rounds, top-K, addPoints,
+//           undistort, velocity, depth)  (ev_dep)
+//   s_out : (ev_dep) D2H of the result block
 //
-// All feature state (prev_pts, ids, track_cnt, undistorted points, n_id) lives in HBM between frames.
+// Buffers touched by more than one frame in flight are rotated: 3 pyramids (prev/cur/next), 2 depth images, 2 eig
+// maps, 2 frame-parameter blocks, 2 result blocks.  All feature state (prev_pts, ids, track_cnt, undistorted points,
+// n_id) lives in HBM between frames and is only touched on s_main.
 #include <stdlib.h>
 #include <new>
 #include <vector>
@@ -25,7 +30,6 @@ std::atomic<uint64_t> g_launches{0};
 
 
 struct FrameParams { double dt; int has_pred; int depth_valid; };
-constexpr int NMS_CELL_BYTES = 16;   // head key + two accepted buffers per cell (nms_cells)
 
 // ------------------------------------------------------------------------------------------------
 // kernels that need the LK device code
@@ -38,7 +42,8 @@ __global__ void __launch_bounds__(LK_THREADS) k_lk_stage(Pyramid I, Pyramid J, c
     if (i >= n) return;
     float2 p = prev_pts[i], init = use_init ? next_pts[i] : p, out;
     int st, iters = 0;
-    lk_track_point(sm, tid, I, J, p, init, use_init != 0, max_level, out, st, iters);
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    lk_track_point(sm, tid, I, J, p, init, use_init != 0, max_level, out, st, iters, pc);
     if (tid == 0) { next_pts[i] = out; status[i] = (uint8_t)st; }
 }
 
@@ -50,7 +55,8 @@ __global__ void __launch_bounds__(LK_THREADS) k_lk_pred(Pyramid prev, Pyramid cu
     if (i >= sc->n_prev) return;
     float2 out;
     int st, iters = 0;
-    lk_track_point(sm, tid, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st, iters);
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    lk_track_point(sm, tid, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st, iters, pc);
     if (tid == 0) { fa.cur_pts[i] = out; fa.status[i] = (uint8_t)st; if (st) atomicAdd(&sc->pred_succ, 1); atomicAdd(&sc->lk_iters, iters); }
 }
 
@@ -63,14 +69,16 @@ __global__ void __launch_bounds__(LK_THREADS) k_track(Pyramid prev, Pyramid cur,
     const int tid = threadIdx.x, i = blockIdx.x;
     if (i >= sc->n_prev) return;
     const float2 p = fa.prev_pts[i];
+    const long long t0 = clock64();
     float2 q;
     int st, iters = 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (fp->has_pred && sc->pred_succ >= 10) { q = fa.cur_pts[i]; st = fa.status[i]; }
-    else lk_track_point(sm, tid, prev, cur, p, p, false, 3, q, st, iters);
+    else lk_track_point(sm, tid, prev, cur, p, p, false, 3, q, st, iters, pc);
     if (flow_back) {
         float2 r;
         int rst;
-        lk_track_point(sm, tid, cur, prev, q, p, true, 1, r, rst, iters);
+        lk_track_point(sm, tid, cur, prev, q, p, true, 1, r, rst, iters, pc);
         double dx = (double)(p.x - r.x), dy = (double)(p.y - r.y);
         st = (st && rst && sqrt(dx * dx + dy * dy) <= 0.5) ? 1 : 0;
     }
@@ -84,7 +92,11 @@ __global__ void __launch_bounds__(LK_THREADS) k_track(Pyramid prev, Pyramid cur,
         int grey = (p_u >= 0 && p_u < row && p_v >= 0 && p_v < col) ? cur.lv[0].ptr[(size_t)p_u * cur.lv[0].pitch + p_v] : 0;
         if (grey > 250) st = 0;
     }
-    if (tid == 0) { fa.cur_pts[i] = q; fa.status[i] = (uint8_t)st; atomicAdd(&sc->lk_iters, iters); }
+    if (tid == 0) {
+        fa.cur_pts[i] = q; fa.status[i] = (uint8_t)st; atomicAdd(&sc->lk_iters, iters);
+        if (fa.dbg && i < 4) for (int k = 0; k < 8; k++) fa.dbg[32 + 8 * i + k] = pc[k];
+        if (fa.dbg) { fa.dbg[64 + 8 * i] = clock64() - t0; fa.dbg[64 + 8 * i + 1] = iters; }
+    }
 }
 
 // setPrediction (feature_tracker.cpp:1006-1027)
@@ -148,38 +160,44 @@ __global__ void k_pitch_copy_u8(const uint8_t* src, int spitch, uint8_t* dst, in
 using namespace gf;
 
 // ------------------------------------------------------------------------------------------------
+constexpr int GF_PIPE = 2;           // frames in flight
+struct OutBlock { OutHeader hdr; uint8_t status[FE_CAP]; gf_obs obs[FE_CAP]; };   // one D2H copy per frame
+
 struct gf_tracker {
     int device, w, h;
     gf_tracker_cfg cfg;
     CamParams cam;
-    cudaStream_t s_main, s_aux;
-    cudaEvent_t ev_fork, ev_eig, ev_t0, ev_t1;
-    cudaEvent_t ev_st[GF_FE_STAGES + 2];   // stage boundaries on s_main (0..6) + aux start/end (7,8)
+    cudaStream_t s_pre, s_main, s_out;
+    cudaEvent_t ev_pyr[2], ev_eig[2], ev_dep[2], ev_t0[2], ev_out[2];
+    cudaEvent_t ev_st[GF_FE_STAGES + 2];   // stage boundaries (profiling mode)
+    cudaEvent_t ev_span0, ev_span1;        // gf_tracker_timer_start / _stop
     bool profiling;
     float stage_ms[GF_FE_STAGES];
-    cudaGraphExec_t graph[4];            // frame body, keyed by (pyramid slot, prediction pending)
-    int graph_kernels[4];
+    // CUDA graphs keyed by frame number mod 6 (= pyramid slot mod 3 x two-slot buffers)
+    cudaGraphExec_t g_pyr[6], g_eig[6], g_dep1[6][2], g_dep2[6];
+    int gk_pyr[6], gk_eig[6], gk_dep1[6][2], gk_dep2[6];
     bool use_graph;
-    uint8_t* d_pyr[2][4];
+    uint8_t* d_pyr[3][4];
     int lw[4], lh[4], lp[4];
-    uint16_t* d_depth; int depth_pitch_el;
-    float* d_eig; int epitch;
-    uint8_t* d_mask; int mpitch;
-    double *d_spec_start, *d_spec_end; int nbands;
+    uint16_t* d_depth[2]; int depth_pitch_el;
+    float* d_eig[2]; int epitch;
+    double* d_cov; float* d_box;          // min-eig intermediates (fe_eig.cuh), only live inside one frame's s_pre work
     NmsGrid grid; size_t grid_cells;
     TrackScalars* d_sc;
     FeatArrays fa;
-    OutHeader* d_hdr; gf_obs* d_obs;
-    FrameParams* d_fp;
+    OutBlock* d_out[2];
+    FrameParams* d_fp[2];
     int* d_tmp_ids; double* d_tmp_xyz;
     // pinned host
-    uint8_t* h_gray; uint16_t* h_depth; OutHeader* h_hdr; gf_obs* h_obs; uint8_t* h_status; FrameParams* h_fp;
+    uint8_t* h_gray; uint16_t* h_depth; OutBlock* h_out[2]; FrameParams* h_fp[2];
     int* h_tmp_ids; double* h_tmp_xyz;
-    int cur;             // pyramid slot that receives the next frame
+    long long n_submitted, n_waited;     // frame counters; n_submitted - n_waited frames are in flight
     double prev_time;
-    bool has_pred, pending, depth_last;
+    bool has_pred, depth_valid[2];
     float last_ms;
 };
+
+static inline int in_flight(const gf_tracker* t) { return (int)(t->n_submitted - t->n_waited); }
 
 static Pyramid make_pyr(const gf_tracker* t, int slot)
 {
@@ -211,13 +229,14 @@ static int select_device(int device)
 
 static int alloc_nms_grid(NmsGrid& g, int w, int h, int min_dist, size_t* smem_bytes)
 {
-    g.cs = min_dist > 16 ? min_dist : 16;
+    g.cs = min_dist > 16 ? min_dist : 16;      // any cell size >= min_dist is exact; larger cells only cost rounds
+    while (nms_smem_bytes((w + g.cs - 1) / g.cs, (h + g.cs - 1) / g.cs) > 160 * 1024) g.cs++;
     g.gw = (w + g.cs - 1) / g.cs;
     g.gh = (h + g.cs - 1) / g.cs;
     g.acc_cap = w * h / 16 + 64;
     GF_CUDA(cudaMalloc(&g.cand_key, (size_t)w * h * sizeof(unsigned long long)));
     GF_CUDA(cudaMalloc(&g.acc_key, (size_t)g.acc_cap * sizeof(unsigned long long)));
-    size_t bytes = (size_t)g.gw * g.gh * NMS_CELL_BYTES;
+    size_t bytes = nms_smem_bytes(g.gw, g.gh);
     if (bytes > 160 * 1024) return set_err(GF_ERR_UNSUPPORTED, "image too large for the min-distance cell grid");
     GF_CUDA(cudaMalloc(&g.dead, (size_t)w * h));
     GF_CUDA(cudaFuncSetAttribute(k_select_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -241,12 +260,23 @@ static int enqueue_gftt_select(cudaStream_t s, TrackScalars* d_sc, const float2*
     return GF_OK;
 }
 
-static int enqueue_min_eig(cudaStream_t s, const Level& img, float* d_eig, int epitch, double* spec_start, double* spec_end,
-                           int nbands, int* d_fixups)
+// cov: cov_rows_elems(w, h) doubles (zero-initialised once: the padding columns of the last block are streamed too);
+// box: box_elems(w, h) floats
+static int enqueue_min_eig(cudaStream_t s, const Level& img, float* d_eig, int epitch, double* d_cov, float* d_box)
 {
-    dim3 g((img.w + EIG_TX - 1) / EIG_TX, nbands);
-    k_min_eig<<<g, EIG_TX, 0, s>>>(img, d_eig, epitch, spec_start, spec_end); GF_LAUNCHED();
-    k_eig_verify<<<(img.w + 127) / 128, 128, 0, s>>>(img, d_eig, epitch, spec_start, spec_end, nbands, d_fixups); GF_LAUNCHED();
+    static bool attr_done[64] = {};     // per device
+    int dev = 0;
+    GF_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        GF_CUDA(cudaFuncSetAttribute(k_box_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BC_SMEM));
+        attr_done[dev & 63] = true;
+    }
+    dim3 g((img.w + EIG_TX - 1) / EIG_TX, (img.h + EIG_BAND - 1) / EIG_BAND);
+    k_cov_rows<<<g, EIG_TX, 0, s>>>(img, d_cov); GF_LAUNCHED();
+    const int bp = (img.w + 31) / 32 * 32;
+    k_box_chain<<<(img.w + 31) / 32, 96, BC_SMEM, s>>>(d_cov, d_box, bp, img.w, img.h); GF_LAUNCHED();
+    dim3 g3((img.w + 63) / 64, (img.h + 15) / 16);
+    k_eig_from_box<<<g3, 256, 0, s>>>(d_box, bp, d_eig, epitch, img.w, img.h); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     return GF_OK;
 }
@@ -283,31 +313,40 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     if (!t) return set_err(GF_ERR_CUDA, "out of host memory");
     memset(t, 0, sizeof(*t));
     t->device = device; t->w = width; t->h = height; t->cfg = *cfg; t->cam = make_cam(cfg->pinhole);
+    GF_CUDA(cudaStreamCreateWithFlags(&t->s_pre, cudaStreamNonBlocking));
     GF_CUDA(cudaStreamCreateWithFlags(&t->s_main, cudaStreamNonBlocking));
-    GF_CUDA(cudaStreamCreateWithFlags(&t->s_aux, cudaStreamNonBlocking));
-    GF_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
-    GF_CUDA(cudaEventCreateWithFlags(&t->ev_eig, cudaEventDisableTiming));
-    GF_CUDA(cudaEventCreate(&t->ev_t0));
-    GF_CUDA(cudaEventCreate(&t->ev_t1));
+    GF_CUDA(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        GF_CUDA(cudaEventCreateWithFlags(&t->ev_pyr[i], cudaEventDisableTiming));
+        GF_CUDA(cudaEventCreateWithFlags(&t->ev_eig[i], cudaEventDisableTiming));
+        GF_CUDA(cudaEventCreateWithFlags(&t->ev_dep[i], cudaEventDisableTiming));
+        GF_CUDA(cudaEventCreate(&t->ev_t0[i]));
+        GF_CUDA(cudaEventCreate(&t->ev_out[i]));
+    }
     for (int i = 0; i < GF_FE_STAGES + 2; i++) GF_CUDA(cudaEventCreate(&t->ev_st[i]));
+    GF_CUDA(cudaEventCreate(&t->ev_span0)); GF_CUDA(cudaEventCreate(&t->ev_span1));
     int lw = width, lh = height;
     for (int l = 0; l < 4; l++) {
         t->lw[l] = lw; t->lh[l] = lh; t->lp[l] = align_up(lw, 16);
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < 3; s++) {
             GF_CUDA(cudaMalloc(&t->d_pyr[s][l], (size_t)t->lp[l] * lh + 16));   // +16: aligned window loads may overrun the last row by <4 B
             GF_CUDA(cudaMemset(t->d_pyr[s][l], 0, (size_t)t->lp[l] * lh + 16));
         }
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
     }
     t->depth_pitch_el = align_up(width, 8);
-    GF_CUDA(cudaMalloc(&t->d_depth, (size_t)t->depth_pitch_el * height * sizeof(uint16_t)));
     t->epitch = align_up(width, 4);
-    GF_CUDA(cudaMalloc(&t->d_eig, (size_t)t->epitch * height * sizeof(float)));
-    t->mpitch = align_up(width, 16);
-    GF_CUDA(cudaMalloc(&t->d_mask, (size_t)t->mpitch * height));
-    t->nbands = (height + EIG_BAND - 1) / EIG_BAND;
-    GF_CUDA(cudaMalloc(&t->d_spec_start, (size_t)t->nbands * 3 * width * sizeof(double)));
-    GF_CUDA(cudaMalloc(&t->d_spec_end, (size_t)t->nbands * 3 * width * sizeof(double)));
+    for (int i = 0; i < 2; i++) {
+        GF_CUDA(cudaMalloc(&t->d_depth[i], (size_t)t->depth_pitch_el * height * sizeof(uint16_t)));
+        GF_CUDA(cudaMalloc(&t->d_eig[i], (size_t)t->epitch * height * sizeof(float)));
+        GF_CUDA(cudaMalloc(&t->d_out[i], sizeof(OutBlock)));
+        GF_CUDA(cudaMalloc(&t->d_fp[i], sizeof(FrameParams)));
+        GF_CUDA(cudaHostAlloc(&t->h_out[i], sizeof(OutBlock), cudaHostAllocDefault));
+        GF_CUDA(cudaHostAlloc(&t->h_fp[i], sizeof(FrameParams), cudaHostAllocDefault));
+    }
+    GF_CUDA(cudaMalloc(&t->d_cov, cov_rows_elems(width, height) * sizeof(double)));
+    GF_CUDA(cudaMemset(t->d_cov, 0, cov_rows_elems(width, height) * sizeof(double)));
+    GF_CUDA(cudaMalloc(&t->d_box, box_elems(width, height) * sizeof(float)));
     rc = alloc_nms_grid(t->grid, width, height, cfg->min_dist, &t->grid_cells);
     if (rc) return rc;
     GF_CUDA(cudaMalloc(&t->d_sc, sizeof(TrackScalars)));
@@ -319,18 +358,12 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     GF_CUDA(cudaMalloc(&fa.kept_pts, FE_CAP * sizeof(float2))); GF_CUDA(cudaMalloc(&fa.kept_ids, FE_CAP * sizeof(int)));
     GF_CUDA(cudaMalloc(&fa.kept_cnt, FE_CAP * sizeof(int))); GF_CUDA(cudaMalloc(&fa.kept_un, FE_CAP * sizeof(float2)));
     GF_CUDA(cudaMalloc(&fa.pred_pts, FE_CAP * sizeof(float2)));
+    GF_CUDA(cudaMalloc(&fa.dbg, FE_DBG_N * sizeof(long long))); GF_CUDA(cudaMemset(fa.dbg, 0, FE_DBG_N * sizeof(long long)));
     GF_CUDA(cudaMemset(fa.status, 0, FE_CAP));
-    GF_CUDA(cudaMalloc(&t->d_hdr, sizeof(OutHeader)));
-    GF_CUDA(cudaMalloc(&t->d_obs, FE_CAP * sizeof(gf_obs)));
-    GF_CUDA(cudaMalloc(&t->d_fp, sizeof(FrameParams)));
     GF_CUDA(cudaMalloc(&t->d_tmp_ids, FE_CAP * sizeof(int)));
     GF_CUDA(cudaMalloc(&t->d_tmp_xyz, FE_CAP * 3 * sizeof(double)));
     GF_CUDA(cudaHostAlloc(&t->h_gray, (size_t)width * height, cudaHostAllocDefault));
     GF_CUDA(cudaHostAlloc(&t->h_depth, (size_t)width * height * sizeof(uint16_t), cudaHostAllocDefault));
-    GF_CUDA(cudaHostAlloc(&t->h_hdr, sizeof(OutHeader), cudaHostAllocDefault));
-    GF_CUDA(cudaHostAlloc(&t->h_obs, FE_CAP * sizeof(gf_obs), cudaHostAllocDefault));
-    GF_CUDA(cudaHostAlloc(&t->h_status, FE_CAP, cudaHostAllocDefault));
-    GF_CUDA(cudaHostAlloc(&t->h_fp, sizeof(FrameParams), cudaHostAllocDefault));
     GF_CUDA(cudaHostAlloc(&t->h_tmp_ids, FE_CAP * sizeof(int), cudaHostAllocDefault));
     GF_CUDA(cudaHostAlloc(&t->h_tmp_xyz, FE_CAP * 3 * sizeof(double), cudaHostAllocDefault));
     t->use_graph = getenv("GF_NO_GRAPH") == nullptr;
@@ -343,21 +376,31 @@ void gf_tracker_destroy(gf_tracker* t)
 {
     if (!t) return;
     cudaSetDevice(t->device);
-    cudaStreamSynchronize(t->s_main); cudaStreamSynchronize(t->s_aux);
-    for (int k = 0; k < 4; k++) if (t->graph[k]) cudaGraphExecDestroy(t->graph[k]);
-    for (int s = 0; s < 2; s++) for (int l = 0; l < 4; l++) cudaFree(t->d_pyr[s][l]);
-    cudaFree(t->d_depth); cudaFree(t->d_eig); cudaFree(t->d_mask); cudaFree(t->d_spec_start); cudaFree(t->d_spec_end);
+    cudaStreamSynchronize(t->s_pre); cudaStreamSynchronize(t->s_main); cudaStreamSynchronize(t->s_out);
+    for (int k = 0; k < 6; k++) {
+        if (t->g_pyr[k]) cudaGraphExecDestroy(t->g_pyr[k]);
+        if (t->g_eig[k]) cudaGraphExecDestroy(t->g_eig[k]);
+        if (t->g_dep2[k]) cudaGraphExecDestroy(t->g_dep2[k]);
+        for (int p = 0; p < 2; p++) if (t->g_dep1[k][p]) cudaGraphExecDestroy(t->g_dep1[k][p]);
+    }
+    for (int s = 0; s < 3; s++) for (int l = 0; l < 4; l++) cudaFree(t->d_pyr[s][l]);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(t->d_depth[i]); cudaFree(t->d_eig[i]); cudaFree(t->d_out[i]); cudaFree(t->d_fp[i]);
+        cudaFreeHost(t->h_out[i]); cudaFreeHost(t->h_fp[i]);
+        cudaEventDestroy(t->ev_pyr[i]); cudaEventDestroy(t->ev_eig[i]); cudaEventDestroy(t->ev_dep[i]);
+        cudaEventDestroy(t->ev_t0[i]); cudaEventDestroy(t->ev_out[i]);
+    }
+    cudaFree(t->d_cov); cudaFree(t->d_box);
     free_nms_grid(t->grid);
     cudaFree(t->d_sc);
     FeatArrays& fa = t->fa;
     cudaFree(fa.prev_pts); cudaFree(fa.ids); cudaFree(fa.track_cnt); cudaFree(fa.prev_un); cudaFree(fa.cur_pts); cudaFree(fa.status);
-    cudaFree(fa.kept_pts); cudaFree(fa.kept_ids); cudaFree(fa.kept_cnt); cudaFree(fa.kept_un); cudaFree(fa.pred_pts);
-    cudaFree(t->d_hdr); cudaFree(t->d_obs); cudaFree(t->d_fp); cudaFree(t->d_tmp_ids); cudaFree(t->d_tmp_xyz);
-    cudaFreeHost(t->h_gray); cudaFreeHost(t->h_depth); cudaFreeHost(t->h_hdr); cudaFreeHost(t->h_obs); cudaFreeHost(t->h_status);
-    cudaFreeHost(t->h_fp); cudaFreeHost(t->h_tmp_ids); cudaFreeHost(t->h_tmp_xyz);
-    cudaStreamDestroy(t->s_main); cudaStreamDestroy(t->s_aux);
+    cudaFree(fa.kept_pts); cudaFree(fa.kept_ids); cudaFree(fa.kept_cnt); cudaFree(fa.kept_un); cudaFree(fa.pred_pts); cudaFree(fa.dbg);
+    cudaFree(t->d_tmp_ids); cudaFree(t->d_tmp_xyz);
+    cudaFreeHost(t->h_gray); cudaFreeHost(t->h_depth); cudaFreeHost(t->h_tmp_ids); cudaFreeHost(t->h_tmp_xyz);
+    cudaStreamDestroy(t->s_pre); cudaStreamDestroy(t->s_main); cudaStreamDestroy(t->s_out);
     for (int i = 0; i < GF_FE_STAGES + 2; i++) cudaEventDestroy(t->ev_st[i]);
-    cudaEventDestroy(t->ev_fork); cudaEventDestroy(t->ev_eig); cudaEventDestroy(t->ev_t0); cudaEventDestroy(t->ev_t1);
+    cudaEventDestroy(t->ev_span0); cudaEventDestroy(t->ev_span1);
     delete t;
 }
 
@@ -369,127 +412,182 @@ int gf_tracker_host_buffers(gf_tracker* t, uint8_t** gray, uint16_t** depth)
     return GF_OK;
 }
 
-// The frame body: everything after the frame is in HBM (d_pyr[cur][0], d_depth) and FrameParams are in h_fp.
-// Pure stream work with fixed addresses, so it can be captured into a CUDA graph.
-static int enqueue_body(gf_tracker* t, int cur, bool has_pred)
+}  // extern "C"
+
+// ---- the four capturable pieces of a frame (fixed addresses for a given frame number mod 6) ----
+#define GF_MARK(k, s) do { if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[k], s)); } while (0)
+
+static int body_pyr(gf_tracker* t, long long f)
 {
-    const int prev = cur ^ 1;
+    const int es = (int)(f % 2);
+    GF_CUDA(cudaMemcpyAsync(t->d_fp[es], t->h_fp[es], sizeof(FrameParams), cudaMemcpyHostToDevice, t->s_pre));
+    return enqueue_pyramid(t->s_pre, t, (int)(f % 3));
+}
+
+static int body_eig(gf_tracker* t, long long f)
+{
+    Pyramid Pc = make_pyr(t, (int)(f % 3));
+    return enqueue_min_eig(t->s_pre, Pc.lv[0], t->d_eig[f % 2], t->epitch, t->d_cov, t->d_box);
+}
+
+static int body_dep1(gf_tracker* t, long long f, bool has_pred)
+{
     cudaStream_t s = t->s_main;
-    GF_CUDA(cudaMemcpyAsync(t->d_fp, t->h_fp, sizeof(FrameParams), cudaMemcpyHostToDevice, s));
-    Pyramid Pc = make_pyr(t, cur), Pp = make_pyr(t, prev);
-#define GF_MARK(k) do { if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[k], s)); } while (0)
-    GF_MARK(0);   // end of upload
-    // fork: min-eig of the new frame does not depend on tracking
-    GF_CUDA(cudaEventRecord(t->ev_fork, s));
-    GF_CUDA(cudaStreamWaitEvent(t->s_aux, t->ev_fork, 0));
-    if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[7], t->s_aux));
-    int rc = enqueue_min_eig(t->s_aux, Pc.lv[0], t->d_eig, t->epitch, t->d_spec_start, t->d_spec_end, t->nbands, &t->d_sc->eig_fixups);
-    if (rc) return rc;
-    GF_CUDA(cudaEventRecord(t->ev_eig, t->s_aux));
-    if (t->profiling) GF_CUDA(cudaEventRecord(t->ev_st[8], t->s_aux));
-    rc = enqueue_pyramid(s, t, cur);
-    if (rc) return rc;
-    GF_MARK(1);
+    Pyramid Pc = make_pyr(t, (int)(f % 3)), Pp = make_pyr(t, (int)((f + 2) % 3));
     const int lk_grid = t->cfg.max_cnt;
     if (has_pred) { k_lk_pred<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa); GF_LAUNCHED(); }
-    k_track<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp, t->cfg.flow_back); GF_LAUNCHED();
-    GF_MARK(2);
+    k_track<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp[f % 2], t->cfg.flow_back); GF_LAUNCHED();
+    GF_MARK(2, s);
     k_compact_setmask<<<1, FE_CAP, 0, s>>>(t->d_sc, t->fa, t->cfg.min_dist); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
-    GF_MARK(3);
-    GF_CUDA(cudaMemcpyAsync(t->h_status, t->fa.status, t->cfg.max_cnt, cudaMemcpyDeviceToHost, s));
-    GF_CUDA(cudaStreamWaitEvent(s, t->ev_eig, 0));
-    rc = enqueue_gftt_select(s, t->d_sc, t->fa.kept_pts, t->cfg.max_cnt, t->d_eig, t->epitch, t->d_mask, t->mpitch, t->w, t->h,
-                             t->cfg.min_dist, t->grid, t->grid_cells);
-    if (rc) return rc;
-    GF_MARK(4);
-    // reference quirk: depth_cam with an empty depth image produces an empty featureFrame (feature_tracker.cpp:342)
-    const int depth_mode = t->cfg.depth_cam ? 1 : 0;
-    k_select_finalize<<<1, 1024, t->grid_cells, s>>>(t->d_sc, t->fa, t->grid, t->w, t->cfg.max_cnt, t->cfg.min_dist, t->cam, &t->d_fp->dt,
-                                                     t->d_depth, t->depth_pitch_el, depth_mode, &t->d_fp->depth_valid, t->h, t->d_hdr, t->d_obs); GF_LAUNCHED();
-    GF_CUDA(cudaGetLastError());
-    GF_MARK(5);
-    GF_CUDA(cudaMemcpyAsync(t->h_hdr, t->d_hdr, sizeof(OutHeader), cudaMemcpyDeviceToHost, s));
-    GF_CUDA(cudaMemcpyAsync(t->h_obs, t->d_obs, (size_t)t->cfg.max_cnt * sizeof(gf_obs), cudaMemcpyDeviceToHost, s));
+    GF_MARK(3, s);
     return GF_OK;
 }
 
-static int enqueue_frame(gf_tracker* t, double time, bool depth_valid)
+static int body_dep2(gf_tracker* t, long long f)
 {
-    const int cur = t->cur;
     cudaStream_t s = t->s_main;
-    t->h_fp->dt = time - t->prev_time;
-    t->h_fp->has_pred = t->has_pred ? 1 : 0;
-    t->h_fp->depth_valid = depth_valid ? 1 : 0;
-    int rc = GF_OK;
-    if (t->use_graph && !t->profiling) {
-        const int key = cur * 2 + (t->has_pred ? 1 : 0);
-        if (!t->graph[key]) {
-            const uint64_t l0 = g_launches.load();
-            cudaGraph_t g = nullptr;
-            GF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            rc = enqueue_body(t, cur, t->has_pred);
-            cudaError_t e = cudaStreamEndCapture(s, &g);
-            if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-            if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "graph capture failed: %s", cudaGetErrorString(e)); return GF_ERR_CUDA; }
-            GF_CUDA(cudaGraphInstantiate(&t->graph[key], g, 0));
-            cudaGraphDestroy(g);
-            t->graph_kernels[key] = (int)(g_launches.load() - l0);
-            g_launches.fetch_sub(t->graph_kernels[key]);      // capture did not launch anything
-        }
-        GF_CUDA(cudaGraphLaunch(t->graph[key], s));
-        g_launches.fetch_add(t->graph_kernels[key]);
-    } else {
-        rc = enqueue_body(t, cur, t->has_pred);
-        if (rc) return rc;
+    const int es = (int)(f % 2);
+    int rc = enqueue_gftt_select(s, t->d_sc, t->fa.kept_pts, t->cfg.max_cnt, t->d_eig[es], t->epitch, nullptr, 0, t->w, t->h,
+                                 t->cfg.min_dist, t->grid, t->grid_cells);
+    if (rc) return rc;
+    GF_MARK(4, s);
+    // reference quirk: depth_cam with an empty depth image produces an empty featureFrame (feature_tracker.cpp:342)
+    const int depth_mode = t->cfg.depth_cam ? 1 : 0;
+    OutBlock* ob = t->d_out[es];
+    k_select_finalize<<<1, 1024, t->grid_cells, s>>>(t->d_sc, t->fa, t->grid, t->w, t->cfg.max_cnt, t->cfg.min_dist, t->cam, &t->d_fp[es]->dt,
+                                                     t->d_depth[es], t->depth_pitch_el, depth_mode, &t->d_fp[es]->depth_valid, t->h,
+                                                     &ob->hdr, ob->obs, ob->status); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_MARK(5, s);
+    return GF_OK;
+}
+
+// Runs one piece: replays its CUDA graph (captured on first use) or, in profiling / GF_NO_GRAPH mode, launches it directly.
+template <class Body>
+static int run_piece(gf_tracker* t, cudaStream_t s, cudaGraphExec_t* exec, int* nk, Body body)
+{
+    if (!t->use_graph || t->profiling) return body();
+    if (!*exec) {
+        const uint64_t l0 = g_launches.load();
+        cudaGraph_t g = nullptr;
+        GF_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = body();
+        cudaError_t e = cudaStreamEndCapture(s, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "graph capture failed: %s", cudaGetErrorString(e)); return GF_ERR_CUDA; }
+        GF_CUDA(cudaGraphInstantiate(exec, g, 0));
+        cudaGraphDestroy(g);
+        *nk = (int)(g_launches.load() - l0);
+        g_launches.fetch_sub(*nk);      // capture did not launch anything
     }
-    GF_CUDA(cudaEventRecord(t->ev_t1, s));
+    GF_CUDA(cudaGraphLaunch(*exec, s));
+    g_launches.fetch_add(*nk);
+    return GF_OK;
+}
+
+// Everything after the H2D (or D2D) copies of frame f have been enqueued on s_pre.
+static int enqueue_frame(gf_tracker* t, long long f, double time, bool depth_valid)
+{
+    const int es = (int)(f % 2), key = (int)(f % 6), hp = t->has_pred ? 1 : 0;
+    t->h_fp[es]->dt = time - t->prev_time;
+    t->h_fp[es]->has_pred = hp;
+    t->h_fp[es]->depth_valid = depth_valid ? 1 : 0;
+    GF_MARK(0, t->s_pre);   // end of upload
+    int rc = run_piece(t, t->s_pre, &t->g_pyr[key], &t->gk_pyr[key], [&] { return body_pyr(t, f); });
+    if (rc) return rc;
+    GF_CUDA(cudaEventRecord(t->ev_pyr[es], t->s_pre));
+    GF_MARK(1, t->s_pre);
+    GF_MARK(7, t->s_pre);
+    rc = run_piece(t, t->s_pre, &t->g_eig[key], &t->gk_eig[key], [&] { return body_eig(t, f); });
+    if (rc) return rc;
+    GF_CUDA(cudaEventRecord(t->ev_eig[es], t->s_pre));
+    GF_MARK(8, t->s_pre);
+    GF_CUDA(cudaStreamWaitEvent(t->s_main, t->ev_pyr[es], 0));
+    rc = run_piece(t, t->s_main, &t->g_dep1[key][hp], &t->gk_dep1[key][hp], [&] { return body_dep1(t, f, hp != 0); });
+    if (rc) return rc;
+    GF_CUDA(cudaStreamWaitEvent(t->s_main, t->ev_eig[es], 0));
+    rc = run_piece(t, t->s_main, &t->g_dep2[key], &t->gk_dep2[key], [&] { return body_dep2(t, f); });
+    if (rc) return rc;
+    GF_CUDA(cudaEventRecord(t->ev_dep[es], t->s_main));
+    GF_CUDA(cudaStreamWaitEvent(t->s_out, t->ev_dep[es], 0));
+    GF_CUDA(cudaMemcpyAsync(t->h_out[es], t->d_out[es], offsetof(OutBlock, obs) + (size_t)t->cfg.max_cnt * sizeof(gf_obs),
+                            cudaMemcpyDeviceToHost, t->s_out));
+    GF_CUDA(cudaEventRecord(t->ev_out[es], t->s_out));
     t->prev_time = time;
     t->has_pred = false;
-    t->cur = cur ^ 1;
-    t->pending = true;
-    t->depth_last = depth_valid;
+    t->depth_valid[es] = depth_valid;
+    t->n_submitted = f + 1;
+    return GF_OK;
+}
+
+extern "C" {
+
+static int check_submit(gf_tracker* t)
+{
+    if (in_flight(t) >= GF_PIPE) return set_err(GF_ERR_INVALID_ARG, "two frames in flight: call gf_tracker_wait first");
+    if (t->profiling && in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "profiling mode runs one frame at a time");
     return GF_OK;
 }
 
 int gf_tracker_submit(gf_tracker* t, double time, const uint8_t* gray, size_t gray_pitch, const uint16_t* depth, size_t depth_pitch)
 {
     if (!t || !gray) return set_err(GF_ERR_INVALID_ARG, "null argument");
-    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected: call gf_tracker_wait first");
+    int rc = check_submit(t);
+    if (rc) return rc;
     GF_CUDA(cudaSetDevice(t->device));
     const int w = t->w, h = t->h;
     if (gray_pitch < (size_t)w) return set_err(GF_ERR_INVALID_ARG, "gray_pitch smaller than width");
     if (depth && depth_pitch < (size_t)w * 2) return set_err(GF_ERR_INVALID_ARG, "depth_pitch smaller than width*2");
     // The caller's buffers are read by the copy engine directly: truly asynchronous when they are pinned
-    // (gf_tracker_host_buffers or any cudaHostAlloc/cudaHostRegister memory); for pageable memory CUDA stages
-    // the data before cudaMemcpy2DAsync returns, so the "only read during the call" contract holds either way.
-    cudaStream_t s = t->s_main;
-    GF_CUDA(cudaEventRecord(t->ev_t0, s));
-    GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[t->cur][0], t->lp[0], gray, gray_pitch, w, h, cudaMemcpyHostToDevice, s));
+    // (gf_tracker_host_buffers or any cudaHostAlloc/cudaHostRegister memory: keep them unchanged until the frame has
+    // been collected); for pageable memory CUDA stages the data before cudaMemcpy2DAsync returns.
+    const long long f = t->n_submitted;
+    cudaStream_t s = t->s_pre;
+    GF_CUDA(cudaEventRecord(t->ev_t0[f % 2], s));
+    GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[f % 3][0], t->lp[0], gray, gray_pitch, w, h, cudaMemcpyHostToDevice, s));
     if (depth)
-        GF_CUDA(cudaMemcpy2DAsync(t->d_depth, (size_t)t->depth_pitch_el * 2, depth, depth_pitch, (size_t)w * 2, h, cudaMemcpyHostToDevice, s));
-    return enqueue_frame(t, time, depth != nullptr);
+        GF_CUDA(cudaMemcpy2DAsync(t->d_depth[f % 2], (size_t)t->depth_pitch_el * 2, depth, depth_pitch, (size_t)w * 2, h, cudaMemcpyHostToDevice, s));
+    return enqueue_frame(t, f, time, depth != nullptr);
+}
+
+int gf_tracker_submit_device(gf_tracker* t, double time, const void* d_gray, const void* d_depth)
+{
+    if (!t || !d_gray) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    int rc = check_submit(t);
+    if (rc) return rc;
+    GF_CUDA(cudaSetDevice(t->device));
+    const int w = t->w, h = t->h;
+    const long long f = t->n_submitted;
+    cudaStream_t s = t->s_pre;
+    GF_CUDA(cudaEventRecord(t->ev_t0[f % 2], s));
+    GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[f % 3][0], t->lp[0], d_gray, w, w, h, cudaMemcpyDeviceToDevice, s));
+    if (d_depth)
+        GF_CUDA(cudaMemcpy2DAsync(t->d_depth[f % 2], (size_t)t->depth_pitch_el * 2, d_depth, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToDevice, s));
+    return enqueue_frame(t, f, time, d_depth != nullptr);
 }
 
 int gf_tracker_wait(gf_tracker* t, gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info)
 {
     if (!t) return set_err(GF_ERR_INVALID_ARG, "null tracker");
-    if (!t->pending) return set_err(GF_ERR_INVALID_ARG, "no frame in flight");
+    if (in_flight(t) == 0) return set_err(GF_ERR_INVALID_ARG, "no frame in flight");
     GF_CUDA(cudaSetDevice(t->device));
-    GF_CUDA(cudaStreamSynchronize(t->s_main));
-    t->pending = false;
-    GF_CUDA(cudaEventElapsedTime(&t->last_ms, t->ev_t0, t->ev_t1));
+    const int es = (int)(t->n_waited % 2);
+    GF_CUDA(cudaEventSynchronize(t->ev_out[es]));
+    t->n_waited++;
+    GF_CUDA(cudaEventElapsedTime(&t->last_ms, t->ev_t0[es], t->ev_out[es]));
     if (t->profiling) {
-        cudaEvent_t b[8] = {t->ev_t0, t->ev_st[0], t->ev_st[1], t->ev_st[2], t->ev_st[3], t->ev_st[4], t->ev_st[5], t->ev_t1};
+        cudaEvent_t b[8] = {t->ev_t0[es], t->ev_st[0], t->ev_st[1], t->ev_st[2], t->ev_st[3], t->ev_st[4], t->ev_st[5], t->ev_out[es]};
         for (int i = 0; i < 7; i++) GF_CUDA(cudaEventElapsedTime(&t->stage_ms[i], b[i], b[i + 1]));
         GF_CUDA(cudaEventElapsedTime(&t->stage_ms[7], t->ev_st[7], t->ev_st[8]));
     }
-    const OutHeader& hd = *t->h_hdr;
+    const OutBlock& ob = *t->h_out[es];
+    const OutHeader& hd = ob.hdr;
     int n = hd.n_out;
-    if (t->cfg.depth_cam && !t->depth_last) n = 0;   // see enqueue_frame
+    if (t->cfg.depth_cam && !t->depth_valid[es]) n = 0;   // see body_dep2
     if (n_out) *n_out = n;
-    if (out && n > 0) memcpy(out, t->h_obs, (size_t)n * sizeof(gf_obs));
-    if (status_out && hd.n_prev > 0) memcpy(status_out, t->h_status, hd.n_prev);
+    if (out && n > 0) memcpy(out, ob.obs, (size_t)n * sizeof(gf_obs));
+    if (status_out && hd.n_prev > 0) memcpy(status_out, ob.status, hd.n_prev);
     if (info) {
         info->n_prev = hd.n_prev; info->n_tracked = hd.n_tracked; info->n_kept = hd.n_kept; info->n_new = hd.n_new;
         info->n_candidates = hd.n_cand; info->nms_rounds = hd.nms_rounds; info->eig_fixups = hd.eig_fixups; info->lk_iterations = hd.lk_iters;
@@ -500,6 +598,7 @@ int gf_tracker_wait(gf_tracker* t, gf_obs* out, int* n_out, uint8_t* status_out,
 int gf_tracker_track(gf_tracker* t, double time, const uint8_t* gray, size_t gray_pitch, const uint16_t* depth, size_t depth_pitch,
                      gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info)
 {
+    if (t && in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected: call gf_tracker_wait first");
     int rc = gf_tracker_submit(t, time, gray, gray_pitch, depth, depth_pitch);
     if (rc) return rc;
     return gf_tracker_wait(t, out, n_out, status_out, info);
@@ -508,16 +607,8 @@ int gf_tracker_track(gf_tracker* t, double time, const uint8_t* gray, size_t gra
 int gf_tracker_track_device(gf_tracker* t, double time, const void* d_gray, const void* d_depth, gf_obs* out, int* n_out,
                             uint8_t* status_out, gf_track_info* info)
 {
-    if (!t || !d_gray) return set_err(GF_ERR_INVALID_ARG, "null argument");
-    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected");
-    GF_CUDA(cudaSetDevice(t->device));
-    cudaStream_t s = t->s_main;
-    const int w = t->w, h = t->h;
-    GF_CUDA(cudaEventRecord(t->ev_t0, s));
-    GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[t->cur][0], t->lp[0], d_gray, w, w, h, cudaMemcpyDeviceToDevice, s));
-    if (d_depth)
-        GF_CUDA(cudaMemcpy2DAsync(t->d_depth, (size_t)t->depth_pitch_el * 2, d_depth, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToDevice, s));
-    int rc = enqueue_frame(t, time, d_depth != nullptr);
+    if (t && in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected");
+    int rc = gf_tracker_submit_device(t, time, d_gray, d_depth);
     if (rc) return rc;
     return gf_tracker_wait(t, out, n_out, status_out, info);
 }
@@ -526,7 +617,7 @@ int gf_tracker_set_prediction(gf_tracker* t, const int32_t* ids, const double* x
 {
     if (!t || (n > 0 && (!ids || !xyz))) return set_err(GF_ERR_INVALID_ARG, "null argument");
     if (n < 0 || n > FE_CAP) return set_err(GF_ERR_CAPACITY, "too many predictions");
-    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
+    if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
     GF_CUDA(cudaSetDevice(t->device));
     cudaStream_t s = t->s_main;
     if (n > 0) {
@@ -546,7 +637,7 @@ int gf_tracker_remove_ids(gf_tracker* t, const int32_t* ids, int n)
 {
     if (!t || (n > 0 && !ids)) return set_err(GF_ERR_INVALID_ARG, "null argument");
     if (n < 0 || n > FE_CAP) return set_err(GF_ERR_CAPACITY, "too many ids");
-    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
+    if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
     if (n == 0) return GF_OK;
     GF_CUDA(cudaSetDevice(t->device));
     cudaStream_t s = t->s_main;
@@ -561,7 +652,7 @@ int gf_tracker_remove_ids(gf_tracker* t, const int32_t* ids, int n)
 int gf_tracker_set_profiling(gf_tracker* t, int enable)
 {
     if (!t) return set_err(GF_ERR_INVALID_ARG, "null tracker");
-    if (t->pending) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
+    if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
     t->profiling = enable != 0;
     return GF_OK;
 }
@@ -570,6 +661,35 @@ int gf_tracker_last_stage_ms(gf_tracker* t, float* ms)
 {
     if (!t || !ms) return set_err(GF_ERR_INVALID_ARG, "null argument");
     memcpy(ms, t->stage_ms, sizeof(t->stage_ms));
+    return GF_OK;
+}
+
+int gf_tracker_debug_read(gf_tracker* t, long long* out, int n)
+{
+    if (!t || !out || n < 0 || n > FE_DBG_N) return set_err(GF_ERR_INVALID_ARG, "bad argument");
+    GF_CUDA(cudaSetDevice(t->device));
+    GF_CUDA(cudaStreamSynchronize(t->s_main));
+    GF_CUDA(cudaMemcpy(out, t->fa.dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
+    return GF_OK;
+}
+
+int gf_tracker_timer_start(gf_tracker* t)
+{
+    if (!t) return set_err(GF_ERR_INVALID_ARG, "null tracker");
+    if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
+    GF_CUDA(cudaSetDevice(t->device));
+    GF_CUDA(cudaEventRecord(t->ev_span0, t->s_pre));     // the first operation of the next frame follows on this stream
+    return GF_OK;
+}
+
+int gf_tracker_timer_stop(gf_tracker* t, float* ms)
+{
+    if (!t || !ms) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
+    GF_CUDA(cudaSetDevice(t->device));
+    GF_CUDA(cudaEventRecord(t->ev_span1, t->s_out));     // after the last result copy
+    GF_CUDA(cudaEventSynchronize(t->ev_span1));
+    GF_CUDA(cudaEventElapsedTime(ms, t->ev_span0, t->ev_span1));
     return GF_OK;
 }
 
@@ -625,13 +745,13 @@ int gf_stage_min_eig(int device, const uint8_t* img, int w, int h, float* eig, i
     int rc = select_device(device); if (rc) return rc;
     DevBuf di, de, s0, s1, fx; int ip;
     rc = upload_image(img, w, h, di, ip); if (rc) return rc;
-    int ep = align_up(w, 4), nb = (h + EIG_BAND - 1) / EIG_BAND;
-    if ((rc = de.alloc((size_t)ep * h * 4)) || (rc = s0.alloc((size_t)nb * 3 * w * 8)) || (rc = s1.alloc((size_t)nb * 3 * w * 8)) || (rc = fx.alloc(4))) return rc;
-    GF_CUDA(cudaMemset(fx.p, 0, 4));
+    int ep = align_up(w, 4);
+    if ((rc = de.alloc((size_t)ep * h * 4)) || (rc = s0.alloc(cov_rows_elems(w, h) * 8)) || (rc = s1.alloc(box_elems(w, h) * 4))) return rc;
+    GF_CUDA(cudaMemset(s0.p, 0, cov_rows_elems(w, h) * 8));
     Level L{di.as<uint8_t>(), w, h, ip};
-    rc = enqueue_min_eig(0, L, de.as<float>(), ep, s0.as<double>(), s1.as<double>(), nb, fx.as<int>()); if (rc) return rc;
+    rc = enqueue_min_eig(0, L, de.as<float>(), ep, s0.as<double>(), s1.as<float>()); if (rc) return rc;
     GF_CUDA(cudaMemcpy2D(eig, (size_t)w * 4, de.p, (size_t)ep * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost));
-    if (n_fixups) GF_CUDA(cudaMemcpy(n_fixups, fx.p, 4, cudaMemcpyDeviceToHost));
+    if (n_fixups) *n_fixups = 0;     // the running sums are no longer speculated
     return GF_OK;
 }
 
@@ -677,9 +797,9 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
     int rc = select_device(device); if (rc) return rc;
     DevBuf di, de, dm, s0, s1, dsc, dk, dhdr, dobs, dummy[8]; int ip;
     rc = upload_image(img, w, h, di, ip); if (rc) return rc;
-    int ep = align_up(w, 4), mp = align_up(w, 16), nb = (h + EIG_BAND - 1) / EIG_BAND;
-    if ((rc = de.alloc((size_t)ep * h * 4)) || (rc = dm.alloc((size_t)mp * h)) || (rc = s0.alloc((size_t)nb * 3 * w * 8)) ||
-        (rc = s1.alloc((size_t)nb * 3 * w * 8)) || (rc = dsc.alloc(sizeof(TrackScalars))) || (rc = dk.alloc((size_t)FE_CAP * 8)) ||
+    int ep = align_up(w, 4), mp = align_up(w, 16);
+    if ((rc = de.alloc((size_t)ep * h * 4)) || (rc = dm.alloc((size_t)mp * h)) || (rc = s0.alloc(cov_rows_elems(w, h) * 8)) ||
+        (rc = s1.alloc(box_elems(w, h) * 4)) || (rc = dsc.alloc(sizeof(TrackScalars))) || (rc = dk.alloc((size_t)FE_CAP * 8)) ||
         (rc = dhdr.alloc(sizeof(OutHeader))) || (rc = dobs.alloc(FE_CAP * sizeof(gf_obs))))
         return rc;
     for (int i = 0; i < 8; i++) if ((rc = dummy[i].alloc(FE_CAP * 8))) return rc;
@@ -691,16 +811,17 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
     rc = alloc_nms_grid(grid, w, h, min_dist, &cells); if (rc) return rc;
     Level L{di.as<uint8_t>(), w, h, ip};
     TrackScalars* sc = dsc.as<TrackScalars>();
-    rc = enqueue_min_eig(0, L, de.as<float>(), ep, s0.as<double>(), s1.as<double>(), nb, &sc->eig_fixups);
+    GF_CUDA(cudaMemset(s0.p, 0, cov_rows_elems(w, h) * 8));
+    rc = enqueue_min_eig(0, L, de.as<float>(), ep, s0.as<double>(), s1.as<float>());
     if (!rc) rc = enqueue_gftt_select(0, sc, dk.as<float2>(), n_kept, de.as<float>(), ep, dm.as<uint8_t>(), mp, w, h, min_dist, grid, cells);
     if (!rc) {
         FeatArrays fa;
         fa.prev_pts = dummy[0].as<float2>(); fa.ids = dummy[1].as<int>(); fa.track_cnt = dummy[2].as<int>(); fa.prev_un = dummy[3].as<float2>();
-        fa.cur_pts = nullptr; fa.status = nullptr; fa.pred_pts = nullptr;
+        fa.cur_pts = nullptr; fa.status = nullptr; fa.pred_pts = nullptr; fa.dbg = nullptr;
         fa.kept_pts = dk.as<float2>(); fa.kept_ids = dummy[4].as<int>(); fa.kept_cnt = dummy[5].as<int>(); fa.kept_un = dummy[6].as<float2>();
         CamParams cam; memset(&cam, 0, sizeof(cam)); cam.fx = cam.fy = 1.0; cam.no_distortion = 1;
         // max_cnt such that exactly max_corners new corners are requested
-        k_select_finalize<<<1, 1024, cells>>>(sc, fa, grid, w, n_kept + max_corners, min_dist, cam, nullptr, nullptr, 0, 0, nullptr, h, dhdr.as<OutHeader>(), dobs.as<gf_obs>()); GF_LAUNCHED();
+        k_select_finalize<<<1, 1024, cells>>>(sc, fa, grid, w, n_kept + max_corners, min_dist, cam, nullptr, nullptr, 0, 0, nullptr, h, dhdr.as<OutHeader>(), dobs.as<gf_obs>(), nullptr); GF_LAUNCHED();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "k_select_finalize launch: %s", cudaGetErrorString(e)); rc = GF_ERR_CUDA; }
     }
@@ -740,7 +861,7 @@ int gf_stage_setmask_order(int device, const int32_t* track_cnt, int n, int32_t*
     for (int i = 0; i < n; i++) e[i] = ((sort_elem)(unsigned)track_cnt[i] << 32) | (unsigned)i;
     DevBuf d; rc = d.alloc((size_t)n * 8); if (rc) return rc;
     GF_CUDA(cudaMemcpy(d.p, e.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
-    k_sort_stage<<<1, 256>>>(d.as<sort_elem>(), n); GF_LAUNCHED();
+    k_sort_stage<<<1, FE_CAP>>>(d.as<sort_elem>(), n); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpy(e.data(), d.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     for (int i = 0; i < n; i++) perm[i] = (int32_t)(e[i] & 0xffffffffu);

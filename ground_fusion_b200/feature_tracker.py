@@ -130,13 +130,25 @@ class FeatureTracker:
         return self._collect(n, info)
 
     def submit(self, cur_time, img, depth=None):
+        """Asynchronous trackImage: up to two frames may be in flight; collect them in order with wait()."""
         dp, dpitch = (depth.ctypes.data, depth.strides[0]) if depth is not None else (None, 0)
         check(self.L.gf_tracker_submit(self._h, float(cur_time), img.ctypes.data, img.strides[0], dp, dpitch))
+
+    def submitDevice(self, cur_time, d_gray_ptr, d_depth_ptr=None):
+        check(self.L.gf_tracker_submit_device(self._h, float(cur_time), d_gray_ptr, d_depth_ptr))
 
     def wait(self):
         n, info = ctypes.c_int(0), TrackInfo()
         check(self.L.gf_tracker_wait(self._h, self._obs.ctypes.data, ctypes.byref(n), self._status.ctypes.data, ctypes.byref(info)))
         return self._collect(n, info)
+
+    def timer_start(self):
+        check(self.L.gf_tracker_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float(0)
+        check(self.L.gf_tracker_timer_stop(self._h, ctypes.byref(ms)))
+        return float(ms.value)
 
     def setPrediction(self, predictPts):
         ids = np.array(sorted(predictPts.keys()), np.int32)

@@ -67,7 +67,7 @@ typedef struct gf_track_info {
     int32_t n_new;      /* corners added by goodFeaturesToTrack                              */
     int32_t n_candidates; /* GFTT local-maximum candidates before the min-distance pass      */
     int32_t nms_rounds; /* parallel min-distance rounds used                                 */
-    int32_t eig_fixups; /* column bands re-run by the box-filter verifier                    */
+    int32_t eig_fixups; /* always 0 (kept for ABI stability: the box-filter sums are no longer speculated) */
     int32_t lk_iterations; /* total LK Newton iterations of this frame (all points, levels, both passes) */
 } gf_track_info;
 
@@ -92,8 +92,14 @@ int gf_tracker_track(gf_tracker* t, double time, const uint8_t* gray, size_t gra
                      const uint16_t* depth, size_t depth_pitch, gf_obs* out, int* n_out,
                      uint8_t* status_out, gf_track_info* info);
 
-/* Asynchronous split of gf_tracker_track for callers that overlap several streams on one GPU:
- * _submit enqueues copies + kernels and returns, _wait blocks for the result of the last _submit. */
+/* Asynchronous split of gf_tracker_track.  _submit enqueues the copies and kernels of one frame and returns;
+ * _wait blocks for the result of the OLDEST frame not yet collected.  Up to two frames may be in flight
+ * (submit t, submit t+1, wait t, submit t+2, wait t+1, ...): the upload, pyramid and min-eig map of frame t+1 then
+ * overlap the tracking of frame t, which is how a recorded sequence (rosbag replay) or a camera with one frame of
+ * buffering is processed at the rate of the dependent chain alone.  Results are identical to the blocking call.
+ * Pinned caller buffers passed to _submit must stay unchanged until that frame has been collected.
+ * gf_tracker_set_prediction / gf_tracker_remove_ids act on the state after the last collected frame and are
+ * therefore only accepted with no frame in flight, exactly as the reference calls them between trackImage calls. */
 int gf_tracker_submit(gf_tracker* t, double time, const uint8_t* gray, size_t gray_pitch,
                       const uint16_t* depth, size_t depth_pitch);
 int gf_tracker_wait(gf_tracker* t, gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info);
@@ -102,20 +108,30 @@ int gf_tracker_wait(gf_tracker* t, gf_obs* out, int* n_out, uint8_t* status_out,
  * (device pointers, tightly packed W x H), nothing is copied from the host. */
 int gf_tracker_track_device(gf_tracker* t, double time, const void* d_gray, const void* d_depth,
                             gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info);
+/* Asynchronous form of gf_tracker_track_device (collect with gf_tracker_wait; same two-frame rule as _submit). */
+int gf_tracker_submit_device(gf_tracker* t, double time, const void* d_gray, const void* d_depth);
 
 /* FeatureTracker::setPrediction (feature_tracker.cpp:1006-1027): xyz are camera-frame 3-D points. */
 int gf_tracker_set_prediction(gf_tracker* t, const int32_t* ids, const double* xyz, int n);
 /* FeatureTracker::removeOutliers (feature_tracker.cpp:1029-1045). */
 int gf_tracker_remove_ids(gf_tracker* t, const int32_t* ids, int n);
 
-/* Device time (ms, CUDA events on the tracker's stream) of the last completed frame. */
+/* Device time (ms, CUDA events) from the first copy to the result copy of the last collected frame (its latency;
+ * with two frames in flight consecutive latencies overlap). */
 int gf_tracker_last_device_ms(gf_tracker* t, float* ms);
+/* Device-side stopwatch over a run of frames: _start records a CUDA event ahead of the next frame's first copy,
+ * _stop one behind the last frame's result copy and returns the elapsed ms.  Both need no frame in flight. */
+int gf_tracker_timer_start(gf_tracker* t);
+int gf_tracker_timer_stop(gf_tracker* t, float* ms);
 /* Optional per-stage CUDA-event timing (adds event records, no synchronisation).  Stage order:
  * 0 upload, 1 pyramid, 2 lk (k_track), 3 setmask, 4 gftt select (mask..nms), 5 finalize, 6 download,
- * 7 min-eig (aux stream, overlaps 1-3). */
+ * 7 min-eig (runs on the upload/pyramid stream, overlaps 2-3).  Profiling mode runs one frame at a time. */
 #define GF_FE_STAGES 8
 int gf_tracker_set_profiling(gf_tracker* t, int enable);
 int gf_tracker_last_stage_ms(gf_tracker* t, float* ms /* GF_FE_STAGES */);
+/* Development aid: clock64 phase counters of the single-CTA kernels ([0..63]) and per-feature LK cycles/iterations
+ * ([64 + 8*i], [64 + 8*i + 1]).  n <= 64 + 8*1024. */
+int gf_tracker_debug_read(gf_tracker* t, long long* out, int n);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage-level entry points (same kernels as the tracker; used by the parity tests, which read like

@@ -82,8 +82,8 @@ def test_lk_empty_and_single(gf):
 def test_setmask_order_matches_std_sort(gf):
     from oracle.fe_oracle import setmask_order
     rng = np.random.default_rng(3)
-    for n in (1, 5, 16, 17, 64, 150, 300, 1000):
-        for span in (2, 6, 50):
+    for n in (1, 2, 5, 16, 17, 18, 33, 64, 100, 150, 257, 300, 400, 511, 512, 513, 1000):
+        for span in (1, 2, 6, 50, 1000):
             tc = np.sort(rng.integers(1, span + 1, n))[::-1].astype(np.int32)   # the tracker's input is non-increasing
             assert np.array_equal(gf.setmask_order(tc), setmask_order(tc))
             tc2 = rng.integers(1, span + 1, n).astype(np.int32)
@@ -138,6 +138,45 @@ def test_track_sequence_c3_300_features(gf):
 
 def test_track_sequence_c4_720p_500_features(gf):
     _run_sequence(gf, seed=2, n_frames=12, w=1280, h=720, max_cnt=500, min_dist=25)
+
+
+def test_two_frames_in_flight_equals_blocking_calls(gf):
+    """submit t+1 before collecting t (upload/pyramid/min-eig of t+1 overlap the tracking of t): same bits as trackImage,
+    which is itself compared with the oracle above; frames with and without a depth image alternate to cover the
+    rotated depth / parameter buffers."""
+    from ground_fusion_b200.synth import SyntheticStream
+    from ground_fusion_b200._lib import GfError
+    from oracle.fe_oracle import IDC_CAM, PinholeCamera
+    cam = PinholeCamera(**IDC_CAM)
+    stream = SyntheticStream(seed=5)
+    frames = [stream.frame(k) for k in range(25)]
+    frames = [(t, g, (d if k % 7 != 3 else None)) for k, (t, g, d) in enumerate(frames)]
+    a = gf.FeatureTracker(640, 480, cam.params8(), 150, 30, 1, 1)
+    want = []
+    for t, g, d in frames:
+        obs = a.trackImageRaw(t, g, d).copy()
+        want.append((obs, a.last_status.copy(), dict(a.last_info)))
+    a.close()
+    b = gf.FeatureTracker(640, 480, cam.params8(), 150, 30, 1, 1)
+    got = []
+    pending = 0
+    for t, g, d in frames:
+        b.submit(t, np.ascontiguousarray(g), None if d is None else np.ascontiguousarray(d))
+        pending += 1
+        if pending == 2:
+            obs = b.wait().copy(); got.append((obs, b.last_status.copy(), dict(b.last_info))); pending -= 1
+    with pytest.raises(GfError):
+        b.removeOutliers({1})                      # state-changing calls need an empty pipeline
+    while pending:
+        obs = b.wait().copy(); got.append((obs, b.last_status.copy(), dict(b.last_info))); pending -= 1
+    with pytest.raises(GfError):
+        b.wait()
+    assert len(got) == len(want)
+    for k, ((o1, s1, i1), (o2, s2, i2)) in enumerate(zip(want, got)):
+        assert i1 == i2, "frame %d: %s vs %s" % (k, i1, i2)
+        assert np.array_equal(s1, s2), "frame %d" % k
+        assert o1.tobytes() == o2.tobytes(), "frame %d" % k
+    b.close()
 
 
 def test_track_no_depth_image_quirk(gf):
