@@ -1,4 +1,4 @@
-timeout 400 python -m pytest tests/test_fe_gpu.py -x -q 2>&1 | tail -5
-timeout 120 python tools/prof_fe_phases.py 4 2>&1 | tail -7
-timeout 250 python bench.py --steps 300 --warmup 20 2>&1 | tail -1 > gpurun_out/bench11.json; python -c "
-import json; d=json.load(open('gpurun_out/bench11.json')); print(d['value'], d['e2e']['value'], d['device_ms_per_step'], d['device_ms_per_step_e2e'], d['stage_ms'])"
+GF_NO_GRAPH=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_track -s 4 -c 1 -o gpurun_out/k_track_r1 -f python tools/prof_fe.py 8 > /dev/null 2>&1
+GF_NO_GRAPH=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_fe_r1f.csv python tools/prof_fe.py 12 > /dev/null 2>&1
+python tools/ncu_summary.py gpurun_out/launches_fe_r1f.csv
+ls -la gpurun_out/k_track_r1.ncu-rep
