@@ -16,6 +16,7 @@
 // All four are enqueued for every iteration up front; kernels return immediately once the state says "done",
 // so the host synchronises exactly once per solve.
 #include <new>
+#include <type_traits>
 #include <vector>
 
 #include "ba_factors.cuh"
@@ -37,7 +38,7 @@ struct BaState {
     double acc_cost[2];          // cost accumulated by k_ba_eval into buffer 0/1
     double cauchy_num, cauchy_den;   // |gs|^2 and v^T H' v accumulated by k_ba_schur
     int it, reuse, done, termination, n_success, invalid_streak, need_linearize, step_valid, cur, first, max_iter, solver_failed;
-    long long prof[16];          // clock64() cycles per phase of k_ba_step, summed over iterations (debug)
+    long long prof[32];          // clock64() cycles per phase of k_ba_step, summed over iterations (debug)
 };
 
 struct BaDev {
@@ -165,7 +166,8 @@ __global__ void k_ba_prior_hessian(BaDev d)
 }
 
 // ------------------------------------------------------------------------------------------------
-// mode 0: linearise at X into the inactive accumulator (if state.need_linearize); mode 1: cost at Xc
+// mode 0: linearise at X into the inactive accumulator (first linearisation); mode 1: linearise at the candidate Xc
+// into the inactive accumulator (cost in acc_cost[inactive])
 __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
 {
     __shared__ double sJ[2 * PAIR_CHUNK][20];
@@ -174,19 +176,17 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
     __shared__ double simu_J[15 * 30], simu_JU[15 * 30], simu_r[15], simu_ru[15];
     const BaState& st = *d.st;
     if (st.done) return;
+    const long long t_eval0 = clock64();
     const int tid = threadIdx.x;
     const int tgt = st.cur ^ 1;            // inactive buffer
     if (mode == 0) { if (!st.need_linearize) return; }
-    else {
-        if (!st.step_valid) return;
-        // zero the inactive accumulator for the linearisation that may follow (safe: nothing reads it now)
-        size_t tot = acc_size(d.nc, d.L);
-        for (size_t e = (size_t)blockIdx.x * blockDim.x + tid; e < tot; e += (size_t)gridDim.x * blockDim.x) d.acc[tgt][e] = 0.0;
-        if (blockIdx.x == 0 && tid == 0) d.st->acc_cost[tgt] = 0.0;
-    }
+    else if (!st.step_valid) return;
+    // mode 1 linearises at the candidate: if k_ba_decide accepts the step this *is* the next linearisation (the same
+    // arithmetic on the same numbers as re-evaluating at X after the copy), if it rejects it the buffer is simply
+    // cleared again by the next k_ba_schur.  The target buffer was zeroed by k_ba_schur of this iteration.
     const double* X = mode == 0 ? d.X : d.Xc;
-    double* costp = mode == 0 ? &d.st->acc_cost[tgt] : &d.st->cand_cost;
-    const bool jac = (mode == 0);
+    double* costp = &d.st->acc_cost[tgt];
+    const bool jac = true;
     const int b = blockIdx.x;
     if (b < d.n_pairs) {
         // ---------------- visual factors of one pose pair ----------------
@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
         }
         cost = block_reduce_sum(cost, sred);
         if (tid == 0 && cost != 0.0) atomicAdd(costp, cost);
+        if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[14], (unsigned long long)(clock64() - t_eval0));
     } else if (b < d.n_pairs + d.n_imu) {
         // ---------------- one IMU factor ----------------
         const int m = b - d.n_pairs;
@@ -269,6 +270,8 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
                 }
             }
         }
+        __syncthreads();
+        if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[15], (unsigned long long)(clock64() - t_eval0));
     } else if (b == d.n_pairs + d.n_imu && d.pn > 0) {
         // ---------------- marginalisation prior: r = r0 + J0 dx, g += J0^T r (H_prior is constant) ----------------
         extern __shared__ double sdyn[];    // dx[pn], r[pn]
@@ -305,6 +308,8 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
                 for (int k = 0; k < pn; k++) s += d.pJ[(size_t)k * pn + c] * rr[k];
                 atomicAdd(&acc_g(d, tgt)[lc], s);
             }
+        __syncthreads();
+        if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[13], (unsigned long long)(clock64() - t_eval0));
     }
 }
 
@@ -320,6 +325,14 @@ __global__ void __launch_bounds__(256) k_ba_schur(BaDev d)
     const BaState& st = *d.st;
     if (st.done) return;
     const bool fresh = st.need_linearize != 0;
+    {   // clear the accumulator that is free during this iteration: k_ba_eval(1) linearises the candidate into it
+        const int freeb = fresh ? st.cur : (st.cur ^ 1);
+        const size_t tot = acc_size(d.nc, d.L);
+        const size_t nthr = (size_t)gridDim.x * gridDim.y * 256;
+        const size_t me = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.y * 16 + threadIdx.x;
+        for (size_t e = me; e < tot; e += nthr) d.acc[freeb][e] = 0.0;
+        if (me == 0) d.st->acc_cost[freeb] = 0.0;
+    }
     if (!fresh && st.reuse) return;               // the previous Gauss-Newton step is still valid
     const int cur = fresh ? (st.cur ^ 1) : st.cur;
     const int nc = d.nc, L = d.L;
@@ -438,6 +451,38 @@ __device__ __forceinline__ double block_reduce_max(double v, double* sh)
 
 // DoglegStrategy::ComputeStep + TrustRegionMinimizer::ComputeTrustRegionStep + candidate point.
 // Dynamic shared memory: packed lower triangle of the (nc+1) x (nc+1) augmented reduced system.
+// Back substitution L^T y = z by one warp.  L: block row b (rows 4b..4b+3) stored as 4 rows of 4(b+1) doubles at
+// offset 8 b (b+1) in shared memory, inv_diag[c] = 1/L[c][c].
+// Lane (c & 31) owns column c: acc_c = sum_{j>c} L[j][c] y_j in a register; per column the dependent chain is
+// DFMA (push) -> DFMA (t = z/l - acc/l) -> SHFL, the loads of row j are independent of it.
+__device__ __noinline__ void warp_backsubst(const double* L, const double* inv_diag, const double* z, double* y, int nc, int lane)
+{
+    constexpr int NS = (MAX_NC + 31) / 32;                  // column slots per lane
+    double accr[NS];
+#pragma unroll
+    for (int q = 0; q < NS; q++) accr[q] = 0.0;
+#pragma unroll
+    for (int slot = NS - 1; slot >= 0; slot--) {
+        if (slot * 32 < nc) {
+            const int c = slot * 32 + lane;
+            const double ir = c < nc ? inv_diag[c] : 0.0;
+            const double zi = c < nc ? z[c] * ir : 0.0;
+            for (int jj = min(31, nc - 1 - slot * 32); jj >= 0; jj--) {
+                const int j = slot * 32 + jj;
+                const double t = fma(-accr[slot], ir, zi);
+                const double yj = __shfl_sync(0xffffffffu, t, jj);
+                if (lane == jj) y[j] = yj;
+                const double* Lrow = L + 8 * (j >> 2) * ((j >> 2) + 1) + (j & 3) * 4 * ((j >> 2) + 1);
+#pragma unroll
+                for (int q = 0; q <= slot; q++) {
+                    const int i = q * 32 + lane;
+                    if (i < j) accr[q] = fma(Lrow[i], yj, accr[q]);
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
 {
     extern __shared__ double S[];                 // packed: S[i*(i+1)/2 + j], j <= i ; row nc = rhs
@@ -548,29 +593,45 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
             first_try = false;
             __syncthreads();
             PH(2);   // load / assemble reduced system
-            // Register-blocked right-looking Cholesky, block size 4.  The (nc+1)-row augmented system (row nc = rhs,
-            // rows above nc padded with identity) is cut into 4x4 blocks (bi, bj), bi >= bj, ordered column-major;
-            // thread t owns blocks t and t + 512 in registers (512 threads x 128 registers: no spills -- with most of
-            // the SM carved out as shared memory a spill costs an L2 round trip).
-            // Per panel p (4 columns): the diagonal owner factors its block and publishes inv(L_pp) [barrier];
-            // panel owners compute L_ip = A_ip L_pp^-T and publish their rows [barrier]; trailing owners apply the
-            // rank-4 update a -= L_i L_j^T (16 LDS.128 -> 64 DFMA).  The factor never leaves the registers: the
-            // blocked back substitution L^T y = z below uses it in place.
+            // Register-blocked right-looking Cholesky, block size 4, with look-ahead on the diagonal.  The (nc+1)-row
+            // augmented system (row nc = rhs, rows above nc padded with identity) is cut into 4x4 blocks (bi, bj), bi >= bj.
+            // The diagonal blocks belong to the last warp (lane l owns (l,l) and (l+32,l+32)), the strictly lower blocks,
+            // ordered column-major, to the other 480 threads (two each), all in registers.
+            // Per panel p (4 columns):  [barrier A]  panel owners compute L_ip = A_ip L_pp^-T from the published inv(L_pp)
+            // and publish their rows  [barrier B]  trailing owners apply the rank-4 update a -= L_i L_j^T (16 LDS.128 ->
+            // 64 DFMA); the diagonal warp updates its blocks too and then factors block p+1 and publishes inv(L_p+1,p+1)
+            // while the other warps are still updating: the sqrt/divide chain of the diagonal (the critical path of a
+            // 165-column factorisation on one SM) overlaps the bandwidth-bound trailing update.
+            // The factor is persisted in S (dead once the blocks sit in registers) for the back substitution.
             {
                 const int N4 = (nc + 4) >> 2;                       // block rows covering rows 0..nc
-                const int nblk = N4 * (N4 + 1) / 2;
-                double* colL4 = S + (((size_t)(nc + 1) * (nc + 2) / 2 + 1) & ~(size_t)1);  // [4][4*N4] panel columns (16 B aligned)
-                double* Linv = colL4 + 16 * N4;                        // [16]
+                const int noff = N4 * (N4 - 1) / 2;                 // strictly lower blocks
+                constexpr int NOFF_T = RB_THREADS - 32;             // threads owning off-diagonal blocks
+                const bool dwarp = tid >= NOFF_T;                   // the diagonal warp
+                // block row bi of the persisted factor = 4 rows of 4*(bi+1) doubles (row-major: a row of L is contiguous)
+                const size_t lp_size = (size_t)8 * N4 * (N4 + 1);
+                const size_t s_size = (size_t)(nc + 1) * (nc + 2) / 2;
+                double* colL4 = S + (((lp_size > s_size ? lp_size : s_size) + 1) & ~(size_t)1);  // [4][4*N4] panel columns (16 B aligned)
+                double* Linv2 = colL4 + 32 * N4;                       // [2][16] inverse of the diagonal factor, double-buffered (colL4 is [2][4][4*N4])
                 const int ld = 4 * N4;
                 int bi[2], bj[2];
                 bool mine[2];
                 double a[2][4][4];
 #pragma unroll
                 for (int b = 0; b < 2; b++) {
-                    const int t = tid + b * RB_THREADS;
-                    mine[b] = t < nblk;
-                    int cj = 0, off = 0;
-                    { int tt = min(t, nblk - 1); while (tt >= off + (N4 - cj)) { off += N4 - cj; cj++; } bi[b] = cj + (tt - off); bj[b] = cj; }
+                    if (dwarp) {
+                        const int q = (tid - NOFF_T) + 32 * b;
+                        mine[b] = q < N4;
+                        bi[b] = bj[b] = min(q, N4 - 1);
+                    } else {
+                        const int t = tid + b * NOFF_T;
+                        mine[b] = t < noff;
+                        int cj = 0, off = 0;
+                        const int tt = min(t, max(noff - 1, 0));
+                        while (cj < N4 - 2 && tt >= off + (N4 - 1 - cj)) { off += N4 - 1 - cj; cj++; }
+                        bi[b] = cj + 1 + (tt - off); bj[b] = cj;
+                        if (noff == 0) { mine[b] = false; bi[b] = 0; bj[b] = 0; }
+                    }
 #pragma unroll
                     for (int rr = 0; rr < 4; rr++)
 #pragma unroll
@@ -585,68 +646,81 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
                         }
                 }
                 __syncthreads();
-                long long tq = clock64(), tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define PQ(k) do { if (tid == 0) { long long t_ = clock64(); tacc[k] += t_ - tq; tq = t_; } } while (0)
-                for (int pnl = 0; pnl < N4; pnl++) {
-                    {   // ---- diagonal block (at most one of the two owned blocks): work on a selected copy to keep the code small ----
-                        const bool d0 = mine[0] && bi[0] == pnl && bj[0] == pnl, d1 = mine[1] && bi[1] == pnl && bj[1] == pnl;
-                        if (d0 || d1) {
-                            double w[4][4], iv[4];
+                // factor diagonal block q in place (this thread's block B), publish inv(L_qq) in buffer q & 1
+                auto factor_diag = [&](auto bc, int q) {
+                    constexpr int B = decltype(bc)::value;
+                    double iv[4];
 #pragma unroll
-                            for (int rr = 0; rr < 4; rr++)
+                    for (int jj = 0; jj < 4; jj++) {
+                        const int j = 4 * q + jj;
+                        if (j < nc) {
+                            const double dj = a[B][jj][jj];
+                            if (!(dj > 0.0)) s_fail = 1;
+                            const double inv = rsqrt(dj);
+                            iv[jj] = inv;
+                            a[B][jj][jj] = dj * inv;
+                            colbuf[1 + j] = inv;
 #pragma unroll
-                                for (int cc = 0; cc < 4; cc++) w[rr][cc] = d1 ? a[1][rr][cc] : a[0][rr][cc];
+                            for (int rr = jj + 1; rr < 4; rr++) a[B][rr][jj] *= inv;
 #pragma unroll
-                            for (int jj = 0; jj < 4; jj++) {
-                                const int j = 4 * pnl + jj;
-                                if (j < nc) {
-                                    const double dj = w[jj][jj];
-                                    if (!(dj > 0.0)) s_fail = 1;
-                                    const double inv = rsqrt(dj);
-                                    iv[jj] = inv;
-                                    w[jj][jj] = dj * inv;
-                                    colbuf[1 + j] = inv;
+                            for (int rr = jj + 1; rr < 4; rr++)
 #pragma unroll
-                                    for (int rr = jj + 1; rr < 4; rr++) w[rr][jj] *= inv;
+                                for (int cc = jj + 1; cc <= rr; cc++) a[B][rr][cc] -= a[B][rr][jj] * a[B][cc][jj];
+                        } else {
+                            a[B][jj][jj] = 1.0; iv[jj] = 1.0;
 #pragma unroll
-                                    for (int rr = jj + 1; rr < 4; rr++)
-#pragma unroll
-                                        for (int cc = jj + 1; cc <= rr; cc++) w[rr][cc] -= w[rr][jj] * w[cc][jj];
-                                } else {
-                                    w[jj][jj] = 1.0; iv[jj] = 1.0;
-#pragma unroll
-                                    for (int rr = jj + 1; rr < 4; rr++) w[rr][jj] = 0.0;
-                                }
-                            }
-                            // inverse of the lower-triangular factor: li[r][c] = (delta_rc - sum_{c<=m<r} w[r][m] li[m][c]) / w[r][r]
-#pragma unroll
-                            for (int cc = 0; cc < 4; cc++) {
-                                double li[4];
-#pragma unroll
-                                for (int rr = 0; rr < 4; rr++) {
-                                    if (rr < cc) { li[rr] = 0.0; continue; }
-                                    double t = (rr == cc) ? 1.0 : 0.0;
-#pragma unroll
-                                    for (int m = 0; m < 4; m++) if (m >= cc && m < rr) t -= w[rr][m] * li[m];
-                                    li[rr] = t * iv[rr];
-                                }
-#pragma unroll
-                                for (int rr = 0; rr < 4; rr++) Linv[rr * 4 + cc] = li[rr];
-                            }
-#pragma unroll
-                            for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                                for (int cc = 0; cc < 4; cc++) { if (d1) a[1][rr][cc] = w[rr][cc]; else a[0][rr][cc] = w[rr][cc]; }
+                            for (int rr = jj + 1; rr < 4; rr++) a[B][rr][jj] = 0.0;
                         }
                     }
-                    PQ(0);
-                    __syncthreads();
-                    PQ(1);
+                    // inverse of the lower-triangular factor: li[r][c] = (delta_rc - sum_{c<=m<r} l[r][m] li[m][c]) / l[r][r]
+                    double* Linv = Linv2 + 16 * (q & 1);
+#pragma unroll
+                    for (int cc = 0; cc < 4; cc++) {
+                        double li[4];
+#pragma unroll
+                        for (int rr = 0; rr < 4; rr++) {
+                            if (rr < cc) { li[rr] = 0.0; continue; }
+                            double t = (rr == cc) ? 1.0 : 0.0;
+#pragma unroll
+                            for (int m = 0; m < 4; m++) if (m >= cc && m < rr) t -= a[B][rr][m] * li[m];
+                            li[rr] = t * iv[rr];
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < 4; rr++) Linv[rr * 4 + cc] = li[rr];
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                        for (int cc = 0; cc <= rr; cc++) S[8 * q * (q + 1) + rr * 4 * (q + 1) + 4 * q + cc] = a[B][rr][cc];   // persisted factor
+                };
+                // rank-4 update of block b with the published columns of one panel
+                auto rank4 = [&](auto bc, const double* col) {
+                    constexpr int B = decltype(bc)::value;
+#pragma unroll
+                    for (int m = 0; m < 4; m++) {
+                        const double2 r01 = *reinterpret_cast<const double2*>(col + m * ld + 4 * bi[B]);
+                        const double2 r23 = *reinterpret_cast<const double2*>(col + m * ld + 4 * bi[B] + 2);
+                        const double2 c01 = *reinterpret_cast<const double2*>(col + m * ld + 4 * bj[B]);
+                        const double2 c23 = *reinterpret_cast<const double2*>(col + m * ld + 4 * bj[B] + 2);
+                        const double lr[4] = {r01.x, r01.y, r23.x, r23.y}, lc[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+                        for (int rr = 0; rr < 4; rr++)
+#pragma unroll
+                            for (int cc = 0; cc < 4; cc++) a[B][rr][cc] -= lr[rr] * lc[cc];
+                    }
+                };
+                using I0 = std::integral_constant<int, 0>;
+                using I1 = std::integral_constant<int, 1>;
+                for (int pnl = -1; pnl < N4; pnl++) {                  // pnl = -1: only the look-ahead (block (0,0) has no update pending)
+                  if (pnl >= 0) {
+                    __syncthreads();                                    // A: inv(L_pp) is published, the trailing updates of panel p-1 are done
                     if (s_fail) break;
-                    {   // ---- panel blocks: X = A L_pp^-T (a thread owns at most one block of a given column... or two: loop) ----
+                    double* colw = colL4 + (pnl & 1) * 4 * ld;
+                    if (!dwarp) {   // ---- panel blocks: X = A L_pp^-T ----
+                        const double* Linv = Linv2 + 16 * (pnl & 1);
 #pragma unroll 1
                         for (int b = 0; b < 2; b++) {
-                            const bool pb_ = b == 0 ? (mine[0] && bj[0] == pnl && bi[0] > pnl) : (mine[1] && bj[1] == pnl && bi[1] > pnl);
+                            const bool pb_ = b == 0 ? (mine[0] && bj[0] == pnl) : (mine[1] && bj[1] == pnl);
                             if (!pb_) continue;
                             double x[4][4];
 #pragma unroll
@@ -659,44 +733,49 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
                                     x[rr][cc] = t;
                                 }
                             const int brow = b == 0 ? bi[0] : bi[1];
+                            const int lpbase = 8 * brow * (brow + 1) + 4 * pnl;
 #pragma unroll
                             for (int rr = 0; rr < 4; rr++)
 #pragma unroll
-                                for (int cc = 0; cc < 4; cc++) { if (b == 0) a[0][rr][cc] = x[rr][cc]; else a[1][rr][cc] = x[rr][cc]; colL4[cc * ld + 4 * brow + rr] = x[rr][cc]; }
+                                for (int cc = 0; cc < 4; cc++) {
+                                    if (b == 0) a[0][rr][cc] = x[rr][cc]; else a[1][rr][cc] = x[rr][cc];
+                                    colw[cc * ld + 4 * brow + rr] = x[rr][cc];
+                                    S[lpbase + rr * 4 * (brow + 1) + cc] = x[rr][cc];
+                                }
+                        }
+                    } else if (pnl >= 1) {
+                        // the diagonal warp has no panel work: it applies panel p-1 to its not yet urgent blocks (q > p)
+                        // from the other column buffer while the panel owners fill this one
+                        const double* colr = colL4 + ((pnl - 1) & 1) * 4 * ld;
+                        if (mine[0] && bi[0] > pnl) rank4(I0(), colr);
+                        if (mine[1] && bi[1] > pnl) rank4(I1(), colr);
+                    }
+                    __syncthreads();                                    // B: the panel's columns are published
+                    if (!dwarp) {                                       // ---- trailing blocks: rank-4 update ----
+                        if (mine[0] && bj[0] > pnl) rank4(I0(), colw);
+                        if (mine[1] && bj[1] > pnl) rank4(I1(), colw);
+                    }
+                  }
+                    // look-ahead: the owner of diagonal block p+1 applies panel p to it and factors it while the other
+                    // warps are still updating
+                    if (dwarp && pnl + 1 < N4) {
+                        const int q = pnl + 1;
+                        if (tid - NOFF_T == (q & 31)) {
+                            const double* colr = colL4 + (pnl & 1) * 4 * ld;
+                            if (q < 32) { if (pnl >= 0) rank4(I0(), colr); factor_diag(I0(), q); }
+                            else { rank4(I1(), colr); factor_diag(I1(), q); }
                         }
                     }
-                    PQ(2);
-                    __syncthreads();
-                    PQ(3);
-#pragma unroll
-                    for (int b = 0; b < 2; b++)
-                        if (mine[b] && bj[b] > pnl) {                                 // ---- trailing block: rank-4 update ----
-#pragma unroll
-                            for (int m = 0; m < 4; m++) {
-                                const double2 r01 = *reinterpret_cast<const double2*>(colL4 + m * ld + 4 * bi[b]);
-                                const double2 r23 = *reinterpret_cast<const double2*>(colL4 + m * ld + 4 * bi[b] + 2);
-                                const double2 c01 = *reinterpret_cast<const double2*>(colL4 + m * ld + 4 * bj[b]);
-                                const double2 c23 = *reinterpret_cast<const double2*>(colL4 + m * ld + 4 * bj[b] + 2);
-                                const double lr[4] = {r01.x, r01.y, r23.x, r23.y}, lc[4] = {c01.x, c01.y, c23.x, c23.y};
-#pragma unroll
-                                for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                                    for (int cc = 0; cc < 4; cc++) a[b][rr][cc] -= lr[rr] * lc[cc];
-                            }
-                        }
-                    PQ(4);
                 }
-                PQ(5);
-                if (tid == 0) for (int k = 0; k < 6; k++) st.prof[8 + k] += tacc[k];
-                // ---- blocked back substitution  L^T y = z ----
-                // z = row nc of the factor (owned by the blocks of block row nc/4); accb[4q..4q+3] accumulates
-                // sum_{p>q} L_pq^T y_p.  Per block row p (descending): the diagonal owner solves its 4x4 system
-                // [barrier], the owners of block row p push L_pq^T y_p to the accumulators of q < p [barrier].
+                // ---- back substitution  L^T y = z  by warp 0 ----
+                // z = row nc of the factor (owned by the blocks of block row nc/4).  The factor was persisted row-major in
+                // S.  Lane (c & 31) owns column c: acc_c = sum_{j>c} L[j][c] y_j in a register; per column the chain is
+                // DFMA (push) -> DFMA (t = z/l - acc/l) -> SHFL, the loads of row j are independent of it.
                 __syncthreads();
                 if (!s_fail) {
                     const int brhs = nc >> 2, rrhs = nc & 3;
 #pragma unroll
-                    for (int b = 0; b < 2; b++) {
+                    for (int b = 0; b < 2; b++)
                         if (mine[b] && bi[b] == brhs) {
 #pragma unroll
                             for (int cc = 0; cc < 4; cc++) {
@@ -705,42 +784,9 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
                                 if (k < nc) zb[k] = zv;
                             }
                         }
-                        if (mine[b] && bi[b] == bj[b]) {
-#pragma unroll
-                            for (int cc = 0; cc < 4; cc++) { accb[4 * bi[b] + cc] = 0.0; if (4 * bi[b] + cc >= nc) zb[4 * bi[b] + cc] = 0.0; }
-                        }
-                    }
-                    __syncthreads();
-                    for (int pb = N4 - 1; pb >= 0; pb--) {
-#pragma unroll
-                        for (int b = 0; b < 2; b++)
-                            if (mine[b] && bi[b] == pb && bj[b] == pb) {
-                                const double t3 = zb[4 * pb + 3] - accb[4 * pb + 3], t2 = zb[4 * pb + 2] - accb[4 * pb + 2];
-                                const double t1 = zb[4 * pb + 1] - accb[4 * pb + 1], t0 = zb[4 * pb + 0] - accb[4 * pb + 0];
-                                // unknowns beyond nc (the rhs row, padding) are zero: their inverse pivot is taken as 0
-                                const double i3 = 4 * pb + 3 < nc ? colbuf[1 + 4 * pb + 3] : 0.0, i2 = 4 * pb + 2 < nc ? colbuf[1 + 4 * pb + 2] : 0.0;
-                                const double i1 = 4 * pb + 1 < nc ? colbuf[1 + 4 * pb + 1] : 0.0, i0 = 4 * pb < nc ? colbuf[1 + 4 * pb] : 0.0;
-                                const double y3 = t3 * i3;
-                                const double y2 = (t2 - a[b][3][2] * y3) * i2;
-                                const double y1 = (t1 - a[b][2][1] * y2 - a[b][3][1] * y3) * i1;
-                                const double y0 = (t0 - a[b][1][0] * y1 - a[b][2][0] * y2 - a[b][3][0] * y3) * i0;
-                                if (4 * pb < nc) yc[4 * pb] = y0;
-                                if (4 * pb + 1 < nc) yc[4 * pb + 1] = y1;
-                                if (4 * pb + 2 < nc) yc[4 * pb + 2] = y2;
-                                if (4 * pb + 3 < nc) yc[4 * pb + 3] = y3;
-                                ybl[0] = y0; ybl[1] = y1; ybl[2] = y2; ybl[3] = y3;
-                            }
-                        __syncthreads();
-#pragma unroll
-                        for (int b = 0; b < 2; b++)
-                            if (mine[b] && bi[b] == pb && bj[b] < pb) {
-                                const double y0 = ybl[0], y1 = ybl[1], y2 = ybl[2], y3 = ybl[3];
-#pragma unroll
-                                for (int cc = 0; cc < 4; cc++) accb[4 * bj[b] + cc] += a[b][0][cc] * y0 + a[b][1][cc] * y1 + a[b][2][cc] * y2 + a[b][3][cc] * y3;
-                            }
-                        __syncthreads();
-                    }
                 }
+                __syncthreads();
+                if (!s_fail && tid < 32) warp_backsubst(S, colbuf + 1, zb, yc, nc, tid);
             }
             __syncthreads();
             PH(3);   // Cholesky
@@ -844,7 +890,7 @@ __global__ void k_ba_decide(BaDev d)
             st.cost_hist[it] = st.x_cost; st.radius_hist[it] = st.radius;
         } else {
             st.invalid_streak = 0;
-            const double x_cost = st.x_cost, cand = st.cand_cost;
+            const double x_cost = st.x_cost, cand = st.acc_cost[st.cur ^ 1];     // candidate cost (k_ba_eval mode 1)
             if (st.step_norm <= 1e-8 * (st.x_norm + 1e-8)) { st.done = 1; st.termination = GF_BA_CONVERGENCE_PARAMETER; st.cost_hist[it] = x_cost; st.radius_hist[it] = st.radius; }
             else if (fabs(x_cost - cand) <= 1e-6 * x_cost) { st.done = 1; st.termination = GF_BA_CONVERGENCE_FUNCTION; st.cost_hist[it] = x_cost; st.radius_hist[it] = st.radius; }
             else {
@@ -877,7 +923,7 @@ struct gf_ba {
     // growable device buffers
     void* dbuf; size_t dcap;
     void* hbuf; size_t hcap;     // pinned staging
-    long long prof[16];
+    long long prof[32];
 };
 
 static int ensure(gf_ba* s, size_t dbytes)
@@ -968,7 +1014,15 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     const int n_pairs = (int)pair_cnt.size();
     std::vector<int> pair_start(n_pairs + 1, 0);
     for (int k = 0; k < n_pairs; k++) pair_start[k + 1] = pair_start[k] + pair_cnt[k];
-    d.n_pairs = n_pairs;
+    // one CTA of k_ba_eval per (pair, chunk of <= PAIR_CHUNK factors): long pairs are cut so that the CTAs are balanced
+    std::vector<int> work_start(1, 0), work_ij;
+    for (int k = 0; k < n_pairs; k++)
+        for (int c0 = pair_start[k]; c0 < pair_start[k + 1]; c0 += PAIR_CHUNK) {
+            work_ij.push_back(pair_ij[2 * k]); work_ij.push_back(pair_ij[2 * k + 1]);
+            work_start.push_back(std::min(c0 + PAIR_CHUNK, pair_start[k + 1]));
+        }
+    const int n_work = (int)work_ij.size() / 2;
+    d.n_pairs = n_work;
     const gf_ba_prior* pr = (p->prior && p->prior->n > 0) ? p->prior : nullptr;
     const int pn = pr ? pr->n : 0;
     std::vector<int> pcol(pn > 0 ? pn : 1, -1);
@@ -993,7 +1047,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
     const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (size_t)p->n_visual),
-                 o_imu = take(sizeof(gf_ba_imu_factor) * (size_t)p->n_imu), o_ps = take(sizeof(int) * (n_pairs + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_pairs > 0 ? n_pairs : 1)),
+                 o_imu = take(sizeof(gf_ba_imu_factor) * (size_t)p->n_imu), o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)),
                  o_cf = take(sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1)), o_pJ = take(sizeof(double) * (size_t)pn * pn), o_pr0 = take(sizeof(double) * pn),
                  o_px0 = take(sizeof(double) * px0_len), o_pcol = take(sizeof(int) * (size_t)(pn > 0 ? pn : 1));
     const size_t upload_bytes = off;
@@ -1017,8 +1071,8 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     }
     if (p->n_imu) memcpy(hb + o_imu, p->imu, sizeof(gf_ba_imu_factor) * (size_t)p->n_imu);
     for (int k = 0; k < p->n_imu; k++) if (p->imu[k].i < 0 || p->imu[k].i >= F || p->imu[k].j < 0 || p->imu[k].j >= F) return set_err(GF_ERR_INVALID_ARG, "imu factor index out of range");
-    memcpy(hb + o_ps, pair_start.data(), sizeof(int) * (n_pairs + 1));
-    if (n_pairs) memcpy(hb + o_pij, pair_ij.data(), sizeof(int) * 2 * n_pairs);
+    memcpy(hb + o_ps, work_start.data(), sizeof(int) * (n_work + 1));
+    if (n_work) memcpy(hb + o_pij, work_ij.data(), sizeof(int) * 2 * n_work);
     memcpy(hb + o_cf, col_feat.data(), sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1));
     if (pr) {
         memcpy(hb + o_pJ, pr->linearized_jacobians, sizeof(double) * (size_t)pn * pn);
@@ -1050,19 +1104,19 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
         GF_CUDA(cudaMemcpyAsync((char*)d.st + offsetof(BaState, max_iter), &mi, sizeof(int), cudaMemcpyHostToDevice, st));
     }
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
-    const int eval_blocks = n_pairs + p->n_imu + (pn ? 1 : 0);
+    const int eval_blocks = n_work + p->n_imu + (pn ? 1 : 0);
     const size_t prior_smem = sizeof(double) * 2 * (size_t)pn;
-    const size_t step_smem = sizeof(double) * ((size_t)(nc + 1) * (nc + 2) / 2 + 16 * (size_t)((nc + 4) / 4) + 16);
+    const size_t n4 = (size_t)((nc + 4) / 4);
+    const size_t step_smem = sizeof(double) * (std::max((size_t)(nc + 1) * (nc + 2) / 2, 8 * n4 * (n4 + 1)) + 2 + 32 * n4 + 32);
     const int iters = p->max_num_iterations;
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 0); GF_LAUNCHED(); }
-    const dim3 sgrid((nc + 15) / 16, (nc + 16) / 16), sblock(16, 16);
+    const dim3 sgrid(nc > 0 ? (nc + 15) / 16 : 1, (nc + 16) / 16), sblock(16, 16);
     for (int it = 0; it <= iters; it++) {
-        if (nc > 0 && it < iters) { k_ba_schur<<<sgrid, sblock, sizeof(double) * (size_t)(L > 0 ? L : 1), st>>>(d); GF_LAUNCHED(); }
+        if (it < iters) { k_ba_schur<<<sgrid, sblock, sizeof(double) * (size_t)(L > 0 ? L : 1), st>>>(d); GF_LAUNCHED(); }
         k_ba_step<<<1, RB_THREADS, step_smem, st>>>(d); GF_LAUNCHED();
         if (it == iters) break;                  // the extra k_ba_step adopts the last linearisation and closes the run
         if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 1); GF_LAUNCHED(); }
         k_ba_decide<<<1, 256, 0, st>>>(d); GF_LAUNCHED();
-        if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 0); GF_LAUNCHED(); }
     }
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpyAsync(hb + o_X, db + o_X, sizeof(double) * (X_FEAT + nfeat), cudaMemcpyDeviceToHost, st));
@@ -1087,10 +1141,10 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
 }
 
 /* debug: clock64() cycles per phase of k_ba_step of the last solve (see PH() markers) */
-int gf_ba_debug_profile(gf_ba* s, long long* out16)
+int gf_ba_debug_profile(gf_ba* s, long long* out32)
 {
-    if (!s || !out16) return set_err(GF_ERR_INVALID_ARG, "null argument");
-    memcpy(out16, s->prof, sizeof(s->prof));
+    if (!s || !out32) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    memcpy(out32, s->prof, sizeof(s->prof));
     return GF_OK;
 }
 

@@ -265,7 +265,7 @@ void gf_ba_destroy(gf_ba* s);
 /* ceres::Solve + double2vector's input: optimises the blocks of `p` in place. */
 int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* summary);
 /* Debug aid: SM cycles spent in each phase of the step kernel during the last solve (16 slots). */
-int gf_ba_debug_profile(gf_ba* s, long long* out16);
+int gf_ba_debug_profile(gf_ba* s, long long* out32);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

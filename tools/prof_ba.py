@@ -10,10 +10,11 @@ for k in range(n):
     print(ba.optimization(pb)["device_ms"])
 
 import ctypes
-prof = (ctypes.c_longlong * 16)()
+prof = (ctypes.c_longlong * 32)()
 ba.L.gf_ba_debug_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
 ba.L.gf_ba_debug_profile(ba._h, prof)
-names = ["adopt+norms", "diag+cauchy", "load S", "cholesky", "backsubst", "landmark backsubst", "dogleg+model", "candidate", "rb:t0 diag", "rb:t0 barA", "rb:t0 panel", "rb:t0 barB", "rb:t0 update", "rb:t0 exit"]
+names = ["adopt+norms", "diag+cauchy", "load S", "cholesky", "backsubst", "landmark backsubst", "dogleg+model", "candidate", "-", "-", "-", "-", "-", "eval: prior CTA max", "eval: visual CTA max", "eval: imu CTA max"]
 tot = sum(list(prof)[:8])
 for n_, v in zip(names, prof):
     print("%-20s %9d cycles %5.1f%%" % (n_, v, 100.0 * v / max(tot, 1)))
+
