@@ -48,6 +48,7 @@ class Problem:
         self.visual = (BaVisualFactor * 1)(); self.n_visual = 0
         self.imu = (BaImuFactor * 1)(); self.n_imu = 0
         self.wheel = (BaWheelFactor * 1)(); self.n_wheel = 0
+        self.ex_wheel_subset_mask = 0                  # PoseSubsetParameterization of the wheel extrinsic (bit k: component k frozen in Plus)
         self.prior = None
         self.gravity = np.array([0.0, 0.0, 9.805])
         self.visual_sqrt_info = 600.0 / 1.5          # FOCAL_LENGTH / 1.5 (estimator.cpp:193)
@@ -74,6 +75,20 @@ class Problem:
             f.linearized_ba[:] = list(d["linearized_ba"]); f.linearized_bg[:] = list(d["linearized_bg"])
             f.jacobian[:] = list(np.asarray(d["jacobian"], float).ravel()); f.covariance[:] = list(np.asarray(d["covariance"], float).ravel())
 
+    def set_wheel(self, rows):
+        """rows: dicts with i, j, sum_dt, delta_p, delta_q(xyzw), jacobian(6x3), covariance(6x6), linearized_sx/sy/sw/td,
+        linearized_vel, linearized_gyr, vel_1, gyr_1 (the WheelIntegrationBase members WheelFactor::Evaluate reads)."""
+        rows = list(rows)
+        self.n_wheel = len(rows)
+        self.wheel = (BaWheelFactor * max(len(rows), 1))()
+        for f, d in zip(self.wheel, rows):
+            f.i, f.j, f.sum_dt = int(d["i"]), int(d["j"]), float(d["sum_dt"])
+            f.delta_p[:] = list(d["delta_p"]); f.delta_q[:] = list(d["delta_q"])
+            f.jacobian[:] = list(np.asarray(d["jacobian"], float).ravel()); f.covariance[:] = list(np.asarray(d["covariance"], float).ravel())
+            f.linearized_sx, f.linearized_sy, f.linearized_sw, f.linearized_td = (float(d[k]) for k in ("linearized_sx", "linearized_sy", "linearized_sw", "linearized_td"))
+            f.linearized_vel[:] = list(d["linearized_vel"]); f.linearized_gyr[:] = list(d["linearized_gyr"])
+            f.vel_1[:] = list(d["vel_1"]); f.gyr_1[:] = list(d["gyr_1"])
+
     def struct(self):
         p = BaProblem()
         p.n_frames, p.n_features, p.n_visual, p.n_imu, p.n_wheel = self.n_frames, self.n_features, self.n_visual, self.n_imu, self.n_wheel
@@ -91,6 +106,7 @@ class Problem:
         p.prior = ctypes.pointer(self._keep) if self._keep is not None else None
         p.gravity[:] = list(self.gravity)
         p.visual_sqrt_info = self.visual_sqrt_info
+        p.ex_wheel_subset_mask = int(self.ex_wheel_subset_mask)
         return p
 
     def clone(self):
@@ -100,7 +116,7 @@ class Problem:
                   "para_td_wheel", "feature_const", "gravity"):
             setattr(q, k, getattr(self, k).copy())
         for k in ("frames_const", "pose0_const", "ex_pose_const", "td_const", "ex_wheel_const", "ix_wheel_const", "td_wheel_const",
-                  "n_visual", "n_imu", "n_wheel", "visual_sqrt_info", "max_num_iterations", "prior"):
+                  "n_visual", "n_imu", "n_wheel", "visual_sqrt_info", "max_num_iterations", "prior", "ex_wheel_subset_mask"):
             setattr(q, k, getattr(self, k))
         q.visual = (BaVisualFactor * max(self.n_visual, 1))(); ctypes.memmove(q.visual, self.visual, ctypes.sizeof(BaVisualFactor) * self.n_visual)
         q.imu = (BaImuFactor * max(self.n_imu, 1))(); ctypes.memmove(q.imu, self.imu, ctypes.sizeof(BaImuFactor) * self.n_imu)

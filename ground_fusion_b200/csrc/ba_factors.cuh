@@ -330,4 +330,183 @@ __device__ inline bool sqrt_info_from_cov(const double* cov, int n, double* out,
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wheel odometry factor.  SO3 exp/log as in Sophus (upstream, un-vendored), right Jacobians as vendored in the reference's
+// utility/sophus_utils.hpp:155-236; the arithmetic mirrors oracle/ba_oracle.c (gfo_eval_wheel).
+constexpr double kSophusEps = 1e-10;
+constexpr double kPi = 3.14159265358979323846;
+__device__ inline void so3_exp_q(const double* w, double* q)
+{
+    const double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    double imag, real;
+    if (t2 < kSophusEps * kSophusEps) {
+        const double t4 = t2 * t2;
+        imag = 0.5 - (1.0 / 48.0) * t2 + (1.0 / 3840.0) * t4;
+        real = 1.0 - (1.0 / 8.0) * t2 + (1.0 / 384.0) * t4;
+    } else {
+        const double t = sqrt(t2), h = 0.5 * t;
+        imag = sin(h) / t; real = cos(h);
+    }
+    q[0] = imag * w[0]; q[1] = imag * w[1]; q[2] = imag * w[2]; q[3] = real;
+}
+__device__ inline void so3_log_q(const double* qin, double* out)
+{
+    double q[4] = {qin[0], qin[1], qin[2], qin[3]};
+    q_normalize(q);
+    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], w = q[3];
+    double f;
+    if (n2 < kSophusEps * kSophusEps) f = 2.0 / w - (2.0 / 3.0) * n2 / (w * w * w);
+    else {
+        const double n = sqrt(n2);
+        if (fabs(w) < kSophusEps) f = (w > 0 ? kPi : -kPi) / n;
+        else f = 2.0 * atan(n / w) / n;
+    }
+    out[0] = f * q[0]; out[1] = f * q[1]; out[2] = f * q[2];
+}
+__device__ inline void so3_exp_R(const double* w, double* R) { double q[4]; so3_exp_q(w, q); q_to_R(q, R); }
+__device__ inline void so3_Jr(const double* phi, double* J)
+{
+    const double n2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+    double h[9], h2[9]; skew(phi, h); m3_mul(h, h, h2);
+    double a, b;
+    if (n2 > kSophusEps) { const double n = sqrt(n2); a = (1.0 - cos(n)) / n2; b = (n - sin(n)) / (n2 * n); }
+    else { a = 0.5; b = 1.0 / 6.0; }
+    for (int k = 0; k < 9; k++) J[k] = ((k % 4 == 0) ? 1.0 : 0.0) - a * h[k] + b * h2[k];
+}
+__device__ inline void so3_Jr_inv(const double* phi, double* J)
+{
+    const double n2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+    double h[9], h2[9]; skew(phi, h); m3_mul(h, h, h2);
+    double b;
+    if (n2 > kSophusEps) {
+        const double n = sqrt(n2);
+        if (n < kPi - 1e-5) b = 1.0 / n2 - (1.0 + cos(n)) / (2.0 * n * sin(n));
+        else b = 1.0 / (kPi * kPi);
+    } else b = 1.0 / 12.0;
+    for (int k = 0; k < 9; k++) J[k] = ((k % 4 == 0) ? 1.0 : 0.0) + 0.5 * h[k] + b * h2[k];
+}
+
+constexpr int WHEEL_COLS = 22;   // local columns of one wheel factor: pose_i 6 | pose_j 6 | ex_wheel 6 | sx | sy | sw | td
+// WheelFactor::Evaluate (reference factor/wheel_factor.h:28-247) + WheelIntegrationBase::evaluate
+// (wheel_integration_base.h:179-219).  res[6] and J[6][22] come out multiplied by sqrt_info = LLT(cov^-1).L^T.
+// M: scratch of 6*12 doubles.  Returns false if the covariance is not positive definite.
+__device__ __noinline__ bool eval_wheel(const gf_ba_wheel_factor& f, const double* pose_i, const double* pose_j, const double* exw,
+                                  double sx, double sy, double sw, double td, double* res, double* J, bool jac, double* M)
+{
+    const double* Pi = pose_i; const double* Qi = pose_i + 3; const double* Pj = pose_j; const double* Qj = pose_j + 3;
+    const double* tio = exw; const double* qio = exw + 3;
+    double dp_dsx[3], dp_dsy[3], dp_dsw[3], dq_dsw[3];
+    for (int k = 0; k < 3; k++) { dp_dsx[k] = f.jacobian[k * 3]; dp_dsy[k] = f.jacobian[k * 3 + 1]; dp_dsw[k] = f.jacobian[k * 3 + 2]; dq_dsw[k] = f.jacobian[(3 + k) * 3 + 2]; }
+    const double dsx = sx - f.linearized_sx, dsy = sy - f.linearized_sy, dsw = sw - f.linearized_sw, dtd = td - f.linearized_td;
+    const double sv[3] = {sx, sy, 1.0};
+    double Ri[9], Rj[9], rio[9]; q_to_R(Qi, Ri); q_to_R(Qj, Rj); q_to_R(qio, rio);
+    double cp[3]; for (int k = 0; k < 3; k++) cp[k] = f.delta_p[k] + dp_dsx[k] * dsx + dp_dsy[k] * dsy + dp_dsw[k] * dsw;
+    double dq0[4] = {f.delta_q[0], f.delta_q[1], f.delta_q[2], f.delta_q[3]}, e[4], cq[4], t3[3];
+    q_normalize(dq0);
+    for (int k = 0; k < 3; k++) t3[k] = dq_dsw[k] * dsw;
+    so3_exp_q(t3, e); q_mul(dq0, e, cq); q_normalize(cq);
+    double Rcq[9]; q_to_R(cq, Rcq);
+    double fcw[3], fcv[3], bcv[3], bcw[3], nbcw[3];
+    for (int k = 0; k < 3; k++) { fcw[k] = sw * f.linearized_gyr[k] * dtd; fcv[k] = sv[k] * f.linearized_vel[k] * dtd; bcv[k] = sv[k] * f.vel_1[k] * dtd; bcw[k] = sw * f.gyr_1[k] * dtd; nbcw[k] = -bcw[k]; }
+    double E1[4], E2[4], qt[4], dqt[4]; so3_exp_q(fcw, E1); so3_exp_q(nbcw, E2);
+    q_mul(E1, cq, qt); q_mul(qt, E2, dqt); q_normalize(dqt);
+    double RE1[9]; q_to_R(E1, RE1);
+    double u[3], inner[3], dpt[3]; m3_v(Rcq, bcv, u);
+    for (int k = 0; k < 3; k++) inner[k] = fcv[k] + cp[k] - u[k];
+    m3_v(RE1, inner, dpt);
+    double Rio[9], RioT[9]; m3_mul(Ri, rio, Rio); m3_T(Rio, RioT);
+    double a1[3], a2[3], dw[3], dpos[3]; m3_v(Rj, tio, a1); m3_v(Ri, tio, a2);
+    for (int k = 0; k < 3; k++) dw[k] = a1[k] + Pj[k] - a2[k] - Pi[k];
+    m3_v(RioT, dw, dpos);
+    double raw[6];
+    for (int k = 0; k < 3; k++) raw[k] = dpos[k] - dpt[k];
+    double qiqio[4], inv1[4], inv2[4], qjqio[4], t1[4], t2[4];
+    q_mul(Qi, qio, qiqio); q_inv(qiqio, inv1); q_inv(dqt, inv2); q_mul(Qj, qio, qjqio);
+    q_mul(inv2, inv1, t1); q_mul(t1, qjqio, t2);
+    double rq[3]; so3_log_q(t2, rq);
+    for (int k = 0; k < 3; k++) raw[3 + k] = rq[k];
+    double U[36];
+    if (!sqrt_info_from_cov(f.covariance, 6, U, M)) return false;
+    for (int i = 0; i < 6; i++) { double v = 0; for (int k = 0; k < 6; k++) v += U[i * 6 + k] * raw[k]; res[i] = v; }
+    if (!jac) return true;
+    double R[6 * WHEEL_COLS];                         // raw Jacobian
+    for (int k = 0; k < 6 * WHEEL_COLS; k++) R[k] = 0.0;
+    auto put = [&](int r0, int c0, const double* B, double sgn) { for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[(r0 + r) * WHEEL_COLS + c0 + c] = sgn * B[r * 3 + c]; };
+    double Jri[9]; so3_Jr_inv(rq, Jri);
+    double drdsw[3]; for (int k = 0; k < 3; k++) drdsw[k] = dq_dsw[k] * dsw;
+    double Jr_drdsw[9]; so3_Jr(drdsw, Jr_drdsw);
+    double S[9], A[9], B[9], C[9], RiT[9], rioT[9]; m3_T(Ri, RiT); m3_T(rio, rioT);
+    {   // pose_i
+        put(0, 0, RioT, -1.0);
+        skew(tio, S); m3_mul(Ri, S, A); m3_mul(RioT, A, B);
+        double w1[3]; m3_v(RiT, dw, w1); skew(w1, S); m3_mul(rioT, S, C);
+        for (int k = 0; k < 9; k++) B[k] += C[k];
+        put(0, 3, B, 1.0);
+        double qa[4], qb[4]; q_inv(qjqio, qa); q_mul(qa, Qi, qb); q_to_R(qb, A); m3_mul(Jri, A, B);
+        put(3, 3, B, -1.0);
+    }
+    {   // pose_j
+        put(0, 6, RioT, 1.0);
+        skew(tio, S); m3_mul(RioT, Rj, A); m3_mul(A, S, B);
+        put(0, 9, B, -1.0);
+        m3_mul(Jri, rioT, B);
+        put(3, 9, B, 1.0);
+    }
+    {   // wheel extrinsic
+        for (int k = 0; k < 9; k++) A[k] = Rj[k] - Ri[k];
+        m3_mul(RioT, A, B);
+        put(0, 12, B, 1.0);
+        skew(dpos, S);
+        put(0, 15, S, 1.0);
+        double qa[4], qb[4], qc[4]; q_inv(qjqio, qa); q_mul(qa, Qi, qb); q_mul(qb, qio, qc); q_to_R(qc, A);
+        for (int k = 0; k < 9; k++) A[k] = ((k % 4 == 0) ? 1.0 : 0.0) - A[k];
+        m3_mul(Jri, A, B);
+        put(3, 15, B, 1.0);
+    }
+    double Jrtd[9], Jrmtd[9], Rfcv[9], Rfcw[9], Rnr[9], Rbcw[9], RcqT[9], nfcw[3], nrq[3];
+    for (int k = 0; k < 3; k++) { nfcw[k] = -fcw[k]; nrq[k] = -rq[k]; }
+    so3_Jr(fcw, Jrtd); so3_Jr(nfcw, Jrmtd);
+    so3_exp_R(fcv, Rfcv); so3_exp_R(fcw, Rfcw); so3_exp_R(nrq, Rnr); so3_exp_R(bcw, Rbcw); m3_T(Rcq, RcqT);
+    for (int axis = 0; axis < 2; axis++) {            // sx, sy (the reference rotates by exp(forward_compensate_v) here)
+        const double* dpds = axis == 0 ? dp_dsx : dp_dsy;
+        double e1[3] = {0, 0, 0}, e2[3] = {0, 0, 0}, w1[3], w2[3], w3[3];
+        e1[axis] = f.linearized_vel[axis] * dtd;
+        e2[axis] = f.vel_1[axis] * dtd;
+        m3_v(Rcq, e2, w1);
+        for (int k = 0; k < 3; k++) w2[k] = e1[k] + dpds[k] - w1[k];
+        m3_v(Rfcv, w2, w3);
+        for (int k = 0; k < 3; k++) R[k * WHEEL_COLS + 18 + axis] = -w3[k];
+    }
+    {   // sw
+        double w1[3], w2[3], w3[3], w4[3], w5[3], lg[3], svv1[3], tot[3], outp[3], r1[3], r2[3], r3[3], r4[3], r5[3];
+        m3_v(Jr_drdsw, dq_dsw, w1); skew(w1, S);
+        for (int k = 0; k < 3; k++) svv1[k] = sv[k] * f.vel_1[k] * dtd;
+        m3_v(S, svv1, w2); m3_v(Rcq, w2, w3);
+        for (int k = 0; k < 3; k++) lg[k] = f.linearized_gyr[k] * dtd;
+        m3_v(Jrtd, lg, w4); skew(w4, S); m3_v(S, inner, w5);
+        for (int k = 0; k < 3; k++) tot[k] = dp_dsw[k] - w3[k] + w5[k];
+        m3_v(Rfcw, tot, outp);
+        m3_v(RcqT, w4, r1);
+        for (int k = 0; k < 3; k++) r2[k] = r1[k] + w1[k];
+        m3_v(Rbcw, r2, r3); m3_v(Rnr, r3, r4); m3_v(Jri, r4, r5);
+        for (int k = 0; k < 3; k++) { R[k * WHEEL_COLS + 20] = -outp[k]; R[(3 + k) * WHEEL_COLS + 20] = -r5[k]; }
+    }
+    {   // td
+        double w1[3], w2[3], w3[3], w4[3], w5[3], svl[3], svv[3], swg[3], swg1[3], r1[3], r2[3], r3[3], r4[3], r5[3], r6[3];
+        for (int k = 0; k < 3; k++) { svl[k] = sv[k] * f.linearized_vel[k]; svv[k] = sv[k] * f.vel_1[k]; swg[k] = sw * f.linearized_gyr[k]; swg1[k] = sw * f.gyr_1[k]; }
+        m3_v(Rcq, svv, w1);
+        m3_v(Jrtd, swg, w2); skew(w2, S); m3_v(S, inner, w3);
+        for (int k = 0; k < 3; k++) w4[k] = svl[k] - w1[k] + w3[k];
+        m3_v(Rfcw, w4, w5);
+        m3_v(RcqT, w2, r1); m3_v(Rbcw, r1, r2);
+        m3_v(Jrmtd, swg1, r3);
+        for (int k = 0; k < 3; k++) r4[k] = r2[k] - r3[k];
+        m3_v(Rnr, r4, r5); m3_v(Jri, r5, r6);
+        for (int k = 0; k < 3; k++) { R[k * WHEEL_COLS + 21] = -w5[k]; R[(3 + k) * WHEEL_COLS + 21] = -r6[k]; }
+    }
+    for (int i = 0; i < 6; i++)
+        for (int c = 0; c < WHEEL_COLS; c++) { double v = 0; for (int k = 0; k < 6; k++) v += U[i * 6 + k] * R[k * WHEEL_COLS + c]; J[i * WHEEL_COLS + c] = v; }
+    return true;
+}
+
 }  // namespace gfba

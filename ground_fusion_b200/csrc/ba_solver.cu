@@ -27,7 +27,8 @@ using namespace gfba;
 namespace gfba {
 
 constexpr int MAXF = GF_BA_MAX_FRAMES;
-constexpr int X_POSE = 0, X_SB = 7 * MAXF, X_EX = X_SB + 9 * MAXF, X_TD = X_EX + 7, X_FEAT = X_TD + 1;
+constexpr int X_POSE = 0, X_SB = 7 * MAXF, X_EX = X_SB + 9 * MAXF, X_TD = X_EX + 7, X_EXW = X_TD + 1, X_IX = X_EXW + 7, X_TDW = X_IX + 3,
+              X_FEAT = X_TDW + 1;
 constexpr int PAIR_THREADS = 256, PAIR_CHUNK = 64;   // factors staged per pass (2*64 rows x 20 cols in smem)
 constexpr int RB_THREADS = 512;                      // k_ba_step block size: 128 registers per thread
 constexpr int MAX_NC = 175;                          // reduced dimension supported by k_ba_step: 4x4 blocks of the (nc+1)-row system <= 1024 threads
@@ -42,8 +43,10 @@ struct BaState {
 };
 
 struct BaDev {
-    int F, nfeat, n_vis, n_imu, n_pairs, nc, L, n;
+    int F, nfeat, n_vis, n_imu, n_wheel, n_pairs, nc, L, n;
     int col_pose[MAXF], col_sb[MAXF], col_ex, col_td;
+    int col_exw, col_ix[3], col_tdw, exw_mask;     // wheel extrinsic / intrinsics / time offset (-1: constant or absent)
+    const gf_ba_wheel_factor* wheel;
     const int* col_feat;
     double *X, *Xc;
     const gf_ba_visual_factor* vis;
@@ -272,7 +275,39 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
         }
         __syncthreads();
         if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[15], (unsigned long long)(clock64() - t_eval0));
-    } else if (b == d.n_pairs + d.n_imu && d.pn > 0) {
+    } else if (b < d.n_pairs + d.n_imu + d.n_wheel) {
+        // ---------------- one wheel factor (6 residuals, 22 local columns) ----------------
+        const gf_ba_wheel_factor& f = d.wheel[b - d.n_pairs - d.n_imu];
+        double* wJ = simu_J;          // [6][WHEEL_COLS]
+        double* wr = simu_r;          // [6]
+        if (tid == 0) {
+            const bool ok = eval_wheel(f, X + X_POSE + 7 * f.i, X + X_POSE + 7 * f.j, X + X_EXW, X[X_IX], X[X_IX + 1], X[X_IX + 2], X[X_TDW], wr, wJ, jac, simu_JU);
+            if (!ok) for (int k = 0; k < 6; k++) { wr[k] = 0.0; for (int c = 0; c < WHEEL_COLS; c++) wJ[k * WHEEL_COLS + c] = 0.0; }
+            double c = 0; for (int k = 0; k < 6; k++) c += 0.5 * wr[k] * wr[k];
+            atomicAdd(costp, c);
+        }
+        __syncthreads();
+        auto col_of = [&](int a) {
+            if (a < 6) return d.col_pose[f.i] < 0 ? -1 : d.col_pose[f.i] + a;
+            if (a < 12) return d.col_pose[f.j] < 0 ? -1 : d.col_pose[f.j] + a - 6;
+            if (a < 18) return d.col_exw < 0 ? -1 : d.col_exw + a - 12;
+            if (a < 21) return d.col_ix[a - 18];
+            return d.col_tdw;
+        };
+        for (int o = tid; o < WHEEL_COLS * (WHEEL_COLS + 1); o += PAIR_THREADS) {
+            if (o < WHEEL_COLS * WHEEL_COLS) {
+                const int a = o / WHEEL_COLS, c = o - a * WHEEL_COLS, ca = col_of(a), cc = col_of(c);
+                if (ca < 0 || cc < 0) continue;
+                double s = 0; for (int r = 0; r < 6; r++) s += wJ[r * WHEEL_COLS + a] * wJ[r * WHEEL_COLS + c];
+                atomicAdd(&acc_H(d, tgt)[(size_t)ca * d.nc + cc], s);
+            } else {
+                const int a = o - WHEEL_COLS * WHEEL_COLS, ca = col_of(a);
+                if (ca < 0) continue;
+                double s = 0; for (int r = 0; r < 6; r++) s += wJ[r * WHEEL_COLS + a] * wr[r];
+                atomicAdd(&acc_g(d, tgt)[ca], s);
+            }
+        }
+    } else if (b == d.n_pairs + d.n_imu + d.n_wheel && d.pn > 0) {
         // ---------------- marginalisation prior: r = r0 + J0 dx, g += J0^T r (H_prior is constant) ----------------
         extern __shared__ double sdyn[];    // dx[pn], r[pn]
         double* dx = sdyn; double* rr = sdyn + d.pn;
@@ -281,8 +316,9 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
             int kind = d.pkind[blk], idx = d.pidx[blk];
             const double* x0 = d.px0 + d.pxoff[blk];
             const double* x = kind == GF_BA_BLOCK_POSE ? X + X_POSE + 7 * d.pindex[blk] : kind == GF_BA_BLOCK_SPEEDBIAS ? X + X_SB + 9 * d.pindex[blk]
-                              : kind == GF_BA_BLOCK_EX_POSE ? X + X_EX : X + X_TD;
-            int size = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1;
+                              : kind == GF_BA_BLOCK_EX_POSE ? X + X_EX : kind == GF_BA_BLOCK_TD ? X + X_TD : kind == GF_BA_BLOCK_EX_WHEEL ? X + X_EXW
+                              : kind == GF_BA_BLOCK_SX ? X + X_IX : kind == GF_BA_BLOCK_SY ? X + X_IX + 1 : kind == GF_BA_BLOCK_SW ? X + X_IX + 2 : X + X_TDW;
+            int size = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1;
             if (size != 7) for (int k = 0; k < size; k++) dx[idx + k] = x[k] - x0[k];
             else {
                 for (int k = 0; k < 3; k++) dx[idx + k] = x[k] - x0[k];
@@ -417,6 +453,13 @@ __device__ inline void plus_all(const BaDev& d, const double* X, const double* d
     if (tid == 0) {
         if (d.col_ex >= 0) pose_plus(X + X_EX, delta + d.col_ex, Y + X_EX);
         if (d.col_td >= 0) Y[X_TD] = X[X_TD] + delta[d.col_td];
+        if (d.col_exw >= 0) {    // PoseSubsetParameterization: masked components are zeroed inside Plus only
+            double dd[6];
+            for (int k = 0; k < 6; k++) dd[k] = ((d.exw_mask >> k) & 1) ? 0.0 : delta[d.col_exw + k];
+            pose_plus(X + X_EXW, dd, Y + X_EXW);
+        }
+        for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) Y[X_IX + k] = X[X_IX + k] + delta[d.col_ix[k]];
+        if (d.col_tdw >= 0) Y[X_TDW] = X[X_TDW] + delta[d.col_tdw];
     }
     for (int k = tid; k < d.nfeat; k += nt) { int c = d.col_feat[k]; if (c >= 0) Y[X_FEAT + k] = X[X_FEAT + k] + delta[c]; }
     __syncthreads();
@@ -427,7 +470,12 @@ __device__ inline void diff_norms(const BaDev& d, const double* A, const double*
     s2 = 0; mx = 0;
     auto acc = [&](int off, int size) { for (int k = 0; k < size; k++) { double v = A[off + k] - (B ? B[off + k] : 0.0); s2 += v * v; mx = fmax(mx, fabs(v)); } };
     for (int f = tid; f < d.F; f += nt) { if (d.col_pose[f] >= 0) acc(X_POSE + 7 * f, 7); if (d.col_sb[f] >= 0) acc(X_SB + 9 * f, 9); }
-    if (tid == 0) { if (d.col_ex >= 0) acc(X_EX, 7); if (d.col_td >= 0) acc(X_TD, 1); }
+    if (tid == 0) {
+        if (d.col_ex >= 0) acc(X_EX, 7); if (d.col_td >= 0) acc(X_TD, 1);
+        if (d.col_exw >= 0) acc(X_EXW, 7);
+        for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) acc(X_IX + k, 1);
+        if (d.col_tdw >= 0) acc(X_TDW, 1);
+    }
     for (int k = tid; k < d.nfeat; k += nt) if (d.col_feat[k] >= 0) acc(X_FEAT + k, 1);
 }
 __device__ __forceinline__ double block_reduce_max(double v, double* sh)
@@ -977,14 +1025,14 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
 {
     if (!s || !p || !sum) return set_err(GF_ERR_INVALID_ARG, "null argument");
     if (p->n_frames < 1 || p->n_frames > GF_BA_MAX_FRAMES) return set_err(GF_ERR_INVALID_ARG, "n_frames out of range");
-    if (p->n_wheel > 0) return set_err(GF_ERR_UNSUPPORTED, "wheel factors are not implemented yet (SURVEY 8a BA-6)");
+    if (p->n_wheel < 0 || (p->n_wheel > 0 && (!p->wheel || !p->para_ex_wheel || !p->para_ix_wheel || !p->para_td_wheel))) return set_err(GF_ERR_INVALID_ARG, "wheel factors without their parameter blocks");
     if (p->max_num_iterations < 0 || p->max_num_iterations > GF_BA_MAX_ITERATIONS) return set_err(GF_ERR_INVALID_ARG, "max_num_iterations out of range");
     GF_CUDA(cudaSetDevice(s->device));
     memset(sum, 0, sizeof(*sum));
     const int F = p->n_frames, nfeat = p->n_features;
     // ---- layout (same rules as ceres::Problem construction, estimator.cpp:2950-3100, 3233-3246, 3291) ----
     BaDev d; memset(&d, 0, sizeof(d));
-    d.F = F; d.nfeat = nfeat; d.n_vis = p->n_visual; d.n_imu = p->n_imu;
+    d.F = F; d.nfeat = nfeat; d.n_vis = p->n_visual; d.n_imu = p->n_imu; d.n_wheel = p->n_wheel;
     const bool use_sb = p->para_speed_bias && !p->pose0_const;
     int c = 0;
     for (int f = 0; f < MAXF; f++) { d.col_pose[f] = -1; d.col_sb[f] = -1; }
@@ -992,6 +1040,12 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     for (int f = 0; f < F; f++) { bool k = p->frames_const || !use_sb; if (!k) { d.col_sb[f] = c; c += 9; } }
     d.col_ex = p->ex_pose_const ? -1 : c; if (!p->ex_pose_const) c += 6;
     d.col_td = p->td_const ? -1 : c; if (!p->td_const) c += 1;
+    d.col_exw = -1; d.col_ix[0] = d.col_ix[1] = d.col_ix[2] = -1; d.col_tdw = -1; d.exw_mask = p->ex_wheel_subset_mask;
+    if (p->n_wheel > 0) {      // estimator.cpp:3008-3056: these blocks only exist with USE_WHEEL
+        if (!p->ex_wheel_const) { d.col_exw = c; c += 6; }
+        if (!p->ix_wheel_const) for (int k = 0; k < 3; k++) d.col_ix[k] = c++;
+        if (!p->td_wheel_const) d.col_tdw = c++;
+    }
     d.nc = c;
     std::vector<int> col_feat(nfeat > 0 ? nfeat : 1, -1);
     for (int v = 0; v < p->n_visual; v++) {
@@ -1033,10 +1087,12 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
         for (int b = 0; b < pr->n_blocks; b++) {
             int kind = pr->block_kind[b], idx = pr->block_index[b];
             d.pkind[b] = kind; d.pindex[b] = idx; d.pidx[b] = pr->block_idx[b]; d.pxoff[b] = (int)px0_len;
-            int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1;
+            int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1;
             int ls = gs == 7 ? 6 : gs;
-            int lc = kind == GF_BA_BLOCK_POSE ? d.col_pose[idx] : kind == GF_BA_BLOCK_SPEEDBIAS ? d.col_sb[idx] : kind == GF_BA_BLOCK_EX_POSE ? d.col_ex : kind == GF_BA_BLOCK_TD ? d.col_td : -1;
-            if (kind > GF_BA_BLOCK_TD) return set_err(GF_ERR_UNSUPPORTED, "prior on wheel blocks not implemented yet");
+            if (kind < 0 || kind > GF_BA_BLOCK_TD_WHEEL) return set_err(GF_ERR_INVALID_ARG, "unknown prior block kind");
+            if ((kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_SPEEDBIAS) && (idx < 0 || idx >= F)) return set_err(GF_ERR_INVALID_ARG, "prior block index out of range");
+            int lc = kind == GF_BA_BLOCK_POSE ? d.col_pose[idx] : kind == GF_BA_BLOCK_SPEEDBIAS ? d.col_sb[idx] : kind == GF_BA_BLOCK_EX_POSE ? d.col_ex : kind == GF_BA_BLOCK_TD ? d.col_td
+                     : kind == GF_BA_BLOCK_EX_WHEEL ? d.col_exw : kind == GF_BA_BLOCK_SX ? d.col_ix[0] : kind == GF_BA_BLOCK_SY ? d.col_ix[1] : kind == GF_BA_BLOCK_SW ? d.col_ix[2] : d.col_tdw;
             if (lc >= 0) for (int k = 0; k < ls; k++) pcol[pr->block_idx[b] + k] = lc + k;
             px0_len += gs;
         }
@@ -1047,7 +1103,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
     const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (size_t)p->n_visual),
-                 o_imu = take(sizeof(gf_ba_imu_factor) * (size_t)p->n_imu), o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)),
+                 o_imu = take(sizeof(gf_ba_imu_factor) * (size_t)p->n_imu), o_whl = take(sizeof(gf_ba_wheel_factor) * (size_t)p->n_wheel), o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)),
                  o_cf = take(sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1)), o_pJ = take(sizeof(double) * (size_t)pn * pn), o_pr0 = take(sizeof(double) * pn),
                  o_px0 = take(sizeof(double) * px0_len), o_pcol = take(sizeof(int) * (size_t)(pn > 0 ? pn : 1));
     const size_t upload_bytes = off;
@@ -1063,6 +1119,8 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     if (p->para_speed_bias) memcpy(hX + X_SB, p->para_speed_bias, sizeof(double) * 9 * F);
     memcpy(hX + X_EX, p->para_ex_pose, sizeof(double) * 7);
     hX[X_TD] = p->para_td[0];
+    hX[X_EXW + 6] = 1.0; hX[X_IX] = hX[X_IX + 1] = hX[X_IX + 2] = 1.0;
+    if (p->n_wheel > 0) { memcpy(hX + X_EXW, p->para_ex_wheel, sizeof(double) * 7); memcpy(hX + X_IX, p->para_ix_wheel, sizeof(double) * 3); hX[X_TDW] = p->para_td_wheel[0]; }
     memcpy(hX + X_FEAT, p->para_feature, sizeof(double) * nfeat);
     {   // factors sorted by pair
         gf_ba_visual_factor* hv = (gf_ba_visual_factor*)(hb + o_vis);
@@ -1070,6 +1128,8 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
         for (int v = 0; v < p->n_visual; v++) { int k = pair_id[p->visual[v].imu_i * F + p->visual[v].imu_j]; hv[fill[k]++] = p->visual[v]; }
     }
     if (p->n_imu) memcpy(hb + o_imu, p->imu, sizeof(gf_ba_imu_factor) * (size_t)p->n_imu);
+    if (p->n_wheel) memcpy(hb + o_whl, p->wheel, sizeof(gf_ba_wheel_factor) * (size_t)p->n_wheel);
+    for (int k = 0; k < p->n_wheel; k++) if (p->wheel[k].i < 0 || p->wheel[k].i >= F || p->wheel[k].j < 0 || p->wheel[k].j >= F) return set_err(GF_ERR_INVALID_ARG, "wheel factor index out of range");
     for (int k = 0; k < p->n_imu; k++) if (p->imu[k].i < 0 || p->imu[k].i >= F || p->imu[k].j < 0 || p->imu[k].j >= F) return set_err(GF_ERR_INVALID_ARG, "imu factor index out of range");
     memcpy(hb + o_ps, work_start.data(), sizeof(int) * (n_work + 1));
     if (n_work) memcpy(hb + o_pij, work_ij.data(), sizeof(int) * 2 * n_work);
@@ -1083,6 +1143,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     d.col_feat = (const int*)(db + o_cf); d.X = (double*)(db + o_X); d.Xc = (double*)(db + o_Xc);
     d.vis = (const gf_ba_visual_factor*)(db + o_vis); d.pair_start = (const int*)(db + o_ps); d.pair_ij = (const int*)(db + o_pij);
     d.imu = (const gf_ba_imu_factor*)(db + o_imu); d.imu_sqrt = (double*)(db + o_sq);
+    d.wheel = (const gf_ba_wheel_factor*)(db + o_whl);
     d.pJ = (const double*)(db + o_pJ); d.pr0 = (const double*)(db + o_pr0); d.px0 = (const double*)(db + o_px0); d.pcol = (const int*)(db + o_pcol);
     d.Hp = (double*)(db + o_Hp); d.acc[0] = (double*)(db + o_a0); d.acc[1] = (double*)(db + o_a1);
     double* vec = (double*)(db + o_vec);
@@ -1104,7 +1165,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
         GF_CUDA(cudaMemcpyAsync((char*)d.st + offsetof(BaState, max_iter), &mi, sizeof(int), cudaMemcpyHostToDevice, st));
     }
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
-    const int eval_blocks = n_work + p->n_imu + (pn ? 1 : 0);
+    const int eval_blocks = n_work + p->n_imu + p->n_wheel + (pn ? 1 : 0);
     const size_t prior_smem = sizeof(double) * 2 * (size_t)pn;
     const size_t n4 = (size_t)((nc + 4) / 4);
     const size_t step_smem = sizeof(double) * (std::max((size_t)(nc + 1) * (nc + 2) / 2, 8 * n4 * (n4 + 1)) + 2 + 32 * n4 + 32);
@@ -1130,9 +1191,10 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     if (p->para_speed_bias) memcpy(p->para_speed_bias, hX + X_SB, sizeof(double) * 9 * F);
     memcpy(p->para_ex_pose, hX + X_EX, sizeof(double) * 7);
     p->para_td[0] = hX[X_TD];
+    if (p->n_wheel > 0) { memcpy(p->para_ex_wheel, hX + X_EXW, sizeof(double) * 7); memcpy(p->para_ix_wheel, hX + X_IX, sizeof(double) * 3); p->para_td_wheel[0] = hX[X_TDW]; }
     memcpy(p->para_feature, hX + X_FEAT, sizeof(double) * nfeat);
     sum->iterations = hs->it; sum->num_successful_steps = hs->n_success; sum->termination = hs->termination;
-    sum->reduced_dim = nc; sum->n_free_landmarks = L; sum->n_residuals = pn + 15 * p->n_imu + 2 * p->n_visual;
+    sum->reduced_dim = nc; sum->n_free_landmarks = L; sum->n_residuals = pn + 15 * p->n_imu + 6 * p->n_wheel + 2 * p->n_visual;
     sum->initial_cost = hs->cost_hist[0]; sum->final_cost = hs->x_cost;
     for (int k = 0; k <= GF_BA_MAX_ITERATIONS; k++) { sum->cost[k] = hs->cost_hist[k]; sum->radius[k] = hs->radius_hist[k]; }
     sum->device_ms = ms;

@@ -164,8 +164,56 @@ class Trajectory:
         return a, w
 
 
+def rot_log(R):
+    c = max(-1.0, min(1.0, (np.trace(R) - 1.0) / 2.0))
+    th = math.acos(c)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return 0.5 * w if th < 1e-9 else th / (2.0 * math.sin(th)) * w
+
+
+# body (IMU) <- wheel odometer frame: a small mounting rotation and a lever arm (synthetic; the shipped configs read it from
+# body_T_wheel in the yaml)
+BODY_T_WHEEL = np.eye(4)
+BODY_T_WHEEL[:3, :3] = rot_exp(np.array([0.01, -0.02, 0.03]))
+BODY_T_WHEEL[:3, 3] = [0.08, -0.02, -0.15]
+
+
+def wheel_factors(tr, times, rng, frame_dt, td_true=0.0):
+    """Synthetic WheelIntegrationBase results between consecutive frames: the relative pose of the odometer frame with
+    noise, plausible sensitivities to the scale intrinsics (sx, sy scale the planar velocity, sw the yaw rate), a 6x6
+    covariance, and the boundary wheel speeds / rates the time-offset compensation reads."""
+    Rio, tio = BODY_T_WHEEL[:3, :3], BODY_T_WHEEL[:3, 3]
+    rows = []
+    for f in range(len(times) - 1):
+        ta, tb = times[f], times[f + 1]
+        Ra, Rb = tr.R(ta) @ Rio, tr.R(tb) @ Rio
+        pa, pb_ = tr.p(ta) + tr.R(ta) @ tio, tr.p(tb) + tr.R(tb) @ tio
+        dp = Ra.T @ (pb_ - pa)
+        dR = Ra.T @ Rb
+        dth = rot_log(dR)
+        dp_n = dp + rng.normal(0, 0.004, 3)
+        dq_n = R_to_q(dR @ rot_exp(rng.normal(0, 0.002, 3)))
+        J = np.zeros((6, 3))
+        J[:3, 0] = [dp[0], 0.1 * dp[1], 0.0]
+        J[:3, 1] = [0.1 * dp[0], dp[1], 0.0]
+        J[:3, 2] = 0.5 * np.cross(dth, dp)
+        J[3:, 2] = dth
+        A = rng.normal(0, 1, (6, 6))
+        cov = np.diag([2e-5, 2e-5, 4e-5, 4e-6, 4e-6, 2e-6]) + 1e-7 * (A @ A.T)
+        def wheel_meas(t):
+            Ro = tr.R(t) @ Rio
+            v_o = Ro.T @ (tr.v(t) + tr.R(t) @ np.cross(tr.omega_b(t), tio))
+            w_o = Rio.T @ tr.omega_b(t)
+            return v_o + rng.normal(0, 0.01, 3), w_o + rng.normal(0, 0.002, 3)
+        v0, w0 = wheel_meas(ta); v1, w1 = wheel_meas(tb)
+        rows.append(dict(i=f, j=f + 1, sum_dt=frame_dt, delta_p=dp_n, delta_q=dq_n, jacobian=J, covariance=cov,
+                         linearized_sx=1.0, linearized_sy=1.0, linearized_sw=1.0, linearized_td=0.0,
+                         linearized_vel=v0, linearized_gyr=w0, vel_1=v1, gyr_1=w1))
+    return rows
+
+
 def make_window(seed=0, n_frames=11, n_landmarks=220, frame_dt=0.1, imu_rate=200, t0=2.0, free_fraction=0.3,
-                pix_noise=0.5 / 460.0, pose_noise=(0.03, 0.01), with_prior=False):
+                pix_noise=0.5 / 460.0, pose_noise=(0.03, 0.01), with_prior=False, with_wheel=False, wheel_free=(True, True, True)):
     """One optimisation problem around a true trajectory.  Returns (Problem, truth dict)."""
     rng = np.random.default_rng(seed)
     tr = Trajectory(seed)
@@ -234,5 +282,12 @@ def make_window(seed=0, n_frames=11, n_landmarks=220, frame_dt=0.1, imu_rate=200
         pb.para_speed_bias[f, :3] = Vv[f] + rng.normal(0, 0.05, 3)
         pb.para_speed_bias[f, 3:6] = ba_est; pb.para_speed_bias[f, 6:9] = bg_est
     pb.para_ex_pose[:3] = tic; pb.para_ex_pose[3:] = R_to_q(ric)
+    if with_wheel:
+        pb.set_wheel(wheel_factors(tr, times, rng, frame_dt))
+        pb.para_ex_wheel[:3] = BODY_T_WHEEL[:3, 3] + rng.normal(0, 0.01, 3)
+        pb.para_ex_wheel[3:] = R_to_q(BODY_T_WHEEL[:3, :3] @ rot_exp(rng.normal(0, 0.005, 3)))
+        pb.para_ix_wheel[:] = [1.01, 0.99, 1.005]
+        pb.para_td_wheel[0] = 0.003
+        pb.ex_wheel_const, pb.ix_wheel_const, pb.td_wheel_const = (0 if wheel_free[0] else 1), (0 if wheel_free[1] else 1), (0 if wheel_free[2] else 1)
     truth = dict(P=P, R=Rm, V=Vv, ba=tr.ba, bg=tr.bg, times=times, landmarks=lms)
     return pb, truth

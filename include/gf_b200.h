@@ -240,6 +240,9 @@ typedef struct gf_ba_problem {
     const gf_ba_prior* prior;         /* nullable                                                 */
     double gravity[3];                /* global G (parameters.cpp:74)                             */
     double visual_sqrt_info;          /* FOCAL_LENGTH / 1.5 (estimator.cpp:193)                   */
+    int32_t ex_wheel_subset_mask;     /* PoseSubsetParameterization of para_Ex_Pose_wheel (estimator.cpp:3008-3027):
+                                       * bit k set = local component k (0-2 translation, 3-5 rotation) is zeroed in Plus;
+                                       * 0 = PoseLocalParameterization                              */
 } gf_ba_problem;
 
 typedef enum gf_ba_termination {

@@ -369,18 +369,207 @@ GFO void gfo_eval_imu(const gf_ba_imu_factor* f, const double* sqrt_info, const 
     }
 }
 
+/* ------------------------------------------------------------------ wheel odometry factor ------- */
+/* Sophus (upstream, un-vendored; the reference's CMake finds it as a system package) SO3<double>::exp / log and the
+ * right Jacobians vendored in utility/sophus_utils.hpp:155-236, restated.  epsilon = 1e-10 (Sophus::Constants<double>). */
+#define SOPHUS_EPS 1e-10
+static void so3_exp_q(const v3 w, q4 q)     /* so3.hpp expAndTheta: quaternion (x,y,z,w) */
+{
+    double t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], imag, real;
+    if (t2 < SOPHUS_EPS * SOPHUS_EPS) {
+        double t4 = t2 * t2;
+        imag = 0.5 - (1.0 / 48.0) * t2 + (1.0 / 3840.0) * t4;
+        real = 1.0 - (1.0 / 8.0) * t2 + (1.0 / 384.0) * t4;
+    } else {
+        double t = sqrt(t2), h = 0.5 * t;
+        imag = sin(h) / t; real = cos(h);
+    }
+    q[0] = imag * w[0]; q[1] = imag * w[1]; q[2] = imag * w[2]; q[3] = real;
+}
+static void so3_log_q(const q4 qin, v3 out)  /* so3.hpp logAndTheta on the normalised quaternion */
+{
+    q4 q; memcpy(q, qin, sizeof(q4)); q_normalize(q);
+    double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], w = q[3], f;
+    if (n2 < SOPHUS_EPS * SOPHUS_EPS) {
+        f = 2.0 / w - (2.0 / 3.0) * n2 / (w * w * w);
+    } else {
+        double n = sqrt(n2);
+        if (fabs(w) < SOPHUS_EPS) f = (w > 0 ? M_PI : -M_PI) / n;
+        else f = 2.0 * atan(n / w) / n;
+    }
+    out[0] = f * q[0]; out[1] = f * q[1]; out[2] = f * q[2];
+}
+static void so3_exp_R(const v3 w, m3 R) { q4 q; so3_exp_q(w, q); q_to_R(q, R); }
+static void so3_Jr(const v3 phi, m3 J)       /* sophus_utils.hpp:155-184 */
+{
+    double n2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+    m3 h, h2; skew(phi, h); m3_mul(h, h, h2);
+    double a, b;
+    if (n2 > SOPHUS_EPS) { double n = sqrt(n2); a = (1.0 - cos(n)) / n2; b = (n - sin(n)) / (n2 * n); }
+    else { a = 0.5; b = 1.0 / 6.0; }
+    for (int k = 0; k < 9; k++) J[k] = ((k % 4 == 0) ? 1.0 : 0.0) - a * h[k] + b * h2[k];
+}
+static void so3_Jr_inv(const v3 phi, m3 J)   /* sophus_utils.hpp:195-236 */
+{
+    double n2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+    m3 h, h2; skew(phi, h); m3_mul(h, h, h2);
+    double b;
+    if (n2 > SOPHUS_EPS) {
+        double n = sqrt(n2);
+        if (n < M_PI - 1e-5) b = 1.0 / n2 - (1.0 + cos(n)) / (2.0 * n * sin(n));   /* epsilonSqrt = 1e-5 */
+        else b = 1.0 / (M_PI * M_PI);
+    } else b = 1.0 / 12.0;
+    for (int k = 0; k < 9; k++) J[k] = ((k % 4 == 0) ? 1.0 : 0.0) + 0.5 * h[k] + b * h2[k];
+}
+
+/* WheelFactor::Evaluate (wheel_factor.h:28-247) + WheelIntegrationBase::evaluate (wheel_integration_base.h:179-219).
+ * Residual rows: 0-2 position, 3-5 rotation.  Jacobians row-major in the GLOBAL block sizes (6x7 for poses with a zero
+ * last column, 6x1 for sx, sy, sw, td), already multiplied by sqrt_info = LLT(cov^-1).L^T (recomputed per call as in
+ * the reference).  The formulas -- including exp(forward_compensate_v) in the sx/sy blocks -- are the reference's. */
+GFO int gfo_eval_wheel(const gf_ba_wheel_factor* f, const double* pose_i, const double* pose_j, const double* exw,
+                       double sx, double sy, double sw, double td, double* res,
+                       double* J0, double* J1, double* J2, double* Jsx, double* Jsy, double* Jsw, double* Jtd)
+{
+    const double* Pi = pose_i; const double* Qi = pose_i + 3; const double* Pj = pose_j; const double* Qj = pose_j + 3;
+    const double* tio = exw; const double* qio = exw + 3;
+    v3 dp_dsx, dp_dsy, dp_dsw, dq_dsw;
+    for (int k = 0; k < 3; k++) { dp_dsx[k] = f->jacobian[k * 3 + 0]; dp_dsy[k] = f->jacobian[k * 3 + 1]; dp_dsw[k] = f->jacobian[k * 3 + 2]; dq_dsw[k] = f->jacobian[(3 + k) * 3 + 2]; }
+    const double dsx = sx - f->linearized_sx, dsy = sy - f->linearized_sy, dsw = sw - f->linearized_sw, dtd = td - f->linearized_td;
+    const double sv[3] = {sx, sy, 1.0};
+    m3 Ri, Rj, rio; q_to_R(Qi, Ri); q_to_R(Qj, Rj); q_to_R(qio, rio);
+    v3 cp; for (int k = 0; k < 3; k++) cp[k] = f->delta_p[k] + dp_dsx[k] * dsx + dp_dsy[k] * dsy + dp_dsw[k] * dsw;
+    q4 dq0, e, cq; memcpy(dq0, f->delta_q, sizeof(q4)); q_normalize(dq0);
+    v3 t3; for (int k = 0; k < 3; k++) t3[k] = dq_dsw[k] * dsw;
+    so3_exp_q(t3, e); q_mul(dq0, e, cq); q_normalize(cq);
+    m3 Rcq; q_to_R(cq, Rcq);
+    v3 fcw, fcv, bcv, bcw, nbcw;
+    for (int k = 0; k < 3; k++) { fcw[k] = sw * f->linearized_gyr[k] * dtd; fcv[k] = sv[k] * f->linearized_vel[k] * dtd; bcv[k] = sv[k] * f->vel_1[k] * dtd; bcw[k] = sw * f->gyr_1[k] * dtd; nbcw[k] = -bcw[k]; }
+    q4 E1, E2, qt, dqt; so3_exp_q(fcw, E1); so3_exp_q(nbcw, E2);
+    q_mul(E1, cq, qt); q_mul(qt, E2, dqt); q_normalize(dqt);
+    m3 RE1; q_to_R(E1, RE1);
+    v3 u, inner, dpt; m3_v(Rcq, bcv, u);
+    for (int k = 0; k < 3; k++) inner[k] = fcv[k] + cp[k] - u[k];
+    m3_v(RE1, inner, dpt);
+    /* (Ri rio)^T (Rj tio + Pj - Ri tio - Pi) */
+    m3 Rio, RioT; m3_mul(Ri, rio, Rio); m3_T(Rio, RioT);
+    v3 a1, a2, dw, dpos; m3_v(Rj, tio, a1); m3_v(Ri, tio, a2);
+    for (int k = 0; k < 3; k++) dw[k] = a1[k] + Pj[k] - a2[k] - Pi[k];
+    m3_v(RioT, dw, dpos);
+    double raw[6];
+    for (int k = 0; k < 3; k++) raw[k] = dpos[k] - dpt[k];
+    q4 qiqio, inv1, inv2, qjqio, t1, t2; q_mul(Qi, qio, qiqio); q_inv(qiqio, inv1); q_inv(dqt, inv2); q_mul(Qj, qio, qjqio);
+    q_mul(inv2, inv1, t1); q_mul(t1, qjqio, t2);
+    v3 rq; so3_log_q(t2, rq);
+    for (int k = 0; k < 3; k++) raw[3 + k] = rq[k];
+    double U[36];
+    if (gfo_sqrt_info(f->covariance, 6, U)) return -1;
+    for (int i = 0; i < 6; i++) { double v = 0; for (int k = 0; k < 6; k++) v += U[i * 6 + k] * raw[k]; res[i] = v; }
+    if (!J0 && !J1 && !J2 && !Jsx && !Jsy && !Jsw && !Jtd) return 0;
+    m3 Jri; so3_Jr_inv(rq, Jri);
+    v3 drdsw; for (int k = 0; k < 3; k++) drdsw[k] = dq_dsw[k] * dsw;
+    m3 Jr_drdsw; so3_Jr(drdsw, Jr_drdsw);
+    m3 S, A, B, C, RiT, rioT; m3_T(Ri, RiT); m3_T(rio, rioT);
+    if (J0) {
+        memset(J0, 0, sizeof(double) * 42);
+        set_blk(J0, 7, 0, 0, RioT, -1.0);
+        skew(tio, S); m3_mul(Ri, S, A); m3_mul(RioT, A, B);                 /* (Ri rio)^T (Ri [tio]x) */
+        v3 w1; m3_v(RiT, dw, w1); skew(w1, S); m3_mul(rioT, S, C);          /* rio^T [Ri^T dw]x */
+        for (int k = 0; k < 9; k++) B[k] += C[k];
+        set_blk(J0, 7, 0, 3, B, 1.0);
+        q4 qa, qb; q_inv(qjqio, qa); q_mul(qa, Qi, qb); q_to_R(qb, A); m3_mul(Jri, A, B);
+        set_blk(J0, 7, 3, 3, B, -1.0);
+        left_mul_sqrt(U, 6, J0, 7);
+    }
+    if (J1) {
+        memset(J1, 0, sizeof(double) * 42);
+        set_blk(J1, 7, 0, 0, RioT, 1.0);
+        skew(tio, S); m3_mul(RioT, Rj, A); m3_mul(A, S, B);
+        set_blk(J1, 7, 0, 3, B, -1.0);
+        m3_mul(Jri, rioT, B);
+        set_blk(J1, 7, 3, 3, B, 1.0);
+        left_mul_sqrt(U, 6, J1, 7);
+    }
+    if (J2) {
+        memset(J2, 0, sizeof(double) * 42);
+        for (int k = 0; k < 9; k++) A[k] = Rj[k] - Ri[k];
+        m3_mul(RioT, A, B);
+        set_blk(J2, 7, 0, 0, B, 1.0);
+        skew(dpos, S);
+        set_blk(J2, 7, 0, 3, S, 1.0);
+        q4 qa, qb, qc; q_inv(qjqio, qa); q_mul(qa, Qi, qb); q_mul(qb, qio, qc); q_to_R(qc, A);
+        for (int k = 0; k < 9; k++) A[k] = ((k % 4 == 0) ? 1.0 : 0.0) - A[k];
+        m3_mul(Jri, A, B);
+        set_blk(J2, 7, 3, 3, B, 1.0);
+        left_mul_sqrt(U, 6, J2, 7);
+    }
+    m3 Jrtd, Jrmtd, Rfcv, Rfcw, Rnr, Rbcw, RcqT;
+    v3 nfcw, nrq; for (int k = 0; k < 3; k++) { nfcw[k] = -fcw[k]; nrq[k] = -rq[k]; }
+    so3_Jr(fcw, Jrtd); so3_Jr(nfcw, Jrmtd);
+    so3_exp_R(fcv, Rfcv); so3_exp_R(fcw, Rfcw); so3_exp_R(nrq, Rnr); so3_exp_R(bcw, Rbcw); m3_T(Rcq, RcqT);
+    for (int axis = 0; axis < 2; axis++) {
+        double* Jo = axis == 0 ? Jsx : Jsy;
+        if (!Jo) continue;
+        const double* dpds = axis == 0 ? dp_dsx : dp_dsy;
+        v3 e1 = {0, 0, 0}, e2 = {0, 0, 0}, w1, w2, w3;
+        e1[axis] = f->linearized_vel[axis] * dtd;            /* I_axis * linearized_vel * dtd */
+        e2[axis] = f->vel_1[axis] * dtd;                     /* I_axis * vel_1 * dtd */
+        m3_v(Rcq, e2, w1);
+        for (int k = 0; k < 3; k++) w2[k] = e1[k] + dpds[k] - w1[k];
+        m3_v(Rfcv, w2, w3);
+        for (int k = 0; k < 3; k++) { Jo[k] = -w3[k]; Jo[3 + k] = 0.0; }
+        left_mul_sqrt(U, 6, Jo, 1);
+    }
+    v3 common;   /* forward_compensate_v + corrected_delta_p - corrected_delta_q * back_compensate_v */
+    for (int k = 0; k < 3; k++) common[k] = inner[k];
+    if (Jsw) {
+        v3 w1, w2, w3, w4, w5, lg;
+        m3_v(Jr_drdsw, dq_dsw, w1); skew(w1, S);
+        v3 svv1; for (int k = 0; k < 3; k++) svv1[k] = sv[k] * f->vel_1[k] * dtd;
+        m3_v(S, svv1, w2); m3_v(Rcq, w2, w3);                                /* Rcq [Jr dq_dsw]x sv vel_1 dtd */
+        for (int k = 0; k < 3; k++) lg[k] = f->linearized_gyr[k] * dtd;
+        m3_v(Jrtd, lg, w4); skew(w4, S); m3_v(S, common, w5);                /* [Jrtd gyr dtd]x common */
+        v3 tot; for (int k = 0; k < 3; k++) tot[k] = dp_dsw[k] - w3[k] + w5[k];
+        v3 outp; m3_v(Rfcw, tot, outp);
+        v3 r1, r2, r3, r4, r5;
+        m3_v(RcqT, w4, r1);                                                   /* Rcq^T Jrtd gyr dtd */
+        for (int k = 0; k < 3; k++) r2[k] = r1[k] + w1[k];
+        m3_v(Rbcw, r2, r3); m3_v(Rnr, r3, r4); m3_v(Jri, r4, r5);
+        for (int k = 0; k < 3; k++) { Jsw[k] = -outp[k]; Jsw[3 + k] = -r5[k]; }
+        left_mul_sqrt(U, 6, Jsw, 1);
+    }
+    if (Jtd) {
+        v3 w1, w2, w3, w4, w5, svl, svv, swg;
+        for (int k = 0; k < 3; k++) { svl[k] = sv[k] * f->linearized_vel[k]; svv[k] = sv[k] * f->vel_1[k]; swg[k] = sw * f->linearized_gyr[k]; }
+        m3_v(Rcq, svv, w1);
+        m3_v(Jrtd, swg, w2); skew(w2, S); m3_v(S, common, w3);
+        for (int k = 0; k < 3; k++) w4[k] = svl[k] - w1[k] + w3[k];
+        m3_v(Rfcw, w4, w5);
+        v3 r1, r2, r3, r4, r5, swg1;
+        for (int k = 0; k < 3; k++) swg1[k] = sw * f->gyr_1[k];
+        m3_v(RcqT, w2, r1); m3_v(Rbcw, r1, r2);
+        m3_v(Jrmtd, swg1, r3);
+        for (int k = 0; k < 3; k++) r4[k] = r2[k] - r3[k];
+        m3_v(Rnr, r4, r5); v3 r6; m3_v(Jri, r5, r6);
+        for (int k = 0; k < 3; k++) { Jtd[k] = -w5[k]; Jtd[3 + k] = -r6[k]; }
+        left_mul_sqrt(U, 6, Jtd, 1);
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ program layout -------------- */
 typedef struct {
     int F, nfeat;
     int col_pose[GF_BA_MAX_FRAMES], col_sb[GF_BA_MAX_FRAMES], col_ex, col_td;
+    int col_exw, col_ix[3], col_tdw;   /* wheel extrinsic, sx sy sw, wheel time offset (only with wheel factors) */
     int* col_feat;   /* -1: constant or unused */
     int n_cam, n_lm, n_cols;
-    int row_prior, row_imu, row_vis, n_rows;
+    int row_prior, row_imu, row_wheel, row_vis, n_rows;
     int use_sb;
 } layout_t;
 
 typedef struct {
     double pose[GF_BA_MAX_FRAMES][7], sb[GF_BA_MAX_FRAMES][9], ex[7], td;
+    double exw[7], ix[3], tdw;
     double* feat;
 } state_t;
 
@@ -390,6 +579,8 @@ static void state_load(const gf_ba_problem* p, state_t* s)
     if (p->para_speed_bias) memcpy(s->sb, p->para_speed_bias, sizeof(double) * 9 * p->n_frames);
     memcpy(s->ex, p->para_ex_pose, sizeof(double) * 7);
     s->td = p->para_td[0];
+    memset(s->exw, 0, sizeof(s->exw)); s->exw[6] = 1.0; s->ix[0] = s->ix[1] = s->ix[2] = 1.0; s->tdw = 0.0;
+    if (p->n_wheel > 0) { memcpy(s->exw, p->para_ex_wheel, sizeof(double) * 7); memcpy(s->ix, p->para_ix_wheel, sizeof(double) * 3); s->tdw = p->para_td_wheel[0]; }
     s->feat = (double*)malloc(sizeof(double) * (p->n_features > 0 ? p->n_features : 1));
     memcpy(s->feat, p->para_feature, sizeof(double) * p->n_features);
 }
@@ -406,6 +597,7 @@ static void state_store(const gf_ba_problem* p, const state_t* s)
     if (p->para_speed_bias) memcpy(p->para_speed_bias, s->sb, sizeof(double) * 9 * p->n_frames);
     memcpy(p->para_ex_pose, s->ex, sizeof(double) * 7);
     p->para_td[0] = s->td;
+    if (p->n_wheel > 0) { memcpy(p->para_ex_wheel, s->exw, sizeof(double) * 7); memcpy(p->para_ix_wheel, s->ix, sizeof(double) * 3); p->para_td_wheel[0] = s->tdw; }
     memcpy(p->para_feature, s->feat, sizeof(double) * p->n_features);
 }
 
@@ -424,6 +616,12 @@ static void make_layout(const gf_ba_problem* p, layout_t* L)
     }
     L->col_ex = p->ex_pose_const ? -1 : c; if (!p->ex_pose_const) c += 6;
     L->col_td = p->td_const ? -1 : c; if (!p->td_const) c += 1;
+    L->col_exw = -1; L->col_ix[0] = L->col_ix[1] = L->col_ix[2] = -1; L->col_tdw = -1;
+    if (p->n_wheel > 0) {      /* estimator.cpp:3008-3056: the wheel blocks only exist with USE_WHEEL */
+        if (!p->ex_wheel_const) { L->col_exw = c; c += 6; }
+        if (!p->ix_wheel_const) for (int k = 0; k < 3; k++) L->col_ix[k] = c++;
+        if (!p->td_wheel_const) L->col_tdw = c++;
+    }
     L->n_cam = c;
     L->col_feat = (int*)malloc(sizeof(int) * (L->nfeat > 0 ? L->nfeat : 1));
     for (int k = 0; k < L->nfeat; k++) L->col_feat[k] = -1;
@@ -436,6 +634,7 @@ static void make_layout(const gf_ba_problem* p, layout_t* L)
     int r = 0;
     L->row_prior = r; r += (p->prior ? p->prior->n : 0);
     L->row_imu = r; r += 15 * p->n_imu;
+    L->row_wheel = r; r += 6 * p->n_wheel;
     L->row_vis = r; r += 2 * p->n_visual;
     L->n_rows = r;
 }
@@ -447,6 +646,11 @@ static const double* prior_block_ptr(const state_t* s, int kind, int index)
     case GF_BA_BLOCK_SPEEDBIAS: return s->sb[index];
     case GF_BA_BLOCK_EX_POSE: return s->ex;
     case GF_BA_BLOCK_TD: return &s->td;
+    case GF_BA_BLOCK_EX_WHEEL: return s->exw;
+    case GF_BA_BLOCK_SX: return &s->ix[0];
+    case GF_BA_BLOCK_SY: return &s->ix[1];
+    case GF_BA_BLOCK_SW: return &s->ix[2];
+    case GF_BA_BLOCK_TD_WHEEL: return &s->tdw;
     default: return NULL;
     }
 }
@@ -465,6 +669,11 @@ static int block_col(const layout_t* L, int kind, int index)
     case GF_BA_BLOCK_SPEEDBIAS: return L->col_sb[index];
     case GF_BA_BLOCK_EX_POSE: return L->col_ex;
     case GF_BA_BLOCK_TD: return L->col_td;
+    case GF_BA_BLOCK_EX_WHEEL: return L->col_exw;
+    case GF_BA_BLOCK_SX: return L->col_ix[0];
+    case GF_BA_BLOCK_SY: return L->col_ix[1];
+    case GF_BA_BLOCK_SW: return L->col_ix[2];
+    case GF_BA_BLOCK_TD_WHEEL: return L->col_tdw;
     default: return -1;
     }
 }
@@ -528,6 +737,25 @@ static double evaluate(const gf_ba_problem* p, const layout_t* L, const state_t*
                 if (c1 >= 0) for (int k = 0; k < 9; k++) J[(size_t)(row + i) * nc + c1 + k] = J1[i * 9 + k];
                 if (c2 >= 0) for (int k = 0; k < 6; k++) J[(size_t)(row + i) * nc + c2 + k] = J2[i * 7 + k];
                 if (c3 >= 0) for (int k = 0; k < 9; k++) J[(size_t)(row + i) * nc + c3 + k] = J3[i * 9 + k];
+            }
+        }
+    }
+    for (int m = 0; m < p->n_wheel; m++) {
+        const gf_ba_wheel_factor* f = &p->wheel[m];
+        double res[6], J0[42], J1[42], J2[42], Jsx[6], Jsy[6], Jsw[6], Jtw[6];
+        gfo_eval_wheel(f, s->pose[f->i], s->pose[f->j], s->exw, s->ix[0], s->ix[1], s->ix[2], s->tdw, res,
+                       J ? J0 : NULL, J ? J1 : NULL, J ? J2 : NULL, J ? Jsx : NULL, J ? Jsy : NULL, J ? Jsw : NULL, J ? Jtw : NULL);
+        int row = L->row_wheel + 6 * m;
+        for (int i = 0; i < 6; i++) { r[row + i] = res[i]; cost += 0.5 * res[i] * res[i]; }
+        if (J) {
+            int c0 = L->col_pose[f->i], c1 = L->col_pose[f->j];
+            for (int i = 0; i < 6; i++) {
+                double* Jr = J + (size_t)(row + i) * nc;
+                if (c0 >= 0) for (int k = 0; k < 6; k++) Jr[c0 + k] = J0[i * 7 + k];
+                if (c1 >= 0) for (int k = 0; k < 6; k++) Jr[c1 + k] = J1[i * 7 + k];
+                if (L->col_exw >= 0) for (int k = 0; k < 6; k++) Jr[L->col_exw + k] = J2[i * 7 + k];
+                if (L->col_ix[0] >= 0) { Jr[L->col_ix[0]] = Jsx[i]; Jr[L->col_ix[1]] = Jsy[i]; Jr[L->col_ix[2]] = Jsw[i]; }
+                if (L->col_tdw >= 0) Jr[L->col_tdw] = Jtw[i];
             }
         }
     }
@@ -607,6 +835,16 @@ static double linearize_blocks(const gf_ba_problem* p, const layout_t* L, const 
         double* Js[4] = {J0, J1, J2, J3};
         add_blocks(H, g, n, 15, res, 4, cols, sizes, lds, Js);
     }
+    for (int m = 0; m < p->n_wheel; m++) {
+        const gf_ba_wheel_factor* f = &p->wheel[m];
+        double res[6], J0[42], J1[42], J2[42], Jsx[6], Jsy[6], Jsw[6], Jtw[6];
+        gfo_eval_wheel(f, s->pose[f->i], s->pose[f->j], s->exw, s->ix[0], s->ix[1], s->ix[2], s->tdw, res, J0, J1, J2, Jsx, Jsy, Jsw, Jtw);
+        for (int i = 0; i < 6; i++) cost += 0.5 * res[i] * res[i];
+        int cols[7] = {L->col_pose[f->i], L->col_pose[f->j], L->col_exw, L->col_ix[0], L->col_ix[1], L->col_ix[2], L->col_tdw};
+        int sizes[7] = {6, 6, 6, 1, 1, 1, 1}, lds[7] = {7, 7, 7, 1, 1, 1, 1};
+        double* Js[7] = {J0, J1, J2, Jsx, Jsy, Jsw, Jtw};
+        add_blocks(H, g, n, 6, res, 7, cols, sizes, lds, Js);
+    }
     for (int v = 0; v < p->n_visual; v++) {
         const gf_ba_visual_factor* f = &p->visual[v];
         double res[2], Ji[14], Jj[14], Jex[14], Jf[2], Jtd[2];
@@ -642,6 +880,12 @@ static double cost_only(const gf_ba_problem* p, const layout_t* L, const state_t
         gfo_eval_imu(f, imu_sqrt_info + 225 * m, p->gravity, s->pose[f->i], s->sb[f->i], s->pose[f->j], s->sb[f->j], res, NULL, NULL, NULL, NULL);
         for (int i = 0; i < 15; i++) cost += 0.5 * res[i] * res[i];
     }
+    for (int m = 0; m < p->n_wheel; m++) {
+        const gf_ba_wheel_factor* f = &p->wheel[m];
+        double res[6];
+        gfo_eval_wheel(f, s->pose[f->i], s->pose[f->j], s->exw, s->ix[0], s->ix[1], s->ix[2], s->tdw, res, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+        for (int i = 0; i < 6; i++) cost += 0.5 * res[i] * res[i];
+    }
     for (int v = 0; v < p->n_visual; v++) {
         const gf_ba_visual_factor* f = &p->visual[v];
         double res[2];
@@ -668,6 +912,14 @@ static void state_plus(const gf_ba_problem* p, const layout_t* L, const state_t*
     }
     if (L->col_ex >= 0) pose_plus(x->ex, delta + L->col_ex, out->ex);
     if (L->col_td >= 0) out->td = x->td + delta[L->col_td];
+    if (L->col_exw >= 0) {   /* PoseLocalParameterization, or PoseSubsetParameterization (pose_subset_parameterization.cpp:29-33):
+                              * the masked components are zeroed inside Plus only, the Jacobian keeps its columns */
+        double dd[6];
+        for (int k = 0; k < 6; k++) dd[k] = ((p->ex_wheel_subset_mask >> k) & 1) ? 0.0 : delta[L->col_exw + k];
+        pose_plus(x->exw, dd, out->exw);
+    }
+    for (int k = 0; k < 3; k++) if (L->col_ix[k] >= 0) out->ix[k] = x->ix[k] + delta[L->col_ix[k]];
+    if (L->col_tdw >= 0) out->tdw = x->tdw + delta[L->col_tdw];
     for (int k = 0; k < L->nfeat; k++) if (L->col_feat[k] >= 0) out->feat[k] = x->feat[k] + delta[L->col_feat[k]];
 }
 /* ambient-space difference norms over the non-constant blocks (x_norm, step_norm, gradient_max_norm) */
@@ -681,6 +933,9 @@ static void state_diff_norms(const layout_t* L, const state_t* a, const state_t*
     }
     if (L->col_ex >= 0) for (int k = 0; k < 7; k++) ACC(a->ex[k] - (b ? b->ex[k] : 0));
     if (L->col_td >= 0) ACC(a->td - (b ? b->td : 0));
+    if (L->col_exw >= 0) for (int k = 0; k < 7; k++) ACC(a->exw[k] - (b ? b->exw[k] : 0));
+    for (int k = 0; k < 3; k++) if (L->col_ix[k] >= 0) ACC(a->ix[k] - (b ? b->ix[k] : 0));
+    if (L->col_tdw >= 0) ACC(a->tdw - (b ? b->tdw : 0));
     for (int k = 0; k < L->nfeat; k++) if (L->col_feat[k] >= 0) ACC(a->feat[k] - (b ? b->feat[k] : 0));
 #undef ACC
     if (l2) *l2 = sqrt(s2);

@@ -5,7 +5,7 @@ import subprocess
 
 import numpy as np
 
-from ground_fusion_b200._lib import BaImuFactor, BaPrior, BaProblem, BaSummary, BaVisualFactor
+from ground_fusion_b200._lib import BaImuFactor, BaPrior, BaProblem, BaSummary, BaVisualFactor, BaWheelFactor
 from ground_fusion_b200.ba_problem import Prior
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -33,6 +33,7 @@ def lib():
         L.gfo_ba_set_tolerances.argtypes = [ctypes.c_double] * 3
         L.gfo_ba_set_tolerances.restype = None
         L.gfo_sqrt_info.argtypes = [_dp, ctypes.c_int, _dp]
+        L.gfo_eval_wheel.argtypes = [ctypes.POINTER(BaWheelFactor), _dp, _dp, _dp] + [ctypes.c_double] * 4 + [_dp] * 8
         _LIB = L
     return _LIB
 
@@ -85,3 +86,16 @@ def marginalize_old(pb):
 
 def set_tolerances(function=1e-6, gradient=1e-10, parameter=1e-8):
     lib().gfo_ba_set_tolerances(function, gradient, parameter)
+
+
+def eval_wheel(f, pose_i, pose_j, exw, sx, sy, sw, td, jac=True):
+    """WheelFactor::Evaluate restatement: returns (res[6], [J_pose_i 6x7, J_pose_j 6x7, J_ex 6x7, J_sx, J_sy, J_sw, J_td (6,)])."""
+    a = [np.ascontiguousarray(v, np.float64) for v in (pose_i, pose_j, exw)]
+    res = np.zeros(6)
+    Js = [np.zeros((6, 7)), np.zeros((6, 7)), np.zeros((6, 7)), np.zeros(6), np.zeros(6), np.zeros(6), np.zeros(6)]
+    ptrs = [j.ctypes.data_as(_dp) if jac else None for j in Js]
+    rc = lib().gfo_eval_wheel(ctypes.byref(f), a[0].ctypes.data_as(_dp), a[1].ctypes.data_as(_dp), a[2].ctypes.data_as(_dp),
+                              float(sx), float(sy), float(sw), float(td), res.ctypes.data_as(_dp), *ptrs)
+    if rc:
+        raise RuntimeError("wheel covariance not positive definite")
+    return res, Js

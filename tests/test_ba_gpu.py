@@ -25,7 +25,7 @@ def rot_err(qa, qb):
     return 2 * np.arccos(np.clip(d, -1, 1))
 
 
-def compare(ba, pb, max_iter):
+def compare(ba, pb, max_iter, mid_rtol=1e-7, final_rtol=1e-9):
     a = pb.clone(); a.max_num_iterations = max_iter
     b = pb.clone(); b.max_num_iterations = max_iter
     so = O.solve(a)
@@ -36,15 +36,17 @@ def compare(ba, pb, max_iter):
     assert sg["reduced_dim"] == so["reduced_dim"] and sg["n_free_landmarks"] == so["n_free_landmarks"]
     # intermediate iterates of the steep phase (cost falling by 1e3 per step) amplify 1e-13 differences of the step
     # (atomic summation order, Schur vs dense elimination); the end points must agree to 1e-9
-    assert np.allclose(sg["cost"], so["cost"], rtol=1e-7, atol=0), (sg["cost"], so["cost"])
+    assert np.allclose(sg["cost"], so["cost"], rtol=mid_rtol, atol=0), (sg["cost"], so["cost"])
     assert np.isclose(sg["initial_cost"], so["initial_cost"], rtol=1e-12)
-    assert np.isclose(sg["final_cost"], so["final_cost"], rtol=1e-9), (sg["final_cost"], so["final_cost"])
+    assert np.isclose(sg["final_cost"], so["final_cost"], rtol=final_rtol), (sg["final_cost"], so["final_cost"])
     assert np.allclose(sg["radius"], so["radius"], rtol=1e-6)
     assert np.abs(a.para_pose[:, :3] - b.para_pose[:, :3]).max() < 1e-6
     assert rot_err(a.para_pose[:, 3:], b.para_pose[:, 3:]).max() < 1e-6
     assert np.abs(a.para_speed_bias - b.para_speed_bias).max() < 1e-6
     assert np.abs(a.para_feature - b.para_feature).max() < 1e-6
     assert np.abs(a.para_ex_pose - b.para_ex_pose).max() < 1e-6
+    assert np.abs(a.para_ex_wheel - b.para_ex_wheel).max() < 1e-6 and np.abs(a.para_ix_wheel - b.para_ix_wheel).max() < 1e-6
+    assert np.abs(a.para_td_wheel - b.para_td_wheel).max() < 1e-6
     return sg
 
 
@@ -61,6 +63,24 @@ def test_solve_with_free_extrinsic_and_td(ba):
     pb.ex_pose_const = 0; pb.td_const = 0
     s = compare(ba, pb, 8)
     assert s["reduced_dim"] == 172
+
+
+@pytest.mark.parametrize("wheel_free,mask", [((True, True, True), 0), ((False, False, False), 0), ((True, False, True), 0),
+                                             ((True, True, False), 0b100100)])
+def test_solve_with_wheel_factors(ba, wheel_free, mask):
+    """C3: WheelFactor between consecutive frames (reference wheel_factor.h), wheel extrinsic / scale intrinsics / time
+    offset free or constant, PoseSubsetParameterization (ADJUST_WHEEL_NO_Z-like mask) on the extrinsic."""
+    pb, _ = make_window(seed=7, with_wheel=True, wheel_free=wheel_free)
+    pb.ex_wheel_subset_mask = mask
+    for it in (1, 8):
+        # the first steps take the cost down by 6 decades (tight wheel covariance): iterate 2 amplifies 1e-13 step
+        # differences to 1e-7 relative, the end point agrees to 1e-9 like everywhere else
+        # with a subset mask the masked directions keep their Jacobian columns but Plus ignores them (reference quirk,
+        # SURVEY BA-3): every step is partly wasted, the run is still far from converged after 8 iterations and the
+        # iterates are more sensitive to summation order; poses still agree to 1e-6
+        s = compare(ba, pb, it, mid_rtol=1e-6, final_rtol=1e-9 if mask == 0 else 1e-7)
+        assert s["reduced_dim"] == 165 + 6 * wheel_free[0] + 3 * wheel_free[1] + wheel_free[2]
+        assert s["n_residuals"] == 150 + 60 + 2 * pb.n_visual
 
 
 def test_solve_with_marginalization_prior(ba):

@@ -37,6 +37,67 @@ def test_imu_and_visual_jacobians_match_finite_differences():
                 assert np.abs(g[sl] - J[sl, c]).max() <= 1e-6 * scale + 1e-7, c
 
 
+def test_wheel_factor_jacobians_match_finite_differences_where_the_reference_is_exact():
+    """WheelFactor (reference factor/wheel_factor.h:28-247).  With td == linearized_td every analytic block of the
+    reference is the exact derivative, so the restatement is pinned by central differences there; with a time offset
+    the pose / extrinsic blocks stay exact while the reference's sx, sy, sw, td blocks are approximations (e.g. the
+    sx/sy blocks rotate by exp(forward_compensate_v)), which the restatement reproduces as written."""
+    from ground_fusion_b200.synth_ba import q_mul
+    pb, _ = make_window(seed=3, with_wheel=True)
+    f = pb.wheel[2]
+    pi, pj, exw = pb.para_pose[f.i].copy(), pb.para_pose[f.j].copy(), pb.para_ex_wheel.copy()
+    sx, sy, sw = pb.para_ix_wheel
+
+    def plus(x, d):
+        y = x.copy(); y[:3] += d[:3]
+        dq = np.array([d[3] / 2, d[4] / 2, d[5] / 2, 1.0]); dq /= np.linalg.norm(dq)
+        y[3:] = q_mul(x[3:], dq); y[3:] /= np.linalg.norm(y[3:])
+        return y
+
+    h = 1e-6
+    for td, scalar_blocks_exact in ((0.0, True), (0.004, False)):
+        res, Js = O.eval_wheel(f, pi, pj, exw, sx, sy, sw, td)
+        assert np.all(np.isfinite(res))
+        for which in range(3):
+            J = np.zeros((6, 6))
+            for k in range(6):
+                d = np.zeros(6); d[k] = h
+                a = [pi, pj, exw]; a[which] = plus(a[which], d)
+                rp, _ = O.eval_wheel(f, a[0], a[1], a[2], sx, sy, sw, td, jac=False)
+                a = [pi, pj, exw]; a[which] = plus(a[which], -d)
+                rm, _ = O.eval_wheel(f, a[0], a[1], a[2], sx, sy, sw, td, jac=False)
+                J[:, k] = (rp - rm) / (2 * h)
+            assert np.abs(J - Js[which][:, :6]).max() < 1e-6 * max(1.0, np.abs(J).max()), which
+            assert np.all(Js[which][:, 6] == 0)
+        for idx in range(4):
+            v = [sx, sy, sw, td]
+            vp = list(v); vp[idx] += h
+            vm = list(v); vm[idx] -= h
+            rp, _ = O.eval_wheel(f, pi, pj, exw, *vp, jac=False)
+            rm, _ = O.eval_wheel(f, pi, pj, exw, *vm, jac=False)
+            err = np.abs((rp - rm) / (2 * h) - Js[3 + idx]).max()
+            if scalar_blocks_exact:
+                assert err < 1e-6, (idx, err)
+            else:
+                assert err < 1.0      # documented approximation of the reference, not a derivative test
+
+
+def test_solve_with_wheel_factors_converges_and_moves_the_wheel_blocks():
+    pb, _ = make_window(seed=5, with_wheel=True)
+    x0 = (pb.para_ex_wheel.copy(), pb.para_ix_wheel.copy(), pb.para_td_wheel.copy())
+    c0 = O.cost(pb)
+    s = O.solve(pb)
+    assert s["final_cost"] < 0.2 * c0 and s["reduced_dim"] == 165 + 6 + 3 + 1
+    assert not np.allclose(pb.para_ex_wheel, x0[0]) and not np.allclose(pb.para_ix_wheel, x0[1]) and pb.para_td_wheel[0] != x0[2][0]
+    assert abs(np.linalg.norm(pb.para_ex_wheel[3:]) - 1.0) < 1e-12
+    # constant wheel blocks stay put
+    pb2, _ = make_window(seed=5, with_wheel=True, wheel_free=(False, False, False))
+    y0 = (pb2.para_ex_wheel.copy(), pb2.para_ix_wheel.copy(), pb2.para_td_wheel.copy())
+    s2 = O.solve(pb2)
+    assert s2["reduced_dim"] == 165
+    assert np.array_equal(pb2.para_ex_wheel, y0[0]) and np.array_equal(pb2.para_ix_wheel, y0[1]) and pb2.para_td_wheel[0] == y0[2][0]
+
+
 def test_huber_corrector_scales_residual_and_jacobian():
     pb, _ = make_window(seed=2, n_landmarks=40)
     r_a, J_a = O.linearize(pb)
