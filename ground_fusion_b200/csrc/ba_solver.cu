@@ -1202,6 +1202,55 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     return GF_OK;
 }
 
+/* Estimator::double2vector (reference estimator.cpp:2440-2494): after the solve the whole window is rotated about z and
+ * shifted so that frame 0 keeps the yaw and the position it had before (the 4 unobservable DoF of a VIO window), with the
+ * reference's Euler-singularity branch.  Pure host code: Utility::R2ypr / ypr2R (utility/utility.h:78-120) restated. */
+static void gf_q_to_R(const double* q, double* R)     /* q = x y z w, normalised first as Quaterniond::normalized() */
+{
+    double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double x = q[0] / n, y = q[1] / n, z = q[2] / n, w = q[3] / n;
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = 1 - 2 * (x * x + y * y);
+}
+static void gf_R2ypr(const double* R, double* ypr)
+{
+    const double n0 = R[0], n1 = R[3], n2 = R[6], o0 = R[1], o1 = R[4], a0 = R[2], a1 = R[5];
+    const double y = atan2(n1, n0);
+    const double p = atan2(-n2, n0 * cos(y) + n1 * sin(y));
+    const double r = atan2(a0 * sin(y) - a1 * cos(y), -o0 * sin(y) + o1 * cos(y));
+    ypr[0] = y / M_PI * 180.0; ypr[1] = p / M_PI * 180.0; ypr[2] = r / M_PI * 180.0;
+}
+int gf_ba_double2vector(const gf_ba_problem* p, const double* R0_before, const double* P0_before, int use_imu,
+                        double* Rs, double* Ps, double* Vs)
+{
+    if (!p || !p->para_pose || !Rs || !Ps || (use_imu && (!R0_before || !P0_before))) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    const int F = p->n_frames;
+    if (F < 1 || F > GF_BA_MAX_FRAMES) return set_err(GF_ERR_INVALID_ARG, "n_frames out of range");
+    double rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (use_imu) {
+        double R00[9], y0[3], y00[3];
+        gf_q_to_R(p->para_pose + 3, R00);
+        // the reference builds R00 with toRotationMatrix() of the un-normalised quaternion; Ceres keeps it unit-norm
+        gf_R2ypr(R0_before, y0); gf_R2ypr(R00, y00);
+        const double yd = (y0[0] - y00[0]) / 180.0 * M_PI;
+        rot[0] = cos(yd); rot[1] = -sin(yd); rot[3] = sin(yd); rot[4] = cos(yd);          // ypr2R(y_diff, 0, 0)
+        if (fabs(fabs(y0[1]) - 90) < 1.0 || fabs(fabs(y00[1]) - 90) < 1.0)                 // euler singular point
+            for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { double v = 0; for (int k = 0; k < 3; k++) v += R0_before[r * 3 + k] * R00[c * 3 + k]; rot[r * 3 + c] = v; }
+    }
+    for (int i = 0; i < F; i++) {
+        double Ri[9];
+        gf_q_to_R(p->para_pose + 7 * i + 3, Ri);
+        for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { double v = 0; for (int k = 0; k < 3; k++) v += rot[r * 3 + k] * Ri[k * 3 + c]; Rs[9 * i + r * 3 + c] = v; }
+        double dpos[3];
+        for (int k = 0; k < 3; k++) dpos[k] = use_imu ? p->para_pose[7 * i + k] - p->para_pose[k] : p->para_pose[7 * i + k];
+        for (int r = 0; r < 3; r++) Ps[3 * i + r] = rot[r * 3] * dpos[0] + rot[r * 3 + 1] * dpos[1] + rot[r * 3 + 2] * dpos[2] + (use_imu ? P0_before[r] : 0.0);
+        if (Vs && use_imu && p->para_speed_bias)
+            for (int r = 0; r < 3; r++) Vs[3 * i + r] = rot[r * 3] * p->para_speed_bias[9 * i] + rot[r * 3 + 1] * p->para_speed_bias[9 * i + 1] + rot[r * 3 + 2] * p->para_speed_bias[9 * i + 2];
+    }
+    return GF_OK;
+}
+
 /* debug: clock64() cycles per phase of k_ba_step of the last solve (see PH() markers) */
 int gf_ba_debug_profile(gf_ba* s, long long* out32)
 {

@@ -3,8 +3,25 @@ over the C ABI (gf_ba_*): the ceres::Solve it performs runs on the GPU; there is
 """
 import ctypes
 
+import numpy as np
+
 from . import _lib
 from ._lib import BaProblem, BaSummary, check
+
+
+def double2vector(problem, R0_before, P0_before, use_imu=True):
+    """Estimator::double2vector (estimator.cpp:2440-2494): Rs [F,3,3], Ps [F,3], Vs [F,3] from the solved para_* arrays,
+    with frame 0's yaw and position restored to their values before the solve.  Host-only (no GPU needed)."""
+    L = _lib.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.gf_ba_double2vector.argtypes = [ctypes.POINTER(BaProblem), dp, dp, ctypes.c_int, dp, dp, dp]
+    F = problem.n_frames
+    R0 = np.ascontiguousarray(R0_before, np.float64).reshape(3, 3); P0 = np.ascontiguousarray(P0_before, np.float64).reshape(3)
+    Rs, Ps, Vs = np.zeros((F, 3, 3)), np.zeros((F, 3)), np.zeros((F, 3))
+    p = problem.struct()
+    check(L.gf_ba_double2vector(ctypes.byref(p), R0.ctypes.data_as(dp), P0.ctypes.data_as(dp), 1 if use_imu else 0,
+                                Rs.ctypes.data_as(dp), Ps.ctypes.data_as(dp), Vs.ctypes.data_as(dp)))
+    return Rs, Ps, Vs
 
 
 class BundleAdjuster:

@@ -270,6 +270,14 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* summary);
 /* Debug aid: SM cycles spent in each phase of the step kernel during the last solve (16 slots). */
 int gf_ba_debug_profile(gf_ba* s, long long* out32);
 
+/* Estimator::double2vector (estimator.cpp:2440-2494), the state part: host-only glue that maps the solved para_* arrays
+ * back to Rs / Ps / Vs, rotating the window about z and shifting it so that frame 0 keeps the yaw and position it had
+ * before the solve (Euler-singularity branch included).
+ *   R0_before: Rs[0] before the solve, 3x3 row-major; P0_before: Ps[0]; use_imu: USE_IMU (0: plain copy)
+ *   Rs [n_frames][9] row-major, Ps [n_frames][3], Vs [n_frames][3] (nullable) */
+int gf_ba_double2vector(const gf_ba_problem* p, const double* R0_before, const double* P0_before, int use_imu,
+                        double* Rs, double* Ps, double* Vs);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

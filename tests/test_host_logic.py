@@ -4,6 +4,8 @@ import os
 import re
 import subprocess
 
+import math
+
 import numpy as np
 import pytest
 
@@ -94,3 +96,31 @@ def test_setmask_sort_is_not_stable():
 def test_obs_struct_layout():
     from ground_fusion_b200._lib import OBS_DTYPE, Obs
     assert ctypes.sizeof(Obs) == 72 and OBS_DTYPE.fields["v"][1] == 8
+
+
+def test_double2vector_matches_numpy_restatement():
+    """Estimator::double2vector (estimator.cpp:2440-2494): host-only entry point of the library against oracle/ba_glue.py,
+    including the Euler-singularity branch (pitch within 1 degree of +-90)."""
+    from ground_fusion_b200.ba_problem import Problem
+    from ground_fusion_b200.estimator import double2vector
+    from oracle import ba_glue as G
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        F = 11
+        pb = Problem(F, 1)
+        q = rng.normal(size=(F, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+        if trial % 5 == 4:      # frame 0 pitched to the singular configuration
+            q[0] = [0, math.sin(math.radians(89.7) / 2), 0, math.cos(math.radians(89.7) / 2)]
+        pb.para_pose[:, :3] = rng.normal(0, 3, (F, 3)); pb.para_pose[:, 3:] = q
+        pb.para_speed_bias[:] = rng.normal(0, 1, (F, 9))
+        R0 = G.ypr2R(rng.uniform(-170, 170, 3) * [1, 0.4, 0.4]); P0 = rng.normal(0, 5, 3)
+        for use_imu in (True, False):
+            Rs, Ps, Vs = double2vector(pb, R0, P0, use_imu)
+            Rw, Pw, Vw = G.double2vector(pb.para_pose, pb.para_speed_bias, R0, P0, use_imu)
+            assert np.abs(Rs - Rw).max() < 1e-12 and np.abs(Ps - Pw).max() < 1e-12
+            if use_imu:
+                assert np.abs(Vs - Vw).max() < 1e-12
+                # the point of the exercise: frame 0 keeps its position, and its yaw away from the singularity
+                assert np.abs(Ps[0] - P0).max() < 1e-12
+                if trial % 5 != 4:
+                    assert abs(G.R2ypr(Rs[0])[0] - G.R2ypr(R0)[0]) < 1e-9
