@@ -12,7 +12,8 @@
 //   k_ba_step       single CTA: Jacobi scaling, Schur complement of the free landmarks into the packed reduced
 //                   system, Cholesky (rhs carried as an extra row), traditional dogleg, model cost change,
 //                   candidate x (+) delta.
-//   k_ba_decide     step acceptance, trust-region / mu update, convergence tests (the Ceres state machine).
+//   (ba_decide)     step acceptance, trust-region / mu update, convergence tests (the Ceres state machine): run by the
+//                   last CTA of k_ba_eval(1) to finish.
 // All four are enqueued for every iteration up front; kernels return immediately once the state says "done",
 // so the host synchronises exactly once per solve.
 #include <new>
@@ -39,6 +40,7 @@ struct BaState {
     double acc_cost[2];          // cost accumulated by k_ba_eval into buffer 0/1
     double cauchy_num, cauchy_den;   // |gs|^2 and v^T H' v accumulated by k_ba_schur
     int it, reuse, done, termination, n_success, invalid_streak, need_linearize, step_valid, cur, first, max_iter, solver_failed;
+    unsigned int eval_ticket;    // CTAs of the current k_ba_eval(1) that have finished: the last one runs the decision
     long long prof[32];          // clock64() cycles per phase of k_ba_step, summed over iterations (debug)
 };
 
@@ -136,22 +138,23 @@ __global__ void __launch_bounds__(128) k_ba_setup(BaDev d)
         if (lane < n && lane != c) { double fct = M[lane * w2 + c]; if (fct != 0.0) M[lane * w2 + c] -= fct * M[c * w2 + c]; }
         __syncwarp();
     }
-    if (ok && lane == 0) {          // Cholesky (lower) of the inverse held in the right half, then transpose out
+    if (ok) {          // Cholesky (lower) of the inverse held in the right half: lane i owns row i (same per-element arithmetic as the oracle)
         double* A = M + n;
-        for (int j = 0; j < n && ok; j++) {
-            double dd = A[j * w2 + j];
-            for (int k = 0; k < j; k++) dd -= A[j * w2 + k] * A[j * w2 + k];
+        for (int j = 0; j < n; j++) {
+            double t = 0.0;
+            if (lane >= j && lane < n) {
+                t = A[lane * w2 + j];
+                for (int k = 0; k < j; k++) t -= A[lane * w2 + k] * A[j * w2 + k];
+            }
+            double dd = __shfl_sync(0xffffffffu, t, j);
             if (!(dd > 0.0)) { ok = false; break; }
             dd = sqrt(dd);
-            A[j * w2 + j] = dd;
-            for (int i = j + 1; i < n; i++) {
-                double t = A[i * w2 + j];
-                for (int k = 0; k < j; k++) t -= A[i * w2 + k] * A[j * w2 + k];
-                A[i * w2 + j] = t / dd;
-            }
+            if (lane == j) A[j * w2 + j] = dd;
+            else if (lane > j && lane < n) A[lane * w2 + j] = t / dd;
+            __syncwarp();
         }
         double* out = d.imu_sqrt + 225 * m;
-        if (ok) for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) out[i * n + j] = (j >= i) ? A[j * w2 + i] : 0.0;
+        if (ok) for (int e = lane; e < n * n; e += 32) { int i = e / n, j = e - i * n; out[e] = (j >= i) ? A[j * w2 + i] : 0.0; }
     }
     if (!ok && lane == 0) d.st->termination = GF_BA_FAILURE;
 }
@@ -169,9 +172,49 @@ __global__ void k_ba_prior_hessian(BaDev d)
 }
 
 // ------------------------------------------------------------------------------------------------
+// TrustRegionMinimizer's step acceptance, radius / mu update and convergence tests; run by the last CTA of k_ba_eval(1)
+__device__ void ba_decide(const BaDev& d)
+{
+    BaState& st = *d.st;
+    if (st.done) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __shared__ int accept;
+    __syncthreads();
+    if (tid == 0) {
+        accept = 0;
+        const int it = st.it;
+        if (!st.step_valid) {
+            if (++st.invalid_streak >= 5) { st.done = 1; st.termination = GF_BA_FAILURE; }
+            st.mu *= 10.0; st.reuse = 0;
+            st.cost_hist[it] = st.x_cost; st.radius_hist[it] = st.radius;
+        } else {
+            st.invalid_streak = 0;
+            const double x_cost = st.x_cost, cand = *(volatile double*)&st.acc_cost[st.cur ^ 1];     // candidate cost, summed by all CTAs of k_ba_eval(1)
+            if (st.step_norm <= 1e-8 * (st.x_norm + 1e-8)) { st.done = 1; st.termination = GF_BA_CONVERGENCE_PARAMETER; st.cost_hist[it] = x_cost; st.radius_hist[it] = st.radius; }
+            else if (fabs(x_cost - cand) <= 1e-6 * x_cost) { st.done = 1; st.termination = GF_BA_CONVERGENCE_FUNCTION; st.cost_hist[it] = x_cost; st.radius_hist[it] = st.radius; }
+            else {
+                double rel = (x_cost - cand) / st.model_change;
+                if (rel > 1e-3) {
+                    accept = 1; st.n_success++;
+                    if (rel < 0.25) st.radius *= 0.5;
+                    if (rel > 0.75) st.radius = fmax(st.radius, 3.0 * st.dogleg_norm);
+                    st.mu = fmax(1e-8, 2.0 * st.mu / 10.0);
+                    st.reuse = 0; st.need_linearize = 1;
+                    st.radius_hist[it] = st.radius;          // cost_hist[it] is written when the new linearisation is adopted
+                } else {
+                    st.radius *= 0.5; st.reuse = 1;
+                    st.cost_hist[it] = x_cost; st.radius_hist[it] = st.radius;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (accept) { const int tot = X_FEAT + d.nfeat; for (int e = tid; e < tot; e += nt) d.X[e] = d.Xc[e]; }
+}
+
 // mode 0: linearise at X into the inactive accumulator (first linearisation); mode 1: linearise at the candidate Xc
 // into the inactive accumulator (cost in acc_cost[inactive])
-__global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
+__device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
 {
     __shared__ double sJ[2 * PAIR_CHUNK][20];
     __shared__ double sR[2 * PAIR_CHUNK];
@@ -346,6 +389,27 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
             }
         __syncthreads();
         if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[13], (unsigned long long)(clock64() - t_eval0));
+    }
+}
+
+__global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
+{
+    ba_eval_body(d, mode);
+    if (mode == 1) {
+        // the last CTA to finish takes the decision (accept / reject, radius, mu, convergence): no separate launch
+        __shared__ int s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int t = atomicAdd(&d.st->eval_ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (threadIdx.x == 0) d.st->eval_ticket = 0u;
+            ba_decide(d);
+        }
     }
 }
 
@@ -672,7 +736,11 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
                         mine[b] = q < N4;
                         bi[b] = bj[b] = min(q, N4 - 1);
                     } else {
-                        const int t = tid + b * NOFF_T;
+                        // warps 3, 7, 11 share the diagonal warp's scheduler / FP64 pipe (warp id mod 4): when the blocks fit they
+                        // take one block each instead of two, so that the diagonal chain is less contended
+                        const int w_ = tid >> 5, npeer = (w_ > 3) + (w_ > 7) + (w_ > 11);
+                        const bool peer = (w_ & 3) == 3, light = noff <= NOFF_T + (NOFF_T - 96);
+                        const int t = !light ? tid + b * NOFF_T : (b == 0 ? tid : (peer ? noff : NOFF_T + (w_ - npeer) * 32 + (tid & 31)));
                         mine[b] = t < noff;
                         int cj = 0, off = 0;
                         const int tt = min(t, max(noff - 1, 0));
@@ -923,43 +991,6 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
 }
 
 // TrustRegionMinimizer: HandleInvalidStep / tolerances / IsStepSuccessful / HandleSuccessfulStep / HandleUnsuccessfulStep
-__global__ void k_ba_decide(BaDev d)
-{
-    BaState& st = *d.st;
-    if (st.done) return;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    __shared__ int accept;
-    if (tid == 0) {
-        accept = 0;
-        const int it = st.it;
-        if (!st.step_valid) {
-            if (++st.invalid_streak >= 5) { st.done = 1; st.termination = GF_BA_FAILURE; }
-            st.mu *= 10.0; st.reuse = 0;
-            st.cost_hist[it] = st.x_cost; st.radius_hist[it] = st.radius;
-        } else {
-            st.invalid_streak = 0;
-            const double x_cost = st.x_cost, cand = st.acc_cost[st.cur ^ 1];     // candidate cost (k_ba_eval mode 1)
-            if (st.step_norm <= 1e-8 * (st.x_norm + 1e-8)) { st.done = 1; st.termination = GF_BA_CONVERGENCE_PARAMETER; st.cost_hist[it] = x_cost; st.radius_hist[it] = st.radius; }
-            else if (fabs(x_cost - cand) <= 1e-6 * x_cost) { st.done = 1; st.termination = GF_BA_CONVERGENCE_FUNCTION; st.cost_hist[it] = x_cost; st.radius_hist[it] = st.radius; }
-            else {
-                double rel = (x_cost - cand) / st.model_change;
-                if (rel > 1e-3) {
-                    accept = 1; st.n_success++;
-                    if (rel < 0.25) st.radius *= 0.5;
-                    if (rel > 0.75) st.radius = fmax(st.radius, 3.0 * st.dogleg_norm);
-                    st.mu = fmax(1e-8, 2.0 * st.mu / 10.0);
-                    st.reuse = 0; st.need_linearize = 1;
-                    st.radius_hist[it] = st.radius;          // cost_hist[it] is written when the new linearisation is adopted
-                } else {
-                    st.radius *= 0.5; st.reuse = 1;
-                    st.cost_hist[it] = x_cost; st.radius_hist[it] = st.radius;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (accept) { const int tot = X_FEAT + d.nfeat; for (int e = tid; e < tot; e += nt) d.X[e] = d.Xc[e]; }
-}
 
 }  // namespace gfba
 
@@ -1176,8 +1207,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
         if (it < iters) { k_ba_schur<<<sgrid, sblock, sizeof(double) * (size_t)(L > 0 ? L : 1), st>>>(d); GF_LAUNCHED(); }
         k_ba_step<<<1, RB_THREADS, step_smem, st>>>(d); GF_LAUNCHED();
         if (it == iters) break;                  // the extra k_ba_step adopts the last linearisation and closes the run
-        if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 1); GF_LAUNCHED(); }
-        k_ba_decide<<<1, 256, 0, st>>>(d); GF_LAUNCHED();
+        k_ba_eval<<<eval_blocks > 0 ? eval_blocks : 1, PAIR_THREADS, prior_smem, st>>>(d, 1); GF_LAUNCHED();   // + decision (last CTA)
     }
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpyAsync(hb + o_X, db + o_X, sizeof(double) * (X_FEAT + nfeat), cudaMemcpyDeviceToHost, st));
