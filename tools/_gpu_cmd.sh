@@ -1,2 +1,4 @@
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_ba_r1f.csv python tools/prof_ba.py 4 > /dev/null 2>&1
-python tools/ncu_summary.py gpurun_out/launches_ba_r1f.csv
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+timeout 400 python bench.py 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench12.json; python -c "
+import json; d=json.load(open('gpurun_out/bench12.json')); print(d['value'], d['e2e']['value'], d['device_ms_per_step'], d['cpu_baseline'], d['ba'], d['clocks'])"
