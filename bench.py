@@ -127,6 +127,33 @@ def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
                        % (wins[0].n_visual, wins[0].n_imu, sm.reduced_dim, sm.n_free_landmarks),
            "e2e": "value already includes the host->device upload of the problem and the download of the blocks"}
     ba.close()
+    # independent windows (several estimators sharing one GPU): one gf_ba handle and one host thread per stream; a solve
+    # occupies 1-121 CTAs for microseconds at a time, so concurrent solves spread over the SMs
+    import threading
+    n_str = 4
+    sets = []
+    for t in range(n_str):
+        ws = [make_window(seed=200 + 10 * t + k)[0] for k in range(2)]
+        sets.append((ws, [w.struct() for w in ws], [(w.para_pose.copy(), w.para_speed_bias.copy(), w.para_feature.copy()) for w in ws], BundleAdjuster(device)))
+    def worker(t, n):
+        ws, st, sv, b = sets[t]
+        for r in range(n):
+            k = r % len(ws)
+            ws[k].para_pose[:] = sv[k][0]; ws[k].para_speed_bias[:] = sv[k][1]; ws[k].para_feature[:] = sv[k][2]
+            b.solve_struct(st[k])
+    for t in range(n_str):
+        worker(t, 2)
+    th = [threading.Thread(target=worker, args=(t, reps)) for t in range(n_str)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    elc = time.perf_counter() - t0
+    out["concurrent_streams"] = {"streams": n_str, "value": n_str * reps / elc, "unit": "solves/s",
+                                 "note": "aggregate of %d independent windows solved concurrently on one GPU (one gf_ba handle + host thread each)" % n_str}
+    for s_ in sets:
+        s_[3].close()
     if with_cpu:
         from oracle import ba_oracle
         t0 = time.perf_counter(); done = 0
