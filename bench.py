@@ -126,6 +126,13 @@ def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
            "workload": "C2 window: 11 frames, %d visual factors, %d IMU factors, reduced system %d + %d free landmarks, max 8 iterations"
                        % (wins[0].n_visual, wins[0].n_imu, sm.reduced_dim, sm.n_free_landmarks),
            "e2e": "value already includes the host->device upload of the problem and the download of the blocks"}
+    # the marginalisation that ends Estimator::optimization() on a keyframe (MARGIN_OLD), on the solved window
+    restore(0); ba.solve_struct(structs[0])
+    ba.marginalize_old(wins[0])
+    mms = []
+    for _ in range(5):
+        ba.marginalize_old(wins[0]); mms.append(ba.last_marg_ms)
+    out["marginalize_old"] = {"device_ms": float(np.median(mms)), "note": "gf_ba_marginalize_old on the solved C2 window (191 marginalised + 76 kept dimensions)"}
     ba.close()
     # independent windows (several estimators sharing one GPU): one gf_ba handle and one host thread per stream; a solve
     # occupies 1-121 CTAs for microseconds at a time, so concurrent solves spread over the SMs
@@ -163,6 +170,10 @@ def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": done / dt, "unit": "solves/s", "cores": 1, "kind": "port",
                                "sample": "%d solves of the same windows, oracle/ba_oracle.c (block-sparse, -O2, 1 thread)" % done}
+        restore(0); ba_oracle.solve(wins[0])
+        t0 = time.perf_counter(); ba_oracle.marginalize_old(wins[0]); 
+        out["marginalize_old"]["cpu_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["marginalize_old"]["cpu_note"] = "oracle uses a plain cyclic Jacobi eigensolver (slower than Eigen's tridiagonal QR the reference calls)"
     return out
 
 

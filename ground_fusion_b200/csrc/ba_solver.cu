@@ -47,6 +47,7 @@ struct BaState {
 struct BaDev {
     int F, nfeat, n_vis, n_imu, n_wheel, n_pairs, nc, L, n;
     int col_pose[MAXF], col_sb[MAXF], col_ex, col_td;
+    int lm_dense;             // marginalisation: landmark columns are ordinary columns of H (cf < nc), no W / hll arrays
     int col_exw, col_ix[3], col_tdw, exw_mask;     // wheel extrinsic / intrinsics / time offset (-1: constant or absent)
     const gf_ba_wheel_factor* wheel;
     const int* col_feat;
@@ -253,7 +254,18 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
                 if (jac) {
                     for (int r = 0; r < 2; r++) { for (int c = 0; c < 20; c++) sJ[2 * tid + r][c] = sc * J[r * 20 + c]; sR[2 * tid + r] = sc * res[r]; }
                     int cf = d.col_feat[f.feature];
-                    if (cf >= 0) {      // landmark terms: h_ll, g_l, W[l][camera cols]
+                    if (cf >= 0 && d.lm_dense) {      // marginalisation: the landmark is a column of the dense matrix
+                        double j0 = sc * J[19], j1 = sc * J[39], r0 = sc * res[0], r1 = sc * res[1];
+                        double* H = acc_H(d, tgt);
+                        atomicAdd(&H[(size_t)cf * d.nc + cf], j0 * j0 + j1 * j1);
+                        atomicAdd(&acc_g(d, tgt)[cf], j0 * r0 + j1 * r1);
+                        for (int q = 0; q < 4; q++) if (cols[q] >= 0)
+                            for (int k = 0; k < bsz[q]; k++) {
+                                const double w_ = j0 * sc * J[boff[q] + k] + j1 * sc * J[20 + boff[q] + k];
+                                atomicAdd(&H[(size_t)cf * d.nc + cols[q] + k], w_);
+                                atomicAdd(&H[(size_t)(cols[q] + k) * d.nc + cf], w_);
+                            }
+                    } else if (cf >= 0) {      // landmark terms: h_ll, g_l, W[l][camera cols]
                         int l = cf - d.nc;
                         double j0 = sc * J[19], j1 = sc * J[39], r0 = sc * res[0], r1 = sc * res[1];
                         atomicAdd(&acc_hll(d, tgt)[l], j0 * j0 + j1 * j1);
@@ -992,6 +1004,184 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
 
 // TrustRegionMinimizer: HandleInvalidStep / tolerances / IsStepSuccessful / HandleSuccessfulStep / HandleUnsuccessfulStep
 
+// ------------------------------------------------------------------------------------------------
+// Marginalisation (MarginalizationInfo::marginalize, reference factor/marginalization_factor.cpp:183-308)
+// ------------------------------------------------------------------------------------------------
+// Symmetric eigendecomposition by cyclic Jacobi in a parallel ordering, one CTA, matrix in global memory (L2).
+// A round pairs every index with exactly one other (round-robin tournament), so the n/2 rotations of a round commute
+// as a similarity A <- J^T A J with J = product of the plane rotations: the matrix splits into disjoint 2x2 blocks
+// (row pair x column pair), each updated independently from the two rotations involved.  V accumulates the rotations
+// (columns = eigenvectors), w = diagonal at convergence (off-norm <= 1e-30 * diag-norm, like the oracle's sweep test).
+__global__ void __launch_bounds__(1024) k_jacobi_eig(double* A, double* V, double* w, int n, int* sweeps_out)
+{
+    extern __shared__ double jsm[];           // c[np/2], s[np/2]; then int pr[np/2], qr[np/2]
+    __shared__ double sred[32];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int np = (n + 1) & ~1, hp = np / 2;
+    double* cs_c = jsm; double* cs_s = jsm + hp;
+    int* pp = reinterpret_cast<int*>(jsm + 2 * hp); int* qq = pp + hp;
+    for (int e = tid; e < n * n; e += nt) V[e] = (e / n == e % n) ? 1.0 : 0.0;
+    __syncthreads();
+    int sweep = 0;
+    for (; sweep < 60; sweep++) {
+        double off = 0, dg = 0;
+        for (int e = tid; e < n * n; e += nt) { int i = e / n, j = e - i * n; double v = A[e]; if (i == j) dg += v * v; else if (j > i) off += v * v; }
+        off = block_reduce_sum(off, sred); dg = block_reduce_sum(dg, sred);
+        if (off <= 1e-30 * dg || off == 0.0) break;
+        for (int round = 0; round < np - 1; round++) {
+            if (tid < hp) {
+                int a = tid == 0 ? np - 1 : (round + tid) % (np - 1);
+                int b = tid == 0 ? round : (round + np - 1 - tid) % (np - 1);
+                int p_ = min(a, b), q_ = max(a, b);
+                double c = 1.0, sn = 0.0;
+                if (q_ < n) {
+                    const double apq = A[(size_t)p_ * n + q_];
+                    if (apq != 0.0) {
+                        const double theta = (A[(size_t)q_ * n + q_] - A[(size_t)p_ * n + p_]) / (2.0 * apq);
+                        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0); sn = t * c;
+                    }
+                }
+                cs_c[tid] = c; cs_s[tid] = sn; pp[tid] = p_; qq[tid] = q_;
+            }
+            __syncthreads();
+            // A <- J^T A J on the 2x2 blocks (row pair r, column pair k).  The blocks are disjoint, so a thread first
+            // issues the loads of four of its blocks (L2 latency paid once per batch), then rotates and stores them.
+            for (int base = tid; base < hp * hp; base += 4 * nt) {
+                double a11[4], a12[4], a21[4], a22[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int task = base + u * nt;
+                    a11[u] = a12[u] = a21[u] = a22[u] = 0.0;
+                    if (task < hp * hp) {
+                        const int r = task / hp, k = task - r * hp;
+                        const int p1 = pp[r], q1 = qq[r], p2 = pp[k], q2 = qq[k];
+                        const bool hq1 = q1 < n, hq2 = q2 < n;          // q == n is the padding index of an odd n
+                        a11[u] = A[(size_t)p1 * n + p2];
+                        if (hq2) a12[u] = A[(size_t)p1 * n + q2];
+                        if (hq1) a21[u] = A[(size_t)q1 * n + p2];
+                        if (hq1 && hq2) a22[u] = A[(size_t)q1 * n + q2];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int task = base + u * nt;
+                    if (task < hp * hp) {
+                        const int r = task / hp, k = task - r * hp;
+                        const int p1 = pp[r], q1 = qq[r], p2 = pp[k], q2 = qq[k];
+                        const double c1 = cs_c[r], s1 = cs_s[r], c2 = cs_c[k], s2 = cs_s[k];
+                        const bool hq1 = q1 < n, hq2 = q2 < n;
+                        // columns: [a.1 a.2] <- [c2 a.1 - s2 a.2, s2 a.1 + c2 a.2]
+                        const double b11 = c2 * a11[u] - s2 * a12[u], b12 = s2 * a11[u] + c2 * a12[u];
+                        const double b21 = c2 * a21[u] - s2 * a22[u], b22 = s2 * a21[u] + c2 * a22[u];
+                        // rows: [b1.; b2.] <- [c1 b1. - s1 b2.; s1 b1. + c1 b2.]
+                        A[(size_t)p1 * n + p2] = c1 * b11 - s1 * b21;
+                        if (hq2) A[(size_t)p1 * n + q2] = c1 * b12 - s1 * b22;
+                        if (hq1) A[(size_t)q1 * n + p2] = s1 * b11 + c1 * b21;
+                        if (hq1 && hq2) A[(size_t)q1 * n + q2] = s1 * b12 + c1 * b22;
+                    }
+                }
+            }
+            for (int base = tid; base < n * hp; base += 4 * nt) {     // V <- V J, same batching
+                double vp[4], vq[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int task = base + u * nt;
+                    vp[u] = vq[u] = 0.0;
+                    if (task < n * hp) {
+                        const int row = task / hp, k = task - row * hp;
+                        if (qq[k] < n) { vp[u] = V[(size_t)row * n + pp[k]]; vq[u] = V[(size_t)row * n + qq[k]]; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int task = base + u * nt;
+                    if (task < n * hp) {
+                        const int row = task / hp, k = task - row * hp;
+                        if (qq[k] < n) {
+                            const double c2 = cs_c[k], s2 = cs_s[k];
+                            V[(size_t)row * n + pp[k]] = c2 * vp[u] - s2 * vq[u];
+                            V[(size_t)row * n + qq[k]] = s2 * vp[u] + c2 * vq[u];
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < n; i += nt) w[i] = A[(size_t)i * n + i];
+    if (tid == 0 && sweeps_out) *sweeps_out = sweep;
+}
+
+struct MargDev {
+    int N, m, n;
+    const double *H, *Hp, *g;     // accumulated by k_ba_eval (N x N, N)
+    double *A, *b;                // N x N, N
+    double *Amm, *Vm, *wm, *Ainv; // m x m ...
+    double *T;                    // n x m
+    double *Ar, *Vr, *wr, *br;    // n x n ...
+    double *J0, *r0;
+};
+
+__global__ void k_marg_pack(MargDev q)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, N = q.N;
+    if (e < N * N) q.A[e] = q.H[e] + q.Hp[e];
+    if (e < N) q.b[e] = q.g[e];
+}
+__global__ void k_marg_amm(MargDev q)      // Amm = 0.5 (Amm + Amm^T)   (marginalization_factor.cpp:278)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, m = q.m, N = q.N;
+    if (e >= m * m) return;
+    const int i = e / m, j = e - i * m;
+    q.Amm[e] = 0.5 * (q.A[(size_t)i * N + j] + q.A[(size_t)j * N + i]);
+}
+__global__ void k_marg_ainv(MargDev q)     // Amm_inv = V diag(w > eps ? 1/w : 0) V^T     (:279-283)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, m = q.m;
+    if (e >= m * m) return;
+    const int i = e / m, j = e - i * m;
+    double v = 0;
+    for (int k = 0; k < m; k++) { const double wk = q.wm[k]; if (wk > 1e-8) v += q.Vm[(size_t)i * m + k] * (1.0 / wk) * q.Vm[(size_t)j * m + k]; }
+    q.Ainv[e] = v;
+}
+__global__ void k_marg_T(MargDev q)        // T = Arm Amm_inv
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, m = q.m, n = q.n, N = q.N;
+    if (e >= n * m) return;
+    const int i = e / m, j = e - i * m;
+    double v = 0;
+    for (int k = 0; k < m; k++) v += q.A[(size_t)(m + i) * N + k] * q.Ainv[(size_t)k * m + j];
+    q.T[e] = v;
+}
+__global__ void k_marg_reduce(MargDev q)   // A = Arr - Arm Amm_inv Amr, b = brr - Arm Amm_inv bmm   (:286-292); lower triangle mirrored
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, m = q.m, n = q.n, N = q.N;
+    if (e < n * n) {
+        const int i = e / n, j = e - i * n;
+        if (j <= i) {
+            double v = q.A[(size_t)(m + i) * N + m + j];
+            for (int k = 0; k < m; k++) v -= q.T[(size_t)i * m + k] * q.A[(size_t)k * N + m + j];
+            q.Ar[(size_t)i * n + j] = v; q.Ar[(size_t)j * n + i] = v;
+        }
+    }
+    if (e < n) { double v = q.b[m + e]; for (int k = 0; k < m; k++) v -= q.T[(size_t)e * m + k] * q.b[k]; q.br[e] = v; }
+}
+__global__ void k_marg_out(MargDev q)      // J0 = sqrt(S) V^T, r0 = sqrt(S^-1) V^T b     (:294-302)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, n = q.n;
+    if (e < n * n) {
+        const int k = e / n, i = e - k * n;
+        const double S = q.wr[k] > 1e-8 ? q.wr[k] : 0.0;
+        q.J0[e] = sqrt(S) * q.Vr[(size_t)i * n + k];
+    }
+    if (e < n) {
+        const double Si = q.wr[e] > 1e-8 ? 1.0 / q.wr[e] : 0.0;
+        double vb = 0; for (int i = 0; i < n; i++) vb += q.Vr[(size_t)i * n + e] * q.br[i];
+        q.r0[e] = sqrt(Si) * vb;
+    }
+}
+
 }  // namespace gfba
 
 // ------------------------------------------------------------------------------------------------
@@ -1230,6 +1420,179 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     sum->device_ms = ms;
     memcpy(s->prof, hs->prof, sizeof(s->prof));
     return GF_OK;
+}
+
+/* MARGIN_OLD (estimator.cpp:3334-3535) + MarginalizationInfo::{preMarginalize, marginalize}
+ * (marginalization_factor.cpp:115-308) on the GPU: the factors that touch frame 0 -- last prior, IMU(0->1), every visual
+ * factor whose landmark starts in frame 0 -- are linearised by the same kernels as the solve into one dense system over
+ * [pose0, speedbias0, those landmarks | kept blocks]; the marginalised part is eliminated with the eigen-truncated
+ * inverse (eps 1e-8) and the result is re-factored into J0 = sqrt(S) V^T, r0 = sqrt(S^-1) V^T b, exactly the reference's
+ * two SelfAdjointEigenSolver calls (here: parallel-ordered Jacobi).  Kept blocks are ordered pose[1..], speedbias[1..],
+ * ex_pose, td and their indices are already shifted by one frame (addr_shift, estimator.cpp:3500-3534).
+ * Wheel / plane / GNSS factors of frame 0 are not included (as in the oracle).  out_x0 / out_J / out_r must hold
+ * 16*n_frames+8, n*n, n doubles.  Returns n (> 0) or a negative error code. */
+int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r, float* device_ms)
+{
+    if (!s || !p || !out || !out_x0 || !out_J || !out_r) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    if (p->n_frames < 2 || p->n_frames > GF_BA_MAX_FRAMES) return set_err(GF_ERR_INVALID_ARG, "n_frames out of range");
+    GF_CUDA(cudaSetDevice(s->device));
+    const int F = p->n_frames, nfeat = p->n_features;
+    const bool use_sb = p->para_speed_bias && !p->pose0_const;
+    // ---- the marginalised and the kept blocks (same rules as the oracle) ----
+    std::vector<int> lm_col(nfeat > 0 ? nfeat : 1, -1);
+    int pos = 0;
+    BaDev d; memset(&d, 0, sizeof(d));
+    d.F = F; d.nfeat = nfeat; d.lm_dense = 1;
+    for (int f = 0; f < MAXF; f++) { d.col_pose[f] = -1; d.col_sb[f] = -1; }
+    d.col_ex = d.col_td = d.col_exw = d.col_tdw = -1; d.col_ix[0] = d.col_ix[1] = d.col_ix[2] = -1;
+    d.col_pose[0] = pos; pos += 6;
+    if (use_sb) { d.col_sb[0] = pos; pos += 9; }
+    std::vector<gf_ba_visual_factor> vis0;
+    for (int v = 0; v < p->n_visual; v++) {
+        const gf_ba_visual_factor& f = p->visual[v];
+        if (f.feature < 0 || f.feature >= nfeat || f.imu_i < 0 || f.imu_i >= F || f.imu_j < 0 || f.imu_j >= F) return set_err(GF_ERR_INVALID_ARG, "visual factor index out of range");
+        if (f.imu_i != 0) continue;
+        if (lm_col[f.feature] < 0) lm_col[f.feature] = pos++;
+        vis0.push_back(f);
+    }
+    const int m = pos;
+    bool used_pose[MAXF] = {}, used_sb[MAXF] = {}, used_ex = false, used_td = false;
+    const gf_ba_prior* pr = (p->prior && p->prior->n > 0) ? p->prior : nullptr;
+    if (pr) {
+        if (pr->n_blocks > 64) return set_err(GF_ERR_CAPACITY, "more than 64 prior blocks");
+        for (int b = 0; b < pr->n_blocks; b++) {
+            const int k = pr->block_kind[b], i = pr->block_index[b];
+            if (k == GF_BA_BLOCK_POSE || k == GF_BA_BLOCK_SPEEDBIAS) { if (i < 0 || i >= F) return set_err(GF_ERR_INVALID_ARG, "prior block index out of range"); (k == GF_BA_BLOCK_POSE ? used_pose : used_sb)[i] = true; }
+            else if (k == GF_BA_BLOCK_EX_POSE) used_ex = true;
+            else if (k == GF_BA_BLOCK_TD) used_td = true;
+            else return set_err(GF_ERR_UNSUPPORTED, "marginalisation of a prior with wheel blocks is not implemented");
+        }
+    }
+    const gf_ba_imu_factor* imu01 = nullptr;
+    for (int k = 0; k < p->n_imu; k++) if (p->imu[k].i == 0 && p->imu[k].j == 1 && p->imu[k].sum_dt < 10.0) { imu01 = &p->imu[k]; used_pose[1] = true; used_sb[1] = true; }
+    for (const auto& f : vis0) { used_pose[f.imu_j] = true; used_ex = true; used_td = true; }
+    for (int f = 1; f < F; f++) if (used_pose[f]) { d.col_pose[f] = pos; pos += 6; }
+    for (int f = 1; f < F; f++) if (used_sb[f] && use_sb) { d.col_sb[f] = pos; pos += 9; }
+    if (used_ex) { d.col_ex = pos; pos += 6; }
+    if (used_td) { d.col_td = pos; pos += 1; }
+    const int N = pos, n = N - m;
+    if (n <= 0) return set_err(GF_ERR_INVALID_ARG, "nothing is kept by the marginalisation");
+    d.nc = N; d.L = 0; d.n = N; d.n_vis = (int)vis0.size(); d.n_imu = imu01 ? 1 : 0; d.n_wheel = 0;
+    // ---- visual factors by pose pair (0, j), cut into chunks ----
+    std::vector<int> cnt(F, 0), start(F + 1, 0);
+    for (const auto& f : vis0) cnt[f.imu_j]++;
+    for (int j = 0; j < F; j++) start[j + 1] = start[j] + cnt[j];
+    std::vector<int> work_start(1, 0), work_ij;
+    for (int j = 0; j < F; j++)
+        for (int c0 = start[j]; c0 < start[j + 1]; c0 += PAIR_CHUNK) { work_ij.push_back(0); work_ij.push_back(j); work_start.push_back(std::min(c0 + PAIR_CHUNK, start[j + 1])); }
+    const int n_work = (int)work_ij.size() / 2;
+    d.n_pairs = n_work;
+    const int pn = pr ? pr->n : 0;
+    std::vector<int> pcol(pn > 0 ? pn : 1, -1);
+    size_t px0_len = 0;
+    if (pr) {
+        d.pn = pn; d.pnb = pr->n_blocks;
+        for (int b = 0; b < pr->n_blocks; b++) {
+            const int kind = pr->block_kind[b], idx = pr->block_index[b];
+            d.pkind[b] = kind; d.pindex[b] = idx; d.pidx[b] = pr->block_idx[b]; d.pxoff[b] = (int)px0_len;
+            const int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1, ls = gs == 7 ? 6 : gs;
+            const int lc = kind == GF_BA_BLOCK_POSE ? d.col_pose[idx] : kind == GF_BA_BLOCK_SPEEDBIAS ? d.col_sb[idx] : kind == GF_BA_BLOCK_EX_POSE ? d.col_ex : d.col_td;
+            if (lc >= 0) for (int k = 0; k < ls; k++) pcol[pr->block_idx[b] + k] = lc + k;
+            px0_len += gs;
+        }
+    }
+    // ---- one upload buffer + work space ----
+    auto al = [](size_t v) { return (v + 15) / 16 * 16; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
+    const size_t nv = vis0.size();
+    const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (nv ? nv : 1)), o_imu = take(sizeof(gf_ba_imu_factor)),
+                 o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)), o_cf = take(sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1)),
+                 o_pJ = take(sizeof(double) * (size_t)pn * pn), o_pr0 = take(sizeof(double) * pn), o_px0 = take(sizeof(double) * px0_len), o_pcol = take(sizeof(int) * (size_t)(pn > 0 ? pn : 1));
+    const size_t upload_bytes = off;
+    const size_t NN = (size_t)N * N, mm = (size_t)m * m, nn = (size_t)n * n;
+    const size_t o_sq = take(sizeof(double) * 225), o_Hp = take(sizeof(double) * NN), o_a0 = take(sizeof(double) * acc_size(N, 0)), o_st = take(sizeof(BaState)),
+                 o_A = take(sizeof(double) * NN), o_b = take(sizeof(double) * N), o_Amm = take(sizeof(double) * mm), o_Vm = take(sizeof(double) * mm), o_wm = take(sizeof(double) * m),
+                 o_Ainv = take(sizeof(double) * mm), o_T = take(sizeof(double) * (size_t)n * m), o_Ar = take(sizeof(double) * nn), o_Vr = take(sizeof(double) * nn),
+                 o_wr = take(sizeof(double) * n), o_br = take(sizeof(double) * n), o_J0 = take(sizeof(double) * nn), o_r0 = take(sizeof(double) * n), o_sw = take(sizeof(int) * 4);
+    int rc = ensure(s, off);
+    if (rc) return rc;
+    char* hb = (char*)s->hbuf; char* db = (char*)s->dbuf;
+    double* hX = (double*)(hb + o_X);
+    memset(hX, 0, sizeof(double) * (X_FEAT + nfeat));
+    memcpy(hX + X_POSE, p->para_pose, sizeof(double) * 7 * F);
+    if (p->para_speed_bias) memcpy(hX + X_SB, p->para_speed_bias, sizeof(double) * 9 * F);
+    memcpy(hX + X_EX, p->para_ex_pose, sizeof(double) * 7);
+    hX[X_TD] = p->para_td[0];
+    hX[X_EXW + 6] = 1.0; hX[X_IX] = hX[X_IX + 1] = hX[X_IX + 2] = 1.0;
+    memcpy(hX + X_FEAT, p->para_feature, sizeof(double) * nfeat);
+    {
+        gf_ba_visual_factor* hv = (gf_ba_visual_factor*)(hb + o_vis);
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (const auto& f : vis0) hv[fill[f.imu_j]++] = f;
+    }
+    if (imu01) memcpy(hb + o_imu, imu01, sizeof(gf_ba_imu_factor));
+    memcpy(hb + o_ps, work_start.data(), sizeof(int) * (n_work + 1));
+    if (n_work) memcpy(hb + o_pij, work_ij.data(), sizeof(int) * 2 * n_work);
+    memcpy(hb + o_cf, lm_col.data(), sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1));
+    if (pr) {
+        memcpy(hb + o_pJ, pr->linearized_jacobians, sizeof(double) * (size_t)pn * pn);
+        memcpy(hb + o_pr0, pr->linearized_residuals, sizeof(double) * pn);
+        memcpy(hb + o_px0, pr->x0, sizeof(double) * px0_len);
+        memcpy(hb + o_pcol, pcol.data(), sizeof(int) * pn);
+    }
+    d.X = (double*)(db + o_X); d.Xc = d.X;
+    d.vis = (const gf_ba_visual_factor*)(db + o_vis); d.pair_start = (const int*)(db + o_ps); d.pair_ij = (const int*)(db + o_pij);
+    d.imu = (const gf_ba_imu_factor*)(db + o_imu); d.imu_sqrt = (double*)(db + o_sq); d.wheel = nullptr;
+    d.col_feat = (const int*)(db + o_cf);
+    d.pJ = (const double*)(db + o_pJ); d.pr0 = (const double*)(db + o_pr0); d.px0 = (const double*)(db + o_px0); d.pcol = (const int*)(db + o_pcol);
+    d.Hp = (double*)(db + o_Hp); d.acc[0] = (double*)(db + o_a0); d.acc[1] = d.acc[0];
+    d.st = (BaState*)(db + o_st);
+    memcpy(d.gravity, p->gravity, sizeof(d.gravity)); d.vis_sqrt_info = p->visual_sqrt_info;
+    const size_t NN_ = (size_t)N * N; (void)NN_;
+    MargDev q;
+    q.N = N; q.m = m; q.n = n; q.H = d.acc[0]; q.Hp = d.Hp; q.g = d.acc[0] + NN;      // acc layout: [H N*N | g N | ...]
+    q.A = (double*)(db + o_A); q.b = (double*)(db + o_b); q.Amm = (double*)(db + o_Amm); q.Vm = (double*)(db + o_Vm); q.wm = (double*)(db + o_wm);
+    q.Ainv = (double*)(db + o_Ainv); q.T = (double*)(db + o_T); q.Ar = (double*)(db + o_Ar); q.Vr = (double*)(db + o_Vr); q.wr = (double*)(db + o_wr);
+    q.br = (double*)(db + o_br); q.J0 = (double*)(db + o_J0); q.r0 = (double*)(db + o_r0);
+    cudaStream_t st = s->s;
+    GF_CUDA(cudaEventRecord(s->e0, st));
+    GF_CUDA(cudaMemcpyAsync(db, hb, upload_bytes, cudaMemcpyHostToDevice, st));
+    GF_CUDA(cudaMemsetAsync(db + o_a0, 0, al(sizeof(double) * acc_size(N, 0)), st));
+    GF_CUDA(cudaMemsetAsync(db + o_st, 0, sizeof(BaState), st));
+    k_ba_setup<<<d.n_imu + 1, 128, 0, st>>>(d); GF_LAUNCHED();        // sqrt_info of IMU(0->1), Hp = 0, state: linearise into buffer 0
+    if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
+    const int eval_blocks = n_work + d.n_imu + (pn ? 1 : 0);
+    if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, sizeof(double) * 2 * (size_t)pn, st>>>(d, 0); GF_LAUNCHED(); }
+    k_marg_pack<<<(int)((NN + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+    k_marg_amm<<<(int)((mm + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+    auto jac_smem = [](int nn_) { int hp = ((nn_ + 1) & ~1) / 2; return (size_t)hp * (2 * sizeof(double) + 2 * sizeof(int)); };
+    k_jacobi_eig<<<1, 1024, jac_smem(m), st>>>(q.Amm, q.Vm, q.wm, m, (int*)(db + o_sw)); GF_LAUNCHED();
+    k_marg_ainv<<<(int)((mm + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+    k_marg_T<<<(int)(((size_t)n * m + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+    k_marg_reduce<<<(int)((nn + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+    k_jacobi_eig<<<1, 1024, jac_smem(n), st>>>(q.Ar, q.Vr, q.wr, n, (int*)(db + o_sw) + 1); GF_LAUNCHED();
+    k_marg_out<<<(int)((nn + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaMemcpyAsync(hb + o_J0, db + o_J0, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+    GF_CUDA(cudaMemcpyAsync(hb + o_r0, db + o_r0, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    GF_CUDA(cudaMemcpyAsync(hb + o_st, db + o_st, sizeof(BaState), cudaMemcpyDeviceToHost, st));
+    GF_CUDA(cudaEventRecord(s->e1, st));
+    GF_CUDA(cudaStreamSynchronize(st));
+    if (((BaState*)(hb + o_st))->termination == GF_BA_FAILURE) return set_err(GF_ERR_INVALID_ARG, "IMU covariance is not positive definite");
+    if (device_ms) GF_CUDA(cudaEventElapsedTime(device_ms, s->e0, s->e1));
+    memcpy(out_J, hb + o_J0, sizeof(double) * nn);
+    memcpy(out_r, hb + o_r0, sizeof(double) * n);
+    // ---- kept blocks after addr_shift ----
+    memset(out, 0, sizeof(*out));
+    out->n = n;
+    int nb = 0; double* xp = out_x0;
+    for (int f = 1; f < F; f++) if (d.col_pose[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_POSE; out->block_index[nb] = f - 1; out->block_idx[nb] = d.col_pose[f] - m; memcpy(xp, p->para_pose + 7 * f, 56); xp += 7; nb++; }
+    for (int f = 1; f < F; f++) if (d.col_sb[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SPEEDBIAS; out->block_index[nb] = f - 1; out->block_idx[nb] = d.col_sb[f] - m; memcpy(xp, p->para_speed_bias + 9 * f, 72); xp += 9; nb++; }
+    if (d.col_ex >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_POSE; out->block_index[nb] = 0; out->block_idx[nb] = d.col_ex - m; memcpy(xp, p->para_ex_pose, 56); xp += 7; nb++; }
+    if (d.col_td >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD; out->block_index[nb] = 0; out->block_idx[nb] = d.col_td - m; xp[0] = p->para_td[0]; xp += 1; nb++; }
+    out->n_blocks = nb; out->x0 = out_x0; out->linearized_jacobians = out_J; out->linearized_residuals = out_r;
+    return n;
 }
 
 /* Estimator::double2vector (reference estimator.cpp:2440-2494): after the solve the whole window is rotated about z and

@@ -3,10 +3,12 @@
 // Mirrors FeatureTracker::trackImage (reference vins_estimator/src/featureTracker/feature_tracker.cpp:103-372).
 // One frame = fixed sequences of copies and kernels on three streams (no host round trip inside the frame; the only
 // synchronisation is the wait for the result).  Up to two frames are in flight: everything that does not depend on
-// the previous frame's result (upload, pyramid, min-eig map) runs ahead on s_pre while s_main is still tracking the
+// the previous frame's result (upload, pyramid, min-eig map) runs ahead on their own streams while s_main is still tracking the
 // previous frame, so in steady state the frame period is the dependent chain alone.
 //
-//   s_pre : H2D gray/depth -> pyrDown x3 (ev_pyr) -> k_cov_rows -> k_box_chain -> k_eig_from_box (ev_eig)
+//   s_up  : H2D gray/depth (ev_up)                  -- the copy of frame t+2 overlaps the pyramid / min-eig kernels of t+1
+//   s_pyr : (ev_up) pyrDown x3 (ev_pyr)
+//   s_eig : (ev_up) k_cov_rows -> k_box_chain -> k_eig_from_box (ev_eig)
 //   s_main: (ev_pyr) [prediction LK] -> k_track (fwd LK 3 lvls + bwd LK 1 lvl + status rules) -> k_compact_setmask
 //           -> (ev_eig) masked max -> candidates -> k_select_finalize (min-distance rounds, top-K, addPoints,
 //           undistort, velocity, depth)  (ev_dep)
@@ -167,8 +169,8 @@ struct gf_tracker {
     int device, w, h;
     gf_tracker_cfg cfg;
     CamParams cam;
-    cudaStream_t s_pre, s_main, s_out;
-    cudaEvent_t ev_pyr[2], ev_eig[2], ev_dep[2], ev_t0[2], ev_out[2];
+    cudaStream_t s_up, s_pyr, s_eig, s_main, s_out;
+    cudaEvent_t ev_up[2], ev_pyr[2], ev_eig[2], ev_dep[2], ev_t0[2], ev_out[2];
     cudaEvent_t ev_st[GF_FE_STAGES + 2];   // stage boundaries (profiling mode)
     cudaEvent_t ev_span0, ev_span1;        // gf_tracker_timer_start / _stop
     bool profiling;
@@ -181,7 +183,7 @@ struct gf_tracker {
     int lw[4], lh[4], lp[4];
     uint16_t* d_depth[2]; int depth_pitch_el;
     float* d_eig[2]; int epitch;
-    double* d_cov; float* d_box;          // min-eig intermediates (fe_eig.cuh), only live inside one frame's s_pre work
+    double* d_cov; float* d_box;          // min-eig intermediates (fe_eig.cuh), only live inside one frame's s_eig work
     NmsGrid grid; size_t grid_cells;
     TrackScalars* d_sc;
     FeatArrays fa;
@@ -313,10 +315,13 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     if (!t) return set_err(GF_ERR_CUDA, "out of host memory");
     memset(t, 0, sizeof(*t));
     t->device = device; t->w = width; t->h = height; t->cfg = *cfg; t->cam = make_cam(cfg->pinhole);
-    GF_CUDA(cudaStreamCreateWithFlags(&t->s_pre, cudaStreamNonBlocking));
+    GF_CUDA(cudaStreamCreateWithFlags(&t->s_up, cudaStreamNonBlocking));
+    GF_CUDA(cudaStreamCreateWithFlags(&t->s_pyr, cudaStreamNonBlocking));
+    GF_CUDA(cudaStreamCreateWithFlags(&t->s_eig, cudaStreamNonBlocking));
     GF_CUDA(cudaStreamCreateWithFlags(&t->s_main, cudaStreamNonBlocking));
     GF_CUDA(cudaStreamCreateWithFlags(&t->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
+        GF_CUDA(cudaEventCreateWithFlags(&t->ev_up[i], cudaEventDisableTiming));
         GF_CUDA(cudaEventCreateWithFlags(&t->ev_pyr[i], cudaEventDisableTiming));
         GF_CUDA(cudaEventCreateWithFlags(&t->ev_eig[i], cudaEventDisableTiming));
         GF_CUDA(cudaEventCreateWithFlags(&t->ev_dep[i], cudaEventDisableTiming));
@@ -376,7 +381,7 @@ void gf_tracker_destroy(gf_tracker* t)
 {
     if (!t) return;
     cudaSetDevice(t->device);
-    cudaStreamSynchronize(t->s_pre); cudaStreamSynchronize(t->s_main); cudaStreamSynchronize(t->s_out);
+    cudaStreamSynchronize(t->s_up); cudaStreamSynchronize(t->s_pyr); cudaStreamSynchronize(t->s_eig); cudaStreamSynchronize(t->s_main); cudaStreamSynchronize(t->s_out);
     for (int k = 0; k < 6; k++) {
         if (t->g_pyr[k]) cudaGraphExecDestroy(t->g_pyr[k]);
         if (t->g_eig[k]) cudaGraphExecDestroy(t->g_eig[k]);
@@ -387,7 +392,7 @@ void gf_tracker_destroy(gf_tracker* t)
     for (int i = 0; i < 2; i++) {
         cudaFree(t->d_depth[i]); cudaFree(t->d_eig[i]); cudaFree(t->d_out[i]); cudaFree(t->d_fp[i]);
         cudaFreeHost(t->h_out[i]); cudaFreeHost(t->h_fp[i]);
-        cudaEventDestroy(t->ev_pyr[i]); cudaEventDestroy(t->ev_eig[i]); cudaEventDestroy(t->ev_dep[i]);
+        cudaEventDestroy(t->ev_up[i]); cudaEventDestroy(t->ev_pyr[i]); cudaEventDestroy(t->ev_eig[i]); cudaEventDestroy(t->ev_dep[i]);
         cudaEventDestroy(t->ev_t0[i]); cudaEventDestroy(t->ev_out[i]);
     }
     cudaFree(t->d_cov); cudaFree(t->d_box);
@@ -398,7 +403,7 @@ void gf_tracker_destroy(gf_tracker* t)
     cudaFree(fa.kept_pts); cudaFree(fa.kept_ids); cudaFree(fa.kept_cnt); cudaFree(fa.kept_un); cudaFree(fa.pred_pts); cudaFree(fa.dbg);
     cudaFree(t->d_tmp_ids); cudaFree(t->d_tmp_xyz);
     cudaFreeHost(t->h_gray); cudaFreeHost(t->h_depth); cudaFreeHost(t->h_tmp_ids); cudaFreeHost(t->h_tmp_xyz);
-    cudaStreamDestroy(t->s_pre); cudaStreamDestroy(t->s_main); cudaStreamDestroy(t->s_out);
+    cudaStreamDestroy(t->s_up); cudaStreamDestroy(t->s_pyr); cudaStreamDestroy(t->s_eig); cudaStreamDestroy(t->s_main); cudaStreamDestroy(t->s_out);
     for (int i = 0; i < GF_FE_STAGES + 2; i++) cudaEventDestroy(t->ev_st[i]);
     cudaEventDestroy(t->ev_span0); cudaEventDestroy(t->ev_span1);
     delete t;
@@ -420,14 +425,14 @@ int gf_tracker_host_buffers(gf_tracker* t, uint8_t** gray, uint16_t** depth)
 static int body_pyr(gf_tracker* t, long long f)
 {
     const int es = (int)(f % 2);
-    GF_CUDA(cudaMemcpyAsync(t->d_fp[es], t->h_fp[es], sizeof(FrameParams), cudaMemcpyHostToDevice, t->s_pre));
-    return enqueue_pyramid(t->s_pre, t, (int)(f % 3));
+    GF_CUDA(cudaMemcpyAsync(t->d_fp[es], t->h_fp[es], sizeof(FrameParams), cudaMemcpyHostToDevice, t->s_pyr));
+    return enqueue_pyramid(t->s_pyr, t, (int)(f % 3));
 }
 
 static int body_eig(gf_tracker* t, long long f)
 {
     Pyramid Pc = make_pyr(t, (int)(f % 3));
-    return enqueue_min_eig(t->s_pre, Pc.lv[0], t->d_eig[f % 2], t->epitch, t->d_cov, t->d_box);
+    return enqueue_min_eig(t->s_eig, Pc.lv[0], t->d_eig[f % 2], t->epitch, t->d_cov, t->d_box);
 }
 
 static int body_dep1(gf_tracker* t, long long f, bool has_pred)
@@ -486,23 +491,26 @@ static int run_piece(gf_tracker* t, cudaStream_t s, cudaGraphExec_t* exec, int* 
     return GF_OK;
 }
 
-// Everything after the H2D (or D2D) copies of frame f have been enqueued on s_pre.
+// Everything after the H2D (or D2D) copies of frame f have been enqueued on s_up.
 static int enqueue_frame(gf_tracker* t, long long f, double time, bool depth_valid)
 {
     const int es = (int)(f % 2), key = (int)(f % 6), hp = t->has_pred ? 1 : 0;
     t->h_fp[es]->dt = time - t->prev_time;
     t->h_fp[es]->has_pred = hp;
     t->h_fp[es]->depth_valid = depth_valid ? 1 : 0;
-    GF_MARK(0, t->s_pre);   // end of upload
-    int rc = run_piece(t, t->s_pre, &t->g_pyr[key], &t->gk_pyr[key], [&] { return body_pyr(t, f); });
+    GF_MARK(0, t->s_up);   // end of upload
+    GF_CUDA(cudaEventRecord(t->ev_up[es], t->s_up));
+    GF_CUDA(cudaStreamWaitEvent(t->s_pyr, t->ev_up[es], 0));
+    GF_CUDA(cudaStreamWaitEvent(t->s_eig, t->ev_up[es], 0));
+    int rc = run_piece(t, t->s_pyr, &t->g_pyr[key], &t->gk_pyr[key], [&] { return body_pyr(t, f); });
     if (rc) return rc;
-    GF_CUDA(cudaEventRecord(t->ev_pyr[es], t->s_pre));
-    GF_MARK(1, t->s_pre);
-    GF_MARK(7, t->s_pre);
-    rc = run_piece(t, t->s_pre, &t->g_eig[key], &t->gk_eig[key], [&] { return body_eig(t, f); });
+    GF_CUDA(cudaEventRecord(t->ev_pyr[es], t->s_pyr));
+    GF_MARK(1, t->s_pyr);
+    GF_MARK(7, t->s_eig);
+    rc = run_piece(t, t->s_eig, &t->g_eig[key], &t->gk_eig[key], [&] { return body_eig(t, f); });
     if (rc) return rc;
-    GF_CUDA(cudaEventRecord(t->ev_eig[es], t->s_pre));
-    GF_MARK(8, t->s_pre);
+    GF_CUDA(cudaEventRecord(t->ev_eig[es], t->s_eig));
+    GF_MARK(8, t->s_eig);
     GF_CUDA(cudaStreamWaitEvent(t->s_main, t->ev_pyr[es], 0));
     rc = run_piece(t, t->s_main, &t->g_dep1[key][hp], &t->gk_dep1[key][hp], [&] { return body_dep1(t, f, hp != 0); });
     if (rc) return rc;
@@ -543,7 +551,7 @@ int gf_tracker_submit(gf_tracker* t, double time, const uint8_t* gray, size_t gr
     // (gf_tracker_host_buffers or any cudaHostAlloc/cudaHostRegister memory: keep them unchanged until the frame has
     // been collected); for pageable memory CUDA stages the data before cudaMemcpy2DAsync returns.
     const long long f = t->n_submitted;
-    cudaStream_t s = t->s_pre;
+    cudaStream_t s = t->s_up;
     GF_CUDA(cudaEventRecord(t->ev_t0[f % 2], s));
     GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[f % 3][0], t->lp[0], gray, gray_pitch, w, h, cudaMemcpyHostToDevice, s));
     if (depth)
@@ -559,7 +567,7 @@ int gf_tracker_submit_device(gf_tracker* t, double time, const void* d_gray, con
     GF_CUDA(cudaSetDevice(t->device));
     const int w = t->w, h = t->h;
     const long long f = t->n_submitted;
-    cudaStream_t s = t->s_pre;
+    cudaStream_t s = t->s_up;
     GF_CUDA(cudaEventRecord(t->ev_t0[f % 2], s));
     GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[f % 3][0], t->lp[0], d_gray, w, w, h, cudaMemcpyDeviceToDevice, s));
     if (d_depth)
@@ -678,7 +686,7 @@ int gf_tracker_timer_start(gf_tracker* t)
     if (!t) return set_err(GF_ERR_INVALID_ARG, "null tracker");
     if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "frame in flight");
     GF_CUDA(cudaSetDevice(t->device));
-    GF_CUDA(cudaEventRecord(t->ev_span0, t->s_pre));     // the first operation of the next frame follows on this stream
+    GF_CUDA(cudaEventRecord(t->ev_span0, t->s_up));      // the first operation of the next frame follows on this stream
     return GF_OK;
 }
 

@@ -6,7 +6,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import BaProblem, BaSummary, check
+from ._lib import BaPrior, BaProblem, BaSummary, check
 
 
 def double2vector(problem, R0_before, P0_before, use_imu=True):
@@ -43,6 +43,26 @@ class BundleAdjuster:
         s = BaSummary()
         check(self.L.gf_ba_solve(self._h, ctypes.byref(p), ctypes.byref(s)))
         return s.as_dict()
+
+    def marginalize_old(self, problem):
+        """MARGIN_OLD on the GPU (estimator.cpp:3334-3535): returns the ba_problem.Prior for the next window (block indices
+        already shifted by one frame).  last_marg_ms holds the CUDA-event time."""
+        from .ba_problem import Prior
+        dp = ctypes.POINTER(ctypes.c_double)
+        self.L.gf_ba_marginalize_old.argtypes = [ctypes.c_void_p, ctypes.POINTER(BaProblem), ctypes.POINTER(BaPrior), dp, dp, dp,
+                                                 ctypes.POINTER(ctypes.c_float)]
+        p = problem.struct()
+        cap = 16 * problem.n_frames + 8
+        x0 = np.zeros(cap); J = np.zeros(cap * cap); r = np.zeros(cap)
+        out = BaPrior(); ms = ctypes.c_float(0)
+        n = self.L.gf_ba_marginalize_old(self._h, ctypes.byref(p), ctypes.byref(out), x0.ctypes.data_as(dp), J.ctypes.data_as(dp),
+                                         r.ctypes.data_as(dp), ctypes.byref(ms))
+        if n <= 0:
+            check(n if n < 0 else -1)
+        self.last_marg_ms = float(ms.value)
+        nb = out.n_blocks
+        return Prior(list(out.block_kind)[:nb], list(out.block_index)[:nb], list(out.block_idx)[:nb], x0.copy(),
+                     J[:n * n].reshape(n, n).copy(), r[:n].copy())
 
     def solve_struct(self, p_struct):
         """Same, for a pre-built ctypes gf_ba_problem (avoids rebuilding it in timing loops)."""

@@ -270,6 +270,18 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* summary);
 /* Debug aid: SM cycles spent in each phase of the step kernel during the last solve (16 slots). */
 int gf_ba_debug_profile(gf_ba* s, long long* out32);
 
+/* MARGIN_OLD: the marginalisation at the end of Estimator::optimization() (estimator.cpp:3334-3535) with
+ * MarginalizationInfo::{preMarginalize, marginalize} (factor/marginalization_factor.cpp:115-308) on the GPU.
+ * Input: the window as it stands after the solve (same descriptor as gf_ba_solve; the constancy flags are ignored, as
+ * the reference's MarginalizationInfo ignores SetParameterBlockConstant).  Output: the prior for the NEXT window --
+ * kept blocks ordered pose[1..], speedbias[1..], ex_pose, td with frame indices already shifted by one, their
+ * linearisation points, J0 = sqrt(S) V^T (n x n row-major) and r0 = sqrt(S^-1) V^T b.
+ *   out_x0 / out_J / out_r: caller buffers of 16*n_frames+8, n*n, n doubles (n <= 16*n_frames+7); `out` points into them.
+ *   device_ms: nullable, CUDA-event time.
+ * Returns n > 0, or a negative gf error code.  Wheel / plane / GNSS factors of frame 0 are not part of the prior yet. */
+int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r,
+                          float* device_ms);
+
 /* Estimator::double2vector (estimator.cpp:2440-2494), the state part: host-only glue that maps the solved para_* arrays
  * back to Rs / Ps / Vs, rotating the window about z and shifting it so that frame 0 keeps the yaw and position it had
  * before the solve (Euler-singularity branch included).
