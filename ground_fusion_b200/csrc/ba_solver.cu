@@ -1012,14 +1012,20 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
 // as a similarity A <- J^T A J with J = product of the plane rotations: the matrix splits into disjoint 2x2 blocks
 // (row pair x column pair), each updated independently from the two rotations involved.  V accumulates the rotations
 // (columns = eigenvectors), w = diagonal at convergence (off-norm <= 1e-30 * diag-norm, like the oracle's sweep test).
-__global__ void __launch_bounds__(1024) k_jacobi_eig(double* A, double* V, double* w, int n, int* sweeps_out)
+__global__ void __launch_bounds__(1024) k_jacobi_eig(double* Ag, double* Vg, double* w, int n, int* sweeps_out, int in_smem)
 {
-    extern __shared__ double jsm[];           // c[np/2], s[np/2]; then int pr[np/2], qr[np/2]
+    extern __shared__ double jsm[];           // c[np/2], s[np/2]; then int pr[np/2], qr[np/2]; then (in_smem) A[n*n], V[n*n]
     __shared__ double sred[32];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int np = (n + 1) & ~1, hp = np / 2;
     double* cs_c = jsm; double* cs_s = jsm + hp;
     int* pp = reinterpret_cast<int*>(jsm + 2 * hp); int* qq = pp + hp;
+    // small matrices (the reduced system of the marginalisation) live in shared memory for the whole decomposition
+    double* A = Ag; double* V = Vg;
+    if (in_smem) {
+        A = jsm + 2 * hp + ((2 * hp * (int)sizeof(int) + 7) / 8); V = A + (size_t)n * n;
+        for (int e = tid; e < n * n; e += nt) A[e] = Ag[e];
+    }
     for (int e = tid; e < n * n; e += nt) V[e] = (e / n == e % n) ? 1.0 : 0.0;
     __syncthreads();
     int sweep = 0;
@@ -1110,6 +1116,7 @@ __global__ void __launch_bounds__(1024) k_jacobi_eig(double* A, double* V, doubl
         }
     }
     for (int i = tid; i < n; i += nt) w[i] = A[(size_t)i * n + i];
+    if (in_smem) for (int e = tid; e < n * n; e += nt) Vg[e] = V[e];
     if (tid == 0 && sweeps_out) *sweeps_out = sweep;
 }
 
@@ -1167,6 +1174,80 @@ __global__ void k_marg_reduce(MargDev q)   // A = Arr - Arm Amm_inv Amr, b = brr
     }
     if (e < n) { double v = q.b[m + e]; for (int k = 0; k < m; k++) v -= q.T[(size_t)e * m + k] * q.b[k]; q.br[e] = v; }
 }
+// ---- structured path: Amm = [[C, B], [B^T, D]] with D the diagonal landmark block --------------------------------------
+// When Amm - eps I is positive definite every eigenvalue passes the reference's eps test, the eigen-truncated inverse IS
+// the inverse, and Arr - Arm Amm^-1 Amr is the ordinary two-stage Schur complement: landmarks (1x1 pivots) first, then
+// the c x c block of pose0 / speedbias0.  Q is the (c+n) x (c+n) system left after the landmarks, order [c | kept].
+// flag[0] is set when the positive-definiteness test fails (the generic Jacobi path is run instead).
+__global__ void k_marg_lm_elim(MargDev q, int c, double* Q, double* qb, double* Ceps, int* flag)
+{
+    const int R = c + q.n, m = q.m, N = q.N;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    auto gi = [&](int i) { return i < c ? i : m + (i - c); };       // compact index -> column of A
+    if (e < R * R) {
+        const int i = e / R, j = e - i * R, ai = gi(i), aj = gi(j);
+        double v = 0.5 * (q.A[(size_t)ai * N + aj] + q.A[(size_t)aj * N + ai]), ve = v;
+        for (int l = c; l < m; l++) {
+            const double d = q.A[(size_t)l * N + l];
+            const double t = 0.5 * (q.A[(size_t)ai * N + l] + q.A[(size_t)l * N + ai]) * 0.5 * (q.A[(size_t)l * N + aj] + q.A[(size_t)aj * N + l]);
+            v -= t / d;
+            if (i < c && j < c) ve -= t / (d - 1e-8);
+        }
+        Q[e] = v;
+        if (i < c && j < c) Ceps[i * c + j] = ve - (i == j ? 1e-8 : 0.0);
+    }
+    if (e < R) {
+        const int ai = gi(e);
+        double v = q.b[ai];
+        for (int l = c; l < m; l++) v -= 0.5 * (q.A[(size_t)ai * N + l] + q.A[(size_t)l * N + ai]) * q.b[l] / q.A[(size_t)l * N + l];
+        qb[e] = v;
+    }
+    if (e >= c && e < m && !(q.A[(size_t)e * N + e] - 1e-8 > 0.0)) atomicExch(flag, 1);
+}
+// single CTA: Cholesky of the c x c block (and of its eps-shifted twin for the test), X = S^-1 [Q_cr | q_c], reduced system
+__global__ void __launch_bounds__(256) k_marg_c_elim(MargDev q, int c, const double* Q, const double* qb, const double* Ceps, int* flag)
+{
+    __shared__ double Lc[15 * 15], Le[15 * 15];
+    __shared__ double X[15 * 128];            // c x (n + 1), n <= 127
+    const int tid = threadIdx.x, n = q.n, R = c + n;
+    if (tid == 0) {
+        bool ok = true;
+        for (int pass = 0; pass < 2 && ok; pass++) {
+            double* L = pass == 0 ? Lc : Le;
+            for (int i = 0; i < c; i++) for (int j = 0; j < c; j++) L[i * c + j] = pass == 0 ? Q[(size_t)i * R + j] : Ceps[i * c + j];
+            for (int j = 0; j < c && ok; j++) {
+                double d = L[j * c + j];
+                for (int k = 0; k < j; k++) d -= L[j * c + k] * L[j * c + k];
+                if (!(d > 0.0)) { ok = false; break; }
+                d = sqrt(d); L[j * c + j] = d;
+                for (int i = j + 1; i < c; i++) { double t = L[i * c + j]; for (int k = 0; k < j; k++) t -= L[i * c + k] * L[j * c + k]; L[i * c + j] = t / d; }
+            }
+        }
+        if (!ok) atomicExch(flag, 1);
+    }
+    __syncthreads();
+    if (*(volatile int*)flag) return;
+    for (int col = tid; col <= n; col += blockDim.x) {          // S x = rhs for the n kept columns and the rhs vector
+        double y[15];
+        for (int i = 0; i < c; i++) { double t = col < n ? Q[(size_t)i * R + c + col] : qb[i]; for (int k = 0; k < i; k++) t -= Lc[i * c + k] * y[k]; y[i] = t / Lc[i * c + i]; }
+        for (int i = c - 1; i >= 0; i--) { double t = y[i]; for (int k = i + 1; k < c; k++) t -= Lc[k * c + i] * y[k]; y[i] = t / Lc[i * c + i]; }
+        for (int i = 0; i < c; i++) X[i * (n + 1) + col] = y[i];
+    }
+    __syncthreads();
+    for (int e = tid; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e - i * n;
+        if (j > i) continue;
+        double v = Q[(size_t)(c + i) * R + c + j];
+        for (int k = 0; k < c; k++) v -= Q[(size_t)(c + i) * R + k] * X[k * (n + 1) + j];
+        q.Ar[(size_t)i * n + j] = v; q.Ar[(size_t)j * n + i] = v;
+    }
+    for (int i = tid; i < n; i += blockDim.x) {
+        double v = qb[c + i];
+        for (int k = 0; k < c; k++) v -= Q[(size_t)(c + i) * R + k] * X[k * (n + 1) + n];
+        q.br[i] = v;
+    }
+}
+
 __global__ void k_marg_out(MargDev q)      // J0 = sqrt(S) V^T, r0 = sqrt(S^-1) V^T b     (:294-302)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x, n = q.n;
@@ -1226,6 +1307,7 @@ int gf_ba_create(gf_ba** out, int device)
     GF_CUDA(cudaStreamCreateWithFlags(&s->s, cudaStreamNonBlocking));
     GF_CUDA(cudaEventCreate(&s->e0)); GF_CUDA(cudaEventCreate(&s->e1));
     GF_CUDA(cudaFuncSetAttribute(k_ba_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GF_CUDA(cudaFuncSetAttribute(k_jacobi_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     *out = s;
     return GF_OK;
 }
@@ -1514,7 +1596,8 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     const size_t o_sq = take(sizeof(double) * 225), o_Hp = take(sizeof(double) * NN), o_a0 = take(sizeof(double) * acc_size(N, 0)), o_st = take(sizeof(BaState)),
                  o_A = take(sizeof(double) * NN), o_b = take(sizeof(double) * N), o_Amm = take(sizeof(double) * mm), o_Vm = take(sizeof(double) * mm), o_wm = take(sizeof(double) * m),
                  o_Ainv = take(sizeof(double) * mm), o_T = take(sizeof(double) * (size_t)n * m), o_Ar = take(sizeof(double) * nn), o_Vr = take(sizeof(double) * nn),
-                 o_wr = take(sizeof(double) * n), o_br = take(sizeof(double) * n), o_J0 = take(sizeof(double) * nn), o_r0 = take(sizeof(double) * n), o_sw = take(sizeof(int) * 4);
+                 o_wr = take(sizeof(double) * n), o_br = take(sizeof(double) * n), o_J0 = take(sizeof(double) * nn), o_r0 = take(sizeof(double) * n), o_sw = take(sizeof(int) * 4),
+                 o_Q = take(sizeof(double) * (size_t)(15 + n) * (15 + n)), o_qb = take(sizeof(double) * (15 + n)), o_ce = take(sizeof(double) * 225);
     int rc = ensure(s, off);
     if (rc) return rc;
     char* hb = (char*)s->hbuf; char* db = (char*)s->dbuf;
@@ -1565,13 +1648,29 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     const int eval_blocks = n_work + d.n_imu + (pn ? 1 : 0);
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, sizeof(double) * 2 * (size_t)pn, st>>>(d, 0); GF_LAUNCHED(); }
     k_marg_pack<<<(int)((NN + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
-    k_marg_amm<<<(int)((mm + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
-    auto jac_smem = [](int nn_) { int hp = ((nn_ + 1) & ~1) / 2; return (size_t)hp * (2 * sizeof(double) + 2 * sizeof(int)); };
-    k_jacobi_eig<<<1, 1024, jac_smem(m), st>>>(q.Amm, q.Vm, q.wm, m, (int*)(db + o_sw)); GF_LAUNCHED();
-    k_marg_ainv<<<(int)((mm + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
-    k_marg_T<<<(int)(((size_t)n * m + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
-    k_marg_reduce<<<(int)((nn + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
-    k_jacobi_eig<<<1, 1024, jac_smem(n), st>>>(q.Ar, q.Vr, q.wr, n, (int*)(db + o_sw) + 1); GF_LAUNCHED();
+    auto jac_smem = [](int nn_, bool in_smem) { int hp = ((nn_ + 1) & ~1) / 2; size_t b = (size_t)hp * (2 * sizeof(double) + 2 * sizeof(int)) + 8; return b + (in_smem ? 2 * sizeof(double) * (size_t)nn_ * nn_ : 0); };
+    const int cdim = use_sb ? 15 : 6, Rdim = cdim + n;
+    int* d_flag = (int*)(db + o_sw) + 2;
+    bool generic = n > 127;                                   // k_marg_c_elim's shared buffer
+    if (!generic) {
+        // regular case: Amm - eps I positive definite => eigen-truncated inverse == inverse => two-stage Schur complement
+        GF_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+        k_marg_lm_elim<<<(Rdim * Rdim + 255) / 256, 256, 0, st>>>(q, cdim, (double*)(db + o_Q), (double*)(db + o_qb), (double*)(db + o_ce), d_flag); GF_LAUNCHED();
+        k_marg_c_elim<<<1, 256, 0, st>>>(q, cdim, (const double*)(db + o_Q), (const double*)(db + o_qb), (const double*)(db + o_ce), d_flag); GF_LAUNCHED();
+        int* h_flag = (int*)(hb + o_sw);
+        GF_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GF_CUDA(cudaStreamSynchronize(st));
+        generic = *h_flag != 0;
+    }
+    if (generic) {   // some eigenvalue of Amm may be below eps: the reference's eigen-truncated inverse, literally
+        k_marg_amm<<<(int)((mm + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+        k_jacobi_eig<<<1, 1024, jac_smem(m, false), st>>>(q.Amm, q.Vm, q.wm, m, (int*)(db + o_sw), 0); GF_LAUNCHED();
+        k_marg_ainv<<<(int)((mm + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+        k_marg_T<<<(int)(((size_t)n * m + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+        k_marg_reduce<<<(int)((nn + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
+    }
+    const bool r_in_smem = jac_smem(n, true) <= 200 * 1024;
+    k_jacobi_eig<<<1, 1024, jac_smem(n, r_in_smem), st>>>(q.Ar, q.Vr, q.wr, n, (int*)(db + o_sw) + 1, r_in_smem ? 1 : 0); GF_LAUNCHED();
     k_marg_out<<<(int)((nn + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpyAsync(hb + o_J0, db + o_J0, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));

@@ -1,3 +1,11 @@
-timeout 600 python -m pytest tests/test_fe_gpu.py -x -q 2>&1 | tail -3
-timeout 400 python bench.py 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench15.json; python -c "
-import json; d=json.load(open('gpurun_out/bench15.json')); print(d['value'], d['e2e']['value'], d['device_ms_per_step'], d['device_ms_per_step_e2e'], d['cpu_baseline']['value']); print(d['stage_ms']); print(d['ba']['marginalize_old'])"
+timeout 600 python -m pytest tests/test_ba_gpu.py -x -q -s 2>&1 | tail -6
+timeout 200 python - <<'PY'
+import sys, time; sys.path.insert(0, '.')
+from ground_fusion_b200.estimator import BundleAdjuster
+from ground_fusion_b200.synth_ba import make_window
+ba = BundleAdjuster(0)
+pb, _ = make_window(seed=100)
+ba.optimization(pb)
+for k in range(4):
+    t = time.perf_counter(); pr = ba.marginalize_old(pb); print("marg device ms %.3f wall ms %.3f n %d" % (ba.last_marg_ms, 1e3 * (time.perf_counter() - t), pr.n))
+PY
