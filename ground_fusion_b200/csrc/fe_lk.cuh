@@ -1,4 +1,4 @@
-// fe_lk.cuh -- pyramidal Lucas-Kanade, one warp per point, bit-exact with OpenCV 4.13's SSE path.
+// fe_lk.cuh -- pyramidal Lucas-Kanade, one CTA of 8 warps per point, bit-exact with OpenCV 4.13's SSE path.
 //
 // Replaces the two cv::calcOpticalFlowPyrLK calls of FeatureTracker::trackImage
 // (reference vins_estimator/src/featureTracker/feature_tracker.cpp:118-153).  The arithmetic follows
@@ -10,7 +10,7 @@
 //   b1/b2:       4 chains of pmaddwd pairs (col k, col k+4 | k+8, k+12) + 1 tail chain,
 //                result = tail + ((c0+c2) + (c1+c3))
 // The order of the float additions is what makes the result bit-exact, and it is inherently sequential.
-// Everything around it is organised to keep those chains short in instructions: the 32-lane parallel phase
+// Everything around it is organised to keep those chains short in instructions: the parallel phase (all 256 threads)
 // produces the *terms* (exact integers converted to float, pair sums for the pmaddwd chains) already laid
 // out in chain order in shared memory, so that the chain phase is one predicated LDS+FADD loop of 105 steps
 // run by 15 (A) or 10 (b) lanes.  Compile with -fmad=false: every float op must round on its own.

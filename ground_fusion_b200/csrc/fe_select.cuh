@@ -1,12 +1,11 @@
 // fe_select.cuh -- the order-dependent part of the front end, kept on the device:
 //   k_compact_setmask : reduceVector x4 + track_cnt++ + setMask   (feature_tracker.cpp:170-179, 56-83)
-//   k_mask_disks      : the mask goodFeaturesToTrack sees          (cv::circle == integer disk d^2<=r^2)
+//   (mask)            : the mask goodFeaturesToTrack sees (cv::circle == integer disk d^2<=r^2 around the kept
+//                       features) is never materialised: tiles test pixels against the kept features in reach
 //   k_eig_max / k_candidates : minMaxLoc(masked) -> threshold -> 3x3 dilate -> local maxima
-//   k_nms_round / k_nms_finish : cv::goodFeaturesToTrack's greedy min-distance pass, parallelised by
-//                       rounds ("accept a candidate once every higher-ranked neighbour within r is
-//                       rejected; reject it once any neighbour within r is accepted") - the accepted set
-//                       is exactly the sequential greedy's; the maxCorners cap = top-K of that set by rank
-//   k_finalize        : top-K by (eig desc, address desc), addPoints, undistortedPts, ptsVelocity, depth
+//   k_select_finalize : cv::goodFeaturesToTrack's greedy min-distance pass by cell-head rounds (the accepted set is
+//                       exactly the sequential greedy's; the maxCorners cap = top-K of that set by rank), then
+//                       addPoints, undistortedPts, ptsVelocity, depth and the state of the next frame
 // Arithmetic and ordering follow oracle/fe_cv_restate.c and oracle/fe_oracle.py.
 #pragma once
 #include "fe_sort.cuh"
