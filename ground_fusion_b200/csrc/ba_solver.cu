@@ -1511,8 +1511,9 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
  * inverse (eps 1e-8) and the result is re-factored into J0 = sqrt(S) V^T, r0 = sqrt(S^-1) V^T b, exactly the reference's
  * two SelfAdjointEigenSolver calls (here: parallel-ordered Jacobi).  Kept blocks are ordered pose[1..], speedbias[1..],
  * ex_pose, td and their indices are already shifted by one frame (addr_shift, estimator.cpp:3500-3534).
- * Wheel / plane / GNSS factors of frame 0 are not included (as in the oracle).  out_x0 / out_J / out_r must hold
- * 16*n_frames+8, n*n, n doubles.  Returns n (> 0) or a negative error code. */
+ * The WheelFactor(0->1) joins when the window has wheel factors (its extrinsic / sx / sy / sw / time offset become kept
+ * blocks); plane / GNSS factors are not implemented.  out_x0 / out_J / out_r must hold 16*n_frames+19, n*n, n doubles.
+ * Returns n (> 0) or a negative error code. */
 int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r, float* device_ms)
 {
     if (!s || !p || !out || !out_x0 || !out_J || !out_r) return set_err(GF_ERR_INVALID_ARG, "null argument");
@@ -1538,7 +1539,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
         vis0.push_back(f);
     }
     const int m = pos;
-    bool used_pose[MAXF] = {}, used_sb[MAXF] = {}, used_ex = false, used_td = false;
+    bool used_pose[MAXF] = {}, used_sb[MAXF] = {}, used_ex = false, used_td = false, used_exw = false, used_ix[3] = {false, false, false}, used_tdw = false;
     const gf_ba_prior* pr = (p->prior && p->prior->n > 0) ? p->prior : nullptr;
     if (pr) {
         if (pr->n_blocks > 64) return set_err(GF_ERR_CAPACITY, "more than 64 prior blocks");
@@ -1547,19 +1548,30 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
             if (k == GF_BA_BLOCK_POSE || k == GF_BA_BLOCK_SPEEDBIAS) { if (i < 0 || i >= F) return set_err(GF_ERR_INVALID_ARG, "prior block index out of range"); (k == GF_BA_BLOCK_POSE ? used_pose : used_sb)[i] = true; }
             else if (k == GF_BA_BLOCK_EX_POSE) used_ex = true;
             else if (k == GF_BA_BLOCK_TD) used_td = true;
-            else return set_err(GF_ERR_UNSUPPORTED, "marginalisation of a prior with wheel blocks is not implemented");
+            else if (k == GF_BA_BLOCK_EX_WHEEL) used_exw = true;
+            else if (k >= GF_BA_BLOCK_SX && k <= GF_BA_BLOCK_SW) used_ix[k - GF_BA_BLOCK_SX] = true;
+            else if (k == GF_BA_BLOCK_TD_WHEEL) used_tdw = true;
+            else return set_err(GF_ERR_INVALID_ARG, "unknown prior block kind");
         }
     }
     const gf_ba_imu_factor* imu01 = nullptr;
     for (int k = 0; k < p->n_imu; k++) if (p->imu[k].i == 0 && p->imu[k].j == 1 && p->imu[k].sum_dt < 10.0) { imu01 = &p->imu[k]; used_pose[1] = true; used_sb[1] = true; }
     for (const auto& f : vis0) { used_pose[f.imu_j] = true; used_ex = true; used_td = true; }
+    // WheelFactor(pre_integrations_wheel[1]) with para_Pose[0] dropped (estimator.cpp:3367-3377)
+    const gf_ba_wheel_factor* wheel01 = nullptr;
+    if (p->n_wheel > 0 && (!p->wheel || !p->para_ex_wheel || !p->para_ix_wheel || !p->para_td_wheel)) return set_err(GF_ERR_INVALID_ARG, "wheel factors without their parameter blocks");
+    for (int k = 0; k < p->n_wheel; k++) if (p->wheel[k].i == 0 && p->wheel[k].j == 1 && p->wheel[k].sum_dt < 10.0) { wheel01 = &p->wheel[k]; used_pose[1] = true; used_exw = true; used_ix[0] = used_ix[1] = used_ix[2] = true; used_tdw = true; }
+    if ((used_exw || used_ix[0] || used_ix[1] || used_ix[2] || used_tdw) && (!p->para_ex_wheel || !p->para_ix_wheel || !p->para_td_wheel)) return set_err(GF_ERR_INVALID_ARG, "prior on wheel blocks without the wheel parameter blocks");
     for (int f = 1; f < F; f++) if (used_pose[f]) { d.col_pose[f] = pos; pos += 6; }
     for (int f = 1; f < F; f++) if (used_sb[f] && use_sb) { d.col_sb[f] = pos; pos += 9; }
     if (used_ex) { d.col_ex = pos; pos += 6; }
     if (used_td) { d.col_td = pos; pos += 1; }
+    if (used_exw) { d.col_exw = pos; pos += 6; }
+    for (int k = 0; k < 3; k++) if (used_ix[k]) d.col_ix[k] = pos++;
+    if (used_tdw) d.col_tdw = pos++;
     const int N = pos, n = N - m;
     if (n <= 0) return set_err(GF_ERR_INVALID_ARG, "nothing is kept by the marginalisation");
-    d.nc = N; d.L = 0; d.n = N; d.n_vis = (int)vis0.size(); d.n_imu = imu01 ? 1 : 0; d.n_wheel = 0;
+    d.nc = N; d.L = 0; d.n = N; d.n_vis = (int)vis0.size(); d.n_imu = imu01 ? 1 : 0; d.n_wheel = wheel01 ? 1 : 0;
     // ---- visual factors by pose pair (0, j), cut into chunks ----
     std::vector<int> cnt(F, 0), start(F + 1, 0);
     for (const auto& f : vis0) cnt[f.imu_j]++;
@@ -1577,8 +1589,9 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
         for (int b = 0; b < pr->n_blocks; b++) {
             const int kind = pr->block_kind[b], idx = pr->block_index[b];
             d.pkind[b] = kind; d.pindex[b] = idx; d.pidx[b] = pr->block_idx[b]; d.pxoff[b] = (int)px0_len;
-            const int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1, ls = gs == 7 ? 6 : gs;
-            const int lc = kind == GF_BA_BLOCK_POSE ? d.col_pose[idx] : kind == GF_BA_BLOCK_SPEEDBIAS ? d.col_sb[idx] : kind == GF_BA_BLOCK_EX_POSE ? d.col_ex : d.col_td;
+            const int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1, ls = gs == 7 ? 6 : gs;
+            const int lc = kind == GF_BA_BLOCK_POSE ? d.col_pose[idx] : kind == GF_BA_BLOCK_SPEEDBIAS ? d.col_sb[idx] : kind == GF_BA_BLOCK_EX_POSE ? d.col_ex : kind == GF_BA_BLOCK_TD ? d.col_td
+                           : kind == GF_BA_BLOCK_EX_WHEEL ? d.col_exw : kind == GF_BA_BLOCK_TD_WHEEL ? d.col_tdw : d.col_ix[kind - GF_BA_BLOCK_SX];
             if (lc >= 0) for (int k = 0; k < ls; k++) pcol[pr->block_idx[b] + k] = lc + k;
             px0_len += gs;
         }
@@ -1588,7 +1601,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
     const size_t nv = vis0.size();
-    const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (nv ? nv : 1)), o_imu = take(sizeof(gf_ba_imu_factor)),
+    const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (nv ? nv : 1)), o_imu = take(sizeof(gf_ba_imu_factor)), o_whl = take(sizeof(gf_ba_wheel_factor)),
                  o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)), o_cf = take(sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1)),
                  o_pJ = take(sizeof(double) * (size_t)pn * pn), o_pr0 = take(sizeof(double) * pn), o_px0 = take(sizeof(double) * px0_len), o_pcol = take(sizeof(int) * (size_t)(pn > 0 ? pn : 1));
     const size_t upload_bytes = off;
@@ -1608,6 +1621,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     memcpy(hX + X_EX, p->para_ex_pose, sizeof(double) * 7);
     hX[X_TD] = p->para_td[0];
     hX[X_EXW + 6] = 1.0; hX[X_IX] = hX[X_IX + 1] = hX[X_IX + 2] = 1.0;
+    if (p->para_ex_wheel && p->para_ix_wheel && p->para_td_wheel) { memcpy(hX + X_EXW, p->para_ex_wheel, sizeof(double) * 7); memcpy(hX + X_IX, p->para_ix_wheel, sizeof(double) * 3); hX[X_TDW] = p->para_td_wheel[0]; }
     memcpy(hX + X_FEAT, p->para_feature, sizeof(double) * nfeat);
     {
         gf_ba_visual_factor* hv = (gf_ba_visual_factor*)(hb + o_vis);
@@ -1615,6 +1629,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
         for (const auto& f : vis0) hv[fill[f.imu_j]++] = f;
     }
     if (imu01) memcpy(hb + o_imu, imu01, sizeof(gf_ba_imu_factor));
+    if (wheel01) memcpy(hb + o_whl, wheel01, sizeof(gf_ba_wheel_factor));
     memcpy(hb + o_ps, work_start.data(), sizeof(int) * (n_work + 1));
     if (n_work) memcpy(hb + o_pij, work_ij.data(), sizeof(int) * 2 * n_work);
     memcpy(hb + o_cf, lm_col.data(), sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1));
@@ -1626,7 +1641,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     }
     d.X = (double*)(db + o_X); d.Xc = d.X;
     d.vis = (const gf_ba_visual_factor*)(db + o_vis); d.pair_start = (const int*)(db + o_ps); d.pair_ij = (const int*)(db + o_pij);
-    d.imu = (const gf_ba_imu_factor*)(db + o_imu); d.imu_sqrt = (double*)(db + o_sq); d.wheel = nullptr;
+    d.imu = (const gf_ba_imu_factor*)(db + o_imu); d.imu_sqrt = (double*)(db + o_sq); d.wheel = (const gf_ba_wheel_factor*)(db + o_whl);
     d.col_feat = (const int*)(db + o_cf);
     d.pJ = (const double*)(db + o_pJ); d.pr0 = (const double*)(db + o_pr0); d.px0 = (const double*)(db + o_px0); d.pcol = (const int*)(db + o_pcol);
     d.Hp = (double*)(db + o_Hp); d.acc[0] = (double*)(db + o_a0); d.acc[1] = d.acc[0];
@@ -1645,7 +1660,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     GF_CUDA(cudaMemsetAsync(db + o_st, 0, sizeof(BaState), st));
     k_ba_setup<<<d.n_imu + 1, 128, 0, st>>>(d); GF_LAUNCHED();        // sqrt_info of IMU(0->1), Hp = 0, state: linearise into buffer 0
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
-    const int eval_blocks = n_work + d.n_imu + (pn ? 1 : 0);
+    const int eval_blocks = n_work + d.n_imu + d.n_wheel + (pn ? 1 : 0);
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, sizeof(double) * 2 * (size_t)pn, st>>>(d, 0); GF_LAUNCHED(); }
     k_marg_pack<<<(int)((NN + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
     auto jac_smem = [](int nn_, bool in_smem) { int hp = ((nn_ + 1) & ~1) / 2; size_t b = (size_t)hp * (2 * sizeof(double) + 2 * sizeof(int)) + 8; return b + (in_smem ? 2 * sizeof(double) * (size_t)nn_ * nn_ : 0); };
@@ -1690,6 +1705,9 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     for (int f = 1; f < F; f++) if (d.col_sb[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SPEEDBIAS; out->block_index[nb] = f - 1; out->block_idx[nb] = d.col_sb[f] - m; memcpy(xp, p->para_speed_bias + 9 * f, 72); xp += 9; nb++; }
     if (d.col_ex >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_POSE; out->block_index[nb] = 0; out->block_idx[nb] = d.col_ex - m; memcpy(xp, p->para_ex_pose, 56); xp += 7; nb++; }
     if (d.col_td >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD; out->block_index[nb] = 0; out->block_idx[nb] = d.col_td - m; xp[0] = p->para_td[0]; xp += 1; nb++; }
+    if (d.col_exw >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_WHEEL; out->block_index[nb] = 0; out->block_idx[nb] = d.col_exw - m; memcpy(xp, p->para_ex_wheel, 56); xp += 7; nb++; }
+    for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SX + k; out->block_index[nb] = 0; out->block_idx[nb] = d.col_ix[k] - m; xp[0] = p->para_ix_wheel[k]; xp += 1; nb++; }
+    if (d.col_tdw >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD_WHEEL; out->block_index[nb] = 0; out->block_idx[nb] = d.col_tdw - m; xp[0] = p->para_td_wheel[0]; xp += 1; nb++; }
     out->n_blocks = nb; out->x0 = out_x0; out->linearized_jacobians = out_J; out->linearized_residuals = out_r;
     return n;
 }

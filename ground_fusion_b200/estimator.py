@@ -52,7 +52,7 @@ class BundleAdjuster:
         self.L.gf_ba_marginalize_old.argtypes = [ctypes.c_void_p, ctypes.POINTER(BaProblem), ctypes.POINTER(BaPrior), dp, dp, dp,
                                                  ctypes.POINTER(ctypes.c_float)]
         p = problem.struct()
-        cap = 16 * problem.n_frames + 8
+        cap = 16 * problem.n_frames + 24
         x0 = np.zeros(cap); J = np.zeros(cap * cap); r = np.zeros(cap)
         out = BaPrior(); ms = ctypes.c_float(0)
         n = self.L.gf_ba_marginalize_old(self._h, ctypes.byref(p), ctypes.byref(out), x0.ctypes.data_as(dp), J.ctypes.data_as(dp),

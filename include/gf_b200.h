@@ -276,9 +276,10 @@ int gf_ba_debug_profile(gf_ba* s, long long* out32);
  * the reference's MarginalizationInfo ignores SetParameterBlockConstant).  Output: the prior for the NEXT window --
  * kept blocks ordered pose[1..], speedbias[1..], ex_pose, td with frame indices already shifted by one, their
  * linearisation points, J0 = sqrt(S) V^T (n x n row-major) and r0 = sqrt(S^-1) V^T b.
- *   out_x0 / out_J / out_r: caller buffers of 16*n_frames+8, n*n, n doubles (n <= 16*n_frames+7); `out` points into them.
+ *   out_x0 / out_J / out_r: caller buffers of 16*n_frames+19, n*n, n doubles (n <= 16*n_frames+17); `out` points into them.
+ *   With wheel factors the WheelFactor(0->1) joins and the wheel extrinsic, sx, sy, sw, wheel time offset follow as kept blocks.
  *   device_ms: nullable, CUDA-event time.
- * Returns n > 0, or a negative gf error code.  Wheel / plane / GNSS factors of frame 0 are not part of the prior yet. */
+ * Returns n > 0, or a negative gf error code.  Plane / GNSS factors of frame 0 are not part of the prior. */
 int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r,
                           float* device_ms);
 

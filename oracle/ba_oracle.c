@@ -1157,7 +1157,8 @@ GFO void gfo_ba_plus(const gf_ba_problem* p, const double* delta)
  * every visual factor whose landmark starts in frame 0 (drop pose0 and the landmark).  Kept blocks are ordered
  * pose[1..], speedbias[1..], ex_pose, td (the reference orders by heap address; only J0^T J0 and J0^T r0 are
  * order-independent and those are what the tests compare).  After addr_shift the kept pose/speedbias indices are
- * decremented by one.  out_x0 / out_J / out_r must hold 7F+9F+8, n*n, n doubles. */
+ * decremented by one.  With wheel factors the WheelFactor(0->1) joins (pose 0 dropped) and the wheel extrinsic, sx, sy,
+ * sw and the wheel time offset follow as kept blocks.  out_x0 / out_J / out_r must hold 16F+19, n*n, n doubles. */
 GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r)
 {
     const int F = p->n_frames;
@@ -1173,22 +1174,30 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
     for (int v = 0; v < p->n_visual; v++) if (p->visual[v].imu_i == 0 && lm_col[p->visual[v].feature] < 0) lm_col[p->visual[v].feature] = pos++;
     const int m = pos;
     /* kept blocks: every other block the factors touch */
-    int used_pose[GF_BA_MAX_FRAMES] = {0}, used_sb[GF_BA_MAX_FRAMES] = {0}, used_ex = 0, used_td = 0;
+    int used_pose[GF_BA_MAX_FRAMES] = {0}, used_sb[GF_BA_MAX_FRAMES] = {0}, used_ex = 0, used_td = 0, used_exw = 0, used_ix[3] = {0, 0, 0}, used_tdw = 0;
     if (p->prior && p->prior->n > 0)
         for (int b = 0; b < p->prior->n_blocks; b++) {
             int k = p->prior->block_kind[b], i = p->prior->block_index[b];
             if (k == GF_BA_BLOCK_POSE) used_pose[i] = 1; else if (k == GF_BA_BLOCK_SPEEDBIAS) used_sb[i] = 1;
             else if (k == GF_BA_BLOCK_EX_POSE) used_ex = 1; else if (k == GF_BA_BLOCK_TD) used_td = 1;
+            else if (k == GF_BA_BLOCK_EX_WHEEL) used_exw = 1; else if (k >= GF_BA_BLOCK_SX && k <= GF_BA_BLOCK_SW) used_ix[k - GF_BA_BLOCK_SX] = 1;
+            else if (k == GF_BA_BLOCK_TD_WHEEL) used_tdw = 1;
         }
     int have_imu01 = 0; const gf_ba_imu_factor* imu01 = NULL;
     for (int k = 0; k < p->n_imu; k++) if (p->imu[k].i == 0 && p->imu[k].j == 1 && p->imu[k].sum_dt < 10.0) { have_imu01 = 1; imu01 = &p->imu[k]; used_pose[1] = 1; used_sb[1] = 1; }
     for (int v = 0; v < p->n_visual; v++) if (p->visual[v].imu_i == 0) { used_pose[p->visual[v].imu_j] = 1; used_ex = 1; used_td = 1; }
-    int col_pose[GF_BA_MAX_FRAMES], col_sb[GF_BA_MAX_FRAMES], col_ex = -1, col_td = -1;
+    /* WheelFactor(pre_integrations_wheel[1]) with para_Pose[0] dropped (estimator.cpp:3367-3377) */
+    const gf_ba_wheel_factor* wheel01 = NULL;
+    for (int k = 0; k < p->n_wheel; k++) if (p->wheel[k].i == 0 && p->wheel[k].j == 1 && p->wheel[k].sum_dt < 10.0) { wheel01 = &p->wheel[k]; used_pose[1] = 1; used_exw = 1; used_ix[0] = used_ix[1] = used_ix[2] = 1; used_tdw = 1; }
+    int col_pose[GF_BA_MAX_FRAMES], col_sb[GF_BA_MAX_FRAMES], col_ex = -1, col_td = -1, col_exw = -1, col_ix[3] = {-1, -1, -1}, col_tdw = -1;
     col_pose[0] = col_p0; col_sb[0] = col_sb0;
     for (int f = 1; f < F; f++) { col_pose[f] = -1; if (used_pose[f]) { col_pose[f] = pos; pos += 6; } }
     for (int f = 1; f < F; f++) { col_sb[f] = -1; if (used_sb[f] && use_sb) { col_sb[f] = pos; pos += 9; } }
     if (used_ex) { col_ex = pos; pos += 6; }
     if (used_td) { col_td = pos; pos += 1; }
+    if (used_exw) { col_exw = pos; pos += 6; }
+    for (int k = 0; k < 3; k++) if (used_ix[k]) col_ix[k] = pos++;
+    if (used_tdw) col_tdw = pos++;
     const int N = pos, n = N - m;
     double* A = (double*)calloc((size_t)N * N + 1, 8);
     double* bvec = (double*)calloc(N + 1, 8);
@@ -1209,11 +1218,13 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
         for (int i = 0; i < pn; i++) { double v = pr->linearized_residuals[i]; for (int k = 0; k < pn; k++) v += pr->linearized_jacobians[(size_t)i * pn + k] * dx[k]; res[i] = v; }
         for (int a = 0; a < pr->n_blocks; a++) {
             int ka = pr->block_kind[a], ia = pr->block_index[a];
-            int ca = ka == GF_BA_BLOCK_POSE ? col_pose[ia] : ka == GF_BA_BLOCK_SPEEDBIAS ? col_sb[ia] : ka == GF_BA_BLOCK_EX_POSE ? col_ex : col_td;
+#define MARG_COL(k_, i_) ((k_) == GF_BA_BLOCK_POSE ? col_pose[i_] : (k_) == GF_BA_BLOCK_SPEEDBIAS ? col_sb[i_] : (k_) == GF_BA_BLOCK_EX_POSE ? col_ex : (k_) == GF_BA_BLOCK_TD ? col_td : \
+                          (k_) == GF_BA_BLOCK_EX_WHEEL ? col_exw : (k_) == GF_BA_BLOCK_TD_WHEEL ? col_tdw : col_ix[(k_) - GF_BA_BLOCK_SX])
+            int ca = MARG_COL(ka, ia);
             int sa = block_global_size(ka); if (sa == 7) sa = 6;
             for (int b2 = 0; b2 < pr->n_blocks; b2++) {
                 int kb = pr->block_kind[b2], ib = pr->block_index[b2];
-                int cb = kb == GF_BA_BLOCK_POSE ? col_pose[ib] : kb == GF_BA_BLOCK_SPEEDBIAS ? col_sb[ib] : kb == GF_BA_BLOCK_EX_POSE ? col_ex : col_td;
+                int cb = MARG_COL(kb, ib);
                 int sb2 = block_global_size(kb); if (sb2 == 7) sb2 = 6;
                 for (int i = 0; i < sa; i++) for (int j = 0; j < sb2; j++) { double v = 0; for (int k = 0; k < pn; k++) v += pr->linearized_jacobians[(size_t)k * pn + pr->block_idx[a] + i] * pr->linearized_jacobians[(size_t)k * pn + pr->block_idx[b2] + j]; A[(size_t)(ca + i) * N + cb + j] += v; }
             }
@@ -1228,6 +1239,13 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
         int cols[4] = {col_pose[0], col_sb[0], col_pose[1], col_sb[1]}, sizes[4] = {6, 9, 6, 9}, lds[4] = {7, 9, 7, 9};
         double* Js[4] = {J0, J1, J2, J3};
         ADD_BLOCKS(15, res, 4, cols, sizes, lds, Js)
+    }
+    if (wheel01) {
+        double res[6], J0[42], J1[42], J2[42], Jsx[6], Jsy[6], Jsw[6], Jtw[6];
+        gfo_eval_wheel(wheel01, s.pose[0], s.pose[1], s.exw, s.ix[0], s.ix[1], s.ix[2], s.tdw, res, J0, J1, J2, Jsx, Jsy, Jsw, Jtw);
+        int cols[7] = {col_pose[0], col_pose[1], col_exw, col_ix[0], col_ix[1], col_ix[2], col_tdw}, sizes[7] = {6, 6, 6, 1, 1, 1, 1}, lds[7] = {7, 7, 7, 1, 1, 1, 1};
+        double* Js[7] = {J0, J1, J2, Jsx, Jsy, Jsw, Jtw};
+        ADD_BLOCKS(6, res, 7, cols, sizes, lds, Js)
     }
     for (int v = 0; v < p->n_visual; v++) {
         const gf_ba_visual_factor* f = &p->visual[v];
@@ -1275,6 +1293,9 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
     for (int f = 1; f < F; f++) if (col_sb[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SPEEDBIAS; out->block_index[nb] = f - 1; out->block_idx[nb] = col_sb[f] - m; memcpy(xp, s.sb[f], 72); xp += 9; nb++; }
     if (col_ex >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_POSE; out->block_index[nb] = 0; out->block_idx[nb] = col_ex - m; memcpy(xp, s.ex, 56); xp += 7; nb++; }
     if (col_td >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD; out->block_index[nb] = 0; out->block_idx[nb] = col_td - m; xp[0] = s.td; xp += 1; nb++; }
+    if (col_exw >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_WHEEL; out->block_index[nb] = 0; out->block_idx[nb] = col_exw - m; memcpy(xp, s.exw, 56); xp += 7; nb++; }
+    for (int k = 0; k < 3; k++) if (col_ix[k] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SX + k; out->block_index[nb] = 0; out->block_idx[nb] = col_ix[k] - m; xp[0] = s.ix[k]; xp += 1; nb++; }
+    if (col_tdw >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD_WHEEL; out->block_index[nb] = 0; out->block_idx[nb] = col_tdw - m; xp[0] = s.tdw; xp += 1; nb++; }
     out->n_blocks = nb; out->x0 = out_x0; out->linearized_jacobians = out_J; out->linearized_residuals = out_r;
     free(lm_col); free(A); free(bvec); free(Amm); free(w); free(V); free(Ainv); free(T); free(Ar); free(br); free(s.feat);
     return n;

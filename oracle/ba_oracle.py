@@ -74,7 +74,7 @@ def marginalize_old(pb):
     """MARGIN_OLD: returns the Prior for the next window (block indices already shifted by one frame)."""
     p = pb.struct()
     F = pb.n_frames
-    cap = 16 * F + 8
+    cap = 16 * F + 24
     x0 = np.zeros(cap); J = np.zeros(cap * cap); r = np.zeros(cap)
     out = BaPrior()
     n = lib().gfo_ba_marginalize_old(ctypes.byref(p), ctypes.byref(out), x0.ctypes.data_as(_dp), J.ctypes.data_as(_dp), r.ctypes.data_as(_dp))

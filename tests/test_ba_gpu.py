@@ -102,17 +102,17 @@ def test_solve_with_marginalization_prior(ba):
     compare(ba, nxt, 8)
 
 
-@pytest.mark.parametrize("seed,chain", [(0, False), (1, True)])
-def test_marginalization_matches_oracle(ba, seed, chain):
+@pytest.mark.parametrize("seed,chain,wheel", [(0, False, False), (1, True, False), (2, True, True)])
+def test_marginalization_matches_oracle(ba, seed, chain, wheel):
     """MARGIN_OLD on the GPU against oracle/ba_oracle.c.  The factor J0 is only defined up to an orthogonal transform
     (eigenvector order / sign), so the gauge-invariant quantities are compared: the information matrix J0^T J0, the
     information vector J0^T r0, the block bookkeeping and the linearisation points.  chain = the window already carries
     a prior (the usual steady state), built by a previous marginalisation."""
-    pb, _ = make_window(seed=seed)
+    pb, _ = make_window(seed=seed, with_wheel=wheel)
     if chain:
         O.solve(pb)
         pb0 = pb
-        pb, _ = make_window(seed=seed)          # same trajectory: reuse it as "the next window" with the prior attached
+        pb, _ = make_window(seed=seed, with_wheel=wheel)   # same trajectory: reuse it as "the next window" with the prior attached
         pb.prior = O.marginalize_old(pb0)
     O.solve(pb)                                  # marginalise at the optimum, as the reference does
     want = O.marginalize_old(pb)
@@ -127,7 +127,7 @@ def test_marginalization_matches_oracle(ba, seed, chain):
     bg, bw = got.J.T @ got.r, want.J.T @ want.r
     assert np.abs(bg - bw).max() <= 1e-6 * np.abs(bw).max(), (np.abs(bg - bw).max(), np.abs(bw).max())
     # and it is usable: a solve with the GPU prior and one with the oracle prior end in the same place
-    nxt_a, _ = make_window(seed=seed + 50); nxt_b = nxt_a.clone()
+    nxt_a, _ = make_window(seed=seed + 50, with_wheel=wheel); nxt_b = nxt_a.clone()
     nxt_a.prior, nxt_b.prior = got, want
     sa, sb = ba.optimization(nxt_a), ba.optimization(nxt_b)
     assert np.isclose(sa["final_cost"], sb["final_cost"], rtol=1e-5), (sa["final_cost"], sb["final_cost"])

@@ -257,3 +257,26 @@ def test_prior_is_consistent_across_a_window_shift():
     # Schur identity above, here only gross consistency is asserted
     assert np.abs(relative(nxt.para_pose) - before).max() < 5e-2
     assert s["final_cost"] <= s["initial_cost"] * (1 + 1e-9)
+
+
+def test_marginalization_with_wheel_factor_keeps_the_wheel_blocks():
+    """MARGIN_OLD with USE_WHEEL (estimator.cpp:3367-3377): WheelFactor(0->1) joins with para_Pose[0] dropped; the wheel
+    extrinsic, sx, sy, sw and the wheel time offset appear as kept blocks, and the next window's solve accepts the prior."""
+    from ground_fusion_b200._lib import BLOCK_EX_WHEEL, BLOCK_SX, BLOCK_SY, BLOCK_SW, BLOCK_TD_WHEEL
+    pb, _ = make_window(seed=2, with_wheel=True)
+    O.solve(pb)
+    pr = O.marginalize_old(pb)
+    assert pr.kinds[-5:] == [BLOCK_EX_WHEEL, BLOCK_SX, BLOCK_SY, BLOCK_SW, BLOCK_TD_WHEEL]
+    assert pr.n == 76 + 6 + 3 + 1
+    sizes = {0: 7, 1: 9, 2: 7, 3: 1, BLOCK_EX_WHEEL: 7, BLOCK_SX: 1, BLOCK_SY: 1, BLOCK_SW: 1, BLOCK_TD_WHEEL: 1}
+    tot = sum(sizes[k] for k in pr.kinds)
+    x0 = pr.x0[:tot]
+    assert np.array_equal(x0[-11:-4], pb.para_ex_wheel) and np.array_equal(x0[-4:-1], pb.para_ix_wheel) and x0[-1] == pb.para_td_wheel[0]
+    # the wheel rows/columns of the information matrix are not empty
+    H = pr.J.T @ pr.J
+    assert np.abs(H[-10:, -10:]).max() > 0
+    nxt, _ = make_window(seed=2, with_wheel=True)
+    nxt.prior = pr
+    c0 = O.cost(nxt)
+    s = O.solve(nxt)
+    assert s["final_cost"] < c0 and np.isfinite(s["final_cost"])
