@@ -104,23 +104,33 @@ __device__ __forceinline__ float eig_from_box(double c0, double c1, double c2)
 // padded row h+1 = D[h-2] (cv::boxFilter's BORDER_REFLECT_101 applied to the cov rows).
 __global__ void __launch_bounds__(EIG_TX) k_cov_rows(Level img, double* __restrict__ Dt)
 {
-    constexpr int IH = EIG_BAND + 2, IW = EIG_TX + 4;     // image tile rows y0-1.., cols x0-2..
+    constexpr int IH = EIG_BAND + 2, IWW = EIG_TX / 4 + 2, IP = 4 * IWW;   // image tile rows y0-1.., cols x0-4.. as 34 aligned words
     constexpr int CH = EIG_BAND, CW = EIG_TX + 2;         // dx/dy tile rows y0.., cols x0-1..
-    __shared__ uint8_t timg[IH][IW + 4];
+    __shared__ __align__(4) uint8_t timg[IH][IP];
     __shared__ float tdx[CH][CW + 2];
     __shared__ float tdy[CH][CW + 2];
     const int w = img.w, h = img.h;
     const int x0 = blockIdx.x * EIG_TX, y0 = blockIdx.y * EIG_BAND;
     const int tid = threadIdx.x;
-    for (int i = tid; i < IH * IW; i += EIG_TX) {
-        int r = i / IW, c = i - r * IW;
-        int yy = y0 - 1 + r, xx = x0 - 2 + c;
-        // clamp far-out indices (only reached by slots that are never used), reflect the border ring
-        yy = min(max(yy, -1), h);
-        xx = min(max(xx, -1), w);
-        yy = reflect101(yy, h);
-        xx = reflect101(xx, w);
-        timg[r][c] = __ldg(img.ptr + (size_t)yy * img.pitch + xx);
+    // aligned 32-bit loads (x0 is a multiple of 128, the pitch of 16): all of a thread's loads are in flight together.
+    // Words left of the image or beyond the row pitch are skipped; the two border columns Sobel reads outside the image
+    // (REFLECT_101: -1 -> 1, w -> w-2) are patched afterwards.
+#pragma unroll
+    for (int it = 0; it < (IH * IWW + EIG_TX - 1) / EIG_TX; it++) {
+        const int i = tid + it * EIG_TX;
+        if (i < IH * IWW) {
+            const int r = i / IWW, j = i - r * IWW;
+            const int yy = reflect101(min(max(y0 - 1 + r, -1), h), h);
+            const int xa = x0 - 4 + 4 * j;
+            if (xa >= 0 && xa < img.pitch)
+                reinterpret_cast<uint32_t*>(&timg[r][0])[j] = __ldg(reinterpret_cast<const uint32_t*>(img.ptr + (size_t)yy * img.pitch + xa));
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < IH; r += EIG_TX) {
+        if (x0 == 0) timg[r][3] = timg[r][5];                               // column -1 := column 1
+        const int cw = w - (x0 - 4);                                          // tile slot of column w
+        if (cw >= 2 && cw < IP) timg[r][cw] = timg[r][cw - 2];              // column w := column w-2
     }
     __syncthreads();
     // Sobel at slots whose (row, col) is inside the image; the column ring is filled by reflection below
@@ -128,10 +138,10 @@ __global__ void __launch_bounds__(EIG_TX) k_cov_rows(Level img, double* __restri
         int r = i / CW, c = i - r * CW;
         int yy = y0 + r, xx = x0 - 1 + c;
         if (yy < h && xx >= 0 && xx < w) {
-            const uint8_t* p = &timg[r][c];  // timg row r <-> image row yy-1, col c <-> xx-1
+            const uint8_t* p = &timg[r][c + 2];  // timg row r <-> image row yy-1, byte c+2 <-> column xx-1
             float dx, dy;
-            sobel_dxdy(p[0], p[1], p[2], p[IW + 4], p[IW + 5], p[IW + 6], p[2 * (IW + 4)], p[2 * (IW + 4) + 1],
-                       p[2 * (IW + 4) + 2], xx >= (w / 32) * 32, dx, dy);
+            sobel_dxdy(p[0], p[1], p[2], p[IP], p[IP + 1], p[IP + 2], p[2 * IP], p[2 * IP + 1],
+                       p[2 * IP + 2], xx >= (w / 32) * 32, dx, dy);
             tdx[r][c] = dx;
             tdy[r][c] = dy;
         }

@@ -9,6 +9,12 @@ for k in range(n):
     pb, _ = make_window(seed=100 + k)
     print(ba.optimization(pb)["device_ms"])
 
+pb, _ = make_window(seed=100)
+ba.optimization(pb)
+for _ in range(2):
+    ba.marginalize_old(pb)
+print('marginalize_old device ms', ba.last_marg_ms)
+
 import ctypes
 prof = (ctypes.c_longlong * 32)()
 ba.L.gf_ba_debug_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
