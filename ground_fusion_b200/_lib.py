@@ -116,7 +116,9 @@ class BaProblem(ctypes.Structure):
                 ("feature_const", ctypes.POINTER(ctypes.c_uint8)), ("frames_const", _i), ("pose0_const", _i), ("ex_pose_const", _i),
                 ("td_const", _i), ("ex_wheel_const", _i), ("ix_wheel_const", _i), ("td_wheel_const", _i),
                 ("visual", ctypes.POINTER(BaVisualFactor)), ("imu", ctypes.POINTER(BaImuFactor)), ("wheel", ctypes.POINTER(BaWheelFactor)),
-                ("prior", ctypes.POINTER(BaPrior)), ("gravity", _d * 3), ("visual_sqrt_info", _d), ("ex_wheel_subset_mask", _i)]
+                ("prior", ctypes.POINTER(BaPrior)), ("gravity", _d * 3), ("visual_sqrt_info", _d), ("ex_wheel_subset_mask", _i),
+                ("n_plane", _i), ("plane_frames", ctypes.POINTER(_i)), ("para_plane_R", _dp), ("para_plane_Z", _dp), ("plane_const", _i),
+                ("plane_r_subset_mask", _i), ("plane_sqrt_info", _d * 3)]
 
 
 class BaSummary(ctypes.Structure):
@@ -133,3 +135,4 @@ class BaSummary(ctypes.Structure):
 
 BLOCK_POSE, BLOCK_SPEEDBIAS, BLOCK_EX_POSE, BLOCK_TD = 0, 1, 2, 3
 BLOCK_EX_WHEEL, BLOCK_SX, BLOCK_SY, BLOCK_SW, BLOCK_TD_WHEEL = 4, 5, 6, 7, 8
+BLOCK_PLANE_R, BLOCK_PLANE_Z = 10, 11

@@ -48,6 +48,9 @@ class Problem:
         self.visual = (BaVisualFactor * 1)(); self.n_visual = 0
         self.imu = (BaImuFactor * 1)(); self.n_imu = 0
         self.wheel = (BaWheelFactor * 1)(); self.n_wheel = 0
+        self.n_plane = 0; self.plane_frames = np.zeros(1, np.int32)        # PlaneFactor (USE_PLANE)
+        self.para_plane_R = np.array([0, 0, 0, 1.0]); self.para_plane_Z = np.zeros(1)
+        self.plane_const = 1; self.plane_r_subset_mask = 0b100; self.plane_sqrt_info = np.array([100.0, 100.0, 100.0])
         self.ex_wheel_subset_mask = 0                  # PoseSubsetParameterization of the wheel extrinsic (bit k: component k frozen in Plus)
         self.prior = None
         self.gravity = np.array([0.0, 0.0, 9.805])
@@ -89,6 +92,11 @@ class Problem:
             f.linearized_vel[:] = list(d["linearized_vel"]); f.linearized_gyr[:] = list(d["linearized_gyr"])
             f.vel_1[:] = list(d["vel_1"]); f.gyr_1[:] = list(d["gyr_1"])
 
+    def set_plane(self, frames):
+        """One PlaneFactor per listed frame (estimator.cpp:3152-3166)."""
+        self.plane_frames = np.ascontiguousarray(list(frames), np.int32) if len(list(frames)) else np.zeros(1, np.int32)
+        self.n_plane = len(list(frames))
+
     def struct(self):
         p = BaProblem()
         p.n_frames, p.n_features, p.n_visual, p.n_imu, p.n_wheel = self.n_frames, self.n_features, self.n_visual, self.n_imu, self.n_wheel
@@ -107,16 +115,22 @@ class Problem:
         p.gravity[:] = list(self.gravity)
         p.visual_sqrt_info = self.visual_sqrt_info
         p.ex_wheel_subset_mask = int(self.ex_wheel_subset_mask)
+        p.n_plane = int(self.n_plane)
+        p.plane_frames = self.plane_frames.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        p.para_plane_R, p.para_plane_Z = _ptr(self.para_plane_R), _ptr(self.para_plane_Z)
+        p.plane_const, p.plane_r_subset_mask = int(self.plane_const), int(self.plane_r_subset_mask)
+        p.plane_sqrt_info[:] = list(self.plane_sqrt_info)
         return p
 
     def clone(self):
         import copy
         q = Problem(self.n_frames, self.n_features)
         for k in ("para_pose", "para_speed_bias", "para_ex_pose", "para_feature", "para_td", "para_ex_wheel", "para_ix_wheel",
-                  "para_td_wheel", "feature_const", "gravity"):
+                  "para_td_wheel", "feature_const", "gravity", "para_plane_R", "para_plane_Z", "plane_frames", "plane_sqrt_info"):
             setattr(q, k, getattr(self, k).copy())
         for k in ("frames_const", "pose0_const", "ex_pose_const", "td_const", "ex_wheel_const", "ix_wheel_const", "td_wheel_const",
-                  "n_visual", "n_imu", "n_wheel", "visual_sqrt_info", "max_num_iterations", "prior", "ex_wheel_subset_mask"):
+                  "n_visual", "n_imu", "n_wheel", "visual_sqrt_info", "max_num_iterations", "prior", "ex_wheel_subset_mask", "n_plane", "plane_const",
+                  "plane_r_subset_mask"):
             setattr(q, k, getattr(self, k))
         q.visual = (BaVisualFactor * max(self.n_visual, 1))(); ctypes.memmove(q.visual, self.visual, ctypes.sizeof(BaVisualFactor) * self.n_visual)
         q.imu = (BaImuFactor * max(self.n_imu, 1))(); ctypes.memmove(q.imu, self.imu, ctypes.sizeof(BaImuFactor) * self.n_imu)

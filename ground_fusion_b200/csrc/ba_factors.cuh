@@ -509,4 +509,36 @@ __device__ __noinline__ bool eval_wheel(const gf_ba_wheel_factor& f, const doubl
     return true;
 }
 
+constexpr int PLANE_COLS = 16;   // local columns of one plane factor: pose_i 6 | wheel extrinsic 6 | plane rotation 3 | plane height 1
+// PlaneFactor::Evaluate (reference factor/plane_factor.h:24-118); mirrors oracle/ba_oracle.c (gfo_eval_plane).
+__device__ inline void eval_plane(const double* pose_i, const double* exw, const double* qpw, double zpw, const double* sinfo,
+                                  double* res, double* J, bool jac)
+{
+    const double* Pi = pose_i; const double* Qi = pose_i + 3; const double* tio = exw; const double* qio = exw + 3;
+    double Ri[9], rio[9], Rpw[9], RiT[9], rioT[9], RpwT[9];
+    q_to_R(Qi, Ri); q_to_R(qio, rio); q_to_R(qpw, Rpw); m3_T(Ri, RiT); m3_T(rio, rioT); m3_T(Rpw, RpwT);
+    const double e3[3] = {0, 0, 1};
+    double a[3], b[3], c[3], t[3], u[3];
+    m3_v(RpwT, e3, a); m3_v(RiT, a, b); m3_v(rioT, b, c);
+    m3_v(Ri, tio, t); for (int k = 0; k < 3; k++) t[k] += Pi[k];
+    m3_v(Rpw, t, u);
+    res[0] = sinfo[0] * c[0]; res[1] = sinfo[1] * c[1]; res[2] = sinfo[2] * (zpw + u[2]);
+    if (!jac) return;
+    for (int k = 0; k < 3 * PLANE_COLS; k++) J[k] = 0.0;
+    double S[9], A[9], B[9];
+    skew(b, S); m3_mul(rioT, S, A);
+    for (int r = 0; r < 2; r++) for (int k = 0; k < 3; k++) J[r * PLANE_COLS + 3 + k] = sinfo[r] * A[r * 3 + k];
+    for (int k = 0; k < 3; k++) J[2 * PLANE_COLS + k] = sinfo[2] * Rpw[6 + k];
+    skew(tio, S); m3_mul(Rpw, Ri, A); m3_mul(A, S, B);
+    for (int k = 0; k < 3; k++) J[2 * PLANE_COLS + 3 + k] = -sinfo[2] * B[6 + k];
+    skew(c, S);
+    for (int r = 0; r < 2; r++) for (int k = 0; k < 3; k++) J[r * PLANE_COLS + 9 + k] = sinfo[r] * S[r * 3 + k];
+    for (int k = 0; k < 3; k++) J[2 * PLANE_COLS + 6 + k] = sinfo[2] * A[6 + k];          // e3^T Rpw Ri
+    skew(a, S); m3_mul(RiT, S, A); m3_mul(rioT, A, B);
+    for (int r = 0; r < 2; r++) for (int k = 0; k < 3; k++) J[r * PLANE_COLS + 12 + k] = sinfo[r] * B[r * 3 + k];
+    skew(t, S); m3_mul(Rpw, S, A);
+    for (int k = 0; k < 3; k++) J[2 * PLANE_COLS + 12 + k] = -sinfo[2] * A[6 + k];
+    J[2 * PLANE_COLS + 15] = sinfo[2];
+}
+
 }  // namespace gfba

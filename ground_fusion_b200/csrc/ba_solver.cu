@@ -29,7 +29,7 @@ namespace gfba {
 
 constexpr int MAXF = GF_BA_MAX_FRAMES;
 constexpr int X_POSE = 0, X_SB = 7 * MAXF, X_EX = X_SB + 9 * MAXF, X_TD = X_EX + 7, X_EXW = X_TD + 1, X_IX = X_EXW + 7, X_TDW = X_IX + 3,
-              X_FEAT = X_TDW + 1;
+              X_PR = X_TDW + 1, X_PZ = X_PR + 4, X_FEAT = X_PZ + 1;
 constexpr int PAIR_THREADS = 256, PAIR_CHUNK = 64;   // factors staged per pass (2*64 rows x 20 cols in smem)
 constexpr int RB_THREADS = 512;                      // k_ba_step block size: 128 registers per thread
 constexpr int MAX_NC = 175;                          // reduced dimension supported by k_ba_step: 4x4 blocks of the (nc+1)-row system <= 1024 threads
@@ -50,6 +50,9 @@ struct BaDev {
     int lm_dense;             // marginalisation: landmark columns are ordinary columns of H (cf < nc), no W / hll arrays
     int col_exw, col_ix[3], col_tdw, exw_mask;     // wheel extrinsic / intrinsics / time offset (-1: constant or absent)
     const gf_ba_wheel_factor* wheel;
+    int n_plane, col_pr, col_pz, pr_mask;          // PlaneFactor: frames, plane rotation (local 3) / height columns
+    const int* plane_frames;
+    double plane_sinfo[3];
     const int* col_feat;
     double *X, *Xc;
     const gf_ba_visual_factor* vis;
@@ -362,7 +365,33 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
                 atomicAdd(&acc_g(d, tgt)[ca], s);
             }
         }
-    } else if (b == d.n_pairs + d.n_imu + d.n_wheel && d.pn > 0) {
+    } else if (d.n_plane > 0 && b == d.n_pairs + d.n_imu + d.n_wheel) {
+        // ---------------- all plane factors (3 residuals, 16 local columns each): one thread per factor ----------------
+        if (tid < d.n_plane) {
+            const int fi = d.plane_frames[tid];
+            double r3[3], Jp[3 * PLANE_COLS];
+            eval_plane(X + X_POSE + 7 * fi, X + X_EXW, X + X_PR, X[X_PZ], d.plane_sinfo, r3, Jp, jac);
+            atomicAdd(costp, 0.5 * (r3[0] * r3[0] + r3[1] * r3[1] + r3[2] * r3[2]));
+            auto col_of = [&](int a) {
+                if (a < 6) return d.col_pose[fi] < 0 ? -1 : d.col_pose[fi] + a;
+                if (a < 12) return d.col_exw < 0 ? -1 : d.col_exw + a - 6;
+                if (a < 15) return d.col_pr < 0 ? -1 : d.col_pr + a - 12;
+                return d.col_pz;
+            };
+            for (int a = 0; a < PLANE_COLS; a++) {
+                const int ca = col_of(a);
+                if (ca < 0) continue;
+                double gsum = 0; for (int r = 0; r < 3; r++) gsum += Jp[r * PLANE_COLS + a] * r3[r];
+                atomicAdd(&acc_g(d, tgt)[ca], gsum);
+                for (int c = 0; c < PLANE_COLS; c++) {
+                    const int cc = col_of(c);
+                    if (cc < 0) continue;
+                    double hsum = 0; for (int r = 0; r < 3; r++) hsum += Jp[r * PLANE_COLS + a] * Jp[r * PLANE_COLS + c];
+                    if (hsum != 0.0) atomicAdd(&acc_H(d, tgt)[(size_t)ca * d.nc + cc], hsum);
+                }
+            }
+        }
+    } else if (b == d.n_pairs + d.n_imu + d.n_wheel + (d.n_plane > 0 ? 1 : 0) && d.pn > 0) {
         // ---------------- marginalisation prior: r = r0 + J0 dx, g += J0^T r (H_prior is constant) ----------------
         extern __shared__ double sdyn[];    // dx[pn], r[pn]
         double* dx = sdyn; double* rr = sdyn + d.pn;
@@ -372,8 +401,9 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
             const double* x0 = d.px0 + d.pxoff[blk];
             const double* x = kind == GF_BA_BLOCK_POSE ? X + X_POSE + 7 * d.pindex[blk] : kind == GF_BA_BLOCK_SPEEDBIAS ? X + X_SB + 9 * d.pindex[blk]
                               : kind == GF_BA_BLOCK_EX_POSE ? X + X_EX : kind == GF_BA_BLOCK_TD ? X + X_TD : kind == GF_BA_BLOCK_EX_WHEEL ? X + X_EXW
-                              : kind == GF_BA_BLOCK_SX ? X + X_IX : kind == GF_BA_BLOCK_SY ? X + X_IX + 1 : kind == GF_BA_BLOCK_SW ? X + X_IX + 2 : X + X_TDW;
-            int size = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1;
+                              : kind == GF_BA_BLOCK_SX ? X + X_IX : kind == GF_BA_BLOCK_SY ? X + X_IX + 1 : kind == GF_BA_BLOCK_SW ? X + X_IX + 2
+                              : kind == GF_BA_BLOCK_TD_WHEEL ? X + X_TDW : kind == GF_BA_BLOCK_PLANE_R ? X + X_PR : X + X_PZ;
+            int size = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : kind == GF_BA_BLOCK_PLANE_R ? 4 : 1;
             if (size != 7) for (int k = 0; k < size; k++) dx[idx + k] = x[k] - x0[k];
             else {
                 for (int k = 0; k < 3; k++) dx[idx + k] = x[k] - x0[k];
@@ -536,6 +566,13 @@ __device__ inline void plus_all(const BaDev& d, const double* X, const double* d
         }
         for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) Y[X_IX + k] = X[X_IX + k] + delta[d.col_ix[k]];
         if (d.col_tdw >= 0) Y[X_TDW] = X[X_TDW] + delta[d.col_tdw];
+        if (d.col_pr >= 0) {     // OrientationSubsetParameterization::Plus
+            double dd[3], dq[4], qn[4];
+            for (int k = 0; k < 3; k++) dd[k] = ((d.pr_mask >> k) & 1) ? 0.0 : delta[d.col_pr + k];
+            delta_q(dd, dq); q_mul(X + X_PR, dq, qn); q_normalize(qn);
+            for (int k = 0; k < 4; k++) Y[X_PR + k] = qn[k];
+            Y[X_PZ] = X[X_PZ] + delta[d.col_pz];
+        }
     }
     for (int k = tid; k < d.nfeat; k += nt) { int c = d.col_feat[k]; if (c >= 0) Y[X_FEAT + k] = X[X_FEAT + k] + delta[c]; }
     __syncthreads();
@@ -551,6 +588,7 @@ __device__ inline void diff_norms(const BaDev& d, const double* A, const double*
         if (d.col_exw >= 0) acc(X_EXW, 7);
         for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) acc(X_IX + k, 1);
         if (d.col_tdw >= 0) acc(X_TDW, 1);
+        if (d.col_pr >= 0) { acc(X_PR, 4); acc(X_PZ, 1); }
     }
     for (int k = tid; k < d.nfeat; k += nt) if (d.col_feat[k] >= 0) acc(X_FEAT + k, 1);
 }
@@ -1334,13 +1372,15 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     if (!s || !p || !sum) return set_err(GF_ERR_INVALID_ARG, "null argument");
     if (p->n_frames < 1 || p->n_frames > GF_BA_MAX_FRAMES) return set_err(GF_ERR_INVALID_ARG, "n_frames out of range");
     if (p->n_wheel < 0 || (p->n_wheel > 0 && (!p->wheel || !p->para_ex_wheel || !p->para_ix_wheel || !p->para_td_wheel))) return set_err(GF_ERR_INVALID_ARG, "wheel factors without their parameter blocks");
+    if (p->n_plane < 0 || p->n_plane > PAIR_THREADS || (p->n_plane > 0 && (!p->plane_frames || !p->para_ex_wheel || !p->para_plane_R || !p->para_plane_Z))) return set_err(GF_ERR_INVALID_ARG, "plane factors without their parameter blocks");
     if (p->max_num_iterations < 0 || p->max_num_iterations > GF_BA_MAX_ITERATIONS) return set_err(GF_ERR_INVALID_ARG, "max_num_iterations out of range");
     GF_CUDA(cudaSetDevice(s->device));
     memset(sum, 0, sizeof(*sum));
     const int F = p->n_frames, nfeat = p->n_features;
     // ---- layout (same rules as ceres::Problem construction, estimator.cpp:2950-3100, 3233-3246, 3291) ----
     BaDev d; memset(&d, 0, sizeof(d));
-    d.F = F; d.nfeat = nfeat; d.n_vis = p->n_visual; d.n_imu = p->n_imu; d.n_wheel = p->n_wheel;
+    d.F = F; d.nfeat = nfeat; d.n_vis = p->n_visual; d.n_imu = p->n_imu; d.n_wheel = p->n_wheel; d.n_plane = p->n_plane;
+    d.pr_mask = p->plane_r_subset_mask; for (int k = 0; k < 3; k++) d.plane_sinfo[k] = p->plane_sqrt_info[k];
     const bool use_sb = p->para_speed_bias && !p->pose0_const;
     int c = 0;
     for (int f = 0; f < MAXF; f++) { d.col_pose[f] = -1; d.col_sb[f] = -1; }
@@ -1349,11 +1389,14 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     d.col_ex = p->ex_pose_const ? -1 : c; if (!p->ex_pose_const) c += 6;
     d.col_td = p->td_const ? -1 : c; if (!p->td_const) c += 1;
     d.col_exw = -1; d.col_ix[0] = d.col_ix[1] = d.col_ix[2] = -1; d.col_tdw = -1; d.exw_mask = p->ex_wheel_subset_mask;
-    if (p->n_wheel > 0) {      // estimator.cpp:3008-3056: these blocks only exist with USE_WHEEL
+    if (p->n_wheel > 0 || p->n_plane > 0) {      // estimator.cpp:3008-3056: these blocks only exist with USE_WHEEL (PlaneFactor reads the extrinsic too)
         if (!p->ex_wheel_const) { d.col_exw = c; c += 6; }
-        if (!p->ix_wheel_const) for (int k = 0; k < 3; k++) d.col_ix[k] = c++;
-        if (!p->td_wheel_const) d.col_tdw = c++;
+        if (p->n_wheel > 0 && !p->ix_wheel_const) for (int k = 0; k < 3; k++) d.col_ix[k] = c++;
+        if (p->n_wheel > 0 && !p->td_wheel_const) d.col_tdw = c++;
     }
+    d.col_pr = d.col_pz = -1;
+    if (p->n_plane > 0 && !p->plane_const) { d.col_pr = c; c += 3; d.col_pz = c++; }
+    for (int k = 0; k < p->n_plane; k++) if (p->plane_frames[k] < 0 || p->plane_frames[k] >= F) return set_err(GF_ERR_INVALID_ARG, "plane factor frame out of range");
     d.nc = c;
     std::vector<int> col_feat(nfeat > 0 ? nfeat : 1, -1);
     for (int v = 0; v < p->n_visual; v++) {
@@ -1395,12 +1438,13 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
         for (int b = 0; b < pr->n_blocks; b++) {
             int kind = pr->block_kind[b], idx = pr->block_index[b];
             d.pkind[b] = kind; d.pindex[b] = idx; d.pidx[b] = pr->block_idx[b]; d.pxoff[b] = (int)px0_len;
-            int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1;
-            int ls = gs == 7 ? 6 : gs;
-            if (kind < 0 || kind > GF_BA_BLOCK_TD_WHEEL) return set_err(GF_ERR_INVALID_ARG, "unknown prior block kind");
+            int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : kind == GF_BA_BLOCK_PLANE_R ? 4 : 1;
+            int ls = gs == 7 ? 6 : gs == 4 ? 3 : gs;      // plane rotation: 4 prior columns, the local parameterisation keeps 3
+            if (kind < 0 || kind > GF_BA_BLOCK_PLANE_Z || kind == GF_BA_BLOCK_FEATURE) return set_err(GF_ERR_INVALID_ARG, "unknown prior block kind");
             if ((kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_SPEEDBIAS) && (idx < 0 || idx >= F)) return set_err(GF_ERR_INVALID_ARG, "prior block index out of range");
             int lc = kind == GF_BA_BLOCK_POSE ? d.col_pose[idx] : kind == GF_BA_BLOCK_SPEEDBIAS ? d.col_sb[idx] : kind == GF_BA_BLOCK_EX_POSE ? d.col_ex : kind == GF_BA_BLOCK_TD ? d.col_td
-                     : kind == GF_BA_BLOCK_EX_WHEEL ? d.col_exw : kind == GF_BA_BLOCK_SX ? d.col_ix[0] : kind == GF_BA_BLOCK_SY ? d.col_ix[1] : kind == GF_BA_BLOCK_SW ? d.col_ix[2] : d.col_tdw;
+                     : kind == GF_BA_BLOCK_EX_WHEEL ? d.col_exw : kind == GF_BA_BLOCK_SX ? d.col_ix[0] : kind == GF_BA_BLOCK_SY ? d.col_ix[1] : kind == GF_BA_BLOCK_SW ? d.col_ix[2]
+                     : kind == GF_BA_BLOCK_TD_WHEEL ? d.col_tdw : kind == GF_BA_BLOCK_PLANE_R ? d.col_pr : d.col_pz;
             if (lc >= 0) for (int k = 0; k < ls; k++) pcol[pr->block_idx[b] + k] = lc + k;
             px0_len += gs;
         }
@@ -1411,7 +1455,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
     const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (size_t)p->n_visual),
-                 o_imu = take(sizeof(gf_ba_imu_factor) * (size_t)p->n_imu), o_whl = take(sizeof(gf_ba_wheel_factor) * (size_t)p->n_wheel), o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)),
+                 o_imu = take(sizeof(gf_ba_imu_factor) * (size_t)p->n_imu), o_whl = take(sizeof(gf_ba_wheel_factor) * (size_t)p->n_wheel), o_plf = take(sizeof(int) * (size_t)(p->n_plane > 0 ? p->n_plane : 1)), o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)),
                  o_cf = take(sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1)), o_pJ = take(sizeof(double) * (size_t)pn * pn), o_pr0 = take(sizeof(double) * pn),
                  o_px0 = take(sizeof(double) * px0_len), o_pcol = take(sizeof(int) * (size_t)(pn > 0 ? pn : 1));
     const size_t upload_bytes = off;
@@ -1429,6 +1473,8 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     hX[X_TD] = p->para_td[0];
     hX[X_EXW + 6] = 1.0; hX[X_IX] = hX[X_IX + 1] = hX[X_IX + 2] = 1.0;
     if (p->n_wheel > 0) { memcpy(hX + X_EXW, p->para_ex_wheel, sizeof(double) * 7); memcpy(hX + X_IX, p->para_ix_wheel, sizeof(double) * 3); hX[X_TDW] = p->para_td_wheel[0]; }
+    hX[X_PR + 3] = 1.0;
+    if (p->n_plane > 0) { memcpy(hX + X_EXW, p->para_ex_wheel, sizeof(double) * 7); memcpy(hX + X_PR, p->para_plane_R, sizeof(double) * 4); hX[X_PZ] = p->para_plane_Z[0]; memcpy(hb + o_plf, p->plane_frames, sizeof(int) * p->n_plane); }
     memcpy(hX + X_FEAT, p->para_feature, sizeof(double) * nfeat);
     {   // factors sorted by pair
         gf_ba_visual_factor* hv = (gf_ba_visual_factor*)(hb + o_vis);
@@ -1451,7 +1497,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     d.col_feat = (const int*)(db + o_cf); d.X = (double*)(db + o_X); d.Xc = (double*)(db + o_Xc);
     d.vis = (const gf_ba_visual_factor*)(db + o_vis); d.pair_start = (const int*)(db + o_ps); d.pair_ij = (const int*)(db + o_pij);
     d.imu = (const gf_ba_imu_factor*)(db + o_imu); d.imu_sqrt = (double*)(db + o_sq);
-    d.wheel = (const gf_ba_wheel_factor*)(db + o_whl);
+    d.wheel = (const gf_ba_wheel_factor*)(db + o_whl); d.plane_frames = (const int*)(db + o_plf);
     d.pJ = (const double*)(db + o_pJ); d.pr0 = (const double*)(db + o_pr0); d.px0 = (const double*)(db + o_px0); d.pcol = (const int*)(db + o_pcol);
     d.Hp = (double*)(db + o_Hp); d.acc[0] = (double*)(db + o_a0); d.acc[1] = (double*)(db + o_a1);
     double* vec = (double*)(db + o_vec);
@@ -1473,7 +1519,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
         GF_CUDA(cudaMemcpyAsync((char*)d.st + offsetof(BaState, max_iter), &mi, sizeof(int), cudaMemcpyHostToDevice, st));
     }
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
-    const int eval_blocks = n_work + p->n_imu + p->n_wheel + (pn ? 1 : 0);
+    const int eval_blocks = n_work + p->n_imu + p->n_wheel + (p->n_plane > 0 ? 1 : 0) + (pn ? 1 : 0);
     const size_t prior_smem = sizeof(double) * 2 * (size_t)pn;
     const size_t n4 = (size_t)((nc + 4) / 4);
     const size_t step_smem = sizeof(double) * (std::max((size_t)(nc + 1) * (nc + 2) / 2, 8 * n4 * (n4 + 1)) + 2 + 32 * n4 + 32);
@@ -1499,9 +1545,10 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     memcpy(p->para_ex_pose, hX + X_EX, sizeof(double) * 7);
     p->para_td[0] = hX[X_TD];
     if (p->n_wheel > 0) { memcpy(p->para_ex_wheel, hX + X_EXW, sizeof(double) * 7); memcpy(p->para_ix_wheel, hX + X_IX, sizeof(double) * 3); p->para_td_wheel[0] = hX[X_TDW]; }
+    if (p->n_plane > 0) { memcpy(p->para_ex_wheel, hX + X_EXW, sizeof(double) * 7); memcpy(p->para_plane_R, hX + X_PR, sizeof(double) * 4); p->para_plane_Z[0] = hX[X_PZ]; }
     memcpy(p->para_feature, hX + X_FEAT, sizeof(double) * nfeat);
     sum->iterations = hs->it; sum->num_successful_steps = hs->n_success; sum->termination = hs->termination;
-    sum->reduced_dim = nc; sum->n_free_landmarks = L; sum->n_residuals = pn + 15 * p->n_imu + 6 * p->n_wheel + 2 * p->n_visual;
+    sum->reduced_dim = nc; sum->n_free_landmarks = L; sum->n_residuals = pn + 15 * p->n_imu + 6 * p->n_wheel + 3 * p->n_plane + 2 * p->n_visual;
     sum->initial_cost = hs->cost_hist[0]; sum->final_cost = hs->x_cost;
     for (int k = 0; k <= GF_BA_MAX_ITERATIONS; k++) { sum->cost[k] = hs->cost_hist[k]; sum->radius[k] = hs->radius_hist[k]; }
     sum->device_ms = ms;
@@ -1532,7 +1579,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     BaDev d; memset(&d, 0, sizeof(d));
     d.F = F; d.nfeat = nfeat; d.lm_dense = 1;
     for (int f = 0; f < MAXF; f++) { d.col_pose[f] = -1; d.col_sb[f] = -1; }
-    d.col_ex = d.col_td = d.col_exw = d.col_tdw = -1; d.col_ix[0] = d.col_ix[1] = d.col_ix[2] = -1;
+    d.col_ex = d.col_td = d.col_exw = d.col_tdw = -1; d.col_ix[0] = d.col_ix[1] = d.col_ix[2] = -1; d.col_pr = d.col_pz = -1; d.n_plane = 0;
     d.col_pose[0] = pos; pos += 6;
     if (use_sb) { d.col_sb[0] = pos; pos += 9; }
     std::vector<gf_ba_visual_factor> vis0;

@@ -213,7 +213,8 @@ def wheel_factors(tr, times, rng, frame_dt, td_true=0.0):
 
 
 def make_window(seed=0, n_frames=11, n_landmarks=220, frame_dt=0.1, imu_rate=200, t0=2.0, free_fraction=0.3,
-                pix_noise=0.5 / 460.0, pose_noise=(0.03, 0.01), with_prior=False, with_wheel=False, wheel_free=(True, True, True)):
+                pix_noise=0.5 / 460.0, pose_noise=(0.03, 0.01), with_prior=False, with_wheel=False, wheel_free=(True, True, True),
+                with_plane=False, plane_free=True):
     """One optimisation problem around a true trajectory.  Returns (Problem, truth dict)."""
     rng = np.random.default_rng(seed)
     tr = Trajectory(seed)
@@ -289,5 +290,19 @@ def make_window(seed=0, n_frames=11, n_landmarks=220, frame_dt=0.1, imu_rate=200
         pb.para_ix_wheel[:] = [1.01, 0.99, 1.005]
         pb.para_td_wheel[0] = 0.003
         pb.ex_wheel_const, pb.ix_wheel_const, pb.td_wheel_const = (0 if wheel_free[0] else 1), (0 if wheel_free[1] else 1), (0 if wheel_free[2] else 1)
+    if with_plane:
+        # ground plane through the odometer origins: z_world of the odometer ~ const; plane frame = world rotated slightly
+        pb.set_plane(range(n_frames))
+        pb.para_ex_wheel[:3] = BODY_T_WHEEL[:3, 3] + rng.normal(0, 0.01, 3)
+        pb.para_ex_wheel[3:] = R_to_q(BODY_T_WHEEL[:3, :3] @ rot_exp(rng.normal(0, 0.005, 3)))
+        nrm = np.mean([Rm[f] @ BODY_T_WHEEL[:3, :3] @ np.array([0, 0, 1.0]) for f in range(n_frames)], axis=0)
+        nrm /= np.linalg.norm(nrm)
+        ax = np.cross(nrm, [0, 0, 1.0]); sn = np.linalg.norm(ax)
+        Rpw = rot_exp(ax / sn * math.asin(min(1.0, sn))) if sn > 1e-12 else np.eye(3)     # takes the mean odometer z axis to e3
+        Rpw = Rpw @ rot_exp(rng.normal(0, 0.003, 3))
+        pb.para_plane_R[:] = R_to_q(Rpw)
+        pb.para_plane_Z[0] = -float(np.mean([(Rpw @ (P[f] + Rm[f] @ BODY_T_WHEEL[:3, 3]))[2] for f in range(n_frames)])) + rng.normal(0, 0.01)
+        pb.plane_sqrt_info[:] = [50.0, 50.0, 20.0]
+        pb.plane_const = 0 if plane_free else 1
     truth = dict(P=P, R=Rm, V=Vv, ba=tr.ba, bg=tr.bg, times=times, landmarks=lms)
     return pb, truth

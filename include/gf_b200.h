@@ -199,7 +199,7 @@ typedef struct gf_ba_wheel_factor {
 typedef enum gf_ba_block_kind {
     GF_BA_BLOCK_POSE = 0, GF_BA_BLOCK_SPEEDBIAS = 1, GF_BA_BLOCK_EX_POSE = 2, GF_BA_BLOCK_TD = 3,
     GF_BA_BLOCK_EX_WHEEL = 4, GF_BA_BLOCK_SX = 5, GF_BA_BLOCK_SY = 6, GF_BA_BLOCK_SW = 7,
-    GF_BA_BLOCK_TD_WHEEL = 8, GF_BA_BLOCK_FEATURE = 9
+    GF_BA_BLOCK_TD_WHEEL = 8, GF_BA_BLOCK_FEATURE = 9, GF_BA_BLOCK_PLANE_R = 10, GF_BA_BLOCK_PLANE_Z = 11
 } gf_ba_block_kind;
 
 /* MarginalizationInfo as consumed by MarginalizationFactor::Evaluate
@@ -243,6 +243,16 @@ typedef struct gf_ba_problem {
     int32_t ex_wheel_subset_mask;     /* PoseSubsetParameterization of para_Ex_Pose_wheel (estimator.cpp:3008-3027):
                                        * bit k set = local component k (0-2 translation, 3-5 rotation) is zeroed in Plus;
                                        * 0 = PoseLocalParameterization                              */
+    /* PlaneFactor (factor/plane_factor.h:20-118, USE_PLANE): one factor per listed frame on (para_Pose[i],
+     * para_Ex_Pose_wheel, para_plane_R, para_plane_Z).  para_ex_wheel must then be given even without wheel factors. */
+    int32_t n_plane;
+    const int32_t* plane_frames;      /* [n_plane] frame index of every PlaneFactor (estimator.cpp:3152-3166)     */
+    double* para_plane_R;             /* [4] x y z w, updated in place                                            */
+    double* para_plane_Z;             /* [1]                                                                      */
+    int32_t plane_const;              /* both plane blocks constant (estimator.cpp:3064-3074)                     */
+    int32_t plane_r_subset_mask;      /* OrientationSubsetParameterization: bit k = local component k zeroed in
+                                       * Plus; the reference uses {2} -> 0b100                                    */
+    double plane_sqrt_info[3];        /* PITCH_N_INV, ROLL_N_INV, ZPW_N_INV                                       */
 } gf_ba_problem;
 
 typedef enum gf_ba_termination {

@@ -556,11 +556,53 @@ GFO int gfo_eval_wheel(const gf_ba_wheel_factor* f, const double* pose_i, const 
     return 0;
 }
 
+/* PlaneFactor::Evaluate (reference factor/plane_factor.h:24-118): roll/pitch of the ground-plane normal seen from the
+ * odometer frame and the height of the odometer origin above the plane.  Jacobians row-major in the global block sizes
+ * (3x7 pose, 3x7 wheel extrinsic, 3x4 plane rotation, 3x1 plane height), multiplied by diag(sqrt_info). */
+GFO void gfo_eval_plane(const double* pose_i, const double* exw, const double* qpw_in, double zpw, const double* sinfo,
+                        double* res, double* J0, double* J1, double* J2, double* J3)
+{
+    const double* Pi = pose_i; const double* Qi = pose_i + 3; const double* tio = exw; const double* qio = exw + 3;
+    q4 qpw = {qpw_in[0], qpw_in[1], qpw_in[2], qpw_in[3]};
+    m3 Ri, rio, Rpw, RiT, rioT, RpwT; q_to_R(Qi, Ri); q_to_R(qio, rio); q_to_R(qpw, Rpw); m3_T(Ri, RiT); m3_T(rio, rioT); m3_T(Rpw, RpwT);
+    const v3 e3 = {0, 0, 1};
+    v3 a, b, c, t, u;
+    m3_v(RpwT, e3, a); m3_v(RiT, a, b); m3_v(rioT, b, c);      /* rio^T Ri^T Rpw^T e3 */
+    m3_v(Ri, tio, t); for (int k = 0; k < 3; k++) t[k] += Pi[k]; /* Pi + Qi tio */
+    m3_v(Rpw, t, u);
+    res[0] = sinfo[0] * c[0]; res[1] = sinfo[1] * c[1]; res[2] = sinfo[2] * (zpw + u[2]);
+    m3 S, A, B;
+    if (J0) {
+        memset(J0, 0, sizeof(double) * 21);
+        skew(b, S); m3_mul(rioT, S, A);                           /* rio^T [Qi^-1 qpw^-1 e3]x : rows 0,1 -> rotation block */
+        for (int r = 0; r < 2; r++) for (int k = 0; k < 3; k++) J0[r * 7 + 3 + k] = sinfo[r] * A[r * 3 + k];
+        for (int k = 0; k < 3; k++) J0[2 * 7 + k] = sinfo[2] * Rpw[2 * 3 + k];                 /* e3^T Rpw */
+        skew(tio, S); m3_mul(Rpw, Ri, A); m3_mul(A, S, B);
+        for (int k = 0; k < 3; k++) J0[2 * 7 + 3 + k] = -sinfo[2] * B[2 * 3 + k];               /* -e3^T Rpw Ri [tio]x */
+    }
+    if (J1) {
+        memset(J1, 0, sizeof(double) * 21);
+        skew(c, S);
+        for (int r = 0; r < 2; r++) for (int k = 0; k < 3; k++) J1[r * 7 + 3 + k] = sinfo[r] * S[r * 3 + k];
+        m3_mul(Rpw, Ri, A);
+        for (int k = 0; k < 3; k++) J1[2 * 7 + k] = sinfo[2] * A[2 * 3 + k];
+    }
+    if (J2) {
+        memset(J2, 0, sizeof(double) * 12);
+        skew(a, S); m3_mul(RiT, S, A); m3_mul(rioT, A, B);        /* rio^T Ri^T [qpw^-1 e3]x */
+        for (int r = 0; r < 2; r++) for (int k = 0; k < 3; k++) J2[r * 4 + k] = sinfo[r] * B[r * 3 + k];
+        skew(t, S); m3_mul(Rpw, S, A);
+        for (int k = 0; k < 3; k++) J2[2 * 4 + k] = -sinfo[2] * A[2 * 3 + k];
+    }
+    if (J3) { J3[0] = 0; J3[1] = 0; J3[2] = sinfo[2]; }
+}
+
 /* ------------------------------------------------------------------ program layout -------------- */
 typedef struct {
     int F, nfeat;
     int col_pose[GF_BA_MAX_FRAMES], col_sb[GF_BA_MAX_FRAMES], col_ex, col_td;
     int col_exw, col_ix[3], col_tdw;   /* wheel extrinsic, sx sy sw, wheel time offset (only with wheel factors) */
+    int col_pr, col_pz, row_plane;     /* plane rotation (local 3) and height (USE_PLANE) */
     int* col_feat;   /* -1: constant or unused */
     int n_cam, n_lm, n_cols;
     int row_prior, row_imu, row_wheel, row_vis, n_rows;
@@ -570,6 +612,7 @@ typedef struct {
 typedef struct {
     double pose[GF_BA_MAX_FRAMES][7], sb[GF_BA_MAX_FRAMES][9], ex[7], td;
     double exw[7], ix[3], tdw;
+    double pr[4], pz;
     double* feat;
 } state_t;
 
@@ -581,6 +624,8 @@ static void state_load(const gf_ba_problem* p, state_t* s)
     s->td = p->para_td[0];
     memset(s->exw, 0, sizeof(s->exw)); s->exw[6] = 1.0; s->ix[0] = s->ix[1] = s->ix[2] = 1.0; s->tdw = 0.0;
     if (p->n_wheel > 0) { memcpy(s->exw, p->para_ex_wheel, sizeof(double) * 7); memcpy(s->ix, p->para_ix_wheel, sizeof(double) * 3); s->tdw = p->para_td_wheel[0]; }
+    s->pr[0] = s->pr[1] = s->pr[2] = 0; s->pr[3] = 1; s->pz = 0;
+    if (p->n_plane > 0) { memcpy(s->exw, p->para_ex_wheel, sizeof(double) * 7); memcpy(s->pr, p->para_plane_R, sizeof(double) * 4); s->pz = p->para_plane_Z[0]; }
     s->feat = (double*)malloc(sizeof(double) * (p->n_features > 0 ? p->n_features : 1));
     memcpy(s->feat, p->para_feature, sizeof(double) * p->n_features);
 }
@@ -598,6 +643,7 @@ static void state_store(const gf_ba_problem* p, const state_t* s)
     memcpy(p->para_ex_pose, s->ex, sizeof(double) * 7);
     p->para_td[0] = s->td;
     if (p->n_wheel > 0) { memcpy(p->para_ex_wheel, s->exw, sizeof(double) * 7); memcpy(p->para_ix_wheel, s->ix, sizeof(double) * 3); p->para_td_wheel[0] = s->tdw; }
+    if (p->n_plane > 0) { memcpy(p->para_ex_wheel, s->exw, sizeof(double) * 7); memcpy(p->para_plane_R, s->pr, sizeof(double) * 4); p->para_plane_Z[0] = s->pz; }
     memcpy(p->para_feature, s->feat, sizeof(double) * p->n_features);
 }
 
@@ -617,11 +663,13 @@ static void make_layout(const gf_ba_problem* p, layout_t* L)
     L->col_ex = p->ex_pose_const ? -1 : c; if (!p->ex_pose_const) c += 6;
     L->col_td = p->td_const ? -1 : c; if (!p->td_const) c += 1;
     L->col_exw = -1; L->col_ix[0] = L->col_ix[1] = L->col_ix[2] = -1; L->col_tdw = -1;
-    if (p->n_wheel > 0) {      /* estimator.cpp:3008-3056: the wheel blocks only exist with USE_WHEEL */
+    if (p->n_wheel > 0 || p->n_plane > 0) {      /* estimator.cpp:3008-3056: the wheel blocks only exist with USE_WHEEL (PlaneFactor reads the extrinsic too) */
         if (!p->ex_wheel_const) { L->col_exw = c; c += 6; }
-        if (!p->ix_wheel_const) for (int k = 0; k < 3; k++) L->col_ix[k] = c++;
-        if (!p->td_wheel_const) L->col_tdw = c++;
+        if (p->n_wheel > 0 && !p->ix_wheel_const) for (int k = 0; k < 3; k++) L->col_ix[k] = c++;
+        if (p->n_wheel > 0 && !p->td_wheel_const) L->col_tdw = c++;
     }
+    L->col_pr = L->col_pz = -1;
+    if (p->n_plane > 0 && !p->plane_const) { L->col_pr = c; c += 3; L->col_pz = c++; }
     L->n_cam = c;
     L->col_feat = (int*)malloc(sizeof(int) * (L->nfeat > 0 ? L->nfeat : 1));
     for (int k = 0; k < L->nfeat; k++) L->col_feat[k] = -1;
@@ -635,6 +683,7 @@ static void make_layout(const gf_ba_problem* p, layout_t* L)
     L->row_prior = r; r += (p->prior ? p->prior->n : 0);
     L->row_imu = r; r += 15 * p->n_imu;
     L->row_wheel = r; r += 6 * p->n_wheel;
+    L->row_plane = r; r += 3 * p->n_plane;
     L->row_vis = r; r += 2 * p->n_visual;
     L->n_rows = r;
 }
@@ -651,6 +700,8 @@ static const double* prior_block_ptr(const state_t* s, int kind, int index)
     case GF_BA_BLOCK_SY: return &s->ix[1];
     case GF_BA_BLOCK_SW: return &s->ix[2];
     case GF_BA_BLOCK_TD_WHEEL: return &s->tdw;
+    case GF_BA_BLOCK_PLANE_R: return s->pr;
+    case GF_BA_BLOCK_PLANE_Z: return &s->pz;
     default: return NULL;
     }
 }
@@ -659,6 +710,7 @@ static int block_global_size(int kind)
     switch (kind) {
     case GF_BA_BLOCK_POSE: case GF_BA_BLOCK_EX_POSE: case GF_BA_BLOCK_EX_WHEEL: return 7;
     case GF_BA_BLOCK_SPEEDBIAS: return 9;
+    case GF_BA_BLOCK_PLANE_R: return 4;
     default: return 1;
     }
 }
@@ -674,6 +726,8 @@ static int block_col(const layout_t* L, int kind, int index)
     case GF_BA_BLOCK_SY: return L->col_ix[1];
     case GF_BA_BLOCK_SW: return L->col_ix[2];
     case GF_BA_BLOCK_TD_WHEEL: return L->col_tdw;
+    case GF_BA_BLOCK_PLANE_R: return L->col_pr;
+    case GF_BA_BLOCK_PLANE_Z: return L->col_pz;
     default: return -1;
     }
 }
@@ -719,7 +773,7 @@ static double evaluate(const gf_ba_problem* p, const layout_t* L, const state_t*
             for (int b = 0; b < pr->n_blocks; b++) {
                 int col = block_col(L, pr->block_kind[b], pr->block_index[b]);
                 if (col < 0) continue;
-                int ls = block_global_size(pr->block_kind[b]); if (ls == 7) ls = 6;
+                int ls = block_global_size(pr->block_kind[b]); if (ls == 7) ls = 6; if (pr->block_kind[b] == GF_BA_BLOCK_PLANE_R) ls = 3;   /* 4 prior columns, the local parameterisation keeps 3 */
                 for (int i = 0; i < n; i++) for (int k = 0; k < ls; k++) J[(size_t)(L->row_prior + i) * nc + col + k] = pr->linearized_jacobians[(size_t)i * n + pr->block_idx[b] + k];
             }
         free(dx);
@@ -758,6 +812,20 @@ static double evaluate(const gf_ba_problem* p, const layout_t* L, const state_t*
                 if (L->col_tdw >= 0) Jr[L->col_tdw] = Jtw[i];
             }
         }
+    }
+    for (int m = 0; m < p->n_plane; m++) {
+        const int fi = p->plane_frames[m];
+        double res[3], J0[21], J1[21], J2[12], J3[3];
+        gfo_eval_plane(s->pose[fi], s->exw, s->pr, s->pz, p->plane_sqrt_info, res, J ? J0 : NULL, J ? J1 : NULL, J ? J2 : NULL, J ? J3 : NULL);
+        int row = L->row_plane + 3 * m;
+        for (int i = 0; i < 3; i++) { r[row + i] = res[i]; cost += 0.5 * res[i] * res[i]; }
+        if (J)
+            for (int i = 0; i < 3; i++) {
+                double* Jr = J + (size_t)(row + i) * nc;
+                if (L->col_pose[fi] >= 0) for (int k = 0; k < 6; k++) Jr[L->col_pose[fi] + k] = J0[i * 7 + k];
+                if (L->col_exw >= 0) for (int k = 0; k < 6; k++) Jr[L->col_exw + k] = J1[i * 7 + k];
+                if (L->col_pr >= 0) { for (int k = 0; k < 3; k++) Jr[L->col_pr + k] = J2[i * 4 + k]; Jr[L->col_pz] = J3[i]; }
+            }
     }
     for (int v = 0; v < p->n_visual; v++) {
         const gf_ba_visual_factor* f = &p->visual[v];
@@ -821,7 +889,7 @@ static double linearize_blocks(const gf_ba_problem* p, const layout_t* L, const 
         for (int b = 0; b < pr->n_blocks; b++) {
             int col = block_col(L, pr->block_kind[b], pr->block_index[b]);
             if (col < 0) continue;
-            int ls = block_global_size(pr->block_kind[b]); if (ls == 7) ls = 6;
+            int ls = block_global_size(pr->block_kind[b]); if (ls == 7) ls = 6; if (pr->block_kind[b] == GF_BA_BLOCK_PLANE_R) ls = 3;   /* 4 prior columns, the local parameterisation keeps 3 */
             for (int k = 0; k < ls; k++) { double v = 0; for (int i = 0; i < pn; i++) v += pr->linearized_jacobians[(size_t)i * pn + pr->block_idx[b] + k] * r[i]; g[col + k] += v; }
         }
         free(dx); free(r);
@@ -844,6 +912,15 @@ static double linearize_blocks(const gf_ba_problem* p, const layout_t* L, const 
         int sizes[7] = {6, 6, 6, 1, 1, 1, 1}, lds[7] = {7, 7, 7, 1, 1, 1, 1};
         double* Js[7] = {J0, J1, J2, Jsx, Jsy, Jsw, Jtw};
         add_blocks(H, g, n, 6, res, 7, cols, sizes, lds, Js);
+    }
+    for (int m = 0; m < p->n_plane; m++) {
+        const int fi = p->plane_frames[m];
+        double res[3], J0[21], J1[21], J2[12], J3[3];
+        gfo_eval_plane(s->pose[fi], s->exw, s->pr, s->pz, p->plane_sqrt_info, res, J0, J1, J2, J3);
+        for (int i = 0; i < 3; i++) cost += 0.5 * res[i] * res[i];
+        int cols[4] = {L->col_pose[fi], L->col_exw, L->col_pr, L->col_pz}, sizes[4] = {6, 6, 3, 1}, lds[4] = {7, 7, 4, 1};
+        double* Js[4] = {J0, J1, J2, J3};
+        add_blocks(H, g, n, 3, res, 4, cols, sizes, lds, Js);
     }
     for (int v = 0; v < p->n_visual; v++) {
         const gf_ba_visual_factor* f = &p->visual[v];
@@ -886,6 +963,11 @@ static double cost_only(const gf_ba_problem* p, const layout_t* L, const state_t
         gfo_eval_wheel(f, s->pose[f->i], s->pose[f->j], s->exw, s->ix[0], s->ix[1], s->ix[2], s->tdw, res, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
         for (int i = 0; i < 6; i++) cost += 0.5 * res[i] * res[i];
     }
+    for (int m = 0; m < p->n_plane; m++) {
+        double res[3];
+        gfo_eval_plane(s->pose[p->plane_frames[m]], s->exw, s->pr, s->pz, p->plane_sqrt_info, res, NULL, NULL, NULL, NULL);
+        for (int i = 0; i < 3; i++) cost += 0.5 * res[i] * res[i];
+    }
     for (int v = 0; v < p->n_visual; v++) {
         const gf_ba_visual_factor* f = &p->visual[v];
         double res[2];
@@ -920,6 +1002,12 @@ static void state_plus(const gf_ba_problem* p, const layout_t* L, const state_t*
     }
     for (int k = 0; k < 3; k++) if (L->col_ix[k] >= 0) out->ix[k] = x->ix[k] + delta[L->col_ix[k]];
     if (L->col_tdw >= 0) out->tdw = x->tdw + delta[L->col_tdw];
+    if (L->col_pr >= 0) {     /* OrientationSubsetParameterization::Plus (orientation_subset_parameterization.cpp:21-37) */
+        v3 dd; q4 dq, q;
+        for (int k = 0; k < 3; k++) dd[k] = ((p->plane_r_subset_mask >> k) & 1) ? 0.0 : delta[L->col_pr + k];
+        delta_q(dd, dq); q_mul(x->pr, dq, q); q_normalize(q); memcpy(out->pr, q, sizeof(q4));
+        out->pz = x->pz + delta[L->col_pz];
+    }
     for (int k = 0; k < L->nfeat; k++) if (L->col_feat[k] >= 0) out->feat[k] = x->feat[k] + delta[L->col_feat[k]];
 }
 /* ambient-space difference norms over the non-constant blocks (x_norm, step_norm, gradient_max_norm) */
@@ -936,6 +1024,7 @@ static void state_diff_norms(const layout_t* L, const state_t* a, const state_t*
     if (L->col_exw >= 0) for (int k = 0; k < 7; k++) ACC(a->exw[k] - (b ? b->exw[k] : 0));
     for (int k = 0; k < 3; k++) if (L->col_ix[k] >= 0) ACC(a->ix[k] - (b ? b->ix[k] : 0));
     if (L->col_tdw >= 0) ACC(a->tdw - (b ? b->tdw : 0));
+    if (L->col_pr >= 0) { for (int k = 0; k < 4; k++) ACC(a->pr[k] - (b ? b->pr[k] : 0)); ACC(a->pz - (b ? b->pz : 0)); }
     for (int k = 0; k < L->nfeat; k++) if (L->col_feat[k] >= 0) ACC(a->feat[k] - (b ? b->feat[k] : 0));
 #undef ACC
     if (l2) *l2 = sqrt(s2);
@@ -1000,7 +1089,7 @@ GFO int gfo_ba_solve(const gf_ba_problem* p, gf_ba_summary* sum)
         int* pc = (int*)malloc(sizeof(int) * pn);
         for (int k = 0; k < pn; k++) pc[k] = -1;
         for (int b = 0; b < pr->n_blocks; b++) { int col = block_col(&L, pr->block_kind[b], pr->block_index[b]); if (col < 0) continue;
-            int ls = block_global_size(pr->block_kind[b]); if (ls == 7) ls = 6; for (int k = 0; k < ls; k++) pc[pr->block_idx[b] + k] = col + k; }
+            int ls = block_global_size(pr->block_kind[b]); if (ls == 7) ls = 6; if (pr->block_kind[b] == GF_BA_BLOCK_PLANE_R) ls = 3;   /* 4 prior columns, the local parameterisation keeps 3 */ for (int k = 0; k < ls; k++) pc[pr->block_idx[b] + k] = col + k; }
         for (int a = 0; a < pn; a++) { if (pc[a] < 0) continue; for (int b = 0; b < pn; b++) { if (pc[b] < 0) continue; double v = 0;
             for (int k = 0; k < pn; k++) v += pr->linearized_jacobians[(size_t)k * pn + a] * pr->linearized_jacobians[(size_t)k * pn + b]; Hp[(size_t)pc[a] * n + pc[b]] = v; } }
         free(pc);

@@ -33,6 +33,8 @@ def lib():
         L.gfo_ba_set_tolerances.argtypes = [ctypes.c_double] * 3
         L.gfo_ba_set_tolerances.restype = None
         L.gfo_sqrt_info.argtypes = [_dp, ctypes.c_int, _dp]
+        L.gfo_eval_plane.argtypes = [_dp, _dp, _dp, ctypes.c_double, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.gfo_eval_plane.restype = None
         L.gfo_eval_wheel.argtypes = [ctypes.POINTER(BaWheelFactor), _dp, _dp, _dp] + [ctypes.c_double] * 4 + [_dp] * 8
         _LIB = L
     return _LIB
@@ -98,4 +100,15 @@ def eval_wheel(f, pose_i, pose_j, exw, sx, sy, sw, td, jac=True):
                               float(sx), float(sy), float(sw), float(td), res.ctypes.data_as(_dp), *ptrs)
     if rc:
         raise RuntimeError("wheel covariance not positive definite")
+    return res, Js
+
+
+def eval_plane(pose_i, exw, qpw, zpw, sinfo, jac=True):
+    """PlaneFactor::Evaluate restatement: (res[3], [J_pose 3x7, J_ex 3x7, J_qpw 3x4, J_zpw (3,)])."""
+    a = [np.ascontiguousarray(v, np.float64) for v in (pose_i, exw, qpw, sinfo)]
+    res = np.zeros(3)
+    Js = [np.zeros((3, 7)), np.zeros((3, 7)), np.zeros((3, 4)), np.zeros(3)]
+    ptrs = [j.ctypes.data_as(_dp) if jac else None for j in Js]
+    lib().gfo_eval_plane(a[0].ctypes.data_as(_dp), a[1].ctypes.data_as(_dp), a[2].ctypes.data_as(_dp), float(zpw), a[3].ctypes.data_as(_dp),
+                         res.ctypes.data_as(_dp), *ptrs)
     return res, Js

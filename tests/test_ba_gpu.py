@@ -83,6 +83,19 @@ def test_solve_with_wheel_factors(ba, wheel_free, mask):
         assert s["n_residuals"] == 150 + 60 + 2 * pb.n_visual
 
 
+@pytest.mark.parametrize("kw", [dict(with_plane=True), dict(with_plane=True, plane_free=False), dict(with_plane=True, with_wheel=True)])
+def test_solve_with_plane_factors(ba, kw):
+    """PlaneFactor per frame (reference plane_factor.h) with free / constant plane blocks, alone and together with wheel factors
+    (the wheel extrinsic is then shared by both factor types)."""
+    pb, _ = make_window(seed=4, **kw)
+    for it in (1, 8):
+        s = compare(ba, pb, it, mid_rtol=1e-6)
+        assert s["n_residuals"] == 150 + 3 * 11 + 2 * pb.n_visual + (60 if kw.get("with_wheel") else 0)
+    a, b = pb.clone(), pb.clone()
+    O.solve(a); ba.optimization(b)
+    assert np.abs(a.para_plane_R - b.para_plane_R).max() < 1e-6 and abs(a.para_plane_Z[0] - b.para_plane_Z[0]) < 1e-6
+
+
 def test_solve_with_marginalization_prior(ba):
     pb, _ = make_window(seed=4)
     q = pb.clone(); O.solve(q)

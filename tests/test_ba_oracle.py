@@ -280,3 +280,53 @@ def test_marginalization_with_wheel_factor_keeps_the_wheel_blocks():
     c0 = O.cost(nxt)
     s = O.solve(nxt)
     assert s["final_cost"] < c0 and np.isfinite(s["final_cost"])
+
+
+def test_plane_factor_jacobians_match_finite_differences_and_solve_moves_the_plane():
+    """PlaneFactor (reference factor/plane_factor.h:24-118): its analytic Jacobians are exact derivatives w.r.t. the right
+    perturbations of PoseLocalParameterization / OrientationSubsetParameterization, so central differences pin them."""
+    from ground_fusion_b200.synth_ba import q_mul
+    pb, _ = make_window(seed=4, with_plane=True)
+    pi, exw, qpw, z, si = pb.para_pose[3].copy(), pb.para_ex_wheel.copy(), pb.para_plane_R.copy(), pb.para_plane_Z[0], pb.plane_sqrt_info
+    res, Js = O.eval_plane(pi, exw, qpw, z, si)
+
+    def plus7(x, d):
+        y = x.copy(); y[:3] += d[:3]
+        dq = np.array([d[3] / 2, d[4] / 2, d[5] / 2, 1.0]); dq /= np.linalg.norm(dq)
+        y[3:] = q_mul(x[3:], dq); y[3:] /= np.linalg.norm(y[3:])
+        return y
+
+    def plus4(q, d):
+        dq = np.array([d[0] / 2, d[1] / 2, d[2] / 2, 1.0]); dq /= np.linalg.norm(dq)
+        y = q_mul(q, dq)
+        return y / np.linalg.norm(y)
+
+    h = 1e-6
+    for which in range(2):
+        J = np.zeros((3, 6))
+        for k in range(6):
+            d = np.zeros(6); d[k] = h
+            a = [pi, exw]; a[which] = plus7(a[which], d)
+            rp, _ = O.eval_plane(a[0], a[1], qpw, z, si, jac=False)
+            a = [pi, exw]; a[which] = plus7(a[which], -d)
+            rm, _ = O.eval_plane(a[0], a[1], qpw, z, si, jac=False)
+            J[:, k] = (rp - rm) / (2 * h)
+        assert np.abs(J - Js[which][:, :6]).max() < 1e-6 and np.all(Js[which][:, 6] == 0)
+    J = np.zeros((3, 3))
+    for k in range(3):
+        d = np.zeros(3); d[k] = h
+        rp, _ = O.eval_plane(pi, exw, plus4(qpw, d), z, si, jac=False)
+        rm, _ = O.eval_plane(pi, exw, plus4(qpw, -d), z, si, jac=False)
+        J[:, k] = (rp - rm) / (2 * h)
+    assert np.abs(J - Js[2][:, :3]).max() < 1e-6 and np.all(Js[2][:, 3] == 0)
+    assert np.allclose(Js[3], [0, 0, si[2]])
+    # solve: free plane blocks move, the yaw component of the plane rotation does not (OrientationSubsetParameterization {2})
+    q0, z0 = pb.para_plane_R.copy(), pb.para_plane_Z[0]
+    c0 = O.cost(pb)
+    s = O.solve(pb)
+    assert s["reduced_dim"] == 165 + 3 + 1 and s["final_cost"] < 1e-3 * c0
+    assert not np.allclose(pb.para_plane_R, q0) and pb.para_plane_Z[0] != z0 and abs(np.linalg.norm(pb.para_plane_R) - 1) < 1e-12
+    pb2, _ = make_window(seed=4, with_plane=True, plane_free=False)
+    q1 = pb2.para_plane_R.copy()
+    s2 = O.solve(pb2)
+    assert s2["reduced_dim"] == 165 and np.array_equal(pb2.para_plane_R, q1)
