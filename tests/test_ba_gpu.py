@@ -83,7 +83,7 @@ def test_solve_with_wheel_factors(ba, wheel_free, mask):
         assert s["n_residuals"] == 150 + 60 + 2 * pb.n_visual
 
 
-@pytest.mark.parametrize("kw", [dict(with_plane=True), dict(with_plane=True, plane_free=False), dict(with_plane=True, with_wheel=True)])
+@pytest.mark.parametrize("kw", [dict(with_plane=True), dict(with_plane=True, plane_free=False), dict(with_plane=True, with_wheel=True, wheel_free=(False, True, True))])
 def test_solve_with_plane_factors(ba, kw):
     """PlaneFactor per frame (reference plane_factor.h) with free / constant plane blocks, alone and together with wheel factors
     (the wheel extrinsic is then shared by both factor types)."""
@@ -94,6 +94,15 @@ def test_solve_with_plane_factors(ba, kw):
     a, b = pb.clone(), pb.clone()
     O.solve(a); ba.optimization(b)
     assert np.abs(a.para_plane_R - b.para_plane_R).max() < 1e-6 and abs(a.para_plane_Z[0] - b.para_plane_Z[0]) < 1e-6
+
+
+def test_reduced_system_capacity_is_reported(ba):
+    """k_ba_step holds the reduced system of at most 175 unknowns in the registers of one CTA; a window with every optional
+    block free (165 + wheel 10 + plane 4 = 179) is refused with GF_ERR_CAPACITY, not silently mis-solved."""
+    from ground_fusion_b200._lib import GfError
+    pb, _ = make_window(seed=4, with_plane=True, with_wheel=True)
+    with pytest.raises(GfError, match="175"):
+        ba.optimization(pb)
 
 
 def test_solve_with_marginalization_prior(ba):
