@@ -1,4 +1,5 @@
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_ba_r1g.csv python tools/prof_ba.py 2 > /dev/null 2>&1
-python tools/ncu_summary.py gpurun_out/launches_ba_r1g.csv
-GF_NO_GRAPH=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_fe_r1g.csv python tools/prof_fe.py 12 > /dev/null 2>&1
-python tools/ncu_summary.py gpurun_out/launches_fe_r1g.csv
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python bench.py 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench17.json; python -c "
+import json; d=json.load(open('gpurun_out/bench17.json')); print(d['value'], d['e2e']['value'], d['cpu_baseline']['value'], d['ba']['value'], d['ba']['cpu_baseline']['value'], d['ba']['marginalize_old']['device_ms'], d['ba']['concurrent_streams']['value'], d['gpu_launches'])"
+tail -2 gpurun_out/bench.err
