@@ -1,5 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 400 python bench.py 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench17.json; python -c "
-import json; d=json.load(open('gpurun_out/bench17.json')); print(d['value'], d['e2e']['value'], d['cpu_baseline']['value'], d['ba']['value'], d['ba']['cpu_baseline']['value'], d['ba']['marginalize_old']['device_ms'], d['ba']['concurrent_streams']['value'], d['gpu_launches'])"
-tail -2 gpurun_out/bench.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ba_step -s 3 -c 1 -o gpurun_out/k_ba_step_r1b -f python tools/prof_ba.py 1 > /dev/null 2>&1
+ls -la gpurun_out/k_ba_step_r1b.ncu-rep
