@@ -544,8 +544,6 @@ __global__ void __launch_bounds__(256) k_ba_schur(BaDev d)
 
 // ------------------------------------------------------------------------------------------------
 // ambient-space helpers over the non-constant blocks
-__device__ __forceinline__ void for_each_free_block(const BaDev& d, int t, int nt, double (*fn)(const BaDev&, int off, int size, void* ctx), void* ctx, double& acc);
-
 __device__ inline void plus_all(const BaDev& d, const double* X, const double* delta, double* Y, int tid, int nt)
 {
     // copy everything, then overwrite the free blocks

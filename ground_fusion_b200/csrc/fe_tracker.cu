@@ -151,12 +151,6 @@ __global__ void __launch_bounds__(FE_CAP) k_remove_ids(TrackScalars* sc, FeatArr
     if (tid == 0) sc->n_prev = s_m;
 }
 
-__global__ void k_pitch_copy_u8(const uint8_t* src, int spitch, uint8_t* dst, int dpitch, int w, int h)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x < w && y < h) dst[(size_t)y * dpitch + x] = src[(size_t)y * spitch + x];
-}
-
 }  // namespace gf
 
 using namespace gf;
@@ -251,10 +245,9 @@ static void free_nms_grid(NmsGrid& g)
 }
 
 // GFTT tail shared by the tracker and gf_stage_gftt: mask -> max -> candidates -> NMS rounds
-static int enqueue_gftt_select(cudaStream_t s, TrackScalars* d_sc, const float2* kept_pts, int max_kept, const float* d_eig,
-                               int epitch, uint8_t* d_mask, int mpitch, int w, int h, int min_dist, NmsGrid& grid, size_t cells)
+static int enqueue_gftt_select(cudaStream_t s, TrackScalars* d_sc, const float2* kept_pts, const float* d_eig, int epitch, int w, int h,
+                               int min_dist, NmsGrid& grid)
 {
-    (void)d_mask; (void)mpitch; (void)max_kept; (void)cells; (void)grid;
     dim3 tg((w + MASK_TX - 1) / MASK_TX, (h + MASK_TY - 1) / MASK_TY);
     k_eig_max<<<tg, 256, 0, s>>>(d_sc, kept_pts, d_eig, epitch, w, h, min_dist); GF_LAUNCHED();
     k_candidates<<<tg, 256, 0, s>>>(d_sc, kept_pts, d_eig, epitch, w, h, min_dist, grid); GF_LAUNCHED();
@@ -453,8 +446,7 @@ static int body_dep2(gf_tracker* t, long long f)
 {
     cudaStream_t s = t->s_main;
     const int es = (int)(f % 2);
-    int rc = enqueue_gftt_select(s, t->d_sc, t->fa.kept_pts, t->cfg.max_cnt, t->d_eig[es], t->epitch, nullptr, 0, t->w, t->h,
-                                 t->cfg.min_dist, t->grid, t->grid_cells);
+    int rc = enqueue_gftt_select(s, t->d_sc, t->fa.kept_pts, t->d_eig[es], t->epitch, t->w, t->h, t->cfg.min_dist, t->grid);
     if (rc) return rc;
     GF_MARK(4, s);
     // reference quirk: depth_cam with an empty depth image produces an empty featureFrame (feature_tracker.cpp:342)
@@ -803,10 +795,10 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
     if (!img || !corners || !n_corners || max_corners < 0 || n_kept < 0 || n_kept + max_corners > FE_CAP || min_dist < 5 || min_dist > 255)
         return set_err(GF_ERR_INVALID_ARG, "bad argument");
     int rc = select_device(device); if (rc) return rc;
-    DevBuf di, de, dm, s0, s1, dsc, dk, dhdr, dobs, dummy[8]; int ip;
+    DevBuf di, de, s0, s1, dsc, dk, dhdr, dobs, dummy[8]; int ip;
     rc = upload_image(img, w, h, di, ip); if (rc) return rc;
-    int ep = align_up(w, 4), mp = align_up(w, 16);
-    if ((rc = de.alloc((size_t)ep * h * 4)) || (rc = dm.alloc((size_t)mp * h)) || (rc = s0.alloc(cov_rows_elems(w, h) * 8)) ||
+    int ep = align_up(w, 4);
+    if ((rc = de.alloc((size_t)ep * h * 4)) || (rc = s0.alloc(cov_rows_elems(w, h) * 8)) ||
         (rc = s1.alloc(box_elems(w, h) * 4)) || (rc = dsc.alloc(sizeof(TrackScalars))) || (rc = dk.alloc((size_t)FE_CAP * 8)) ||
         (rc = dhdr.alloc(sizeof(OutHeader))) || (rc = dobs.alloc(FE_CAP * sizeof(gf_obs))))
         return rc;
@@ -821,7 +813,7 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
     TrackScalars* sc = dsc.as<TrackScalars>();
     GF_CUDA(cudaMemset(s0.p, 0, cov_rows_elems(w, h) * 8));
     rc = enqueue_min_eig(0, L, de.as<float>(), ep, s0.as<double>(), s1.as<float>());
-    if (!rc) rc = enqueue_gftt_select(0, sc, dk.as<float2>(), n_kept, de.as<float>(), ep, dm.as<uint8_t>(), mp, w, h, min_dist, grid, cells);
+    if (!rc) rc = enqueue_gftt_select(0, sc, dk.as<float2>(), de.as<float>(), ep, w, h, min_dist, grid);
     if (!rc) {
         FeatArrays fa;
         fa.prev_pts = dummy[0].as<float2>(); fa.ids = dummy[1].as<int>(); fa.track_cnt = dummy[2].as<int>(); fa.prev_un = dummy[3].as<float2>();
