@@ -1161,6 +1161,154 @@ __global__ void __launch_bounds__(1024) k_jacobi_eig(double* Ag, double* Vg, dou
     if (tid == 0 && sweeps_out) *sweeps_out = sweep;
 }
 
+// Symmetric eigendecomposition for the reduced system of the marginalisation (n <= 128): Householder tridiagonalisation +
+// implicit-shift QL (EISPACK tred2 / tql2, the algorithm family of Eigen's SelfAdjointEigenSolver; same restatement as
+// oracle/ba_oracle.c sym_eig_ql).  One CTA of 128 threads, V column-major in shared memory.  The Householder steps are
+// thread-parallel over rows/columns; in the QL phase thread 0 runs the scalar recurrence of a sweep and publishes the plane
+// rotations, then every thread applies them to its own row of V.
+constexpr int QL_T = 128;
+__global__ void __launch_bounds__(QL_T) k_sym_eig_ql(const double* __restrict__ Ag, double* __restrict__ Vg, double* __restrict__ wg, int n)
+{
+    extern __shared__ double qsm[];          // V[n*n] | d[n] | e[n+1] | rc[n] | rs[n]
+    __shared__ double sred[32];
+    __shared__ double sh_h, sh_scale, sh_hh;
+    __shared__ int sh_m, sh_more;
+    double* V = qsm; double* d = V + (size_t)n * n; double* e = d + n; double* rc = e + n + 1; double* rs = rc + n;
+    const int tid = threadIdx.x;
+#define VV(i, j) V[(size_t)(j) * n + (i)]
+    for (int t = tid; t < n * n; t += QL_T) V[t] = Ag[t];              // symmetric: row-major == column-major
+    __syncthreads();
+    for (int j = tid; j < n; j += QL_T) d[j] = VV(n - 1, j);
+    __syncthreads();
+    for (int i = n - 1; i > 0; i--) {                                   // ---- tred2 ----
+        double sc = 0.0;
+        for (int k = tid; k < i; k += QL_T) sc += fabs(d[k]);
+        sc = block_reduce_sum(sc, sred);
+        if (sc == 0.0) {
+            if (tid == 0) e[i] = d[i - 1];
+            __syncthreads();
+            for (int j = tid; j < i; j += QL_T) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; VV(j, i) = 0.0; }
+            __syncthreads();
+        } else {
+            double hs = 0.0;
+            for (int k = tid; k < i; k += QL_T) { const double t = d[k] / sc; d[k] = t; hs += t * t; }
+            hs = block_reduce_sum(hs, sred);
+            if (tid == 0) {
+                double f = d[i - 1], g = sqrt(hs);
+                if (f > 0) g = -g;
+                e[i] = sc * g; sh_h = hs - f * g; d[i - 1] = f - g;
+            }
+            __syncthreads();
+            const double h = sh_h;
+            // e = (symmetric matrix held in the lower triangle) * d, V[j][i] = d[j]
+            for (int j = tid; j < i; j += QL_T) {
+                double g = 0.0;
+                for (int k = 0; k <= j; k++) g += VV(j, k) * d[k];
+                for (int k = j + 1; k < i; k++) g += VV(k, j) * d[k];
+                rc[j] = g / h;                                       // e[j] / h (kept aside: VV(j, i) aliases nothing of e)
+                VV(j, i) = d[j];
+            }
+            __syncthreads();
+            double fs = 0.0;
+            for (int j = tid; j < i; j += QL_T) fs += rc[j] * d[j];
+            fs = block_reduce_sum(fs, sred);
+            const double hh = fs / (h + h);
+            for (int j = tid; j < i; j += QL_T) e[j] = rc[j] - hh * d[j];
+            __syncthreads();
+            for (int t = tid; t < i * i; t += QL_T) {                    // rank-2 update of the lower triangle
+                const int j = t / i, k = t - j * i;
+                if (k >= j) VV(k, j) -= (d[j] * e[k] + e[j] * d[k]);
+            }
+            __syncthreads();
+            for (int j = tid; j < i; j += QL_T) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; }
+            if (tid == 0) d[i] = h;
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) d[i] = 0.0;
+        __syncthreads();
+    }
+    for (int i = 0; i < n - 1; i++) {                                   // ---- accumulate the transformations ----
+        if (tid == 0) { VV(n - 1, i) = VV(i, i); VV(i, i) = 1.0; }
+        __syncthreads();
+        const double h = d[i + 1];
+        if (h != 0.0) {
+            for (int k = tid; k <= i; k += QL_T) rc[k] = VV(k, i + 1) / h;
+            __syncthreads();
+            for (int j = tid; j <= i; j += QL_T) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
+                for (int k = 0; k <= i; k++) VV(k, j) -= g * rc[k];
+            }
+            __syncthreads();
+        }
+        for (int k = tid; k <= i; k += QL_T) VV(k, i + 1) = 0.0;
+        __syncthreads();
+    }
+    for (int j = tid; j < n; j += QL_T) { d[j] = VV(n - 1, j); VV(n - 1, j) = 0.0; }
+    __syncthreads();
+    if (tid == 0) { VV(n - 1, n - 1) = 1.0; for (int i = 1; i < n; i++) e[i - 1] = e[i]; e[n - 1] = 0.0; }
+    __syncthreads();
+    // ---- tql2 ----
+    double f = 0.0, tst1 = 0.0;                                          // thread 0's scalars
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        if (tid == 0) {
+            const double t = fabs(d[l]) + fabs(e[l]);
+            if (t > tst1) tst1 = t;
+            int m = l;
+            while (m < n) { if (fabs(e[m]) <= eps * tst1) break; m++; }
+            sh_m = m;
+        }
+        __syncthreads();
+        const int m = sh_m;
+        if (m > l) {
+            int iter = 0;
+            while (true) {
+                if (tid == 0) {
+                    iter++;
+                    double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = hypot(p, 1.0);
+                    if (p < 0) r = -r;
+                    d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
+                    const double dl1 = d[l + 1];
+                    double h = g - d[l];
+                    for (int i = l + 2; i < n; i++) d[i] -= h;
+                    f += h;
+                    p = d[m];
+                    double c = 1.0, c2 = c, c3 = c, s_ = 0.0, s2 = 0.0;
+                    const double el1 = e[l + 1];
+                    for (int i = m - 1; i >= l; i--) {
+                        c3 = c2; c2 = c; s2 = s_;
+                        g = c * e[i]; h = c * p; r = hypot(p, e[i]);
+                        e[i + 1] = s_ * r; s_ = e[i] / r; c = p / r; p = c * d[i] - s_ * g; d[i + 1] = h + s_ * (c * g + s_ * d[i]);
+                        rc[i] = c; rs[i] = s_;
+                    }
+                    p = -s_ * s2 * c3 * el1 * e[l] / dl1; e[l] = s_ * p; d[l] = c * p;
+                    sh_more = (fabs(e[l]) > eps * tst1 && iter < 200) ? 1 : 0;
+                }
+                __syncthreads();
+                if (tid < n) {                                           // this thread's row of V
+                    const int k = tid;
+                    double hi = VV(k, m);
+                    for (int i = m - 1; i >= l; i--) {
+                        const double c = rc[i], s_ = rs[i], lo = VV(k, i);
+                        VV(k, i + 1) = s_ * lo + c * hi;
+                        hi = c * lo - s_ * hi;
+                    }
+                    VV(k, l) = hi;
+                }
+                __syncthreads();
+                if (!sh_more) break;
+            }
+        }
+        if (tid == 0) { d[l] = d[l] + f; e[l] = 0.0; }
+        __syncthreads();
+    }
+    for (int t = tid; t < n * n; t += QL_T) { const int i = t / n, j = t - i * n; Vg[t] = VV(i, j); }     // row-major out, columns = eigenvectors
+    for (int j = tid; j < n; j += QL_T) wg[j] = d[j];
+#undef VV
+}
+
 struct MargDev {
     int N, m, n;
     const double *H, *Hp, *g;     // accumulated by k_ba_eval (N x N, N)
@@ -1349,6 +1497,7 @@ int gf_ba_create(gf_ba** out, int device)
     GF_CUDA(cudaEventCreate(&s->e0)); GF_CUDA(cudaEventCreate(&s->e1));
     GF_CUDA(cudaFuncSetAttribute(k_ba_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     GF_CUDA(cudaFuncSetAttribute(k_jacobi_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GF_CUDA(cudaFuncSetAttribute(k_sym_eig_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     *out = s;
     return GF_OK;
 }
@@ -1734,8 +1883,12 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
         k_marg_T<<<(int)(((size_t)n * m + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
         k_marg_reduce<<<(int)((nn + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
     }
-    const bool r_in_smem = jac_smem(n, true) <= 200 * 1024;
-    k_jacobi_eig<<<1, 1024, jac_smem(n, r_in_smem), st>>>(q.Ar, q.Vr, q.wr, n, (int*)(db + o_sw) + 1, r_in_smem ? 1 : 0); GF_LAUNCHED();
+    if (n <= 128) {   // tridiagonalisation + implicit QL in shared memory (what the reference's Eigen solver does)
+        k_sym_eig_ql<<<1, QL_T, sizeof(double) * ((size_t)n * n + 4 * (size_t)n + 8), st>>>(q.Ar, q.Vr, q.wr, n); GF_LAUNCHED();
+    } else {
+        const bool r_in_smem = jac_smem(n, true) <= 200 * 1024;
+        k_jacobi_eig<<<1, 1024, jac_smem(n, r_in_smem), st>>>(q.Ar, q.Vr, q.wr, n, (int*)(db + o_sw) + 1, r_in_smem ? 1 : 0); GF_LAUNCHED();
+    }
     k_marg_out<<<(int)((nn + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpyAsync(hb + o_J0, db + o_J0, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));

@@ -207,6 +207,99 @@ static void sym_eig(const double* Ain, int n, double* w, double* V)
     free(A);
 }
 
+/* Symmetric eigendecomposition the way Eigen's SelfAdjointEigenSolver does it -- Householder tridiagonalisation followed
+ * by implicit-shift QL -- restated from the classic EISPACK tred2 / tql2 routines (public domain; Eigen's implementation
+ * is the same algorithm family).  V: row-major n x n, columns = eigenvectors; w: eigenvalues (unsorted order of
+ * deflation, as needed by the marginalisation, which is order-independent). */
+static void sym_eig_ql(const double* Ain, int n, double* w, double* V)
+{
+    double* d = w;
+    double* e = (double*)malloc(sizeof(double) * (n + 1));
+    memcpy(V, Ain, sizeof(double) * n * n);          /* symmetric: row-major == column-major */
+#define VV(i, j) V[(size_t)(j) * n + (i)]              /* column-major while working: the inner loops run down columns */
+    for (int j = 0; j < n; j++) d[j] = VV(n - 1, j);
+    for (int i = n - 1; i > 0; i--) {                       /* tred2 */
+        double scale = 0.0, h = 0.0;
+        for (int k = 0; k < i; k++) scale += fabs(d[k]);
+        if (scale == 0.0) {
+            e[i] = d[i - 1];
+            for (int j = 0; j < i; j++) { d[j] = VV(i - 1, j); VV(i, j) = 0.0; VV(j, i) = 0.0; }
+        } else {
+            for (int k = 0; k < i; k++) { d[k] /= scale; h += d[k] * d[k]; }
+            double f = d[i - 1], g = sqrt(h);
+            if (f > 0) g = -g;
+            e[i] = scale * g; h = h - f * g; d[i - 1] = f - g;
+            for (int j = 0; j < i; j++) e[j] = 0.0;
+            for (int j = 0; j < i; j++) {
+                f = d[j]; VV(j, i) = f; g = e[j] + VV(j, j) * f;
+                for (int k = j + 1; k <= i - 1; k++) { g += VV(k, j) * d[k]; e[k] += VV(k, j) * f; }
+                e[j] = g;
+            }
+            f = 0.0;
+            for (int j = 0; j < i; j++) { e[j] /= h; f += e[j] * d[j]; }
+            double hh = f / (h + h);
+            for (int j = 0; j < i; j++) e[j] -= hh * d[j];
+            for (int j = 0; j < i; j++) {
+                f = d[j]; g = e[j];
+                for (int k = j; k <= i - 1; k++) VV(k, j) -= (f * e[k] + g * d[k]);
+                d[j] = VV(i - 1, j); VV(i, j) = 0.0;
+            }
+        }
+        d[i] = h;
+    }
+    for (int i = 0; i < n - 1; i++) {                       /* accumulate the transformations */
+        VV(n - 1, i) = VV(i, i); VV(i, i) = 1.0;
+        double h = d[i + 1];
+        if (h != 0.0) {
+            for (int k = 0; k <= i; k++) d[k] = VV(k, i + 1) / h;
+            for (int j = 0; j <= i; j++) {
+                double g = 0.0;
+                for (int k = 0; k <= i; k++) g += VV(k, i + 1) * VV(k, j);
+                for (int k = 0; k <= i; k++) VV(k, j) -= g * d[k];
+            }
+        }
+        for (int k = 0; k <= i; k++) VV(k, i + 1) = 0.0;
+    }
+    for (int j = 0; j < n; j++) { d[j] = VV(n - 1, j); VV(n - 1, j) = 0.0; }
+    VV(n - 1, n - 1) = 1.0; e[0] = 0.0;
+    for (int i = 1; i < n; i++) e[i - 1] = e[i];            /* tql2 */
+    e[n - 1] = 0.0;
+    double f = 0.0, tst1 = 0.0;
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < n; l++) {
+        double t = fabs(d[l]) + fabs(e[l]);
+        if (t > tst1) tst1 = t;
+        int m = l;
+        while (m < n) { if (fabs(e[m]) <= eps * tst1) break; m++; }
+        if (m > l) {
+            int iter = 0;
+            do {
+                iter++;
+                double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = hypot(p, 1.0);
+                if (p < 0) r = -r;
+                d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
+                double dl1 = d[l + 1], h = g - d[l];
+                for (int i = l + 2; i < n; i++) d[i] -= h;
+                f += h;
+                p = d[m];
+                double c = 1.0, c2 = c, c3 = c, el1 = e[l + 1], s = 0.0, s2 = 0.0;
+                for (int i = m - 1; i >= l; i--) {
+                    c3 = c2; c2 = c; s2 = s;
+                    g = c * e[i]; h = c * p; r = hypot(p, e[i]);
+                    e[i + 1] = s * r; s = e[i] / r; c = p / r; p = c * d[i] - s * g; d[i + 1] = h + s * (c * g + s * d[i]);
+                    for (int k = 0; k < n; k++) { h = VV(k, i + 1); VV(k, i + 1) = s * VV(k, i) + c * h; VV(k, i) = c * VV(k, i) - s * h; }
+                }
+                p = -s * s2 * c3 * el1 * e[l] / dl1; e[l] = s * p; d[l] = c * p;
+            } while (fabs(e[l]) > eps * tst1 && iter < 200);
+        }
+        d[l] = d[l] + f; e[l] = 0.0;
+    }
+#undef VV
+    for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) { double t = V[(size_t)i * n + j]; V[(size_t)i * n + j] = V[(size_t)j * n + i]; V[(size_t)j * n + i] = t; }
+    free(e);
+}
+GFO void gfo_sym_eig(const double* A, int n, double* w, double* V, int method) { if (method == 0) sym_eig(A, n, w, V); else sym_eig_ql(A, n, w, V); }
+
 /* ------------------------------------------------------------------ factors --------------------- */
 /* ProjectionTwoFrameOneCamFactor::Evaluate (projectionTwoFrameOneCamFactor.cpp:43-151).
  * Jacobians are row-major num_residuals x global_size, any may be NULL. */

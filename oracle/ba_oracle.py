@@ -33,6 +33,8 @@ def lib():
         L.gfo_ba_set_tolerances.argtypes = [ctypes.c_double] * 3
         L.gfo_ba_set_tolerances.restype = None
         L.gfo_sqrt_info.argtypes = [_dp, ctypes.c_int, _dp]
+        L.gfo_sym_eig.argtypes = [_dp, ctypes.c_int, _dp, _dp, ctypes.c_int]
+        L.gfo_sym_eig.restype = None
         L.gfo_eval_plane.argtypes = [_dp, _dp, _dp, ctypes.c_double, _dp, _dp, _dp, _dp, _dp, _dp]
         L.gfo_eval_plane.restype = None
         L.gfo_eval_wheel.argtypes = [ctypes.POINTER(BaWheelFactor), _dp, _dp, _dp] + [ctypes.c_double] * 4 + [_dp] * 8
@@ -112,3 +114,13 @@ def eval_plane(pose_i, exw, qpw, zpw, sinfo, jac=True):
     lib().gfo_eval_plane(a[0].ctypes.data_as(_dp), a[1].ctypes.data_as(_dp), a[2].ctypes.data_as(_dp), float(zpw), a[3].ctypes.data_as(_dp),
                          res.ctypes.data_as(_dp), *ptrs)
     return res, Js
+
+
+def sym_eig(A, method="ql"):
+    """Eigendecomposition of a symmetric matrix by the oracle's solvers: "jacobi" (cyclic Jacobi, used by marginalize_old) or
+    "ql" (Householder tridiagonalisation + implicit QL, the algorithm of the reference's Eigen solver).  Returns (w, V)."""
+    A = np.ascontiguousarray(A, np.float64)
+    n = A.shape[0]
+    w = np.zeros(n); V = np.zeros((n, n))
+    lib().gfo_sym_eig(A.ctypes.data_as(_dp), n, w.ctypes.data_as(_dp), V.ctypes.data_as(_dp), 0 if method == "jacobi" else 1)
+    return w, V

@@ -330,3 +330,23 @@ def test_plane_factor_jacobians_match_finite_differences_and_solve_moves_the_pla
     q1 = pb2.para_plane_R.copy()
     s2 = O.solve(pb2)
     assert s2["reduced_dim"] == 165 and np.array_equal(pb2.para_plane_R, q1)
+
+
+def test_eigensolvers_agree_with_numpy_and_with_each_other():
+    """The two symmetric eigensolvers of the oracle (cyclic Jacobi; tred2 + tql2 as restated for the CUDA kernel
+    k_sym_eig_ql) against numpy.linalg.eigvalsh, including rank-deficient and badly scaled matrices."""
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 7, 40, 76):
+        for kind in range(3):
+            B = rng.normal(size=(n, n if kind != 1 else max(1, n - 3)))
+            A = B @ B.T
+            if kind == 2:
+                sc = 10.0 ** rng.uniform(-3, 4, n)
+                A = A * np.outer(sc, sc)
+            A = 0.5 * (A + A.T)
+            want = np.linalg.eigvalsh(A)
+            for method in ("jacobi", "ql"):
+                w, V = O.sym_eig(A, method)
+                assert np.abs(np.sort(w) - want).max() <= 1e-12 * max(np.abs(want).max(), 1e-300), (n, kind, method)
+                assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+                assert np.abs(V @ np.diag(w) @ V.T - A).max() <= 1e-12 * max(np.abs(A).max(), 1e-300)
