@@ -1,2 +1,11 @@
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_ba_step -s 3 -c 1 -o gpurun_out/k_ba_step_r1b -f python tools/prof_ba.py 1 > /dev/null 2>&1
-ls -la gpurun_out/k_ba_step_r1b.ncu-rep
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 200 python - <<'PY'
+import sys, time; sys.path.insert(0, '.')
+from ground_fusion_b200.estimator import BundleAdjuster
+from ground_fusion_b200.synth_ba import make_window
+ba = BundleAdjuster(0)
+pb, _ = make_window(seed=100)
+ba.optimization(pb)
+for k in range(3):
+    pr = ba.marginalize_old(pb); print("marg device ms %.3f" % ba.last_marg_ms)
+PY
