@@ -350,3 +350,24 @@ def test_eigensolvers_agree_with_numpy_and_with_each_other():
                 assert np.abs(np.sort(w) - want).max() <= 1e-12 * max(np.abs(want).max(), 1e-300), (n, kind, method)
                 assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
                 assert np.abs(V @ np.diag(w) @ V.T - A).max() <= 1e-12 * max(np.abs(A).max(), 1e-300)
+
+
+GOLDEN_CASES = {"ba_c2_seed0": dict(seed=0), "ba_c3_wheel_seed1": dict(seed=1, with_wheel=True), "ba_plane_seed2": dict(seed=2, with_plane=True)}
+
+
+def _golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_oracle_matches_committed_golden_fixtures(name):
+    """tests/golden/ba_*.npz (made by tests/golden/make_ba_golden.py): regression pin of the oracle itself."""
+    g = _golden(name)
+    pb, _ = make_window(**GOLDEN_CASES[name])
+    s = O.solve(pb)
+    assert s["iterations"] == int(g["iterations"]) and s["termination"] == int(g["termination"]) and s["reduced_dim"] == int(g["reduced_dim"])
+    assert np.allclose(s["cost"], g["cost"], rtol=1e-12) and np.allclose(s["radius"], g["radius"], rtol=1e-12)
+    for k in ("para_pose", "para_speed_bias", "para_feature", "para_ex_pose", "para_td", "para_ex_wheel", "para_ix_wheel", "para_td_wheel",
+              "para_plane_R", "para_plane_Z"):
+        assert np.allclose(getattr(pb, k), g[k], rtol=0, atol=1e-12), k
