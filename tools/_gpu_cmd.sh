@@ -1,11 +1,4 @@
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 200 python - <<'PY'
-import sys, time; sys.path.insert(0, '.')
-from ground_fusion_b200.estimator import BundleAdjuster
-from ground_fusion_b200.synth_ba import make_window
-ba = BundleAdjuster(0)
-pb, _ = make_window(seed=100)
-ba.optimization(pb)
-for k in range(3):
-    pr = ba.marginalize_old(pb); print("marg device ms %.3f" % ba.last_marg_ms)
-PY
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python bench.py 2>gpurun_out/bench.err | tail -1 > gpurun_out/bench18.json; python -c "
+import json; d=json.load(open('gpurun_out/bench18.json')); print(d['value'], d['e2e']['value'], d['cpu_baseline']['value'], d['ba']['value'], d['ba']['cpu_baseline']['value'], d['ba']['marginalize_old'], d['ba']['concurrent_streams']['value'])"
