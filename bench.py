@@ -218,15 +218,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from ground_fusion_b200 import _lib
     from ground_fusion_b200.feature_tracker import FeatureTracker
-    from oracle.fe_oracle import IDC_CAM, PinholeCamera   # camera constants only (config/realsense/idc_cam.yaml)
+    from ground_fusion_b200.synth import idc_params8      # config/realsense/idc_cam.yaml
 
     gray, depth = make_frames(rank, args.ring)
     d_gray = torch.from_numpy(gray).cuda()
     d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
     h_gray = torch.from_numpy(gray).pin_memory(); h_depth = torch.from_numpy(depth.view(np.int16)).pin_memory()
     hg, hd = h_gray.numpy(), h_depth.numpy().view(np.uint16)
-    cam = PinholeCamera(**IDC_CAM)
-    tr = FeatureTracker(W, H, cam.params8(), MAX_CNT, MIN_DIST, 1, 1, device=local)
+    tr = FeatureTracker(W, H, idc_params8(), MAX_CNT, MIN_DIST, 1, 1, device=local)
 
     def barrier():
         torch.cuda.synchronize()

@@ -9,6 +9,17 @@ import math
 
 import numpy as np
 
+# config/realsense/idc_cam.yaml of the reference (PINHOLE: fx fy cx cy, radtan k1 k2 p1 p2): the camera of configs C1-C3
+IDC_CAM = dict(fx=6.2097277909374247e+02, fy=6.2212293397677581e+02, cx=3.1175896455154810e+02,
+               cy=2.4718077836114819e+02, k1=1.4865749308203452e-01, k2=-4.6815685578576460e-01,
+               p1=1.6205585303208318e-03, p2=-8.9101576735577930e-03)
+
+
+def idc_params8():
+    """gf_tracker_cfg.pinhole order: fx fy cx cy k1 k2 p1 p2."""
+    c = IDC_CAM
+    return [c["fx"], c["fy"], c["cx"], c["cy"], c["k1"], c["k2"], c["p1"], c["p2"]]
+
 try:
     import cv2
 except Exception:  # pragma: no cover

@@ -111,9 +111,7 @@ class PinholeCamera:
         return self.fx * x + self.cx, self.fy * y + self.cy
 
 
-IDC_CAM = dict(fx=6.2097277909374247e+02, fy=6.2212293397677581e+02, cx=3.1175896455154810e+02,
-               cy=2.4718077836114819e+02, k1=1.4865749308203452e-01, k2=-4.6815685578576460e-01,
-               p1=1.6205585303208318e-03, p2=-8.9101576735577930e-03)  # config/realsense/idc_cam.yaml
+from ground_fusion_b200.synth import IDC_CAM  # noqa: E402  (config/realsense/idc_cam.yaml; shared with bench.py's GPU arm)
 
 
 class FeatureTrackerOracle:

@@ -5,9 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ground_fusion_b200.feature_tracker import FeatureTracker
 from ground_fusion_b200._lib import lib
 from ground_fusion_b200.synth import SyntheticStream
-from oracle.fe_oracle import IDC_CAM, PinholeCamera
+from ground_fusion_b200.synth import idc_params8
 st = SyntheticStream(seed=0)
-tr = FeatureTracker(640, 480, PinholeCamera(**IDC_CAM).params8(), 150, 30, 1, 1)
+tr = FeatureTracker(640, 480, idc_params8(), 150, 30, 1, 1)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 N = 64 + 8 * 150
 buf = (ctypes.c_longlong * N)()
