@@ -124,3 +124,36 @@ def test_double2vector_matches_numpy_restatement():
                 assert np.abs(Ps[0] - P0).max() < 1e-12
                 if trial % 5 != 4:
                     assert abs(G.R2ypr(Rs[0])[0] - G.R2ypr(R0)[0]) < 1e-9
+
+
+def test_header_is_valid_c_and_cxx_and_matches_the_ctypes_mirror(tmp_path):
+    """include/gf_b200.h must compile as C99 and as C++11 on its own (it is what the reference-side adaptor includes), and
+    the ctypes mirrors in ground_fusion_b200/_lib.py must agree with it on every struct size and on the offsets of the last
+    members (ABI drift between the header and the Python host side is otherwise silent)."""
+    import ctypes
+    import subprocess
+    from ground_fusion_b200 import _lib
+    inc = os.path.join(ROOT, "include")
+    structs = {"gf_tracker_cfg": _lib.TrackerCfg, "gf_obs": _lib.Obs, "gf_track_info": _lib.TrackInfo,
+               "gf_ba_visual_factor": _lib.BaVisualFactor, "gf_ba_imu_factor": _lib.BaImuFactor, "gf_ba_wheel_factor": _lib.BaWheelFactor,
+               "gf_ba_prior": _lib.BaPrior, "gf_ba_problem": _lib.BaProblem, "gf_ba_summary": _lib.BaSummary}
+    last = {"gf_ba_problem": "plane_sqrt_info", "gf_ba_wheel_factor": "gyr_1", "gf_ba_prior": "linearized_residuals", "gf_ba_summary": "device_ms",
+            "gf_tracker_cfg": "pinhole"}
+    body = '#include <stdio.h>\n#include <stddef.h>\n#include "gf_b200.h"\nint main(void) {\n'
+    for name in structs:
+        body += '  printf("%s %%zu\\n", sizeof(%s));\n' % (name, name)
+    for name, member in last.items():
+        body += '  printf("%s.%s %%zu\\n", offsetof(%s, %s));\n' % (name, member, name, member)
+    body += "  return 0;\n}\n"
+    out = {}
+    for comp, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "cpp")):
+        src = tmp_path / ("abi." + ext)
+        src.write_text(body)
+        exe = tmp_path / ("abi_" + ext)
+        subprocess.check_call([comp, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe)])
+        out[ext] = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert out["c"] == out["cpp"]
+    for name, cls in structs.items():
+        assert int(out["c"][name]) == ctypes.sizeof(cls), (name, out["c"][name], ctypes.sizeof(cls))
+    for name, member in last.items():
+        assert int(out["c"]["%s.%s" % (name, member)]) == getattr(structs[name], member).offset, (name, member)
