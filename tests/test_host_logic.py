@@ -157,3 +157,63 @@ def test_header_is_valid_c_and_cxx_and_matches_the_ctypes_mirror(tmp_path):
         assert int(out["c"][name]) == ctypes.sizeof(cls), (name, out["c"][name], ctypes.sizeof(cls))
     for name, member in last.items():
         assert int(out["c"]["%s.%s" % (name, member)]) == getattr(structs[name], member).offset, (name, member)
+
+
+def test_parallel_partition_formulation_equals_unguarded_partition():
+    """fe_sort.cuh replays libstdc++'s __unguarded_partition_pivot with one warp per range: L = ascending positions where
+    `lo` stops, R = descending positions where `hi` stops (both on the ORIGINAL range, after the median-of-3 move), swap k
+    exchanges L[k] and R[k] while L[k] < R[k], cut = min(L[k*], R[k*-1]).  This model of the kernel's index arithmetic is
+    checked against the sequential algorithm on random ranges with heavy ties (the GPU test compares the kernel itself with
+    std::sort)."""
+    import random
+
+    def comp(a, b):
+        return a[0] > b[0]
+
+    def sequential(v, first, last):
+        v = list(v)
+        mid = first + (last - first) // 2
+        a, b, c = first + 1, mid, last - 1
+
+        def sw(i, j):
+            v[i], v[j] = v[j], v[i]
+        if comp(v[a], v[b]):
+            if comp(v[b], v[c]): sw(first, b)
+            elif comp(v[a], v[c]): sw(first, c)
+            else: sw(first, a)
+        elif comp(v[a], v[c]): sw(first, a)
+        elif comp(v[b], v[c]): sw(first, c)
+        else: sw(first, b)
+        after_median = list(v)
+        lo, hi = first + 1, last
+        while True:
+            while comp(v[lo], v[first]): lo += 1
+            hi -= 1
+            while comp(v[first], v[hi]): hi -= 1
+            if not lo < hi:
+                return v, lo, after_median
+            sw(lo, hi); lo += 1
+
+    def parallel(med, first, last):
+        v = list(med); pv = v[first][0]
+        L = [p for p in range(first + 1, last) if not v[p][0] > pv]
+        R = [p for p in range(first + 1, last) if not pv > v[p][0]][::-1]
+        m = min(len(L), len(R))
+        ks = sum(1 for k in range(m) if L[k] < R[k])
+        for k in range(ks):
+            v[L[k]], v[R[k]] = v[R[k]], v[L[k]]
+        cut = 10 ** 9
+        if ks < len(L): cut = L[ks]
+        if ks >= 1: cut = min(cut, R[ks - 1])
+        return v, cut
+
+    random.seed(1)
+    for _ in range(20000):
+        n = random.randint(17, 80)
+        span = random.choice([1, 2, 3, 6, 50])
+        v = [(random.randint(1, span), i) for i in range(n)]
+        if random.random() < 0.3:
+            v.sort(key=lambda e: -e[0])
+        vs, cs, med = sequential(v, 0, n)
+        vp, cp = parallel(med, 0, n)
+        assert vs == vp and cs == cp
