@@ -217,3 +217,42 @@ def test_parallel_partition_formulation_equals_unguarded_partition():
         vs, cs, med = sequential(v, 0, n)
         vp, cp = parallel(med, 0, n)
         assert vs == vp and cs == cp
+
+
+def test_cell_head_rounds_equal_the_sequential_greedy_min_distance_pass():
+    """Model of nms_cells (fe_select.cuh): candidates ranked by a unique key bid for the head of their r-sized cell; a head
+    that outranks the heads of the 8 surrounding cells is accepted, accepted corners kill alive candidates closer than r in
+    the next round.  The accepted SET must equal cv::goodFeaturesToTrack's sequential greedy (accept in rank order unless an
+    accepted corner lies within d^2 < r^2)."""
+    rng = np.random.default_rng(7)
+    for trial in range(60):
+        w, h = int(rng.integers(60, 400)), int(rng.integers(60, 300))
+        r = int(rng.integers(5, 40)); cs = max(r, 16)
+        n = int(rng.integers(1, 600))
+        xs = rng.integers(1, w - 1, n); ys = rng.integers(1, h - 1, n)
+        pts = list({(int(x), int(y)) for x, y in zip(xs, ys)})
+        keys = rng.permutation(len(pts))                     # distinct ranks, larger = better
+        order = sorted(range(len(pts)), key=lambda i: -keys[i])
+        seq = []
+        for i in order:
+            x, y = pts[i]
+            if all((x - a) ** 2 + (y - b) ** 2 >= r * r for a, b in seq):
+                seq.append((x, y))
+        alive = set(range(len(pts))); acc = []; new = []
+        rounds = 0
+        while alive:
+            rounds += 1
+            alive = {i for i in alive if all((pts[i][0] - a) ** 2 + (pts[i][1] - b) ** 2 >= r * r for a, b in new)}
+            head = {}
+            for i in alive:
+                c = (pts[i][0] // cs, pts[i][1] // cs)
+                if c not in head or keys[i] > keys[head[c]]:
+                    head[c] = i
+            new = []
+            for c, i in head.items():
+                if all(keys[head.get((c[0] + dx, c[1] + dy), i)] <= keys[i] for dx in (-1, 0, 1) for dy in (-1, 0, 1)):
+                    new.append(pts[i]); alive.discard(i)
+            assert new or not alive, "the globally best head can always decide"
+            acc += new
+            assert rounds < 200
+        assert sorted(acc) == sorted(seq), (trial, len(acc), len(seq))
