@@ -98,6 +98,25 @@ def cpu_reference_fps(gray, depth, budget_s, warm=3):
     return done / dt, done, cv2.getNumThreads()
 
 
+def ba_roofline(nc, n_lm, iterations, device_ms, step_share=0.77):
+    """Algorithmic FP64 work of k_ba_step (the dominant kernel: 77 % of a solve's kernel time in
+    profiles/r1_ncu_launches_ba_v5.csv) against the FP64 rate of the ONE SM a single-CTA kernel can use (58 DFMA/clk measured
+    on a B200 SM).  Per launch: Cholesky of the (nc+1)-row reduced system (nc+1)^3/3 FMA, the two triangular solves nc^2 FMA,
+    landmark back-substitution and dogleg / model terms ~3*n_lm*nc FMA."""
+    launches = iterations + 1
+    fma = iterations * ((nc + 1) ** 3 / 3.0 + nc * nc + 3.0 * n_lm * nc)
+    flops = 2.0 * fma
+    sm_peak = 58.0 * 2 * 1.965e9
+    t = step_share * device_ms * 1e-3
+    ach = flops / t if t > 0 else None
+    return {"kernel": "k_ba_step (single CTA: adoption, register-blocked Cholesky with look-ahead, back substitution, dogleg)",
+            "bound": "latency: 43 dependent panels per factorisation, FP64 pipe 8 % busy (profiles/r1_ncu_k_ba_step_full.txt)",
+            "algorithmic_flops_per_launch": flops / launches, "launches_per_solve": launches,
+            "time_share_of_solve": step_share, "achieved": ach / 1e9 if ach else None, "unit": "GFLOP/s (FP64)",
+            "peak": sm_peak / 1e9, "peak_source": "58 DFMA/clk measured on one B200 SM x 1.965 GHz x 2 flop",
+            "frac": (ach / sm_peak) if ach else None}
+
+
 def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
     """Sliding-window solves/s (C2: 11 frames, ~1.5 k visual factors, 10 IMU factors, 8 iterations max) on the GPU
     through gf_ba_solve (host descriptor in, optimised blocks out: this IS the end-to-end call) next to the CPU oracle."""
@@ -126,6 +145,7 @@ def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
            "workload": "C2 window: 11 frames, %d visual factors, %d IMU factors, reduced system %d + %d free landmarks, max 8 iterations"
                        % (wins[0].n_visual, wins[0].n_imu, sm.reduced_dim, sm.n_free_landmarks),
            "e2e": "value already includes the host->device upload of the problem and the download of the blocks"}
+    out["roofline"] = ba_roofline(int(sm.reduced_dim), int(sm.n_free_landmarks), iters / reps, dev_ms / reps)
     # the marginalisation that ends Estimator::optimization() on a keyframe (MARGIN_OLD), on the solved window
     restore(0); ba.solve_struct(structs[0])
     ba.marginalize_old(wins[0])
