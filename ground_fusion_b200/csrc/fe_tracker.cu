@@ -293,6 +293,8 @@ const char* gf_last_error(void) { return g_err; }
 const char* gf_version(void) { return "gf_b200 0.1 sm_100a"; }
 uint64_t gf_kernel_launch_count(void) { return g_launches.load(); }
 
+static int tracker_init(gf_tracker* t, int width, int height, const gf_tracker_cfg* cfg);
+
 int gf_tracker_create(gf_tracker** out, int device, int width, int height, const gf_tracker_cfg* cfg)
 {
     if (!out || !cfg) return set_err(GF_ERR_INVALID_ARG, "null argument");
@@ -308,6 +310,22 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     if (!t) return set_err(GF_ERR_CUDA, "out of host memory");
     memset(t, 0, sizeof(*t));
     t->device = device; t->w = width; t->h = height; t->cfg = *cfg; t->cam = make_cam(cfg->pinhole);
+    rc = tracker_init(t, width, height, cfg);
+    if (rc) {                       // release whatever was created before the failure; keep the error text of the failure
+        char keep[sizeof(g_err)];
+        memcpy(keep, g_err, sizeof(keep));
+        gf_tracker_destroy(t);
+        cudaGetLastError();
+        memcpy(g_err, keep, sizeof(keep));
+        return rc;
+    }
+    *out = t;
+    return GF_OK;
+}
+
+static int tracker_init(gf_tracker* t, int width, int height, const gf_tracker_cfg* cfg)
+{
+    int rc;
     GF_CUDA(cudaStreamCreateWithFlags(&t->s_up, cudaStreamNonBlocking));
     GF_CUDA(cudaStreamCreateWithFlags(&t->s_pyr, cudaStreamNonBlocking));
     GF_CUDA(cudaStreamCreateWithFlags(&t->s_eig, cudaStreamNonBlocking));
@@ -366,7 +384,6 @@ int gf_tracker_create(gf_tracker** out, int device, int width, int height, const
     GF_CUDA(cudaHostAlloc(&t->h_tmp_xyz, FE_CAP * 3 * sizeof(double), cudaHostAllocDefault));
     t->use_graph = getenv("GF_NO_GRAPH") == nullptr;
     GF_CUDA(cudaDeviceSynchronize());
-    *out = t;
     return GF_OK;
 }
 
@@ -374,7 +391,7 @@ void gf_tracker_destroy(gf_tracker* t)
 {
     if (!t) return;
     cudaSetDevice(t->device);
-    cudaStreamSynchronize(t->s_up); cudaStreamSynchronize(t->s_pyr); cudaStreamSynchronize(t->s_eig); cudaStreamSynchronize(t->s_main); cudaStreamSynchronize(t->s_out);
+    cudaDeviceSynchronize();        // (a partially built tracker may lack some of its streams)
     for (int k = 0; k < 6; k++) {
         if (t->g_pyr[k]) cudaGraphExecDestroy(t->g_pyr[k]);
         if (t->g_eig[k]) cudaGraphExecDestroy(t->g_eig[k]);
@@ -385,8 +402,7 @@ void gf_tracker_destroy(gf_tracker* t)
     for (int i = 0; i < 2; i++) {
         cudaFree(t->d_depth[i]); cudaFree(t->d_eig[i]); cudaFree(t->d_out[i]); cudaFree(t->d_fp[i]);
         cudaFreeHost(t->h_out[i]); cudaFreeHost(t->h_fp[i]);
-        cudaEventDestroy(t->ev_up[i]); cudaEventDestroy(t->ev_pyr[i]); cudaEventDestroy(t->ev_eig[i]); cudaEventDestroy(t->ev_dep[i]);
-        cudaEventDestroy(t->ev_t0[i]); cudaEventDestroy(t->ev_out[i]);
+        for (cudaEvent_t e : {t->ev_up[i], t->ev_pyr[i], t->ev_eig[i], t->ev_dep[i], t->ev_t0[i], t->ev_out[i]}) if (e) cudaEventDestroy(e);
     }
     cudaFree(t->d_cov); cudaFree(t->d_box);
     free_nms_grid(t->grid);
@@ -396,9 +412,11 @@ void gf_tracker_destroy(gf_tracker* t)
     cudaFree(fa.kept_pts); cudaFree(fa.kept_ids); cudaFree(fa.kept_cnt); cudaFree(fa.kept_un); cudaFree(fa.pred_pts); cudaFree(fa.dbg);
     cudaFree(t->d_tmp_ids); cudaFree(t->d_tmp_xyz);
     cudaFreeHost(t->h_gray); cudaFreeHost(t->h_depth); cudaFreeHost(t->h_tmp_ids); cudaFreeHost(t->h_tmp_xyz);
-    cudaStreamDestroy(t->s_up); cudaStreamDestroy(t->s_pyr); cudaStreamDestroy(t->s_eig); cudaStreamDestroy(t->s_main); cudaStreamDestroy(t->s_out);
-    for (int i = 0; i < GF_FE_STAGES + 2; i++) cudaEventDestroy(t->ev_st[i]);
-    cudaEventDestroy(t->ev_span0); cudaEventDestroy(t->ev_span1);
+    for (cudaStream_t st_ : {t->s_up, t->s_pyr, t->s_eig, t->s_main, t->s_out}) if (st_) cudaStreamDestroy(st_);
+    for (int i = 0; i < GF_FE_STAGES + 2; i++) if (t->ev_st[i]) cudaEventDestroy(t->ev_st[i]);
+    if (t->ev_span0) cudaEventDestroy(t->ev_span0);
+    if (t->ev_span1) cudaEventDestroy(t->ev_span1);
+    cudaGetLastError();
     delete t;
 }
 
@@ -611,6 +629,32 @@ int gf_tracker_track_device(gf_tracker* t, double time, const void* d_gray, cons
     int rc = gf_tracker_submit_device(t, time, d_gray, d_depth);
     if (rc) return rc;
     return gf_tracker_wait(t, out, n_out, status_out, info);
+}
+
+int gf_tracker_track_batch(gf_tracker* t, int n, const double* times, const void* const* gray, size_t gray_pitch,
+                           const void* const* depth, size_t depth_pitch, int on_device,
+                           gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info)
+{
+    if (!t || n < 0 || (n > 0 && (!times || !gray))) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected");
+    if (t->profiling) return set_err(GF_ERR_INVALID_ARG, "profiling mode runs one frame at a time");
+    const size_t cap = (size_t)t->cfg.max_cnt;
+    int collected = 0;
+    auto collect = [&]() {
+        const int k = collected++;
+        return gf_tracker_wait(t, out ? out + (size_t)k * cap : nullptr, n_out ? n_out + k : nullptr,
+                               status_out ? status_out + (size_t)k * cap : nullptr, info ? info + k : nullptr);
+    };
+    for (int k = 0; k < n; k++) {
+        if (!gray[k]) return set_err(GF_ERR_INVALID_ARG, "null frame pointer");
+        const void* dk = depth ? depth[k] : nullptr;
+        int rc = on_device ? gf_tracker_submit_device(t, times[k], gray[k], dk)
+                           : gf_tracker_submit(t, times[k], (const uint8_t*)gray[k], gray_pitch, (const uint16_t*)dk, depth_pitch);
+        if (rc) return rc;
+        if (in_flight(t) == GF_PIPE) { rc = collect(); if (rc) return rc; }
+    }
+    while (in_flight(t) > 0) { int rc = collect(); if (rc) return rc; }
+    return GF_OK;
 }
 
 int gf_tracker_set_prediction(gf_tracker* t, const int32_t* ids, const double* xyz, int n)

@@ -129,10 +129,41 @@ class FeatureTracker:
                                              ctypes.byref(n), self._status.ctypes.data, ctypes.byref(info)))
         return self._collect(n, info)
 
+    @staticmethod
+    def _frame(img, dtype, shape):
+        if not (isinstance(img, np.ndarray) and img.dtype == dtype and img.shape == shape and img.strides[1] == img.itemsize):
+            raise ValueError("frame must be a %s array of shape %s with contiguous rows" % (np.dtype(dtype).name, shape))
+        return img
+
     def submit(self, cur_time, img, depth=None):
-        """Asynchronous trackImage: up to two frames may be in flight; collect them in order with wait()."""
+        """Asynchronous trackImage: up to two frames may be in flight; collect them in order with wait().
+        The arrays are read by the copy engine after this call returns: keep them alive and unchanged until wait()."""
+        img = self._frame(img, np.uint8, (self.height, self.width))
+        if depth is not None:
+            depth = self._frame(depth, np.uint16, (self.height, self.width))
         dp, dpitch = (depth.ctypes.data, depth.strides[0]) if depth is not None else (None, 0)
         check(self.L.gf_tracker_submit(self._h, float(cur_time), img.ctypes.data, img.strides[0], dp, dpitch))
+
+    def trackBatch(self, times, gray_ptrs, depth_ptrs=None, on_device=False, gray_pitch=None, depth_pitch=None, want=True):
+        """n consecutive trackImage calls in ONE library call (gf_tracker_track_batch: two frames in flight inside the
+        library).  gray_ptrs / depth_ptrs: integer addresses of the frames (host, ideally pinned, or device).  Returns a
+        list of (obs, status, info) per frame when `want`, else None (bench loops that only need the work done)."""
+        n = len(times)
+        t = np.ascontiguousarray(times, np.float64)
+        g = (ctypes.c_void_p * n)(*[int(a) for a in gray_ptrs])
+        d = (ctypes.c_void_p * n)(*[(int(a) if a else None) for a in depth_ptrs]) if depth_ptrs is not None else None
+        obs = np.zeros((n, self.max_cnt), OBS_DTYPE) if want else None
+        st = np.zeros((n, self.max_cnt), np.uint8) if want else None
+        cnt = np.zeros(n, np.int32)
+        info = (TrackInfo * n)()
+        check(self.L.gf_tracker_track_batch(self._h, n, t.ctypes.data, g, int(gray_pitch or self.width), d,
+                                            int(depth_pitch or 2 * self.width), int(bool(on_device)),
+                                            obs.ctypes.data if want else None, cnt.ctypes.data, st.ctypes.data if want else None, info))
+        self.last_info = info[n - 1].as_dict() if n else {}
+        self.batch_infos = [info[k].as_dict() for k in range(n)]
+        if not want:
+            return None
+        return [(obs[k, :cnt[k]].copy(), st[k, :info[k].n_prev].copy(), info[k].as_dict()) for k in range(n)]
 
     def submitDevice(self, cur_time, d_gray_ptr, d_depth_ptr=None):
         check(self.L.gf_tracker_submit_device(self._h, float(cur_time), d_gray_ptr, d_depth_ptr))

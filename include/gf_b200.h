@@ -111,6 +111,16 @@ int gf_tracker_track_device(gf_tracker* t, double time, const void* d_gray, cons
 /* Asynchronous form of gf_tracker_track_device (collect with gf_tracker_wait; same two-frame rule as _submit). */
 int gf_tracker_submit_device(gf_tracker* t, double time, const void* d_gray, const void* d_depth);
 
+/* A recorded run of n consecutive frames (rosbag replay, one call per batch): the same submit / wait pipeline as above,
+ * two frames in flight, driven from inside the library so that the host costs one call per batch instead of ~10 driver
+ * calls per frame.  Frame k = (times[k], gray[k], depth[k] or NULL / depth == NULL); on_device != 0: the pointers are
+ * device pointers to tightly packed frames (pitches ignored), else host pointers with the given row pitches (pinned
+ * buffers make the uploads asynchronous).  Results of frame k land at out + k*max_cnt, n_out[k],
+ * status_out + k*max_cnt, info[k] (each nullable).  Identical to n calls of gf_tracker_track. */
+int gf_tracker_track_batch(gf_tracker* t, int n, const double* times, const void* const* gray, size_t gray_pitch,
+                           const void* const* depth, size_t depth_pitch, int on_device,
+                           gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info);
+
 /* FeatureTracker::setPrediction (feature_tracker.cpp:1006-1027): xyz are camera-frame 3-D points. */
 int gf_tracker_set_prediction(gf_tracker* t, const int32_t* ids, const double* xyz, int n);
 /* FeatureTracker::removeOutliers (feature_tracker.cpp:1029-1045). */

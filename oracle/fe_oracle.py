@@ -40,8 +40,31 @@ def _sortlib():
         L = ctypes.CDLL(_SORT_SO)
         L.gfo_setmask_order.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.gfo_setmask_order.restype = None
+        L.gfo_setmask.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 4 + [ctypes.c_void_p] * 2
+        L.gfo_setmask.restype = ctypes.c_int
         _sort_lib = L
     return _sort_lib
+
+
+_glue_lib = None
+
+
+def _gluelib():
+    global _glue_lib
+    if _glue_lib is None:
+        so = os.path.join(_HERE, "_build", "libgf_oracle_glue.so")
+        src = os.path.join(_HERE, "fe_glue.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(so), exist_ok=True)
+            subprocess.check_call(["gcc", "-O3", "-ffp-contract=off", "-shared", "-fPIC", "-fvisibility=hidden", "-o", so, src, "-lm"])
+        L = ctypes.CDLL(so)
+        vp, i = ctypes.c_void_p, ctypes.c_int
+        L.gfo_status_rules.argtypes = [vp, vp, vp, vp, vp, i, i, vp, i, i, vp]
+        L.gfo_status_rules.restype = None
+        L.gfo_finalize.argtypes = [vp, vp, i, vp, vp, vp, i, ctypes.c_double, vp, i, i, i, vp, vp]
+        L.gfo_finalize.restype = None
+        _glue_lib = L
+    return _glue_lib
 
 
 def setmask_order(track_cnt):
@@ -244,17 +267,20 @@ class FeatureTrackerOracle:
         self.prev_time = self.cur_time
         self.hasPrediction = False
 
+        # feature_tracker.cpp:318-366: depth_cam == 0 -> depth "-2.4 for debug" (:338); depth_cam != 0 -> entries only when
+        # the depth image is present (:342); depth_cam != 0 with an empty depth image returns an EMPTY frame
         featureFrame = {}
-        for i, fid in enumerate(self.ids):
-            if self.depth_cam and depth is not None:
-                r, c = c_round(self.cur_pts[i][1]), c_round(self.cur_pts[i][0])
-                depth_value = int(depth[r, c]) / 1000
-            else:
-                depth_value = -2.4   # feature_tracker.cpp:338 "for debug"
-            featureFrame[fid] = np.array([float(cur_un_pts[i][0]), float(cur_un_pts[i][1]), 1.0,
-                                          float(self.cur_pts[i][0]), float(self.cur_pts[i][1]),
-                                          float(pts_velocity[i][0]), float(pts_velocity[i][1]),
-                                          depth_value], np.float64)
+        if self.depth_cam == 0 or depth is not None:
+            for i, fid in enumerate(self.ids):
+                if self.depth_cam:
+                    r, c = c_round(self.cur_pts[i][1]), c_round(self.cur_pts[i][0])
+                    depth_value = int(depth[r, c]) / 1000
+                else:
+                    depth_value = -2.4
+                featureFrame[fid] = np.array([float(cur_un_pts[i][0]), float(cur_un_pts[i][1]), 1.0,
+                                              float(self.cur_pts[i][0]), float(self.cur_pts[i][1]),
+                                              float(pts_velocity[i][0]), float(pts_velocity[i][1]),
+                                              depth_value], np.float64)
         return featureFrame
 
     # feature_tracker.cpp:1006-1027
@@ -276,6 +302,131 @@ class FeatureTrackerOracle:
         self.prev_pts = self.prev_pts[keep]
         self.ids = [v for v, k in zip(self.ids, keep) if k]
         self.track_cnt = [v for v, k in zip(self.track_cnt, keep) if k]
+
+
+class FeatureTrackerOracleFast(FeatureTrackerOracle):
+    """The same restatement with the per-feature glue vectorised (NumPy) or moved to C (setMask: oracle/stdsort_helper.cpp),
+    so that a timing of it is dominated by the three OpenCV calls like the compiled C++ reference, not by the Python
+    interpreter.  tests/test_fe_oracle.py::test_fast_oracle_equals_loop_oracle keeps it equal to the loop version above.
+    t_cv accumulates the seconds spent inside cv2 (calcOpticalFlowPyrLK, goodFeaturesToTrack) and the C setMask."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.ids = np.zeros(0, np.int64)
+        self.track_cnt = np.zeros(0, np.int32)
+        self.prev_un_ids = np.zeros(0, np.int64)
+        self.prev_un = np.zeros((0, 2), np.float32)
+        self.t_cv = 0.0
+        self._mask = None
+        self._cam8 = np.array(self.cam.params8(), np.float64)
+
+    def _lk_t(self, *a):
+        import time
+        t0 = time.perf_counter()
+        r = self._lk(*a)
+        self.t_cv += time.perf_counter() - t0
+        return r
+
+    def _lift(self, u, v):
+        c = self.cam
+        mx_d = c.inv_K11 * u + c.inv_K13
+        my_d = c.inv_K22 * v + c.inv_K23
+        if c.no_distortion:
+            return mx_d, my_d
+        dx, dy = c.distortion(mx_d, my_d)          # elementwise float64: the same operations in the same order
+        mx_u, my_u = mx_d - dx, my_d - dy
+        for _ in range(1, 8):
+            dx, dy = c.distortion(mx_u, my_u)
+            mx_u, my_u = mx_d - dx, my_d - dy
+        return mx_u, my_u
+
+    def trackImage(self, cur_time, img, depth=None):
+        import time
+        G = _gluelib()
+        self.cur_time = float(cur_time)
+        cur_img = np.ascontiguousarray(img, np.uint8)
+        self.row, self.col = cur_img.shape
+        self.cur_pts = np.zeros((0, 2), np.float32)
+        self.last_status = np.zeros(0, np.uint8)
+        if len(self.prev_pts) > 0:
+            if self.hasPrediction:
+                self.cur_pts, status = self._lk_t(self.prev_img, cur_img, self.prev_pts, self.predict_pts, 1, True)
+                if int(status.sum()) < 10:
+                    self.cur_pts, status = self._lk_t(self.prev_img, cur_img, self.prev_pts, None, 3, False)
+            else:
+                self.cur_pts, status = self._lk_t(self.prev_img, cur_img, self.prev_pts, None, 3, False)
+            reverse_pts, reverse_status = self.cur_pts, status
+            if self.FLOW_BACK:
+                reverse_pts, reverse_status = self._lk_t(cur_img, self.prev_img, self.cur_pts, self.prev_pts, 1, True)
+            st = np.empty(len(status), np.uint8)
+            G.gfo_status_rules(self.prev_pts.ctypes.data, self.cur_pts.ctypes.data, reverse_pts.ctypes.data, status.ctypes.data,
+                               reverse_status.ctypes.data, len(status), self.FLOW_BACK, cur_img.ctypes.data, self.row, self.col, st.ctypes.data)
+            self.last_status = st
+            ok = st.view(np.bool_)
+            self.prev_pts = self.prev_pts[ok]; self.cur_pts = self.cur_pts[ok]
+            self.ids = self.ids[ok]; self.track_cnt = self.track_cnt[ok]
+        self.track_cnt = self.track_cnt + 1
+        # setMask (:56-83) in C: std::sort + walk + filled circles
+        t0 = time.perf_counter()
+        if self._mask is None or self._mask.shape != cur_img.shape:
+            self._mask = np.empty(cur_img.shape, np.uint8)
+        self._mask.fill(255)
+        n = len(self.cur_pts)
+        r = np.rint(self.cur_pts).astype(np.int32).T.copy() if n else np.zeros((2, 0), np.int32)     # cvRound
+        tc = np.ascontiguousarray(self.track_cnt, np.int32)
+        keep = np.empty(max(n, 1), np.int32)
+        nk = _sortlib().gfo_setmask(tc.ctypes.data, r[0].ctypes.data, r[1].ctypes.data, n, self.MIN_DIST, self.row, self.col,
+                                    self._mask.ctypes.data, keep.ctypes.data)
+        keep = keep[:nk]
+        self.cur_pts = self.cur_pts[keep]; self.ids = self.ids[keep]; self.track_cnt = self.track_cnt[keep]
+        self.mask = self._mask
+        n_max_cnt = self.MAX_CNT - len(self.cur_pts)
+        n_pts = np.zeros((0, 2), np.float32)
+        if n_max_cnt > 0:
+            c = cv2.goodFeaturesToTrack(cur_img, n_max_cnt, 0.01, self.MIN_DIST, mask=self.mask)
+            if c is not None:
+                n_pts = c.reshape(-1, 2)
+        self.t_cv += time.perf_counter() - t0
+        self.last_n_pts = n_pts
+        if len(n_pts):                                                           # addPoints (:85-93)
+            self.cur_pts = np.concatenate([self.cur_pts.reshape(-1, 2), n_pts], 0)
+            self.ids = np.concatenate([self.ids, np.arange(self.n_id, self.n_id + len(n_pts), dtype=np.int64)])
+            self.n_id += len(n_pts)
+            self.track_cnt = np.concatenate([self.track_cnt, np.ones(len(n_pts), np.int32)])
+        # undistortedPts (:797-808), ptsVelocity (:810-847), observation vectors (:318-366): oracle/fe_glue.c
+        n = len(self.cur_pts)
+        self.cur_pts = np.ascontiguousarray(self.cur_pts, np.float32)
+        cur_un = np.empty((n, 2), np.float32)
+        obs = np.empty((n, 8), np.float64)
+        if depth is not None:
+            depth = np.ascontiguousarray(depth, np.uint16)
+        G.gfo_finalize(self.cur_pts.ctypes.data, self.ids.ctypes.data, n, self._cam8.ctypes.data, self.prev_un_ids.ctypes.data,
+                       self.prev_un.ctypes.data, len(self.prev_un_ids), self.cur_time - self.prev_time,
+                       depth.ctypes.data if depth is not None else None, self.row, self.col, self.depth_cam,
+                       cur_un.ctypes.data, obs.ctypes.data)
+        self.prev_img = cur_img
+        self.prev_pts = self.cur_pts
+        self.prev_un_ids, self.prev_un = self.ids, cur_un
+        self.prev_un_pts_map = self.cur_un_pts_map = None
+        self.prev_time = self.cur_time
+        self.hasPrediction = False
+        if not (self.depth_cam == 0 or depth is not None):
+            return {}
+        return dict(zip(self.ids.tolist(), obs))
+
+    def setPrediction(self, predictPts):
+        self.hasPrediction = True
+        pp = self.prev_pts.copy().reshape(-1, 2)
+        for i, fid in enumerate(self.ids.tolist()):
+            if fid in predictPts:
+                X, Y, Z = predictPts[fid]
+                u, v = self.cam.space_to_plane(float(X), float(Y), float(Z))
+                pp[i] = (np.float32(u), np.float32(v))
+        self.predict_pts = pp
+
+    def removeOutliers(self, removePtsIds):
+        keep = ~np.isin(self.ids, np.fromiter(removePtsIds, np.int64, len(removePtsIds)))
+        self.prev_pts = self.prev_pts[keep]; self.ids = self.ids[keep]; self.track_cnt = self.track_cnt[keep]
 
 
 def cv_calls_only(prev_img, cur_img, prev_pts, mask, n_new, min_dist, flow_back=True):

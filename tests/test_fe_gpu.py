@@ -179,6 +179,52 @@ def test_two_frames_in_flight_equals_blocking_calls(gf):
     b.close()
 
 
+@pytest.mark.parametrize("name", ["fe_c2_seed0", "fe_c3_seed1"])
+def test_gpu_reproduces_golden_fixture(gf, name):
+    """The committed fixtures (tests/golden/fe_*.npz, written by make_fe_golden.py from the cv2 oracle) replayed through the
+    C ABI on the GPU: ids, inlier masks, new corners and observation vectors of every frame, bit for bit."""
+    import os
+    from ground_fusion_b200.synth import IDC_CAM, SyntheticStream
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    seed, w, h, max_cnt, min_dist, frames = [int(v) for v in g["meta"]]
+    params8 = [IDC_CAM[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")]
+    st = SyntheticStream(seed=seed, width=w, height=h)
+    tr = gf.FeatureTracker(w, h, params8, max_cnt, min_dist, 1, 1)
+    for k in range(frames):
+        t, gray, depth = st.frame(k)
+        got = tr.trackImageRaw(t, gray, depth)
+        assert np.array_equal(got["id"], g["ids_%d" % k]), "frame %d: ids" % k
+        assert np.array_equal(tr.last_status, g["status_%d" % k]), "frame %d: inlier mask" % k
+        assert tr.last_info["n_new"] == len(g["npts_%d" % k]), "frame %d: new corners" % k
+        assert np.array_equal(got["v"].reshape(-1, 8), g["obs_%d" % k]), "frame %d: observations" % k
+    tr.close()
+
+
+def test_missing_depth_frames_match_oracle(gf):
+    """Frames whose depth image is missing (depth_cam = 1): the reference returns an EMPTY featureFrame
+    (feature_tracker.cpp:342) but still advances its state; GPU and oracle are compared on every frame, the
+    empty ones included."""
+    from ground_fusion_b200.synth import SyntheticStream
+    from oracle.fe_oracle import IDC_CAM, FeatureTrackerOracle, PinholeCamera
+    cam = PinholeCamera(**IDC_CAM)
+    stream = SyntheticStream(seed=6)
+    gpu = gf.FeatureTracker(640, 480, cam.params8(), 150, 30, 1, 1)
+    ref = FeatureTrackerOracle(cam, 150, 30, 1, 1)
+    for k in range(16):
+        t, gray, depth = stream.frame(k)
+        if k % 5 == 2:
+            depth = None
+        got = gpu.trackImage(t, gray, depth)
+        want = ref.trackImage(t, gray, depth)
+        assert np.array_equal(gpu.last_status, ref.last_status), "frame %d" % k
+        assert sorted(got) == sorted(want), "frame %d" % k
+        if depth is None:
+            assert len(got) == 0
+        for fid in want:
+            assert np.array_equal(got[fid], want[fid]), "frame %d id %d" % (k, fid)
+    gpu.close()
+
+
 def test_track_no_depth_image_quirk(gf):
     """depth_cam with an empty depth image yields an empty featureFrame (feature_tracker.cpp:342)."""
     from oracle.fe_oracle import IDC_CAM, PinholeCamera

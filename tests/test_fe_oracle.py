@@ -142,3 +142,36 @@ def test_oracle_first_frame_properties():
     d2 = ((p[:, None] - p[None]) ** 2).sum(-1) + np.eye(150) * 1e9
     assert d2.min() >= 30 * 30              # min-distance property of the detector
     assert all(v[5] == 0 and v[6] == 0 for v in ff.values())   # no velocity on the first frame
+
+
+def test_fast_oracle_equals_loop_oracle():
+    """bench.py's CPU arm times FeatureTrackerOracleFast (glue vectorised / in C); it must be the same function as the
+    line-by-line loop restatement: ids, inlier masks, new corners, observation vectors, incl. setPrediction /
+    removeOutliers feedback and frames without a depth image."""
+    from ground_fusion_b200.synth import SyntheticStream
+    from oracle.fe_oracle import IDC_CAM, FeatureTrackerOracle, FeatureTrackerOracleFast, PinholeCamera
+    cam = PinholeCamera(**IDC_CAM)
+    st = SyntheticStream(seed=3)
+    a = FeatureTrackerOracle(cam, 150, 30, 1, 1)
+    b = FeatureTrackerOracleFast(cam, 150, 30, 1, 1)
+    rng = np.random.default_rng(0)
+    for k in range(14):
+        t, gray, depth = st.frame(k)
+        if k == 9:
+            depth = None
+        fa, fb = a.trackImage(t, gray, depth), b.trackImage(t, gray, depth)
+        assert list(a.ids) == list(b.ids) and list(a.track_cnt) == list(b.track_cnt), "frame %d" % k
+        assert np.array_equal(a.last_status, b.last_status), "frame %d" % k
+        assert np.array_equal(a.last_n_pts, b.last_n_pts), "frame %d" % k
+        assert sorted(fa) == sorted(fb)
+        for fid in fa:
+            assert np.array_equal(fa[fid], fb[fid]), "frame %d id %d" % (k, fid)
+        if k in (4, 7) and fa:
+            pred = {}
+            for fid in list(fa)[::2]:
+                d = max(fa[fid][7], 0.5)
+                pred[fid] = (fa[fid][0] * d + rng.normal(0, 0.002), fa[fid][1] * d + rng.normal(0, 0.002), d)
+            rm = set(list(fa)[1::9])                      # estimator.cpp:1132-1136: removeOutliers, then setPrediction
+            a.removeOutliers(rm); b.removeOutliers(rm)
+            a.setPrediction(pred); b.setPrediction(pred)
+    assert b.t_cv > 0
