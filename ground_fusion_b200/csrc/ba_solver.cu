@@ -16,11 +16,13 @@
 //                   last CTA of k_ba_eval(1) to finish.
 // All four are enqueued for every iteration up front; kernels return immediately once the state says "done",
 // so the host synchronises exactly once per solve.
+#include <stdlib.h>
 #include <new>
 #include <type_traits>
 #include <vector>
 
 #include "ba_factors.cuh"
+#include "ba_chol.cuh"
 
 using namespace gf;
 using namespace gfba;
@@ -31,8 +33,8 @@ constexpr int MAXF = GF_BA_MAX_FRAMES;
 constexpr int X_POSE = 0, X_SB = 7 * MAXF, X_EX = X_SB + 9 * MAXF, X_TD = X_EX + 7, X_EXW = X_TD + 1, X_IX = X_EXW + 7, X_TDW = X_IX + 3,
               X_PR = X_TDW + 1, X_PZ = X_PR + 4, X_FEAT = X_PZ + 1;
 constexpr int PAIR_THREADS = 256, PAIR_CHUNK = 64;   // factors staged per pass (2*64 rows x 20 cols in smem)
-constexpr int RB_THREADS = 512;                      // k_ba_step block size: 128 registers per thread
-constexpr int MAX_NC = 175;                          // reduced dimension supported by k_ba_step: 4x4 blocks of the (nc+1)-row system <= 1024 threads
+constexpr int RB_THREADS = ST_THREADS;               // k_ba_step block size (ba_chol.cuh)
+constexpr int SCHUR_WARPS = 8;                       // k_ba_schur: one warp per 8x8 tile of the reduced system
 
 struct BaState {
     double x_cost, cand_cost, radius, mu, alpha, dogleg_norm, model_change, x_norm, step_norm, grad_max;
@@ -66,7 +68,9 @@ struct BaDev {
     double* Hp;               // [nc*nc]
     double* acc[2];           // accumulators: [H nc*nc | g n | W L*nc | hll L]
     double *scale, *diag, *gs, *gn, *step, *delta;
-    double* Sg;               // [(nc+1)*nc] reduced system written by k_ba_schur (row nc = rhs)
+    double* Sg;               // reduced system written by k_ba_schur: row-major 8x8 tiles tix(I,J) of the (nc+1)-row augmented matrix (row nc = rhs)
+    double* Lg;               // factor tiles beyond tile_cap (spill, L2-resident)
+    int tile_cap;             // factor tiles kept in shared memory (TILE_CAP; smaller only when GF_BA_TILE_CAP is set, to test the spill path)
     double gravity[3], vis_sqrt_info;
     BaState* st;
 };
@@ -226,7 +230,12 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
     __shared__ double simu_J[15 * 30], simu_JU[15 * 30], simu_r[15], simu_ru[15];
     const BaState& st = *d.st;
     if (st.done) return;
+#ifdef GF_PROFILE
     const long long t_eval0 = clock64();
+#define PHMAX(k) do { if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[k], (unsigned long long)(clock64() - t_eval0)); } while (0)
+#else
+#define PHMAX(k) do { } while (0)
+#endif
     const int tid = threadIdx.x;
     const int tgt = st.cur ^ 1;            // inactive buffer
     if (mode == 0) { if (!st.need_linearize) return; }
@@ -301,7 +310,7 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
         }
         cost = block_reduce_sum(cost, sred);
         if (tid == 0 && cost != 0.0) atomicAdd(costp, cost);
-        if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[14], (unsigned long long)(clock64() - t_eval0));
+        PHMAX(14);
     } else if (b < d.n_pairs + d.n_imu) {
         // ---------------- one IMU factor ----------------
         const int m = b - d.n_pairs;
@@ -332,7 +341,7 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
             }
         }
         __syncthreads();
-        if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[15], (unsigned long long)(clock64() - t_eval0));
+        PHMAX(15);
     } else if (b < d.n_pairs + d.n_imu + d.n_wheel) {
         // ---------------- one wheel factor (6 residuals, 22 local columns) ----------------
         const gf_ba_wheel_factor& f = d.wheel[b - d.n_pairs - d.n_imu];
@@ -430,7 +439,7 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
                 atomicAdd(&acc_g(d, tgt)[lc], s);
             }
         __syncthreads();
-        if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[13], (unsigned long long)(clock64() - t_eval0));
+        PHMAX(13);
     }
 }
 
@@ -456,22 +465,68 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Reduced camera system for the Gauss-Newton solve, (H' + mu D^2) with the free landmarks eliminated:
+// Reduced camera system for the Gauss-Newton solve, (H' + mu D^2) with the free landmarks eliminated (Ceres' SchurEliminator):
 //   S[a][b] = H'[a][b] + [a==b] mu D_a^2 - s_a s_b sum_l c_l W[l][a] W[l][b],   c_l = s_l^2 / (h'_ll + mu D_l^2)
-//   rhs[b]  = g'[b] - s_b sum_l c_l W[l][b] g_l
-// (primes = Jacobi-scaled).  One thread per entry of the lower triangle; W stays in L2.  Everything it needs
-// (scale, D, c_l) is recomputed locally from the accumulators so that it can run before k_ba_step adopts them.
-__global__ void __launch_bounds__(256) k_ba_schur(BaDev d)
+//   rhs[b]  = g'[b] - s_b sum_l c_l W[l][b] g_l                (primes = Jacobi-scaled; stored as row nc of the system)
+// One warp per 8x8 tile (I,J), I >= J, of the (nc+1)-row augmented system: the rank-L update sum_l c_l w_la w_lb is a chain
+// of DMMA.8x8x4 over the landmarks (A[m][k] = c_l W[l0+k][8I+m], B[k][n] = W[l0+k][8J+n]; the right-hand side is the same
+// product with "column nc" of W := g_l).  The tile is written row-major to Sg[tix(I,J)*64], which k_ba_step's left-looking
+// Cholesky streams.  ss / sv / cl: Jacobi scale, Cauchy direction v_c = g_c s_c^2 / D_c^2 (null: no Cauchy terms) and c_l.
+__device__ __forceinline__ void schur_tile(const BaDev& d, const double* __restrict__ H, const double* __restrict__ g, const double* __restrict__ W,
+                                           const double* __restrict__ ss, const double* __restrict__ sv, const double* __restrict__ cl, double mu,
+                                           int I, int J, int lane, double& num, double& den)
 {
-    extern __shared__ double cl[];                 // [L]
+    const int nc = d.nc, L = d.L;
+    const double* Hp = d.Hp;
+    const int ka = lane & 3, ia = 8 * I + (lane >> 2), ib = 8 * J + (lane >> 2);
+    auto wx = [&](int l, int c) { return c < nc ? W[(size_t)l * nc + c] : (c == nc ? g[nc + l] : 0.0); };
+    double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+    for (int l0 = 0; l0 < L; l0 += 8) {
+        const int la = l0 + ka, lb = l0 + 4 + ka;
+        double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
+        if (la < L) { a0 = cl[la] * wx(la, ia); b0 = wx(la, ib); }
+        if (lb < L) { a1 = cl[lb] * wx(lb, ia); b1 = wx(lb, ib); }
+        dmma884(acc0[0], acc0[1], a0, b0);
+        dmma884(acc1[0], acc1[1], a1, b1);
+    }
+    const int a = 8 * I + (lane >> 2);
+    double out[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const int b = 8 * J + 2 * (lane & 3) + e;
+        const double acc = acc0[e] + acc1[e];
+        double v;
+        if (a > nc || b > nc) v = (a == b) ? 1.0 : 0.0;                      // padding rows of the last tile row
+        else if (a == nc) v = (b == nc) ? 1.0 : (g[b] - acc) * ss[b];       // right-hand side (s_nc = 1)
+        else if (b == nc) v = 0.0;                                           // above the diagonal of the last tile: unused
+        else {
+            const double sa = ss[a], sb = ss[b];
+            const double hab = H[(size_t)a * nc + b] + Hp[(size_t)a * nc + b];
+            v = hab * sa * sb;
+            if (a == b) {
+                double hd = v; hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd); v += mu * hd;
+                if (sv) { const double gsa = g[a] * sa / sqrt(hd); num += gsa * gsa; }
+            }
+            v -= acc * sa * sb;
+            if (sv && b <= a) den += (a == b ? 1.0 : 2.0) * sv[a] * hab * sv[b];
+        }
+        out[e] = v;
+    }
+    *reinterpret_cast<double2*>(d.Sg + (size_t)tix(I, J) * 64 + (lane >> 2) * 8 + 2 * (lane & 3)) = make_double2(out[0], out[1]);
+}
+
+__global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
+{
+    extern __shared__ double ssm[];                // cl[L] | ss[nc+1] | sv[nc]
     const BaState& st = *d.st;
     if (st.done) return;
     const bool fresh = st.need_linearize != 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {   // clear the accumulator that is free during this iteration: k_ba_eval(1) linearises the candidate into it
         const int freeb = fresh ? st.cur : (st.cur ^ 1);
         const size_t tot = acc_size(d.nc, d.L);
-        const size_t nthr = (size_t)gridDim.x * gridDim.y * 256;
-        const size_t me = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.y * 16 + threadIdx.x;
+        const size_t nthr = (size_t)gridDim.x * blockDim.x;
+        const size_t me = (size_t)blockIdx.x * blockDim.x + tid;
         for (size_t e = me; e < tot; e += nthr) d.acc[freeb][e] = 0.0;
         if (me == 0) d.st->acc_cost[freeb] = 0.0;
     }
@@ -482,64 +537,54 @@ __global__ void __launch_bounds__(256) k_ba_schur(BaDev d)
     const double* W = acc_W(d, cur); const double* hll = acc_hll(d, cur);
     const bool first = st.first != 0;
     const double mu = st.mu;
-    const int tid = threadIdx.y * 16 + threadIdx.x;
+    double* cl = ssm; double* ss = ssm + L; double* sv = ss + nc + 1;
+    // everything (scale, D, c_l) is recomputed locally from the accumulators so that this kernel can run before k_ba_step adopts them
     auto scale_of = [&](int c) { return first ? 1.0 / (1.0 + sqrt(c < nc ? H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c] : hll[c - nc])) : d.scale[c]; };
-    for (int l = tid; l < L; l += 256) {
-        double sl = scale_of(nc + l);
-        double hd = hll[l] * sl * sl;
-        double hc = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);     // D_l^2
+    for (int l = tid; l < L; l += blockDim.x) {
+        const double sl = scale_of(nc + l), hd = hll[l] * sl * sl;
+        const double hc = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);     // D_l^2
         cl[l] = sl * sl / (hd + mu * hc);
     }
+    for (int c = tid; c <= nc; c += blockDim.x) {
+        if (c == nc) { ss[c] = 1.0; continue; }
+        const double sc_ = scale_of(c);
+        double hd = (H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c]) * sc_ * sc_;
+        hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);
+        ss[c] = sc_; sv[c] = g[c] * sc_ * sc_ / hd;        // v = gs / D (times the Jacobi scale, because H is unscaled)
+    }
     __syncthreads();
-    // v = gs / D (times the Jacobi scale, because H below is unscaled): v_c = g_c s_c^2 / D_c^2
-    auto vcam = [&](int c) { double sc_ = scale_of(c); double hd = (H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c]) * sc_ * sc_;
-                             hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd); return g[c] * sc_ * sc_ / hd; };
-    __shared__ double sred2[8];
+    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2;
     double num = 0, den = 0;
-    const int a = blockIdx.y * 16 + threadIdx.y, b = blockIdx.x * 16 + threadIdx.x;
-    if (a <= nc && b < nc && b <= a) {
-        const double sb = scale_of(b);
-        double acc = 0;
-        if (a < nc) {
-            const double sa = scale_of(a);
-            for (int l = 0; l < L; l++) acc += cl[l] * W[(size_t)l * nc + a] * W[(size_t)l * nc + b];
-            const double hab = H[(size_t)a * nc + b] + Hp[(size_t)a * nc + b];
-            double v = hab * sa * sb;
-            if (a == b) {
-                double hd = v; hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd); v += mu * hd;
-                double gsa = g[a] * sa / sqrt(hd); num += gsa * gsa;
-            }
-            d.Sg[(size_t)a * (a + 1) / 2 + b] = v - acc * sa * sb;
-            den += (a == b ? 1.0 : 2.0) * vcam(a) * hab * vcam(b);
-        } else {
-            for (int l = 0; l < L; l++) acc += cl[l] * W[(size_t)l * nc + b] * g[nc + l];
-            d.Sg[(size_t)nc * (nc + 1) / 2 + b] = g[b] * sb - acc * sb;
+    const int gw = blockIdx.x * SCHUR_WARPS + warp, nw = gridDim.x * SCHUR_WARPS;
+    for (int t = gw; t < ntiles; t += nw) {
+        int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while (tix(I + 1, 0) <= t) I++;
+        while (tix(I, 0) > t) I--;
+        schur_tile(d, H, g, W, ss, sv, cl, mu, I, t - tix(I, 0), lane, num, den);
+    }
+    // landmark part of the Cauchy quadratic form: 2 v_l (W v_c)_l + h_ll v_l^2, warp per landmark
+    for (int l = gw; l < L; l += nw) {
+        double t = 0;
+        for (int c = lane; c < nc; c += 32) t += W[(size_t)l * nc + c] * sv[c];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) {
+            const double sl = scale_of(nc + l), hd = hll[l] * sl * sl;
+            const double hc = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);
+            const double vl = g[nc + l] * sl * sl / hc;
+            den += 2.0 * vl * t + hll[l] * vl * vl;
+            const double gsl = g[nc + l] * sl / sqrt(hc); num += gsl * gsl;
         }
     }
-    // landmark part of the Cauchy quadratic form: 2 v_l (W v_c)_l + h_ll v_l^2, warp per landmark in the column-0 CTAs
-    if (blockIdx.x == 0) {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int l = blockIdx.y * 8 + warp; l < L; l += gridDim.y * 8) {
-            double t = 0;
-            for (int c = lane; c < nc; c += 32) t += W[(size_t)l * nc + c] * vcam(c);
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            if (lane == 0) {
-                double sl = scale_of(nc + l), hd = hll[l] * sl * sl;
-                double hc = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);
-                double vl = g[nc + l] * sl * sl / hc;
-                den += 2.0 * vl * t + hll[l] * vl * vl;
-                double gsl = g[nc + l] * sl / sqrt(hc); num += gsl * gsl;
-            }
-        }
-    }
+    __shared__ double sred2[2 * SCHUR_WARPS];
     for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
-    if ((tid & 31) == 0) sred2[tid >> 5] = den;
+    if (lane == 0) { sred2[warp] = den; sred2[SCHUR_WARPS + warp] = num; }
     __syncthreads();
-    if (tid == 0) { double t = 0; for (int k = 0; k < 8; k++) t += sred2[k]; if (t != 0.0) atomicAdd(&d.st->cauchy_den, t); }
-    __syncthreads();
-    if ((tid & 31) == 0) sred2[tid >> 5] = num;
-    __syncthreads();
-    if (tid == 0) { double t = 0; for (int k = 0; k < 8; k++) t += sred2[k]; if (t != 0.0) atomicAdd(&d.st->cauchy_num, t); }
+    if (tid == 0) {
+        double t = 0, u = 0;
+        for (int k = 0; k < SCHUR_WARPS; k++) { t += sred2[k]; u += sred2[SCHUR_WARPS + k]; }
+        if (t != 0.0) atomicAdd(&d.st->cauchy_den, t);
+        if (u != 0.0) atomicAdd(&d.st->cauchy_num, u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -610,53 +655,27 @@ __device__ __forceinline__ double block_reduce_max(double v, double* sh)
 }
 
 // DoglegStrategy::ComputeStep + TrustRegionMinimizer::ComputeTrustRegionStep + candidate point.
-// Dynamic shared memory: packed lower triangle of the (nc+1) x (nc+1) augmented reduced system.
-// Back substitution L^T y = z by one warp.  L: block row b (rows 4b..4b+3) stored as 4 rows of 4(b+1) doubles at
-// offset 8 b (b+1) in shared memory, inv_diag[c] = 1/L[c][c].
-// Lane (c & 31) owns column c: acc_c = sum_{j>c} L[j][c] y_j in a register; per column the dependent chain is
-// DFMA (push) -> DFMA (t = z/l - acc/l) -> SHFL, the loads of row j are independent of it.
-__device__ __noinline__ void warp_backsubst(const double* L, const double* inv_diag, const double* z, double* y, int nc, int lane)
-{
-    constexpr int NS = (MAX_NC + 31) / 32;                  // column slots per lane
-    double accr[NS];
-#pragma unroll
-    for (int q = 0; q < NS; q++) accr[q] = 0.0;
-#pragma unroll
-    for (int slot = NS - 1; slot >= 0; slot--) {
-        if (slot * 32 < nc) {
-            const int c = slot * 32 + lane;
-            const double ir = c < nc ? inv_diag[c] : 0.0;
-            const double zi = c < nc ? z[c] * ir : 0.0;
-            for (int jj = min(31, nc - 1 - slot * 32); jj >= 0; jj--) {
-                const int j = slot * 32 + jj;
-                const double t = fma(-accr[slot], ir, zi);
-                const double yj = __shfl_sync(0xffffffffu, t, jj);
-                if (lane == jj) y[j] = yj;
-                const double* Lrow = L + 8 * (j >> 2) * ((j >> 2) + 1) + (j & 3) * 4 * ((j >> 2) + 1);
-#pragma unroll
-                for (int q = 0; q <= slot; q++) {
-                    const int i = q * 32 + lane;
-                    if (i < j) accr[q] = fma(Lrow[i], yj, accr[q]);
-                }
-            }
-        }
-    }
-}
-
+// Dynamic shared memory: factor tiles (<= TILE_CAP) | inverses of the diagonal tiles | scratch tile | last diagonal tile | y.
+template <int R>
 __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
 {
-    extern __shared__ double S[];                 // packed: S[i*(i+1)/2 + j], j <= i ; row nc = rhs
+    extern __shared__ double S[];
     __shared__ double sred[32];
-    __shared__ double colbuf[MAX_NC + 2];
-    __shared__ double yc[MAX_NC + 1];
-    __shared__ double zb[MAX_NC + 5], accb[MAX_NC + 5], ybl[4];
     __shared__ int s_fail;
     BaState& st = *d.st;
     if (st.done) return;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int nc = d.nc, L = d.L, n = d.n;
+    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2;
+    TileStore T; T.Ls = S; T.Lg = d.Lg; T.cap = d.tile_cap;
+    double* Linv = S + (size_t)64 * min(ntiles, d.tile_cap);
+    double* S8 = Linv + 64 * n8; double* Ld = S8 + 64; double* yc = Ld + 64;
+#ifdef GF_PROFILE
     long long t_last = clock64();
 #define PH(k) do { if (tid == 0) { long long t_ = clock64(); st.prof[k] += t_ - t_last; t_last = t_; } } while (0)
+#else
+#define PH(k) do { } while (0)
+#endif
     if (st.need_linearize) {                      // a fresh linearisation landed in the inactive buffer: adopt it
         __syncthreads();
         if (tid == 0) { st.cur ^= 1; st.need_linearize = 0; st.x_cost = st.acc_cost[st.cur]; }
@@ -725,233 +744,23 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
                 d.gn[nc + l] = 1.0 / v;
             }
             __syncthreads();
-            if (first_try) {
-                // the reduced system was assembled by k_ba_schur (same mu) in packed order: flat copy into shared memory
-                const int tri = (nc + 1) * (nc + 2) / 2;
-                for (int e = tid; e < tri - 1; e += nt) S[e] = d.Sg[e];
-                if (tid == 0) S[tri - 1] = 0.0;
-            } else {
-                // retry with a larger mu (rare): assemble here
-                for (int a = warp; a <= nc; a += nwarp)
-                    for (int b = lane; b <= a; b += 32) {
-                        double v;
-                        if (a < nc) {
-                            v = (H[(size_t)a * nc + b] + Hp[(size_t)a * nc + b]) * sc[a] * sc[b];
-                            if (a == b) v += mu * d.diag[a] * d.diag[a];
-                            double t = 0;
-                            for (int l = 0; l < L; l++) t += d.gn[nc + l] * sc[nc + l] * sc[nc + l] * W[(size_t)l * nc + a] * W[(size_t)l * nc + b];
-                            v -= t * sc[a] * sc[b];
-                        } else if (b < nc) {
-                            v = g[b] * sc[b];
-                            double t = 0;
-                            for (int l = 0; l < L; l++) t += d.gn[nc + l] * sc[nc + l] * sc[nc + l] * W[(size_t)l * nc + b] * g[nc + l];
-                            v -= t * sc[b];
-                        } else v = 0.0;
-                        S[a * (a + 1) / 2 + b] = v;
-                    }
+            if (!first_try) {
+                // retry with a larger mu (rare): the reduced system is assembled here, by this CTA alone, with the same tile routine
+                for (int l = tid; l < L; l += nt) d.step[nc + l] = d.gn[nc + l] * sc[nc + l] * sc[nc + l];     // c_l (scratch)
+                __syncthreads();
+                double dummy0 = 0, dummy1 = 0;
+                for (int t = warp; t < ntiles; t += nwarp) {
+                    int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                    while (tix(I + 1, 0) <= t) I++;
+                    while (tix(I, 0) > t) I--;
+                    schur_tile(d, H, g, W, sc, nullptr, d.step + nc, mu, I, t - tix(I, 0), lane, dummy0, dummy1);
+                }
             }
             first_try = false;
             __syncthreads();
-            PH(2);   // load / assemble reduced system
-            // Register-blocked right-looking Cholesky, block size 4, with look-ahead on the diagonal.  The (nc+1)-row
-            // augmented system (row nc = rhs, rows above nc padded with identity) is cut into 4x4 blocks (bi, bj), bi >= bj.
-            // The diagonal blocks belong to the last warp (lane l owns (l,l) and (l+32,l+32)), the strictly lower blocks,
-            // ordered column-major, to the other 480 threads (two each), all in registers.
-            // Per panel p (4 columns):  [barrier A]  panel owners compute L_ip = A_ip L_pp^-T from the published inv(L_pp)
-            // and publish their rows  [barrier B]  trailing owners apply the rank-4 update a -= L_i L_j^T (16 LDS.128 ->
-            // 64 DFMA); the diagonal warp updates its blocks too and then factors block p+1 and publishes inv(L_p+1,p+1)
-            // while the other warps are still updating: the sqrt/divide chain of the diagonal (the critical path of a
-            // 165-column factorisation on one SM) overlaps the bandwidth-bound trailing update.
-            // The factor is persisted in S (dead once the blocks sit in registers) for the back substitution.
-            {
-                const int N4 = (nc + 4) >> 2;                       // block rows covering rows 0..nc
-                const int noff = N4 * (N4 - 1) / 2;                 // strictly lower blocks
-                constexpr int NOFF_T = RB_THREADS - 32;             // threads owning off-diagonal blocks
-                const bool dwarp = tid >= NOFF_T;                   // the diagonal warp
-                // block row bi of the persisted factor = 4 rows of 4*(bi+1) doubles (row-major: a row of L is contiguous)
-                const size_t lp_size = (size_t)8 * N4 * (N4 + 1);
-                const size_t s_size = (size_t)(nc + 1) * (nc + 2) / 2;
-                double* colL4 = S + (((lp_size > s_size ? lp_size : s_size) + 1) & ~(size_t)1);  // [4][4*N4] panel columns (16 B aligned)
-                double* Linv2 = colL4 + 32 * N4;                       // [2][16] inverse of the diagonal factor, double-buffered (colL4 is [2][4][4*N4])
-                const int ld = 4 * N4;
-                int bi[2], bj[2];
-                bool mine[2];
-                double a[2][4][4];
-#pragma unroll
-                for (int b = 0; b < 2; b++) {
-                    if (dwarp) {
-                        const int q = (tid - NOFF_T) + 32 * b;
-                        mine[b] = q < N4;
-                        bi[b] = bj[b] = min(q, N4 - 1);
-                    } else {
-                        // warps 3, 7, 11 share the diagonal warp's scheduler / FP64 pipe (warp id mod 4): when the blocks fit they
-                        // take one block each instead of two, so that the diagonal chain is less contended
-                        const int w_ = tid >> 5, npeer = (w_ > 3) + (w_ > 7) + (w_ > 11);
-                        const bool peer = (w_ & 3) == 3, light = noff <= NOFF_T + (NOFF_T - 96);
-                        const int t = !light ? tid + b * NOFF_T : (b == 0 ? tid : (peer ? noff : NOFF_T + (w_ - npeer) * 32 + (tid & 31)));
-                        mine[b] = t < noff;
-                        int cj = 0, off = 0;
-                        const int tt = min(t, max(noff - 1, 0));
-                        while (cj < N4 - 2 && tt >= off + (N4 - 1 - cj)) { off += N4 - 1 - cj; cj++; }
-                        bi[b] = cj + 1 + (tt - off); bj[b] = cj;
-                        if (noff == 0) { mine[b] = false; bi[b] = 0; bj[b] = 0; }
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                        for (int cc = 0; cc < 4; cc++) {
-                            const int i = 4 * bi[b] + rr, k = 4 * bj[b] + cc;
-                            double v = 0.0;
-                            if (mine[b]) {
-                                if (i > nc || (i == nc && k == nc)) v = (i == k) ? 1.0 : 0.0;      // padding / unused rhs diagonal
-                                else if (k <= i) v = S[i * (i + 1) / 2 + k];
-                            }
-                            a[b][rr][cc] = v;
-                        }
-                }
-                __syncthreads();
-                // factor diagonal block q in place (this thread's block B), publish inv(L_qq) in buffer q & 1
-                auto factor_diag = [&](auto bc, int q) {
-                    constexpr int B = decltype(bc)::value;
-                    double iv[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; jj++) {
-                        const int j = 4 * q + jj;
-                        if (j < nc) {
-                            const double dj = a[B][jj][jj];
-                            if (!(dj > 0.0)) s_fail = 1;
-                            const double inv = rsqrt(dj);
-                            iv[jj] = inv;
-                            a[B][jj][jj] = dj * inv;
-                            colbuf[1 + j] = inv;
-#pragma unroll
-                            for (int rr = jj + 1; rr < 4; rr++) a[B][rr][jj] *= inv;
-#pragma unroll
-                            for (int rr = jj + 1; rr < 4; rr++)
-#pragma unroll
-                                for (int cc = jj + 1; cc <= rr; cc++) a[B][rr][cc] -= a[B][rr][jj] * a[B][cc][jj];
-                        } else {
-                            a[B][jj][jj] = 1.0; iv[jj] = 1.0;
-#pragma unroll
-                            for (int rr = jj + 1; rr < 4; rr++) a[B][rr][jj] = 0.0;
-                        }
-                    }
-                    // inverse of the lower-triangular factor: li[r][c] = (delta_rc - sum_{c<=m<r} l[r][m] li[m][c]) / l[r][r]
-                    double* Linv = Linv2 + 16 * (q & 1);
-#pragma unroll
-                    for (int cc = 0; cc < 4; cc++) {
-                        double li[4];
-#pragma unroll
-                        for (int rr = 0; rr < 4; rr++) {
-                            if (rr < cc) { li[rr] = 0.0; continue; }
-                            double t = (rr == cc) ? 1.0 : 0.0;
-#pragma unroll
-                            for (int m = 0; m < 4; m++) if (m >= cc && m < rr) t -= a[B][rr][m] * li[m];
-                            li[rr] = t * iv[rr];
-                        }
-#pragma unroll
-                        for (int rr = 0; rr < 4; rr++) Linv[rr * 4 + cc] = li[rr];
-                    }
-#pragma unroll
-                    for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                        for (int cc = 0; cc <= rr; cc++) S[8 * q * (q + 1) + rr * 4 * (q + 1) + 4 * q + cc] = a[B][rr][cc];   // persisted factor
-                };
-                // rank-4 update of block b with the published columns of one panel
-                auto rank4 = [&](auto bc, const double* col) {
-                    constexpr int B = decltype(bc)::value;
-#pragma unroll
-                    for (int m = 0; m < 4; m++) {
-                        const double2 r01 = *reinterpret_cast<const double2*>(col + m * ld + 4 * bi[B]);
-                        const double2 r23 = *reinterpret_cast<const double2*>(col + m * ld + 4 * bi[B] + 2);
-                        const double2 c01 = *reinterpret_cast<const double2*>(col + m * ld + 4 * bj[B]);
-                        const double2 c23 = *reinterpret_cast<const double2*>(col + m * ld + 4 * bj[B] + 2);
-                        const double lr[4] = {r01.x, r01.y, r23.x, r23.y}, lc[4] = {c01.x, c01.y, c23.x, c23.y};
-#pragma unroll
-                        for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                            for (int cc = 0; cc < 4; cc++) a[B][rr][cc] -= lr[rr] * lc[cc];
-                    }
-                };
-                using I0 = std::integral_constant<int, 0>;
-                using I1 = std::integral_constant<int, 1>;
-                for (int pnl = -1; pnl < N4; pnl++) {                  // pnl = -1: only the look-ahead (block (0,0) has no update pending)
-                  if (pnl >= 0) {
-                    __syncthreads();                                    // A: inv(L_pp) is published, the trailing updates of panel p-1 are done
-                    if (s_fail) break;
-                    double* colw = colL4 + (pnl & 1) * 4 * ld;
-                    if (!dwarp) {   // ---- panel blocks: X = A L_pp^-T ----
-                        const double* Linv = Linv2 + 16 * (pnl & 1);
-#pragma unroll 1
-                        for (int b = 0; b < 2; b++) {
-                            const bool pb_ = b == 0 ? (mine[0] && bj[0] == pnl) : (mine[1] && bj[1] == pnl);
-                            if (!pb_) continue;
-                            double x[4][4];
-#pragma unroll
-                            for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                                for (int cc = 0; cc < 4; cc++) {
-                                    double t = 0.0;
-#pragma unroll
-                                    for (int m = 0; m < 4; m++) if (m <= cc) t += (b == 0 ? a[0][rr][m] : a[1][rr][m]) * Linv[cc * 4 + m];
-                                    x[rr][cc] = t;
-                                }
-                            const int brow = b == 0 ? bi[0] : bi[1];
-                            const int lpbase = 8 * brow * (brow + 1) + 4 * pnl;
-#pragma unroll
-                            for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                                for (int cc = 0; cc < 4; cc++) {
-                                    if (b == 0) a[0][rr][cc] = x[rr][cc]; else a[1][rr][cc] = x[rr][cc];
-                                    colw[cc * ld + 4 * brow + rr] = x[rr][cc];
-                                    S[lpbase + rr * 4 * (brow + 1) + cc] = x[rr][cc];
-                                }
-                        }
-                    } else if (pnl >= 1) {
-                        // the diagonal warp has no panel work: it applies panel p-1 to its not yet urgent blocks (q > p)
-                        // from the other column buffer while the panel owners fill this one
-                        const double* colr = colL4 + ((pnl - 1) & 1) * 4 * ld;
-                        if (mine[0] && bi[0] > pnl) rank4(I0(), colr);
-                        if (mine[1] && bi[1] > pnl) rank4(I1(), colr);
-                    }
-                    __syncthreads();                                    // B: the panel's columns are published
-                    if (!dwarp) {                                       // ---- trailing blocks: rank-4 update ----
-                        if (mine[0] && bj[0] > pnl) rank4(I0(), colw);
-                        if (mine[1] && bj[1] > pnl) rank4(I1(), colw);
-                    }
-                  }
-                    // look-ahead: the owner of diagonal block p+1 applies panel p to it and factors it while the other
-                    // warps are still updating
-                    if (dwarp && pnl + 1 < N4) {
-                        const int q = pnl + 1;
-                        if (tid - NOFF_T == (q & 31)) {
-                            const double* colr = colL4 + (pnl & 1) * 4 * ld;
-                            if (q < 32) { if (pnl >= 0) rank4(I0(), colr); factor_diag(I0(), q); }
-                            else { rank4(I1(), colr); factor_diag(I1(), q); }
-                        }
-                    }
-                }
-                // ---- back substitution  L^T y = z  by warp 0 ----
-                // z = row nc of the factor (owned by the blocks of block row nc/4).  The factor was persisted row-major in
-                // S.  Lane (c & 31) owns column c: acc_c = sum_{j>c} L[j][c] y_j in a register; per column the chain is
-                // DFMA (push) -> DFMA (t = z/l - acc/l) -> SHFL, the loads of row j are independent of it.
-                __syncthreads();
-                if (!s_fail) {
-                    const int brhs = nc >> 2, rrhs = nc & 3;
-#pragma unroll
-                    for (int b = 0; b < 2; b++)
-                        if (mine[b] && bi[b] == brhs) {
-#pragma unroll
-                            for (int cc = 0; cc < 4; cc++) {
-                                const int k = 4 * bj[b] + cc;
-                                const double zv = rrhs == 0 ? a[b][0][cc] : rrhs == 1 ? a[b][1][cc] : rrhs == 2 ? a[b][2][cc] : a[b][3][cc];
-                                if (k < nc) zb[k] = zv;
-                            }
-                        }
-                }
-                __syncthreads();
-                if (!s_fail && tid < 32) warp_backsubst(S, colbuf + 1, zb, yc, nc, tid);
-            }
+            PH(2);   // (re)assembly of the reduced system
+            const bool ok_f = chol_factor<R>(d.Sg, T, Linv, S8, Ld, nc, n8, &s_fail);
+            if (ok_f && tid < 32) chol_backsubst(T, Linv, Ld, yc, nc, tid);
             __syncthreads();
             PH(3);   // Cholesky
             if (!s_fail) {
@@ -1463,6 +1272,7 @@ struct gf_ba {
     void* dbuf; size_t dcap;
     void* hbuf; size_t hcap;     // pinned staging
     long long prof[32];
+    int tile_cap;
 };
 
 static int ensure(gf_ba* s, size_t dbytes)
@@ -1495,7 +1305,10 @@ int gf_ba_create(gf_ba** out, int device)
     s->device = device;
     GF_CUDA(cudaStreamCreateWithFlags(&s->s, cudaStreamNonBlocking));
     GF_CUDA(cudaEventCreate(&s->e0)); GF_CUDA(cudaEventCreate(&s->e1));
-    GF_CUDA(cudaFuncSetAttribute(k_ba_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    s->tile_cap = TILE_CAP;
+    if (const char* e_ = getenv("GF_BA_TILE_CAP")) { const int v = atoi(e_); if (v >= 0 && v < TILE_CAP) s->tile_cap = v; }
+    GF_CUDA(cudaFuncSetAttribute(k_ba_step<MAXR / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GF_CUDA(cudaFuncSetAttribute(k_ba_step<MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GF_CUDA(cudaFuncSetAttribute(k_jacobi_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     GF_CUDA(cudaFuncSetAttribute(k_sym_eig_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     *out = s;
@@ -1554,7 +1367,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     }
     for (int k = 0; k < nfeat; k++) if (col_feat[k] == -2) col_feat[k] = c++;
     d.L = c - d.nc; d.n = c;
-    if (d.nc > MAX_NC) return set_err(GF_ERR_CAPACITY, "reduced system larger than 175");
+    if (d.nc > MAX_NC) return set_err(GF_ERR_CAPACITY, "reduced system larger than 383 unknowns");
     // ---- sort visual factors by pose pair ----
     std::vector<int> pair_id(F * F, -1), pair_cnt;
     std::vector<int> pair_ij;
@@ -1598,6 +1411,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     }
     // ---- pack one upload buffer ----
     const int nc = d.nc, L = d.L, n = d.n;
+    const int n8 = (nc + 8) / 8, ntiles = n8 * (n8 + 1) / 2;      // 8x8 tiles of the (nc+1)-row augmented reduced system
     auto al = [](size_t v) { return (v + 15) / 16 * 16; };
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
@@ -1608,7 +1422,8 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     const size_t upload_bytes = off;
     const size_t o_Xc = take(sizeof(double) * (X_FEAT + nfeat)), o_sq = take(sizeof(double) * 225 * (size_t)(p->n_imu > 0 ? p->n_imu : 1)),
                  o_Hp = take(sizeof(double) * (size_t)nc * nc), o_a0 = take(sizeof(double) * acc_size(nc, L)), o_a1 = take(sizeof(double) * acc_size(nc, L)),
-                 o_vec = take(sizeof(double) * 6 * (size_t)(n > 0 ? n : 1)), o_Sg = take(sizeof(double) * (size_t)(nc + 1) * (nc > 0 ? nc : 1)), o_st = take(sizeof(BaState));
+                 o_vec = take(sizeof(double) * 6 * (size_t)(n > 0 ? n : 1)), o_Sg = take(sizeof(double) * 64 * (size_t)ntiles),
+                 o_Lg = take(sizeof(double) * 64 * (size_t)(ntiles > s->tile_cap ? ntiles - s->tile_cap : 1)), o_st = take(sizeof(BaState));
     int rc = ensure(s, off);
     if (rc) return rc;
     char* hb = (char*)s->hbuf; char* db = (char*)s->dbuf;
@@ -1650,7 +1465,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     double* vec = (double*)(db + o_vec);
     const size_t nn = (size_t)(n > 0 ? n : 1);
     d.scale = vec; d.diag = vec + nn; d.gs = vec + 2 * nn; d.gn = vec + 3 * nn; d.step = vec + 4 * nn; d.delta = vec + 5 * nn;
-    d.Sg = (double*)(db + o_Sg);
+    d.Sg = (double*)(db + o_Sg); d.Lg = (double*)(db + o_Lg); d.tile_cap = s->tile_cap;
     d.st = (BaState*)(db + o_st);
     for (int k = 0; k < 3; k++) d.gravity[k] = p->gravity[k];
     d.vis_sqrt_info = p->visual_sqrt_info;
@@ -1668,14 +1483,16 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
     const int eval_blocks = n_work + p->n_imu + p->n_wheel + (p->n_plane > 0 ? 1 : 0) + (pn ? 1 : 0);
     const size_t prior_smem = sizeof(double) * 2 * (size_t)pn;
-    const size_t n4 = (size_t)((nc + 4) / 4);
-    const size_t step_smem = sizeof(double) * (std::max((size_t)(nc + 1) * (nc + 2) / 2, 8 * n4 * (n4 + 1)) + 2 + 32 * n4 + 32);
+    const size_t step_smem = sizeof(double) * (64 * (size_t)std::min(ntiles, s->tile_cap) + 64 * (size_t)n8 + 128 + (size_t)((nc + 8) & ~7));
+    const size_t schur_smem = sizeof(double) * (size_t)(L + 2 * nc + 2);
+    const int schur_grid = (ntiles + SCHUR_WARPS - 1) / SCHUR_WARPS;
     const int iters = p->max_num_iterations;
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 0); GF_LAUNCHED(); }
-    const dim3 sgrid(nc > 0 ? (nc + 15) / 16 : 1, (nc + 16) / 16), sblock(16, 16);
     for (int it = 0; it <= iters; it++) {
-        if (it < iters) { k_ba_schur<<<sgrid, sblock, sizeof(double) * (size_t)(L > 0 ? L : 1), st>>>(d); GF_LAUNCHED(); }
-        k_ba_step<<<1, RB_THREADS, step_smem, st>>>(d); GF_LAUNCHED();
+        if (it < iters) { k_ba_schur<<<schur_grid, SCHUR_WARPS * 32, schur_smem, st>>>(d); GF_LAUNCHED(); }
+        if (n8 <= (MAXR / 2) * ST_WARPS) k_ba_step<MAXR / 2><<<1, RB_THREADS, step_smem, st>>>(d);
+        else k_ba_step<MAXR><<<1, RB_THREADS, step_smem, st>>>(d);
+        GF_LAUNCHED();
         if (it == iters) break;                  // the extra k_ba_step adopts the last linearisation and closes the run
         k_ba_eval<<<eval_blocks > 0 ? eval_blocks : 1, PAIR_THREADS, prior_smem, st>>>(d, 1); GF_LAUNCHED();   // + decision (last CTA)
     }
@@ -1973,3 +1790,70 @@ int gf_ba_debug_profile(gf_ba* s, long long* out32)
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Stage-level entry point (tests): the solver's tiled Cholesky + back substitution on an arbitrary SPD system.
+namespace gfba {
+template <int R>
+__global__ void __launch_bounds__(ST_THREADS) k_stage_chol(const double* Ag, double* Lg, int cap, int nc, double* y, int* fail)
+{
+    extern __shared__ double S[];
+    __shared__ int s_fail;
+    const int tid = threadIdx.x;
+    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2;
+    TileStore T; T.Ls = S; T.Lg = Lg; T.cap = cap;
+    double* Linv = S + (size_t)64 * min(ntiles, cap);
+    double* S8 = Linv + 64 * n8; double* Ld = S8 + 64; double* yc = Ld + 64;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+    const bool ok = chol_factor<R>(Ag, T, Linv, S8, Ld, nc, n8, &s_fail);
+    if (ok && tid < 32) chol_backsubst(T, Linv, Ld, yc, nc, tid);
+    __syncthreads();
+    if (ok) for (int c = tid; c < nc; c += blockDim.x) y[c] = yc[c];
+    if (tid == 0) *fail = ok ? 0 : 1;
+}
+}  // namespace gfba
+
+extern "C" int gf_stage_spd_solve(int device, const double* A, const double* b, int n, double* x, int tile_cap)
+{
+    if (!A || !b || !x || n < 1 || n > MAX_NC) return set_err(GF_ERR_INVALID_ARG, "bad argument (1 <= n <= 383)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(GF_ERR_NO_DEVICE, "no CUDA device visible; libgf_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_err(GF_ERR_INVALID_ARG, "device index out of range");
+    GF_CUDA(cudaSetDevice(device));
+    const int n8 = (n + 8) / 8, ntiles = n8 * (n8 + 1) / 2;
+    const int cap = (tile_cap >= 0 && tile_cap < TILE_CAP) ? tile_cap : TILE_CAP;
+    std::vector<double> tiles((size_t)ntiles * 64, 0.0);
+    for (int I = 0; I < n8; I++)
+        for (int J = 0; J <= I; J++)
+            for (int r = 0; r < 8; r++)
+                for (int c = 0; c < 8; c++) {
+                    const int i = 8 * I + r, j = 8 * J + c;
+                    double v;
+                    if (i > n || j > n) v = (i == j) ? 1.0 : 0.0;
+                    else if (i == n) v = (j == n) ? 1.0 : b[j];
+                    else if (j == n) v = 0.0;
+                    else v = A[(size_t)i * n + j];
+                    tiles[(size_t)tix(I, J) * 64 + r * 8 + c] = v;
+                }
+    double *dA = nullptr, *dL = nullptr, *dy = nullptr; int* df = nullptr;
+    const size_t spill = (size_t)(ntiles > cap ? ntiles - cap : 1) * 64;
+    GF_CUDA(cudaMalloc(&dA, tiles.size() * sizeof(double)));
+    GF_CUDA(cudaMalloc(&dL, spill * sizeof(double)));
+    GF_CUDA(cudaMalloc(&dy, (size_t)n * sizeof(double)));
+    GF_CUDA(cudaMalloc(&df, sizeof(int)));
+    GF_CUDA(cudaMemcpy(dA, tiles.data(), tiles.size() * sizeof(double), cudaMemcpyHostToDevice));
+    const size_t smem = sizeof(double) * (64 * (size_t)std::min(ntiles, cap) + 64 * (size_t)n8 + 128 + (size_t)((n + 8) & ~7));
+    GF_CUDA(cudaFuncSetAttribute(k_stage_chol<MAXR / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GF_CUDA(cudaFuncSetAttribute(k_stage_chol<MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (n8 <= (MAXR / 2) * ST_WARPS) k_stage_chol<MAXR / 2><<<1, ST_THREADS, smem>>>(dA, dL, cap, n, dy, df);
+    else k_stage_chol<MAXR><<<1, ST_THREADS, smem>>>(dA, dL, cap, n, dy, df);
+    GF_LAUNCHED();
+    int fail = 0;
+    cudaError_t e = cudaMemcpy(&fail, df, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && !fail) e = cudaMemcpy(x, dy, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dA); cudaFree(dL); cudaFree(dy); cudaFree(df);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "gf_stage_spd_solve: %s", cudaGetErrorString(e)); return GF_ERR_CUDA; }
+    if (fail) return set_err(GF_ERR_INVALID_ARG, "matrix is not positive definite");
+    return GF_OK;
+}

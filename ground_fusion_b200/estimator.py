@@ -24,6 +24,19 @@ def double2vector(problem, R0_before, P0_before, use_imu=True):
     return Rs, Ps, Vs
 
 
+def spd_solve(A, b, device=0, tile_cap=-1):
+    """x = A^-1 b through the back end's own dense solver (gf_stage_spd_solve: 8x8-tile Cholesky on FP64 tensor-core MMAs)."""
+    L = _lib.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.gf_stage_spd_solve.argtypes = [ctypes.c_int, dp, dp, ctypes.c_int, dp, ctypes.c_int]
+    A = np.ascontiguousarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
+    n = len(b)
+    assert A.shape == (n, n)
+    x = np.zeros(n)
+    check(L.gf_stage_spd_solve(int(device), A.ctypes.data_as(dp), b.ctypes.data_as(dp), n, x.ctypes.data_as(dp), int(tile_cap)))
+    return x
+
+
 class BundleAdjuster:
     """One solver workspace bound to one GPU (gf_ba).  optimization(problem) updates the para_* arrays of
     `problem` (ground_fusion_b200.ba_problem.Problem) in place, like Estimator::optimization() does with

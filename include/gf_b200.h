@@ -164,6 +164,13 @@ int gf_stage_gftt(int device, const uint8_t* img, int w, int h, const float* kep
 /* The permutation libstdc++'s std::sort produces for setMask's comparator (device replica). */
 int gf_stage_setmask_order(int device, const int32_t* track_cnt, int n, int32_t* perm);
 
+/* The back end's dense linear solver on its own (same device code as gf_ba_solve: 8x8-tile left-looking Cholesky with FP64
+ * tensor-core MMAs + back substitution; replaces Ceres' dense Cholesky of the reduced camera system, call site
+ * estimator.cpp:3303-3318): x = A^-1 b for a symmetric positive definite A (n x n row-major, lower triangle read),
+ * 1 <= n <= 383.  tile_cap < 0: default number of factor tiles kept in shared memory; smaller values force the L2 spill
+ * path (tests). */
+int gf_stage_spd_solve(int device, const double* A, const double* b, int n, double* x, int tile_cap);
+
 /* ------------------------------------------------------------------------------------------------
  * Back end: Estimator::optimization() (estimator.cpp:2890-3636).  The caller (the Estimator adaptor)
  * fills one gf_ba_problem per call from its members exactly where the reference builds the

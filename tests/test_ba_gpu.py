@@ -96,13 +96,64 @@ def test_solve_with_plane_factors(ba, kw):
     assert np.abs(a.para_plane_R - b.para_plane_R).max() < 1e-6 and abs(a.para_plane_Z[0] - b.para_plane_Z[0]) < 1e-6
 
 
-def test_reduced_system_capacity_is_reported(ba):
-    """k_ba_step holds the reduced system of at most 175 unknowns in the registers of one CTA; a window with every optional
-    block free (165 + wheel 10 + plane 4 = 179) is refused with GF_ERR_CAPACITY, not silently mis-solved."""
-    from ground_fusion_b200._lib import GfError
+def test_all_optional_blocks_free_179_unknowns(ba):
+    """A window with every optional block free (165 + wheel 10 + plane 4 = 179 reduced unknowns; refused by the round-1
+    solver, whose register-blocked factorisation stopped at 175) against the oracle."""
     pb, _ = make_window(seed=4, with_plane=True, with_wheel=True)
-    with pytest.raises(GfError, match="175"):
-        ba.optimization(pb)
+    for it in (1, 8):
+        s = compare(ba, pb, it, mid_rtol=1e-6)
+        assert s["reduced_dim"] == 179
+
+
+@pytest.mark.parametrize("n", [1, 5, 7, 8, 9, 63, 64, 165, 179, 191, 192, 245, 383])
+@pytest.mark.parametrize("tile_cap", [-1, 10])
+def test_dense_solver_matches_numpy(n, tile_cap):
+    """The solver's tiled Cholesky + back substitution on its own (gf_stage_spd_solve) for sizes up to the capacity
+    (383 = 48 block rows; C4 with GNSS blocks is ~245), with the factor in shared memory (-1) and mostly spilled to L2 (10)."""
+    from ground_fusion_b200.estimator import spd_solve
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n + 5))
+    A = B @ B.T + n * np.eye(n)
+    b = rng.standard_normal(n)
+    x = spd_solve(A, b, tile_cap=tile_cap)
+    want = np.linalg.solve(A, b)
+    assert np.abs(x - want).max() <= 1e-11 * max(1.0, np.abs(want).max()) * np.linalg.cond(A)
+
+
+def test_dense_solver_graded_and_indefinite():
+    from ground_fusion_b200._lib import GfError
+    from ground_fusion_b200.estimator import spd_solve
+    rng = np.random.default_rng(0)
+    n = 120
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = (Q * np.logspace(0, 9, n)) @ Q.T          # information matrices of a VIO window span ~10 decades
+    A = 0.5 * (A + A.T)
+    b = rng.standard_normal(n)
+    x = spd_solve(A, b)
+    assert np.abs(A @ x - b).max() <= 1e-6 * np.abs(b).max()
+    A[17, 17] = -1.0
+    with pytest.raises(GfError, match="positive definite"):
+        spd_solve(A, b)
+
+
+def test_capacity_error_beyond_383():
+    from ground_fusion_b200._lib import GfError
+    from ground_fusion_b200.estimator import spd_solve
+    with pytest.raises(GfError):
+        spd_solve(np.eye(384), np.ones(384))
+
+
+def test_solve_with_factor_spilled_to_l2(monkeypatch):
+    """GF_BA_TILE_CAP=40 keeps only 40 of the C2 system's 231 factor tiles in shared memory: same results through the spill path."""
+    from ground_fusion_b200.estimator import BundleAdjuster
+    monkeypatch.setenv("GF_BA_TILE_CAP", "40")
+    b2 = BundleAdjuster(0)
+    monkeypatch.delenv("GF_BA_TILE_CAP")
+    try:
+        pb, _ = make_window(seed=1)
+        compare(b2, pb, 8)
+    finally:
+        b2.close()
 
 
 def test_solve_with_marginalization_prior(ba):
