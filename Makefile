@@ -24,6 +24,13 @@ $(OUT): $(BUILD)/fe_tracker.o $(BUILD)/ba_solver.o
 oracle:
 	$(MAKE) -C oracle
 
+# development aid: the same library with the clock64() phase counters compiled in (GF_B200_LIB=... selects it)
+profile: $(SRCS) $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -DGF_PROFILE -dc -o $(BUILD)/fe_tracker_prof.o $(CSRC)/fe_tracker.cu
+	$(NVCC) $(filter-out -fmad=false,$(NVFLAGS)) -DGF_PROFILE -dc -o $(BUILD)/ba_solver_prof.o $(CSRC)/ba_solver.cu
+	$(NVCC) $(ARCH) -shared -o ground_fusion_b200/libgf_b200_prof.so $(BUILD)/fe_tracker_prof.o $(BUILD)/ba_solver_prof.o
+
 clean:
 	rm -f $(OUT) build_ptxas.log; $(MAKE) -C oracle clean
-.PHONY: all oracle clean
+.PHONY: all oracle clean profile

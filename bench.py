@@ -3,26 +3,30 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one FeatureTracker::trackImage call on one 640x480 RGB-D frame of a synthetic stream with
-150 features (BASELINE.json configs[1], "C2").  Rank r tracks its own stream (seed r): weak scaling, no
-data-path collective; the timed region is bracketed by barrier + synchronize and the
-maximum over ranks is reported.
+A "step" is one pass of FeatureTracker::trackImage over one batch of FRAMES_PER_STEP = 100 consecutive 640x480 RGB-D frames
+of a synthetic stream with 150 features (BASELINE.json configs[1], "C2"), submitted as ONE library call
+(gf_tracker_track_batch: two frames in flight).  Rank r tracks its own stream (seed r): weak scaling, no data-path
+collective; the timed region of K steps is bracketed by barrier + synchronize and the maximum over ranks is
+reported.
 
-  value      frames/s with the frame already resident in HBM (gf_tracker_track_device)
-  e2e        frames/s through gf_tracker_track with pinned HOST buffers (H2D of gray+depth and D2H of
-             the observations inside the timed region)
-  roofline   of the dominant kernel (k_track: forward+reverse pyramidal LK), algorithmic bytes / duration
-  cpu_baseline  the cv2-based oracle of the same call on this box's host cores (bounded sample)
-  ba         (when the back end is built) sliding-window solves/s next to the CPU oracle
+  value         frames/s with the frames already resident in HBM (device pointers)
+  e2e           frames/s through the same call with pinned HOST frames: the H2D copy of gray + depth and the D2H copy of
+                the observations of every frame are inside the timed region
+  roofline      of the dominant kernel (k_track: forward + reverse pyramidal LK), algorithmic bytes / duration
+  cpu_baseline  the reference's CPU path on this box's host cores (bounded sample): its three OpenCV calls (cv2 4.13)
+                + its glue in C (oracle/fe_oracle.py::FeatureTrackerOracleFast); both the whole call and the OpenCV part
+  streams       N=1: several independent trackers on one GPU (1/2/4/8 host threads): the multi-stream figure of SURVEY 8(d)
+  configs       N=1: C3 (300 features) and C4 front end (1280x720, 500 features) lines; N>1: the C5 line (300 features / stream)
+  ba            N=1: sliding-window solves/s through gf_ba_solve next to the CPU oracle, roofline against the measured
+                FP64 rate of the device, marginalisation times
 
---impl reference times the reference's CPU path: the reference cannot be compiled here (ROS/Eigen/Ceres/
-OpenCV C++ absent), so this is the line-by-line restatement on the same three OpenCV entry points
-(oracle/fe_oracle.py; kind "port").
+--impl reference times the reference's CPU path: the reference cannot be compiled here (ROS / Eigen / Ceres / OpenCV C++
+absent), so this is the restatement on the same three OpenCV entry points (kind "port"), all host threads.
 """
 import argparse
+import ctypes
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -32,8 +36,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, MAX_CNT, MIN_DIST = 640, 480, 150, 30
-RING = 160            # distinct frames per stream: 160 x 0.92 MB = 147 MB > 126 MB L2
+FRAMES_PER_STEP = 100
+WORKLOADS = {
+    "C2": dict(w=640, h=480, max_cnt=150, min_dist=30, ring=160,
+               name="C2: synthetic 640x480 RGB-D stream, 150 features, min_dist 30, flow_back 1 (BASELINE.json configs[1])"),
+    "C3": dict(w=640, h=480, max_cnt=300, min_dist=20, ring=160,
+               name="C3/C5 front end: synthetic 640x480 RGB-D stream, 300 features, min_dist 20 (BASELINE.json configs[2], [4])"),
+    "C4": dict(w=1280, h=720, max_cnt=500, min_dist=25, ring=56,
+               name="C4 front end: synthetic 1280x720 RGB-D stream, 500 features, min_dist 25 (BASELINE.json configs[3])"),
+}
 
 
 def tri(k, n):
@@ -43,85 +54,210 @@ def tri(k, n):
 
 
 class ClockSampler(threading.Thread):
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons through NVML (no process is forked while a timed region runs); rank 0 only."""
 
-    def __init__(self, gpu):
+    def __init__(self, gpu, period=0.05):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.period, self.rows, self.stop_flag, self.active = gpu, period, [], False, False
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu]) if vis and vis.split(",")[gpu].isdigit() else gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
 
     def run(self):
+        nv = self.nv if self.h is not None else None
         while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+            if self.active and nv is not None:
+                try:
+                    self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                      nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+                except Exception:
+                    try:
+                        self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+                    except Exception:
+                        pass
+            time.sleep(self.period)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[1]) for r in self.rows)
-        reasons = []
-        for i, name in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
-            if any(r[i].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][2]), "reasons": reasons, "samples": len(self.rows)}
+        sm = sorted(r[0] for r in self.rows)
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        reasons = [name for b, name in bits.items() if any(r[1] & b for r in self.rows)]
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_sm), "reasons": reasons, "samples": len(self.rows),
+                "source": "NVML, sampled every %d ms inside the timed regions (rank 0)" % int(self.period * 1e3)}
 
 
-def make_frames(seed, n):
+def pin_to_local_cpus(local_rank, n_local):
+    """Give every rank a disjoint slice of the CPUs that are NUMA-local to its GPU (falls back to doing nothing)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bus.lower()[-12:]
+        txt = open(path).read().strip()
+        cpus = []
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        cpus = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not cpus:
+            return None
+        # the ranks whose GPUs share this NUMA node split its CPUs evenly
+        same = [r for r in range(n_local) if _cpulist_of(r) == txt]
+        k = same.index(local_rank) if local_rank in same else 0
+        per = max(1, len(cpus) // max(1, len(same)))
+        mine = cpus[k * per:(k + 1) * per] or cpus
+        os.sched_setaffinity(0, mine)
+        return "%d cpus NUMA-local to the GPU (%s)" % (len(mine), txt)
+    except Exception:
+        return None
+
+
+def _cpulist_of(idx):
+    try:
+        import pynvml
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        return open("/sys/bus/pci/devices/%s/local_cpulist" % bus.lower()[-12:]).read().strip()
+    except Exception:
+        return None
+
+
+def make_frames(seed, n, w, h):
     from ground_fusion_b200.synth import SyntheticStream
-    st = SyntheticStream(seed=seed, width=W, height=H)
-    gray = np.empty((n, H, W), np.uint8)
-    depth = np.empty((n, H, W), np.uint16)
+    st = SyntheticStream(seed=seed, width=w, height=h)
+    gray = np.empty((n, h, w), np.uint8)
+    depth = np.empty((n, h, w), np.uint16)
     for k in range(n):
         _, gray[k], depth[k] = st.frame(k)
     return gray, depth
 
 
-def cpu_reference_fps(gray, depth, budget_s, warm=3):
-    """frames/s of the cv2-based oracle (the reference's three OpenCV calls + its glue) on host cores."""
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference(gray, depth, wl, n_steps, frames_per_step, warm_steps=1):
+    """frames/s of the reference's CPU path (cv2 calls + C glue) over n_steps bounded samples; also the OpenCV-only rate."""
     import cv2
-    from oracle.fe_oracle import IDC_CAM, FeatureTrackerOracle, PinholeCamera
-    ft = FeatureTrackerOracle(PinholeCamera(**IDC_CAM), MAX_CNT, MIN_DIST, 1, 1)
+    from oracle.fe_oracle import IDC_CAM, FeatureTrackerOracleFast, PinholeCamera
+    sc = wl["w"] / 640.0
+    cam = PinholeCamera(IDC_CAM["fx"] * sc, IDC_CAM["fy"] * sc, IDC_CAM["cx"] * sc, IDC_CAM["cy"] * sc,
+                        IDC_CAM["k1"], IDC_CAM["k2"], IDC_CAM["p1"], IDC_CAM["p2"])
+    ft = FeatureTrackerOracleFast(cam, wl["max_cnt"], wl["min_dist"], 1, 1)
     n = len(gray)
     k = 0
-    for _ in range(warm):
+    for _ in range(warm_steps * frames_per_step):
         ft.trackImage(k / 30.0, gray[tri(k, n)], depth[tri(k, n)]); k += 1
-    t0 = time.perf_counter(); done = 0
-    while time.perf_counter() - t0 < budget_s:
-        ft.trackImage(k / 30.0, gray[tri(k, n)], depth[tri(k, n)]); k += 1; done += 1
+    ft.t_cv = 0.0
+    t0 = time.perf_counter()
+    for _ in range(n_steps * frames_per_step):
+        ft.trackImage(k / 30.0, gray[tri(k, n)], depth[tri(k, n)]); k += 1
     dt = time.perf_counter() - t0
-    return done / dt, done, cv2.getNumThreads()
+    done = n_steps * frames_per_step
+    return {"fps": done / dt, "cv_only_fps": done / ft.t_cv, "glue_fraction": 1.0 - ft.t_cv / dt, "frames": done, "threads": cv2.getNumThreads()}
 
 
-def ba_roofline(nc, n_lm, iterations, device_ms, step_share=0.77):
-    """Algorithmic FP64 work of k_ba_step (the dominant kernel: 77 % of a solve's kernel time in
-    profiles/r1_ncu_launches_ba_v5.csv) against the FP64 rate of the ONE SM a single-CTA kernel can use (58 DFMA/clk measured
-    on a B200 SM).  Per launch: Cholesky of the (nc+1)-row reduced system (nc+1)^3/3 FMA, the two triangular solves nc^2 FMA,
-    landmark back-substitution and dogleg / model terms ~3*n_lm*nc FMA."""
-    launches = iterations + 1
-    fma = iterations * ((nc + 1) ** 3 / 3.0 + nc * nc + 3.0 * n_lm * nc)
-    flops = 2.0 * fma
-    sm_peak = 58.0 * 2 * 1.965e9
-    t = step_share * device_ms * 1e-3
-    ach = flops / t if t > 0 else None
-    return {"kernel": "k_ba_step (single CTA: adoption, register-blocked Cholesky with look-ahead, back substitution, dogleg)",
-            "bound": "latency: 43 dependent panels per factorisation, FP64 pipe 8 % busy (profiles/r1_ncu_k_ba_step_full.txt)",
-            "algorithmic_flops_per_launch": flops / launches, "launches_per_solve": launches,
-            "time_share_of_solve": step_share, "achieved": ach / 1e9 if ach else None, "unit": "GFLOP/s (FP64)",
-            "peak": sm_peak / 1e9, "peak_source": "58 DFMA/clk measured on one B200 SM x 1.965 GHz x 2 flop",
-            "frac": (ach / sm_peak) if ach else None}
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+class Ring:
+    """Frames of one stream: resident in HBM and in pinned host memory."""
+
+    def __init__(self, seed, wl, torch):
+        self.n = wl["ring"]
+        gray, depth = make_frames(seed, self.n, wl["w"], wl["h"])
+        self.gray, self.depth = gray, depth
+        self.d_gray = torch.from_numpy(gray).cuda()
+        self.d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
+        self.h_gray = torch.from_numpy(gray).pin_memory()
+        self.h_depth = torch.from_numpy(depth.view(np.int16)).pin_memory()
+        fb_g, fb_d = wl["w"] * wl["h"], wl["w"] * wl["h"] * 2
+        self.ptr = {"device": ([self.d_gray.data_ptr() + i * fb_g for i in range(self.n)], [self.d_depth.data_ptr() + i * fb_d for i in range(self.n)]),
+                    "host": ([self.h_gray.data_ptr() + i * fb_g for i in range(self.n)], [self.h_depth.data_ptr() + i * fb_d for i in range(self.n)])}
 
 
-def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
-    """Sliding-window solves/s (C2: 11 frames, ~1.5 k visual factors, 10 IMU factors, 8 iterations max) on the GPU
-    through gf_ba_solve (host descriptor in, optimised blocks out: this IS the end-to-end call) next to the CPU oracle."""
+class Stream:
+    def __init__(self, ring, wl, device, offset=0):
+        from ground_fusion_b200.feature_tracker import FeatureTracker
+        from ground_fusion_b200.synth import idc_params8
+        sc = wl["w"] / 640.0
+        p8 = idc_params8()
+        p8 = [p8[0] * sc, p8[1] * sc, p8[2] * sc, p8[3] * sc] + p8[4:]
+        self.tr = FeatureTracker(wl["w"], wl["h"], p8, wl["max_cnt"], wl["min_dist"], 1, 1, device=device)
+        self.ring, self.k, self.dev_ms = ring, offset, 0.0
+
+    def run(self, n_steps, mode):
+        """n_steps batches of FRAMES_PER_STEP frames; returns the device time of the run (CUDA events on the tracker's streams)."""
+        g, d = self.ring.ptr[mode]
+        n = self.ring.n
+        self.tr.timer_start()
+        for _ in range(n_steps):
+            idx = [tri(self.k + j, n) for j in range(FRAMES_PER_STEP)]
+            times = [(self.k + j) / 30.0 for j in range(FRAMES_PER_STEP)]
+            self.tr.trackBatch(times, [g[i] for i in idx], [d[i] for i in idx], on_device=(mode == "device"), want=False)
+            self.k += FRAMES_PER_STEP
+        self.dev_ms = self.tr.timer_stop()
+        return self.dev_ms
+
+
+def timed(streams, n_steps, mode, barrier, sampler=None):
+    """K steps on every stream of this rank (one host thread per stream); wall clock between barriers."""
+    barrier()
+    if sampler is not None:
+        sampler.active = True
+    t0 = time.perf_counter()
+    if len(streams) == 1:
+        streams[0].run(n_steps, mode)
+    else:
+        th = [threading.Thread(target=s.run, args=(n_steps, mode)) for s in streams]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+    barrier()
+    el = time.perf_counter() - t0
+    if sampler is not None:
+        sampler.active = False
+    return el, max(s.dev_ms for s in streams)
+
+
+def fe_line(wl, rings, device, n_streams, steps, warmup, barrier, sampler, reduce_max):
+    streams = [Stream(rings[0], wl, device, offset=17 * s) for s in range(n_streams)]
+    from ground_fusion_b200 import _lib
+    timed(streams, warmup, "device", barrier)
+    l0 = _lib.lib().gf_kernel_launch_count()
+    el_dev, ms_dev = timed(streams, steps, "device", barrier, sampler)
+    launches = _lib.lib().gf_kernel_launch_count() - l0
+    timed(streams, max(1, warmup // 2), "host", barrier)
+    el_e2e, ms_e2e = timed(streams, steps, "host", barrier, sampler)
+    el_dev, el_e2e, ms_dev, ms_e2e = reduce_max([el_dev, el_e2e, ms_dev, ms_e2e])
+    infos = streams[0].tr.batch_infos
+    for s in streams:
+        s.tr.close()
+    frames = n_streams * steps * FRAMES_PER_STEP
+    return {"value": frames / el_dev, "e2e": frames / el_e2e, "ms_per_step": 1e3 * el_dev / steps, "ms_per_step_e2e": 1e3 * el_e2e / steps,
+            "device_ms_per_step": ms_dev / steps, "device_ms_per_step_e2e": ms_e2e / steps, "streams_per_gpu": n_streams, "gpu_launches": int(launches),
+            "mean_features_tracked": float(np.mean([i["n_tracked"] for i in infos])), "mean_lk_iterations": float(np.mean([i["lk_iterations"] for i in infos]))}
+
+
+def ba_bench(device, clocks_mhz, n_windows=8, reps=200, cpu_seconds=8.0):
+    """Sliding-window solves/s (C2: 11 frames, ~1.8 k visual factors, 10 IMU factors, 8 iterations max) on the GPU through
+    gf_ba_solve (host descriptor in, optimised blocks out: this IS the end-to-end call) next to the CPU oracle."""
+    from ground_fusion_b200 import _lib
     from ground_fusion_b200.estimator import BundleAdjuster
     from ground_fusion_b200.synth_ba import make_window
+    L = _lib.lib()
     wins = [make_window(seed=100 + k)[0] for k in range(n_windows)]
     saved = [(w.para_pose.copy(), w.para_speed_bias.copy(), w.para_feature.copy(), w.para_ex_pose.copy(), w.para_td.copy()) for w in wins]
     structs = [w.struct() for w in wins]
@@ -130,38 +266,59 @@ def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
         w, sv = wins[k], saved[k]
         w.para_pose[:] = sv[0]; w.para_speed_bias[:] = sv[1]; w.para_feature[:] = sv[2]; w.para_ex_pose[:] = sv[3]; w.para_td[:] = sv[4]
     ba = BundleAdjuster(device)
+    L.gf_ba_debug_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
     for k in range(n_windows):
         restore(k); ba.solve_struct(structs[k])
-    dev_ms = 0.0; iters = 0
+    dev_ms = 0.0; iters = 0; step_cycles = 0; step_launches = 0
+    prof = (ctypes.c_longlong * 32)()
     t0 = time.perf_counter()
     for r in range(reps):
         k = r % n_windows
         restore(k)
         sm = ba.solve_struct(structs[k])
         dev_ms += sm.device_ms; iters += sm.iterations
+        L.gf_ba_debug_profile(ba._h, prof)
+        step_cycles += prof[30]; step_launches += prof[31]
     el = time.perf_counter() - t0
+    nc, n_lm = int(sm.reduced_dim), int(sm.n_free_landmarks)
     out = {"metric": "ba_solves_per_sec", "value": reps / el, "unit": "solves/s", "ms_per_solve": 1e3 * el / reps,
            "device_ms_per_solve": dev_ms / reps, "iterations_per_solve": iters / reps,
            "workload": "C2 window: 11 frames, %d visual factors, %d IMU factors, reduced system %d + %d free landmarks, max 8 iterations"
-                       % (wins[0].n_visual, wins[0].n_imu, sm.reduced_dim, sm.n_free_landmarks),
+                       % (wins[0].n_visual, wins[0].n_imu, nc, n_lm),
            "e2e": "value already includes the host->device upload of the problem and the download of the blocks"}
-    out["roofline"] = ba_roofline(int(sm.reduced_dim), int(sm.n_free_landmarks), iters / reps, dev_ms / reps)
+    # roofline of the dominant kernel (k_ba_step: tiled Cholesky on DMMA + back substitution + dogleg), per launch:
+    # (nc+1)^3/3 (factorisation) + nc^2 (two triangular solves) + 3 n_lm nc (landmark back substitution, dogleg terms) FMA
+    dfma, dmma = ctypes.c_double(0), ctypes.c_double(0)
+    L.gf_probe_fp64.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    L.gf_probe_fp64(device, ctypes.byref(dfma), ctypes.byref(dmma))
+    fma = (nc + 1) ** 3 / 3.0 + nc * nc + 3.0 * n_lm * nc
+    mhz = clocks_mhz or 1965.0
+    t_launch = (step_cycles / max(1, step_launches)) / (mhz * 1e6)
+    ach = 2.0 * fma / t_launch / 1e9 if t_launch > 0 else None
+    n_sm = 148
+    out["roofline"] = {"kernel": "k_ba_step (one CTA: 8x8-tile left-looking Cholesky on DMMA.8x8x4, back substitution, dogleg, candidate)",
+                       "bound": "tensor", "unit": "GFLOP/s (FP64)", "achieved": ach, "peak": dmma.value, "frac": ach / dmma.value if ach else None,
+                       "peak_source": "gf_probe_fp64: DMMA.8x8x4 on all SMs, measured in this run (plain DFMA: %.0f GFLOP/s)" % dfma.value,
+                       "frac_of_one_sm": ach / (dmma.value / n_sm) if ach else None,
+                       "algorithmic_flops_per_launch": 2.0 * fma, "launch_us": 1e6 * t_launch, "launches_per_solve": step_launches / reps,
+                       "time_share_of_solve": (step_cycles / (mhz * 1e3)) / dev_ms if dev_ms else None, "traffic": None,
+                       "note": "a single window is a dependent chain of %d panel factorisations on ONE SM (latency-bound: rsqrt chain of the 8x8 diagonal "
+                               "tiles); the kernel cannot use more than 1/%d of the device, see frac_of_one_sm" % ((nc + 8) // 8, n_sm)}
     # the marginalisation that ends Estimator::optimization() on a keyframe (MARGIN_OLD), on the solved window
     restore(0); ba.solve_struct(structs[0])
     ba.marginalize_old(wins[0])
     mms = []
     for _ in range(5):
         ba.marginalize_old(wins[0]); mms.append(ba.last_marg_ms)
-    out["marginalize_old"] = {"device_ms": float(np.median(mms)), "note": "gf_ba_marginalize_old on the solved C2 window (191 marginalised + 76 kept dimensions)"}
+    out["marginalize_old"] = {"device_ms": float(np.median(mms)), "note": "gf_ba_marginalize_old on the solved C2 window"}
     ba.close()
-    # independent windows (several estimators sharing one GPU): one gf_ba handle and one host thread per stream; a solve
-    # occupies 1-121 CTAs for microseconds at a time, so concurrent solves spread over the SMs
-    import threading
+    # independent windows (several estimators sharing one GPU): one gf_ba handle and one host thread per stream
     n_str = 4
     sets = []
     for t in range(n_str):
         ws = [make_window(seed=200 + 10 * t + k)[0] for k in range(2)]
         sets.append((ws, [w.struct() for w in ws], [(w.para_pose.copy(), w.para_speed_bias.copy(), w.para_feature.copy()) for w in ws], BundleAdjuster(device)))
+
     def worker(t, n):
         ws, st, sv, b = sets[t]
         for r in range(n):
@@ -181,50 +338,49 @@ def ba_bench(device, n_windows=8, reps=40, cpu_seconds=8.0, with_cpu=True):
                                  "note": "aggregate of %d independent windows solved concurrently on one GPU (one gf_ba handle + host thread each)" % n_str}
     for s_ in sets:
         s_[3].close()
-    if with_cpu:
-        from oracle import ba_oracle
-        t0 = time.perf_counter(); done = 0
-        while time.perf_counter() - t0 < cpu_seconds:
-            k = done % n_windows
-            restore(k); ba_oracle.solve(wins[k]); done += 1
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": done / dt, "unit": "solves/s", "cores": 1, "kind": "port",
-                               "sample": "%d solves of the same windows, oracle/ba_oracle.c (block-sparse, -O2, 1 thread)" % done}
-        restore(0); ba_oracle.solve(wins[0])
-        t0 = time.perf_counter(); ba_oracle.marginalize_old(wins[0]); 
-        out["marginalize_old"]["cpu_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
-        out["marginalize_old"]["cpu_note"] = "oracle uses a plain cyclic Jacobi eigensolver (slower than Eigen's tridiagonal QR the reference calls)"
+    from oracle import ba_oracle
+    t0 = time.perf_counter(); done = 0
+    while time.perf_counter() - t0 < cpu_seconds:
+        k = done % n_windows
+        restore(k); ba_oracle.solve(wins[k]); done += 1
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"value": done / dt, "unit": "solves/s", "cores": 1, "kind": "port",
+                           "sample": "%d solves of the same windows, oracle/ba_oracle.c (block-sparse Schur, gcc -O3 as the reference, 1 thread)" % done}
+    out["speedup_vs_cpu"] = out["value"] / out["cpu_baseline"]["value"]
+    restore(0); ba_oracle.solve(wins[0])
+    t0 = time.perf_counter(); ba_oracle.marginalize_old(wins[0])
+    out["marginalize_old"]["cpu_oracle_ms"] = 1e3 * (time.perf_counter() - t0)
     return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--ring", type=int, default=RING)
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--no-extras", action="store_true", help="only the headline C2 line (no stream sweep, C3/C4, BA)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    cfg = {"workload": "C2: synthetic 640x480 RGB-D stream, 150 features, min_dist 30, flow_back 1 (BASELINE.json configs[1])",
-           "frames_ring": args.ring, "l2_policy": "inputs larger than L2 (ring of %d distinct frames = %.0f MB per stream)" % (args.ring, args.ring * W * H * 3 / 1e6),
+    wl = WORKLOADS["C2"]
+    cfg = {"workload": wl["name"], "frames_per_step": FRAMES_PER_STEP, "frames_ring": wl["ring"],
+           "l2_policy": "inputs larger than L2 (ring of %d distinct frames = %.0f MB per stream)" % (wl["ring"], wl["ring"] * wl["w"] * wl["h"] * 3 / 1e6),
            "streams_per_gpu": 1, "parallelism": "one independent stream per GPU"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        gray, depth = make_frames(0, min(args.ring, 60))
-        vals = []
-        for _ in range(max(1, min(args.steps, 3))):          # each step = a bounded sample of the workload
-            fps, done, cores = cpu_reference_fps(gray, depth, min(args.cpu_seconds, 10.0))
-            vals.append(fps)
-        v = float(np.median(vals))
+        gray, depth = make_frames(0, 60, wl["w"], wl["h"])
+        fps_step = 20                     # each step = a bounded sample (20 frames) of the 100-frame batch
+        r = cpu_reference(gray, depth, wl, max(1, args.steps), fps_step, warm_steps=max(1, min(args.warmup, 3)))
+        v = r["fps"]
         print(json.dumps({"impl": "reference", "metric": "tracker_frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak",
-                          "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic", "config": cfg,
-                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                                           "sample": "%d frames of the C2 stream per sample, cv2 %s threads" % (done, cores)},
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * fps_step / v, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8/f32 (OpenCV)", "data": "synthetic", "config": cfg,
+                          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": r["threads"], "kind": "port",
+                                           "sample": "%d frames of the C2 stream per step (bounded sample of the 100-frame batch), %d steps; cv2 %d threads" % (fps_step, args.steps, r["threads"]),
+                                           "opencv_calls_only": r["cv_only_fps"], "glue_fraction": r["glue_fraction"]},
                           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -236,16 +392,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    affinity = pin_to_local_cpus(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     from ground_fusion_b200 import _lib
-    from ground_fusion_b200.feature_tracker import FeatureTracker
-    from ground_fusion_b200.synth import idc_params8      # config/realsense/idc_cam.yaml
-
-    gray, depth = make_frames(rank, args.ring)
-    d_gray = torch.from_numpy(gray).cuda()
-    d_depth = torch.from_numpy(depth.view(np.int16)).cuda()
-    h_gray = torch.from_numpy(gray).pin_memory(); h_depth = torch.from_numpy(depth.view(np.int16)).pin_memory()
-    hg, hd = h_gray.numpy(), h_depth.numpy().view(np.uint16)
-    tr = FeatureTracker(W, H, idc_params8(), MAX_CNT, MIN_DIST, 1, 1, device=local)
 
     def barrier():
         torch.cuda.synchronize()
@@ -253,94 +401,112 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(n, mode, k0):
-        """n frames through the asynchronous API, two in flight (submit k+1 before collecting k).  Returns the
-        device time of the whole run (CUDA events around the first copy and the last result copy)."""
-        tr.timer_start()
-        pending = 0
-        for k in range(k0, k0 + n):
-            i = tri(k, args.ring)
-            if mode == "device":
-                tr.submitDevice(k / 30.0, d_gray[i].data_ptr(), d_depth[i].data_ptr())
-            else:
-                tr.submit(k / 30.0, hg[i], hd[i])      # pinned ring: unchanged until collected
-            pending += 1
-            if pending == 2:
-                tr.wait(); pending -= 1
-        while pending:
-            tr.wait(); pending -= 1
-        return tr.timer_stop()
+    def reduce_max(vals):
+        if dist is None:
+            return vals
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
-    sampler = ClockSampler(local); sampler.start()
-    launches0 = _lib.lib().gf_kernel_launch_count()
-    # ---- kernel-side value: frames already in HBM ----
-    run(args.warmup, "device", 0)
-    barrier(); t0 = time.perf_counter()
-    dev_ms = run(args.steps, "device", args.warmup)
-    barrier(); el_dev = time.perf_counter() - t0
-    launches = _lib.lib().gf_kernel_launch_count() - launches0
-    # ---- stage breakdown (separate pass; event records only) ----
-    tr.set_profiling(True)
-    stage = {}; iters = 0; nprev = 0
-    for k in range(args.warmup + args.steps, args.warmup + args.steps + 50):
-        i = tri(k, args.ring)
-        tr.trackDevice(k / 30.0, d_gray[i].data_ptr(), d_depth[i].data_ptr())
-        for s, v in tr.last_stage_ms().items():
-            stage[s] = stage.get(s, 0.0) + v / 50.0
-        iters += tr.last_info["lk_iterations"] / 50.0; nprev += tr.last_info["n_prev"] / 50.0
-    tr.set_profiling(False)
-    # ---- end to end: host buffers in, observations out ----
-    k1 = args.warmup + args.steps + 50
-    run(args.warmup, "host", k1)
-    barrier(); t0 = time.perf_counter()
-    dev_ms_e2e = run(args.steps, "host", k1 + args.warmup)
-    barrier(); el_e2e = time.perf_counter() - t0
-    sampler.stop_flag = True; sampler.join(timeout=2)
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(local); sampler.start()
+    ring = Ring(rank, wl, torch)
+    head = fe_line(wl, [ring], local, 1, args.steps, args.warmup, barrier, sampler, reduce_max)
+    clocks = sampler.summary() if sampler is not None else None
 
-    if dist is not None:
-        tt = torch.tensor([el_dev, el_e2e, dev_ms, dev_ms_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        el_dev, el_e2e, dev_ms, dev_ms_e2e = float(tt[0]), float(tt[1]), float(tt[2]), float(tt[3])
+    extra = {}
+    if world > 1 and not args.no_extras:
+        # C5: 300 features per stream, one stream per GPU
+        w5 = WORKLOADS["C3"]
+        ring5 = Ring(rank, w5, torch)
+        c5 = fe_line(w5, [ring5], local, 1, args.steps, args.warmup, barrier, None, reduce_max)
+        extra["C5"] = {"workload": w5["name"] + ", one stream per GPU", "value": world * c5["value"], "e2e": world * c5["e2e"], "unit": "frames/s",
+                       "ms_per_step": c5["ms_per_step"]}
+        del ring5
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
-    # algorithmic bytes of k_track per launch (SURVEY 8d): prev-window gathers (23x23 per level: 4 fwd + 2 bwd
-    # levels per feature) + next-image window per LK iteration (22x22)
-    lk_bytes = nprev * 6 * 23 * 23 + iters * 22 * 22
-    lk_s = stage.get("lk", 0.0) / 1e3
-    roof = {"kernel": "k_track (fwd 4-level + reverse 2-level LK, one 8-warp CTA per feature)", "bound": "hbm",
-            "achieved": (lk_bytes / lk_s / 1e9) if lk_s > 0 else None, "peak": hbm,
-            "unit": "GB/s", "frac": (lk_bytes / lk_s / 1e9 / hbm) if lk_s > 0 else None,
-            "traffic": 876544, "traffic_source": "dram__bytes_read+write of one k_track launch, profiles/r1_ncu_k_track_full.txt",
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-            "algorithmic_bytes_per_launch": lk_bytes, "kernel_ms": stage.get("lk"),
-            "note": "latency-bound by construction: per feature a chain of ~22 dependent LK iterations, each 105 dependent FADDs in OpenCV lane order; kernel_ms is the stage time of a profiled (one frame at a time) pass"}
-    value = world * args.steps / el_dev
-    out = {"metric": "tracker_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1000.0 * el_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    out = {"metric": "tracker_frames_per_sec", "value": world * head["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u8/i32 fixed point + f32 (LK, min-eig), f64 (box sums, undistortion)", "data": "synthetic", "config": cfg,
-           "device_ms_per_step": dev_ms / args.steps, "device_ms_per_step_e2e": dev_ms_e2e / args.steps,
-           "timing": "value/e2e: wall clock between barrier+synchronize, max over ranks; device_ms_per_step*: CUDA events "
-                     "around the same K frames on the tracker's streams (first copy .. last result copy), max over ranks",
-           "frames_in_flight": 2, "stage_ms": stage,
-           "e2e": {"value": world * args.steps / el_e2e, "unit": "frames/s", "h2d_bytes_per_step": W * H * 3,
-                   "d2h_bytes_per_step": MAX_CNT * 72 + 40 + MAX_CNT},
-           "gpu_launches": int(launches), "roofline": roof, "clocks": sampler.summary()}
-    if world == 1:
-        fps, done, cores = cpu_reference_fps(gray[:60], depth[:60], args.cpu_seconds)
-        out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                               "sample": "%d frames of the same C2 stream, cv2-based oracle (reference's OpenCV calls + glue)" % done}
+           "device_ms_per_step": head["device_ms_per_step"], "device_ms_per_step_e2e": head["device_ms_per_step_e2e"],
+           "timing": "value/e2e: wall clock between barrier+synchronize around K steps of %d frames, max over ranks; device_ms_per_step*: CUDA events "
+                     "around the same frames on the tracker's streams (first copy .. last result copy), max over ranks" % FRAMES_PER_STEP,
+           "frames_in_flight": 2, "mean_features_tracked": head["mean_features_tracked"],
+           "e2e": {"value": world * head["e2e"], "unit": "frames/s", "h2d_bytes_per_step": FRAMES_PER_STEP * wl["w"] * wl["h"] * 3,
+                   "d2h_bytes_per_step": FRAMES_PER_STEP * (wl["max_cnt"] * 72 + 40 + 1024), "ms_per_step": head["ms_per_step_e2e"]},
+           "gpu_launches": head["gpu_launches"], "gpu_launches_note": "kernels launched by libgf_b200 (rank 0) inside the K timed device-resident steps",
+           "clocks": clocks, "cpu_affinity": affinity}
+    out.update(extra)
+
+    if world == 1 and not args.no_extras:
+        from ground_fusion_b200.feature_tracker import FeatureTracker
+        from ground_fusion_b200.synth import idc_params8
+        # ---- stage breakdown + roofline of the dominant kernel (profiling mode: one frame at a time, event records only) ----
+        tr = FeatureTracker(wl["w"], wl["h"], idc_params8(), wl["max_cnt"], wl["min_dist"], 1, 1, device=local)
+        g, d = ring.ptr["device"]
+        for k in range(30):
+            tr.trackDevice(k / 30.0, g[tri(k, ring.n)], d[tri(k, ring.n)])
+        tr.set_profiling(True)
+        stage = {}; iters = 0; nprev = 0
+        for k in range(30, 80):
+            tr.trackDevice(k / 30.0, g[tri(k, ring.n)], d[tri(k, ring.n)])
+            for s, v in tr.last_stage_ms().items():
+                stage[s] = stage.get(s, 0.0) + v / 50.0
+            iters += tr.last_info["lk_iterations"] / 50.0; nprev += tr.last_info["n_prev"] / 50.0
+        tr.set_profiling(False); tr.close()
+        lk_bytes = nprev * 6 * 23 * 23 + iters * 22 * 22        # window gathers (4 fwd + 2 bwd levels) + one 22x22 window per LK iteration
+        lk_s = stage.get("lk", 0.0) / 1e3
+        out["stage_ms"] = stage
+        out["roofline"] = {"kernel": "k_track (fwd 4-level + reverse 2-level LK, one 8-warp CTA per feature)", "bound": "hbm",
+                           "achieved": (lk_bytes / lk_s / 1e9) if lk_s > 0 else None, "peak": hbm, "unit": "GB/s",
+                           "frac": (lk_bytes / lk_s / 1e9 / hbm) if lk_s > 0 else None,
+                           "traffic": 876544, "traffic_source": "dram__bytes_read+write of one k_track launch, profiles/r1_ncu_k_track_full.txt",
+                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                           "algorithmic_bytes_per_launch": lk_bytes, "kernel_ms": stage.get("lk"),
+                           "note": "latency-bound by construction: per feature a chain of ~22 dependent LK iterations, each 105 dependent FADDs in OpenCV lane order; "
+                                   "throughput comes from concurrent streams (see streams)"}
+        # ---- several independent streams on one GPU ----
+        sweep = {}
+        for ns in (2, 4, 8):
+            r = fe_line(wl, [ring], local, ns, max(4, args.steps // 2), 2, barrier, None, reduce_max)
+            sweep[str(ns)] = {"value": r["value"], "e2e": r["e2e"]}
+        sweep["1"] = {"value": head["value"], "e2e": head["e2e"]}
+        out["streams"] = {"unit": "frames/s", "per_streams_per_gpu": sweep,
+                          "note": "independent trackers (gf_tracker handles) sharing one B200, one host thread each; C2 workload"}
+        # ---- the other configurations ----
+        cfgs = {}
+        for name in ("C3", "C4"):
+            w2 = WORKLOADS[name]
+            ring2 = ring if (w2["w"], w2["h"]) == (wl["w"], wl["h"]) else Ring(0, w2, torch)
+            r = fe_line(w2, [ring2], local, 1, max(4, args.steps // 2), 2, barrier, None, reduce_max)
+            cpu = cpu_reference(ring2.gray[:40], ring2.depth[:40], w2, 1, 40 if name == "C3" else 20)
+            cfgs[name] = {"workload": w2["name"], "value": r["value"], "e2e": r["e2e"], "unit": "frames/s", "ms_per_step": r["ms_per_step"],
+                          "mean_features_tracked": r["mean_features_tracked"],
+                          "cpu_baseline": {"value": cpu["fps"], "opencv_calls_only": cpu["cv_only_fps"], "cores": cpu["threads"], "kind": "port", "sample": "%d frames" % cpu["frames"]}}
+            if ring2 is not ring:
+                del ring2
+        out["configs"] = cfgs
+        # ---- CPU baseline of the headline workload ----
+        cpu = cpu_reference(ring.gray[:60], ring.depth[:60], wl, max(1, int(args.cpu_seconds / 0.6)), 100, warm_steps=1)
+        out["cpu_baseline"] = {"value": cpu["fps"], "unit": "frames/s", "cores": cpu["threads"], "kind": "port",
+                               "sample": "%d frames of the same C2 stream: the reference's three OpenCV calls (cv2 4.13) + its glue in C (FeatureTrackerOracleFast)" % cpu["frames"],
+                               "opencv_calls_only": cpu["cv_only_fps"], "glue_fraction": cpu["glue_fraction"]}
         try:
-            out["ba"] = ba_bench(local, cpu_seconds=min(args.cpu_seconds, 8.0))
+            out["ba"] = ba_bench(local, (clocks or {}).get("sm_mhz"), cpu_seconds=min(args.cpu_seconds, 8.0))
         except Exception as e:      # the FE line must survive a BA problem
             out["ba"] = {"error": repr(e)}
+    if sampler is not None:
+        sampler.stop_flag = True
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgf_b200.so")
+LIB_PATH = os.environ.get("GF_B200_LIB") or os.path.join(_HERE, "libgf_b200.so")   # GF_B200_LIB: a -DGF_PROFILE build (tools/)
 _LIB = None
 
 

@@ -94,8 +94,9 @@ class Problem:
 
     def set_plane(self, frames):
         """One PlaneFactor per listed frame (estimator.cpp:3152-3166)."""
-        self.plane_frames = np.ascontiguousarray(list(frames), np.int32) if len(list(frames)) else np.zeros(1, np.int32)
-        self.n_plane = len(list(frames))
+        frames = list(frames)                      # materialise once: `frames` may be a generator
+        self.plane_frames = np.ascontiguousarray(frames, np.int32) if frames else np.zeros(1, np.int32)
+        self.n_plane = len(frames)
 
     def struct(self):
         p = BaProblem()

@@ -43,6 +43,7 @@ struct BaState {
     double cauchy_num, cauchy_den;   // |gs|^2 and v^T H' v accumulated by k_ba_schur
     int it, reuse, done, termination, n_success, invalid_streak, need_linearize, step_valid, cur, first, max_iter, solver_failed;
     unsigned int eval_ticket;    // CTAs of the current k_ba_eval(1) that have finished: the last one runs the decision
+    int setup_failed;            // sticky: an IMU covariance was singular / not positive definite (k_ba_setup); nothing is solved
     long long prof[32];          // clock64() cycles per phase of k_ba_step, summed over iterations (debug)
 };
 
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(128) k_ba_setup(BaDev d)
     const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     const int nc = d.nc;
     for (int e = gid; e < nc * nc; e += gsz) d.Hp[e] = 0.0;
+    if (d.Xc != d.X) for (int e = gid; e < X_FEAT + d.nfeat; e += gsz) d.Xc[e] = d.X[e];      // constant blocks of the candidate never change again
     if (gid == 0) {
         BaState& s = *d.st;
         s.radius = 1e4; s.mu = 1e-8; s.reuse = 0; s.done = 0; s.it = 0; s.n_success = 0; s.invalid_streak = 0;
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(128) k_ba_setup(BaDev d)
         double* out = d.imu_sqrt + 225 * m;
         if (ok) for (int e = lane; e < n * n; e += 32) { int i = e / n, j = e - i * n; out[e] = (j >= i) ? A[j * w2 + i] : 0.0; }
     }
-    if (!ok && lane == 0) d.st->termination = GF_BA_FAILURE;
+    if (!ok && lane == 0) d.st->setup_failed = 1;      // zeroed by the host before the launch; every later kernel returns at once
 }
 __global__ void k_ba_prior_hessian(BaDev d)
 {
@@ -184,7 +186,7 @@ __global__ void k_ba_prior_hessian(BaDev d)
 __device__ void ba_decide(const BaDev& d)
 {
     BaState& st = *d.st;
-    if (st.done) return;
+    if (st.done || st.setup_failed) return;
     const int tid = threadIdx.x, nt = blockDim.x;
     __shared__ int accept;
     __syncthreads();
@@ -229,7 +231,7 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
     __shared__ double sred[32];
     __shared__ double simu_J[15 * 30], simu_JU[15 * 30], simu_r[15], simu_ru[15];
     const BaState& st = *d.st;
-    if (st.done) return;
+    if (st.done || st.setup_failed) return;
 #ifdef GF_PROFILE
     const long long t_eval0 = clock64();
 #define PHMAX(k) do { if (tid == 0) atomicMax((unsigned long long*)&d.st->prof[k], (unsigned long long)(clock64() - t_eval0)); } while (0)
@@ -465,6 +467,94 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
 }
 
 // ------------------------------------------------------------------------------------------------
+// ambient-space helpers over the non-constant blocks
+// Y = X (+) delta on the FREE blocks only (constant blocks of Y already equal X: k_ba_setup copies X once and nothing else
+// ever writes them) and, in the same pass, this thread's share of |X - Y|^2 and max |X - Y| over the ambient coordinates.
+__device__ inline void plus_free(const BaDev& d, const double* X, const double* delta, double* Y, int tid, int nt, double& s2, double& mx)
+{
+    s2 = 0; mx = 0;
+    auto acc = [&](int off, int size) { for (int k = 0; k < size; k++) { const double v = X[off + k] - Y[off + k]; s2 += v * v; mx = fmax(mx, fabs(v)); } };
+    for (int f = tid; f < d.F; f += nt) {
+        if (d.col_pose[f] >= 0) { pose_plus(X + X_POSE + 7 * f, delta + d.col_pose[f], Y + X_POSE + 7 * f); acc(X_POSE + 7 * f, 7); }
+        if (d.col_sb[f] >= 0) { for (int k = 0; k < 9; k++) Y[X_SB + 9 * f + k] = X[X_SB + 9 * f + k] + delta[d.col_sb[f] + k]; acc(X_SB + 9 * f, 9); }
+    }
+    if (tid == nt - 1) {
+        if (d.col_ex >= 0) { pose_plus(X + X_EX, delta + d.col_ex, Y + X_EX); acc(X_EX, 7); }
+        if (d.col_td >= 0) { Y[X_TD] = X[X_TD] + delta[d.col_td]; acc(X_TD, 1); }
+    }
+    if (tid == nt - 2) {
+        if (d.col_exw >= 0) {    // PoseSubsetParameterization: masked components are zeroed inside Plus only
+            double dd[6];
+            for (int k = 0; k < 6; k++) dd[k] = ((d.exw_mask >> k) & 1) ? 0.0 : delta[d.col_exw + k];
+            pose_plus(X + X_EXW, dd, Y + X_EXW); acc(X_EXW, 7);
+        }
+        for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) { Y[X_IX + k] = X[X_IX + k] + delta[d.col_ix[k]]; acc(X_IX + k, 1); }
+        if (d.col_tdw >= 0) { Y[X_TDW] = X[X_TDW] + delta[d.col_tdw]; acc(X_TDW, 1); }
+    }
+    if (tid == nt - 3 && d.col_pr >= 0) {     // OrientationSubsetParameterization::Plus
+        double dd[3], dq[4], qn[4];
+        for (int k = 0; k < 3; k++) dd[k] = ((d.pr_mask >> k) & 1) ? 0.0 : delta[d.col_pr + k];
+        delta_q(dd, dq); q_mul(X + X_PR, dq, qn); q_normalize(qn);
+        for (int k = 0; k < 4; k++) Y[X_PR + k] = qn[k];
+        Y[X_PZ] = X[X_PZ] + delta[d.col_pz];
+        acc(X_PR, 4); acc(X_PZ, 1);
+    }
+    for (int k = tid; k < d.nfeat; k += nt) { const int c = d.col_feat[k]; if (c >= 0) { Y[X_FEAT + k] = X[X_FEAT + k] + delta[c]; acc(X_FEAT + k, 1); } }
+}
+// sum of squares of A over the ambient coordinates of the free blocks
+__device__ inline double free_norm2(const BaDev& d, const double* A, int tid, int nt)
+{
+    double s2 = 0;
+    auto acc = [&](int off, int size) { for (int k = 0; k < size; k++) s2 += A[off + k] * A[off + k]; };
+    for (int f = tid; f < d.F; f += nt) { if (d.col_pose[f] >= 0) acc(X_POSE + 7 * f, 7); if (d.col_sb[f] >= 0) acc(X_SB + 9 * f, 9); }
+    if (tid == nt - 1) {
+        if (d.col_ex >= 0) acc(X_EX, 7);
+        if (d.col_td >= 0) acc(X_TD, 1);
+        if (d.col_exw >= 0) acc(X_EXW, 7);
+        for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) acc(X_IX + k, 1);
+        if (d.col_tdw >= 0) acc(X_TDW, 1);
+        if (d.col_pr >= 0) { acc(X_PR, 4); acc(X_PZ, 1); }
+    }
+    for (int k = tid; k < d.nfeat; k += nt) if (d.col_feat[k] >= 0) acc(X_FEAT + k, 1);
+    return s2;
+}
+__device__ __forceinline__ double block_reduce_max(double v, double* sh)
+{
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double t = 0;
+    if (w == 0) {
+        t = (l < nw) ? sh[l] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (l == 0) sh[0] = t;
+    }
+    __syncthreads();
+    t = sh[0];
+    __syncthreads();
+    return t;
+}
+// N sums at once over a CTA of <= 8 warps: two barriers in total; every thread ends up with all N totals.  sh: N * 8 doubles.
+template <int N>
+__device__ __forceinline__ void block_reduce_sums(double (&v)[N], double* sh)
+{
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < N; k++)
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    __syncthreads();
+    if (l == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k++) sh[k * 8 + w] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; k++) { double t = 0; for (int q = 0; q < nw; q++) t += sh[k * 8 + q]; v[k] = t; }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Reduced camera system for the Gauss-Newton solve, (H' + mu D^2) with the free landmarks eliminated (Ceres' SchurEliminator):
 //   S[a][b] = H'[a][b] + [a==b] mu D_a^2 - s_a s_b sum_l c_l W[l][a] W[l][b],   c_l = s_l^2 / (h'_ll + mu D_l^2)
 //   rhs[b]  = g'[b] - s_b sum_l c_l W[l][b] g_l                (primes = Jacobi-scaled; stored as row nc of the system)
@@ -519,7 +609,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
 {
     extern __shared__ double ssm[];                // cl[L] | ss[nc+1] | sv[nc]
     const BaState& st = *d.st;
-    if (st.done) return;
+    if (st.done || st.setup_failed) return;
     const bool fresh = st.need_linearize != 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     {   // clear the accumulator that is free during this iteration: k_ba_eval(1) linearises the candidate into it
@@ -553,7 +643,7 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
         ss[c] = sc_; sv[c] = g[c] * sc_ * sc_ / hd;        // v = gs / D (times the Jacobi scale, because H is unscaled)
     }
     __syncthreads();
-    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2;
+    const int n8 = (nc + 8) >> 3, ntiles = st.it >= st.max_iter ? 0 : n8 * (n8 + 1) / 2;   // the closing launch only needs the norms
     double num = 0, den = 0;
     const int gw = blockIdx.x * SCHUR_WARPS + warp, nw = gridDim.x * SCHUR_WARPS;
     for (int t = gw; t < ntiles; t += nw) {
@@ -576,6 +666,33 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
         }
     }
     __shared__ double sred2[2 * SCHUR_WARPS];
+    if (blockIdx.x == gridDim.x - 1) {
+        // ---- this CTA also prepares what k_ba_step needs before it can factor: D, gs = g'/D, e_l = 1 / (h'_ll + mu D_l^2), the
+        // Jacobi scale (iteration 0) and, for a fresh linearisation, |x| and the gradient max-norm |x - Plus(x, -g)|_inf
+        // (TrustRegionMinimizer's gradient tolerance test) -- off the single-CTA critical path ----
+        const int n = d.n, nt = blockDim.x;
+        for (int c = tid; c < n; c += nt) {
+            const double sc_ = c < nc ? ss[c] : scale_of(c);
+            double hd = (c < nc ? H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c] : hll[c - nc]) * sc_ * sc_;
+            const double hraw = hd;
+            hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);
+            const double D = sqrt(hd);
+            if (first) d.scale[c] = sc_;
+            d.diag[c] = D;
+            d.gs[c] = g[c] * sc_ / D;
+            if (c >= nc) d.gn[c] = 1.0 / (hraw + mu * hd);
+            if (fresh) d.delta[c] = -g[c];
+        }
+        if (fresh) {
+            __syncthreads();
+            double s2, mx;
+            plus_free(d, d.X, d.delta, d.Xc, tid, nt, s2, mx);       // Xc is free scratch here: the accepted candidate has become X
+            mx = block_reduce_max(mx, sred2);
+            double xs2 = free_norm2(d, d.X, tid, nt);
+            xs2 = block_reduce_sum(xs2, sred2);
+            if (tid == 0) { d.st->grad_max = mx; d.st->x_norm = sqrt(xs2); }
+        }
+    }
     for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
     if (lane == 0) { sred2[warp] = den; sred2[SCHUR_WARPS + warp] = num; }
     __syncthreads();
@@ -587,166 +704,72 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// ambient-space helpers over the non-constant blocks
-__device__ inline void plus_all(const BaDev& d, const double* X, const double* delta, double* Y, int tid, int nt)
-{
-    // copy everything, then overwrite the free blocks
-    const int tot = X_FEAT + d.nfeat;
-    for (int e = tid; e < tot; e += nt) Y[e] = X[e];
-    __syncthreads();
-    for (int f = tid; f < d.F; f += nt) {
-        if (d.col_pose[f] >= 0) pose_plus(X + X_POSE + 7 * f, delta + d.col_pose[f], Y + X_POSE + 7 * f);
-        if (d.col_sb[f] >= 0) for (int k = 0; k < 9; k++) Y[X_SB + 9 * f + k] = X[X_SB + 9 * f + k] + delta[d.col_sb[f] + k];
-    }
-    if (tid == 0) {
-        if (d.col_ex >= 0) pose_plus(X + X_EX, delta + d.col_ex, Y + X_EX);
-        if (d.col_td >= 0) Y[X_TD] = X[X_TD] + delta[d.col_td];
-        if (d.col_exw >= 0) {    // PoseSubsetParameterization: masked components are zeroed inside Plus only
-            double dd[6];
-            for (int k = 0; k < 6; k++) dd[k] = ((d.exw_mask >> k) & 1) ? 0.0 : delta[d.col_exw + k];
-            pose_plus(X + X_EXW, dd, Y + X_EXW);
-        }
-        for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) Y[X_IX + k] = X[X_IX + k] + delta[d.col_ix[k]];
-        if (d.col_tdw >= 0) Y[X_TDW] = X[X_TDW] + delta[d.col_tdw];
-        if (d.col_pr >= 0) {     // OrientationSubsetParameterization::Plus
-            double dd[3], dq[4], qn[4];
-            for (int k = 0; k < 3; k++) dd[k] = ((d.pr_mask >> k) & 1) ? 0.0 : delta[d.col_pr + k];
-            delta_q(dd, dq); q_mul(X + X_PR, dq, qn); q_normalize(qn);
-            for (int k = 0; k < 4; k++) Y[X_PR + k] = qn[k];
-            Y[X_PZ] = X[X_PZ] + delta[d.col_pz];
-        }
-    }
-    for (int k = tid; k < d.nfeat; k += nt) { int c = d.col_feat[k]; if (c >= 0) Y[X_FEAT + k] = X[X_FEAT + k] + delta[c]; }
-    __syncthreads();
-}
-// sum of squares / max abs of (A - B) over the ambient coordinates of the free blocks (B may be null)
-__device__ inline void diff_norms(const BaDev& d, const double* A, const double* B, double& s2, double& mx, int tid, int nt)
-{
-    s2 = 0; mx = 0;
-    auto acc = [&](int off, int size) { for (int k = 0; k < size; k++) { double v = A[off + k] - (B ? B[off + k] : 0.0); s2 += v * v; mx = fmax(mx, fabs(v)); } };
-    for (int f = tid; f < d.F; f += nt) { if (d.col_pose[f] >= 0) acc(X_POSE + 7 * f, 7); if (d.col_sb[f] >= 0) acc(X_SB + 9 * f, 9); }
-    if (tid == 0) {
-        if (d.col_ex >= 0) acc(X_EX, 7); if (d.col_td >= 0) acc(X_TD, 1);
-        if (d.col_exw >= 0) acc(X_EXW, 7);
-        for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) acc(X_IX + k, 1);
-        if (d.col_tdw >= 0) acc(X_TDW, 1);
-        if (d.col_pr >= 0) { acc(X_PR, 4); acc(X_PZ, 1); }
-    }
-    for (int k = tid; k < d.nfeat; k += nt) if (d.col_feat[k] >= 0) acc(X_FEAT + k, 1);
-}
-__device__ __forceinline__ double block_reduce_max(double v, double* sh)
-{
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if (l == 0) sh[w] = v;
-    __syncthreads();
-    double t = 0;
-    if (w == 0) {
-        t = (l < nw) ? sh[l] : 0.0;
-        for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
-        if (l == 0) sh[0] = t;
-    }
-    __syncthreads();
-    t = sh[0];
-    __syncthreads();
-    return t;
-}
-
-// DoglegStrategy::ComputeStep + TrustRegionMinimizer::ComputeTrustRegionStep + candidate point.
-// Dynamic shared memory: factor tiles (<= TILE_CAP) | inverses of the diagonal tiles | scratch tile | last diagonal tile | y.
-template <int R>
+// DoglegStrategy::ComputeStep + TrustRegionMinimizer::ComputeTrustRegionStep + candidate point, one CTA.
+// Dynamic shared memory: factor tiles (<= tile_cap; first filled with the reduced system by a TMA bulk copy) | inverses of the
+// diagonal tiles | 2 scratch tiles | last diagonal tile | y.  After the back substitution the tile area is dead and holds delta.
+template <int R, bool SPILL>
 __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
 {
-    extern __shared__ double S[];
-    __shared__ double sred[32];
-    __shared__ int s_fail;
+    extern __shared__ __align__(128) double S[];
+    __shared__ double sred[64];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ int s_fail, s_go;
     BaState& st = *d.st;
-    if (st.done) return;
-    const int tid = threadIdx.x, nt = blockDim.x;
+    if (st.done || st.setup_failed) return;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
     const int nc = d.nc, L = d.L, n = d.n;
-    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2;
-    TileStore T; T.Ls = S; T.Lg = d.Lg; T.cap = d.tile_cap;
-    double* Linv = S + (size_t)64 * min(ntiles, d.tile_cap);
-    double* S8 = Linv + 64 * n8; double* Ld = S8 + 64; double* yc = Ld + 64;
+    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2, ntl = min(ntiles, d.tile_cap);
+    TileStoreT<SPILL> T; T.sb = ch_tiles_u32(); T.Lg = d.Lg; T.cap = d.tile_cap;
+    double* Linv = S + (size_t)64 * ntl;
+    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64;
+    const long long t_kernel0 = clock64();      // always on (two clock reads per launch): SM cycles of the launches that took a step
 #ifdef GF_PROFILE
     long long t_last = clock64();
 #define PH(k) do { if (tid == 0) { long long t_ = clock64(); st.prof[k] += t_ - t_last; t_last = t_; } } while (0)
 #else
 #define PH(k) do { } while (0)
 #endif
-    if (st.need_linearize) {                      // a fresh linearisation landed in the inactive buffer: adopt it
-        __syncthreads();
-        if (tid == 0) { st.cur ^= 1; st.need_linearize = 0; st.x_cost = st.acc_cost[st.cur]; }
-        __syncthreads();
-        const int cur = st.cur;
-        double* H = acc_H(d, cur); const double* Hp = d.Hp;
-        // total Hessian diagonal includes the prior
-        if (st.first) {                           // Jacobi scaling, fixed at iteration 0
-            for (int c = tid; c < nc; c += nt) d.scale[c] = 1.0 / (1.0 + sqrt(H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c]));
-            for (int l = tid; l < L; l += nt) d.scale[nc + l] = 1.0 / (1.0 + sqrt(acc_hll(d, cur)[l]));
-        }
-        __syncthreads();
-        // gradient_max_norm = |x - Plus(x, -g)|_inf with the unscaled gradient
-        for (int c = tid; c < n; c += nt) d.delta[c] = -acc_g(d, cur)[c];
-        __syncthreads();
-        plus_all(d, d.X, d.delta, d.Xc, tid, nt);
-        double s2, mx; diff_norms(d, d.X, d.Xc, s2, mx, tid, nt);
-        mx = block_reduce_max(mx, sred);
-        double xs2, xmx; diff_norms(d, d.X, nullptr, xs2, xmx, tid, nt);
-        xs2 = block_reduce_sum(xs2, sred);
-        if (tid == 0) {
-            st.grad_max = mx; st.x_norm = sqrt(xs2);
+    if (tid == 0) {
+        // ---- adoption of a fresh linearisation (its vectors and norms were prepared by k_ba_schur) + iteration bookkeeping ----
+        int go = 1;
+        if (st.need_linearize) {
+            st.cur ^= 1; st.need_linearize = 0; st.x_cost = st.acc_cost[st.cur];
             if (st.first) { st.cost_hist[0] = st.x_cost; st.radius_hist[0] = st.radius; st.first = 0; }
-            else { st.cost_hist[st.it] = st.x_cost; }      // cost after the accepted step of iteration `it`
-            if (mx <= 1e-10 || n == 0) { st.done = 1; st.termination = GF_BA_CONVERGENCE_GRADIENT; }
+            else st.cost_hist[st.it] = st.x_cost;          // cost after the accepted step of iteration `it`
+            if (st.grad_max <= 1e-10 || n == 0) { st.done = 1; st.termination = GF_BA_CONVERGENCE_GRADIENT; go = 0; }
             st.reuse = 0;
         }
-        __syncthreads();
-        if (st.done) return;
+        if (go && (st.it >= st.max_iter || st.radius < 1e-32)) { st.done = 1; st.termination = GF_BA_NO_CONVERGENCE; go = 0; }
+        if (go) {
+            st.it++; st.step_valid = 0; st.solver_failed = 0;
+            ch_mbar_init(&mbar, 1);
+            if (!st.reuse) chol_issue_load(d.Sg, S, ntl, &mbar);      // the copy engine streams the reduced system in while the CTA gets going
+        }
+        s_go = go; s_fail = 0;
     }
-    PH(0);   // adoption, scaling, gradient norms
-    // ---- TrustRegionMinimizer: iteration bookkeeping ----
-    if (st.it >= st.max_iter || st.radius < 1e-32) { if (tid == 0) { st.done = 1; st.termination = GF_BA_NO_CONVERGENCE; } return; }
     __syncthreads();
-    if (tid == 0) { st.it++; st.step_valid = 0; st.solver_failed = 0; }
-    __syncthreads();
+    if (!s_go) return;
+    PH(0);   // adoption + bookkeeping
     const int cur = st.cur;
-    const double* H = acc_H(d, cur); const double* Hp = d.Hp; const double* g = acc_g(d, cur);
-    const double* W = acc_W(d, cur); const double* hll = acc_hll(d, cur);
+    const double* g = acc_g(d, cur); const double* W = acc_W(d, cur); const double* hll = acc_hll(d, cur);
+    const double* H = acc_H(d, cur);
     const double* sc = d.scale;
     if (!st.reuse) {
-        // diag = sqrt(clamp(diag(H'), 1e-6, 1e32)); gs = g'/D ; Cauchy alpha = |gs|^2 / (v^T H' v), v = gs / D
-        for (int c = tid; c < n; c += nt) {
-            double hd = (c < nc) ? (H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c]) : hll[c - nc];
-            hd *= sc[c] * sc[c];
-            hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);
-            double D = sqrt(hd);
-            d.diag[c] = D;
-            d.gs[c] = g[c] * sc[c] / D;
-        }
-        __syncthreads();
         if (tid == 0) { st.alpha = st.cauchy_num / st.cauchy_den; st.cauchy_num = 0.0; st.cauchy_den = 0.0; }   // accumulated by k_ba_schur
-        PH(1);   // diag, Cauchy point
         // ---- ComputeGaussNewtonStep: (H' + mu D^2) y = g' by Schur complement on the landmarks + Cholesky ----
-        const int warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
+        unsigned ld_phase = 0;
         bool first_try = true;
         while (true) {
             const double mu = st.mu;
-            __syncthreads();
-            if (tid == 0) s_fail = 0;
-            __syncthreads();
-            // e_l = 1 / (h'll + mu D_l^2)   (kept in gn[nc + l] for now)
-            for (int l = tid; l < L; l += nt) {
-                double v = hll[l] * sc[nc + l] * sc[nc + l] + mu * d.diag[nc + l] * d.diag[nc + l];
-                if (!(v > 0)) s_fail = 1;
-                d.gn[nc + l] = 1.0 / v;
-            }
-            __syncthreads();
             if (!first_try) {
-                // retry with a larger mu (rare): the reduced system is assembled here, by this CTA alone, with the same tile routine
-                for (int l = tid; l < L; l += nt) d.step[nc + l] = d.gn[nc + l] * sc[nc + l] * sc[nc + l];     // c_l (scratch)
+                // retry with a larger mu (rare): e_l and the reduced system are rebuilt here, by this CTA alone
+                __syncthreads();
+                if (tid == 0) s_fail = 0;
+                for (int l = tid; l < L; l += nt) {
+                    const double v = hll[l] * sc[nc + l] * sc[nc + l] + mu * d.diag[nc + l] * d.diag[nc + l];
+                    d.gn[nc + l] = 1.0 / v;
+                    d.step[nc + l] = sc[nc + l] * sc[nc + l] / v;                               // c_l (scratch)
+                }
                 __syncthreads();
                 double dummy0 = 0, dummy1 = 0;
                 for (int t = warp; t < ntiles; t += nwarp) {
@@ -755,30 +778,46 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
                     while (tix(I, 0) > t) I--;
                     schur_tile(d, H, g, W, sc, nullptr, d.step + nc, mu, I, t - tix(I, 0), lane, dummy0, dummy1);
                 }
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");                                // generic writes (dead factor, new Sg) before the async-proxy refill
+                __syncthreads();
+                if (tid == 0) chol_issue_load(d.Sg, S, ntl, &mbar);
             }
             first_try = false;
-            __syncthreads();
-            PH(2);   // (re)assembly of the reduced system
-            const bool ok_f = chol_factor<R>(d.Sg, T, Linv, S8, Ld, nc, n8, &s_fail);
-            if (ok_f && tid < 32) chol_backsubst(T, Linv, Ld, yc, nc, tid);
-            __syncthreads();
+            if (ntl > 0) ch_mbar_wait(&mbar, ld_phase & 1);
+            ld_phase++;
+            PH(2);   // reduced system in shared memory
+            const bool ok_f = chol_factor<R, SPILL>(d.Sg, T, Linv, S8, Ld, nc, n8, &s_fail);
             PH(3);   // Cholesky
-            if (!s_fail) {
+            bool ok = ok_f;
+            if (ok) {
+                chol_backsubst(T, Linv, Ld, yc, nc);
                 __syncthreads();
-                for (int c = tid; c < nc; c += nt) if (!isfinite(yc[c])) s_fail = 1;
-                __syncthreads();
-                PH(4);   // back substitution
+                int bad = 0;
+                for (int c = tid; c < nc; c += nt) if (!isfinite(yc[c])) bad = 1;
+                ok = __syncthreads_or(bad) == 0;
             }
-            if (!s_fail) {
-                // y_l = e_l (g'_l - w'_l . y_c) ; gn = -D y
-                for (int l = warp; l < L; l += nwarp) {
-                    double t = 0;
-                    for (int b = lane; b < nc; b += 32) t += W[(size_t)l * nc + b] * sc[b] * yc[b];
-                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                    if (lane == 0) d.step[nc + l] = d.gn[nc + l] * (g[nc + l] * sc[nc + l] - t * sc[nc + l]);   // temp
-                }
+            PH(4);   // back substitution
+            if (ok) {
+                // y_l = e_l (g'_l - w'_l . y_c) ; gn = -D y.  v = s .* y_c staged once; four landmarks per warp pass keep 4 x nc/32 loads in flight
+                double* vbuf = nc <= 64 * ntl ? S : d.step;                                      // the factor is dead: the tile area holds v
+                for (int c = tid; c < nc; c += nt) vbuf[c] = sc[c] * yc[c];
                 __syncthreads();
-                for (int c = tid; c < n; c += nt) { double y = (c < nc) ? yc[c] : d.step[c]; d.gn[c] = -d.diag[c] * y; }
+                for (int l0 = 4 * warp; l0 < L; l0 += 4 * nwarp) {
+                    double t[4] = {0, 0, 0, 0};
+                    for (int b = lane; b < nc; b += 32) {
+                        const double vb = vbuf[b];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) if (l0 + q < L) t[q] = fma(W[(size_t)(l0 + q) * nc + b], vb, t[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        for (int o = 16; o > 0; o >>= 1) t[q] += __shfl_xor_sync(0xffffffffu, t[q], o);
+                        const int l = l0 + q;
+                        if (lane == 0 && l < L) d.gn[nc + l] = -d.diag[nc + l] * (d.gn[nc + l] * (g[nc + l] * sc[nc + l] - t[q] * sc[nc + l]));
+                    }
+                }
+                for (int c = tid; c < nc; c += nt) d.gn[c] = -d.diag[c] * yc[c];
                 __syncthreads();
                 PH(5);   // landmark back substitution
                 break;
@@ -793,10 +832,16 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
         __syncthreads();
     }
     if (!st.solver_failed) {
-        // ---- ComputeTraditionalDoglegStep ----
-        double g2 = 0, n2 = 0, ga = 0;
-        for (int c = tid; c < n; c += nt) { g2 += d.gs[c] * d.gs[c]; n2 += d.gn[c] * d.gn[c]; ga += d.gs[c] * d.gn[c]; }
-        g2 = block_reduce_sum(g2, sred); n2 = block_reduce_sum(n2, sred); ga = block_reduce_sum(ga, sred);
+        // ---- ComputeTraditionalDoglegStep: one pass over the vectors, one 7-way reduction ----
+        //   u = gs / D, y = -gn / D (the Gauss-Newton solution of (H' + mu D^2) y = g'), g' = scaled gradient
+        double r7[7] = {0, 0, 0, 0, 0, 0, 0};      // |gs|^2, |gn|^2, gs.gn, y.g', y.D^2.y, u.g', u.D^2.y
+        for (int c = tid; c < n; c += nt) {
+            const double gs_ = d.gs[c], gn_ = d.gn[c], D = d.diag[c], gp = g[c] * sc[c], u = gs_ / D, y = -gn_ / D;
+            r7[0] += gs_ * gs_; r7[1] += gn_ * gn_; r7[2] += gs_ * gn_;
+            r7[3] += y * gp; r7[4] += y * D * D * y; r7[5] += u * gp; r7[6] += u * D * D * y;
+        }
+        block_reduce_sums<7>(r7, sred);
+        const double g2 = r7[0], n2 = r7[1], ga = r7[2], ygp = r7[3], yDy = r7[4], ugp = r7[5], uDy = r7[6];
         const double gnorm = sqrt(g2), gnn = sqrt(n2), radius = st.radius, alpha = st.alpha;
         double ca, cb, dn;                      // step = ca * gs + cb * gn  (D-space)
         if (gnn <= radius) { ca = 0; cb = 1; dn = gnn; }
@@ -810,33 +855,22 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
             double beta = (cc <= 0) ? (dd - cc) / bma2 : (radius * radius - a2) / (dd + cc);
             ca = -alpha * (1.0 - beta); cb = beta; dn = -1.0;
         }
-        double nn = 0;
-        for (int c = tid; c < n; c += nt) { double s = ca * d.gs[c] + cb * d.gn[c]; nn += s * s; d.step[c] = s / d.diag[c]; }
-        nn = block_reduce_sum(nn, sred);
-        if (dn < 0) dn = sqrt(nn);
-        // model_cost_change = -(s^T g' + s^T H' s / 2) with s = (ca gs + cb gn) / D.  No mat-vec is needed:
-        //   u = gs / D, w = gn / D = -y;  u^T H' u = |gs|^2 / alpha (Cauchy),  H' y = g' - mu D^2 y  =>
-        //   w^T H' w = y^T g' - mu y^T D^2 y,   u^T H' w = -(u^T g' - mu u^T D^2 y)
-        double sg = 0, sHs = 0;
-        {
-            double ygp = 0, yDy = 0, ugp = 0, uDy = 0;
-            for (int c = tid; c < n; c += nt) {
-                double gp = g[c] * sc[c], D = d.diag[c], u = d.gs[c] / D, y = -d.gn[c] / D;
-                sg += d.step[c] * gp;
-                ygp += y * gp; yDy += y * D * D * y; ugp += u * gp; uDy += u * D * D * y;
-            }
-            ygp = block_reduce_sum(ygp, sred); yDy = block_reduce_sum(yDy, sred); ugp = block_reduce_sum(ugp, sred); uDy = block_reduce_sum(uDy, sred);
-            const double mu_used = st.mu;
-            const double uHu = g2 / alpha, wHw = ygp - mu_used * yDy, uHw = -(ugp - mu_used * uDy);
-            sHs = (tid == 0) ? (ca * ca * uHu + 2.0 * ca * cb * uHw + cb * cb * wHw) : 0.0;
-            for (int c = tid; c < n; c += nt) d.delta[c] = d.step[c] * sc[c];
-        }
-        sg = block_reduce_sum(sg, sred); sHs = block_reduce_sum(sHs, sred);
-        PH(6);   // dogleg + model cost change
+        if (dn < 0) dn = sqrt(fmax(ca * ca * g2 + 2.0 * ca * cb * ga + cb * cb * n2, 0.0));      // |ca gs + cb gn|
+        // model_cost_change = -(s^T g' + s^T H' s / 2) with s = (ca gs + cb gn) / D = ca u - cb y.  No mat-vec is needed:
+        //   u^T H' u = |gs|^2 / alpha (Cauchy),  H' y = g' - mu D^2 y  =>  y^T H' y = y^T g' - mu y^T D^2 y,  u^T H' y = u^T g' - mu u^T D^2 y
+        const double mu_used = st.mu;
+        const double uHu = g2 / alpha, wHw = ygp - mu_used * yDy, uHw = -(ugp - mu_used * uDy);
+        const double sg = ca * ugp - cb * ygp;
+        const double sHs = ca * ca * uHu + 2.0 * ca * cb * uHw + cb * cb * wHw;
         const double model_change = -(sg + 0.5 * sHs);
+        PH(6);   // dogleg + model cost change
+        // ---- candidate point x (+) delta, delta = s .* scale ----
+        double* dl = (n <= 64 * ntl) ? S : d.delta;               // the factor is dead: delta lives in the tile area when it fits
         __syncthreads();
-        plus_all(d, d.X, d.delta, d.Xc, tid, nt);
-        double s2, mx; diff_norms(d, d.X, d.Xc, s2, mx, tid, nt);
+        for (int c = tid; c < n; c += nt) dl[c] = (ca * d.gs[c] + cb * d.gn[c]) / d.diag[c] * sc[c];
+        __syncthreads();
+        double s2, mx;
+        plus_free(d, d.X, dl, d.Xc, tid, nt, s2, mx);
         s2 = block_reduce_sum(s2, sred);
         if (tid == 0) {
             st.dogleg_norm = dn; st.model_change = model_change; st.step_norm = sqrt(s2);
@@ -845,6 +879,7 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
         }
         PH(7);   // candidate point
     }
+    if (tid == 0) { st.prof[30] += clock64() - t_kernel0; st.prof[31] += 1; }
 }
 
 // TrustRegionMinimizer: HandleInvalidStep / tolerances / IsStepSuccessful / HandleSuccessfulStep / HandleUnsuccessfulStep
@@ -1307,8 +1342,8 @@ int gf_ba_create(gf_ba** out, int device)
     GF_CUDA(cudaEventCreate(&s->e0)); GF_CUDA(cudaEventCreate(&s->e1));
     s->tile_cap = TILE_CAP;
     if (const char* e_ = getenv("GF_BA_TILE_CAP")) { const int v = atoi(e_); if (v >= 0 && v < TILE_CAP) s->tile_cap = v; }
-    GF_CUDA(cudaFuncSetAttribute(k_ba_step<MAXR / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    GF_CUDA(cudaFuncSetAttribute(k_ba_step<MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GF_CUDA(cudaFuncSetAttribute(k_ba_step<MAXR / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    GF_CUDA(cudaFuncSetAttribute(k_ba_step<MAXR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     GF_CUDA(cudaFuncSetAttribute(k_jacobi_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     GF_CUDA(cudaFuncSetAttribute(k_sym_eig_ql, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     *out = s;
@@ -1331,6 +1366,10 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
 {
     if (!s || !p || !sum) return set_err(GF_ERR_INVALID_ARG, "null argument");
     if (p->n_frames < 1 || p->n_frames > GF_BA_MAX_FRAMES) return set_err(GF_ERR_INVALID_ARG, "n_frames out of range");
+    if (p->n_visual < 0 || p->n_imu < 0 || p->n_features < 0) return set_err(GF_ERR_INVALID_ARG, "negative factor / feature count");
+    if (!p->para_pose || !p->para_ex_pose || !p->para_td) return set_err(GF_ERR_INVALID_ARG, "null parameter block");
+    if ((p->n_features > 0 && (!p->para_feature || !p->feature_const)) || (p->n_visual > 0 && !p->visual) || (p->n_imu > 0 && (!p->imu || !p->para_speed_bias)))
+        return set_err(GF_ERR_INVALID_ARG, "factor table or parameter block missing");
     if (p->n_wheel < 0 || (p->n_wheel > 0 && (!p->wheel || !p->para_ex_wheel || !p->para_ix_wheel || !p->para_td_wheel))) return set_err(GF_ERR_INVALID_ARG, "wheel factors without their parameter blocks");
     if (p->n_plane < 0 || p->n_plane > PAIR_THREADS || (p->n_plane > 0 && (!p->plane_frames || !p->para_ex_wheel || !p->para_plane_R || !p->para_plane_Z))) return set_err(GF_ERR_INVALID_ARG, "plane factors without their parameter blocks");
     if (p->max_num_iterations < 0 || p->max_num_iterations > GF_BA_MAX_ITERATIONS) return set_err(GF_ERR_INVALID_ARG, "max_num_iterations out of range");
@@ -1483,15 +1522,15 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
     const int eval_blocks = n_work + p->n_imu + p->n_wheel + (p->n_plane > 0 ? 1 : 0) + (pn ? 1 : 0);
     const size_t prior_smem = sizeof(double) * 2 * (size_t)pn;
-    const size_t step_smem = sizeof(double) * (64 * (size_t)std::min(ntiles, s->tile_cap) + 64 * (size_t)n8 + 128 + (size_t)((nc + 8) & ~7));
+    const size_t step_smem = sizeof(double) * (64 * (size_t)std::min(ntiles, s->tile_cap) + 64 * (size_t)n8 + 192 + (size_t)((nc + 8) & ~7));
     const size_t schur_smem = sizeof(double) * (size_t)(L + 2 * nc + 2);
     const int schur_grid = (ntiles + SCHUR_WARPS - 1) / SCHUR_WARPS;
     const int iters = p->max_num_iterations;
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 0); GF_LAUNCHED(); }
     for (int it = 0; it <= iters; it++) {
-        if (it < iters) { k_ba_schur<<<schur_grid, SCHUR_WARPS * 32, schur_smem, st>>>(d); GF_LAUNCHED(); }
-        if (n8 <= (MAXR / 2) * ST_WARPS) k_ba_step<MAXR / 2><<<1, RB_THREADS, step_smem, st>>>(d);
-        else k_ba_step<MAXR><<<1, RB_THREADS, step_smem, st>>>(d);
+        k_ba_schur<<<schur_grid, SCHUR_WARPS * 32, schur_smem, st>>>(d); GF_LAUNCHED();      // (the closing launch only prepares the norms)
+        if (ntiles <= s->tile_cap && n8 <= (MAXR / 2) * CH_BULK) k_ba_step<MAXR / 2, false><<<1, RB_THREADS, step_smem, st>>>(d);
+        else k_ba_step<MAXR, true><<<1, RB_THREADS, step_smem, st>>>(d);
         GF_LAUNCHED();
         if (it == iters) break;                  // the extra k_ba_step adopts the last linearisation and closes the run
         k_ba_eval<<<eval_blocks > 0 ? eval_blocks : 1, PAIR_THREADS, prior_smem, st>>>(d, 1); GF_LAUNCHED();   // + decision (last CTA)
@@ -1504,6 +1543,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     float ms = 0;
     GF_CUDA(cudaEventElapsedTime(&ms, s->e0, s->e1));
     const BaState* hs = (const BaState*)(hb + o_st);
+    if (hs->setup_failed) return set_err(GF_ERR_INVALID_ARG, "an IMU covariance is singular or not positive definite; parameter blocks left untouched");
     memcpy(p->para_pose, hX + X_POSE, sizeof(double) * 7 * F);
     if (p->para_speed_bias) memcpy(p->para_speed_bias, hX + X_SB, sizeof(double) * 9 * F);
     memcpy(p->para_ex_pose, hX + X_EX, sizeof(double) * 7);
@@ -1713,7 +1753,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     GF_CUDA(cudaMemcpyAsync(hb + o_st, db + o_st, sizeof(BaState), cudaMemcpyDeviceToHost, st));
     GF_CUDA(cudaEventRecord(s->e1, st));
     GF_CUDA(cudaStreamSynchronize(st));
-    if (((BaState*)(hb + o_st))->termination == GF_BA_FAILURE) return set_err(GF_ERR_INVALID_ARG, "IMU covariance is not positive definite");
+    if (((BaState*)(hb + o_st))->setup_failed) return set_err(GF_ERR_INVALID_ARG, "IMU covariance is not positive definite");
     if (device_ms) GF_CUDA(cudaEventElapsedTime(device_ms, s->e0, s->e1));
     memcpy(out_J, hb + o_J0, sizeof(double) * nn);
     memcpy(out_r, hb + o_r0, sizeof(double) * n);
@@ -1794,20 +1834,22 @@ int gf_ba_debug_profile(gf_ba* s, long long* out32)
 // ------------------------------------------------------------------------------------------------
 // Stage-level entry point (tests): the solver's tiled Cholesky + back substitution on an arbitrary SPD system.
 namespace gfba {
-template <int R>
+template <int R, bool SPILL>
 __global__ void __launch_bounds__(ST_THREADS) k_stage_chol(const double* Ag, double* Lg, int cap, int nc, double* y, int* fail)
 {
-    extern __shared__ double S[];
+    extern __shared__ __align__(128) double S[];
+    __shared__ __align__(8) unsigned long long mbar;
     __shared__ int s_fail;
     const int tid = threadIdx.x;
-    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2;
-    TileStore T; T.Ls = S; T.Lg = Lg; T.cap = cap;
-    double* Linv = S + (size_t)64 * min(ntiles, cap);
-    double* S8 = Linv + 64 * n8; double* Ld = S8 + 64; double* yc = Ld + 64;
-    if (tid == 0) s_fail = 0;
+    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2, ntl = min(ntiles, cap);
+    TileStoreT<SPILL> T; T.sb = ch_tiles_u32(); T.Lg = Lg; T.cap = cap;
+    double* Linv = S + (size_t)64 * ntl;
+    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64;
+    if (tid == 0) { s_fail = 0; ch_mbar_init(&mbar, 1); chol_issue_load(Ag, S, ntl, &mbar); }
     __syncthreads();
-    const bool ok = chol_factor<R>(Ag, T, Linv, S8, Ld, nc, n8, &s_fail);
-    if (ok && tid < 32) chol_backsubst(T, Linv, Ld, yc, nc, tid);
+    if (ntl > 0) ch_mbar_wait(&mbar, 0);
+    const bool ok = chol_factor<R, SPILL>(Ag, T, Linv, S8, Ld, nc, n8, &s_fail);
+    if (ok) chol_backsubst(T, Linv, Ld, yc, nc);
     __syncthreads();
     if (ok) for (int c = tid; c < nc; c += blockDim.x) y[c] = yc[c];
     if (tid == 0) *fail = ok ? 0 : 1;
@@ -1843,11 +1885,11 @@ extern "C" int gf_stage_spd_solve(int device, const double* A, const double* b, 
     GF_CUDA(cudaMalloc(&dy, (size_t)n * sizeof(double)));
     GF_CUDA(cudaMalloc(&df, sizeof(int)));
     GF_CUDA(cudaMemcpy(dA, tiles.data(), tiles.size() * sizeof(double), cudaMemcpyHostToDevice));
-    const size_t smem = sizeof(double) * (64 * (size_t)std::min(ntiles, cap) + 64 * (size_t)n8 + 128 + (size_t)((n + 8) & ~7));
-    GF_CUDA(cudaFuncSetAttribute(k_stage_chol<MAXR / 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    GF_CUDA(cudaFuncSetAttribute(k_stage_chol<MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (n8 <= (MAXR / 2) * ST_WARPS) k_stage_chol<MAXR / 2><<<1, ST_THREADS, smem>>>(dA, dL, cap, n, dy, df);
-    else k_stage_chol<MAXR><<<1, ST_THREADS, smem>>>(dA, dL, cap, n, dy, df);
+    const size_t smem = sizeof(double) * (64 * (size_t)std::min(ntiles, cap) + 64 * (size_t)n8 + 192 + (size_t)((n + 8) & ~7));
+    GF_CUDA(cudaFuncSetAttribute(k_stage_chol<MAXR / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    GF_CUDA(cudaFuncSetAttribute(k_stage_chol<MAXR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    if (ntiles <= cap && n8 <= (MAXR / 2) * CH_BULK) k_stage_chol<MAXR / 2, false><<<1, ST_THREADS, smem>>>(dA, dL, cap, n, dy, df);
+    else k_stage_chol<MAXR, true><<<1, ST_THREADS, smem>>>(dA, dL, cap, n, dy, df);
     GF_LAUNCHED();
     int fail = 0;
     cudaError_t e = cudaMemcpy(&fail, df, sizeof(int), cudaMemcpyDeviceToHost);
@@ -1855,5 +1897,71 @@ extern "C" int gf_stage_spd_solve(int device, const double* A, const double* b, 
     cudaFree(dA); cudaFree(dL); cudaFree(dy); cudaFree(df);
     if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "gf_stage_spd_solve: %s", cudaGetErrorString(e)); return GF_ERR_CUDA; }
     if (fail) return set_err(GF_ERR_INVALID_ARG, "matrix is not positive definite");
+    return GF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 rate probe (bench.py quotes the back end's roofline against it): dependent-free DFMA and DMMA.8x8x4 loops on every SM.
+namespace gfba {
+__global__ void __launch_bounds__(256) k_probe_dfma(double* out, int n)
+{
+    double a0 = out[0] + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = out[1], c = out[2];
+    for (int i = 0; i < n; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[8] = a0;
+}
+__global__ void __launch_bounds__(256) k_probe_dmma(double* out, int n)
+{
+    const double a = out[1], b = out[2];
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k][0] = c[k][1] = 0.0;
+    for (int i = 0; i < n; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) dmma884(c[k][0], c[k][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += c[k][0] + c[k][1];
+    if (s == 12345.678) out[8] = s;
+}
+}  // namespace gfba
+
+extern "C" int gf_probe_fp64(int device, double* dfma_gflops, double* dmma_gflops)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return set_err(GF_ERR_NO_DEVICE, "no CUDA device visible; libgf_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_err(GF_ERR_INVALID_ARG, "device index out of range");
+    GF_CUDA(cudaSetDevice(device));
+    cudaDeviceProp pr;
+    GF_CUDA(cudaGetDeviceProperties(&pr, device));
+    double* d = nullptr;
+    GF_CUDA(cudaMalloc(&d, 4096));
+    const double h[4] = {1.0000001, 0.9999999, 1e-9, 0.0};
+    GF_CUDA(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    GF_CUDA(cudaEventCreate(&e0)); GF_CUDA(cudaEventCreate(&e1));
+    const int grid = pr.multiProcessorCount * 4, n = 1 << 15;
+    double res[2] = {0, 0};
+    for (int which = 0; which < 2; which++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            GF_CUDA(cudaEventRecord(e0));
+            if (which == 0) k_probe_dfma<<<grid, 256>>>(d, n); else k_probe_dmma<<<grid, 256>>>(d, n);
+            GF_LAUNCHED();
+            GF_CUDA(cudaEventRecord(e1));
+            GF_CUDA(cudaEventSynchronize(e1));
+            float ms = 0; GF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double fma = which == 0 ? 8.0 * n * 256.0 * grid : 8.0 * n * 256.0 * (256 / 32) * grid;
+        res[which] = 2.0 * fma / (best * 1e-3) / 1e9;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (dfma_gflops) *dfma_gflops = res[0];
+    if (dmma_gflops) *dmma_gflops = res[1];
     return GF_OK;
 }

@@ -171,6 +171,10 @@ int gf_stage_setmask_order(int device, const int32_t* track_cnt, int n, int32_t*
  * path (tests). */
 int gf_stage_spd_solve(int device, const double* A, const double* b, int n, double* x, int tile_cap);
 
+/* Measured FP64 rates of the whole device (GFLOP/s, 2 flops per FMA): plain DFMA and tensor-core DMMA.8x8x4.  bench.py
+ * quotes the back end's roofline fraction against these (MEASURED_PEAKS.json holds no FP64 figure). */
+int gf_probe_fp64(int device, double* dfma_gflops, double* dmma_gflops);
+
 /* ------------------------------------------------------------------------------------------------
  * Back end: Estimator::optimization() (estimator.cpp:2890-3636).  The caller (the Estimator adaptor)
  * fills one gf_ba_problem per call from its members exactly where the reference builds the
@@ -294,7 +298,9 @@ int gf_ba_create(gf_ba** out, int device);
 void gf_ba_destroy(gf_ba* s);
 /* ceres::Solve + double2vector's input: optimises the blocks of `p` in place. */
 int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* summary);
-/* Debug aid: SM cycles spent in each phase of the step kernel during the last solve (16 slots). */
+/* Counters of the last solve (32 slots).  [30] = SM cycles (clock64) spent inside the k_ba_step launches that took a
+ * trust-region step, [31] = their number: bench.py derives the step kernel's achieved FP64 rate from them.  Slots 0..15 are
+ * per-phase cycles and only filled in a -DGF_PROFILE build. */
 int gf_ba_debug_profile(gf_ba* s, long long* out32);
 
 /* MARGIN_OLD: the marginalisation at the end of Estimator::optimization() (estimator.cpp:3334-3535) with

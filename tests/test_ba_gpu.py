@@ -101,7 +101,9 @@ def test_all_optional_blocks_free_179_unknowns(ba):
     solver, whose register-blocked factorisation stopped at 175) against the oracle."""
     pb, _ = make_window(seed=4, with_plane=True, with_wheel=True)
     for it in (1, 8):
-        s = compare(ba, pb, it, mid_rtol=1e-6)
+        # the plane rotation's subset parameterisation wastes part of every step (SURVEY BA-3), the run is far from converged
+        # after 8 iterations and its cost is sensitive to summation order at the 1e-8 level; blocks still agree to 1e-6
+        s = compare(ba, pb, it, mid_rtol=1e-6, final_rtol=1e-7)
         assert s["reduced_dim"] == 179
 
 
@@ -154,6 +156,23 @@ def test_solve_with_factor_spilled_to_l2(monkeypatch):
         compare(b2, pb, 8)
     finally:
         b2.close()
+
+
+def test_singular_imu_covariance_is_an_error(ba):
+    """A singular pre-integration covariance must not be solved with whatever the workspace held before: the call fails
+    and leaves every parameter block untouched (Eigen's LLT in the reference would produce NaNs here)."""
+    from ground_fusion_b200._lib import GfError
+    pb, _ = make_window(seed=0)
+    ba.optimization(pb.clone())                       # leave a valid sqrt-information matrix in the reused workspace
+    bad = pb.clone()
+    cov = np.array(bad.imu[3].covariance).reshape(15, 15)
+    cov[7, :] = 0.0; cov[:, 7] = 0.0
+    bad.imu[3].covariance[:] = list(cov.ravel())
+    before = bad.para_pose.copy()
+    with pytest.raises(GfError, match="covariance"):
+        ba.optimization(bad)
+    assert np.array_equal(bad.para_pose, before)
+    compare(ba, pb, 8)                                # and the handle is still usable
 
 
 def test_solve_with_marginalization_prior(ba):

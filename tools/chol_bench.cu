@@ -1,0 +1,95 @@
+// Microbenchmark of the back end's tiled Cholesky (ba_chol.cuh) with per-warp, per-panel clock64() stamps.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/chol_bench tools/chol_bench.cu && tools/chol_bench [n]
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cmath>
+__device__ long long* g_stamps;
+#ifndef GF_NO_STAMPS
+#define GF_CHOL_STAMP(k) do { if (lane == 0) g_stamps[(J * 16 + w) * 8 + (k)] = clock64(); } while (0)
+#else
+#define GF_CHOL_STAMP(k) do { } while (0)
+#endif
+#define GF_CHOL_STAMP_AFTER(k, dep) do { const double v_ = *(volatile double*)&(dep); if (lane == 0) g_stamps[(J * 16 + w) * 8 + (k)] = clock64() + (v_ == 1.2345e300 ? 1 : 0); } while (0)
+#include "../ground_fusion_b200/csrc/ba_chol.cuh"
+namespace gf { thread_local char g_err[512]; std::atomic<uint64_t> g_launches{0}; }
+using namespace gfba;
+
+template <int R, bool SPILL>
+__global__ void __launch_bounds__(ST_THREADS) k_bench(const double* Ag, double* Lg, int cap, int nc, double* y, long long* stamps, long long* tot)
+{
+    extern __shared__ __align__(128) double S[];
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ int s_fail;
+    const int tid = threadIdx.x;
+    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2, ntl = min(ntiles, cap);
+    TileStoreT<SPILL> T; T.sb = ch_tiles_u32(); T.Lg = Lg; T.cap = cap;
+    double* Linv = S + (size_t)64 * ntl;
+    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64;
+    const long long tl0 = clock64();
+    if (tid == 0) { g_stamps = stamps; s_fail = 0; ch_mbar_init(&mbar, 1); chol_issue_load(Ag, S, ntl, &mbar); }
+    __syncthreads();
+    if (ntl > 0) ch_mbar_wait(&mbar, 0);
+    __syncthreads();
+    const long long t0 = clock64();
+    const bool ok = chol_factor<R, SPILL>(Ag, T, Linv, S8, Ld, nc, n8, &s_fail);
+    const long long t1 = clock64();
+    if (ok) chol_backsubst(T, Linv, Ld, yc, nc);
+    __syncthreads();
+    const long long t2 = clock64();
+    if (tid == 0) { tot[0] = t1 - t0; tot[1] = t2 - t1; tot[2] = t0 - tl0; }
+    for (int c = tid; c < nc; c += blockDim.x) y[c] = yc[c];
+}
+
+int main(int argc, char** argv)
+{
+    const int n = argc > 1 ? atoi(argv[1]) : 165;
+    const int n8 = (n + 8) / 8, ntiles = n8 * (n8 + 1) / 2;
+    std::vector<double> A((size_t)n * n), b(n), tiles((size_t)ntiles * 64, 0.0);
+    srand(1);
+    std::vector<double> B((size_t)n * (n + 3));
+    for (auto& v : B) { const double u1 = (rand() + 1.0) / (RAND_MAX + 2.0), u2 = rand() / (double)RAND_MAX; v = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2); }   // N(0,1): cond(A) ~ 1e3..1e4
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { double s = 0; for (int k = 0; k < n + 3; k++) s += B[(size_t)i * (n + 3) + k] * B[(size_t)j * (n + 3) + k]; A[(size_t)i * n + j] = s + (i == j ? n : 0); }
+    for (auto& v : b) v = rand() / (double)RAND_MAX - 0.5;
+    for (int I = 0; I < n8; I++) for (int J = 0; J <= I; J++) for (int r = 0; r < 8; r++) for (int c = 0; c < 8; c++) {
+        const int i = 8 * I + r, j = 8 * J + c; double v;
+        if (i > n || j > n) v = i == j; else if (i == n) v = j == n ? 1.0 : b[j]; else if (j == n) v = 0; else v = A[(size_t)i * n + j];
+        tiles[(size_t)tix(I, J) * 64 + r * 8 + c] = v;
+    }
+    double *dA, *dL, *dy; long long *dst, *dtot;
+    cudaMalloc(&dA, tiles.size() * 8); cudaMalloc(&dL, 64 * 8 * 1300); cudaMalloc(&dy, n * 8); cudaMalloc(&dst, 48 * 16 * 8 * 8); cudaMalloc(&dtot, 64);
+    cudaMemcpy(dA, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice);
+    const size_t smem = 8 * (64 * (size_t)std::min(ntiles, TILE_CAP) + 64 * (size_t)n8 + 192 + (size_t)((n + 8) & ~7));
+    cudaFuncSetAttribute(k_bench<MAXR / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    cudaFuncSetAttribute(k_bench<MAXR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    for (int rep = 0; rep < 3; rep++) {
+        if (ntiles <= TILE_CAP && n8 <= (MAXR / 2) * CH_BULK) k_bench<MAXR / 2, false><<<1, ST_THREADS, smem>>>(dA, dL, TILE_CAP, n, dy, dst, dtot);
+        else k_bench<MAXR, true><<<1, ST_THREADS, smem>>>(dA, dL, TILE_CAP, n, dy, dst, dtot);
+        cudaDeviceSynchronize();
+    }
+    std::vector<long long> st(48 * 16 * 8), tot(3);
+    cudaMemcpy(st.data(), dst, st.size() * 8, cudaMemcpyDeviceToHost); cudaMemcpy(tot.data(), dtot, 24, cudaMemcpyDeviceToHost);
+    std::vector<double> y(n); cudaMemcpy(y.data(), dy, n * 8, cudaMemcpyDeviceToHost);
+    double res = 0; for (int i = 0; i < n; i++) { double s = -b[i]; for (int j = 0; j < n; j++) s += A[(size_t)i * n + j] * y[j]; res = fmax(res, fabs(s)); }
+    {   // host reference: plain Cholesky solve in double
+        std::vector<double> Lh(A), yh(b);
+        for (int j = 0; j < n; j++) { double dj = Lh[(size_t)j * n + j]; for (int k = 0; k < j; k++) dj -= Lh[(size_t)j * n + k] * Lh[(size_t)j * n + k]; dj = sqrt(dj); Lh[(size_t)j * n + j] = dj;
+            for (int i = j + 1; i < n; i++) { double t = Lh[(size_t)i * n + j]; for (int k = 0; k < j; k++) t -= Lh[(size_t)i * n + k] * Lh[(size_t)j * n + k]; Lh[(size_t)i * n + j] = t / dj; } }
+        for (int i = 0; i < n; i++) { double t = yh[i]; for (int k = 0; k < i; k++) t -= Lh[(size_t)i * n + k] * yh[k]; yh[i] = t / Lh[(size_t)i * n + i]; }
+        for (int i = n - 1; i >= 0; i--) { double t = yh[i]; for (int k = i + 1; k < n; k++) t -= Lh[(size_t)k * n + i] * yh[k]; yh[i] = t / Lh[(size_t)i * n + i]; }
+        double err = 0, mx = 0; for (int i = 0; i < n; i++) { err = fmax(err, fabs(yh[i] - y[i])); mx = fmax(mx, fabs(yh[i])); }
+        printf("max |x - x_host| / max |x_host| = %.2e\n", err / mx);
+    }
+    printf("n=%d n8=%d  TMA load %lld, factor %lld cycles, backsubst %lld cycles, residual %.2e  (%s)\n", n, n8, tot[2], tot[0], tot[1], res, cudaGetErrorString(cudaGetLastError()));
+    printf("per panel: warp 0 = diagonal warp [chol8_inv], bulk warps: [wait inv | TRSM + next diagonal partial | panel barrier | finish panel | sums of next panel]\n");
+    const int NW = ST_WARPS;
+    for (int J = 0; J < n8; J++) {
+        const long long* sd = &st[(J * 16) * 8];
+        printf("J=%2d: D[wait %lld own-tile %lld chol8 %lld]", J, sd[1] - sd[0], sd[2] - sd[1], sd[3] - sd[2]);
+        for (int w = 1; w < NW; w++) { const long long* s = &st[(J * 16 + w) * 8]; printf(" [%lld %lld %lld %lld %lld]", J ? s[1] - s[0] : 0, s[2] - s[1], s[3] - s[2], s[4] - s[3], s[5] - s[4]); }
+        printf("\n");
+    }
+    long long tD = 0; for (int J = 0; J < n8; J++) tD += st[(J * 16) * 8 + 3] - st[(J * 16) * 8 + 2];
+    printf("sum of chol8_inv on the diagonal warp: %lld cycles\n", tD);
+    return 0;
+}

@@ -35,6 +35,34 @@ __global__ void k_tput(double* out, long long* cyc, int n)
     for (int k = 0; k < NACC; k++) s += c[k][0] + c[k][1];
     out[64 + (threadIdx.x & 31)] = s;
 }
+// DFMA warps and DMMA warps at the same time: do the FP64 CUDA-core pipe and the DMMA tensor sub-pipe add up?
+__global__ void k_mixed(double* out, long long* cyc, int n, int dmma_warps)
+{
+    const int w = threadIdx.x >> 5;
+    double a = out[threadIdx.x & 7], b = out[8 + (threadIdx.x & 7)];
+    double c[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { c[k][0] = a + k; c[k][1] = b + k; }
+    __syncthreads();
+    long long t0 = clock64();
+    if (w < dmma_warps) {
+        for (int i = 0; i < n; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) dmma(c[k][0], c[k][1], a, b);
+        }
+    } else {
+        for (int i = 0; i < n; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) { c[k][0] = fma(c[k][0], a, b); c[k][1] = fma(c[k][1], a, b); }
+        }
+    }
+    long long t1 = clock64();
+    cyc[w] = t1 - t0;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += c[k][0] + c[k][1];
+    out[64 + (threadIdx.x & 31)] = s;
+}
 // barrier cost with many warps + named barrier subsets
 __global__ void k_bar(long long* cyc, int n)
 {
@@ -84,6 +112,11 @@ int main()
         printf("%4d thr: __syncthreads %.1f cycles\n", thr, hc[0] / 2048.0);
         k_bar64<<<1, thr>>>(c, 2048); cudaMemcpy(hc, c, 8, cudaMemcpyDeviceToHost);
         printf("%4d thr: named barrier of 2 warps %.1f cycles\n", thr, hc[0] / 2048.0);
+    }
+    for (int dw : {0, 4, 8}) {
+        k_mixed<<<1, 256>>>(d, c, n, dw); cudaMemcpy(hc, c, 64, cudaMemcpyDeviceToHost);
+        long long mx = 0; for (int i = 0; i < 8; i++) mx = hc[i] > mx ? hc[i] : mx;
+        printf("8 warps, %d DMMA + %d DFMA warps: %.1f FMA/clk/SM in total (slowest warp)\n", dw, 8 - dw, (dw * 8.0 * n * 256 + (8 - dw) * 16.0 * n * 32) / (double)mx);
     }
     k_flag<<<1, 64>>>(c, 2048); cudaMemcpy(hc, c, 8, cudaMemcpyDeviceToHost);
     printf("shared-memory flag round trip between two warps: %.1f cycles\n", hc[0] / 2048.0);
