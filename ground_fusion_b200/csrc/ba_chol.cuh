@@ -24,7 +24,7 @@ namespace gfba {
 #endif
 constexpr int ST_THREADS = GF_ST_THREADS;       // k_ba_step block size: 8 warps x 255 registers (the 8x8 diagonal factorisation lives in registers)
 constexpr int ST_WARPS = ST_THREADS / 32;
-constexpr int TILE_CAP = 384;                   // factor tiles resident in shared memory (512 B each); the rest spills to L2
+constexpr int TILE_CAP = 376;                   // factor tiles resident in shared memory (512 B each); the rest spills to L2
 constexpr int MAX_N8 = 48;                      // block rows of the augmented system
 constexpr int MAX_NC = 8 * MAX_N8 - 1;          // reduced dimension supported by the solver (383)
 constexpr int MAXR = 2 * ((MAX_N8 + 2 * (ST_WARPS - 1) - 1) / (2 * (ST_WARPS - 1)));   // block rows per bulk warp, even; kernels are instantiated for MAXR / 2 and MAXR
@@ -465,87 +465,85 @@ __device__ __forceinline__ bool chol_factor(const double* __restrict__ Ag, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Back substitution  L^T y = z  over the leading nc x nc part of the factor by the whole CTA (256 threads).  z = row nc of the
-// factor.  Thread t keeps the running right-hand side of columns t and t + ST_THREADS in registers, so warp w holds the 32
-// columns (4 blocks) 32w.. of a slot.  Groups of 32 columns are solved from the bottom: inside the owning warp block by block with
-// shuffles (y_J = L_JJ^-T rhs_J through the stored inverse, then the warp's own lower columns are updated), then y of the
-// whole group is published and, after ONE barrier, every other thread subtracts the 32 x 1 column strip of L^T y.
+// Back substitution  L^T y = z  over the leading nc x nc part of the factor (z = row nc of the factor), the whole CTA, as a
+// two-stage pipeline so that the dependent chain is ~220 cycles per 8x8 block and meets no CTA-wide barrier:
+//   warp 0 ("chain")  per block J from the bottom: rhs_J = zz_J - L_{J+1,J}^T y_{J+1} (its own, freshest term, in registers),
+//                     y_J = L_JJ^-T rhs_J through the stored inverse, publish y_J.
+//   warps 1.. ("helpers")  when y_I is published: zz_K -= L_{I,K}^T y_I for all columns of the blocks K < I-1, one column per
+//                     thread, all loads issued before the 2 x 4-deep FMA chains.  Their result for y_I is needed by the chain
+//                     two blocks later, so it never waits for them in steady state.
+// zz: nr doubles of shared memory (running right-hand side), y: nc doubles (output).  Named barriers 5,6 (y_I published, by
+// parity) and 7,8 (helpers done with y_I, by parity); the analysis of why two of each suffice is in DESIGN.md.
 template <bool SPILL>
 __device__ __forceinline__ void chol_backsubst(const TileStoreT<SPILL>& T, const double* __restrict__ Linv, const double* __restrict__ Ld,
-                                               double* __restrict__ y, int nc)
+                                               double* __restrict__ y, double* __restrict__ zz, int nc)
 {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int ir = nc >> 3, rr = nc & 7;              // tile row / local row of the right-hand-side row
-    double z[2];
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int c = tid + ST_THREADS * q;
-        z[q] = 0.0;
-        if (c < nc) z[q] = (c >> 3) == ir ? Ld[rr * 8 + (c & 7)] : T.at(tix(ir, c >> 3), rr, c & 7);
-    }
+    for (int c = tid; c < nc; c += ST_THREADS) zz[c] = (c >> 3) == ir ? Ld[rr * 8 + (c & 7)] : T.at(tix(ir, c >> 3), rr, c & 7);
+    __syncthreads();
     const int jtop = (nc - 1) >> 3;
-    for (int G = jtop >> 2; G >= 0; G--) {                 // group G = blocks 4G .. 4G+3 = columns 32G .. 32G+31
-        const int slot = G / ST_WARPS, ow = G % ST_WARPS;
-        if (w == ow) {
-            double zs = slot ? z[1] : z[0];
-            for (int jj = min(3, jtop - 4 * G); jj >= 0; jj--) {
-                const int J = 4 * G + jj, c0 = 8 * J;
-                const int k = lane & 7;
-                const double* Li = Linv + 64 * J + (k >> 2) * 32 + (k & 3);
-                double li[8], rh[8];
+    constexpr int NB_ALL = ST_THREADS;
+    if (w == 0) {
+        const int k = lane & 7;
+        double yprev = 0.0;                                   // y_{J+1}[k] (lane k, replicated in the four lane groups)
+        for (int J = jtop; J >= 0; J--) {
+            const int c0 = 8 * J;
+            // operands that do not depend on the helpers: the inverse column and the tile column of the chain's own term
+            const double* Li = Linv + 64 * J + (k >> 2) * 32 + (k & 3);
+            double li[8], lt[8];
 #pragma unroll
-                for (int r = 0; r < 8; r++) li[r] = Li[r * 4];
+            for (int r = 0; r < 8; r++) li[r] = Li[r * 4];
+            if (J < jtop) {
+                const int t = tix(J + 1, J);
 #pragma unroll
-                for (int r = 0; r < 8; r++) rh[r] = __shfl_sync(0xffffffffu, zs, 8 * jj + r);
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int r = 0; r < 8; r += 2) {
-                    s0 = fma((r >= k && c0 + r < nc) ? li[r] : 0.0, rh[r], s0);
-                    s1 = fma((r + 1 >= k && c0 + r + 1 < nc) ? li[r + 1] : 0.0, rh[r + 1], s1);
-                }
-                const double yk = s0 + s1;                   // lane l holds y[c0 + (l & 7)]
-                if (lane < 8 && c0 + lane < nc) y[c0 + lane] = yk;
-                if (jj > 0) {                                // the warp's own lower columns (lanes < 8 jj)
-                    double yv[8];
-#pragma unroll
-                    for (int r = 0; r < 8; r++) yv[r] = __shfl_sync(0xffffffffu, yk, r);
-                    if (lane < 8 * jj) {
-                        const int t = tix(J, 4 * G + (lane >> 3));
-                        double lv[8];
-#pragma unroll
-                        for (int r = 0; r < 8; r++) lv[r] = T.at(t, r, lane & 7);
-                        double u0 = zs, u1 = 0.0;
-#pragma unroll
-                        for (int r = 0; r < 8; r += 2) {
-                            u0 = fma(-lv[r], (c0 + r < nc) ? yv[r] : 0.0, u0);
-                            u1 = fma(-lv[r + 1], (c0 + r + 1 < nc) ? yv[r + 1] : 0.0, u1);
-                        }
-                        zs = u0 + u1;
-                    }
-                }
+                for (int q = 0; q < 8; q++) lt[q] = T.at(t, q, k);
             }
+            if (J + 2 <= jtop) nb_sync(7 + ((J + 2) & 1), NB_ALL);          // helpers are done with y_{J+2}: zz_J is final up to the chain's own term
+            double rhs = (c0 + k < nc) ? zz[c0 + k] : 0.0;
+            if (J < jtop) {
+                double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q += 2) {
+                    u0 = fma(lt[q], __shfl_sync(0xffffffffu, yprev, q), u0);
+                    u1 = fma(lt[q + 1], __shfl_sync(0xffffffffu, yprev, q + 1), u1);
+                }
+                rhs -= u0 + u1;
+            }
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < 8; r += 2) {
+                s0 = fma((r >= k) ? li[r] : 0.0, __shfl_sync(0xffffffffu, rhs, r), s0);
+                s1 = fma((r + 1 >= k) ? li[r + 1] : 0.0, __shfl_sync(0xffffffffu, rhs, r + 1), s1);
+            }
+            const double yk = (c0 + k < nc) ? s0 + s1 : 0.0;
+            if (lane < 8 && c0 + lane < nc) y[c0 + lane] = yk;
+            yprev = yk;
+            if (J >= 2) { __threadfence_block(); nb_arrive(5 + (J & 1), NB_ALL); }      // y_J published (helpers have columns to update only for J >= 2)
         }
-        __syncthreads();
-        if (G > 0) {
-            const int c0 = 32 * G, nb = min(4, jtop - 4 * G + 1);
+    } else {
+        const int ht = tid - 32;                              // helper thread index, ST_THREADS - 32 of them
+        for (int I = jtop; I >= 2; I--) {
+            nb_sync(5 + (I & 1), NB_ALL);
+            const int c0 = 8 * I, cend = 8 * (I - 1);        // columns [0, cend)
+            double yv[8];
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int c = tid + ST_THREADS * q;
-                if (c < c0) {
-                    double u[4] = {z[q], 0.0, 0.0, 0.0};
-                    for (int b = 0; b < nb; b++) {
-                        const int t = tix(4 * G + b, c >> 3);
-                        double lv[8], yv[8];
+            for (int r = 0; r < 8; r++) yv[r] = (c0 + r < nc) ? y[c0 + r] : 0.0;
+            for (int c = ht; c < cend; c += ST_THREADS - 32) {
+                const int t = tix(I, c >> 3);
+                double lv[8];
 #pragma unroll
-                        for (int r = 0; r < 8; r++) { lv[r] = T.at(t, r, c & 7); yv[r] = (c0 + 8 * b + r < nc) ? y[c0 + 8 * b + r] : 0.0; }
+                for (int r = 0; r < 8; r++) lv[r] = T.at(t, r, c & 7);
+                double u0 = zz[c], u1 = 0.0;
 #pragma unroll
-                        for (int r = 0; r < 8; r++) u[r & 3] = fma(-lv[r], yv[r], u[r & 3]);
-                    }
-                    z[q] = (u[0] + u[1]) + (u[2] + u[3]);
-                }
+                for (int r = 0; r < 8; r += 2) { u0 = fma(-lv[r], yv[r], u0); u1 = fma(-lv[r + 1], yv[r + 1], u1); }
+                zz[c] = u0 + u1;
             }
+            __threadfence_block();
+            nb_arrive(7 + (I & 1), NB_ALL);
         }
     }
+    __syncthreads();
 }
 
 }  // namespace gfba

@@ -127,8 +127,16 @@ __global__ void __launch_bounds__(128) k_ba_setup(BaDev d)
     __syncwarp();
     bool ok = true;
     for (int c = 0; c < n; c++) {
-        int piv = c;
-        for (int r = c + 1; r < n; r++) if (fabs(M[r * w2 + c]) > fabs(M[piv * w2 + c])) piv = r;   // uniform across lanes
+        // partial pivoting: the first row (lowest index) with the largest |M[r][c]|, r >= c, by a warp argmax (same choice as the
+        // sequential scan of the oracle)
+        double pv = (lane >= c && lane < n) ? fabs(M[lane * w2 + c]) : -1.0;
+        int piv = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, pv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, piv, o);
+            if (ov > pv || (ov == pv && oi < piv)) { pv = ov; piv = oi; }
+        }
         if (M[piv * w2 + c] == 0.0) { ok = false; break; }
         __syncwarp();
         if (piv != c && lane < w2) { double t = M[c * w2 + lane]; M[c * w2 + lane] = M[piv * w2 + lane]; M[piv * w2 + lane] = t; }
@@ -473,33 +481,34 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
 __device__ inline void plus_free(const BaDev& d, const double* X, const double* delta, double* Y, int tid, int nt, double& s2, double& mx)
 {
     s2 = 0; mx = 0;
-    auto acc = [&](int off, int size) { for (int k = 0; k < size; k++) { const double v = X[off + k] - Y[off + k]; s2 += v * v; mx = fmax(mx, fabs(v)); } };
+    auto put = [&](int off, int size, const double* nv) {      // Y := nv and |X - nv| from the registers (Y is not read back)
+        for (int k = 0; k < size; k++) { Y[off + k] = nv[k]; const double v = X[off + k] - nv[k]; s2 += v * v; mx = fmax(mx, fabs(v)); }
+    };
     for (int f = tid; f < d.F; f += nt) {
-        if (d.col_pose[f] >= 0) { pose_plus(X + X_POSE + 7 * f, delta + d.col_pose[f], Y + X_POSE + 7 * f); acc(X_POSE + 7 * f, 7); }
-        if (d.col_sb[f] >= 0) { for (int k = 0; k < 9; k++) Y[X_SB + 9 * f + k] = X[X_SB + 9 * f + k] + delta[d.col_sb[f] + k]; acc(X_SB + 9 * f, 9); }
+        if (d.col_pose[f] >= 0) { double o[7]; pose_plus(X + X_POSE + 7 * f, delta + d.col_pose[f], o); put(X_POSE + 7 * f, 7, o); }
+        if (d.col_sb[f] >= 0) { double o[9]; for (int k = 0; k < 9; k++) o[k] = X[X_SB + 9 * f + k] + delta[d.col_sb[f] + k]; put(X_SB + 9 * f, 9, o); }
     }
     if (tid == nt - 1) {
-        if (d.col_ex >= 0) { pose_plus(X + X_EX, delta + d.col_ex, Y + X_EX); acc(X_EX, 7); }
-        if (d.col_td >= 0) { Y[X_TD] = X[X_TD] + delta[d.col_td]; acc(X_TD, 1); }
+        if (d.col_ex >= 0) { double o[7]; pose_plus(X + X_EX, delta + d.col_ex, o); put(X_EX, 7, o); }
+        if (d.col_td >= 0) { const double o = X[X_TD] + delta[d.col_td]; put(X_TD, 1, &o); }
     }
     if (tid == nt - 2) {
         if (d.col_exw >= 0) {    // PoseSubsetParameterization: masked components are zeroed inside Plus only
-            double dd[6];
+            double dd[6], o[7];
             for (int k = 0; k < 6; k++) dd[k] = ((d.exw_mask >> k) & 1) ? 0.0 : delta[d.col_exw + k];
-            pose_plus(X + X_EXW, dd, Y + X_EXW); acc(X_EXW, 7);
+            pose_plus(X + X_EXW, dd, o); put(X_EXW, 7, o);
         }
-        for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) { Y[X_IX + k] = X[X_IX + k] + delta[d.col_ix[k]]; acc(X_IX + k, 1); }
-        if (d.col_tdw >= 0) { Y[X_TDW] = X[X_TDW] + delta[d.col_tdw]; acc(X_TDW, 1); }
+        for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) { const double o = X[X_IX + k] + delta[d.col_ix[k]]; put(X_IX + k, 1, &o); }
+        if (d.col_tdw >= 0) { const double o = X[X_TDW] + delta[d.col_tdw]; put(X_TDW, 1, &o); }
     }
     if (tid == nt - 3 && d.col_pr >= 0) {     // OrientationSubsetParameterization::Plus
         double dd[3], dq[4], qn[4];
         for (int k = 0; k < 3; k++) dd[k] = ((d.pr_mask >> k) & 1) ? 0.0 : delta[d.col_pr + k];
         delta_q(dd, dq); q_mul(X + X_PR, dq, qn); q_normalize(qn);
-        for (int k = 0; k < 4; k++) Y[X_PR + k] = qn[k];
-        Y[X_PZ] = X[X_PZ] + delta[d.col_pz];
-        acc(X_PR, 4); acc(X_PZ, 1);
+        put(X_PR, 4, qn);
+        const double o = X[X_PZ] + delta[d.col_pz]; put(X_PZ, 1, &o);
     }
-    for (int k = tid; k < d.nfeat; k += nt) { const int c = d.col_feat[k]; if (c >= 0) { Y[X_FEAT + k] = X[X_FEAT + k] + delta[c]; acc(X_FEAT + k, 1); } }
+    for (int k = tid; k < d.nfeat; k += nt) { const int c = d.col_feat[k]; if (c >= 0) { const double o = X[X_FEAT + k] + delta[c]; put(X_FEAT + k, 1, &o); } }
 }
 // sum of squares of A over the ambient coordinates of the free blocks
 __device__ inline double free_norm2(const BaDev& d, const double* A, int tid, int nt)
@@ -571,13 +580,20 @@ __device__ __forceinline__ void schur_tile(const BaDev& d, const double* __restr
     const int ka = lane & 3, ia = 8 * I + (lane >> 2), ib = 8 * J + (lane >> 2);
     auto wx = [&](int l, int c) { return c < nc ? W[(size_t)l * nc + c] : (c == nc ? g[nc + l] : 0.0); };
     double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
-    for (int l0 = 0; l0 < L; l0 += 8) {
-        const int la = l0 + ka, lb = l0 + 4 + ka;
-        double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
-        if (la < L) { a0 = cl[la] * wx(la, ia); b0 = wx(la, ib); }
-        if (lb < L) { a1 = cl[lb] * wx(lb, ia); b1 = wx(lb, ib); }
-        dmma884(acc0[0], acc0[1], a0, b0);
-        dmma884(acc1[0], acc1[1], a1, b1);
+    for (int l0 = 0; l0 < L; l0 += 64) {           // 32 loads from L2 in flight per lane, then sixteen MMAs on two accumulators
+        double av[16], bv[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int l = l0 + 4 * k + ka;
+            av[k] = 0.0; bv[k] = 0.0;
+            if (l < L) { av[k] = wx(l, ia); bv[k] = wx(l, ib); }
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int l = l0 + 4 * k + ka;
+            const double ak = l < L ? cl[l] * av[k] : 0.0;
+            if (k & 1) dmma884(acc1[0], acc1[1], ak, bv[k]); else dmma884(acc0[0], acc0[1], ak, bv[k]);
+        }
     }
     const int a = 8 * I + (lane >> 2);
     double out[2];
@@ -607,11 +623,12 @@ __device__ __forceinline__ void schur_tile(const BaDev& d, const double* __restr
 
 __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
 {
-    extern __shared__ double ssm[];                // cl[L] | ss[nc+1] | sv[nc]
+    extern __shared__ double ssm[];                // tile CTAs: cl[L] | ss[nc+1] | sv[nc];  last CTA: delta[n]
+    __shared__ double sred2[2 * SCHUR_WARPS];
     const BaState& st = *d.st;
     if (st.done || st.setup_failed) return;
     const bool fresh = st.need_linearize != 0;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nt = blockDim.x;
     {   // clear the accumulator that is free during this iteration: k_ba_eval(1) linearises the candidate into it
         const int freeb = fresh ? st.cur : (st.cur ^ 1);
         const size_t tot = acc_size(d.nc, d.L);
@@ -622,20 +639,49 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
     }
     if (!fresh && st.reuse) return;               // the previous Gauss-Newton step is still valid
     const int cur = fresh ? (st.cur ^ 1) : st.cur;
-    const int nc = d.nc, L = d.L;
+    const int nc = d.nc, L = d.L, n = d.n;
     const double* H = acc_H(d, cur); const double* Hp = d.Hp; const double* g = acc_g(d, cur);
     const double* W = acc_W(d, cur); const double* hll = acc_hll(d, cur);
     const bool first = st.first != 0;
     const double mu = st.mu;
-    double* cl = ssm; double* ss = ssm + L; double* sv = ss + nc + 1;
     // everything (scale, D, c_l) is recomputed locally from the accumulators so that this kernel can run before k_ba_step adopts them
     auto scale_of = [&](int c) { return first ? 1.0 / (1.0 + sqrt(c < nc ? H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c] : hll[c - nc])) : d.scale[c]; };
-    for (int l = tid; l < L; l += blockDim.x) {
+    if (blockIdx.x == gridDim.x - 1) {
+        // ---- the last CTA prepares what k_ba_step needs before it can factor: D, gs = g'/D, e_l = 1 / (h'_ll + mu D_l^2), the
+        // Jacobi scale (iteration 0) and, for a fresh linearisation, |x| and the gradient max-norm |x - Plus(x, -g)|_inf
+        // (TrustRegionMinimizer's gradient tolerance test) -- off the single-CTA critical path of k_ba_step ----
+        double* dl = ssm;
+        for (int c = tid; c < n; c += nt) {
+            const double sc_ = scale_of(c);
+            double hd = (c < nc ? H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c] : hll[c - nc]) * sc_ * sc_;
+            const double hraw = hd;
+            hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);
+            const double D = sqrt(hd), gc = g[c];
+            if (first) d.scale[c] = sc_;
+            d.diag[c] = D;
+            d.gs[c] = gc * sc_ / D;
+            if (c >= nc) d.gn[c] = 1.0 / (hraw + mu * hd);
+            dl[c] = -gc;
+        }
+        if (fresh) {
+            __syncthreads();
+            double s2, mx;
+            plus_free(d, d.X, dl, d.Xc, tid, nt, s2, mx);            // Xc is free scratch here: the accepted candidate has become X
+            mx = block_reduce_max(mx, sred2);
+            double xs2 = free_norm2(d, d.X, tid, nt);
+            xs2 = block_reduce_sum(xs2, sred2);
+            if (tid == 0) { d.st->grad_max = mx; d.st->x_norm = sqrt(xs2); }
+        }
+        return;
+    }
+    if (st.it >= st.max_iter) return;             // the closing launch only needs the norms
+    double* cl = ssm; double* ss = ssm + L; double* sv = ss + nc + 1;
+    for (int l = tid; l < L; l += nt) {
         const double sl = scale_of(nc + l), hd = hll[l] * sl * sl;
         const double hc = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);     // D_l^2
         cl[l] = sl * sl / (hd + mu * hc);
     }
-    for (int c = tid; c <= nc; c += blockDim.x) {
+    for (int c = tid; c <= nc; c += nt) {
         if (c == nc) { ss[c] = 1.0; continue; }
         const double sc_ = scale_of(c);
         double hd = (H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c]) * sc_ * sc_;
@@ -643,19 +689,26 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
         ss[c] = sc_; sv[c] = g[c] * sc_ * sc_ / hd;        // v = gs / D (times the Jacobi scale, because H is unscaled)
     }
     __syncthreads();
-    const int n8 = (nc + 8) >> 3, ntiles = st.it >= st.max_iter ? 0 : n8 * (n8 + 1) / 2;   // the closing launch only needs the norms
+    const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2;
     double num = 0, den = 0;
-    const int gw = blockIdx.x * SCHUR_WARPS + warp, nw = gridDim.x * SCHUR_WARPS;
+    const int gw = blockIdx.x * SCHUR_WARPS + warp, nw = (gridDim.x - 1) * SCHUR_WARPS;
     for (int t = gw; t < ntiles; t += nw) {
         int I = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
         while (tix(I + 1, 0) <= t) I++;
         while (tix(I, 0) > t) I--;
         schur_tile(d, H, g, W, ss, sv, cl, mu, I, t - tix(I, 0), lane, num, den);
     }
-    // landmark part of the Cauchy quadratic form: 2 v_l (W v_c)_l + h_ll v_l^2, warp per landmark
-    for (int l = gw; l < L; l += nw) {
+    // landmark part of the Cauchy quadratic form: 2 v_l (W v_c)_l + h_ll v_l^2, warp per landmark (taken from the back of the
+    // warp list: the front warps own a tile each)
+    for (int l = nw - 1 - gw; l < L; l += nw) {
         double t = 0;
-        for (int c = lane; c < nc; c += 32) t += W[(size_t)l * nc + c] * sv[c];
+        for (int c0 = 0; c0 < nc; c0 += 256) {
+            double wv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int c = c0 + 32 * k + lane; wv[k] = c < nc ? W[(size_t)l * nc + c] : 0.0; }
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const int c = c0 + 32 * k + lane; if (c < nc) t = fma(wv[k], sv[c], t); }
+        }
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
         if (lane == 0) {
             const double sl = scale_of(nc + l), hd = hll[l] * sl * sl;
@@ -663,34 +716,6 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
             const double vl = g[nc + l] * sl * sl / hc;
             den += 2.0 * vl * t + hll[l] * vl * vl;
             const double gsl = g[nc + l] * sl / sqrt(hc); num += gsl * gsl;
-        }
-    }
-    __shared__ double sred2[2 * SCHUR_WARPS];
-    if (blockIdx.x == gridDim.x - 1) {
-        // ---- this CTA also prepares what k_ba_step needs before it can factor: D, gs = g'/D, e_l = 1 / (h'_ll + mu D_l^2), the
-        // Jacobi scale (iteration 0) and, for a fresh linearisation, |x| and the gradient max-norm |x - Plus(x, -g)|_inf
-        // (TrustRegionMinimizer's gradient tolerance test) -- off the single-CTA critical path ----
-        const int n = d.n, nt = blockDim.x;
-        for (int c = tid; c < n; c += nt) {
-            const double sc_ = c < nc ? ss[c] : scale_of(c);
-            double hd = (c < nc ? H[(size_t)c * nc + c] + Hp[(size_t)c * nc + c] : hll[c - nc]) * sc_ * sc_;
-            const double hraw = hd;
-            hd = hd < 1e-6 ? 1e-6 : (hd > 1e32 ? 1e32 : hd);
-            const double D = sqrt(hd);
-            if (first) d.scale[c] = sc_;
-            d.diag[c] = D;
-            d.gs[c] = g[c] * sc_ / D;
-            if (c >= nc) d.gn[c] = 1.0 / (hraw + mu * hd);
-            if (fresh) d.delta[c] = -g[c];
-        }
-        if (fresh) {
-            __syncthreads();
-            double s2, mx;
-            plus_free(d, d.X, d.delta, d.Xc, tid, nt, s2, mx);       // Xc is free scratch here: the accepted candidate has become X
-            mx = block_reduce_max(mx, sred2);
-            double xs2 = free_norm2(d, d.X, tid, nt);
-            xs2 = block_reduce_sum(xs2, sred2);
-            if (tid == 0) { d.st->grad_max = mx; d.st->x_norm = sqrt(xs2); }
         }
     }
     for (int o = 16; o > 0; o >>= 1) { num += __shfl_xor_sync(0xffffffffu, num, o); den += __shfl_xor_sync(0xffffffffu, den, o); }
@@ -721,7 +746,7 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
     const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2, ntl = min(ntiles, d.tile_cap);
     TileStoreT<SPILL> T; T.sb = ch_tiles_u32(); T.Lg = d.Lg; T.cap = d.tile_cap;
     double* Linv = S + (size_t)64 * ntl;
-    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64;
+    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64; double* zz = yc + ((nc + 8) & ~7);
     const long long t_kernel0 = clock64();      // always on (two clock reads per launch): SM cycles of the launches that took a step
 #ifdef GF_PROFILE
     long long t_last = clock64();
@@ -791,7 +816,7 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
             PH(3);   // Cholesky
             bool ok = ok_f;
             if (ok) {
-                chol_backsubst(T, Linv, Ld, yc, nc);
+                chol_backsubst(T, Linv, Ld, yc, zz, nc);
                 __syncthreads();
                 int bad = 0;
                 for (int c = tid; c < nc; c += nt) if (!isfinite(yc[c])) bad = 1;
@@ -805,10 +830,21 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
                 __syncthreads();
                 for (int l0 = 4 * warp; l0 < L; l0 += 4 * nwarp) {
                     double t[4] = {0, 0, 0, 0};
-                    for (int b = lane; b < nc; b += 32) {
-                        const double vb = vbuf[b];
+                    for (int b0 = 0; b0 < nc; b0 += 192) {            // 6 x 4 loads from L2 in flight per lane, then the FMAs
+                        double wv[6][4];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) if (l0 + q < L) t[q] = fma(W[(size_t)(l0 + q) * nc + b], vb, t[q]);
+                        for (int k = 0; k < 6; k++) {
+                            const int b = b0 + 32 * k + lane;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) wv[k][q] = (b < nc && l0 + q < L) ? W[(size_t)(l0 + q) * nc + b] : 0.0;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 6; k++) {
+                            const int b = b0 + 32 * k + lane;
+                            const double vb = b < nc ? vbuf[b] : 0.0;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) t[q] = fma(wv[k][q], vb, t[q]);
+                        }
                     }
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
@@ -1522,9 +1558,9 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
     const int eval_blocks = n_work + p->n_imu + p->n_wheel + (p->n_plane > 0 ? 1 : 0) + (pn ? 1 : 0);
     const size_t prior_smem = sizeof(double) * 2 * (size_t)pn;
-    const size_t step_smem = sizeof(double) * (64 * (size_t)std::min(ntiles, s->tile_cap) + 64 * (size_t)n8 + 192 + (size_t)((nc + 8) & ~7));
-    const size_t schur_smem = sizeof(double) * (size_t)(L + 2 * nc + 2);
-    const int schur_grid = (ntiles + SCHUR_WARPS - 1) / SCHUR_WARPS;
+    const size_t step_smem = sizeof(double) * (64 * (size_t)std::min(ntiles, s->tile_cap) + 64 * (size_t)n8 + 192 + 2 * (size_t)((nc + 8) & ~7));
+    const size_t schur_smem = sizeof(double) * (size_t)std::max(L + 2 * nc + 2, n + 1);
+    const int schur_grid = (ntiles + SCHUR_WARPS - 1) / SCHUR_WARPS + 1;      // + the CTA that prepares k_ba_step's vectors and norms
     const int iters = p->max_num_iterations;
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 0); GF_LAUNCHED(); }
     for (int it = 0; it <= iters; it++) {
@@ -1844,12 +1880,12 @@ __global__ void __launch_bounds__(ST_THREADS) k_stage_chol(const double* Ag, dou
     const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2, ntl = min(ntiles, cap);
     TileStoreT<SPILL> T; T.sb = ch_tiles_u32(); T.Lg = Lg; T.cap = cap;
     double* Linv = S + (size_t)64 * ntl;
-    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64;
+    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64; double* zz = yc + ((nc + 8) & ~7);
     if (tid == 0) { s_fail = 0; ch_mbar_init(&mbar, 1); chol_issue_load(Ag, S, ntl, &mbar); }
     __syncthreads();
     if (ntl > 0) ch_mbar_wait(&mbar, 0);
     const bool ok = chol_factor<R, SPILL>(Ag, T, Linv, S8, Ld, nc, n8, &s_fail);
-    if (ok) chol_backsubst(T, Linv, Ld, yc, nc);
+    if (ok) chol_backsubst(T, Linv, Ld, yc, zz, nc);
     __syncthreads();
     if (ok) for (int c = tid; c < nc; c += blockDim.x) y[c] = yc[c];
     if (tid == 0) *fail = ok ? 0 : 1;
@@ -1885,7 +1921,7 @@ extern "C" int gf_stage_spd_solve(int device, const double* A, const double* b, 
     GF_CUDA(cudaMalloc(&dy, (size_t)n * sizeof(double)));
     GF_CUDA(cudaMalloc(&df, sizeof(int)));
     GF_CUDA(cudaMemcpy(dA, tiles.data(), tiles.size() * sizeof(double), cudaMemcpyHostToDevice));
-    const size_t smem = sizeof(double) * (64 * (size_t)std::min(ntiles, cap) + 64 * (size_t)n8 + 192 + (size_t)((n + 8) & ~7));
+    const size_t smem = sizeof(double) * (64 * (size_t)std::min(ntiles, cap) + 64 * (size_t)n8 + 192 + 2 * (size_t)((n + 8) & ~7));
     GF_CUDA(cudaFuncSetAttribute(k_stage_chol<MAXR / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     GF_CUDA(cudaFuncSetAttribute(k_stage_chol<MAXR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     if (ntiles <= cap && n8 <= (MAXR / 2) * CH_BULK) k_stage_chol<MAXR / 2, false><<<1, ST_THREADS, smem>>>(dA, dL, cap, n, dy, df);

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_bench(const double* Ag, double* 
     const int n8 = (nc + 8) >> 3, ntiles = n8 * (n8 + 1) / 2, ntl = min(ntiles, cap);
     TileStoreT<SPILL> T; T.sb = ch_tiles_u32(); T.Lg = Lg; T.cap = cap;
     double* Linv = S + (size_t)64 * ntl;
-    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64;
+    double* S8 = Linv + 64 * n8; double* Ld = S8 + 128; double* yc = Ld + 64; double* zz = yc + ((nc + 8) & ~7);
     const long long tl0 = clock64();
     if (tid == 0) { g_stamps = stamps; s_fail = 0; ch_mbar_init(&mbar, 1); chol_issue_load(Ag, S, ntl, &mbar); }
     __syncthreads();
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_bench(const double* Ag, double* 
     const long long t0 = clock64();
     const bool ok = chol_factor<R, SPILL>(Ag, T, Linv, S8, Ld, nc, n8, &s_fail);
     const long long t1 = clock64();
-    if (ok) chol_backsubst(T, Linv, Ld, yc, nc);
+    if (ok) chol_backsubst(T, Linv, Ld, yc, zz, nc);
     __syncthreads();
     const long long t2 = clock64();
     if (tid == 0) { tot[0] = t1 - t0; tot[1] = t2 - t1; tot[2] = t0 - tl0; }
@@ -59,7 +59,7 @@ int main(int argc, char** argv)
     double *dA, *dL, *dy; long long *dst, *dtot;
     cudaMalloc(&dA, tiles.size() * 8); cudaMalloc(&dL, 64 * 8 * 1300); cudaMalloc(&dy, n * 8); cudaMalloc(&dst, 48 * 16 * 8 * 8); cudaMalloc(&dtot, 64);
     cudaMemcpy(dA, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice);
-    const size_t smem = 8 * (64 * (size_t)std::min(ntiles, TILE_CAP) + 64 * (size_t)n8 + 192 + (size_t)((n + 8) & ~7));
+    const size_t smem = 8 * (64 * (size_t)std::min(ntiles, TILE_CAP) + 64 * (size_t)n8 + 192 + 2 * (size_t)((n + 8) & ~7));
     cudaFuncSetAttribute(k_bench<MAXR / 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     cudaFuncSetAttribute(k_bench<MAXR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     for (int rep = 0; rep < 3; rep++) {

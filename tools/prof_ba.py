@@ -19,8 +19,7 @@ import ctypes
 prof = (ctypes.c_longlong * 32)()
 ba.L.gf_ba_debug_profile.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
 ba.L.gf_ba_debug_profile(ba._h, prof)
-names = ["adopt+norms", "diag+cauchy", "e_l / reassembly", "cholesky", "finite check", "landmark backsubst", "dogleg+model", "candidate", "backsubst", "-", "-", "-", "-", "eval: prior CTA max", "eval: visual CTA max", "eval: imu CTA max",
-         "chol A (warp 0)", "chol B (warp 0)", "chol barrier 1 wait", "chol C", "chol barrier 2 wait", "chol8_inv (diag warps)"]
+names = ["adopt+bookkeeping", "-", "wait for the TMA load", "cholesky", "backsubst + finite check", "landmark backsubst", "dogleg+model", "candidate", "-", "-", "-", "-", "-", "eval: prior CTA max", "eval: visual CTA max", "eval: imu CTA max"]
 tot = sum(list(prof)[:9])
 for n_, v in zip(names, prof):
     print("%-20s %9d cycles %5.1f%%" % (n_, v, 100.0 * v / max(tot, 1)))
