@@ -3,7 +3,8 @@
 // Ceres 1.14's trust_region_minimizer.cc / dogleg_strategy.cc; parity with Ceres itself is unpinned).
 //
 // Data flow of one solve (everything stays on the device between the upload and the final download):
-//   k_ba_setup      IMU sqrt-information matrices, H_prior = J0^T J0, solver state
+//   (host)          initial solver state and candidate := x travel with the problem upload; H_prior and the accumulators are memset
+//   k_ba_prior_hessian  H_prior = J0^T J0
 //   k_ba_eval       mode 0 "linearise": one CTA per pose pair (i,j) evaluates its visual factors, stages the
 //                   Huber-corrected Jacobian slab [Ji|Jj|Jex|Jtd] in shared memory and reduces it to block
 //                   Hessians; one CTA per IMU factor; one CTA for the marginalisation prior.  Landmark terms
@@ -43,7 +44,7 @@ struct BaState {
     double cauchy_num, cauchy_den;   // |gs|^2 and v^T H' v accumulated by k_ba_schur
     int it, reuse, done, termination, n_success, invalid_streak, need_linearize, step_valid, cur, first, max_iter, solver_failed;
     unsigned int eval_ticket;    // CTAs of the current k_ba_eval(1) that have finished: the last one runs the decision
-    int setup_failed;            // sticky: an IMU covariance was singular / not positive definite (k_ba_setup); nothing is solved
+    int setup_failed;            // sticky: an IMU covariance was singular / not positive definite (first k_ba_eval); nothing is solved
     long long prof[32];          // clock64() cycles per phase of k_ba_step, summed over iterations (debug)
 };
 
@@ -102,26 +103,12 @@ __device__ __forceinline__ double block_reduce_sum(double v, double* sh)
 }
 
 // ------------------------------------------------------------------------------------------------
-// IMU sqrt-information matrices, one warp per factor: the same Gauss-Jordan (partial pivoting) + Cholesky as
-// gfba::sqrt_info_from_cov / the oracle, element updates spread over the lanes (identical arithmetic per element).
-__global__ void __launch_bounds__(128) k_ba_setup(BaDev d)
+// IMU sqrt-information matrix  sqrt_info = LLT(cov^-1).L^T  (reference imu_factor.h:73), one warp: the same Gauss-Jordan
+// (partial pivoting) + Cholesky as gfba::sqrt_info_from_cov / the oracle, element updates spread over the lanes (identical
+// arithmetic per element).  M: 15 x 30 doubles of shared memory.  Run by the IMU CTAs of the first k_ba_eval, next to the
+// thread that evaluates the factor; false = the covariance is singular / not positive definite.
+__device__ __forceinline__ bool imu_sqrt_info_warp(const double* __restrict__ cov, double* M, double* __restrict__ out, int lane)
 {
-    __shared__ double Ms[4][15 * 30];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
-    const int nc = d.nc;
-    for (int e = gid; e < nc * nc; e += gsz) d.Hp[e] = 0.0;
-    if (d.Xc != d.X) for (int e = gid; e < X_FEAT + d.nfeat; e += gsz) d.Xc[e] = d.X[e];      // constant blocks of the candidate never change again
-    if (gid == 0) {
-        BaState& s = *d.st;
-        s.radius = 1e4; s.mu = 1e-8; s.reuse = 0; s.done = 0; s.it = 0; s.n_success = 0; s.invalid_streak = 0;
-        s.need_linearize = 1; s.step_valid = 0; s.cur = 1; s.first = 1; s.acc_cost[0] = s.acc_cost[1] = 0.0;   // first linearisation goes to buffer 0
-        s.x_cost = 0; s.cand_cost = 0;
-    }
-    const int m = blockIdx.x * 4 + warp;
-    if (m >= d.n_imu) return;
-    double* M = Ms[warp];
-    const double* cov = d.imu[m].covariance;
     const int n = 15, w2 = 30;
     for (int e = lane; e < n * w2; e += 32) { int i = e / w2, j = e - i * w2; M[e] = j < n ? cov[i * n + j] : ((j - n) == i ? 1.0 : 0.0); }
     __syncwarp();
@@ -171,10 +158,9 @@ __global__ void __launch_bounds__(128) k_ba_setup(BaDev d)
             else if (lane > j && lane < n) A[lane * w2 + j] = t / dd;
             __syncwarp();
         }
-        double* out = d.imu_sqrt + 225 * m;
         if (ok) for (int e = lane; e < n * n; e += 32) { int i = e / n, j = e - i * n; out[e] = (j >= i) ? A[j * w2 + i] : 0.0; }
     }
-    if (!ok && lane == 0) d.st->setup_failed = 1;      // zeroed by the host before the launch; every later kernel returns at once
+    return ok;
 }
 __global__ void k_ba_prior_hessian(BaDev d)
 {
@@ -327,6 +313,10 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
         const gf_ba_imu_factor& f = d.imu[m];
         const double* U = d.imu_sqrt + 225 * m;
         if (tid == 0) eval_imu_raw(f, d.gravity, X + X_POSE + 7 * f.i, X + X_SB + 9 * f.i, X + X_POSE + 7 * f.j, X + X_SB + 9 * f.j, simu_r, simu_J, jac);
+        if (mode == 0 && (tid >> 5) == 1) {          // first linearisation: the sqrt-information matrix of this factor, once per solve, on a second warp
+            const bool ok = imu_sqrt_info_warp(f.covariance, simu_JU, d.imu_sqrt + 225 * m, tid & 31);
+            if (!ok && (tid & 31) == 0) d.st->setup_failed = 1;      // sticky; zeroed by the host; every later kernel returns at once
+        }
         __syncthreads();
         if (tid < 15) { double s = 0; for (int k = 0; k < 15; k++) s += U[tid * 15 + k] * simu_r[k]; simu_ru[tid] = s; }
         if (jac) for (int o = tid; o < 450; o += PAIR_THREADS) { int r = o / 30, c = o - r * 30; double s = 0; for (int k = 0; k < 15; k++) s += U[r * 15 + k] * simu_J[k * 30 + c]; simu_JU[o] = s; }
@@ -476,7 +466,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
 
 // ------------------------------------------------------------------------------------------------
 // ambient-space helpers over the non-constant blocks
-// Y = X (+) delta on the FREE blocks only (constant blocks of Y already equal X: k_ba_setup copies X once and nothing else
+// Y = X (+) delta on the FREE blocks only (constant blocks of Y already equal X: the host uploads the candidate as a copy of X and nothing else
 // ever writes them) and, in the same pass, this thread's share of |X - Y|^2 and max |X - Y| over the ambient coordinates.
 __device__ inline void plus_free(const BaDev& d, const double* X, const double* delta, double* Y, int tid, int nt, double& s2, double& mx)
 {
@@ -1494,11 +1484,12 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
                  o_imu = take(sizeof(gf_ba_imu_factor) * (size_t)p->n_imu), o_whl = take(sizeof(gf_ba_wheel_factor) * (size_t)p->n_wheel), o_plf = take(sizeof(int) * (size_t)(p->n_plane > 0 ? p->n_plane : 1)), o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)),
                  o_cf = take(sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1)), o_pJ = take(sizeof(double) * (size_t)pn * pn), o_pr0 = take(sizeof(double) * pn),
                  o_px0 = take(sizeof(double) * px0_len), o_pcol = take(sizeof(int) * (size_t)(pn > 0 ? pn : 1));
+    const size_t o_Xc = take(sizeof(double) * (X_FEAT + nfeat)), o_st = take(sizeof(BaState));     // uploaded too: candidate := x, initial solver state
     const size_t upload_bytes = off;
-    const size_t o_Xc = take(sizeof(double) * (X_FEAT + nfeat)), o_sq = take(sizeof(double) * 225 * (size_t)(p->n_imu > 0 ? p->n_imu : 1)),
+    const size_t o_sq = take(sizeof(double) * 225 * (size_t)(p->n_imu > 0 ? p->n_imu : 1)),
                  o_Hp = take(sizeof(double) * (size_t)nc * nc), o_a0 = take(sizeof(double) * acc_size(nc, L)), o_a1 = take(sizeof(double) * acc_size(nc, L)),
                  o_vec = take(sizeof(double) * 6 * (size_t)(n > 0 ? n : 1)), o_Sg = take(sizeof(double) * 64 * (size_t)ntiles),
-                 o_Lg = take(sizeof(double) * 64 * (size_t)(ntiles > s->tile_cap ? ntiles - s->tile_cap : 1)), o_st = take(sizeof(BaState));
+                 o_Lg = take(sizeof(double) * 64 * (size_t)(ntiles > s->tile_cap ? ntiles - s->tile_cap : 1));
     int rc = ensure(s, off);
     if (rc) return rc;
     char* hb = (char*)s->hbuf; char* db = (char*)s->dbuf;
@@ -1513,6 +1504,12 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     hX[X_PR + 3] = 1.0;
     if (p->n_plane > 0) { memcpy(hX + X_EXW, p->para_ex_wheel, sizeof(double) * 7); memcpy(hX + X_PR, p->para_plane_R, sizeof(double) * 4); hX[X_PZ] = p->para_plane_Z[0]; memcpy(hb + o_plf, p->plane_frames, sizeof(int) * p->n_plane); }
     memcpy(hX + X_FEAT, p->para_feature, sizeof(double) * nfeat);
+    memcpy(hb + o_Xc, hX, sizeof(double) * (X_FEAT + nfeat));           // the candidate starts as a copy: its constant blocks never change
+    {   // TrustRegionMinimizer / DoglegStrategy initial state; the first linearisation goes to buffer 0
+        BaState* h0 = (BaState*)(hb + o_st);
+        memset(h0, 0, sizeof(BaState));
+        h0->radius = 1e4; h0->mu = 1e-8; h0->need_linearize = 1; h0->cur = 1; h0->first = 1; h0->max_iter = p->max_num_iterations;
+    }
     {   // factors sorted by pair
         gf_ba_visual_factor* hv = (gf_ba_visual_factor*)(hb + o_vis);
         std::vector<int> fill(pair_start.begin(), pair_start.end() - 1);
@@ -1548,13 +1545,7 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     cudaStream_t st = s->s;
     GF_CUDA(cudaEventRecord(s->e0, st));
     GF_CUDA(cudaMemcpyAsync(db, hb, upload_bytes, cudaMemcpyHostToDevice, st));
-    GF_CUDA(cudaMemsetAsync(db + o_a0, 0, al(sizeof(double) * acc_size(nc, L)) * 2, st));
-    GF_CUDA(cudaMemsetAsync(db + o_st, 0, sizeof(BaState), st));
-    k_ba_setup<<<(p->n_imu + 3) / 4 + 1, 128, 0, st>>>(d); GF_LAUNCHED();
-    {   // max_iter into the state (after setup zeroed/initialised it)
-        int mi = p->max_num_iterations;
-        GF_CUDA(cudaMemcpyAsync((char*)d.st + offsetof(BaState, max_iter), &mi, sizeof(int), cudaMemcpyHostToDevice, st));
-    }
+    GF_CUDA(cudaMemsetAsync(db + o_Hp, 0, al(sizeof(double) * (size_t)nc * nc) + al(sizeof(double) * acc_size(nc, L)) * 2, st));   // H_prior, both accumulators
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
     const int eval_blocks = n_work + p->n_imu + p->n_wheel + (p->n_plane > 0 ? 1 : 0) + (pn ? 1 : 0);
     const size_t prior_smem = sizeof(double) * 2 * (size_t)pn;
@@ -1696,9 +1687,10 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (nv ? nv : 1)), o_imu = take(sizeof(gf_ba_imu_factor)), o_whl = take(sizeof(gf_ba_wheel_factor)),
                  o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)), o_cf = take(sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1)),
                  o_pJ = take(sizeof(double) * (size_t)pn * pn), o_pr0 = take(sizeof(double) * pn), o_px0 = take(sizeof(double) * px0_len), o_pcol = take(sizeof(int) * (size_t)(pn > 0 ? pn : 1));
+    const size_t o_st = take(sizeof(BaState));
     const size_t upload_bytes = off;
     const size_t NN = (size_t)N * N, mm = (size_t)m * m, nn = (size_t)n * n;
-    const size_t o_sq = take(sizeof(double) * 225), o_Hp = take(sizeof(double) * NN), o_a0 = take(sizeof(double) * acc_size(N, 0)), o_st = take(sizeof(BaState)),
+    const size_t o_sq = take(sizeof(double) * 225), o_Hp = take(sizeof(double) * NN), o_a0 = take(sizeof(double) * acc_size(N, 0)),
                  o_A = take(sizeof(double) * NN), o_b = take(sizeof(double) * N), o_Amm = take(sizeof(double) * mm), o_Vm = take(sizeof(double) * mm), o_wm = take(sizeof(double) * m),
                  o_Ainv = take(sizeof(double) * mm), o_T = take(sizeof(double) * (size_t)n * m), o_Ar = take(sizeof(double) * nn), o_Vr = take(sizeof(double) * nn),
                  o_wr = take(sizeof(double) * n), o_br = take(sizeof(double) * n), o_J0 = take(sizeof(double) * nn), o_r0 = take(sizeof(double) * n), o_sw = take(sizeof(int) * 4),
@@ -1715,6 +1707,11 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     hX[X_EXW + 6] = 1.0; hX[X_IX] = hX[X_IX + 1] = hX[X_IX + 2] = 1.0;
     if (p->para_ex_wheel && p->para_ix_wheel && p->para_td_wheel) { memcpy(hX + X_EXW, p->para_ex_wheel, sizeof(double) * 7); memcpy(hX + X_IX, p->para_ix_wheel, sizeof(double) * 3); hX[X_TDW] = p->para_td_wheel[0]; }
     memcpy(hX + X_FEAT, p->para_feature, sizeof(double) * nfeat);
+    {   // state: linearise into buffer 0 (k_ba_eval mode 0 also forms the sqrt-information of IMU(0->1))
+        BaState* h0 = (BaState*)(hb + o_st);
+        memset(h0, 0, sizeof(BaState));
+        h0->radius = 1e4; h0->mu = 1e-8; h0->need_linearize = 1; h0->cur = 1; h0->first = 1;
+    }
     {
         gf_ba_visual_factor* hv = (gf_ba_visual_factor*)(hb + o_vis);
         std::vector<int> fill(start.begin(), start.end() - 1);
@@ -1748,9 +1745,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     cudaStream_t st = s->s;
     GF_CUDA(cudaEventRecord(s->e0, st));
     GF_CUDA(cudaMemcpyAsync(db, hb, upload_bytes, cudaMemcpyHostToDevice, st));
-    GF_CUDA(cudaMemsetAsync(db + o_a0, 0, al(sizeof(double) * acc_size(N, 0)), st));
-    GF_CUDA(cudaMemsetAsync(db + o_st, 0, sizeof(BaState), st));
-    k_ba_setup<<<d.n_imu + 1, 128, 0, st>>>(d); GF_LAUNCHED();        // sqrt_info of IMU(0->1), Hp = 0, state: linearise into buffer 0
+    GF_CUDA(cudaMemsetAsync(db + o_Hp, 0, al(sizeof(double) * NN) + al(sizeof(double) * acc_size(N, 0)), st));     // H_prior and the accumulator
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
     const int eval_blocks = n_work + d.n_imu + d.n_wheel + (pn ? 1 : 0);
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, sizeof(double) * 2 * (size_t)pn, st>>>(d, 0); GF_LAUNCHED(); }
