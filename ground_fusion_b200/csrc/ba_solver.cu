@@ -1597,7 +1597,10 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
  * The WheelFactor(0->1) joins when the window has wheel factors (its extrinsic / sx / sy / sw / time offset become kept
  * blocks); plane / GNSS factors are not implemented.  out_x0 / out_J / out_r must hold 16*n_frames+19, n*n, n doubles.
  * Returns n (> 0) or a negative error code. */
-int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r, float* device_ms)
+}  // extern "C" (reopened below)
+
+enum { GF_MARG_OLD = 0, GF_MARG_SECOND_NEW = 1 };
+static int marg_run(gf_ba* s, const gf_ba_problem* p, int mode, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r, float* device_ms)
 {
     if (!s || !p || !out || !out_x0 || !out_J || !out_r) return set_err(GF_ERR_INVALID_ARG, "null argument");
     if (p->n_frames < 2 || p->n_frames > GF_BA_MAX_FRAMES) return set_err(GF_ERR_INVALID_ARG, "n_frames out of range");
@@ -1611,10 +1614,19 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     d.F = F; d.nfeat = nfeat; d.lm_dense = 1;
     for (int f = 0; f < MAXF; f++) { d.col_pose[f] = -1; d.col_sb[f] = -1; }
     d.col_ex = d.col_td = d.col_exw = d.col_tdw = -1; d.col_ix[0] = d.col_ix[1] = d.col_ix[2] = -1; d.col_pr = d.col_pz = -1; d.n_plane = 0;
-    d.col_pose[0] = pos; pos += 6;
-    if (use_sb) { d.col_sb[0] = pos; pos += 9; }
+    const bool old_ = mode == GF_MARG_OLD;
+    const int fdrop = old_ ? 0 : F - 2;                        // MARGIN_OLD drops frame 0, MARGIN_SECOND_NEW para_Pose[WINDOW_SIZE - 1]
+    const gf_ba_prior* pr = (p->prior && p->prior->n > 0) ? p->prior : nullptr;
+    if (!old_) {
+        // estimator.cpp:3538-3539: only when the last prior holds para_Pose[WINDOW_SIZE - 1]; otherwise the prior stays as it is
+        bool has = false;
+        if (pr) for (int b = 0; b < pr->n_blocks; b++) if (pr->block_kind[b] == GF_BA_BLOCK_POSE && pr->block_index[b] == fdrop) has = true;
+        if (!has) return 0;
+    }
+    d.col_pose[fdrop] = pos; pos += 6;
+    if (old_ && use_sb) { d.col_sb[0] = pos; pos += 9; }
     std::vector<gf_ba_visual_factor> vis0;
-    for (int v = 0; v < p->n_visual; v++) {
+    for (int v = 0; old_ && v < p->n_visual; v++) {
         const gf_ba_visual_factor& f = p->visual[v];
         if (f.feature < 0 || f.feature >= nfeat || f.imu_i < 0 || f.imu_i >= F || f.imu_j < 0 || f.imu_j >= F) return set_err(GF_ERR_INVALID_ARG, "visual factor index out of range");
         if (f.imu_i != 0) continue;
@@ -1622,8 +1634,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
         vis0.push_back(f);
     }
     const int m = pos;
-    bool used_pose[MAXF] = {}, used_sb[MAXF] = {}, used_ex = false, used_td = false, used_exw = false, used_ix[3] = {false, false, false}, used_tdw = false;
-    const gf_ba_prior* pr = (p->prior && p->prior->n > 0) ? p->prior : nullptr;
+    bool used_pose[MAXF] = {}, used_sb[MAXF] = {}, used_ex = false, used_td = false, used_exw = false, used_ix[3] = {false, false, false}, used_tdw = false, used_pr = false, used_pz = false;
     if (pr) {
         if (pr->n_blocks > 64) return set_err(GF_ERR_CAPACITY, "more than 64 prior blocks");
         for (int b = 0; b < pr->n_blocks; b++) {
@@ -1634,27 +1645,43 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
             else if (k == GF_BA_BLOCK_EX_WHEEL) used_exw = true;
             else if (k >= GF_BA_BLOCK_SX && k <= GF_BA_BLOCK_SW) used_ix[k - GF_BA_BLOCK_SX] = true;
             else if (k == GF_BA_BLOCK_TD_WHEEL) used_tdw = true;
+            else if (k == GF_BA_BLOCK_PLANE_R) used_pr = true;
+            else if (k == GF_BA_BLOCK_PLANE_Z) used_pz = true;
             else return set_err(GF_ERR_INVALID_ARG, "unknown prior block kind");
         }
     }
     const gf_ba_imu_factor* imu01 = nullptr;
-    for (int k = 0; k < p->n_imu; k++) if (p->imu[k].i == 0 && p->imu[k].j == 1 && p->imu[k].sum_dt < 10.0) { imu01 = &p->imu[k]; used_pose[1] = true; used_sb[1] = true; }
+    for (int k = 0; old_ && k < p->n_imu; k++) if (p->imu[k].i == 0 && p->imu[k].j == 1 && p->imu[k].sum_dt < 10.0) { imu01 = &p->imu[k]; used_pose[1] = true; used_sb[1] = true; }
     for (const auto& f : vis0) { used_pose[f.imu_j] = true; used_ex = true; used_td = true; }
     // WheelFactor(pre_integrations_wheel[1]) with para_Pose[0] dropped (estimator.cpp:3367-3377)
     const gf_ba_wheel_factor* wheel01 = nullptr;
     if (p->n_wheel > 0 && (!p->wheel || !p->para_ex_wheel || !p->para_ix_wheel || !p->para_td_wheel)) return set_err(GF_ERR_INVALID_ARG, "wheel factors without their parameter blocks");
-    for (int k = 0; k < p->n_wheel; k++) if (p->wheel[k].i == 0 && p->wheel[k].j == 1 && p->wheel[k].sum_dt < 10.0) { wheel01 = &p->wheel[k]; used_pose[1] = true; used_exw = true; used_ix[0] = used_ix[1] = used_ix[2] = true; used_tdw = true; }
-    if ((used_exw || used_ix[0] || used_ix[1] || used_ix[2] || used_tdw) && (!p->para_ex_wheel || !p->para_ix_wheel || !p->para_td_wheel)) return set_err(GF_ERR_INVALID_ARG, "prior on wheel blocks without the wheel parameter blocks");
-    for (int f = 1; f < F; f++) if (used_pose[f]) { d.col_pose[f] = pos; pos += 6; }
-    for (int f = 1; f < F; f++) if (used_sb[f] && use_sb) { d.col_sb[f] = pos; pos += 9; }
+    for (int k = 0; old_ && k < p->n_wheel; k++) if (p->wheel[k].i == 0 && p->wheel[k].j == 1 && p->wheel[k].sum_dt < 10.0) { wheel01 = &p->wheel[k]; used_pose[1] = true; used_exw = true; used_ix[0] = used_ix[1] = used_ix[2] = true; used_tdw = true; }
+    // PlaneFactor(para_Pose[0], para_Ex_Pose_wheel, para_plane_R, para_plane_Z) with para_Pose[0] dropped (estimator.cpp:3379-3390)
+    bool plane0 = false;
+    for (int k = 0; old_ && k < p->n_plane; k++) if (p->plane_frames && p->plane_frames[k] == 0) plane0 = true;
+    if (plane0) {
+        if (!p->para_ex_wheel || !p->para_plane_R || !p->para_plane_Z) return set_err(GF_ERR_INVALID_ARG, "plane factor without its parameter blocks");
+        used_exw = used_pr = used_pz = true;
+    }
+    if ((used_ix[0] || used_ix[1] || used_ix[2] || used_tdw) && (!p->para_ix_wheel || !p->para_td_wheel)) return set_err(GF_ERR_INVALID_ARG, "prior on wheel blocks without the wheel parameter blocks");
+    if (used_exw && !p->para_ex_wheel) return set_err(GF_ERR_INVALID_ARG, "prior on the wheel extrinsic without para_ex_wheel");
+    if ((used_pr || used_pz) && (!p->para_plane_R || !p->para_plane_Z)) return set_err(GF_ERR_INVALID_ARG, "prior on the plane blocks without para_plane_R / para_plane_Z");
+    for (int f = 0; f < F; f++) if (f != fdrop && used_pose[f]) { d.col_pose[f] = pos; pos += 6; }
+    for (int f = 0; f < F; f++) if (!(old_ && f == 0) && used_sb[f] && use_sb) { d.col_sb[f] = pos; pos += 9; }
     if (used_ex) { d.col_ex = pos; pos += 6; }
     if (used_td) { d.col_td = pos; pos += 1; }
     if (used_exw) { d.col_exw = pos; pos += 6; }
     for (int k = 0; k < 3; k++) if (used_ix[k]) d.col_ix[k] = pos++;
     if (used_tdw) d.col_tdw = pos++;
+    // the plane rotation has 4 columns here: MarginalizationInfo::localSize only knows the 7 -> 6 case (marginalization_factor.h),
+    // PlaneFactor fills the first three (plane_factor.h:95-101), the fourth stays zero
+    if (used_pr) { d.col_pr = pos; pos += 4; }
+    if (used_pz) d.col_pz = pos++;
     const int N = pos, n = N - m;
     if (n <= 0) return set_err(GF_ERR_INVALID_ARG, "nothing is kept by the marginalisation");
-    d.nc = N; d.L = 0; d.n = N; d.n_vis = (int)vis0.size(); d.n_imu = imu01 ? 1 : 0; d.n_wheel = wheel01 ? 1 : 0;
+    d.nc = N; d.L = 0; d.n = N; d.n_vis = (int)vis0.size(); d.n_imu = imu01 ? 1 : 0; d.n_wheel = wheel01 ? 1 : 0; d.n_plane = plane0 ? 1 : 0;
+    d.pr_mask = 0; for (int k = 0; k < 3; k++) d.plane_sinfo[k] = p->plane_sqrt_info[k];
     // ---- visual factors by pose pair (0, j), cut into chunks ----
     std::vector<int> cnt(F, 0), start(F + 1, 0);
     for (const auto& f : vis0) cnt[f.imu_j]++;
@@ -1672,9 +1699,10 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
         for (int b = 0; b < pr->n_blocks; b++) {
             const int kind = pr->block_kind[b], idx = pr->block_index[b];
             d.pkind[b] = kind; d.pindex[b] = idx; d.pidx[b] = pr->block_idx[b]; d.pxoff[b] = (int)px0_len;
-            const int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : 1, ls = gs == 7 ? 6 : gs;
+            const int gs = (kind == GF_BA_BLOCK_POSE || kind == GF_BA_BLOCK_EX_POSE || kind == GF_BA_BLOCK_EX_WHEEL) ? 7 : kind == GF_BA_BLOCK_SPEEDBIAS ? 9 : kind == GF_BA_BLOCK_PLANE_R ? 4 : 1, ls = gs == 7 ? 6 : gs;
             const int lc = kind == GF_BA_BLOCK_POSE ? d.col_pose[idx] : kind == GF_BA_BLOCK_SPEEDBIAS ? d.col_sb[idx] : kind == GF_BA_BLOCK_EX_POSE ? d.col_ex : kind == GF_BA_BLOCK_TD ? d.col_td
-                           : kind == GF_BA_BLOCK_EX_WHEEL ? d.col_exw : kind == GF_BA_BLOCK_TD_WHEEL ? d.col_tdw : d.col_ix[kind - GF_BA_BLOCK_SX];
+                           : kind == GF_BA_BLOCK_EX_WHEEL ? d.col_exw : kind == GF_BA_BLOCK_TD_WHEEL ? d.col_tdw : kind == GF_BA_BLOCK_PLANE_R ? d.col_pr : kind == GF_BA_BLOCK_PLANE_Z ? d.col_pz
+                           : d.col_ix[kind - GF_BA_BLOCK_SX];
             if (lc >= 0) for (int k = 0; k < ls; k++) pcol[pr->block_idx[b] + k] = lc + k;
             px0_len += gs;
         }
@@ -1684,7 +1712,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += al(bytes); return o; };
     const size_t nv = vis0.size();
-    const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (nv ? nv : 1)), o_imu = take(sizeof(gf_ba_imu_factor)), o_whl = take(sizeof(gf_ba_wheel_factor)),
+    const size_t o_X = take(sizeof(double) * (X_FEAT + nfeat)), o_vis = take(sizeof(gf_ba_visual_factor) * (nv ? nv : 1)), o_imu = take(sizeof(gf_ba_imu_factor)), o_whl = take(sizeof(gf_ba_wheel_factor)), o_plf = take(sizeof(int) * 4),
                  o_ps = take(sizeof(int) * (n_work + 1)), o_pij = take(sizeof(int) * 2 * (size_t)(n_work > 0 ? n_work : 1)), o_cf = take(sizeof(int) * (size_t)(nfeat > 0 ? nfeat : 1)),
                  o_pJ = take(sizeof(double) * (size_t)pn * pn), o_pr0 = take(sizeof(double) * pn), o_px0 = take(sizeof(double) * px0_len), o_pcol = take(sizeof(int) * (size_t)(pn > 0 ? pn : 1));
     const size_t o_st = take(sizeof(BaState));
@@ -1705,7 +1733,11 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     memcpy(hX + X_EX, p->para_ex_pose, sizeof(double) * 7);
     hX[X_TD] = p->para_td[0];
     hX[X_EXW + 6] = 1.0; hX[X_IX] = hX[X_IX + 1] = hX[X_IX + 2] = 1.0;
-    if (p->para_ex_wheel && p->para_ix_wheel && p->para_td_wheel) { memcpy(hX + X_EXW, p->para_ex_wheel, sizeof(double) * 7); memcpy(hX + X_IX, p->para_ix_wheel, sizeof(double) * 3); hX[X_TDW] = p->para_td_wheel[0]; }
+    if (p->para_ex_wheel) memcpy(hX + X_EXW, p->para_ex_wheel, sizeof(double) * 7);
+    if (p->para_ix_wheel && p->para_td_wheel) { memcpy(hX + X_IX, p->para_ix_wheel, sizeof(double) * 3); hX[X_TDW] = p->para_td_wheel[0]; }
+    hX[X_PR + 3] = 1.0;
+    if (p->para_plane_R && p->para_plane_Z) { memcpy(hX + X_PR, p->para_plane_R, sizeof(double) * 4); hX[X_PZ] = p->para_plane_Z[0]; }
+    ((int*)(hb + o_plf))[0] = 0;                               // the one PlaneFactor of the marginalisation sits on frame 0
     memcpy(hX + X_FEAT, p->para_feature, sizeof(double) * nfeat);
     {   // state: linearise into buffer 0 (k_ba_eval mode 0 also forms the sqrt-information of IMU(0->1))
         BaState* h0 = (BaState*)(hb + o_st);
@@ -1731,6 +1763,7 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     d.X = (double*)(db + o_X); d.Xc = d.X;
     d.vis = (const gf_ba_visual_factor*)(db + o_vis); d.pair_start = (const int*)(db + o_ps); d.pair_ij = (const int*)(db + o_pij);
     d.imu = (const gf_ba_imu_factor*)(db + o_imu); d.imu_sqrt = (double*)(db + o_sq); d.wheel = (const gf_ba_wheel_factor*)(db + o_whl);
+    d.plane_frames = (const int*)(db + o_plf);
     d.col_feat = (const int*)(db + o_cf);
     d.pJ = (const double*)(db + o_pJ); d.pr0 = (const double*)(db + o_pr0); d.px0 = (const double*)(db + o_px0); d.pcol = (const int*)(db + o_pcol);
     d.Hp = (double*)(db + o_Hp); d.acc[0] = (double*)(db + o_a0); d.acc[1] = d.acc[0];
@@ -1747,11 +1780,11 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     GF_CUDA(cudaMemcpyAsync(db, hb, upload_bytes, cudaMemcpyHostToDevice, st));
     GF_CUDA(cudaMemsetAsync(db + o_Hp, 0, al(sizeof(double) * NN) + al(sizeof(double) * acc_size(N, 0)), st));     // H_prior and the accumulator
     if (pn) { k_ba_prior_hessian<<<(pn * pn + 255) / 256, 256, 0, st>>>(d); GF_LAUNCHED(); }
-    const int eval_blocks = n_work + d.n_imu + d.n_wheel + (pn ? 1 : 0);
+    const int eval_blocks = n_work + d.n_imu + d.n_wheel + d.n_plane + (pn ? 1 : 0);
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, sizeof(double) * 2 * (size_t)pn, st>>>(d, 0); GF_LAUNCHED(); }
     k_marg_pack<<<(int)((NN + 255) / 256), 256, 0, st>>>(q); GF_LAUNCHED();
     auto jac_smem = [](int nn_, bool in_smem) { int hp = ((nn_ + 1) & ~1) / 2; size_t b = (size_t)hp * (2 * sizeof(double) + 2 * sizeof(int)) + 8; return b + (in_smem ? 2 * sizeof(double) * (size_t)nn_ * nn_ : 0); };
-    const int cdim = use_sb ? 15 : 6, Rdim = cdim + n;
+    const int cdim = (old_ && use_sb) ? 15 : 6, Rdim = cdim + n;
     int* d_flag = (int*)(db + o_sw) + 2;
     bool generic = n > 127;                                   // k_marg_c_elim's shared buffer
     if (!generic) {
@@ -1788,19 +1821,39 @@ int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, do
     if (device_ms) GF_CUDA(cudaEventElapsedTime(device_ms, s->e0, s->e1));
     memcpy(out_J, hb + o_J0, sizeof(double) * nn);
     memcpy(out_r, hb + o_r0, sizeof(double) * n);
-    // ---- kept blocks after addr_shift ----
+    // ---- kept blocks after addr_shift (estimator.cpp:3500-3534 / 3583-3621): MARGIN_OLD shifts every frame down by one,
+    // MARGIN_SECOND_NEW moves frame F-1 into the slot of the dropped frame F-2 ----
     memset(out, 0, sizeof(*out));
     out->n = n;
     int nb = 0; double* xp = out_x0;
-    for (int f = 1; f < F; f++) if (d.col_pose[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_POSE; out->block_index[nb] = f - 1; out->block_idx[nb] = d.col_pose[f] - m; memcpy(xp, p->para_pose + 7 * f, 56); xp += 7; nb++; }
-    for (int f = 1; f < F; f++) if (d.col_sb[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SPEEDBIAS; out->block_index[nb] = f - 1; out->block_idx[nb] = d.col_sb[f] - m; memcpy(xp, p->para_speed_bias + 9 * f, 72); xp += 9; nb++; }
+    auto shifted = [&](int f) { return old_ ? f - 1 : (f == F - 1 ? F - 2 : f); };
+    for (int f = 0; f < F; f++) if (f != fdrop && d.col_pose[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_POSE; out->block_index[nb] = shifted(f); out->block_idx[nb] = d.col_pose[f] - m; memcpy(xp, p->para_pose + 7 * f, 56); xp += 7; nb++; }
+    for (int f = 0; f < F; f++) if (!(old_ && f == 0) && d.col_sb[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SPEEDBIAS; out->block_index[nb] = shifted(f); out->block_idx[nb] = d.col_sb[f] - m; memcpy(xp, p->para_speed_bias + 9 * f, 72); xp += 9; nb++; }
     if (d.col_ex >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_POSE; out->block_index[nb] = 0; out->block_idx[nb] = d.col_ex - m; memcpy(xp, p->para_ex_pose, 56); xp += 7; nb++; }
     if (d.col_td >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD; out->block_index[nb] = 0; out->block_idx[nb] = d.col_td - m; xp[0] = p->para_td[0]; xp += 1; nb++; }
     if (d.col_exw >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_WHEEL; out->block_index[nb] = 0; out->block_idx[nb] = d.col_exw - m; memcpy(xp, p->para_ex_wheel, 56); xp += 7; nb++; }
     for (int k = 0; k < 3; k++) if (d.col_ix[k] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SX + k; out->block_index[nb] = 0; out->block_idx[nb] = d.col_ix[k] - m; xp[0] = p->para_ix_wheel[k]; xp += 1; nb++; }
     if (d.col_tdw >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD_WHEEL; out->block_index[nb] = 0; out->block_idx[nb] = d.col_tdw - m; xp[0] = p->para_td_wheel[0]; xp += 1; nb++; }
+    if (d.col_pr >= 0) { out->block_kind[nb] = GF_BA_BLOCK_PLANE_R; out->block_index[nb] = 0; out->block_idx[nb] = d.col_pr - m; memcpy(xp, p->para_plane_R, 32); xp += 4; nb++; }
+    if (d.col_pz >= 0) { out->block_kind[nb] = GF_BA_BLOCK_PLANE_Z; out->block_index[nb] = 0; out->block_idx[nb] = d.col_pz - m; xp[0] = p->para_plane_Z[0]; xp += 1; nb++; }
     out->n_blocks = nb; out->x0 = out_x0; out->linearized_jacobians = out_J; out->linearized_residuals = out_r;
     return n;
+}
+
+extern "C" {
+
+int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r, float* device_ms)
+{
+    return marg_run(s, p, GF_MARG_OLD, out, out_x0, out_J, out_r, device_ms);
+}
+
+/* MARGIN_SECOND_NEW (estimator.cpp:3536-3631): the only factor is the last prior, evaluated at the current state (r = r0 + J0 dx),
+ * para_Pose[WINDOW_SIZE - 1] (frame n_frames - 2) is marginalised by the same eigen-truncated Schur complement and the result is
+ * re-factored into J0 / r0; frame n_frames - 1 takes the index of the dropped frame.  Returns n > 0, 0 when the prior does not
+ * hold that pose (the reference then keeps the prior untouched), or a negative error code. */
+int gf_ba_marginalize_second_new(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r, float* device_ms)
+{
+    return marg_run(s, p, GF_MARG_SECOND_NEW, out, out_x0, out_J, out_r, device_ms);
 }
 
 /* Estimator::double2vector (reference estimator.cpp:2440-2494): after the solve the whole window is rotated about z and

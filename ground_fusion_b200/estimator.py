@@ -57,25 +57,34 @@ class BundleAdjuster:
         check(self.L.gf_ba_solve(self._h, ctypes.byref(p), ctypes.byref(s)))
         return s.as_dict()
 
-    def marginalize_old(self, problem):
-        """MARGIN_OLD on the GPU (estimator.cpp:3334-3535): returns the ba_problem.Prior for the next window (block indices
-        already shifted by one frame).  last_marg_ms holds the CUDA-event time."""
+    def _marginalize(self, problem, fn_name):
         from .ba_problem import Prior
         dp = ctypes.POINTER(ctypes.c_double)
-        self.L.gf_ba_marginalize_old.argtypes = [ctypes.c_void_p, ctypes.POINTER(BaProblem), ctypes.POINTER(BaPrior), dp, dp, dp,
-                                                 ctypes.POINTER(ctypes.c_float)]
+        fn = getattr(self.L, fn_name)
+        fn.argtypes = [ctypes.c_void_p, ctypes.POINTER(BaProblem), ctypes.POINTER(BaPrior), dp, dp, dp, ctypes.POINTER(ctypes.c_float)]
         p = problem.struct()
         cap = 16 * problem.n_frames + 24
         x0 = np.zeros(cap); J = np.zeros(cap * cap); r = np.zeros(cap)
         out = BaPrior(); ms = ctypes.c_float(0)
-        n = self.L.gf_ba_marginalize_old(self._h, ctypes.byref(p), ctypes.byref(out), x0.ctypes.data_as(dp), J.ctypes.data_as(dp),
-                                         r.ctypes.data_as(dp), ctypes.byref(ms))
-        if n <= 0:
-            check(n if n < 0 else -1)
+        n = fn(self._h, ctypes.byref(p), ctypes.byref(out), x0.ctypes.data_as(dp), J.ctypes.data_as(dp), r.ctypes.data_as(dp), ctypes.byref(ms))
+        if n < 0:
+            check(n)
+        if n == 0:
+            return None
         self.last_marg_ms = float(ms.value)
         nb = out.n_blocks
         return Prior(list(out.block_kind)[:nb], list(out.block_index)[:nb], list(out.block_idx)[:nb], x0.copy(),
                      J[:n * n].reshape(n, n).copy(), r[:n].copy())
+
+    def marginalize_old(self, problem):
+        """MARGIN_OLD on the GPU (estimator.cpp:3334-3535): returns the ba_problem.Prior for the next window (block indices
+        already shifted by one frame).  last_marg_ms holds the CUDA-event time."""
+        return self._marginalize(problem, "gf_ba_marginalize_old")
+
+    def marginalize_second_new(self, problem):
+        """MARGIN_SECOND_NEW on the GPU (estimator.cpp:3536-3631): the last prior with para_Pose[WINDOW_SIZE - 1] marginalised;
+        None when the prior does not hold that pose (the reference then keeps the prior as it is)."""
+        return self._marginalize(problem, "gf_ba_marginalize_second_new")
 
     def solve_struct(self, p_struct):
         """Same, for a pre-built ctypes gf_ba_problem (avoids rebuilding it in timing loops)."""

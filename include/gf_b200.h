@@ -306,15 +306,25 @@ int gf_ba_debug_profile(gf_ba* s, long long* out32);
 /* MARGIN_OLD: the marginalisation at the end of Estimator::optimization() (estimator.cpp:3334-3535) with
  * MarginalizationInfo::{preMarginalize, marginalize} (factor/marginalization_factor.cpp:115-308) on the GPU.
  * Input: the window as it stands after the solve (same descriptor as gf_ba_solve; the constancy flags are ignored, as
- * the reference's MarginalizationInfo ignores SetParameterBlockConstant).  Output: the prior for the NEXT window --
- * kept blocks ordered pose[1..], speedbias[1..], ex_pose, td with frame indices already shifted by one, their
- * linearisation points, J0 = sqrt(S) V^T (n x n row-major) and r0 = sqrt(S^-1) V^T b.
- *   out_x0 / out_J / out_r: caller buffers of 16*n_frames+19, n*n, n doubles (n <= 16*n_frames+17); `out` points into them.
- *   With wheel factors the WheelFactor(0->1) joins and the wheel extrinsic, sx, sy, sw, wheel time offset follow as kept blocks.
+ * the reference's MarginalizationInfo ignores SetParameterBlockConstant).  Factors: the last prior, IMUFactor(0->1),
+ * WheelFactor(0->1) (when the window has wheel factors), PlaneFactor on frame 0 (when plane_frames lists frame 0) and every
+ * visual factor whose landmark starts in frame 0.  Output: the prior for the NEXT window -- kept blocks ordered pose[1..],
+ * speedbias[1..], ex_pose, td, wheel extrinsic, sx, sy, sw, wheel time offset, plane rotation (4 columns: MarginalizationInfo
+ * only knows the 7 -> 6 local size), plane height, with frame indices already shifted by one, their linearisation points,
+ * J0 = sqrt(S) V^T (n x n row-major) and r0 = sqrt(S^-1) V^T b.
+ *   out_x0 / out_J / out_r: caller buffers of 16*n_frames+24, n*n, n doubles (n <= 16*n_frames+22); `out` points into them.
  *   device_ms: nullable, CUDA-event time.
- * Returns n > 0, or a negative gf error code.  Plane / GNSS factors of frame 0 are not part of the prior. */
+ * Returns n > 0, or a negative gf error code.  GNSS factors are not implemented (gnss_comm is not vendored). */
 int gf_ba_marginalize_old(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r,
                           float* device_ms);
+
+/* MARGIN_SECOND_NEW (estimator.cpp:3536-3631): the only factor is the last prior evaluated at the current state; para_Pose
+ * [WINDOW_SIZE - 1] (frame n_frames - 2 of the descriptor) is marginalised by the same eigen-truncated Schur complement
+ * (preMarginalize + marginalize) and frame n_frames - 1 takes its index (addr_shift, estimator.cpp:3583-3621).  Same buffers
+ * as gf_ba_marginalize_old.  Returns n > 0, 0 when the prior does not hold that pose (the reference then keeps the prior
+ * unchanged: estimator.cpp:3538-3539), or a negative error code. */
+int gf_ba_marginalize_second_new(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r,
+                                 float* device_ms);
 
 /* Estimator::double2vector (estimator.cpp:2440-2494), the state part: host-only glue that maps the solved para_* arrays
  * back to Rs / Ps / Vs, rotating the window about z and shifting it so that frame 0 keeps the yaw and position it had

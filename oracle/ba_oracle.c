@@ -1341,7 +1341,7 @@ GFO void gfo_ba_plus(const gf_ba_problem* p, const double* delta)
  * order-independent and those are what the tests compare).  After addr_shift the kept pose/speedbias indices are
  * decremented by one.  With wheel factors the WheelFactor(0->1) joins (pose 0 dropped) and the wheel extrinsic, sx, sy,
  * sw and the wheel time offset follow as kept blocks.  out_x0 / out_J / out_r must hold 16F+19, n*n, n doubles. */
-GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r)
+static int marg_run(const gf_ba_problem* p, int second_new, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r)
 {
     const int F = p->n_frames;
     const int use_sb = (p->para_speed_bias != NULL) && !p->pose0_const;
@@ -1350,13 +1350,19 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
     int* lm_col = (int*)malloc(sizeof(int) * (p->n_features + 1));
     for (int k = 0; k < p->n_features; k++) lm_col[k] = -1;
     int pos = 0;
+    const int old_ = !second_new, fdrop = old_ ? 0 : F - 2;     /* MARGIN_SECOND_NEW drops para_Pose[WINDOW_SIZE - 1] (estimator.cpp:3549-3551) */
+    if (!old_) {
+        int has = 0;
+        if (p->prior && p->prior->n > 0) for (int b = 0; b < p->prior->n_blocks; b++) if (p->prior->block_kind[b] == GF_BA_BLOCK_POSE && p->prior->block_index[b] == fdrop) has = 1;
+        if (!has) { free(lm_col); free(s.feat); return 0; }
+    }
     const int col_p0 = pos; pos += 6;
     int col_sb0 = -1;
-    if (use_sb) { col_sb0 = pos; pos += 9; }
-    for (int v = 0; v < p->n_visual; v++) if (p->visual[v].imu_i == 0 && lm_col[p->visual[v].feature] < 0) lm_col[p->visual[v].feature] = pos++;
+    if (old_ && use_sb) { col_sb0 = pos; pos += 9; }
+    for (int v = 0; old_ && v < p->n_visual; v++) if (p->visual[v].imu_i == 0 && lm_col[p->visual[v].feature] < 0) lm_col[p->visual[v].feature] = pos++;
     const int m = pos;
     /* kept blocks: every other block the factors touch */
-    int used_pose[GF_BA_MAX_FRAMES] = {0}, used_sb[GF_BA_MAX_FRAMES] = {0}, used_ex = 0, used_td = 0, used_exw = 0, used_ix[3] = {0, 0, 0}, used_tdw = 0;
+    int used_pose[GF_BA_MAX_FRAMES] = {0}, used_sb[GF_BA_MAX_FRAMES] = {0}, used_ex = 0, used_td = 0, used_exw = 0, used_ix[3] = {0, 0, 0}, used_tdw = 0, used_pr = 0, used_pz = 0;
     if (p->prior && p->prior->n > 0)
         for (int b = 0; b < p->prior->n_blocks; b++) {
             int k = p->prior->block_kind[b], i = p->prior->block_index[b];
@@ -1364,22 +1370,31 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
             else if (k == GF_BA_BLOCK_EX_POSE) used_ex = 1; else if (k == GF_BA_BLOCK_TD) used_td = 1;
             else if (k == GF_BA_BLOCK_EX_WHEEL) used_exw = 1; else if (k >= GF_BA_BLOCK_SX && k <= GF_BA_BLOCK_SW) used_ix[k - GF_BA_BLOCK_SX] = 1;
             else if (k == GF_BA_BLOCK_TD_WHEEL) used_tdw = 1;
+            else if (k == GF_BA_BLOCK_PLANE_R) used_pr = 1; else if (k == GF_BA_BLOCK_PLANE_Z) used_pz = 1;
         }
     int have_imu01 = 0; const gf_ba_imu_factor* imu01 = NULL;
-    for (int k = 0; k < p->n_imu; k++) if (p->imu[k].i == 0 && p->imu[k].j == 1 && p->imu[k].sum_dt < 10.0) { have_imu01 = 1; imu01 = &p->imu[k]; used_pose[1] = 1; used_sb[1] = 1; }
-    for (int v = 0; v < p->n_visual; v++) if (p->visual[v].imu_i == 0) { used_pose[p->visual[v].imu_j] = 1; used_ex = 1; used_td = 1; }
+    for (int k = 0; old_ && k < p->n_imu; k++) if (p->imu[k].i == 0 && p->imu[k].j == 1 && p->imu[k].sum_dt < 10.0) { have_imu01 = 1; imu01 = &p->imu[k]; used_pose[1] = 1; used_sb[1] = 1; }
+    for (int v = 0; old_ && v < p->n_visual; v++) if (p->visual[v].imu_i == 0) { used_pose[p->visual[v].imu_j] = 1; used_ex = 1; used_td = 1; }
     /* WheelFactor(pre_integrations_wheel[1]) with para_Pose[0] dropped (estimator.cpp:3367-3377) */
     const gf_ba_wheel_factor* wheel01 = NULL;
-    for (int k = 0; k < p->n_wheel; k++) if (p->wheel[k].i == 0 && p->wheel[k].j == 1 && p->wheel[k].sum_dt < 10.0) { wheel01 = &p->wheel[k]; used_pose[1] = 1; used_exw = 1; used_ix[0] = used_ix[1] = used_ix[2] = 1; used_tdw = 1; }
-    int col_pose[GF_BA_MAX_FRAMES], col_sb[GF_BA_MAX_FRAMES], col_ex = -1, col_td = -1, col_exw = -1, col_ix[3] = {-1, -1, -1}, col_tdw = -1;
-    col_pose[0] = col_p0; col_sb[0] = col_sb0;
-    for (int f = 1; f < F; f++) { col_pose[f] = -1; if (used_pose[f]) { col_pose[f] = pos; pos += 6; } }
-    for (int f = 1; f < F; f++) { col_sb[f] = -1; if (used_sb[f] && use_sb) { col_sb[f] = pos; pos += 9; } }
+    for (int k = 0; old_ && k < p->n_wheel; k++) if (p->wheel[k].i == 0 && p->wheel[k].j == 1 && p->wheel[k].sum_dt < 10.0) { wheel01 = &p->wheel[k]; used_pose[1] = 1; used_exw = 1; used_ix[0] = used_ix[1] = used_ix[2] = 1; used_tdw = 1; }
+    /* PlaneFactor(para_Pose[0], para_Ex_Pose_wheel, para_plane_R, para_plane_Z), para_Pose[0] dropped (estimator.cpp:3379-3390) */
+    int plane0 = 0;
+    for (int k = 0; old_ && k < p->n_plane; k++) if (p->plane_frames[k] == 0) plane0 = 1;
+    if (plane0) { used_exw = 1; used_pr = 1; used_pz = 1; }
+    int col_pose[GF_BA_MAX_FRAMES], col_sb[GF_BA_MAX_FRAMES], col_ex = -1, col_td = -1, col_exw = -1, col_ix[3] = {-1, -1, -1}, col_tdw = -1, col_pr = -1, col_pz = -1;
+    for (int f = 0; f < F; f++) { col_pose[f] = -1; col_sb[f] = -1; }
+    col_pose[fdrop] = col_p0; if (old_) col_sb[0] = col_sb0;
+    for (int f = 0; f < F; f++) if (f != fdrop && used_pose[f]) { col_pose[f] = pos; pos += 6; }
+    for (int f = 0; f < F; f++) if (!(old_ && f == 0) && used_sb[f] && use_sb) { col_sb[f] = pos; pos += 9; }
     if (used_ex) { col_ex = pos; pos += 6; }
     if (used_td) { col_td = pos; pos += 1; }
     if (used_exw) { col_exw = pos; pos += 6; }
     for (int k = 0; k < 3; k++) if (used_ix[k]) col_ix[k] = pos++;
     if (used_tdw) col_tdw = pos++;
+    /* the plane rotation keeps its 4 global columns: MarginalizationInfo::localSize only maps 7 -> 6 (marginalization_factor.h) */
+    if (used_pr) { col_pr = pos; pos += 4; }
+    if (used_pz) col_pz = pos++;
     const int N = pos, n = N - m;
     double* A = (double*)calloc((size_t)N * N + 1, 8);
     double* bvec = (double*)calloc(N + 1, 8);
@@ -1401,7 +1416,7 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
         for (int a = 0; a < pr->n_blocks; a++) {
             int ka = pr->block_kind[a], ia = pr->block_index[a];
 #define MARG_COL(k_, i_) ((k_) == GF_BA_BLOCK_POSE ? col_pose[i_] : (k_) == GF_BA_BLOCK_SPEEDBIAS ? col_sb[i_] : (k_) == GF_BA_BLOCK_EX_POSE ? col_ex : (k_) == GF_BA_BLOCK_TD ? col_td : \
-                          (k_) == GF_BA_BLOCK_EX_WHEEL ? col_exw : (k_) == GF_BA_BLOCK_TD_WHEEL ? col_tdw : col_ix[(k_) - GF_BA_BLOCK_SX])
+                          (k_) == GF_BA_BLOCK_EX_WHEEL ? col_exw : (k_) == GF_BA_BLOCK_TD_WHEEL ? col_tdw : (k_) == GF_BA_BLOCK_PLANE_R ? col_pr : (k_) == GF_BA_BLOCK_PLANE_Z ? col_pz : col_ix[(k_) - GF_BA_BLOCK_SX])
             int ca = MARG_COL(ka, ia);
             int sa = block_global_size(ka); if (sa == 7) sa = 6;
             for (int b2 = 0; b2 < pr->n_blocks; b2++) {
@@ -1429,7 +1444,14 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
         double* Js[7] = {J0, J1, J2, Jsx, Jsy, Jsw, Jtw};
         ADD_BLOCKS(6, res, 7, cols, sizes, lds, Js)
     }
-    for (int v = 0; v < p->n_visual; v++) {
+    if (plane0) {
+        double res[3], J0[21], J1[21], J2[12], J3[3];
+        gfo_eval_plane(s.pose[0], s.exw, s.pr, s.pz, p->plane_sqrt_info, res, J0, J1, J2, J3);
+        int cols[4] = {col_pose[0], col_exw, col_pr, col_pz}, sizes[4] = {6, 6, 4, 1}, lds[4] = {7, 7, 4, 1};
+        double* Js[4] = {J0, J1, J2, J3};
+        ADD_BLOCKS(3, res, 4, cols, sizes, lds, Js)
+    }
+    for (int v = 0; old_ && v < p->n_visual; v++) {
         const gf_ba_visual_factor* f = &p->visual[v];
         if (f->imu_i != 0) continue;
         double res[2], Ji[14], Jj[14], Jex[14], Jf[2], Jtd[2];
@@ -1467,18 +1489,32 @@ GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double*
         for (int i = 0; i < n; i++) { out_J[(size_t)k * n + i] = ss * V[(size_t)i * n + k]; vb += V[(size_t)i * n + k] * br[i]; }
         out_r[k] = sis * vb;
     }
-    /* kept blocks after addr_shift (estimator.cpp:3500-3534) */
+    /* kept blocks after addr_shift (estimator.cpp:3500-3534 / 3583-3621): MARGIN_OLD shifts every frame down by one,
+     * MARGIN_SECOND_NEW moves frame F-1 into the slot of the dropped frame F-2 */
     memset(out, 0, sizeof(*out));
     out->n = n;
     int nb = 0; double* xp = out_x0;
-    for (int f = 1; f < F; f++) if (col_pose[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_POSE; out->block_index[nb] = f - 1; out->block_idx[nb] = col_pose[f] - m; memcpy(xp, s.pose[f], 56); xp += 7; nb++; }
-    for (int f = 1; f < F; f++) if (col_sb[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SPEEDBIAS; out->block_index[nb] = f - 1; out->block_idx[nb] = col_sb[f] - m; memcpy(xp, s.sb[f], 72); xp += 9; nb++; }
+#define SHIFTED(f_) (old_ ? (f_) - 1 : ((f_) == F - 1 ? F - 2 : (f_)))
+    for (int f = 0; f < F; f++) if (f != fdrop && col_pose[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_POSE; out->block_index[nb] = SHIFTED(f); out->block_idx[nb] = col_pose[f] - m; memcpy(xp, s.pose[f], 56); xp += 7; nb++; }
+    for (int f = 0; f < F; f++) if (!(old_ && f == 0) && col_sb[f] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SPEEDBIAS; out->block_index[nb] = SHIFTED(f); out->block_idx[nb] = col_sb[f] - m; memcpy(xp, s.sb[f], 72); xp += 9; nb++; }
     if (col_ex >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_POSE; out->block_index[nb] = 0; out->block_idx[nb] = col_ex - m; memcpy(xp, s.ex, 56); xp += 7; nb++; }
     if (col_td >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD; out->block_index[nb] = 0; out->block_idx[nb] = col_td - m; xp[0] = s.td; xp += 1; nb++; }
     if (col_exw >= 0) { out->block_kind[nb] = GF_BA_BLOCK_EX_WHEEL; out->block_index[nb] = 0; out->block_idx[nb] = col_exw - m; memcpy(xp, s.exw, 56); xp += 7; nb++; }
     for (int k = 0; k < 3; k++) if (col_ix[k] >= 0) { out->block_kind[nb] = GF_BA_BLOCK_SX + k; out->block_index[nb] = 0; out->block_idx[nb] = col_ix[k] - m; xp[0] = s.ix[k]; xp += 1; nb++; }
     if (col_tdw >= 0) { out->block_kind[nb] = GF_BA_BLOCK_TD_WHEEL; out->block_index[nb] = 0; out->block_idx[nb] = col_tdw - m; xp[0] = s.tdw; xp += 1; nb++; }
+    if (col_pr >= 0) { out->block_kind[nb] = GF_BA_BLOCK_PLANE_R; out->block_index[nb] = 0; out->block_idx[nb] = col_pr - m; memcpy(xp, s.pr, 32); xp += 4; nb++; }
+    if (col_pz >= 0) { out->block_kind[nb] = GF_BA_BLOCK_PLANE_Z; out->block_index[nb] = 0; out->block_idx[nb] = col_pz - m; xp[0] = s.pz; xp += 1; nb++; }
     out->n_blocks = nb; out->x0 = out_x0; out->linearized_jacobians = out_J; out->linearized_residuals = out_r;
     free(lm_col); free(A); free(bvec); free(Amm); free(w); free(V); free(Ainv); free(T); free(Ar); free(br); free(s.feat);
     return n;
+}
+GFO int gfo_ba_marginalize_old(const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r)
+{
+    return marg_run(p, 0, out, out_x0, out_J, out_r);
+}
+/* MARGIN_SECOND_NEW (estimator.cpp:3536-3631): the last prior is the only factor (MarginalizationFactor evaluated at the current
+ * state, no loss function), para_Pose[WINDOW_SIZE - 1] is marginalised; returns 0 when the prior does not hold that pose. */
+GFO int gfo_ba_marginalize_second_new(const gf_ba_problem* p, gf_ba_prior* out, double* out_x0, double* out_J, double* out_r)
+{
+    return marg_run(p, 1, out, out_x0, out_J, out_r);
 }

@@ -88,6 +88,23 @@ def marginalize_old(pb):
     return Prior(list(out.block_kind)[:nb], list(out.block_index)[:nb], list(out.block_idx)[:nb], x0.copy(), J[:n * n].reshape(n, n).copy(), r[:n].copy())
 
 
+def marginalize_second_new(pb):
+    """MARGIN_SECOND_NEW (estimator.cpp:3536-3631): the last prior with para_Pose[WINDOW_SIZE - 1] (frame n_frames - 2)
+    marginalised; None when the prior does not hold that pose (the reference then leaves the prior untouched)."""
+    p = pb.struct()
+    F = pb.n_frames
+    cap = 16 * F + 24
+    x0 = np.zeros(cap); J = np.zeros(cap * cap); r = np.zeros(cap)
+    out = BaPrior()
+    n = lib().gfo_ba_marginalize_second_new(ctypes.byref(p), ctypes.byref(out), x0.ctypes.data_as(_dp), J.ctypes.data_as(_dp), r.ctypes.data_as(_dp))
+    if n < 0:
+        raise RuntimeError("marginalisation failed: %d" % n)
+    if n == 0:
+        return None
+    nb = out.n_blocks
+    return Prior(list(out.block_kind)[:nb], list(out.block_index)[:nb], list(out.block_idx)[:nb], x0.copy(), J[:n * n].reshape(n, n).copy(), r[:n].copy())
+
+
 def set_tolerances(function=1e-6, gradient=1e-10, parameter=1e-8):
     lib().gfo_ba_set_tolerances(function, gradient, parameter)
 

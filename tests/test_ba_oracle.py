@@ -282,6 +282,91 @@ def test_marginalization_with_wheel_factor_keeps_the_wheel_blocks():
     assert s["final_cost"] < c0 and np.isfinite(s["final_cost"])
 
 
+def _block_cols(prior):
+    """{(kind, index): [prior columns]} with the local sizes MarginalizationInfo uses (7 -> 6, plane rotation 4)."""
+    size = lambda k: 6 if k in (0, 2, 4) else 9 if k == 1 else 4 if k == 10 else 1
+    return {(k, i): list(range(c, c + size(k))) for k, i, c in zip(prior.kinds, prior.indices, prior.idx)}
+
+
+def test_margin_second_new_is_the_schur_complement_of_the_prior():
+    """MARGIN_SECOND_NEW (estimator.cpp:3536-3631): the last prior is the only factor; with the state at the prior's
+    linearisation point (dx = 0, r = r0) the new prior must be the Schur complement of J0^T J0 / J0^T r0 with respect to
+    para_Pose[WINDOW_SIZE - 1], with frame F-1 re-indexed to F-2."""
+    pb, _ = make_window(seed=8)
+    O.solve(pb)
+    pr = O.marginalize_old(pb)                     # holds poses 0..9 of the next window, speed-bias 0, ex, td
+    nxt, _ = make_window(seed=58)
+    nxt.prior = pr
+    sizes = {0: 7, 1: 9, 2: 7, 3: 1}
+    off = 0
+    for k, i in zip(pr.kinds, pr.indices):          # put the state on the linearisation point
+        if k == 0: nxt.para_pose[i] = pr.x0[off:off + 7]
+        elif k == 1: nxt.para_speed_bias[i] = pr.x0[off:off + 9]
+        elif k == 2: nxt.para_ex_pose[:] = pr.x0[off:off + 7]
+        elif k == 3: nxt.para_td[0] = pr.x0[off]
+        off += sizes[k]
+    new = O.marginalize_second_new(nxt)
+    F = nxt.n_frames
+    assert (0, F - 2) in _block_cols(pr)
+    old_cols, new_cols = _block_cols(pr), _block_cols(new)
+    assert set(new_cols) == {(k, (F - 2 if (k in (0, 1) and i == F - 1) else i)) for (k, i) in old_cols if (k, i) != (0, F - 2)}
+    H, b = pr.J.T @ pr.J, pr.J.T @ pr.r
+    m = old_cols[(0, F - 2)]
+    keep, keep_new = [], []
+    for (k, i), c in new_cols.items():
+        src = (k, F - 1) if (k in (0, 1) and i == F - 2) else (k, i)
+        keep += old_cols[src]; keep_new += c
+    w, V = np.linalg.eigh(0.5 * (H[np.ix_(m, m)] + H[np.ix_(m, m)].T))
+    Ainv = (V * np.where(w > 1e-8, 1 / np.where(w > 1e-8, w, 1), 0)) @ V.T
+    A = H[np.ix_(keep, keep)] - H[np.ix_(keep, m)] @ Ainv @ H[np.ix_(m, keep)]
+    bb = b[keep] - H[np.ix_(keep, m)] @ Ainv @ b[m]
+    Hn, bn = (new.J.T @ new.J)[np.ix_(keep_new, keep_new)], (new.J.T @ new.r)[keep_new]
+    wv, Vv = np.linalg.eigh(0.5 * (A + A.T)); kv = wv > 1e-8      # eigenvalues <= 1e-8 are dropped (marginalization_factor.cpp:294-302)
+    assert np.allclose(Hn, (Vv[:, kv] * wv[kv]) @ Vv[:, kv].T, rtol=1e-6, atol=1e-7 * np.abs(A).max())
+    assert np.allclose(bn, Vv[:, kv] @ (Vv[:, kv].T @ bb), rtol=1e-6, atol=1e-7 * np.abs(bb).max())
+    # the linearisation point of the kept blocks is the current state
+    assert np.array_equal(new.x0[:7], nxt.para_pose[0])
+    # without that pose in the prior the reference leaves the prior alone
+    nxt2, _ = make_window(seed=58)
+    keep_b = [j for j, (k, i) in enumerate(zip(pr.kinds, pr.indices)) if not (k == 0 and i == F - 2)]
+    from ground_fusion_b200.ba_problem import Prior
+    nxt2.prior = Prior([pr.kinds[j] for j in keep_b], [pr.indices[j] for j in keep_b], [pr.idx[j] for j in keep_b], pr.x0, pr.J, pr.r)
+    assert O.marginalize_second_new(nxt2) is None
+    # and a solve accepts the new prior
+    chk, _ = make_window(seed=58); chk.prior = new
+    sres = O.solve(chk)
+    assert np.isfinite(sres["final_cost"]) and sres["final_cost"] <= sres["initial_cost"]
+
+
+def test_marginalization_with_plane_factor_keeps_the_plane_blocks():
+    """MARGIN_OLD with USE_PLANE (estimator.cpp:3379-3390): PlaneFactor(para_Pose[0], para_Ex_Pose_wheel, para_plane_R,
+    para_plane_Z) joins with para_Pose[0] dropped; the wheel extrinsic and the two plane blocks become kept blocks.  The
+    plane rotation keeps its 4 global columns (MarginalizationInfo::localSize only maps 7 -> 6), the fourth stays empty."""
+    from ground_fusion_b200._lib import BLOCK_EX_WHEEL, BLOCK_PLANE_R, BLOCK_PLANE_Z
+    pb, _ = make_window(seed=3, with_plane=True)
+    O.solve(pb)
+    pr = O.marginalize_old(pb)
+    assert pr.kinds[-3:] == [BLOCK_EX_WHEEL, BLOCK_PLANE_R, BLOCK_PLANE_Z]
+    assert pr.n == 76 + 6 + 4 + 1
+    H = pr.J.T @ pr.J
+    cols = _block_cols(pr)
+    cr, cz = cols[(BLOCK_PLANE_R, 0)], cols[(BLOCK_PLANE_Z, 0)]
+    assert np.abs(H[np.ix_(cr[:3], cr[:3])]).max() > 0 and np.abs(H[cz, cz]).max() > 0
+    assert np.abs(H[cr[3], :]).max() < 1e-9 * np.abs(H).max()        # PlaneFactor's Jacobian has no fourth column (plane_factor.h:95-101)
+    # without the plane factor the same window gives a prior without those blocks
+    pb0, _ = make_window(seed=3)
+    O.solve(pb0)
+    assert BLOCK_PLANE_R not in O.marginalize_old(pb0).kinds
+    # the prior is usable in a solve with plane factors (prior columns 0..2 of the rotation map to its 3 local columns)
+    nxt, _ = make_window(seed=53, with_plane=True)
+    nxt.prior = pr
+    sres = O.solve(nxt)
+    assert np.isfinite(sres["final_cost"]) and sres["final_cost"] <= sres["initial_cost"]
+    # and the prior of that window carries the plane blocks on
+    pr2 = O.marginalize_old(nxt)
+    assert pr2.kinds[-3:] == [BLOCK_EX_WHEEL, BLOCK_PLANE_R, BLOCK_PLANE_Z]
+
+
 def test_plane_factor_jacobians_match_finite_differences_and_solve_moves_the_plane():
     """PlaneFactor (reference factor/plane_factor.h:24-118): its analytic Jacobians are exact derivatives w.r.t. the right
     perturbations of PoseLocalParameterization / OrientationSubsetParameterization, so central differences pin them."""
