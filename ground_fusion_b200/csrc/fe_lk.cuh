@@ -124,7 +124,11 @@ __device__ __forceinline__ float lk_chain(const float* T, int lane, int nq)
 
 // One pyramid level for one point.  All LK_THREADS threads of the CTA call this with identical scalar arguments
 // and keep identical copies of the scalar state; warp 0 owns the sequential chains.
-#define LKP(i) do { long long t_ = clock64(); pc[i] += t_ - tl; tl = t_; } while (0)
+#ifdef GF_PROFILE
+#define LKP(i) do { long long t_ = gf_clock(); pc[i] += t_ - tl; tl = t_; } while (0)
+#else
+#define LKP(i) do { } while (0)
+#endif
 
 // Window origin of a point on one level (OpenCV: prevPt = prevPts[i] * (1/(1<<level)) - halfWin, then floor)
 __device__ __forceinline__ void lk_origin(float2 p, int l, float& ppx, float& ppy, int& ipx, int& ipy)
@@ -163,7 +167,7 @@ __device__ __forceinline__ LKUnit lk_unit(int u)
 __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, const Level& J, float2 p,
                                          float& nx, float& ny, int level, int& status, int& iters, long long* pc)
 {
-    long long tl = clock64();
+    long long tl = gf_clock();
     const float FLT_SCALE = 1.f / (1 << 20);
     float ppx, ppy;
     int ipx, ipy;
@@ -351,7 +355,7 @@ __device__ __forceinline__ void lk_track_point(LKSmem& S, int tid, const Pyramid
 {
     status = 1;
     float nx = 0.f, ny = 0.f;
-    long long tl = clock64();
+    long long tl = gf_clock();
     __syncthreads();
     for (int i = tid; i < 3 * LK_Q; i += LK_THREADS) S.terms[i] = 0.f;    // chain padding must read +0.0f
     // the template windows of all levels depend only on p: fetch them together (one memory latency instead of one per level)

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
     __shared__ SortWork swork;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int n = sc->n_prev;
-    const long long c0 = clock64();
+    const long long c0 = gf_clock();
     // ---- reduceVector (stable compaction by status) ----
     int keep = (tid < n) ? (fa.status[tid] != 0) : 0;
     unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -94,10 +94,10 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
         elems[p] = ((sort_elem)(unsigned)cnt << 32) | (unsigned)p;
     }
     __syncthreads();
-    const long long c1 = clock64();
+    const long long c1 = gf_clock();
     // ---- std::sort replica: same comparisons and moves as libstdc++, replayed in parallel (fe_sort.cuh) ----
     setmask_sort_parallel(elems, m, swork);
-    const long long c2 = clock64();
+    const long long c2 = gf_clock();
     int src = 0;
     if (tid < m) {
         src = (int)(elems[tid] & 0xffffffffu);
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
         int undecided = __syncthreads_or((tid < m) && ns == 0);
         if (!undecided) break;
     }
-    const long long c3 = clock64();
+    const long long c3 = gf_clock();
     // ---- emit kept features in sorted order ----
     int k = (tid < m) && (my == 1);
     bal = __ballot_sync(0xffffffffu, k);
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(FE_CAP) k_compact_setmask(TrackScalars* sc, Fe
         sc->n_cand = 0; sc->max_key = 0; sc->n_new = 0; sc->nms_rounds = 0;
         for (int i = 0; i < 16; i++) sc->nms_remaining[i] = 0;
     }
-    GF_DBG(0, c1 - c0); GF_DBG(1, c2 - c1); GF_DBG(2, c3 - c2); GF_DBG(3, clock64() - c3);
+    GF_DBG(0, c1 - c0); GF_DBG(1, c2 - c1); GF_DBG(2, c3 - c2); GF_DBG(3, gf_clock() - c3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,7 +344,7 @@ __device__ __forceinline__ void nms_cells(TrackScalars* sc, const NmsGrid& g, in
     __shared__ int s_nacc;
     if (tid == 0) s_nacc = 0;
     int rounds = 0;
-    long long tA = 0, tB = 0, tC = 0, tl = clock64();
+    long long tA = 0, tB = 0, tC = 0, tl = gf_clock();
     const long long tstart = tl;
     __syncthreads();
     while (true) {
@@ -387,7 +387,7 @@ __device__ __forceinline__ void nms_cells(TrackScalars* sc, const NmsGrid& g, in
             if (!g.dead[i]) { const unsigned long long key = __ldg(&g.cand_key[i]); if (visit(key, cell_of(key))) g.dead[i] = 1; }
         }
         __syncthreads();
-        { long long t_ = clock64(); tA += t_ - tl; tl = t_; }
+        { long long t_ = gf_clock(); tA += t_ - tl; tl = t_; }
         // phase B: among the candidates that carry the cell's best eig bits, the largest address wins
         auto visit2 = [&](unsigned long long key, int c) {
             if (hh[c] == (unsigned)(key >> 32)) atomicMax(&hl[c], (unsigned)(key & 0xffffffffu));
@@ -408,7 +408,7 @@ __device__ __forceinline__ void nms_cells(TrackScalars* sc, const NmsGrid& g, in
         // next round's election arrays and this round's "accepted nearby" flags start clean
         for (int c = tid; c < ncp; c += nt) { head_hi[(p ^ 1) * ncp + c] = 0u; head_lo[(p ^ 1) * ncp + c] = 0u; flag[(p ^ 1) * ncp + c] = 0; }
         __syncthreads();
-        { long long t_ = clock64(); tB += t_ - tl; tl = t_; }
+        { long long t_ = gf_clock(); tB += t_ - tl; tl = t_; }
         // phase C: a head that outranks its 8 neighbours is accepted
         int any = 0;
         int* acc_next = acc + (p ^ 1) * ncp;
@@ -441,10 +441,10 @@ __device__ __forceinline__ void nms_cells(TrackScalars* sc, const NmsGrid& g, in
         }
         rounds++;
         const int more = __syncthreads_or(any);
-        { long long t_ = clock64(); tC += t_ - tl; tl = t_; }
+        { long long t_ = gf_clock(); tC += t_ - tl; tl = t_; }
         if (!more) break;
     }
-    if (dbg && tid == 0) { dbg[13] = tA; dbg[14] = tB; dbg[15] = tC; dbg[17] = clock64() - tstart; }
+    if (dbg && tid == 0) { dbg[13] = tA; dbg[14] = tB; dbg[15] = tC; dbg[17] = gf_clock() - tstart; }
     if (tid == 0) { sc->n_acc = min(s_nacc, g.acc_cap); sc->nms_rounds = rounds; }
     __syncthreads();
 }
@@ -495,9 +495,9 @@ __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, Feat
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ unsigned long long keys[FE_SORT_CAP];
     const int tid = threadIdx.x;
-    const long long c0 = clock64();
+    const long long c0 = gf_clock();
     nms_cells(sc, g, w, min_dist, dyn_smem, fa.dbg);
-    const long long c1 = clock64();
+    const long long c1 = gf_clock();
     const double dt = dt_ptr ? *dt_ptr : 1.0;
     const int depth_cam = depth_cam_cfg && depth_valid_ptr && *depth_valid_ptr;
     const int ncand = sc->n_cand;
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, Feat
             __syncthreads();
         }
     }
-    const long long c2 = clock64();
+    const long long c2 = gf_clock();
     const int total = n_kept + n_new;
     const int n_id = sc->n_id;
     // addPoints + per-feature outputs; thread i <-> feature i of the new cur_pts order (kept..., new...)
@@ -597,7 +597,7 @@ __global__ void __launch_bounds__(1024) k_select_finalize(TrackScalars* sc, Feat
         sc->n_new = n_new; sc->n_out = total;
         sc->n_prev = total; sc->n_id = n_id + n_new; sc->eig_fixups = 0;
     }
-    GF_DBG(8, c1 - c0); GF_DBG(9, c2 - c1); GF_DBG(10, clock64() - c2); GF_DBG(11, nacc); GF_DBG(12, ncand);
+    GF_DBG(8, c1 - c0); GF_DBG(9, c2 - c1); GF_DBG(10, gf_clock() - c2); GF_DBG(11, nacc); GF_DBG(12, ncand);
 }
 
 }  // namespace gf

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(LK_THREADS) k_track(Pyramid prev, Pyramid cur,
     const int tid = threadIdx.x, i = blockIdx.x;
     if (i >= sc->n_prev) return;
     const float2 p = fa.prev_pts[i];
-    const long long t0 = clock64();
+    const long long t0 = gf_clock();
     float2 q;
     int st, iters = 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(LK_THREADS) k_track(Pyramid prev, Pyramid cur,
     if (tid == 0) {
         fa.cur_pts[i] = q; fa.status[i] = (uint8_t)st; atomicAdd(&sc->lk_iters, iters);
         if (fa.dbg && i < 4) for (int k = 0; k < 8; k++) fa.dbg[32 + 8 * i + k] = pc[k];
-        if (fa.dbg) { fa.dbg[64 + 8 * i] = clock64() - t0; fa.dbg[64 + 8 * i + 1] = iters; }
+        if (fa.dbg) { fa.dbg[64 + 8 * i] = gf_clock() - t0; fa.dbg[64 + 8 * i + 1] = iters; }
     }
 }
 

@@ -31,6 +31,14 @@ inline int set_err(int code, const char* fmt, const char* a = "", const char* b 
 
 #define GF_LAUNCHED() (gf::g_launches.fetch_add(1, std::memory_order_relaxed))
 
+// Development-time cycle counters (gf_tracker_debug_read / gf_ba_debug_profile): compiled in only with -DGF_PROFILE
+// (`make profile`); in the product build the clock reads are constants and every counter update folds away.
+#ifdef GF_PROFILE
+#define gf_clock() clock64()
+#else
+#define gf_clock() 0LL
+#endif
+
 // BORDER_REFLECT_101; valid for -n < i < 2n-1
 __host__ __device__ __forceinline__ int reflect101(int i, int n)
 {

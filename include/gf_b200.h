@@ -334,6 +334,27 @@ int gf_ba_marginalize_second_new(gf_ba* s, const gf_ba_problem* p, gf_ba_prior* 
 int gf_ba_double2vector(const gf_ba_problem* p, const double* R0_before, const double* P0_before, int use_imu,
                         double* Rs, double* Ps, double* Vs);
 
+/* ------------------------------------------------------------------------------------------------
+ * FeatureManager kernels (vins_estimator/src/estimator/feature_manager.cpp): the per-landmark work either side of
+ * Estimator::optimization().  The observation lists (std::list<FeaturePerId>) stay with the caller and are passed flattened:
+ * landmark i has n_obs[i] consecutive observations from frame start_frame[i] on, stored at obs_offset[i] in points
+ * (FeaturePerFrame::point, xyz) / depths (FeaturePerFrame::depth).  All pointers are HOST pointers.
+ * ---------------------------------------------------------------------------------------------- */
+/* FeatureManager::triangulateWithDepth (:726-799) followed by FeatureManager::triangulate (:668-723), as processImage calls
+ * them (estimator.cpp:1090-1102): landmarks with >= 4 observations and estimated_depth <= 0 get a depth -- the mean of the
+ * RGB-D depths (0.1 .. depth_threshold) that re-project within 10/460 into another frame (estimate_flag 1), else the DLT
+ * depth over all observations (flag 2); results < 0.1 become init_depth (flag 0).  Ps [n_frames][3], Rs [n_frames][9] row-major. */
+int gf_fm_triangulate(int device, int n_features, const int32_t* start_frame, const int32_t* n_obs, const int32_t* obs_offset, int n_obs_total,
+                      const double* points, const double* depths, double* estimated_depth, int32_t* estimate_flag,
+                      int n_frames, const double* Ps, const double* Rs, const double* tic, const double* ric, double depth_threshold, double init_depth);
+/* Sum of FeatureManager::compensatedParallax2 (:977-1011) over n landmarks: pts_i / pts_j are their points (xyz) in frames
+ * frame_count-2 / frame_count-1 (addFeatureCheckParallax :96-104 divides by n and compares with MIN_PARALLAX). */
+int gf_fm_parallax(int device, int n, const double* pts_i, const double* pts_j, double* parallax_sum);
+/* The depth transfer of FeatureManager::removeBackShiftDepth (:838-849) for n landmarks that start in the marginalised frame:
+ * uv_i = their first observation (xyz), estimated_depth updated in place (<= 0 after the transfer -> init_depth). */
+int gf_fm_back_shift_depth(int device, int n, const double* uv_i, double* estimated_depth, const double* marg_R, const double* marg_P,
+                           const double* new_R, const double* new_P, double init_depth);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
