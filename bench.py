@@ -353,6 +353,38 @@ def ba_bench(device, clocks_mhz, n_windows=8, reps=200, cpu_seconds=8.0):
     return out
 
 
+def ate_replay(device, n_frames=64):
+    """BASELINE.json's accuracy bar: the same synthetic RGB-D + IMU sequence replayed through the whole loop (front end ->
+    FeatureManager -> optimization() -> marginalisation -> slideWindow, ground_fusion_b200/replay.py) once on the GPU library
+    and once on the CPU oracles; ATE of each against the stream's ground truth and the largest distance between the two
+    estimated trajectories.  The bar is |ATE_gpu - ATE_cpu| <= 1 mm."""
+    import numpy as np
+    from ground_fusion_b200.estimator import BundleAdjuster
+    from ground_fusion_b200.feature_manager import FeatureManager
+    from ground_fusion_b200.feature_tracker import FeatureTracker
+    from ground_fusion_b200.replay import replay
+    from ground_fusion_b200.synth import IDC_CAM, SyntheticStream
+    from oracle.replay_adapters import oracle_components
+    cam = dict(IDC_CAM, k1=0.0, k2=0.0, p1=0.0, p2=0.0)       # the renderer is an ideal pinhole
+    p8 = [cam[k] for k in ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2")]
+    tr, fm, ba = oracle_components(cam, depth_threshold=4.0)
+    t0 = time.perf_counter()
+    want = replay(SyntheticStream(seed=0), tr, fm, ba, n_frames)
+    t_cpu = time.perf_counter() - t0
+    gtr, gfm, gba = FeatureTracker(640, 480, p8, 150, 30, 1, 1, device=device), FeatureManager(depth_threshold=4.0, device=device), BundleAdjuster(device)
+    t0 = time.perf_counter()
+    got = replay(SyntheticStream(seed=0), gtr, gfm, gba, n_frames)
+    t_gpu = time.perf_counter() - t0
+    gtr.close(); gba.close()
+    diff = float(np.linalg.norm(got["P_est"] - want["P_est"], axis=1).max())
+    return {"frames": n_frames, "ate_gpu_m": got["ate_m"], "ate_cpu_oracle_m": want["ate_m"], "abs_ate_difference_m": abs(got["ate_m"] - want["ate_m"]),
+            "max_trajectory_difference_m": diff, "within_1mm": bool(abs(got["ate_m"] - want["ate_m"]) <= 1e-3),
+            "solves": len(got["iterations"]), "margin_old": got["n_margin_old"], "margin_second_new": got["n_margin_second_new"],
+            "same_iteration_counts": bool(list(got["iterations"]) == list(want["iterations"])),
+            "wall_s": {"gpu_pipeline_incl_rendering": t_gpu, "cpu_oracle_pipeline_incl_rendering": t_cpu},
+            "note": "synthetic 640x480 RGB-D + IMU stream (seed 0), first 11 frames initialised from ground truth (the reference's SfM initialisation is outside the path), depth_threshold 4 m"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -505,6 +537,10 @@ def main():
             out["ba"] = ba_bench(local, (clocks or {}).get("sm_mhz"), cpu_seconds=min(args.cpu_seconds, 8.0))
         except Exception as e:      # the FE line must survive a BA problem
             out["ba"] = {"error": repr(e)}
+        try:
+            out["ate"] = ate_replay(local)
+        except Exception as e:
+            out["ate"] = {"error": repr(e)}
     if sampler is not None:
         sampler.stop_flag = True
     print(json.dumps(out))

@@ -1,0 +1,123 @@
+"""The reference-side C++ adaptor (adaptor/): FeatureTracker and Estimator::optimization() with the reference's class
+surfaces on top of the C ABI.  CPU: it compiles and links against libgf_b200.so with stub cv::Mat / Eigen headers.  GPU: the
+harness drives trackImage and optimization() and the results equal what the Python mirror gets from the same library."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HARNESS = os.path.join(ROOT, "adaptor", "_build", "harness")
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "adaptor")])
+    return HARNESS
+
+
+def test_adaptor_compiles_and_binds_the_c_abi():
+    exe = build()
+    syms = subprocess.check_output(["nm", "-D", "--undefined-only", exe]).decode()
+    for s in ("gf_tracker_create", "gf_tracker_track", "gf_tracker_set_prediction", "gf_tracker_remove_ids", "gf_ba_create", "gf_ba_solve",
+              "gf_ba_marginalize_old", "gf_ba_marginalize_second_new", "gf_last_error"):
+        assert (" U " + s) in syms, s
+
+
+@pytest.mark.gpu
+def test_trackimage_through_the_cpp_adaptor(tmp_path):
+    from ground_fusion_b200.feature_tracker import FeatureTracker
+    from ground_fusion_b200.synth import SyntheticStream, idc_params8
+    exe = build()
+    st, n, p8 = SyntheticStream(seed=3), 12, idc_params8()
+    frames = [st.frame(k) for k in range(n)]
+    with open(tmp_path / "fe.bin", "wb") as f:
+        f.write(struct.pack("<4i8d3i", n, 640, 480, 1, *p8, 150, 30, 1))
+        for t, g, d in frames:
+            f.write(struct.pack("<d", t)); f.write(np.ascontiguousarray(g, np.uint8).tobytes()); f.write(np.ascontiguousarray(d, np.uint16).tobytes())
+    subprocess.check_call([exe, "fe", str(tmp_path / "fe.bin"), str(tmp_path / "fe.out")], timeout=120)
+    raw = open(tmp_path / "fe.out", "rb").read()
+    tr = FeatureTracker(640, 480, p8, 150, 30, 1, 1)
+    off = 0
+    for t, g, d in frames:
+        want = tr.trackImage(t, g, d)
+        (m,) = struct.unpack_from("<i", raw, off); off += 4
+        assert m == len(want) and m > 50
+        for fid in sorted(want):
+            (got_id,) = struct.unpack_from("<i", raw, off); off += 4
+            v = np.frombuffer(raw, np.float64, 8, off); off += 64
+            assert got_id == fid and np.array_equal(v, want[fid])          # same library, same frames: identical bits
+    assert off == len(raw)
+    tr.close()
+
+
+def _dump_window(f, pb, flag):
+    F = pb.n_frames
+    f.write(struct.pack("<2i", flag, pb.n_features))
+    f.write(pb.para_pose.tobytes()); f.write(pb.para_speed_bias.tobytes()); f.write(pb.para_ex_pose.tobytes())
+    assert pb.n_imu == F - 1
+    for k in range(F - 1):
+        u = pb.imu[k]
+        assert (u.i, u.j) == (k, k + 1)
+        f.write(struct.pack("<d", u.sum_dt))
+        for a in (u.delta_p, u.delta_q, u.delta_v, u.linearized_ba, u.linearized_bg, u.jacobian, u.covariance):
+            f.write(np.array(list(a), np.float64).tobytes())
+    rows = {}
+    for k in range(pb.n_visual):
+        v = pb.visual[k]
+        rows.setdefault(v.feature, []).append(v)
+    assert sorted(rows) == list(range(pb.n_features))
+    for k in range(pb.n_features):
+        vs = rows[k]
+        assert [v.imu_j for v in vs] == list(range(vs[0].imu_i + 1, vs[0].imu_i + 1 + len(vs)))      # contiguous track
+        f.write(struct.pack("<3id", vs[0].imu_i, len(vs) + 1, 1 if pb.feature_const[k] else 0, pb.para_feature[k]))
+        f.write(struct.pack("<6d", *vs[0].pts_i, *vs[0].vel_i, vs[0].td_i))
+        for v in vs:
+            f.write(struct.pack("<6d", *v.pts_j, *v.vel_j, v.td_j))
+
+
+@pytest.mark.gpu
+def test_optimization_through_the_cpp_adaptor(tmp_path):
+    """Three consecutive optimization() calls (MARGIN_OLD, MARGIN_OLD, MARGIN_SECOND_NEW): the prior travels inside the C++
+    object exactly as last_marginalization_info does in the reference."""
+    from ground_fusion_b200.estimator import BundleAdjuster
+    from ground_fusion_b200.synth_ba import make_window
+    exe = build()
+    flags = [0, 0, 1]
+    wins = [make_window(seed=20 + k, n_landmarks=180)[0] for k in range(3)]
+    ba = BundleAdjuster(0)
+    prior = None
+    # Python side
+    want = []
+    for w, fl in zip(wins, flags):
+        q = w.clone(); q.prior = prior
+        s = ba.optimization(q)
+        nxt = ba.marginalize_old(q) if fl == 0 else ba.marginalize_second_new(q)
+        if nxt is not None:
+            prior = nxt
+        want.append((q, s, prior.J.shape[0]))
+    ba.close()
+    # C++ side: same three windows in one process
+    with open(tmp_path / "all.bin", "wb") as f:
+        f.write(struct.pack("<3i3d", 11, 3, 8, *wins[0].gravity))
+        for w, fl in zip(wins, flags):
+            _dump_window(f, w, fl)
+    subprocess.check_call([exe, "ba", str(tmp_path / "all.bin"), str(tmp_path / "ba.out")], timeout=120)
+    raw = np.fromfile(tmp_path / "ba.out", np.float64)
+    off = 0
+    for k, (q, s, pn) in enumerate(want):
+        F, nfeat = q.n_frames, q.n_features
+        pose = raw[off:off + 7 * F].reshape(F, 7); off += 7 * F
+        sb = raw[off:off + 9 * F].reshape(F, 9); off += 9 * F
+        feat = raw[off:off + nfeat]; off += nfeat
+        it, cost, pdim, term = raw[off:off + 4]; off += 4
+        assert int(it) == s["iterations"] and int(term) == s["termination"] and int(pdim) == pn
+        # two runs of the solver differ in the last bits (atomic accumulation order); windows 1 and 2 carry a prior taken from
+        # an unrelated window, which amplifies that to ~1e-6 relative
+        tol = 1e-9 if k == 0 else 1e-4
+        np.testing.assert_allclose(cost, s["final_cost"], rtol=tol)
+        np.testing.assert_allclose(pose, q.para_pose, atol=1e3 * tol)
+        np.testing.assert_allclose(sb, q.para_speed_bias, atol=1e4 * tol)
+        np.testing.assert_allclose(feat, q.para_feature[:nfeat], atol=1e4 * tol)
+    assert off == raw.size
