@@ -15,17 +15,19 @@
 // out in chain order in shared memory, so that the chain phase is one predicated LDS+FADD loop of 105 steps
 // run by 15 (A) or 10 (b) lanes.  Compile with -fmad=false: every float op must round on its own.
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, fe_tracker.cu)
 #include "gf_common.cuh"
+#include "fe_eig.cuh"      // smem_u32, mbar_* helpers
 
 namespace gf {
 
 constexpr int LK_WIN = 21;
 constexpr int LK_NPIX = LK_WIN * LK_WIN;  // 441
 constexpr int LK_IREG = 24;               // staged I window incl. Scharr apron + bilinear +1
-constexpr int LK_IPITCH = 32;             // bytes per staged I row (24 + up to 3 bytes of alignment slack)
+constexpr int LK_IPITCH = 48;             // bytes per staged I row (24 + up to 15 bytes of alignment slack: TMA boxes start 16-byte aligned)
 constexpr int LK_SCH = 22;                // integer positions needing a derivative
 constexpr int LK_JR = 40;                 // cached J region (window 22 + 9 px drift each side)
-constexpr int LK_JPITCH = 48;             // bytes per staged J row (40 + up to 3 bytes of alignment slack)
+constexpr int LK_JPITCH = 80;             // bytes per staged J row (40 + up to 15 bytes of alignment slack; 80 keeps four rows on distinct banks)
 constexpr int LK_THREADS = 256;            // one CTA of 8 warps per feature (two warps per SM scheduler), ~one feature per SM
 constexpr int LK_MAXLEV = 4;               // pyramid levels 0..3
 constexpr int LK_CHAIN = 84, LK_TAIL = 105;        // terms per SIMD-lane chain / tail chain of the A sums
@@ -34,16 +36,57 @@ constexpr int LK_AT = 4 * LK_CHAIN + LK_TAIL;       // 441 terms per A quantity
 constexpr int LK_BT = 4 * LK_BCHAIN + LK_TAIL;      // 273 terms per b component (168 pair units + 105 tail pixels)
 constexpr int LK_Q = 5 * LK_TAIL;                   // slots per quantity: [step 0..104][chain 0..4], short chains padded with +0.0f
 
-struct __align__(16) LKSmem {
+struct __align__(128) LKSmem {
     uint8_t ireg[LK_MAXLEV][LK_IREG * LK_IPITCH];   // per level: raw bytes, row r at r*32, first needed column at byte xoff
+    uint8_t jreg[LK_JR * LK_JPITCH];                // 128-byte aligned like ireg[l]: both are TMA box destinations
     int16_t sch[LK_SCH * LK_SCH * 2];
     int16_t pI[LK_NPIX + 1];
     int16_t pdx[LK_NPIX + 1];
     int16_t pdy[LK_NPIX + 1];
-    uint8_t jreg[LK_JR * LK_JPITCH];
     float terms[3 * LK_Q];                 // [quantity][step][chain]; slots beyond a chain's length hold +0.0f (x + 0 is exact)
     float sums[4];                         // chain results broadcast from warp 0
+    unsigned long long mbar;               // completion barrier of the window loads
 };
+static_assert((LK_IREG * LK_IPITCH) % 128 == 0 && (LK_MAXLEV * LK_IREG * LK_IPITCH) % 128 == 0, "TMA destinations must be 128-byte aligned");
+
+// ---- 2-D TMA staging of the LK windows --------------------------------------------------------------------------------
+// A window that lies inside its pyramid level is one cp.async.bulk.tensor.2d box: LK_IPITCH x LK_IREG bytes for a template
+// window, LK_JPITCH x LK_JR for a search region (the box is as wide as the staged row pitch, so the box IS the staging
+// layout).  The innermost box coordinate must put the box start on a 16-byte boundary -- measured on B200: an unaligned x
+// raises "illegal instruction" at the UTMALDG (tools/tma_probe.cu) -- so the box starts at x0 & ~15 and the first needed
+// column sits at byte x0 & 15 of every staged row.  Tensor maps: u8, rank 2, {w, h}, row stride = level pitch, no swizzle;
+// columns beyond the image width are zero-filled and never read.  Windows that touch the border keep the REFLECT_101 gathers.
+struct LKMapSet {
+    CUtensorMap prevI[LK_MAXLEV], curJ[LK_MAXLEV];   // forward pass: templates from the previous pyramid, search in the current one
+    CUtensorMap curI[LK_MAXLEV], prevJ[LK_MAXLEV];   // reverse pass
+    int enabled, pad_[15];
+};
+struct LKTma { const CUtensorMap* mi; const CUtensorMap* mj; unsigned phase; bool on; };
+
+__device__ __forceinline__ void lk_tma_box(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void lk_tma_wait(LKSmem& S, LKTma& T)
+{
+    while (!mbar_try_wait(&S.mbar, T.phase)) { }
+    T.phase ^= 1u;
+}
+// once per kernel, before the first lk_track_point
+__device__ __forceinline__ void lk_tma_init(LKSmem& S, int tid)
+{
+    if (tid == 0) {
+        mbar_init(&S.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+template <int RW, int RH>
+__device__ __forceinline__ bool lk_inside(const Level& L, int x0, int y0)
+{
+    return x0 >= 0 && y0 >= 0 && x0 + RW <= L.w && y0 + RH <= L.h;
+}
 
 __device__ __forceinline__ int lk_descale(int v, int n) { return (v + (1 << (n - 1))) >> n; }
 
@@ -103,9 +146,9 @@ __device__ __forceinline__ int lk_stage_part(uint8_t* dst, const Level& L, int x
     return 0;
 }
 template <int RW, int RH>
-__device__ __forceinline__ int lk_stage_offset(const Level& L, int x0, int y0)
+__device__ __forceinline__ int lk_stage_offset(const Level& L, int x0, int y0, bool tma = false)
 {
-    return (x0 >= 0 && y0 >= 0 && x0 + RW <= L.w && y0 + RH <= L.h) ? (x0 & 3) : 0;
+    return (x0 >= 0 && y0 >= 0 && x0 + RW <= L.w && y0 + RH <= L.h) ? (tma ? (x0 & 15) : (x0 & 3)) : 0;
 }
 
 // One sequential float chain per lane: lane (q*5 + c) of the first nq*5 lanes adds the 105 slots of chain c of
@@ -165,9 +208,9 @@ __device__ __forceinline__ LKUnit lk_unit(int u)
 // and keep identical copies of the scalar state; warp 0 owns the sequential chains.  The level's 24x24 window of I
 // is already staged in S.ireg[level] (lk_track_point).
 __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, const Level& J, float2 p,
-                                         float& nx, float& ny, int level, int& status, int& iters, long long* pc)
+                                         float& nx, float& ny, int level, int& status, int& iters, long long* pc, LKTma& T)
 {
-    long long tl = gf_clock();
+    long long tl = gf_clock(); (void)tl; (void)pc;
     const float FLT_SCALE = 1.f / (1 << 20);
     float ppx, ppy;
     int ipx, ipy;
@@ -180,7 +223,7 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
     int iw00, iw01, iw10, iw11;
     lk_weights(a, b, iw00, iw01, iw10, iw11);
     const uint8_t* ireg = S.ireg[level];
-    const int ioff = lk_stage_offset<LK_IREG, LK_IREG>(I, ipx - 1, ipy - 1);
+    const int ioff = lk_stage_offset<LK_IREG, LK_IREG>(I, ipx - 1, ipy - 1, T.on);
     __syncthreads();     // previous level's readers of sch / pI / terms are done
     // ---- Scharr derivative at the 22x22 integer positions (0 outside the image) ----
     for (int i = tid; i < LK_SCH * LK_SCH; i += LK_THREADS) {
@@ -239,9 +282,20 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
                 if (tid == 0) S.sums[q] = t + ((l0 + l2) + (l1 + l3));
             }
         } else if (inwin) {
-            joff = lk_stage_part<LK_JR, LK_JR, LK_JPITCH>(S.jreg, J, jx0, jy0, tid - 32, LK_THREADS - 32);
+            if (T.on && lk_inside<LK_JR, LK_JR>(J, jx0, jy0)) {
+                if (tid == 32) {     // previous readers / writers of jreg finished before the barrier at the top of this level
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&S.mbar, LK_JR * LK_JPITCH);
+                    lk_tma_box(S.jreg, T.mj + level, jx0 & ~15, jy0, &S.mbar);
+                }
+            } else {
+                joff = lk_stage_part<LK_JR, LK_JR, LK_JPITCH>(S.jreg, J, jx0, jy0, tid - 32, LK_THREADS - 32);
+            }
         }
-        if (inwin) joff = lk_stage_offset<LK_JR, LK_JR>(J, jx0, jy0);
+        if (inwin) {
+            joff = lk_stage_offset<LK_JR, LK_JR>(J, jx0, jy0, T.on);
+            if (T.on && lk_inside<LK_JR, LK_JR>(J, jx0, jy0)) lk_tma_wait(S, T);
+        }
     }
     // this thread's share of the mismatch terms and the template values it needs (constant over the iterations)
     const LKUnit U1 = lk_unit(tid < LK_BT ? tid : 0);
@@ -278,7 +332,17 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
             jx0 = iqx - 9;
             jy0 = iqy - 9;
             __syncthreads();
-            joff = lk_stage<LK_JR, LK_JR, LK_JPITCH>(S.jreg, J, jx0, jy0, tid);
+            if (T.on && lk_inside<LK_JR, LK_JR>(J, jx0, jy0)) {
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&S.mbar, LK_JR * LK_JPITCH);
+                    lk_tma_box(S.jreg, T.mj + level, jx0 & ~15, jy0, &S.mbar);
+                }
+                lk_tma_wait(S, T);
+                joff = jx0 & 15;
+            } else {
+                joff = lk_stage<LK_JR, LK_JR, LK_JPITCH>(S.jreg, J, jx0, jy0, tid);
+            }
             jvalid = true;
         }
         a = qx - (float)iqx;
@@ -351,20 +415,36 @@ __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, con
 // Whole pyramid for one point.  init is only read when use_init.
 __device__ __forceinline__ void lk_track_point(LKSmem& S, int tid, const Pyramid& I, const Pyramid& J,
                                                float2 p, float2 init, bool use_init, int max_level,
-                                               float2& out, int& status, int& iters, long long* pc)
+                                               float2& out, int& status, int& iters, long long* pc, LKTma& T)
 {
     status = 1;
     float nx = 0.f, ny = 0.f;
-    long long tl = gf_clock();
+    long long tl = gf_clock(); (void)tl; (void)pc;
     __syncthreads();
     for (int i = tid; i < 3 * LK_Q; i += LK_THREADS) S.terms[i] = 0.f;    // chain padding must read +0.0f
     // the template windows of all levels depend only on p: fetch them together (one memory latency instead of one per level)
+    int n_box = 0;
     for (int l = 0; l <= max_level; l++) {
         float ppx, ppy;
         int ipx, ipy;
         lk_origin(p, l, ppx, ppy, ipx, ipy);
-        if (!(ipx < -LK_WIN || ipx >= I.lv[l].w || ipy < -LK_WIN || ipy >= I.lv[l].h))
-            lk_stage<LK_IREG, LK_IREG, LK_IPITCH>(S.ireg[l], I.lv[l], ipx - 1, ipy - 1, tid);
+        if (ipx < -LK_WIN || ipx >= I.lv[l].w || ipy < -LK_WIN || ipy >= I.lv[l].h) continue;
+        if (T.on && lk_inside<LK_IREG, LK_IREG>(I.lv[l], ipx - 1, ipy - 1)) n_box++;
+        else lk_stage<LK_IREG, LK_IREG, LK_IPITCH>(S.ireg[l], I.lv[l], ipx - 1, ipy - 1, tid);
+    }
+    if (n_box) {            // the same test again by the issuing thread: one transaction count for all boxes of this point
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&S.mbar, n_box * LK_IREG * LK_IPITCH);
+            for (int l = 0; l <= max_level; l++) {
+                float ppx, ppy;
+                int ipx, ipy;
+                lk_origin(p, l, ppx, ppy, ipx, ipy);
+                if (ipx < -LK_WIN || ipx >= I.lv[l].w || ipy < -LK_WIN || ipy >= I.lv[l].h) continue;
+                if (lk_inside<LK_IREG, LK_IREG>(I.lv[l], ipx - 1, ipy - 1)) lk_tma_box(S.ireg[l], T.mi + l, (ipx - 1) & ~15, ipy - 1, &S.mbar);
+            }
+        }
+        lk_tma_wait(S, T);
     }
     __syncthreads();
     LKP(0);
@@ -374,7 +454,7 @@ __device__ __forceinline__ void lk_track_point(LKSmem& S, int tid, const Pyramid
             if (use_init) { nx = init.x * sc; ny = init.y * sc; }
             else { nx = p.x * sc; ny = p.y * sc; }
         } else { nx = nx * 2.f; ny = ny * 2.f; }
-        lk_level(S, tid, I.lv[l], J.lv[l], p, nx, ny, l, status, iters, pc);
+        lk_level(S, tid, I.lv[l], J.lv[l], p, nx, ny, l, status, iters, pc, T);
     }
     out = make_float2(nx, ny);
 }

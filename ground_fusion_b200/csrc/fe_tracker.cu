@@ -31,56 +31,96 @@ thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 
 
-struct FrameParams { double dt; int has_pred; int depth_valid; };
+struct FrameParams {
+    double dt; int has_pred; int depth_valid;
+    // batch pipeline only: where k_copy_in finds the frame (device pointers: the caller's, or the tracker's staging buffers)
+    const uint8_t* src_gray; const uint16_t* src_depth; long long src_gray_pitch, src_depth_pitch;   // pitches in bytes
+};
+
+// Frame intake of the batch pipeline: copies the frame named by *fp into pyramid level 0 and the depth slot (16 B per thread when
+// source and row pitch allow it).  A kernel instead of a memcpy node because the source address changes every frame while the
+// graph stays fixed.
+__global__ void __launch_bounds__(256) k_copy_in(const FrameParams* __restrict__ fp, uint8_t* __restrict__ dst_gray, int gray_pitch,
+                                                 uint16_t* __restrict__ dst_depth, int depth_pitch_el, int w, int h)
+{
+    const uint8_t* sg = fp->src_gray;
+    const uint8_t* sd = (const uint8_t*)fp->src_depth;
+    const long long gp = fp->src_gray_pitch, dp = fp->src_depth_pitch;
+    const int depth_rows = (fp->depth_valid && sd) ? h : 0;
+    const int row = blockIdx.y;                       // rows 0..h-1: gray, h..2h-1: depth
+    const bool is_depth = row >= h;
+    if (is_depth && row - h >= depth_rows) return;
+    const uint8_t* src = is_depth ? sd + (long long)(row - h) * dp : sg + (long long)row * gp;
+    uint8_t* dst = is_depth ? (uint8_t*)(dst_depth + (size_t)(row - h) * depth_pitch_el) : dst_gray + (size_t)row * gray_pitch;
+    const int nbytes = is_depth ? 2 * w : w;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x >= nbytes) return;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0 && x + 16 <= nbytes) {
+        *(uint4*)(dst + x) = __ldg((const uint4*)(src + x));
+    } else {
+        for (int k = x; k < min(x + 16, nbytes); k++) dst[k] = __ldg(src + k);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // kernels that need the LK device code
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LK_THREADS) k_lk_stage(Pyramid I, Pyramid J, const float2* prev_pts, float2* next_pts,
-                                                         int n, int max_level, int use_init, uint8_t* status)
+                                                         int n, int max_level, int use_init, uint8_t* status, const __grid_constant__ LKMapSet M)
 {
     __shared__ LKSmem sm;
     const int tid = threadIdx.x, i = blockIdx.x;
     if (i >= n) return;
+    lk_tma_init(sm, tid);
+    LKTma T{M.prevI, M.curJ, 0u, M.enabled != 0};
     float2 p = prev_pts[i], init = use_init ? next_pts[i] : p, out;
     int st, iters = 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    lk_track_point(sm, tid, I, J, p, init, use_init != 0, max_level, out, st, iters, pc);
+    lk_track_point(sm, tid, I, J, p, init, use_init != 0, max_level, out, st, iters, pc, T);
     if (tid == 0) { next_pts[i] = out; status[i] = (uint8_t)st; }
 }
 
 // Prediction pass (feature_tracker.cpp:118-124): maxLevel 1 seeded with predict_pts; counts successes.
-__global__ void __launch_bounds__(LK_THREADS) k_lk_pred(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa)
+__global__ void __launch_bounds__(LK_THREADS) k_lk_pred(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa, const __grid_constant__ LKMapSet M)
 {
     __shared__ LKSmem sm;
     const int tid = threadIdx.x, i = blockIdx.x;
     if (i >= sc->n_prev) return;
+    lk_tma_init(sm, tid);
+    LKTma T{M.prevI, M.curJ, 0u, M.enabled != 0};
     float2 out;
     int st, iters = 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    lk_track_point(sm, tid, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st, iters, pc);
+    lk_track_point(sm, tid, prev, cur, fa.prev_pts[i], fa.pred_pts[i], true, 1, out, st, iters, pc, T);
     if (tid == 0) { fa.cur_pts[i] = out; fa.status[i] = (uint8_t)st; if (st) atomicAdd(&sc->pred_succ, 1); atomicAdd(&sc->lk_iters, iters); }
 }
 
 // Forward LK (3 levels) + reverse check (1 level, USE_INITIAL_FLOW) + inBorder + grey<=250
 // (feature_tracker.cpp:118-168).  One CTA of 4 warps per feature.
-__global__ void __launch_bounds__(LK_THREADS) k_track(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa,
-                                                      const FrameParams* fp, int flow_back)
+#ifndef GF_TRACK_MIN_CTAS
+#define GF_TRACK_MIN_CTAS 3          // 79 registers: three features per SM when several streams share the GPU (2: 116 registers)
+#endif
+__global__ void __launch_bounds__(LK_THREADS, GF_TRACK_MIN_CTAS) k_track(Pyramid prev, Pyramid cur, TrackScalars* sc, FeatArrays fa,
+                                                      const FrameParams* fp, int flow_back, const __grid_constant__ LKMapSet M)
 {
     __shared__ LKSmem sm;
     const int tid = threadIdx.x, i = blockIdx.x;
     if (i >= sc->n_prev) return;
+    gf_pdl_trigger();
+    lk_tma_init(sm, tid);
+    LKTma T{M.prevI, M.curJ, 0u, M.enabled != 0};
     const float2 p = fa.prev_pts[i];
     const long long t0 = gf_clock();
     float2 q;
     int st, iters = 0;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (fp->has_pred && sc->pred_succ >= 10) { q = fa.cur_pts[i]; st = fa.status[i]; }
-    else lk_track_point(sm, tid, prev, cur, p, p, false, 3, q, st, iters, pc);
+    else lk_track_point(sm, tid, prev, cur, p, p, false, 3, q, st, iters, pc, T);
     if (flow_back) {
         float2 r;
         int rst;
-        lk_track_point(sm, tid, cur, prev, q, p, true, 1, r, rst, iters, pc);
+        T.mi = M.curI; T.mj = M.prevJ;          // roles swap for the reverse check
+        lk_track_point(sm, tid, cur, prev, q, p, true, 1, r, rst, iters, pc, T);
         double dx = (double)(p.x - r.x), dy = (double)(p.y - r.y);
         st = (st && rst && sqrt(dx * dx + dy * dy) <= 0.5) ? 1 : 0;
     }
@@ -172,8 +212,15 @@ struct gf_tracker {
     // CUDA graphs keyed by frame number mod 6 (= pyramid slot mod 3 x two-slot buffers)
     cudaGraphExec_t g_pyr[6], g_eig[6], g_dep1[6][2], g_dep2[6];
     int gk_pyr[6], gk_eig[6], gk_dep1[6][2], gk_dep2[6];
-    bool use_graph;
+    bool use_graph, use_pdl;
+    // batch pipeline (gf_tracker_track_batch): one graph launch per frame on s_main = {track + select of frame f} || {intake,
+    // pyramid and min-eig map of frame f+1}; keyed by frame number mod 6 like the pieces above
+    cudaGraphExec_t gb_prep[6], gb_dep[6], gb_both[6];
+    int gbk_prep[6], gbk_dep[6], gbk_both[6];
+    cudaEvent_t ev_fork, ev_fork2, ev_join[2];
+    uint8_t* d_stage_gray[2]; uint16_t* d_stage_depth[2];   // H2D landing buffers of the batch pipeline (host frames)
     uint8_t* d_pyr[3][4];
+    LKMapSet lk_maps[3];                   // [cur slot]: previous pyramid = slot (cur + 2) % 3
     int lw[4], lh[4], lp[4];
     uint16_t* d_depth[2]; int depth_pitch_el;
     float* d_eig[2]; int epitch;
@@ -189,7 +236,7 @@ struct gf_tracker {
     int* h_tmp_ids; double* h_tmp_xyz;
     long long n_submitted, n_waited;     // frame counters; n_submitted - n_waited frames are in flight
     double prev_time;
-    bool has_pred, depth_valid[2];
+    bool has_pred, depth_valid[2], t0_valid[2];
     float last_ms;
 };
 
@@ -200,6 +247,43 @@ static Pyramid make_pyr(const gf_tracker* t, int slot)
     Pyramid P;
     for (int l = 0; l < 4; l++) { P.lv[l].ptr = t->d_pyr[slot][l]; P.lv[l].w = t->lw[l]; P.lv[l].h = t->lh[l]; P.lv[l].pitch = t->lp[l]; }
     return P;
+}
+
+// ---- tensor maps of the LK windows (fe_lk.cuh) ----
+typedef CUresult (*gf_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int encode_u8_box(CUtensorMap* m, const Level& L, int box_w, int box_h)
+{
+    static gf_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return set_err(GF_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = (gf_encode_tiled_fn)p;
+    }
+    if (((uintptr_t)L.ptr & 15) || (L.pitch & 15)) return set_err(GF_ERR_UNSUPPORTED, "pyramid level not addressable by a tensor map");
+    const cuuint64_t dims[2] = {(cuuint64_t)L.w, (cuuint64_t)L.h}, strides[1] = {(cuuint64_t)L.pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)L.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d) for a %dx%d level", (int)r, L.w, L.h); return GF_ERR_CUDA; }
+    return GF_OK;
+}
+// Window maps for LK from `prev` to `cur` and back.  GF_LK_NO_TMA=1 keeps the per-thread loads (A/B measurements).
+static int make_lk_maps(LKMapSet* M, const Pyramid& prev, const Pyramid& cur, int levels = LK_MAXLEV)
+{
+    memset(M, 0, sizeof(*M));
+    if (getenv("GF_LK_NO_TMA")) return GF_OK;
+    for (int l = 0; l < LK_MAXLEV; l++) {
+        const int k = l < levels ? l : levels - 1;
+        int rc;
+        if ((rc = encode_u8_box(&M->prevI[l], prev.lv[k], LK_IPITCH, LK_IREG)) || (rc = encode_u8_box(&M->curJ[l], cur.lv[k], LK_JPITCH, LK_JR)) ||
+            (rc = encode_u8_box(&M->curI[l], cur.lv[k], LK_IPITCH, LK_IREG)) || (rc = encode_u8_box(&M->prevJ[l], prev.lv[k], LK_JPITCH, LK_JR)))
+            return rc;
+    }
+    M->enabled = 1;
+    return GF_OK;
 }
 
 static CamParams make_cam(const double* p)
@@ -244,13 +328,26 @@ static void free_nms_grid(NmsGrid& g)
     cudaFree(g.cand_key); cudaFree(g.acc_key); cudaFree(g.dead);
 }
 
+// Launch with (pdl) or without a programmatic dependency on the previous kernel of the stream (gf_pdl_wait / gf_pdl_trigger).
+template <class... KArgs, class... Args>
+static cudaError_t launch_k(void (*k)(KArgs...), dim3 g, dim3 b, size_t smem, cudaStream_t s, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = g; cfg.blockDim = b; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k, KArgs(args)...);
+}
+
 // GFTT tail shared by the tracker and gf_stage_gftt: mask -> max -> candidates -> NMS rounds
 static int enqueue_gftt_select(cudaStream_t s, TrackScalars* d_sc, const float2* kept_pts, const float* d_eig, int epitch, int w, int h,
-                               int min_dist, NmsGrid& grid)
+                               int min_dist, NmsGrid& grid, bool pdl = false)
 {
     dim3 tg((w + MASK_TX - 1) / MASK_TX, (h + MASK_TY - 1) / MASK_TY);
-    k_eig_max<<<tg, 256, 0, s>>>(d_sc, kept_pts, d_eig, epitch, w, h, min_dist); GF_LAUNCHED();
-    k_candidates<<<tg, 256, 0, s>>>(d_sc, kept_pts, d_eig, epitch, w, h, min_dist, grid); GF_LAUNCHED();
+    GF_CUDA(launch_k(k_eig_max, tg, dim3(256), 0, s, pdl, d_sc, kept_pts, d_eig, epitch, w, h, min_dist)); GF_LAUNCHED();
+    GF_CUDA(launch_k(k_candidates, tg, dim3(256), 0, s, pdl, d_sc, kept_pts, d_eig, epitch, w, h, min_dist, grid)); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     return GF_OK;
 }
@@ -340,6 +437,8 @@ static int tracker_init(gf_tracker* t, int width, int height, const gf_tracker_c
         GF_CUDA(cudaEventCreate(&t->ev_out[i]));
     }
     for (int i = 0; i < GF_FE_STAGES + 2; i++) GF_CUDA(cudaEventCreate(&t->ev_st[i]));
+    GF_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming)); GF_CUDA(cudaEventCreateWithFlags(&t->ev_fork2, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) GF_CUDA(cudaEventCreateWithFlags(&t->ev_join[i], cudaEventDisableTiming));
     GF_CUDA(cudaEventCreate(&t->ev_span0)); GF_CUDA(cudaEventCreate(&t->ev_span1));
     int lw = width, lh = height;
     for (int l = 0; l < 4; l++) {
@@ -350,6 +449,10 @@ static int tracker_init(gf_tracker* t, int width, int height, const gf_tracker_c
         }
         lw = (lw + 1) / 2; lh = (lh + 1) / 2;
     }
+    for (int c = 0; c < 3; c++) {
+        rc = make_lk_maps(&t->lk_maps[c], make_pyr(t, (c + 2) % 3), make_pyr(t, c));
+        if (rc) return rc;
+    }
     t->depth_pitch_el = align_up(width, 8);
     t->epitch = align_up(width, 4);
     for (int i = 0; i < 2; i++) {
@@ -357,6 +460,8 @@ static int tracker_init(gf_tracker* t, int width, int height, const gf_tracker_c
         GF_CUDA(cudaMalloc(&t->d_eig[i], (size_t)t->epitch * height * sizeof(float)));
         GF_CUDA(cudaMalloc(&t->d_out[i], sizeof(OutBlock)));
         GF_CUDA(cudaMalloc(&t->d_fp[i], sizeof(FrameParams)));
+        GF_CUDA(cudaMalloc(&t->d_stage_gray[i], (size_t)width * height));
+        GF_CUDA(cudaMalloc(&t->d_stage_depth[i], (size_t)width * height * sizeof(uint16_t)));
         GF_CUDA(cudaHostAlloc(&t->h_out[i], sizeof(OutBlock), cudaHostAllocDefault));
         GF_CUDA(cudaHostAlloc(&t->h_fp[i], sizeof(FrameParams), cudaHostAllocDefault));
     }
@@ -383,6 +488,7 @@ static int tracker_init(gf_tracker* t, int width, int height, const gf_tracker_c
     GF_CUDA(cudaHostAlloc(&t->h_tmp_ids, FE_CAP * sizeof(int), cudaHostAllocDefault));
     GF_CUDA(cudaHostAlloc(&t->h_tmp_xyz, FE_CAP * 3 * sizeof(double), cudaHostAllocDefault));
     t->use_graph = getenv("GF_NO_GRAPH") == nullptr;
+    t->use_pdl = getenv("GF_PDL") != nullptr;      // programmatic dependent launch inside dep(f): measured slower on B200, off by default
     GF_CUDA(cudaDeviceSynchronize());
     return GF_OK;
 }
@@ -396,11 +502,14 @@ void gf_tracker_destroy(gf_tracker* t)
         if (t->g_pyr[k]) cudaGraphExecDestroy(t->g_pyr[k]);
         if (t->g_eig[k]) cudaGraphExecDestroy(t->g_eig[k]);
         if (t->g_dep2[k]) cudaGraphExecDestroy(t->g_dep2[k]);
+        for (cudaGraphExec_t g : {t->gb_prep[k], t->gb_dep[k], t->gb_both[k]}) if (g) cudaGraphExecDestroy(g);
         for (int p = 0; p < 2; p++) if (t->g_dep1[k][p]) cudaGraphExecDestroy(t->g_dep1[k][p]);
     }
     for (int s = 0; s < 3; s++) for (int l = 0; l < 4; l++) cudaFree(t->d_pyr[s][l]);
     for (int i = 0; i < 2; i++) {
         cudaFree(t->d_depth[i]); cudaFree(t->d_eig[i]); cudaFree(t->d_out[i]); cudaFree(t->d_fp[i]);
+        cudaFree(t->d_stage_gray[i]); cudaFree(t->d_stage_depth[i]);
+        if (t->ev_join[i]) cudaEventDestroy(t->ev_join[i]);
         cudaFreeHost(t->h_out[i]); cudaFreeHost(t->h_fp[i]);
         for (cudaEvent_t e : {t->ev_up[i], t->ev_pyr[i], t->ev_eig[i], t->ev_dep[i], t->ev_t0[i], t->ev_out[i]}) if (e) cudaEventDestroy(e);
     }
@@ -414,6 +523,8 @@ void gf_tracker_destroy(gf_tracker* t)
     cudaFreeHost(t->h_gray); cudaFreeHost(t->h_depth); cudaFreeHost(t->h_tmp_ids); cudaFreeHost(t->h_tmp_xyz);
     for (cudaStream_t st_ : {t->s_up, t->s_pyr, t->s_eig, t->s_main, t->s_out}) if (st_) cudaStreamDestroy(st_);
     for (int i = 0; i < GF_FE_STAGES + 2; i++) if (t->ev_st[i]) cudaEventDestroy(t->ev_st[i]);
+    if (t->ev_fork) cudaEventDestroy(t->ev_fork);
+    if (t->ev_fork2) cudaEventDestroy(t->ev_fork2);
     if (t->ev_span0) cudaEventDestroy(t->ev_span0);
     if (t->ev_span1) cudaEventDestroy(t->ev_span1);
     cudaGetLastError();
@@ -446,33 +557,36 @@ static int body_eig(gf_tracker* t, long long f)
     return enqueue_min_eig(t->s_eig, Pc.lv[0], t->d_eig[f % 2], t->epitch, t->d_cov, t->d_box);
 }
 
-static int body_dep1(gf_tracker* t, long long f, bool has_pred)
+static int body_dep1(gf_tracker* t, long long f, bool has_pred, bool pdl = false)
 {
     cudaStream_t s = t->s_main;
     Pyramid Pc = make_pyr(t, (int)(f % 3)), Pp = make_pyr(t, (int)((f + 2) % 3));
     const int lk_grid = t->cfg.max_cnt;
-    if (has_pred) { k_lk_pred<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa); GF_LAUNCHED(); }
-    k_track<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp[f % 2], t->cfg.flow_back); GF_LAUNCHED();
+    const LKMapSet& M = t->lk_maps[f % 3];
+    if (has_pred) { k_lk_pred<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, M); GF_LAUNCHED(); }
+    k_track<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp[f % 2], t->cfg.flow_back, M); GF_LAUNCHED();
     GF_MARK(2, s);
-    k_compact_setmask<<<1, FE_CAP, 0, s>>>(t->d_sc, t->fa, t->cfg.min_dist); GF_LAUNCHED();
+    GF_CUDA(launch_k(k_compact_setmask, dim3(1), dim3(FE_CAP), 0, s, pdl, t->d_sc, t->fa, t->cfg.min_dist)); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_MARK(3, s);
     return GF_OK;
 }
 
-static int body_dep2(gf_tracker* t, long long f)
+static int body_dep2(gf_tracker* t, long long f, bool mirror = false)
 {
+    const bool pdl = mirror && t->use_pdl;
     cudaStream_t s = t->s_main;
     const int es = (int)(f % 2);
-    int rc = enqueue_gftt_select(s, t->d_sc, t->fa.kept_pts, t->d_eig[es], t->epitch, t->w, t->h, t->cfg.min_dist, t->grid);
+    int rc = enqueue_gftt_select(s, t->d_sc, t->fa.kept_pts, t->d_eig[es], t->epitch, t->w, t->h, t->cfg.min_dist, t->grid, pdl);
     if (rc) return rc;
     GF_MARK(4, s);
     // reference quirk: depth_cam with an empty depth image produces an empty featureFrame (feature_tracker.cpp:342)
     const int depth_mode = t->cfg.depth_cam ? 1 : 0;
     OutBlock* ob = t->d_out[es];
-    k_select_finalize<<<1, 1024, t->grid_cells, s>>>(t->d_sc, t->fa, t->grid, t->w, t->cfg.max_cnt, t->cfg.min_dist, t->cam, &t->d_fp[es]->dt,
-                                                     t->d_depth[es], t->depth_pitch_el, depth_mode, &t->d_fp[es]->depth_valid, t->h,
-                                                     &ob->hdr, ob->obs, ob->status); GF_LAUNCHED();
+    GF_CUDA(launch_k(k_select_finalize, dim3(1), dim3(1024), t->grid_cells, s, pdl, t->d_sc, t->fa, t->grid, t->w,
+                     t->cfg.max_cnt, t->cfg.min_dist, t->cam, (const double*)&t->d_fp[es]->dt, (const uint16_t*)t->d_depth[es], t->depth_pitch_el, depth_mode,
+                     (const int*)&t->d_fp[es]->depth_valid, t->h, &ob->hdr, ob->obs, ob->status,
+                     mirror ? reinterpret_cast<uint4*>(t->h_out[es]) : (uint4*)nullptr, (int)offsetof(OutBlock, obs))); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_MARK(5, s);
     return GF_OK;
@@ -539,6 +653,49 @@ static int enqueue_frame(gf_tracker* t, long long f, double time, bool depth_val
     return GF_OK;
 }
 
+// ---- batch pipeline: the bodies of gb_prep / gb_dep / gb_both (see gf_tracker) ----
+// Frame intake + pyramid + min-eig map of frame f, enqueued on m with the min-eig chain forked to s_eig and joined back.
+static int body_prep_b(gf_tracker* t, long long f, cudaStream_t m)
+{
+    const int es = (int)(f % 2), slot = (int)(f % 3);
+    GF_CUDA(cudaMemcpyAsync(t->d_fp[es], t->h_fp[es], sizeof(FrameParams), cudaMemcpyHostToDevice, m));
+    dim3 g((2 * t->w + 16 * 256 - 1) / (16 * 256), 2 * t->h);
+    k_copy_in<<<g, 256, 0, m>>>(t->d_fp[es], t->d_pyr[slot][0], t->lp[0], t->d_depth[es], t->depth_pitch_el, t->w, t->h); GF_LAUNCHED();
+    GF_CUDA(cudaEventRecord(t->ev_fork2, m));
+    GF_CUDA(cudaStreamWaitEvent(t->s_eig, t->ev_fork2, 0));
+    int rc = enqueue_pyramid(m, t, slot);
+    if (rc) return rc;
+    Pyramid Pc = make_pyr(t, slot);
+    rc = enqueue_min_eig(t->s_eig, Pc.lv[0], t->d_eig[es], t->epitch, t->d_cov, t->d_box);
+    if (rc) return rc;
+    GF_CUDA(cudaEventRecord(t->ev_join[1], t->s_eig));
+    GF_CUDA(cudaStreamWaitEvent(m, t->ev_join[1], 0));
+    return GF_OK;
+}
+
+// Track + setMask + corner selection + observations of frame f (result block mirrored to pinned host memory), on s_main.
+static int body_dep_b(gf_tracker* t, long long f)
+{
+    int rc = body_dep1(t, f, false, t->use_pdl);
+    if (rc) return rc;
+    return body_dep2(t, f, true);      // the result block reaches the pinned host buffer from inside k_select_finalize
+}
+
+// dep(f) on s_main with prep(f + 1) as a parallel branch on s_pyr (+ s_eig): nothing in prep(f + 1) touches what dep(f) reads
+// (pyramid slots f % 3 and (f - 1) % 3, eig / depth / params / out slots f % 2).
+static int body_both_b(gf_tracker* t, long long f)
+{
+    GF_CUDA(cudaEventRecord(t->ev_fork, t->s_main));
+    GF_CUDA(cudaStreamWaitEvent(t->s_pyr, t->ev_fork, 0));
+    int rc = body_prep_b(t, f + 1, t->s_pyr);
+    if (rc) return rc;
+    rc = body_dep_b(t, f);
+    if (rc) return rc;
+    GF_CUDA(cudaEventRecord(t->ev_join[0], t->s_pyr));
+    GF_CUDA(cudaStreamWaitEvent(t->s_main, t->ev_join[0], 0));
+    return GF_OK;
+}
+
 extern "C" {
 
 static int check_submit(gf_tracker* t)
@@ -563,6 +720,7 @@ int gf_tracker_submit(gf_tracker* t, double time, const uint8_t* gray, size_t gr
     const long long f = t->n_submitted;
     cudaStream_t s = t->s_up;
     GF_CUDA(cudaEventRecord(t->ev_t0[f % 2], s));
+    t->t0_valid[f % 2] = true;
     GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[f % 3][0], t->lp[0], gray, gray_pitch, w, h, cudaMemcpyHostToDevice, s));
     if (depth)
         GF_CUDA(cudaMemcpy2DAsync(t->d_depth[f % 2], (size_t)t->depth_pitch_el * 2, depth, depth_pitch, (size_t)w * 2, h, cudaMemcpyHostToDevice, s));
@@ -579,6 +737,7 @@ int gf_tracker_submit_device(gf_tracker* t, double time, const void* d_gray, con
     const long long f = t->n_submitted;
     cudaStream_t s = t->s_up;
     GF_CUDA(cudaEventRecord(t->ev_t0[f % 2], s));
+    t->t0_valid[f % 2] = true;
     GF_CUDA(cudaMemcpy2DAsync(t->d_pyr[f % 3][0], t->lp[0], d_gray, w, w, h, cudaMemcpyDeviceToDevice, s));
     if (d_depth)
         GF_CUDA(cudaMemcpy2DAsync(t->d_depth[f % 2], (size_t)t->depth_pitch_el * 2, d_depth, (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToDevice, s));
@@ -593,7 +752,8 @@ int gf_tracker_wait(gf_tracker* t, gf_obs* out, int* n_out, uint8_t* status_out,
     const int es = (int)(t->n_waited % 2);
     GF_CUDA(cudaEventSynchronize(t->ev_out[es]));
     t->n_waited++;
-    GF_CUDA(cudaEventElapsedTime(&t->last_ms, t->ev_t0[es], t->ev_out[es]));
+    if (t->t0_valid[es]) GF_CUDA(cudaEventElapsedTime(&t->last_ms, t->ev_t0[es], t->ev_out[es]));
+    else t->last_ms = 0.f;          // batch pipeline: frames are not stamped individually
     if (t->profiling) {
         cudaEvent_t b[8] = {t->ev_t0[es], t->ev_st[0], t->ev_st[1], t->ev_st[2], t->ev_st[3], t->ev_st[4], t->ev_st[5], t->ev_out[es]};
         for (int i = 0; i < 7; i++) GF_CUDA(cudaEventElapsedTime(&t->stage_ms[i], b[i], b[i + 1]));
@@ -645,13 +805,80 @@ int gf_tracker_track_batch(gf_tracker* t, int n, const double* times, const void
         return gf_tracker_wait(t, out ? out + (size_t)k * cap : nullptr, n_out ? n_out + k : nullptr,
                                status_out ? status_out + (size_t)k * cap : nullptr, info ? info + k : nullptr);
     };
-    for (int k = 0; k < n; k++) {
-        if (!gray[k]) return set_err(GF_ERR_INVALID_ARG, "null frame pointer");
+    for (int k = 0; k < n; k++) if (!gray[k]) return set_err(GF_ERR_INVALID_ARG, "null frame pointer");
+    auto submit_plain = [&](int k) {
         const void* dk = depth ? depth[k] : nullptr;
-        int rc = on_device ? gf_tracker_submit_device(t, times[k], gray[k], dk)
-                           : gf_tracker_submit(t, times[k], (const uint8_t*)gray[k], gray_pitch, (const uint16_t*)dk, depth_pitch);
+        return on_device ? gf_tracker_submit_device(t, times[k], gray[k], dk)
+                         : gf_tracker_submit(t, times[k], (const uint8_t*)gray[k], gray_pitch, (const uint16_t*)dk, depth_pitch);
+    };
+    int k0 = 0;
+    if (!t->use_graph) {                      // GF_NO_GRAPH: frame by frame through the streams of gf_tracker_submit
+        for (int k = 0; k < n; k++) {
+            int rc = submit_plain(k);
+            if (rc) return rc;
+            if (in_flight(t) == GF_PIPE) { rc = collect(); if (rc) return rc; }
+        }
+        k0 = n;
+    } else if (n > 0 && t->has_pred) {        // a pending setPrediction only concerns the first frame: take it through the other path
+        int rc = submit_plain(0);
         if (rc) return rc;
-        if (in_flight(t) == GF_PIPE) { rc = collect(); if (rc) return rc; }
+        rc = collect();
+        if (rc) return rc;
+        k0 = 1;
+    }
+    if (k0 < n) {
+        GF_CUDA(cudaSetDevice(t->device));
+        const int w = t->w, h = t->h;
+        if (!on_device) {
+            if (gray_pitch < (size_t)w) return set_err(GF_ERR_INVALID_ARG, "gray_pitch smaller than width");
+            if (depth && depth_pitch < (size_t)w * 2) return set_err(GF_ERR_INVALID_ARG, "depth_pitch smaller than width*2");
+        }
+        // Makes frame k reachable by its intake kernel: fills the pinned FrameParams slot the graph uploads and, for host frames,
+        // copies them to the staging slot on s_up (s_main then waits for that copy before the graph that holds prep(k)).
+        auto stage = [&](int k, long long f) -> int {
+            const int es = (int)(f % 2);
+            const void* dk = depth ? depth[k] : nullptr;
+            FrameParams* fp = t->h_fp[es];
+            fp->dt = times[k] - (k > 0 ? times[k - 1] : t->prev_time);
+            fp->has_pred = 0;
+            fp->depth_valid = dk ? 1 : 0;
+            if (on_device) {
+                fp->src_gray = (const uint8_t*)gray[k]; fp->src_gray_pitch = w;
+                fp->src_depth = (const uint16_t*)dk; fp->src_depth_pitch = 2ll * w;
+            } else {
+                GF_CUDA(cudaMemcpy2DAsync(t->d_stage_gray[es], w, gray[k], gray_pitch, w, h, cudaMemcpyHostToDevice, t->s_up));
+                if (dk) GF_CUDA(cudaMemcpy2DAsync(t->d_stage_depth[es], (size_t)w * 2, dk, depth_pitch, (size_t)w * 2, h, cudaMemcpyHostToDevice, t->s_up));
+                GF_CUDA(cudaEventRecord(t->ev_up[es], t->s_up));
+                GF_CUDA(cudaStreamWaitEvent(t->s_main, t->ev_up[es], 0));
+                fp->src_gray = t->d_stage_gray[es]; fp->src_gray_pitch = w;
+                fp->src_depth = dk ? t->d_stage_depth[es] : nullptr; fp->src_depth_pitch = 2ll * w;
+            }
+            return GF_OK;
+        };
+        long long f = t->n_submitted;
+        int rc = stage(k0, f);
+        if (rc) return rc;
+        { const int key = (int)(f % 6); rc = run_piece(t, t->s_main, &t->gb_prep[key], &t->gbk_prep[key], [&] { return body_prep_b(t, f, t->s_main); }); }
+        if (rc) return rc;
+        for (int k = k0; k < n; k++) {
+            f = t->n_submitted;
+            const int es = (int)(f % 2), key = (int)(f % 6);
+            if (k + 1 < n) {
+                rc = stage(k + 1, f + 1);
+                if (rc) return rc;
+                rc = run_piece(t, t->s_main, &t->gb_both[key], &t->gbk_both[key], [&] { return body_both_b(t, f); });
+            } else {
+                rc = run_piece(t, t->s_main, &t->gb_dep[key], &t->gbk_dep[key], [&] { return body_dep_b(t, f); });
+            }
+            if (rc) return rc;
+            GF_CUDA(cudaEventRecord(t->ev_out[es], t->s_main));
+            t->prev_time = times[k];
+            t->has_pred = false;
+            t->depth_valid[es] = depth && depth[k];
+            t->t0_valid[es] = false;
+            t->n_submitted = f + 1;
+            if (in_flight(t) == GF_PIPE) { rc = collect(); if (rc) return rc; }
+        }
     }
     while (in_flight(t) > 0) { int rc = collect(); if (rc) return rc; }
     return GF_OK;
@@ -826,7 +1053,9 @@ int gf_stage_lk(int device, const uint8_t* prev, const uint8_t* next, int w, int
     if ((rc = dp.alloc((size_t)n * 8)) || (rc = dq.alloc((size_t)n * 8)) || (rc = dst.alloc(n))) return rc;
     GF_CUDA(cudaMemcpy(dp.p, prev_pts, (size_t)n * 8, cudaMemcpyHostToDevice));
     GF_CUDA(cudaMemcpy(dq.p, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice));
-    k_lk_stage<<<n, LK_THREADS>>>(P[0], P[1], dp.as<float2>(), dq.as<float2>(), n, max_level, use_initial_flow, dst.as<uint8_t>()); GF_LAUNCHED();
+    LKMapSet M;
+    rc = make_lk_maps(&M, P[0], P[1], max_level + 1); if (rc) return rc;
+    k_lk_stage<<<n, LK_THREADS>>>(P[0], P[1], dp.as<float2>(), dq.as<float2>(), n, max_level, use_initial_flow, dst.as<uint8_t>(), M); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpy(next_pts, dq.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     GF_CUDA(cudaMemcpy(status, dst.p, n, cudaMemcpyDeviceToHost));

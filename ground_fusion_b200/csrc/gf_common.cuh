@@ -58,4 +58,12 @@ struct Pyramid {
     Level lv[4];
 };
 
+
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become
+// resident as soon as every CTA of its predecessor has executed gf_pdl_trigger (or exited); it must not touch anything the
+// predecessor chain writes before gf_pdl_wait, which returns once the predecessor grid has completed and its writes are visible.
+// Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void gf_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gf_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 }  // namespace gf

@@ -267,3 +267,66 @@ def test_prediction_and_remove_outliers(gf):
             pred = {int(o["id"]): (5.0, 5.0, 1.0) for o in got}
             gpu.setPrediction(pred); ref.setPrediction(pred)
     gpu.close()
+
+
+@pytest.mark.parametrize("on_device", [False, True])
+def test_batch_pipeline_equals_blocking_calls(gf, on_device):
+    """gf_tracker_track_batch runs one graph per frame ({track + select of frame f} || {intake + pyramid + min-eig of f+1});
+    the frames must come out exactly as from trackImage: batches of 1, 2, 5, 7 and 10 frames back to back, frames without a
+    depth image in between, a setPrediction before a batch (first frame takes the other path), a removeOutliers and a
+    plain trackImage call between batches, host and device-resident frames."""
+    import torch
+    from ground_fusion_b200.synth import SyntheticStream
+    from oracle.fe_oracle import IDC_CAM, PinholeCamera
+    cam = PinholeCamera(**IDC_CAM)
+    stream = SyntheticStream(seed=9)
+    frames = [stream.frame(k) for k in range(27)]
+    frames = [(t, np.ascontiguousarray(g), (np.ascontiguousarray(d) if k % 6 != 4 else None)) for k, (t, g, d) in enumerate(frames)]
+    splits = [1, 2, 5, 7, 10]                       # 25 frames in batches, then frame 25 alone, then a batch of one
+    a = gf.FeatureTracker(640, 480, cam.params8(), 150, 30, 1, 1)
+    b = gf.FeatureTracker(640, 480, cam.params8(), 150, 30, 1, 1)
+    keep = []
+
+    def ptrs(fr):
+        if not on_device:
+            return [g.ctypes.data for _, g, _ in fr], [(d.ctypes.data if d is not None else 0) for _, _, d in fr]
+        gs = [torch.from_numpy(g).cuda() for _, g, _ in fr]
+        ds = [(torch.from_numpy(d.view(np.int16)).cuda() if d is not None else None) for _, _, d in fr]
+        keep.append((gs, ds))
+        torch.cuda.synchronize()
+        return [x.data_ptr() for x in gs], [(x.data_ptr() if x is not None else 0) for x in ds]
+
+    def plain(tr, fr):
+        out = []
+        for t, g, d in fr:
+            obs = tr.trackImageRaw(t, g, d).copy()
+            out.append((obs, tr.last_status.copy(), dict(tr.last_info)))
+        return out
+
+    def check(want, got, base):
+        assert len(want) == len(got)
+        for k, ((o1, s1, i1), (o2, s2, i2)) in enumerate(zip(want, got)):
+            assert i1 == i2, "frame %d: %s vs %s" % (base + k, i1, i2)
+            assert np.array_equal(s1, s2), "frame %d" % (base + k)
+            assert o1.tobytes() == o2.tobytes(), "frame %d" % (base + k)
+
+    pos = 0
+    for n in splits:
+        fr = frames[pos:pos + n]
+        want = plain(a, fr)
+        gp, dp = ptrs(fr)
+        got = b.trackBatch([t for t, _, _ in fr], gp, dp, on_device=on_device)
+        check(want, got, pos)
+        pos += n
+        last = want[-1][0]
+        if n == 2:                                   # prediction pending when the next batch starts
+            pred = {int(o["id"]): (o["v"][0] * 2.0, o["v"][1] * 2.0, 2.0) for o in last[::2]}
+            a.setPrediction(pred); b.setPrediction(pred)
+        if n == 5:
+            rm = set(int(i) for i in last["id"][::5])
+            a.removeOutliers(rm); b.removeOutliers(rm)
+    check(plain(a, frames[25:26]), plain(b, frames[25:26]), 25)      # the per-frame path after batches ...
+    fr = frames[26:27]
+    gp, dp = ptrs(fr)
+    check(plain(a, fr), b.trackBatch([fr[0][0]], gp, dp, on_device=on_device), 26)   # ... and a batch after it
+    a.close(); b.close()
