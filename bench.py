@@ -211,14 +211,35 @@ class Stream:
         return self.dev_ms
 
 
-def timed(streams, n_steps, mode, barrier, sampler=None):
-    """K steps on every stream of this rank (one host thread per stream); wall clock between barriers."""
+def run_multi(streams, n_steps, mode):
+    """The same n_steps on S streams through gf_tracker_track_batch_multi: one host thread feeds all the streams."""
+    from ground_fusion_b200.feature_tracker import FeatureTracker
+    for s in streams:
+        s.tr.timer_start()
+    for _ in range(n_steps):
+        times, gp, dp = [], [], []
+        for s in streams:
+            g, d = s.ring.ptr[mode]
+            idx = [tri(s.k + j, s.ring.n) for j in range(FRAMES_PER_STEP)]
+            times.append([(s.k + j) / 30.0 for j in range(FRAMES_PER_STEP)])
+            gp.append([g[i] for i in idx]); dp.append([d[i] for i in idx])
+            s.k += FRAMES_PER_STEP
+        FeatureTracker.trackBatchMulti([s.tr for s in streams], times, gp, dp, on_device=(mode == "device"), want=False)
+    for s in streams:
+        s.dev_ms = s.tr.timer_stop()
+
+
+def timed(streams, n_steps, mode, barrier, sampler=None, threads=False):
+    """K steps on every stream of this rank; wall clock between barriers.  Several streams: one host thread and
+    gf_tracker_track_batch_multi, or (threads=True, for comparison) one host thread per stream."""
     barrier()
     if sampler is not None:
         sampler.active = True
     t0 = time.perf_counter()
     if len(streams) == 1:
         streams[0].run(n_steps, mode)
+    elif not threads:
+        run_multi(streams, n_steps, mode)
     else:
         th = [threading.Thread(target=s.run, args=(n_steps, mode)) for s in streams]
         for x in th:
@@ -232,15 +253,15 @@ def timed(streams, n_steps, mode, barrier, sampler=None):
     return el, max(s.dev_ms for s in streams)
 
 
-def fe_line(wl, rings, device, n_streams, steps, warmup, barrier, sampler, reduce_max):
+def fe_line(wl, rings, device, n_streams, steps, warmup, barrier, sampler, reduce_max, threads=False):
     streams = [Stream(rings[0], wl, device, offset=17 * s) for s in range(n_streams)]
     from ground_fusion_b200 import _lib
-    timed(streams, warmup, "device", barrier)
+    timed(streams, warmup, "device", barrier, threads=threads)
     l0 = _lib.lib().gf_kernel_launch_count()
-    el_dev, ms_dev = timed(streams, steps, "device", barrier, sampler)
+    el_dev, ms_dev = timed(streams, steps, "device", barrier, sampler, threads=threads)
     launches = _lib.lib().gf_kernel_launch_count() - l0
-    timed(streams, max(1, warmup // 2), "host", barrier)
-    el_e2e, ms_e2e = timed(streams, steps, "host", barrier, sampler)
+    timed(streams, max(1, warmup // 2), "host", barrier, threads=threads)
+    el_e2e, ms_e2e = timed(streams, steps, "host", barrier, sampler, threads=threads)
     el_dev, el_e2e, ms_dev, ms_e2e = reduce_max([el_dev, el_e2e, ms_dev, ms_e2e])
     infos = streams[0].tr.batch_infos
     for s in streams:
@@ -509,12 +530,14 @@ def main():
                                    "throughput comes from concurrent streams (see streams)"}
         # ---- several independent streams on one GPU ----
         sweep = {}
-        for ns in (2, 4, 8):
+        for ns in (2, 4, 8, 16):
             r = fe_line(wl, [ring], local, ns, max(4, args.steps // 2), 2, barrier, None, reduce_max)
             sweep[str(ns)] = {"value": r["value"], "e2e": r["e2e"]}
         sweep["1"] = {"value": head["value"], "e2e": head["e2e"]}
+        r = fe_line(wl, [ring], local, 8, max(4, args.steps // 2), 2, barrier, None, reduce_max, threads=True)
         out["streams"] = {"unit": "frames/s", "per_streams_per_gpu": sweep,
-                          "note": "independent trackers (gf_tracker handles) sharing one B200, one host thread each; C2 workload"}
+                          "eight_streams_one_host_thread_each": {"value": r["value"], "e2e": r["e2e"]},
+                          "note": "independent trackers (gf_tracker handles) sharing one B200, all fed by ONE host thread through gf_tracker_track_batch_multi; eight_streams_one_host_thread_each = the same 8 trackers driven by 8 host threads calling gf_tracker_track_batch (they contend on the driver's launch locks); C2 workload"}
         # ---- the other configurations ----
         cfgs = {}
         for name in ("C3", "C4"):

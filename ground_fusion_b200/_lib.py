@@ -61,6 +61,7 @@ def lib():
         L.gf_tracker_wait.argtypes = [vp, vp, ctypes.POINTER(i), vp, ctypes.POINTER(TrackInfo)]
         L.gf_tracker_track_device.argtypes = [vp, d, vp, vp, vp, ctypes.POINTER(i), vp, ctypes.POINTER(TrackInfo)]
         L.gf_tracker_track_batch.argtypes = [vp, i, vp, vp, sz, vp, sz, i, vp, vp, vp, vp]
+        L.gf_tracker_track_batch_multi.argtypes = [vp, i, i, vp, vp, sz, vp, sz, i, vp, vp, vp, vp]
         L.gf_tracker_set_prediction.argtypes = [vp, vp, vp, i]
         L.gf_tracker_remove_ids.argtypes = [vp, vp, i]
         L.gf_tracker_last_device_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]

@@ -210,7 +210,7 @@ __device__ __forceinline__ LKUnit lk_unit(int u)
 __device__ __forceinline__ void lk_level(LKSmem& S, int tid, const Level& I, const Level& J, float2 p,
                                          float& nx, float& ny, int level, int& status, int& iters, long long* pc, LKTma& T)
 {
-    long long tl = gf_clock(); (void)tl; (void)pc;
+    [[maybe_unused]] long long tl = gf_clock();
     const float FLT_SCALE = 1.f / (1 << 20);
     float ppx, ppy;
     int ipx, ipy;
@@ -419,7 +419,7 @@ __device__ __forceinline__ void lk_track_point(LKSmem& S, int tid, const Pyramid
 {
     status = 1;
     float nx = 0.f, ny = 0.f;
-    long long tl = gf_clock(); (void)tl; (void)pc;
+    [[maybe_unused]] long long tl = gf_clock();
     __syncthreads();
     for (int i = tid; i < 3 * LK_Q; i += LK_THREADS) S.terms[i] = 0.f;    // chain padding must read +0.0f
     // the template windows of all levels depend only on p: fetch them together (one memory latency instead of one per level)

