@@ -523,7 +523,7 @@ def main():
         out["roofline"] = {"kernel": "k_track (fwd 4-level + reverse 2-level LK, one 8-warp CTA per feature)", "bound": "hbm",
                            "achieved": (lk_bytes / lk_s / 1e9) if lk_s > 0 else None, "peak": hbm, "unit": "GB/s",
                            "frac": (lk_bytes / lk_s / 1e9 / hbm) if lk_s > 0 else None,
-                           "traffic": 876544, "traffic_source": "dram__bytes_read+write of one k_track launch, profiles/r1_ncu_k_track_full.txt",
+                           "traffic": 899072, "traffic_source": "dram__bytes_read+write of one k_track launch, profiles/r2_ncu_k_track_full.txt",
                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                            "algorithmic_bytes_per_launch": lk_bytes, "kernel_ms": stage.get("lk"),
                            "note": "latency-bound by construction: per feature a chain of ~22 dependent LK iterations, each 105 dependent FADDs in OpenCV lane order; "
@@ -537,7 +537,7 @@ def main():
         r = fe_line(wl, [ring], local, 8, max(4, args.steps // 2), 2, barrier, None, reduce_max, threads=True)
         out["streams"] = {"unit": "frames/s", "per_streams_per_gpu": sweep,
                           "eight_streams_one_host_thread_each": {"value": r["value"], "e2e": r["e2e"]},
-                          "note": "independent trackers (gf_tracker handles) sharing one B200, all fed by ONE host thread through gf_tracker_track_batch_multi; eight_streams_one_host_thread_each = the same 8 trackers driven by 8 host threads calling gf_tracker_track_batch (they contend on the driver's launch locks); C2 workload"}
+                          "note": "independent trackers (gf_tracker handles) sharing one B200, all fed by ONE host thread through gf_tracker_track_batch_multi; eight_streams_one_host_thread_each = the same 8 trackers driven by 8 host threads calling gf_tracker_track_batch; e2e saturates on the host link (0.92 MB per frame: 31 k frames/s = 28.5 GB/s); C2 workload"}
         # ---- the other configurations ----
         cfgs = {}
         for name in ("C3", "C4"):
