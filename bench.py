@@ -437,6 +437,14 @@ def main():
                           "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    # libraries (NCCL's version banner, torchrun warnings) may write to fd 1: keep it for the one JSON line, send the rest to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
@@ -566,7 +574,7 @@ def main():
             out["ate"] = {"error": repr(e)}
     if sampler is not None:
         sampler.stop_flag = True
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.destroy_process_group()
 
