@@ -445,6 +445,8 @@ __device__ __forceinline__ void ba_eval_body(const BaDev& d, int mode)
 
 __global__ void __launch_bounds__(PAIR_THREADS) k_ba_eval(BaDev d, int mode)
 {
+    gf::gf_pdl_trigger();      // no-ops unless launched with a programmatic dependency (gf_ba_solve)
+    gf::gf_pdl_wait();
     ba_eval_body(d, mode);
     if (mode == 1) {
         // the last CTA to finish takes the decision (accept / reject, radius, mu, convergence): no separate launch
@@ -615,6 +617,8 @@ __global__ void __launch_bounds__(SCHUR_WARPS * 32) k_ba_schur(BaDev d)
 {
     extern __shared__ double ssm[];                // tile CTAs: cl[L] | ss[nc+1] | sv[nc];  last CTA: delta[n]
     __shared__ double sred2[2 * SCHUR_WARPS];
+    gf::gf_pdl_trigger();
+    gf::gf_pdl_wait();
     const BaState& st = *d.st;
     if (st.done || st.setup_failed) return;
     const bool fresh = st.need_linearize != 0;
@@ -729,6 +733,8 @@ __global__ void __launch_bounds__(RB_THREADS) k_ba_step(BaDev d)
     __shared__ double sred[64];
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ int s_fail, s_go;
+    gf::gf_pdl_trigger();
+    gf::gf_pdl_wait();
     BaState& st = *d.st;
     if (st.done || st.setup_failed) return;
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nt >> 5;
@@ -1554,13 +1560,26 @@ int gf_ba_solve(gf_ba* s, const gf_ba_problem* p, gf_ba_summary* sum)
     const int schur_grid = (ntiles + SCHUR_WARPS - 1) / SCHUR_WARPS + 1;      // + the CTA that prepares k_ba_step's vectors and norms
     const int iters = p->max_num_iterations;
     if (eval_blocks > 0) { k_ba_eval<<<eval_blocks, PAIR_THREADS, prior_smem, st>>>(d, 0); GF_LAUNCHED(); }
+    // Every kernel of the loop is launched with a programmatic dependency on its predecessor: its CTAs become resident while the
+    // predecessor still runs and sit in griddepcontrol.wait, which hides the launch latency at the 26 kernel boundaries of a solve
+    // (measured on B200, C2 window: 0.775 -> 0.740 ms per solve; GF_BA_NO_PDL=1 restores plain stream order for A/B runs)
+    static const bool pdl = getenv("GF_BA_NO_PDL") == nullptr;
+    auto launch = [&](auto kern, int grid, int block, size_t smem, auto... args) -> cudaError_t {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, kern, args...);
+    };
     for (int it = 0; it <= iters; it++) {
-        k_ba_schur<<<schur_grid, SCHUR_WARPS * 32, schur_smem, st>>>(d); GF_LAUNCHED();      // (the closing launch only prepares the norms)
-        if (ntiles <= s->tile_cap && n8 <= (MAXR / 2) * CH_BULK) k_ba_step<MAXR / 2, false><<<1, RB_THREADS, step_smem, st>>>(d);
-        else k_ba_step<MAXR, true><<<1, RB_THREADS, step_smem, st>>>(d);
+        GF_CUDA(launch(k_ba_schur, schur_grid, SCHUR_WARPS * 32, schur_smem, d)); GF_LAUNCHED();      // (the closing launch only prepares the norms)
+        if (ntiles <= s->tile_cap && n8 <= (MAXR / 2) * CH_BULK) GF_CUDA(launch(k_ba_step<MAXR / 2, false>, 1, RB_THREADS, step_smem, d));
+        else GF_CUDA(launch(k_ba_step<MAXR, true>, 1, RB_THREADS, step_smem, d));
         GF_LAUNCHED();
         if (it == iters) break;                  // the extra k_ba_step adopts the last linearisation and closes the run
-        k_ba_eval<<<eval_blocks > 0 ? eval_blocks : 1, PAIR_THREADS, prior_smem, st>>>(d, 1); GF_LAUNCHED();   // + decision (last CTA)
+        GF_CUDA(launch(k_ba_eval, eval_blocks > 0 ? eval_blocks : 1, PAIR_THREADS, prior_smem, d, 1)); GF_LAUNCHED();   // + decision (last CTA)
     }
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpyAsync(hb + o_X, db + o_X, sizeof(double) * (X_FEAT + nfeat), cudaMemcpyDeviceToHost, st));
