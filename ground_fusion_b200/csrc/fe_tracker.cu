@@ -212,7 +212,7 @@ struct gf_tracker {
     // CUDA graphs keyed by frame number mod 6 (= pyramid slot mod 3 x two-slot buffers)
     cudaGraphExec_t g_pyr[6], g_eig[6], g_dep1[6][2], g_dep2[6];
     int gk_pyr[6], gk_eig[6], gk_dep1[6][2], gk_dep2[6];
-    bool use_graph, use_pdl, batch_pipeline;
+    bool use_graph, use_pdl, pdl_single_cta, batch_pipeline;
     // batch pipeline (gf_tracker_track_batch): one graph launch per frame on s_main = {track + select of frame f} || {intake,
     // pyramid and min-eig map of frame f+1}; keyed by frame number mod 6 like the pieces above
     cudaGraphExec_t gb_prep[6], gb_dep[6], gb_both[6];
@@ -489,6 +489,7 @@ static int tracker_init(gf_tracker* t, int width, int height, const gf_tracker_c
     GF_CUDA(cudaHostAlloc(&t->h_tmp_xyz, FE_CAP * 3 * sizeof(double), cudaHostAllocDefault));
     t->use_graph = getenv("GF_NO_GRAPH") == nullptr;
     t->batch_pipeline = getenv("GF_BATCH_PIPELINE") != nullptr;   // one graph per frame for batches (see gf_tracker_track_batch_multi)
+    t->pdl_single_cta = getenv("GF_FE_PDL1") != nullptr && !t->profiling;   // PDL only into the two single-CTA kernels
     t->use_pdl = getenv("GF_PDL") != nullptr;      // programmatic dependent launch inside dep(f): measured slower on B200, off by default
     GF_CUDA(cudaDeviceSynchronize());
     return GF_OK;
@@ -567,7 +568,7 @@ static int body_dep1(gf_tracker* t, long long f, bool has_pred, bool pdl = false
     if (has_pred) { k_lk_pred<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, M); GF_LAUNCHED(); }
     k_track<<<lk_grid, LK_THREADS, 0, s>>>(Pp, Pc, t->d_sc, t->fa, t->d_fp[f % 2], t->cfg.flow_back, M); GF_LAUNCHED();
     GF_MARK(2, s);
-    GF_CUDA(launch_k(k_compact_setmask, dim3(1), dim3(FE_CAP), 0, s, pdl, t->d_sc, t->fa, t->cfg.min_dist)); GF_LAUNCHED();
+    GF_CUDA(launch_k(k_compact_setmask, dim3(1), dim3(FE_CAP), 0, s, pdl || (t->pdl_single_cta && !t->profiling), t->d_sc, t->fa, t->cfg.min_dist)); GF_LAUNCHED();
     GF_CUDA(cudaGetLastError());
     GF_MARK(3, s);
     return GF_OK;
@@ -584,7 +585,7 @@ static int body_dep2(gf_tracker* t, long long f, bool mirror = false)
     // reference quirk: depth_cam with an empty depth image produces an empty featureFrame (feature_tracker.cpp:342)
     const int depth_mode = t->cfg.depth_cam ? 1 : 0;
     OutBlock* ob = t->d_out[es];
-    GF_CUDA(launch_k(k_select_finalize, dim3(1), dim3(1024), t->grid_cells, s, pdl, t->d_sc, t->fa, t->grid, t->w,
+    GF_CUDA(launch_k(k_select_finalize, dim3(1), dim3(1024), t->grid_cells, s, pdl || (t->pdl_single_cta && !t->profiling), t->d_sc, t->fa, t->grid, t->w,
                      t->cfg.max_cnt, t->cfg.min_dist, t->cam, (const double*)&t->d_fp[es]->dt, (const uint16_t*)t->d_depth[es], t->depth_pitch_el, depth_mode,
                      (const int*)&t->d_fp[es]->depth_valid, t->h, &ob->hdr, ob->obs, ob->status,
                      mirror ? reinterpret_cast<uint4*>(t->h_out[es]) : (uint4*)nullptr, (int)offsetof(OutBlock, obs))); GF_LAUNCHED();
