@@ -7,6 +7,11 @@
 //                          (addFeatureCheckParallax :96-104: the keyframe test)
 //   gf_fm_back_shift_depth removeBackShiftDepth (:818-856): depth of a landmark transferred from the marginalised frame 0 to
 //                          the new first frame
+// and the per-landmark loops of the estimator that feed the front end back (estimator.cpp, after optimization()):
+//   gf_fm_reprojection_errors  the sums behind Estimator::outliersRejection (:3909-3966) and movingConsistencyCheckW (:3968-4011):
+//                          sum over the later observations of reprojectionError (:3888-3898) and reprojectionError3D (:3900-3907)
+//   gf_fm_predict_next     Estimator::predictPtsInNextFrame (:3853-3886): landmarks carried into the constant-velocity prediction of
+//                          the next frame's camera (the xyz that FeatureTracker::setPrediction takes)
 // One thread per landmark: the work is O(obs^2) <= 121 small FP64 steps per landmark and there are <= a few hundred
 // landmarks; the list bookkeeping (std::list<FeaturePerId>) stays on the host (ground_fusion_b200/feature_manager.py).
 #include <vector>
@@ -165,6 +170,62 @@ __global__ void k_fm_back_shift(int n, const double* __restrict__ uv /* xyz */, 
     est[i] = pj[2] > 0 ? pj[2] : init_depth;
 }
 
+// err2d[i] = sum_j |pi(T_cj^-1 T_ci (depth uv_i)) - uv_j|,  err3d[i] = sum_j |T_cj^-1 T_ci (depth uv_i) - uv_j| / depth over the
+// observations j after the first; cnt[i] = their number
+__global__ void k_fm_reproj(int nf, const int* __restrict__ start, const int* __restrict__ nobs, const int* __restrict__ off, const double* __restrict__ pts,
+                            const double* __restrict__ depth, double* __restrict__ err2d, double* __restrict__ err3d, int* __restrict__ cnt, FmPoses ps)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    const int fi = start[i], n = nobs[i];
+    const double d = depth[i];
+    const double* uvi = pts + 3 * (size_t)off[i];
+    double a[3] = {d * uvi[0], d * uvi[1], d * uvi[2]}, b[3], pw[3];
+    m3_v(ps.ric, a, b);
+    for (int k = 0; k < 3; k++) b[k] += ps.tic[k];
+    m3_v(ps.R[fi], b, pw);
+    for (int k = 0; k < 3; k++) pw[k] += ps.P[fi][k];
+    double ricT[9];
+    m3_T(ps.ric, ricT);
+    double e2 = 0, e3 = 0;
+    int c = 0;
+    for (int j = 1; j < n; j++) {
+        const int fj = fi + j;
+        const double* uvj = pts + 3 * (size_t)(off[i] + j);
+        double RjT[9], t[3], u[3], pc[3];
+        m3_T(ps.R[fj], RjT);
+        for (int k = 0; k < 3; k++) t[k] = pw[k] - ps.P[fj][k];
+        m3_v(RjT, t, u);
+        for (int k = 0; k < 3; k++) u[k] -= ps.tic[k];
+        m3_v(ricT, u, pc);
+        const double rx = pc[0] / pc[2] - uvj[0], ry = pc[1] / pc[2] - uvj[1];
+        e2 += sqrt(rx * rx + ry * ry);
+        const double dx = pc[0] - uvj[0], dy = pc[1] - uvj[1], dz = pc[2] - uvj[2];
+        e3 += sqrt(dx * dx + dy * dy + dz * dz) / d;
+        c++;
+    }
+    err2d[i] = e2; err3d[i] = e3; cnt[i] = c;
+}
+
+// out[i] = ric^T (nextR^T (Rs[f_i] (ric (depth uv_i) + tic) + Ps[f_i] - nextP) - tic),  nextT = curT (prevT^-1 curT) in T[0..11] (R 9, P 3)
+__global__ void k_fm_predict(int n, const int* __restrict__ first, const double* __restrict__ uv, const double* __restrict__ depth, double* __restrict__ out,
+                             FmPoses ps, const double* __restrict__ T)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int fi = first[i];
+    const double d = depth[i];
+    double a[3] = {d * uv[3 * i], d * uv[3 * i + 1], d * uv[3 * i + 2]}, b[3], pw[3], nRT[9], ricT[9], l[3], c[3];
+    m3_v(ps.ric, a, b);
+    for (int k = 0; k < 3; k++) b[k] += ps.tic[k];
+    m3_v(ps.R[fi], b, pw);
+    for (int k = 0; k < 3; k++) pw[k] += ps.P[fi][k] - T[9 + k];
+    m3_T(T, nRT); m3_v(nRT, pw, l);
+    for (int k = 0; k < 3; k++) l[k] -= ps.tic[k];
+    m3_T(ps.ric, ricT); m3_v(ricT, l, c);
+    out[3 * i] = c[0]; out[3 * i + 1] = c[1]; out[3 * i + 2] = c[2];
+}
+
 }  // namespace gffm
 
 using namespace gffm;
@@ -209,6 +270,67 @@ int gf_fm_triangulate(int device, int n_features, const int32_t* start_frame, co
     GF_CUDA(cudaGetLastError());
     GF_CUDA(cudaMemcpy(estimated_depth, b_e.p, 8 * (size_t)n_features, cudaMemcpyDeviceToHost));
     GF_CUDA(cudaMemcpy(estimate_flag, b_f.p, 4 * (size_t)n_features, cudaMemcpyDeviceToHost));
+    return GF_OK;
+}
+
+int gf_fm_reprojection_errors(int device, int n_features, const int32_t* start_frame, const int32_t* n_obs, const int32_t* obs_offset, int n_obs_total,
+                              const double* points, const double* estimated_depth, int n_frames, const double* Ps, const double* Rs, const double* tic,
+                              const double* ric, double* err2d_sum, double* err3d_sum, int32_t* count)
+{
+    if (n_features < 0 || n_frames < 1 || n_frames > GF_BA_MAX_FRAMES || !Ps || !Rs || !tic || !ric ||
+        (n_features > 0 && (!start_frame || !n_obs || !obs_offset || !points || !estimated_depth || !err2d_sum || !err3d_sum || !count)))
+        return set_err(GF_ERR_INVALID_ARG, "bad argument");
+    if (n_features == 0) return GF_OK;
+    for (int i = 0; i < n_features; i++)
+        if (n_obs[i] < 1 || start_frame[i] < 0 || start_frame[i] + n_obs[i] > n_frames || obs_offset[i] < 0 || obs_offset[i] + n_obs[i] > n_obs_total)
+            return set_err(GF_ERR_INVALID_ARG, "observation list out of range");
+    int rc = fm_device(device);
+    if (rc) return rc;
+    FmPoses ps; memset(&ps, 0, sizeof(ps));
+    memcpy(ps.P, Ps, sizeof(double) * 3 * n_frames); memcpy(ps.R, Rs, sizeof(double) * 9 * n_frames); memcpy(ps.tic, tic, 24); memcpy(ps.ric, ric, 72);
+    FmBuf b_s, b_n, b_o, b_p, b_d, b_2, b_3, b_c;
+    if ((rc = b_s.put(start_frame, 4 * (size_t)n_features)) || (rc = b_n.put(n_obs, 4 * (size_t)n_features)) || (rc = b_o.put(obs_offset, 4 * (size_t)n_features)) ||
+        (rc = b_p.put(points, 24 * (size_t)n_obs_total)) || (rc = b_d.put(estimated_depth, 8 * (size_t)n_features))) return rc;
+    GF_CUDA(cudaMalloc(&b_2.p, 8 * (size_t)n_features)); GF_CUDA(cudaMalloc(&b_3.p, 8 * (size_t)n_features)); GF_CUDA(cudaMalloc(&b_c.p, 4 * (size_t)n_features));
+    k_fm_reproj<<<(n_features + 63) / 64, 64>>>(n_features, (const int*)b_s.p, (const int*)b_n.p, (const int*)b_o.p, (const double*)b_p.p, (const double*)b_d.p,
+                                                (double*)b_2.p, (double*)b_3.p, (int*)b_c.p, ps);
+    GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaMemcpy(err2d_sum, b_2.p, 8 * (size_t)n_features, cudaMemcpyDeviceToHost));
+    GF_CUDA(cudaMemcpy(err3d_sum, b_3.p, 8 * (size_t)n_features, cudaMemcpyDeviceToHost));
+    GF_CUDA(cudaMemcpy(count, b_c.p, 4 * (size_t)n_features, cudaMemcpyDeviceToHost));
+    return GF_OK;
+}
+
+int gf_fm_predict_next(int device, int n, const int32_t* first_frame, const double* uv_first, const double* estimated_depth, int n_frames, int frame_count,
+                       const double* Ps, const double* Rs, const double* tic, const double* ric, double* pts_cam)
+{
+    if (n < 0 || n_frames < 2 || n_frames > GF_BA_MAX_FRAMES || frame_count < 1 || frame_count >= n_frames || !Ps || !Rs || !tic || !ric ||
+        (n > 0 && (!first_frame || !uv_first || !estimated_depth || !pts_cam)))
+        return set_err(GF_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return GF_OK;
+    for (int i = 0; i < n; i++) if (first_frame[i] < 0 || first_frame[i] >= n_frames) return set_err(GF_ERR_INVALID_ARG, "frame index out of range");
+    // nextT = curT * (prevT^-1 * curT), constant-velocity motion (estimator.cpp:3859-3863); host side, 4x4 in FP64
+    const double* Rc = Rs + 9 * frame_count; const double* Pc = Ps + 3 * frame_count;
+    const double* Rp = Rs + 9 * (frame_count - 1); const double* Pp = Ps + 3 * (frame_count - 1);
+    double dR[9], dP[3], t[3], T[12];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double v = 0; for (int k = 0; k < 3; k++) v += Rp[k * 3 + i] * Rc[k * 3 + j]; dR[i * 3 + j] = v; }   // Rp^T Rc
+    for (int k = 0; k < 3; k++) t[k] = Pc[k] - Pp[k];
+    for (int i = 0; i < 3; i++) dP[i] = Rp[0 * 3 + i] * t[0] + Rp[1 * 3 + i] * t[1] + Rp[2 * 3 + i] * t[2];                                                       // Rp^T (Pc - Pp)
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double v = 0; for (int k = 0; k < 3; k++) v += Rc[i * 3 + k] * dR[k * 3 + j]; T[i * 3 + j] = v; }
+    for (int i = 0; i < 3; i++) T[9 + i] = Rc[i * 3] * dP[0] + Rc[i * 3 + 1] * dP[1] + Rc[i * 3 + 2] * dP[2] + Pc[i];
+    int rc = fm_device(device);
+    if (rc) return rc;
+    FmPoses ps; memset(&ps, 0, sizeof(ps));
+    memcpy(ps.P, Ps, sizeof(double) * 3 * n_frames); memcpy(ps.R, Rs, sizeof(double) * 9 * n_frames); memcpy(ps.tic, tic, 24); memcpy(ps.ric, ric, 72);
+    FmBuf b_f, b_u, b_d, b_t, b_o;
+    if ((rc = b_f.put(first_frame, 4 * (size_t)n)) || (rc = b_u.put(uv_first, 24 * (size_t)n)) || (rc = b_d.put(estimated_depth, 8 * (size_t)n)) || (rc = b_t.put(T, sizeof(T))))
+        return rc;
+    GF_CUDA(cudaMalloc(&b_o.p, 24 * (size_t)n));
+    k_fm_predict<<<(n + 63) / 64, 64>>>(n, (const int*)b_f.p, (const double*)b_u.p, (const double*)b_d.p, (double*)b_o.p, ps, (const double*)b_t.p);
+    GF_LAUNCHED();
+    GF_CUDA(cudaGetLastError());
+    GF_CUDA(cudaMemcpy(pts_cam, b_o.p, 24 * (size_t)n, cudaMemcpyDeviceToHost));
     return GF_OK;
 }
 

@@ -41,6 +41,8 @@ class FeatureManager:
                                              ctypes.c_double, ctypes.c_double]
         self.L.gf_fm_parallax.argtypes = [ctypes.c_int, ctypes.c_int, _dp, _dp, _dp]
         self.L.gf_fm_back_shift_depth.argtypes = [ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, _dp, ctypes.c_double]
+        self.L.gf_fm_reprojection_errors.argtypes = [ctypes.c_int, ctypes.c_int, _ip, _ip, _ip, ctypes.c_int, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
+        self.L.gf_fm_predict_next.argtypes = [ctypes.c_int, ctypes.c_int, _ip, _dp, _dp, ctypes.c_int, ctypes.c_int, _dp, _dp, _dp, _dp, _dp]
         self.device = int(device)
         self.feature = []
         self.MIN_PARALLAX = min_parallax_px / FOCAL_LENGTH       # parameters.cpp:345-346
@@ -132,6 +134,63 @@ class FeatureManager:
         for it, e, f in zip(feats, est, flag):
             it.used_num = len(it.obs)
             it.estimated_depth, it.estimate_flag = float(e), int(f)
+
+    # ---- the per-landmark loops of the estimator that feed the front end back (estimator.cpp:3853-4011) ----
+    def _reprojection_errors(self, feats, Ps, Rs, tic, ric):
+        n = len(feats)
+        nobs = np.array([len(it.obs) for it in feats], np.int32)
+        off = np.zeros(n, np.int32); off[1:] = np.cumsum(nobs)[:-1]
+        pts = np.ascontiguousarray(np.concatenate([np.asarray(it.obs, np.float64).reshape(-1, 9)[:, 0:3] for it in feats], 0))
+        start = np.array([it.start_frame for it in feats], np.int32)
+        est = np.array([it.estimated_depth for it in feats], np.float64)
+        Ps_ = np.ascontiguousarray(Ps, np.float64).reshape(-1, 3); Rs_ = np.ascontiguousarray(Rs, np.float64).reshape(-1, 9)
+        tic_ = np.ascontiguousarray(tic, np.float64); ric_ = np.ascontiguousarray(ric, np.float64).reshape(9)
+        e2 = np.zeros(n); e3 = np.zeros(n); cnt = np.zeros(n, np.int32)
+        check(self.L.gf_fm_reprojection_errors(self.device, n, start.ctypes.data_as(_ip), nobs.ctypes.data_as(_ip), off.ctypes.data_as(_ip), int(nobs.sum()),
+                                               _d(pts), _d(est), len(Ps_), _d(Ps_), _d(Rs_), _d(tic_), _d(ric_), _d(e2), _d(e3), cnt.ctypes.data_as(_ip)))
+        return e2, e3, cnt
+
+    def outliersRejection(self, Ps, Rs, tic, ric):
+        """Estimator::outliersRejection (estimator.cpp:3909-3966): ids whose mean reprojection error exceeds 3 px at FOCAL_LENGTH."""
+        feats = [it for it in self.feature if len(it.obs) >= 4]
+        for it in self.feature:
+            it.used_num = len(it.obs)
+        if not feats:
+            return set()
+        e2, _, cnt = self._reprojection_errors(feats, Ps, Rs, tic, ric)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            bad = (e2 / cnt) * FOCAL_LENGTH > 3
+        return {it.feature_id for it, b in zip(feats, bad) if b}
+
+    def movingConsistencyCheckW(self, Ps, Rs, tic, ric):
+        """Estimator::movingConsistencyCheckW (estimator.cpp:3968-4011)."""
+        feats = [it for it in self.feature if len(it.obs) >= 2 and it.start_frame < self.WINDOW_SIZE - 2 and not it.estimated_depth < 0]
+        if not feats:
+            return set()
+        e2, e3, cnt = self._reprojection_errors(feats, Ps, Rs, tic, ric)
+        out = set()
+        for it, a, b, c in zip(feats, e2, e3, cnt):
+            if c > 0 and (FOCAL_LENGTH * a / c > 10 or b / c > 2.0):
+                out.add(it.feature_id)
+        return out
+
+    def predictPtsInNextFrame(self, frame_count, Ps, Rs, tic, ric):
+        """Estimator::predictPtsInNextFrame (estimator.cpp:3853-3886): {feature_id: xyz in the predicted next camera}, the argument
+        of FeatureTracker::setPrediction."""
+        if frame_count < 2:
+            return {}
+        feats = [it for it in self.feature if it.estimated_depth > 0 and len(it.obs) >= 2 and it.start_frame + len(it.obs) - 1 == frame_count]
+        if not feats:
+            return {}
+        n = len(feats)
+        first = np.array([it.start_frame for it in feats], np.int32)
+        uv = np.ascontiguousarray([np.asarray(it.obs[0], np.float64)[0:3] for it in feats])
+        dep = np.array([it.estimated_depth for it in feats], np.float64)
+        Ps_ = np.ascontiguousarray(Ps, np.float64).reshape(-1, 3); Rs_ = np.ascontiguousarray(Rs, np.float64).reshape(-1, 9)
+        tic_ = np.ascontiguousarray(tic, np.float64); ric_ = np.ascontiguousarray(ric, np.float64).reshape(9)
+        out = np.zeros((n, 3))
+        check(self.L.gf_fm_predict_next(self.device, n, first.ctypes.data_as(_ip), _d(uv), _d(dep), len(Ps_), int(frame_count), _d(Ps_), _d(Rs_), _d(tic_), _d(ric_), _d(out)))
+        return {it.feature_id: out[k].copy() for k, it in enumerate(feats)}
 
     def removeOutlier(self, outlierIndex):
         self.feature = [it for it in self.feature if it.feature_id not in outlierIndex]

@@ -364,6 +364,23 @@ int gf_fm_parallax(int device, int n, const double* pts_i, const double* pts_j, 
 int gf_fm_back_shift_depth(int device, int n, const double* uv_i, double* estimated_depth, const double* marg_R, const double* marg_P,
                            const double* new_R, const double* new_P, double init_depth);
 
+/* The per-landmark loops of the estimator that run after optimization() and feed the front end back (single-threaded mode,
+ * estimator.cpp:1115-1140).  Same flattened observation lists as gf_fm_triangulate.
+ * Estimator::outliersRejection (:3909-3966) and Estimator::movingConsistencyCheckW (:3968-4011) both average, per landmark, the
+ * reprojection error of its first observation into every later one (reprojectionError :3888-3898, reprojectionError3D
+ * :3900-3907): err2d_sum[i], err3d_sum[i] = the sums, count[i] = the number of later observations.  The thresholds stay with
+ * the caller (outliersRejection: n_obs >= 4 and FOCAL_LENGTH * err2d / count > 3; movingConsistencyCheckW: n_obs >= 2,
+ * start_frame < WINDOW_SIZE - 2, depth >= 0 and FOCAL_LENGTH * err2d / count > 10 or err3d / count > 2). */
+int gf_fm_reprojection_errors(int device, int n_features, const int32_t* start_frame, const int32_t* n_obs, const int32_t* obs_offset, int n_obs_total,
+                              const double* points, const double* estimated_depth, int n_frames, const double* Ps, const double* Rs, const double* tic,
+                              const double* ric, double* err2d_sum, double* err3d_sum, int32_t* count);
+/* Estimator::predictPtsInNextFrame (:3853-3886): n landmarks (estimated_depth > 0, >= 2 observations, seen in frame frame_count:
+ * the caller's selection) given by their first frame, first observation (xyz) and depth, carried into the camera of the next
+ * frame predicted by constant-velocity motion nextT = curT (prevT^-1 curT).  pts_cam [n][3] is what FeatureTracker::setPrediction
+ * (gf_tracker_set_prediction) takes. */
+int gf_fm_predict_next(int device, int n, const int32_t* first_frame, const double* uv_first, const double* estimated_depth, int n_frames, int frame_count,
+                       const double* Ps, const double* Rs, const double* tic, const double* ric, double* pts_cam);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -173,6 +173,65 @@ class FeatureManagerOracle:
                 it.estimated_depth = INIT_DEPTH; it.estimate_flag = 0
 
     # feature_manager.cpp:801-816
+    # ---- the estimator's per-landmark loops after optimization() (estimator.cpp:3853-4011), with 4x4 homogeneous transforms ----
+    @staticmethod
+    def _T(R, P):
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = P
+        return T
+
+    def _errors(self, it, Ps, Rs, tic, ric):
+        """(sum of reprojectionError, sum of reprojectionError3D, count) of a landmark's first observation into the later ones."""
+        Tbc = self._T(ric, tic)
+        i = it.start_frame
+        d = it.estimated_depth
+        pw = self._T(Rs[i], Ps[i]) @ Tbc @ np.append(d * it.feature_per_frame[0].point, 1.0)
+        e2 = e3 = 0.0; cnt = 0
+        for k, fr in enumerate(it.feature_per_frame):
+            if k == 0:
+                continue
+            j = i + k
+            pc = (np.linalg.inv(self._T(Rs[j], Ps[j]) @ Tbc) @ pw)[:3]
+            e2 += float(np.hypot(pc[0] / pc[2] - fr.point[0], pc[1] / pc[2] - fr.point[1]))
+            e3 += float(np.linalg.norm(pc - fr.point)) / d
+            cnt += 1
+        return e2, e3, cnt
+
+    def outliersRejection(self, Ps, Rs, tic, ric):
+        out = set()
+        for it in self.feature:
+            it.used_num = len(it.feature_per_frame)
+            if it.used_num < 4:
+                continue
+            e2, _, cnt = self._errors(it, Ps, Rs, tic, ric)
+            if e2 / cnt * FOCAL_LENGTH > 3:
+                out.add(it.feature_id)
+        return out
+
+    def movingConsistencyCheckW(self, Ps, Rs, tic, ric):
+        out = set()
+        for it in self.feature:
+            it.used_num = len(it.feature_per_frame)
+            if not (it.used_num >= 2 and it.start_frame < self.WINDOW_SIZE - 2) or it.estimated_depth < 0:
+                continue
+            e2, e3, cnt = self._errors(it, Ps, Rs, tic, ric)
+            if cnt > 0 and (FOCAL_LENGTH * e2 / cnt > 10 or e3 / cnt > 2.0):
+                out.add(it.feature_id)
+        return out
+
+    def predictPtsInNextFrame(self, frame_count, Ps, Rs, tic, ric):
+        if frame_count < 2:
+            return {}
+        cur, prev = self._T(Rs[frame_count], Ps[frame_count]), self._T(Rs[frame_count - 1], Ps[frame_count - 1])
+        nxt = cur @ (np.linalg.inv(prev) @ cur)
+        Tbc = self._T(ric, tic)
+        out = {}
+        for it in self.feature:
+            if it.estimated_depth > 0 and len(it.feature_per_frame) >= 2 and it.start_frame + len(it.feature_per_frame) - 1 == frame_count:
+                i = it.start_frame
+                pw = self._T(Rs[i], Ps[i]) @ Tbc @ np.append(it.estimated_depth * it.feature_per_frame[0].point, 1.0)
+                out[it.feature_id] = (np.linalg.inv(nxt @ Tbc) @ pw)[:3]
+        return out
+
     def removeOutlier(self, outlierIndex):
         self.feature = [it for it in self.feature if it.feature_id not in outlierIndex]
 

@@ -77,3 +77,35 @@ def test_replay_on_the_gpu_matches_the_oracle_pipeline():
     d = np.linalg.norm(got["P_est"] - want["P_est"], axis=1)
     assert d.max() < 1e-4, d.max()
     assert abs(got["ate_m"] - want["ate_m"]) < 1e-4 and got["ate_m"] < 5e-3
+
+
+def test_feedback_loops_match_oracle():
+    """gf_fm_reprojection_errors / gf_fm_predict_next behind outliersRejection, movingConsistencyCheckW and predictPtsInNextFrame
+    (estimator.cpp:3853-4011) against the oracle's 4x4-transform restatement, with a non-trivial camera extrinsic."""
+    from oracle.fm_oracle import FeatureManagerOracle
+    Ps, Rs, lms, frames = scene(seed=3, n_lm=150, noise=1e-4)
+    a, b = FeatureManagerOracle(depth_threshold=50.0), _gpu_fm(depth_threshold=50.0)
+    fill(a, frames); fill(b, frames)
+    a.triangulateAll(10, Ps, Rs, np.zeros(3), np.eye(3)); b.triangulateAll(10, Ps, Rs, np.zeros(3), np.eye(3))
+    ang = 0.05
+    ric = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    tic = np.array([0.02, -0.01, 0.03])
+    for k, (x, y) in enumerate(zip(a.feature, b.feature)):       # same depths on both sides, some of them wrong
+        y.estimated_depth = x.estimated_depth
+        if k % 11 == 5 and x.estimated_depth > 0:
+            x.estimated_depth *= 0.4; y.estimated_depth = x.estimated_depth
+    wa, wb = a.outliersRejection(Ps, Rs, tic, ric), b.outliersRejection(Ps, Rs, tic, ric)
+    assert wa == wb and len(wa) >= 5
+    ma, mb = a.movingConsistencyCheckW(Ps, Rs, tic, ric), b.movingConsistencyCheckW(Ps, Rs, tic, ric)
+    assert ma == mb and len(ma) >= 5
+    feats = [it for it in a.feature if len(it.feature_per_frame) >= 2 and it.estimated_depth > 0]
+    gf = [it for it in b.feature if len(it.obs) >= 2 and it.estimated_depth > 0]
+    e2, e3, cnt = b._reprojection_errors(gf, Ps, Rs, tic, ric)
+    for it, x2, x3, c in zip(feats, e2, e3, cnt):
+        w2, w3, wc = a._errors(it, Ps, Rs, tic, ric)
+        assert c == wc and abs(x2 - w2) <= 1e-10 * max(1.0, w2) and abs(x3 - w3) <= 1e-10 * max(1.0, w3)
+    for fc in (10, 7, 1):
+        pa, pb = a.predictPtsInNextFrame(fc, Ps, Rs, tic, ric), b.predictPtsInNextFrame(fc, Ps, Rs, tic, ric)
+        assert set(pa) == set(pb) and (fc == 1 or len(pa) > 5)
+        for k in pa:
+            assert np.allclose(pa[k], pb[k], rtol=1e-11, atol=1e-11), (fc, k)

@@ -137,3 +137,58 @@ def test_replay_loop_with_the_cpu_oracles_tracks_the_trajectory():
     r = replay(SyntheticStream(seed=0), tr, fm, ba, 36)
     assert len(r["P_est"]) == 26 and r["n_margin_old"] >= 2 and r["n_margin_second_new"] >= 5
     assert r["ate_m"] < 5e-3
+
+
+def _prepared(seed=3, noise=1e-4):
+    Ps, Rs, lms, frames = scene(seed=seed, n_lm=150, noise=noise)
+    fm = FeatureManagerOracle(depth_threshold=50.0)
+    fill(fm, frames)
+    tic, ric = np.array([0.02, -0.01, 0.03]), np.eye(3)
+    fm.triangulateAll(10, Ps, Rs, np.zeros(3), np.eye(3))      # the scene is generated with body = camera
+    return fm, Ps, Rs, lms, tic, ric
+
+
+def test_outlier_rejection_and_consistency_check_flag_the_corrupted_landmarks():
+    """Estimator::outliersRejection / movingConsistencyCheckW (estimator.cpp:3909-4011) on a consistent scene: nothing is flagged;
+    a landmark whose depth is wrong by a factor re-projects off its later observations and is flagged by both."""
+    fm, Ps, Rs, lms, _, _ = _prepared()
+    z, I = np.zeros(3), np.eye(3)
+    assert fm.outliersRejection(Ps, Rs, z, I) == set() and fm.movingConsistencyCheckW(Ps, Rs, z, I) == set()
+    long_ = [it for it in fm.feature if len(it.feature_per_frame) >= 6 and it.start_frame < 8 and it.estimated_depth > 0]
+    bad = {long_[0].feature_id, long_[3].feature_id}
+    for it in fm.feature:
+        if it.feature_id in bad:
+            it.estimated_depth *= 0.35
+    assert fm.outliersRejection(Ps, Rs, z, I) == bad
+    assert bad <= fm.movingConsistencyCheckW(Ps, Rs, z, I)
+
+
+def test_prediction_lands_on_the_true_landmark_under_constant_velocity():
+    """predictPtsInNextFrame (estimator.cpp:3853-3886): with poses that really move at constant velocity the predicted camera-frame
+    point is the landmark seen from the next pose."""
+    rng = np.random.default_rng(0)
+    a = 0.03
+    dR = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    dP = np.array([0.1, 0.01, 0.02])
+    Rs, Ps = [np.eye(3)], [np.zeros(3)]
+    for _ in range(11):
+        Ps.append(Ps[-1] + Rs[-1] @ dP); Rs.append(Rs[-1] @ dR)
+    Rs, Ps = np.array(Rs), np.array(Ps)
+    tic, ric = np.array([0.05, 0.0, 0.02]), np.array([[0, 0, 1.0], [-1, 0, 0], [0, -1, 0]])
+    fm = FeatureManagerOracle()
+    lms = np.stack([rng.uniform(3, 8, 30), rng.uniform(-2, 2, 30), rng.uniform(-1, 1, 30)], 1)
+    for f in range(11):
+        img = {}
+        for l in range(30):
+            pc = ric.T @ (Rs[f].T @ (lms[l] - Ps[f]) - tic)
+            img[l] = np.array([pc[0] / pc[2], pc[1] / pc[2], 1.0, 0, 0, 0, 0, pc[2]])
+        fm.addFeatureCheckParallax(f, img, 0.0)
+    for it in fm.feature:
+        pc = ric.T @ (Rs[0].T @ (lms[it.feature_id] - Ps[0]) - tic)
+        it.estimated_depth = pc[2]
+    pred = fm.predictPtsInNextFrame(10, Ps, Rs, tic, ric)
+    assert len(pred) == 30
+    for l, p in pred.items():
+        want = ric.T @ (Rs[11].T @ (lms[l] - Ps[11]) - tic)
+        assert np.allclose(p, want, atol=1e-9)
+    assert fm.predictPtsInNextFrame(1, Ps, Rs, tic, ric) == {}
