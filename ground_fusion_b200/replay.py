@@ -46,9 +46,13 @@ class ImuFromStream:
 class WindowEstimator:
     """Estimator's sliding window (estimator.h:229-341) with the NON_LINEAR branch of processImage."""
 
-    def __init__(self, fm, ba, imu_propagate=True, max_iter=8):
+    def __init__(self, fm, ba, imu_propagate=True, max_iter=8, tracker=None, use_mcc=False):
+        """tracker: the front end, when the estimator feeds it back as the reference does with MULTIPLE_THREAD 0 (removeOutliers +
+        setPrediction after every optimisation, estimator.cpp:1132-1136); None: no feedback (MULTIPLE_THREAD 1).  use_mcc: USE_MCC."""
         W = WINDOW_SIZE
         self.fm, self.ba = fm, ba
+        self.tracker, self.use_mcc = tracker, use_mcc
+        self.n_removed = self.n_predicted = 0
         self.Ps = np.zeros((W + 1, 3)); self.Rs = np.tile(np.eye(3), (W + 1, 1, 1)); self.Vs = np.zeros((W + 1, 3))
         self.Bas = np.zeros((W + 1, 3)); self.Bgs = np.zeros((W + 1, 3))
         self.pre = [None] * (W + 1); self.bufs = [[] for _ in range(W + 1)]
@@ -96,7 +100,18 @@ class WindowEstimator:
                 return None
             self.nonlinear = True
         self.fm.triangulateAll(fc, self.Ps, self.Rs, self.tic, self.ric)
+        removeIndex = set()
+        if self.use_mcc:                                  # estimator.cpp:1104-1109
+            removeIndex = self.fm.movingConsistencyCheckW(self.Ps, self.Rs, self.tic, self.ric)
+            self.fm.removeOutlier(removeIndex)
         self.optimization()
+        if not self.use_mcc:                              # :1123-1129 -- this set shadows the outer one: the tracker is not told about it
+            self.fm.removeOutlier(self.fm.movingConsistencyCheckW(self.Ps, self.Rs, self.tic, self.ric))
+        if self.tracker is not None:                      # :1131-1136 (MULTIPLE_THREAD 0)
+            self.tracker.removeOutliers(removeIndex)
+            pred = self.fm.predictPtsInNextFrame(self.frame_count, self.Ps, self.Rs, self.tic, self.ric)
+            self.tracker.setPrediction(pred)
+            self.n_removed += len(removeIndex); self.n_predicted += len(pred)
         self.slideWindow()
         self.fm.removeFailures()
         return self.Ps[WINDOW_SIZE].copy(), self.Rs[WINDOW_SIZE].copy()
@@ -166,11 +181,12 @@ class WindowEstimator:
             self.fm.removeFront(self.frame_count)                 # slideWindowNew (estimator.cpp:3839-3851)
 
 
-def replay(stream, tracker, fm, ba, n_frames, imu_per_frame=7, imu_propagate=True, max_iter=8):
+def replay(stream, tracker, fm, ba, n_frames, imu_per_frame=7, imu_propagate=True, max_iter=8, feedback=False, use_mcc=False):
     """Runs n_frames of `stream` through tracker -> fm -> ba.  Returns dict(t, P_est, P_gt, R_est, R_gt, keyframes, ...).
-    tracker.trackImage(t, gray, depth) -> {id: v[8]};  fm / ba: see WindowEstimator."""
+    tracker.trackImage(t, gray, depth) -> {id: v[8]};  fm / ba: see WindowEstimator.  feedback: the estimator calls the tracker's
+    removeOutliers / setPrediction after every optimisation (the reference with MULTIPLE_THREAD 0)."""
     imu = ImuFromStream(stream)
-    est = WindowEstimator(fm, ba, imu_propagate=imu_propagate, max_iter=max_iter)
+    est = WindowEstimator(fm, ba, imu_propagate=imu_propagate, max_iter=max_iter, tracker=tracker if feedback else None, use_mcc=use_mcc)
     out_t, out_P, out_R, gt_P, gt_R, iters = [], [], [], [], [], []
     t_prev = None
     for k in range(n_frames):
@@ -195,4 +211,5 @@ def replay(stream, tracker, fm, ba, n_frames, imu_per_frame=7, imu_propagate=Tru
     P_est, P_gt = np.array(out_P), np.array(gt_P)
     ate = float(np.sqrt(np.mean(np.sum((P_est - P_gt) ** 2, axis=1)))) if len(P_est) else float("nan")
     return {"t": np.array(out_t), "P_est": P_est, "P_gt": P_gt, "R_est": np.array(out_R), "R_gt": np.array(gt_R), "ate_m": ate,
-            "n_margin_old": est.n_old, "n_margin_second_new": est.n_second_new, "iterations": iters}
+            "n_margin_old": est.n_old, "n_margin_second_new": est.n_second_new, "iterations": iters,
+            "n_removed": est.n_removed, "n_predicted": est.n_predicted}

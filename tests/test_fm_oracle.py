@@ -2,6 +2,7 @@
 and of the replay loop (ground_fusion_b200/replay.py) driven by the CPU oracles.  The reference has no tests for this class:
 the restatement is pinned by geometric ground truth (a landmark seen from known poses must come back with its true depth)."""
 import numpy as np
+import pytest
 
 from oracle.fm_oracle import INIT_DEPTH, FeatureManagerOracle
 
@@ -192,3 +193,17 @@ def test_prediction_lands_on_the_true_landmark_under_constant_velocity():
         want = ric.T @ (Rs[11].T @ (lms[l] - Ps[11]) - tic)
         assert np.allclose(p, want, atol=1e-9)
     assert fm.predictPtsInNextFrame(1, Ps, Rs, tic, ric) == {}
+
+
+@pytest.mark.parametrize("use_mcc", [False, True])
+def test_replay_with_the_estimator_feeding_the_tracker_back(use_mcc):
+    """The loop with MULTIPLE_THREAD 0 semantics (estimator.cpp:1104-1136): after every optimisation the tracker gets
+    removeOutliers + setPrediction; driven by the oracles the trajectory stays within millimetres of the ground truth."""
+    from ground_fusion_b200.replay import replay
+    from ground_fusion_b200.synth import IDC_CAM, SyntheticStream
+    from oracle.replay_adapters import oracle_components
+    cam = dict(IDC_CAM, k1=0.0, k2=0.0, p1=0.0, p2=0.0)
+    tr, fm, ba = oracle_components(cam, depth_threshold=4.0)
+    r = replay(SyntheticStream(seed=0), tr, fm, ba, 30, feedback=True, use_mcc=use_mcc)
+    assert len(r["iterations"]) == 20 and r["n_predicted"] > 20 * 50
+    assert r["ate_m"] < 5e-3, r["ate_m"]
