@@ -509,10 +509,10 @@ def main():
            "clocks": clocks, "cpu_affinity": affinity}
     out.update(extra)
 
-    if world == 1 and not args.no_extras:
+    # ---- stage breakdown + roofline of the dominant kernel (profiling mode: one frame at a time, event records only); rank 0, any N ----
+    try:
         from ground_fusion_b200.feature_tracker import FeatureTracker
         from ground_fusion_b200.synth import idc_params8
-        # ---- stage breakdown + roofline of the dominant kernel (profiling mode: one frame at a time, event records only) ----
         tr = FeatureTracker(wl["w"], wl["h"], idc_params8(), wl["max_cnt"], wl["min_dist"], 1, 1, device=local)
         g, d = ring.ptr["device"]
         for k in range(30):
@@ -536,6 +536,9 @@ def main():
                            "algorithmic_bytes_per_launch": lk_bytes, "kernel_ms": stage.get("lk"),
                            "note": "latency-bound by construction: per feature a chain of ~22 dependent LK iterations, each 105 dependent FADDs in OpenCV lane order; "
                                    "throughput comes from concurrent streams (see streams)"}
+    except Exception as e_:      # the headline line must survive
+        out["roofline"] = {"error": repr(e_)}
+    if world == 1 and not args.no_extras:
         # ---- several independent streams on one GPU ----
         sweep = {}
         for ns in (2, 4, 8, 16):
