@@ -277,10 +277,15 @@ static int make_lk_maps(LKMapSet* M, const Pyramid& prev, const Pyramid& cur, in
     if (getenv("GF_LK_NO_TMA")) return GF_OK;
     for (int l = 0; l < LK_MAXLEV; l++) {
         const int k = l < levels ? l : levels - 1;
-        int rc;
-        if ((rc = encode_u8_box(&M->prevI[l], prev.lv[k], LK_IPITCH, LK_IREG)) || (rc = encode_u8_box(&M->curJ[l], cur.lv[k], LK_JPITCH, LK_JR)) ||
-            (rc = encode_u8_box(&M->curI[l], cur.lv[k], LK_IPITCH, LK_IREG)) || (rc = encode_u8_box(&M->prevJ[l], prev.lv[k], LK_JPITCH, LK_JR)))
-            return rc;
+        // a level narrower than the search box (images below 640 px wide at level 3) keeps the per-thread loads for the whole set:
+        // boxes wider than the tensor are not something this code has been run with
+        const bool fits = prev.lv[k].w >= LK_JPITCH && cur.lv[k].w >= LK_JPITCH && prev.lv[k].h >= LK_JR && cur.lv[k].h >= LK_JR;
+        if (!fits ||
+            encode_u8_box(&M->prevI[l], prev.lv[k], LK_IPITCH, LK_IREG) || encode_u8_box(&M->curJ[l], cur.lv[k], LK_JPITCH, LK_JR) ||
+            encode_u8_box(&M->curI[l], cur.lv[k], LK_IPITCH, LK_IREG) || encode_u8_box(&M->prevJ[l], prev.lv[k], LK_JPITCH, LK_JR)) {
+            memset(M, 0, sizeof(*M));          // enabled = 0: the kernels stage the windows with ordinary loads
+            return GF_OK;
+        }
     }
     M->enabled = 1;
     return GF_OK;
